@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs a reference `metaeuk`
+binary; env METAEUK_REF, default /tmp/oracle-build/src/metaeuk, built out-of-tree from
+/root/reference with the recipe in SURVEY.md section 8c).  Nothing here runs on the GPU box:
+the outputs are committed as small fixtures and read by tests/.
+
+For every case it
+  1. writes seeded synthetic proteins / contigs / fragments,
+  2. runs the reference modules with exactly the flags `metaeuk predictexons` passes
+     (captured from a reference run): createdb, extractorfs, translatenucs,
+     prefilter, align, resultspercontig, collectoptimalset,
+  3. dumps inputs (sequences in the reference's *local id* order = data-offset order,
+     reference/lib/mmseqs/src/commons/DBReader.cpp LINEAR_ACCCESS) and every stage's result DB
+     per key into one JSON file  tests/golden/<case>.json.gz
+
+Result DB record formats: SURVEY.md Appendix B.
+"""
+import gzip
+import json
+import os
+import random
+import shutil
+import subprocess
+import sys
+import tempfile
+
+REF = os.environ.get("METAEUK_REF", "/tmp/oracle-build/src/metaeuk")
+HERE = os.path.dirname(os.path.abspath(__file__))
+AA = "ACDEFGHIKLMNPQRSTVWY"
+W = [7.8, 1.9, 5.4, 6.3, 3.9, 7.4, 2.3, 5.1, 5.7, 9.0, 2.2, 4.5, 5.2, 4.3, 5.1, 7.1, 5.8, 6.4, 1.3, 3.2]
+BASES = "TCAG"
+CODE = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+CODON = {}
+_i = 0
+for _a in BASES:
+    for _b in BASES:
+        for _c in BASES:
+            CODON.setdefault(CODE[_i], []).append(_a + _b + _c)
+            _i += 1
+
+PREF_FLAGS = ("--sub-mat aa:blosum62.out,nucl:nucleotide.out --seed-sub-mat aa:VTML80.out,nucl:nucleotide.out "
+              "-k 0 --target-search-mode 0 --k-score seq:2147483647,prof:2147483647 --alph-size aa:21,nucl:5 "
+              "--max-seq-len 65535 --max-seqs {maxseqs} --split 1 --split-mode 2 --split-memory-limit 0 -c 0 --cov-mode 0 "
+              "--comp-bias-corr 1 --comp-bias-corr-scale 1 --diag-score 1 --exact-kmer-matching 0 --mask {mask} "
+              "--mask-prob 0.9 --mask-lower-case 0 --mask-n-repeat 0 --min-ungapped-score 15 --add-self-matches 0 "
+              "--spaced-kmer-mode 1 --db-load-mode 0 --pca substitution:1.100,context:1.400 "
+              "--pcb substitution:4.100,context:5.800 --threads {thr} --compressed 0 -v 3 -s 4.0")
+ALN_FLAGS = ("--sub-mat aa:blosum62.out,nucl:nucleotide.out -a 0 --alignment-mode 2 --alignment-output-mode 0 "
+             "--wrapped-scoring 0 -e 100 --min-seq-id 0 --min-aln-len 11 --seq-id-mode 0 --alt-ali 0 -c 0 --cov-mode 0 "
+             "--max-seq-len 65535 --comp-bias-corr 1 --comp-bias-corr-scale 1 --max-rejected 2147483647 "
+             "--max-accept 2147483647 --add-self-matches 0 --db-load-mode 0 --pca substitution:1.100,context:1.400 "
+             "--pcb substitution:4.100,context:5.800 --score-bias 0 --realign 0 --realign-score-bias -0.2 "
+             "--realign-max-seqs 2147483647 --corr-score-weight 0 --gap-open aa:11,nucl:5 --gap-extend aa:1,nucl:2 "
+             "--zdrop 40 --threads {thr} --compressed 0 -v 3")
+ORF_FLAGS = ("--min-length 15 --max-length 32734 --max-gaps 2147483647 --contig-start-mode 2 --contig-end-mode 2 "
+             "--orf-start-mode 1 --forward-frames 1,2,3 --reverse-frames 1,2,3 --translation-table 1 --translate 0 "
+             "--use-all-table-starts 0 --id-offset 0 --create-lookup 0 --threads {thr} --compressed 0 -v 3")
+DP_FLAGS = ("--metaeuk-eval 0.001 --metaeuk-tcov 0.5 --max-intron 10000 --min-intron 15 --min-exon-aa 11 "
+            "--max-overlap 10 --max-exon-sets {sets} --set-gap-open -1 --set-gap-extend -1 --score-bias 0 "
+            "--threads {thr} --compressed 0 -v 3")
+
+
+def run(cmd, log):
+    r = subprocess.run(cmd, shell=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log.append("$ " + cmd + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise SystemExit("reference command failed: " + cmd)
+    return r.stdout
+
+
+def read_db(path):
+    """-> list of (key, bytes) in data-offset order (the reference's LINEAR_ACCCESS local ids)."""
+    if os.path.exists(path):
+        files = [path]
+    else:
+        files = []
+        i = 0
+        while os.path.exists("%s.%d" % (path, i)):
+            files.append("%s.%d" % (path, i))
+            i += 1
+    data = b"".join(open(f, "rb").read() for f in files)
+    idx = []
+    for line in open(path + ".index"):
+        k, o, l = line.split("\t")
+        idx.append((int(o), int(k), int(l)))
+    idx.sort()
+    return [(k, data[o:o + l]) for o, k, l in idx]
+
+
+def seqdb(path):
+    return [(k, e[:-2].decode()) for k, e in read_db(path)]  # strip "\n\0"
+
+
+def resdb(path):
+    return {str(k): e[:-1].decode() for k, e in read_db(path)}  # strip "\0"
+
+
+IDX_FLAGS = ("--seed-sub-mat aa:VTML80.out,nucl:nucleotide.out -k 6 -s 4 --mask {mask} --mask-prob 0.9 "
+             "--mask-lower-case 0 --mask-n-repeat 0 --spaced-kmer-mode 1 --comp-bias-corr 1 --split 1 --threads {thr} -v 3")
+NUM2AA = "ACDEFGHIKLMNPQRSTVWYX"
+
+
+def ref_index(tmp, db, mask, thr, log):
+    """Run the reference `indexdb` (same IndexBuilder::fillDatabase the prefilter calls,
+    reference/lib/mmseqs/src/prefiltering/IndexBuilder.cpp:55) and pull out of the .idx DB
+    (entry ids: PrefilteringIndexReader.cpp:10-34): the tantan-MASKED target sequences
+    (SEQINDEXDATA=14 / SEQINDEXSEQOFFSET=16), and sha256 digests of the k-mer index
+    (ENTRIES=9, ENTRIESOFFSETS=10) and of the 3-mer similarity table (SCOREMATRIX3MER=4)."""
+    import hashlib
+    import struct
+    out = run("%s indexdb %s/%s %s/%s %s" % (REF, tmp, db, tmp, db, IDX_FLAGS.format(mask=mask, thr=thr)), log)
+    ent = {}
+    for line in open("%s/%s.idx.index" % (tmp, db)):
+        k, o, l = line.split("\t")
+        ent[int(k)] = (int(o), int(l))
+    f = open("%s/%s.idx" % (tmp, db), "rb")
+
+    def get(k):
+        o, l = ent[k]
+        f.seek(o)
+        return f.read(l)
+    nseq = struct.unpack("<q", get(13)[:8])[0]
+    seqoff = struct.unpack("<%dq" % (nseq + 1), get(16)[:8 * (nseq + 1)])
+    seqdata = get(14)
+    masked = ["".join(NUM2AA[c] for c in seqdata[seqoff[i]:seqoff[i + 1]]) for i in range(nseq)]
+    nent = struct.unpack("<q", get(12)[:8])[0]
+    entries = get(9)[:6 * nent]
+    offsets = get(10)[:8 * (20 ** 6 + 1)]
+    sm3 = get(4)
+    nsc = 8000 * 8032
+    res = {
+        "masked_targets": masked, "idx_n_entries": nent,
+        "idx_entries_sha256": hashlib.sha256(entries).hexdigest(),
+        "idx_offsets_u64_sha256": hashlib.sha256(offsets).hexdigest(),
+        "sim3_score_i16_sha256": hashlib.sha256(sm3[:2 * nsc]).hexdigest(),
+        "sim3_index_u32_sha256": hashlib.sha256(sm3[2 * nsc:2 * nsc + 4 * nsc]).hexdigest(),
+        "idx_masked_residues": int(out.split("Masked residues: ")[1].split()[0]),
+    }
+    f.close()
+    os.remove("%s/%s.idx" % (tmp, db))
+    return res
+
+
+def rand_prot(rng, mean=330, sd=120, lo=60):
+    L = max(lo, int(rng.gauss(mean, sd)))
+    return "".join(rng.choices(AA, weights=W, k=L))
+
+
+def mutate(rng, s, rate):
+    return "".join(rng.choice(AA) if rng.random() < rate else c for c in s)
+
+
+def rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def make_proteins(rng, n, family=0, lowcomplex=0):
+    prots = [rand_prot(rng) for _ in range(n)]
+    if family:
+        base = rand_prot(rng, 220, 10)
+        for _ in range(family):
+            prots.append(mutate(rng, base, rng.choice([0.05, 0.1, 0.2, 0.3])))
+    for _ in range(lowcomplex):
+        unit = "".join(rng.choices(AA, k=rng.randint(1, 4)))
+        p = rand_prot(rng, 150, 20)
+        p = p[:60] + unit * (80 // len(unit)) + p[60:]
+        prots.append(p)
+    rng.shuffle(prots)
+    return prots
+
+
+def make_contigs(rng, prots, nc, cl):
+    out = []
+    for _ in range(nc):
+        parts = []
+        total = 0
+        while total < cl:
+            inter = "".join(rng.choices("ACGT", k=rng.randint(200, 1500)))
+            parts.append(inter)
+            total += len(inter)
+            if rng.random() < 0.8:
+                p = mutate(rng, rng.choice(prots), rng.choice([0.1, 0.3, 0.5]))
+                k = rng.randint(1, 4)
+                cuts = sorted(rng.sample(range(20, len(p) - 20), k - 1)) if len(p) > 60 and k > 1 else []
+                segs = [p[a:b] for a, b in zip([0] + cuts, cuts + [len(p)])]
+                gene = ""
+                for j, sg in enumerate(segs):
+                    gene += "".join(rng.choice(CODON[x]) for x in sg)
+                    if j < len(segs) - 1:
+                        gene += "".join(rng.choices("ACGT", k=rng.randint(40, 600)))
+                if rng.random() < 0.5:
+                    gene = rc(gene)
+                parts.append(gene)
+                total += len(gene)
+        out.append("".join(parts)[:cl])
+    return out
+
+
+def make_fragments(rng, prots, n):
+    """AA query fragments: half mutated protein slices, half background; a few with X / short / long."""
+    out = []
+    for i in range(n):
+        L = max(15, int(rng.gauss(100, 40)))
+        if i % 2 == 0:
+            p = rng.choice(prots)
+            if len(p) > L:
+                a = rng.randrange(0, len(p) - L)
+                s = mutate(rng, p[a:a + L], rng.choice([0.1, 0.3, 0.5]))
+            else:
+                s = mutate(rng, p, 0.2)
+        else:
+            s = "".join(rng.choices(AA, weights=W, k=L))
+        if i % 37 == 5:
+            j = rng.randrange(len(s))
+            s = s[:j] + "X" + s[j + 1:]
+        out.append(s)
+    out.append("ACDEFGHIK")          # shorter than the spaced window (no k-mer)
+    out.append("ACDEFGHIKL")         # exactly one window
+    out.append(mutate(rng, prots[0] + prots[1], 0.1))  # long query spanning two targets
+    return out
+
+
+def write_fasta(path, seqs, prefix):
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">%s%d\n%s\n" % (prefix, i, s))
+
+
+def case_fragments(name, seed, nprot, nfrag, family=0, lowcomplex=0, mask=1, maxseqs=300, thr=8):
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    prots = make_proteins(rng, nprot, family, lowcomplex)
+    frags = make_fragments(rng, prots, nfrag)
+    write_fasta(tmp + "/proteins.faa", prots, "P")
+    write_fasta(tmp + "/frags.faa", frags, "F")
+    run("%s createdb %s/proteins.faa %s/proteins -v 3" % (REF, tmp, tmp), log)
+    run("%s createdb %s/frags.faa %s/frags --shuffle 0 -v 3" % (REF, tmp, tmp), log)
+    run("%s prefilter %s/frags %s/proteins %s/pref %s" % (REF, tmp, tmp, tmp, PREF_FLAGS.format(mask=mask, thr=thr, maxseqs=maxseqs)), log)
+    run("%s align %s/frags %s/proteins %s/pref %s/aln %s" % (REF, tmp, tmp, tmp, tmp, ALN_FLAGS.format(thr=thr)), log)
+    preflog = log[-2]
+    out = {
+        "case": name, "kind": "fragments", "seed": seed, "mask": mask, "max_seqs": maxseqs,
+        "targets": seqdb(tmp + "/proteins"), "queries": seqdb(tmp + "/frags"),
+        "pref": resdb(tmp + "/pref"), "aln": resdb(tmp + "/aln"),
+        "masked_residues": int(preflog.split("Masked residues: ")[1].split()[0]),
+        "kmer_thr": int(preflog.split("k-mer similarity threshold: ")[1].split()[0]),
+        "ref_version": run("%s version" % REF, log).strip(),
+    }
+    out.update(ref_index(tmp, "proteins", mask, thr, log))
+    assert out["idx_masked_residues"] == out["masked_residues"]
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+    print(name, "targets", len(out["targets"]), "queries", len(out["queries"]),
+          "masked", out["masked_residues"],
+          "pref lines", sum(v.count("\n") for v in out["pref"].values()),
+          "aln lines", sum(v.count("\n") for v in out["aln"].values()))
+
+
+def case_contigs(name, seed, nprot, nc, cl, mask=1, sets=1, thr=8):
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    prots = make_proteins(rng, nprot)
+    contigs = make_contigs(rng, prots, nc, cl)
+    write_fasta(tmp + "/proteins.faa", prots, "P")
+    write_fasta(tmp + "/contigs.fna", contigs, "C")
+    run("%s createdb %s/proteins.faa %s/proteins -v 3" % (REF, tmp, tmp), log)
+    run("%s createdb %s/contigs.fna %s/contigs -v 3" % (REF, tmp, tmp), log)
+    run("%s extractorfs %s/contigs %s/nucl_6f %s" % (REF, tmp, tmp, ORF_FLAGS.format(thr=thr)), log)
+    run("%s translatenucs %s/nucl_6f %s/aa_6f --translation-table 1 --add-orf-stop 0 -v 3 --compressed 0 --threads %d" % (REF, tmp, tmp, thr), log)
+    run("%s prefilter %s/aa_6f %s/proteins %s/pref %s" % (REF, tmp, tmp, tmp, PREF_FLAGS.format(mask=mask, thr=thr, maxseqs=300)), log)
+    preflog = log[-1]
+    run("%s align %s/aa_6f %s/proteins %s/pref %s/aln %s" % (REF, tmp, tmp, tmp, tmp, ALN_FLAGS.format(thr=thr)), log)
+    run("%s resultspercontig %s/contigs %s/nucl_6f %s/aln %s/bycontig --threads %d --compressed 0 -v 3" % (REF, tmp, tmp, tmp, tmp, thr), log)
+    run("%s collectoptimalset %s/bycontig %s/proteins %s/dp %s" % (REF, tmp, tmp, tmp, DP_FLAGS.format(thr=thr, sets=sets)), log)
+    out = {
+        "case": name, "kind": "contigs", "seed": seed, "mask": mask, "max_exon_sets": sets,
+        "targets": seqdb(tmp + "/proteins"),
+        "contig_lens": {str(k): len(s) for k, s in seqdb(tmp + "/contigs")},
+        "queries": seqdb(tmp + "/aa_6f"),
+        "orf_headers": {str(k): e[:-1].decode() for k, e in read_db(tmp + "/nucl_6f_h")},
+        "pref": resdb(tmp + "/pref"), "aln": resdb(tmp + "/aln"),
+        "bycontig": resdb(tmp + "/bycontig"), "dp": resdb(tmp + "/dp"),
+        "masked_residues": int(preflog.split("Masked residues: ")[1].split()[0]),
+        "kmer_thr": int(preflog.split("k-mer similarity threshold: ")[1].split()[0]),
+        "ref_version": run("%s version" % REF, log).strip(),
+    }
+    out.update(ref_index(tmp, "proteins", mask, thr, log))
+    assert out["idx_masked_residues"] == out["masked_residues"]
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+    print(name, "targets", len(out["targets"]), "fragments", len(out["queries"]),
+          "masked", out["masked_residues"],
+          "pref lines", sum(v.count("\n") for v in out["pref"].values()),
+          "aln lines", sum(v.count("\n") for v in out["aln"].values()),
+          "dp lines", sum(v.count("\n") for v in out["dp"].values()))
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF):
+        raise SystemExit("reference binary not found: " + REF)
+    which = sys.argv[1:] or ["frag_small", "frag_family", "frag_nomask", "contigs_small", "contigs_sets"]
+    if "frag_small" in which:
+        case_fragments("frag_small", 4321, nprot=600, nfrag=400)
+    if "frag_family" in which:   # >300 homologous targets: exercises the top-300 cut and its tie order
+        case_fragments("frag_family", 99, nprot=300, nfrag=60, family=700)
+    if "frag_nomask" in which:   # low-complexity targets with --mask 0
+        case_fragments("frag_nomask", 7, nprot=300, nfrag=200, lowcomplex=30, mask=0)
+    if "contigs_small" in which:
+        case_contigs("contigs_small", 1234, nprot=400, nc=24, cl=9000)
+    if "contigs_sets" in which:
+        case_contigs("contigs_sets", 77, nprot=200, nc=12, cl=9000, sets=3)
