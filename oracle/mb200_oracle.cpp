@@ -1,0 +1,644 @@
+// oracle/mb200_oracle.cpp
+//
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+// Scalar CPU restatement of the reference's predictexons hot path:
+// MMseqs2 k-mer prefilter -> gapped Smith-Waterman -> MetaEuk exon-chaining DP.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+// Parity: PINNED.  tests/test_oracle_golden.py checks every stage of this file against outputs of the
+// unmodified reference (tests/golden/*.json.gz, produced by tests/golden/make_golden.py).
+//
+// Each function cites the reference file:line it restates ("M/" = reference/lib/mmseqs/).
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: the float composition-bias code must not be fused).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "submat_data.h"
+
+namespace {
+
+const int AL = 21;          // alphabet incl. X (=20)
+const int XRES = 20;
+const int KSZ = 6;          // k (M/src/prefiltering/IndexTable.h:439-449 -> 6 below 3.35 G residues)
+const int SPACED_LEN = 10;  // spaced_seed_6 = 1101010011 (M/src/commons/Sequence.h:23)
+const int SPACED_OFF[KSZ] = {0, 1, 3, 5, 8, 9};
+const size_t TABLE = 64000000;  // 20^6
+const int ROW3 = 8000;      // the reference pads rows to its SIMD width with -255 (ExtendedSubstitutionMatrix.cpp:23-24,56-59); padding is never read
+const int N3 = 8000;
+
+// ---------------------------------------------------------------------------------------------
+// a1  SubstitutionMatrix ctor / readProbMatrix / BaseMatrix::generateSubMatrix
+//     M/src/commons/SubstitutionMatrix.cpp:12-57,326-419 ; M/src/commons/BaseMatrix.cpp:100-159
+// ---------------------------------------------------------------------------------------------
+void build_submat(const double S[21][21], const double bg[21], double lambda, float bitFactorF, float scoreBiasF,
+                  int16_t out[441], double pBackOut[21]) {
+    double pBack[21];
+    for (int i = 0; i < AL; i++) pBack[i] = bg[i];
+    bool xIsPositive = false;   // SubstitutionMatrix.cpp:369-377
+    for (int j = 0; j < AL; j++) if (S[XRES][j] > 0 || S[j][XRES] > 0) { xIsPositive = true; break; }
+    if (!xIsPositive) for (int i = 0; i < AL - 1; i++) pBack[i] = pBack[i] * (1.0 - pBack[XRES]);  // :404-408
+    double prob[21][21];
+    for (int i = 0; i < AL; i++) for (int j = 0; j < AL; j++) prob[i][j] = std::exp(lambda * S[i][j]) * pBack[i] * pBack[j];  // :410-416
+    // BaseMatrix::computeBackground (BaseMatrix.cpp:96-108): row sums, X forced to ANY_BACK
+    double pb2[21];
+    for (int i = 0; i < AL; i++) { pb2[i] = 0; for (int j = 0; j < AL; j++) pb2[i] += prob[i][j]; }
+    pb2[AL - 1] = 1E-5;
+    double bitFactor = bitFactorF, scoreBias = scoreBiasF;  // float ctor args widened (SubstitutionMatrix.cpp:12, BaseMatrix.cpp:141)
+    for (int i = 0; i < AL; i++) for (int j = 0; j < AL; j++) {
+        double sm = std::log2(prob[i][j] / (pb2[i] * pb2[j]));                 // BaseMatrix.cpp:125-127
+        double v = bitFactor * sm + scoreBias;                                 // :149
+        out[i * AL + j] = (short)((v < 0.0) ? v - 0.5 : v + 0.5);               // :150
+    }
+    for (int i = 0; i < AL; i++) pBackOut[i] = pBack[i];   // the member pBack calcLocalAaBiasCorrection reads
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5  SubstitutionMatrix::calcLocalAaBiasCorrection   M/src/commons/SubstitutionMatrix.cpp:79-109
+// ---------------------------------------------------------------------------------------------
+void comp_bias(const int16_t mat[441], const double pBack[21], const uint8_t *seq, int N, float *bias, float scale) {
+    const int windowSize = 40;
+    for (int i = 0; i < N; i++) {
+        const int minPos = std::max(0, (i - windowSize / 2));
+        const int maxPos = std::min(N, (i + windowSize / 2));
+        const int windowLength = maxPos - minPos;
+        int sumSubScores = 0;
+        const int16_t *subMat = mat + seq[i] * AL;
+        for (int j = minPos; j < maxPos; j++) sumSubScores += subMat[seq[j]];
+        sumSubScores -= subMat[seq[i]];
+        float deltaS_i = (float)sumSubScores;
+        deltaS_i /= -1.0 * static_cast<float>(windowLength);
+        for (int a = 0; a < AL; a++) deltaS_i += pBack[a] * static_cast<float>(subMat[a]);
+        bias[i] = scale * deltaS_i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2  ExtendedSubstitutionMatrix::calcScoreMatrix (k=3)  M/src/prefiltering/ExtendedSubstitutionMatrix.cpp:20-69
+//     neighbours of every 3-mer sorted by descending score, stable w.r.t. cartesian order (first letter outermost)
+// ---------------------------------------------------------------------------------------------
+void build_sim3(const int16_t mat[441], int16_t *score, uint32_t *index) {
+#pragma omp parallel
+    {
+        std::vector<std::pair<short, unsigned int>> tmp(N3);
+#pragma omp for schedule(static)
+        for (int a0 = 0; a0 < 20; a0++) for (int a1 = 0; a1 < 20; a1++) for (int a2 = 0; a2 < 20; a2++) {
+            const unsigned int i_index = a0 + a1 * 20 + a2 * 400;   // Indexer::int2index, little-endian (Indexer.h:21-84)
+            int j = 0;
+            for (int b0 = 0; b0 < 20; b0++) for (int b1 = 0; b1 < 20; b1++) for (int b2 = 0; b2 < 20; b2++) {
+                short s = 0;
+                s += mat[a0 * AL + b0]; s += mat[a1 * AL + b1]; s += mat[a2 * AL + b2];
+                tmp[j].first = s; tmp[j].second = b0 + b1 * 20 + b2 * 400; j++;
+            }
+            std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<short, unsigned int> &l, const std::pair<short, unsigned int> &r) { return l.first > r.first; });
+            for (int z = 0; z < N3; z++) { score[(size_t)i_index * ROW3 + z] = tmp[z].first; index[(size_t)i_index * ROW3 + z] = tmp[z].second; }
+        }
+    }
+}
+
+struct Entry { uint32_t seqId; uint16_t pos; };   // IndexEntryLocal, 6 B packed in the reference (IndexTable.h:25-39)
+
+struct Oracle {
+    int16_t seedMat[441], ungMat[441], alnMat[441];
+    double seedPBack[21], ungPBack[21], alnPBack[21];
+    std::vector<int16_t> sim3Score; std::vector<uint32_t> sim3Index;
+    // index
+    std::vector<uint64_t> offsets; std::vector<Entry> entries;
+    std::vector<uint8_t> masked; std::vector<uint64_t> moff;      // masked target residues (SequenceLookup)
+    std::vector<uint8_t> unmasked; std::vector<uint64_t> uoff;    // unmasked target residues (align stage)
+    uint32_t nT = 0; uint64_t totalResidues = 0;
+    // parameters (MetaEuk defaults)
+    int kmerThr = 127; int maxResListLen = 300; int minDiagScore = 15; int binSize = 2;
+    int gapOpen = 11, gapExtend = 1; double evalThr = 100; int minAlnLen = 11;
+};
+
+// ---------------------------------------------------------------------------------------------
+// a3  IndexBuilder::fillDatabase + IndexTable::{addKmerCount,addSequence,sortDBSeqLists}
+//     M/src/prefiltering/IndexBuilder.cpp:55-239 ; IndexTable.h:133-173,348-401,182-189
+//     input = ALREADY MASKED residues (tantan masking, Masker.cpp:14-58, is a host preprocessing input)
+// ---------------------------------------------------------------------------------------------
+void index_build(Oracle &o) {
+    o.offsets.assign(TABLE + 1, 0);
+    char idScore[21];
+    for (int a = 0; a < AL; a++) idScore[a] = (char)o.seedMat[a * AL + a];   // getScoreLookup, IndexBuilder.cpp:10-21
+    std::vector<std::vector<std::pair<uint32_t, uint16_t>>> perSeq(o.nT);     // (kmer, first pos) sorted by kmer
+#pragma omp parallel for schedule(dynamic, 100)
+    for (uint32_t t = 0; t < o.nT; t++) {
+        const uint8_t *s = &o.masked[o.moff[t]];
+        const int L = (int)(o.moff[t + 1] - o.moff[t]);
+        std::vector<std::pair<uint32_t, uint16_t>> &v = perSeq[t];
+        for (int p = 0; p + SPACED_LEN <= L; p++) {                          // Sequence::hasNextKmer, Sequence.h:92-94
+            bool hasX = false; int sc = 0; uint32_t idx = 0; uint32_t pw = 1;
+            for (int k = 0; k < KSZ; k++) { uint8_t c = s[p + SPACED_OFF[k]]; if (c == XRES) hasX = true; sc += idScore[c]; idx += c * pw; pw *= 20; }
+            if (hasX) continue;                                               // IndexTable.h:141-143
+            if (o.kmerThr > 0 && sc < o.kmerThr) continue;                    // IndexTable.h:144-152
+            v.push_back(std::make_pair(idx, (uint16_t)p));
+        }
+        std::sort(v.begin(), v.end());                                        // by (kmer, pos)  IndexTable.h:386-388
+        size_t w = 0;
+        for (size_t i = 0; i < v.size(); i++) if (i == 0 || v[i].first != v[i - 1].first) v[w++] = v[i];   // first position only, :390-399
+        v.resize(w);
+    }
+    for (uint32_t t = 0; t < o.nT; t++) for (auto &e : perSeq[t]) o.offsets[e.first + 1]++;
+    for (size_t i = 0; i < TABLE; i++) o.offsets[i + 1] += o.offsets[i];
+    o.entries.resize(o.offsets[TABLE]);
+    std::vector<uint64_t> cur(o.offsets.begin(), o.offsets.end() - 1);
+    // inserting targets in ascending seqId order yields lists sorted by (seqId,pos) == sortDBSeqLists (IndexTable.h:182-189)
+    for (uint32_t t = 0; t < o.nT; t++) for (auto &e : perSeq[t]) { Entry &x = o.entries[cur[e.first]++]; x.seqId = t; x.pos = e.second; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9  UngappedAlignment::scalarDiagonalScoring / computeSingelSequenceScores
+//     M/src/prefiltering/UngappedAlignment.cpp:30-43,416-430  (sequences < 32768 only)
+// ---------------------------------------------------------------------------------------------
+int diag_score(const int8_t *prof /*[L][21]*/, int qLen, const uint8_t *t, int tLen, uint16_t diag16) {
+    int diagonal = (short)diag16;
+    unsigned short dist = std::min((unsigned short)(0 - diag16), (unsigned short)(diag16 - 0));   // distanceFromDiagonal :364-369
+    const int8_t *p; const uint8_t *d; unsigned int n;
+    if (diagonal >= 0 && dist < (unsigned)qLen) { n = std::min((unsigned)tLen, (unsigned)qLen - dist); p = prof + dist * AL; d = t; }
+    else if (diagonal < 0 && dist < (unsigned)tLen) { n = std::min((unsigned)tLen - dist, (unsigned)qLen); p = prof; d = t + dist; }
+    else return 0;
+    int max = 0, score = 0;
+    for (unsigned int pos = 0; pos < n; pos++) {
+        int curr = p[pos * AL + d[pos]];
+        score = curr + score; score = (score < 0) ? 0 : score; max = (score > max) ? score : max;
+    }
+    return max;
+}
+
+struct Cand { uint32_t id; uint16_t diag; uint8_t count; };   // CounterResult (CacheFriendlyOperations.h:46-66)
+struct PrefHit { uint32_t seqId; int32_t score; uint16_t diag; };   // hit_t (QueryMatcher.h:33-48)
+struct PrefStats { uint64_t kmers, lookups, dbMatches, doubleHits, diagCells, results; };
+
+// ---------------------------------------------------------------------------------------------
+// a4,a6,a7,a8,a10  QueryMatcher::matchQuery / match  M/src/prefiltering/QueryMatcher.cpp:85-211,213-346
+// ---------------------------------------------------------------------------------------------
+int prefilter_query(const Oracle &o, const uint8_t *q, int L, std::vector<PrefHit> &out, PrefStats &st) {
+    out.clear();
+    if (L >= 32768) return -2;
+    std::vector<float> bias(L > 0 ? L : 1);
+    comp_bias(o.seedMat, o.seedPBack, q, L, bias.data(), 1.0f);                 // QueryMatcher.cpp:91-93 (kmerSubMat)
+    // UngappedAlignment::createProfile  UngappedAlignment.cpp:385-414
+    std::vector<int8_t> prof((size_t)(L > 0 ? L : 1) * AL);
+    for (int pos = 0; pos < L; pos++) {
+        float aaCorrBias = bias[pos];
+        aaCorrBias = (aaCorrBias < 0.0) ? aaCorrBias / 4 - 0.5 : aaCorrBias / 4 + 0.5;
+        char corr = static_cast<char>(aaCorrBias);
+        for (int a = 0; a < AL; a++) prof[(size_t)pos * AL + a] = (char)(o.ungMat[q[pos] * AL + a] + corr);
+    }
+    // ---- match(): similar k-mers + index lists in arrival order (QueryMatcher.cpp:225-322)
+    struct Hit { uint32_t id; uint16_t diag; };
+    std::vector<Hit> hits;
+    const size_t maxDbMatches = std::max((size_t)1000000, (size_t)o.nT) * 2;    // QueryMatcher.cpp:44
+    for (int i = 0; i + SPACED_LEN <= L; i++) {
+        float biasCorrection = 0;
+        for (int k = 0; k < KSZ; k++) biasCorrection += bias[i + SPACED_OFF[k]];
+        bool hasX = false; uint8_t w[KSZ];
+        for (int k = 0; k < KSZ; k++) { w[k] = q[i + SPACED_OFF[k]]; if (w[k] == XRES) hasX = true; }
+        if (hasX) continue;                                                     // :234-238
+        short b = static_cast<short>((biasCorrection < 0.0) ? biasCorrection - 0.5 : biasCorrection + 0.5);
+        short thr = std::max(o.kmerThr - b, 0);                                 // :240-241
+        // KmerGenerator::generateKmerList / calculateArrayProduct  KmerGenerator.cpp:107-183,186-216
+        const uint32_t idx0 = w[0] + w[1] * 20 + w[2] * 400, idx1 = w[3] + w[4] * 20 + w[5] * 400;
+        const int16_t *s0 = &o.sim3Score[(size_t)idx0 * ROW3]; const uint32_t *k0 = &o.sim3Index[(size_t)idx0 * ROW3];
+        const int16_t *s1 = &o.sim3Score[(size_t)idx1 * ROW3]; const uint32_t *k1 = &o.sim3Index[(size_t)idx1 * ROW3];
+        const short possibleRest0 = s1[0];
+        const short cutoff1 = thr - possibleRest0;
+        for (int a = 0; a < N3; a++) {
+            const short score_i = s0[a];
+            if (score_i < cutoff1) break;
+            const short cutoff2 = thr - score_i - 0;
+            for (int c = 0; c < N3 && s1[c] >= cutoff2; c++) {
+                const size_t kmer = (size_t)k0[a] + (size_t)k1[c] * 8000;
+                st.kmers++;
+                const uint64_t lo = o.offsets[kmer], hi = o.offsets[kmer + 1];   // IndexTable::getDBSeqList IndexTable.h:176-180
+                st.lookups++;
+                if (hits.size() + (hi - lo) >= maxDbMatches) return -3;         // reference overflow path (QueryMatcher.cpp:281-316) not restated
+                for (uint64_t e = lo; e < hi; e++) { Hit h; h.id = o.entries[e].seqId; h.diag = (uint16_t)(i - o.entries[e].pos); hits.push_back(h); }
+            }
+        }
+    }
+    st.dbMatches += hits.size();
+    // ---- a8 CacheFriendlyOperations<BIN>::findDuplicates  CacheFriendlyOperations.cpp:38-49,185-274,337-347
+    const unsigned BIN = o.binSize; unsigned shift = 0; while ((1u << shift) < BIN) shift++;
+    std::vector<std::vector<Hit>> bins(BIN);
+    for (auto &h : hits) bins[h.id & (BIN - 1)].push_back(h);
+    std::vector<uint8_t> last((o.nT >> shift) + 2, 0);
+    std::vector<Cand> found;
+    for (unsigned bin = 0; bin < BIN; bin++) {
+        std::vector<Hit> tmp;
+        for (auto &e : bins[bin]) {
+            const unsigned hb = e.id >> shift; const uint8_t cur = (uint8_t)e.diag; const uint8_t prev = last[hb];
+            if (cur == prev) tmp.push_back(e);
+            last[hb] = cur;
+        }
+        for (size_t n = tmp.size(); n-- > 0;) last[tmp[n].id >> shift] = (uint8_t)((uint8_t)tmp[n].diag + 1);       // :236-241
+        size_t base = found.size(); size_t cnt = 0; found.resize(base + tmp.size() + 1);
+        for (size_t n = 0; n < tmp.size(); n++) {                                                                   // :244-262
+            const unsigned hb = tmp[n].id >> shift;
+            found[base + cnt].id = tmp[n].id; found[base + cnt].count = 0; found[base + cnt].diag = tmp[n].diag;
+            cnt += (last[hb] != (uint8_t)tmp[n].diag) ? 1 : 0;
+            last[hb] = (uint8_t)tmp[n].diag;
+        }
+        found.resize(base + cnt);
+        for (auto &e : bins[bin]) last[e.id >> shift] = 0;                                                          // :264-271
+    }
+    st.doubleHits += found.size();
+    // ---- a9 ungapped diagonal scores  UngappedAlignment.cpp:331-362 (count==0 entries only; all are 0 here)
+    for (auto &c : found) {
+        const uint8_t *t = &o.masked[o.moff[c.id]]; const int tLen = (int)(o.moff[c.id + 1] - o.moff[c.id]);
+        if (tLen >= 32768) return -2;
+        int mx = diag_score(prof.data(), L, t, tLen, c.diag);
+        c.count = (uint8_t)std::min(255, mx);
+        int diagonal = (short)c.diag; unsigned short dist = std::min((unsigned short)(0 - c.diag), (unsigned short)(c.diag - 0));
+        st.diagCells += (diagonal >= 0) ? (dist < (unsigned)L ? std::min((unsigned)tLen, (unsigned)L - dist) : 0) : (dist < (unsigned)tLen ? std::min((unsigned)tLen - dist, (unsigned)L) : 0);
+    }
+    // ---- a10 keepMaxScoreElementOnly  CacheFriendlyOperations.cpp:74-82,350-380
+    {
+        std::vector<std::vector<Cand>> cb(BIN);
+        for (auto &c : found) cb[c.id & (BIN - 1)].push_back(c);
+        size_t n = 0;
+        for (unsigned bin = 0; bin < BIN; bin++) {
+            for (auto &e : cb[bin]) { uint8_t &d = last[e.id >> shift]; d = std::max(d, e.count); }
+            for (auto &e : cb[bin]) {
+                uint8_t &d = last[e.id >> shift];
+                found[n] = e;
+                bool keep = (d == e.count);
+                n += keep; d = d * (1 - keep);
+            }
+        }
+        found.resize(n);
+        std::fill(last.begin(), last.end(), 0);   // the reference memsets at the start of the next keepMaxElement (:353)
+    }
+    // ---- histogram, threshold, stable counting sort (QueryMatcher.cpp:153-176,498-523; QueryMatcher.h:206-216)
+    unsigned int scoreSizes[256]; memset(scoreSizes, 0, sizeof(scoreSizes));
+    for (auto &c : found) scoreSizes[c.count]++;
+    const size_t maxHits = std::min((size_t)o.maxResListLen, (size_t)o.nT);
+    auto computeScoreThreshold = [&](const unsigned int *ss) { size_t fh = 0; size_t thr = 0; for (thr = 255; thr > 0; thr--) { fh += ss[thr]; if (fh >= maxHits) break; } return (unsigned)thr; };
+    unsigned int diagonalThr = std::max((unsigned)o.minDiagScore, computeScoreThreshold(scoreSizes));
+    auto radixSort = [&](const unsigned int *ss, const std::vector<Cand> &in, unsigned thr, std::vector<Cand> &res) {
+        size_t N = in.size(); res.assign(N + 1, Cand());
+        std::vector<size_t> ptr(256); size_t prev = N;
+        for (int i = 0; i < 256; i++) { ptr[i] = prev - ss[i]; prev = ptr[i]; }
+        size_t above = 0;
+        for (size_t i = 0; i < N; i++) if (in[i].count >= thr) { above++; res[ptr[in[i].count]++] = in[i]; }
+        return above;
+    };
+    auto exactScore = [&](const Cand &c) {   // scoreSingelSequenceByCounterResult  UngappedAlignment.cpp:432-446
+        const uint8_t *t = &o.masked[o.moff[c.id]]; const int tLen = (int)(o.moff[c.id + 1] - o.moff[c.id]);
+        return diag_score(prof.data(), L, t, tLen, c.diag);
+    };
+    std::vector<Cand> sorted;
+    size_t above = radixSort(scoreSizes, found, diagonalThr, sorted);
+    int rescale = 0; unsigned getThr = diagonalThr;
+    if (diagonalThr >= 255) {   // scoreIsTruncated: rescoreHits  QueryMatcher.cpp:160-170,525-544
+        memset(scoreSizes, 0, sizeof(scoreSizes));
+        int maxSelfScore = diag_score(prof.data(), L, q, L, 0);
+        maxSelfScore = maxSelfScore - 255; maxSelfScore = std::max(1, maxSelfScore); maxSelfScore = std::min(maxSelfScore, 65535);
+        float fltMax = (float)maxSelfScore; size_t elements = 0;
+        for (size_t i = 0; i < above && sorted[i].count >= 255; i++) {
+            unsigned int ns = (unsigned)exactScore(sorted[i]); ns -= 255;
+            float sc = (float)std::min(ns, 65535u);
+            sorted[i].count = (unsigned char)((sc / fltMax) * 255.0f + 0.5);
+            scoreSizes[sorted[i].count]++; elements++;
+        }
+        std::vector<Cand> in(sorted.begin(), sorted.begin() + elements), res2;
+        above = radixSort(scoreSizes, in, 0, res2); sorted.swap(res2);
+        rescale = maxSelfScore; getThr = 0;
+    }
+    // ---- getResult<UNGAPPED_DIAGONAL_SCORE>  QueryMatcher.cpp:363-420
+    for (size_t i = 0; i < above && out.size() < maxHits; i++) {
+        const Cand &c = sorted[i];
+        if (c.count >= getThr) {
+            PrefHit h; h.seqId = c.id; h.score = c.count; h.diag = c.diag;
+            if (rescale != 0) h.score = (int)(255u + ((unsigned)c.count * (unsigned)rescale / 255u));
+            else if ((int)c.count >= 255) h.score = exactScore(c);
+            out.push_back(h);
+        }
+    }
+    // ---- final order  QueryMatcher.cpp:203-209, QueryMatcher.h:38-48
+    std::sort(out.begin(), out.end(), [](const PrefHit &a, const PrefHit &b) {
+        if (abs(a.score) > abs(b.score)) return true; if (abs(b.score) > abs(a.score)) return false; return a.seqId < b.seqId; });
+    st.results += out.size();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11-a13  SmithWaterman::ssw_init / sw_sse2_byte|word / ssw_align_private  -- restated as exact Gotoh
+//     M/src/alignment/StripedSmithWaterman.cpp:1216-1345, 638-940, 309-545  
+// ---------------------------------------------------------------------------------------------
+struct SwEnd { int score, ref, read; };
+// one pass: columns = target residues in order given by (tBegin, tStep, nCols); rows = query profile rows 0..qn-1.
+// Returns max score, FIRST column reaching it (strictly greater than before), smallest row equal to max in that column.
+// terminate>0: stop after the first column whose column maximum == terminate (reverse pass, :900).
+SwEnd sw_pass(const int16_t *alnMat, const uint8_t *qres, const int8_t *qbias, int qn, const uint8_t *t, int tBegin, int tStep, int nCols,
+              int gapO, int gapE, int terminate) {
+    std::vector<int> H(qn + 1, 0), E(qn + 1, 0), Hmax;   // H[j+1] = H(prev column, row j)
+    int max = 0, end_db = -1, end_q = qn - 1;
+    for (int c = 0, ti = tBegin; c < nCols; c++, ti += tStep) {
+        const int16_t *row = alnMat + t[ti] * AL;
+        int diagPrev = 0;   // H(col-1,row-1)
+        int F = 0, hUp = 0; // within this column
+        int colMax = 0;
+        std::vector<int> Hnew(qn + 1, 0);
+        for (int j = 0; j < qn; j++) {
+            int s = row[qres[j]] + qbias[j];
+            int e = E[j + 1];                                   // E(col,j) prepared from previous column
+            int f = (j == 0) ? 0 : std::max(F - gapE, hUp - gapO);
+            int h = diagPrev + s; if (h < 0) h = 0; if (e > h) h = e; if (f > h) h = f;
+            diagPrev = H[j + 1];
+            Hnew[j + 1] = h; F = f; hUp = h;
+            int en = std::max(e - gapE, h - gapO); if (en < 0) en = 0;   // unsigned-saturating in the reference; equivalent
+            E[j + 1] = en;
+            if (h > colMax) colMax = h;
+        }
+        H.swap(Hnew);
+        if (colMax > max) { max = colMax; end_db = ti; Hmax = H; }
+        if (terminate > 0 && colMax == terminate) break;
+    }
+    if (end_db >= 0) for (int j = 0; j < qn; j++) if (Hmax[j + 1] == max) { if (j < end_q) end_q = j; break; }
+    SwEnd r; r.score = max; r.ref = end_db; r.read = end_q; return r;
+}
+
+struct AlnRes { int score; int qStart, qEnd, dbStart, dbEnd; double evalue; int bitScore; float seqId; float qCov, tCov; int alnLen; int passed; };
+
+// ---------------------------------------------------------------------------------------------
+// a14  EvalueComputation (ALP, fixed BLOSUM62 11/1 parameter set)  M/src/alignment/EvalueComputation.h:18-40,56-69
+//      Sls::AlignmentEvaluer::area -> pvalues::get_appr_tail_prob_with_cov_without_errors
+//      M/lib/alp/sls_alignment_evaluer.cpp:989-1028 ; M/lib/alp/sls_pvalues.cpp:342-364,366-532 ; sls_basic.cpp:107-165
+// ---------------------------------------------------------------------------------------------
+struct Alp {
+    double lambda = 0.27359865037097330642, K = 0.044620920658722244834;
+    double a1 = 1.5938724404943873658, b1 = -19.959867650284412122, a2 = 1.5938724404943873658, b2 = -19.959867650284412122;
+    double alpha1 = 30.455610143099914211, beta1 = -622.28684628915891608, alpha2 = 30.455610143099914211, beta2 = -622.28684628915891608;
+    double sigma = 29.602444874818868215, tau = -601.81087985041381216;
+    double vi_y_thr, vj_y_thr, c_y_thr, logK;
+    Alp() {
+        const double nat_cut_off_in_max = 2.0;   // sls_pvalues.hpp
+        vi_y_thr = std::max(nat_cut_off_in_max * alpha2 / lambda, 0.0);   // alpha_I = d_alpha2
+        vj_y_thr = std::max(nat_cut_off_in_max * alpha1 / lambda, 0.0);   // alpha_J = d_alpha1
+        c_y_thr = std::max(nat_cut_off_in_max * sigma / lambda, 0.0);
+        logK = std::log(K);
+    }
+    // sls_basic::normal_probability(double) -- the one-argument overload the area code calls (M/lib/alp/sls_basic.hpp:195-198)
+    static double normal_probability(double x_) { return 0.5 * erfc(-sqrt(0.5) * x_); }
+    double area(double y_, double m_ /*seqlen2 = db residues*/, double n_ /*seqlen1 = query len*/) const {
+        // ai_hat = a_I = d_a2 ; aj_hat = a_J = d_a1 (sls_alignment_evaluer.cpp:679-683)
+        const double pi = 3.1415926535897932384626433832795;
+        const double const_val = 1 / sqrt(2.0 * pi);   // M/lib/alp/sls_basic.hpp:58-59
+        double m_li_y = m_ - (a2 * y_ + b2);
+        double vi_y = std::max(vi_y_thr, alpha2 * y_ + beta2);
+        double sqrt_vi_y = sqrt(vi_y);
+        double m_F = (sqrt_vi_y == 0.0) ? 1e100 : m_li_y / sqrt_vi_y;
+        double P_m_F = normal_probability(m_F);
+        double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
+        double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
+        double n_lj_y = n_ - (a1 * y_ + b1);
+        double vj_y = std::max(vj_y_thr, alpha1 * y_ + beta1);
+        double sqrt_vj_y = sqrt(vj_y);
+        double n_F = (sqrt_vj_y == 0.0) ? 1e100 : n_lj_y / sqrt_vj_y;
+        double P_n_F = normal_probability(n_F);
+        double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
+        double p2 = n_lj_y * P_n_F - sqrt_vj_y * E_n_F;
+        double c_y = std::max(c_y_thr, sigma * y_ + tau);
+        return p1 * p2 + c_y * (P_m_F * P_n_F);
+    }
+    double evalue(double score, double qLen, double dbRes) const { return (K * exp(-lambda * score)) * area(score, qLen, dbRes); }
+    double bitScore(double score) const { return (lambda * score - logK) / log(2.0); }
+};
+
+void align_pair(const Oracle &o, const Alp &alp, const uint8_t *q, int qLen, const int8_t *cb, const uint8_t *t, int tLen, AlnRes &r) {
+    memset(&r, 0, sizeof(r)); r.qStart = r.dbStart = -1;
+    SwEnd f = sw_pass(o.alnMat, q, cb, qLen, t, 0, 1, tLen, o.gapOpen, o.gapExtend, 0);
+    r.score = f.score; r.dbEnd = f.ref; r.qEnd = f.read;
+    if (f.ref == -1) { r.evalue = 0; r.passed = 0; r.qEnd = qLen - 1; return; }
+    r.evalue = alp.evalue(f.score, qLen, (double)o.totalResidues);            // StripedSmithWaterman.cpp:389
+    r.bitScore = (int)(alp.bitScore(f.score) + 0.5);                          // Matcher.cpp:130
+    if (r.evalue > o.evalThr) { r.passed = 0; return; }                       // :390-398 (covThr 0 always passes)
+    // reverse pass on the reversed query prefix / target prefix  :400-476
+    std::vector<uint8_t> qr(f.read + 1); std::vector<int8_t> cbr(f.read + 1);
+    for (int j = 0; j <= f.read; j++) { qr[j] = q[f.read - j]; cbr[j] = cb[f.read - j]; }
+    SwEnd b = sw_pass(o.alnMat, qr.data(), cbr.data(), f.read + 1, t, f.ref, -1, f.ref + 1, o.gapOpen, o.gapExtend, f.score);
+    if (b.score != f.score) { r.passed = -1; return; }                        // the reference EXITs here (:466-473)
+    r.dbStart = b.ref; r.qStart = f.read - b.read;
+    auto cov = [](unsigned s, unsigned e, unsigned len) { return (std::min(len, std::max(s, e)) - std::min(s, e) + 1) / (float)len; };   // :1671-1673
+    r.qCov = cov(r.qStart, r.qEnd, qLen); r.tCov = cov(r.dbStart, r.dbEnd, tLen);
+    r.alnLen = std::max(abs(r.qEnd - r.qStart), abs(r.dbEnd - r.dbStart)) + 1;                     // Matcher.cpp:156-158
+    unsigned qa = std::max((unsigned)(r.qEnd - r.qStart), 1u), ta = std::max((unsigned)(r.dbEnd - r.dbStart), 1u);
+    float sid = ((uint16_t)r.score / static_cast<float>(std::max(qa, ta))) * 0.1656 + 0.1141;      // Matcher.cpp:160-164
+    sid = std::min(sid, 1.0f); r.seqId = std::max(0.0f, sid);
+    r.passed = (r.evalue <= o.evalThr && r.alnLen >= o.minAlnLen) ? 1 : 0;                         // Alignment.cpp:548-567
+}
+
+// int8 composition bias for the align stage  StripedSmithWaterman.cpp:1229-1237
+void aln_comp_bias(const Oracle &o, const uint8_t *q, int L, int8_t *cb) {
+    std::vector<float> tmp(L > 0 ? L : 1);
+    comp_bias(o.alnMat, o.alnPBack, q, L, tmp.data(), 1.0f);
+    for (int i = 0; i < L; i++) cb[i] = (int8_t)((tmp[i] < 0.0) ? tmp[i] - 0.5 : tmp[i] + 0.5);
+}
+
+}  // namespace
+
+// =============================================================================================
+//  C API (ctypes).  All arrays caller-owned unless stated.
+// =============================================================================================
+extern "C" {
+
+struct mbo_hit { uint32_t seqId; int32_t score; int32_t diag; };   // diag = (short)diagonal as written to pref DB
+struct mbo_aln { uint32_t seqId; int32_t score; int32_t bitScore; int32_t qStart, qEnd, dbStart, dbEnd, alnLen, passed; float seqId_est; float pad; double evalue; };
+struct mbo_stats { uint64_t kmers, lookups, dbMatches, doubleHits, diagCells, results; };
+
+void *mbo_create(void) {
+    Oracle *o = new Oracle();
+    build_submat(MB200_VTML80_HALFBITS, MB200_VTML80_BACKGROUND, MB200_VTML80_LAMBDA, 8.0f, -0.2f, o->seedMat, o->seedPBack);     // Prefiltering.cpp:68, :990
+    build_submat(MB200_BLOSUM62_HALFBITS, MB200_BLOSUM62_BACKGROUND, MB200_BLOSUM62_LAMBDA, 2.0f, -0.2f, o->ungMat, o->ungPBack);  // Prefiltering.cpp:69
+    build_submat(MB200_BLOSUM62_HALFBITS, MB200_BLOSUM62_BACKGROUND, MB200_BLOSUM62_LAMBDA, 2.0f, 0.0f, o->alnMat, o->alnPBack);   // Alignment.cpp:152
+    return o;
+}
+void mbo_destroy(void *h) { delete (Oracle *)h; }
+void mbo_set_params(void *h, int kmerThr, int maxResListLen, int minDiagScore, int binSize, int gapOpen, int gapExtend, double evalThr, int minAlnLen) {
+    Oracle *o = (Oracle *)h; o->kmerThr = kmerThr; o->maxResListLen = maxResListLen; o->minDiagScore = minDiagScore; o->binSize = binSize;
+    o->gapOpen = gapOpen; o->gapExtend = gapExtend; o->evalThr = evalThr; o->minAlnLen = minAlnLen;
+}
+void mbo_get_matrices(void *h, int16_t *seed, int16_t *ung, int16_t *aln, double *seedPBack, double *alnPBack) {
+    Oracle *o = (Oracle *)h; memcpy(seed, o->seedMat, 882); memcpy(ung, o->ungMat, 882); memcpy(aln, o->alnMat, 882);
+    memcpy(seedPBack, o->seedPBack, 168); memcpy(alnPBack, o->alnPBack, 168);
+}
+void mbo_build_sim3(void *h) { Oracle *o = (Oracle *)h; o->sim3Score.resize((size_t)N3 * ROW3); o->sim3Index.resize((size_t)N3 * ROW3); build_sim3(o->seedMat, o->sim3Score.data(), o->sim3Index.data()); }
+const int16_t *mbo_sim3_score(void *h) { return ((Oracle *)h)->sim3Score.data(); }
+const uint32_t *mbo_sim3_index(void *h) { return ((Oracle *)h)->sim3Index.data(); }
+
+// targets: masked + unmasked residue codes (0..20), offsets[nT+1]
+int mbo_set_targets(void *h, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT) {
+    Oracle *o = (Oracle *)h; o->nT = nT; o->moff.assign(off, off + nT + 1); o->uoff = o->moff;
+    o->masked.assign(masked, masked + off[nT]); o->unmasked.assign(unmasked, unmasked + off[nT]); o->totalResidues = off[nT];
+    for (uint32_t t = 0; t < nT; t++) if (off[t + 1] - off[t] >= 32768) return -2;
+    index_build(*o);
+    return 0;
+}
+uint64_t mbo_index_entries(void *h) { return ((Oracle *)h)->entries.size(); }
+// copy out: offsets as u64[20^6+1], entries packed 6 B (u32 seqId, u16 pos) exactly as IndexEntryLocal
+void mbo_index_copy(void *h, uint64_t *offsets, uint8_t *entries6) {
+    Oracle *o = (Oracle *)h; memcpy(offsets, o->offsets.data(), (TABLE + 1) * 8);
+    for (size_t i = 0; i < o->entries.size(); i++) { memcpy(entries6 + i * 6, &o->entries[i].seqId, 4); memcpy(entries6 + i * 6 + 4, &o->entries[i].pos, 2); }
+}
+void mbo_comp_bias(void *h, int which, const uint8_t *q, int L, float *out) {
+    Oracle *o = (Oracle *)h; if (which == 0) comp_bias(o->seedMat, o->seedPBack, q, L, out, 1.0f); else comp_bias(o->alnMat, o->alnPBack, q, L, out, 1.0f);
+}
+
+// prefilter a batch: q residues concatenated, qOff[nQ+1].  hits: caller buffer of nQ*maxResListLen, hitCount[nQ].
+int mbo_prefilter(void *h, const uint8_t *q, const uint64_t *qOff, uint32_t nQ, mbo_hit *hits, uint32_t *hitCount, mbo_stats *stats, int threads) {
+    Oracle *o = (Oracle *)h; int err = 0; PrefStats tot; memset(&tot, 0, sizeof(tot));
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel
+    {
+        std::vector<PrefHit> out; PrefStats st; memset(&st, 0, sizeof(st));
+#pragma omp for schedule(dynamic, 1)
+        for (uint32_t i = 0; i < nQ; i++) {
+            int rc = prefilter_query(*o, q + qOff[i], (int)(qOff[i + 1] - qOff[i]), out, st);
+            if (rc != 0) {
+#pragma omp critical
+                err = rc;
+                hitCount[i] = 0; continue;
+            }
+            hitCount[i] = (uint32_t)out.size();
+            for (size_t k = 0; k < out.size(); k++) { mbo_hit &x = hits[(size_t)i * o->maxResListLen + k]; x.seqId = out[k].seqId; x.score = out[k].score; x.diag = (short)out[k].diag; }
+        }
+#pragma omp critical
+        { tot.kmers += st.kmers; tot.lookups += st.lookups; tot.dbMatches += st.dbMatches; tot.doubleHits += st.doubleHits; tot.diagCells += st.diagCells; tot.results += st.results; }
+    }
+    if (stats) { stats->kmers = tot.kmers; stats->lookups = tot.lookups; stats->dbMatches = tot.dbMatches; stats->doubleHits = tot.doubleHits; stats->diagCells = tot.diagCells; stats->results = tot.results; }
+    return err;
+}
+
+// align: for query i, its prefilter hits hitSeqId[hitOff[i]..hitOff[i+1]) in prefilter order. alns has the same layout.
+// (Alignment::run hot loop, M/src/alignment/Alignment.cpp:312-405; sorting by Matcher::compareHits is left to the caller.)
+int mbo_align(void *h, const uint8_t *q, const uint64_t *qOff, uint32_t nQ, const uint32_t *hitSeqId, const uint64_t *hitOff, mbo_aln *alns, uint64_t *cells, int threads) {
+    Oracle *o = (Oracle *)h; Alp alp; int err = 0; uint64_t totCells = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 5) reduction(+ : totCells)
+    for (uint32_t i = 0; i < nQ; i++) {
+        const uint8_t *qs = q + qOff[i]; const int L = (int)(qOff[i + 1] - qOff[i]);
+        if (hitOff[i + 1] == hitOff[i]) continue;
+        std::vector<int8_t> cb(L > 0 ? L : 1); aln_comp_bias(*o, qs, L, cb.data());
+        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
+            const uint32_t t = hitSeqId[k]; AlnRes r;
+            const uint8_t *ts = &o->unmasked[o->uoff[t]]; const int tLen = (int)(o->uoff[t + 1] - o->uoff[t]);
+            align_pair(*o, alp, qs, L, cb.data(), ts, tLen, r);
+            if (r.passed < 0) err = -4;
+            mbo_aln &a = alns[k]; a.seqId = t; a.score = r.score; a.bitScore = r.bitScore; a.qStart = r.qStart; a.qEnd = r.qEnd; a.dbStart = r.dbStart; a.dbEnd = r.dbEnd;
+            a.alnLen = r.alnLen; a.passed = r.passed; a.seqId_est = r.seqId; a.pad = 0; a.evalue = r.evalue;
+            totCells += (uint64_t)L * tLen + ((r.dbStart >= 0) ? (uint64_t)(r.qEnd + 1) * (r.dbEnd + 1) : 0);
+        }
+    }
+    if (cells) *cells = totCells;
+    return err;
+}
+
+double mbo_evalue(double score, double qLen, double dbResidues) { Alp a; return a.evalue(score, qLen, dbResidues); }
+int mbo_bitscore(double score) { Alp a; return (int)(a.bitScore(score) + 0.5); }
+
+// ---------------------------------------------------------------------------------------------
+// a16-a18  exon-chaining DP   reference/src/exonpredictor/collectoptimalset.cpp:36-222,224-424 ;
+//          reference/src/commons/PredictionParser.h:15-65,166-182
+// One call = one contig.  cands sorted by (targetKey, orfKey) as resultspercontig emits them (resultspercontig.cpp:17-32,182).
+// ---------------------------------------------------------------------------------------------
+struct mbo_cand { uint32_t targetKey; int32_t bitScore; int32_t qStart, qEnd; int32_t tStart, tEnd, tLen; uint32_t orfKey; int32_t fragFrom, fragTo; };
+struct mbo_exon { uint32_t candIdx; int32_t contigStart, contigEnd, nucLen; };   // contigStart/End signed as in PotentialExon
+struct mbo_call { uint32_t targetKey; int32_t strand; int32_t totalBitScore; int32_t nExons; uint32_t exonBegin; int32_t lowCoord, highCoord; int32_t pad; double evalue; };
+
+struct PE { uint32_t cand; int strand; int bitScore; int tStart, tEnd, tLen; double tCov; int cStart, cEnd, nucLen, aaLen; bool used; };
+
+static int dp_find(std::vector<PE> &c, std::vector<PE> &opt, size_t minIntron, size_t maxIntron, size_t maxOv, int gapO, int gapE, double tcovThr) {
+    size_t n = c.size(); if (n == 0) return 0;
+    std::stable_sort(c.begin(), c.end(), [](const PE &a, const PE &b) {       // PredictionParser.h:166-182
+        if (a.used < b.used) return true; if (a.used > b.used) return false;
+        if (a.cStart < b.cStart) return true; if (a.cStart > b.cStart) return false;
+        if (a.cEnd < b.cEnd) return true; if (a.cEnd > b.cEnd) return false; return false; });
+    size_t firstUsed = n; for (size_t i = 0; i < n; i++) if (c[i].used) { firstUsed = i; break; }
+    c.resize(firstUsed); n = c.size();
+    if (n == 0) return 0;   // (the reference would read c[0] of an empty vector here; unreachable with max-exon-sets loops guarded by size()>0 only before the call)
+    int targetLength = c[0].tLen;
+    struct Row { size_t prev; int score; size_t nEx; double cov; int aaLen; };
+    std::vector<Row> R(n);
+    for (size_t i = 0; i < n; i++) { R[i].prev = i; R[i].score = c[i].bitScore; R[i].nEx = 1; R[i].cov = c[i].tCov; R[i].aaLen = c[i].aaLen; }
+    int best = 0; size_t last = 0;
+    for (size_t cur = 0; cur < n; cur++) {
+        for (size_t prev = 0; prev < cur; prev++) {
+            const PE &a = c[prev], &b = c[cur];
+            // isPairCompatible  collectoptimalset.cpp:36-82
+            if (a.strand != b.strand) continue;
+            if (b.cEnd < a.cEnd) continue;
+            int diffOnContig = b.cStart - a.cEnd - 1; if (diffOnContig < 0) continue;
+            size_t dnn = abs(diffOnContig); if (dnn < minIntron || dnn > maxIntron) continue;
+            int diffAAs = b.tStart - a.tEnd - 1; size_t ov = 0;
+            if (diffAAs < 0) { ov = abs(diffAAs); if (ov > maxOv) continue; }
+            if (b.tStart < a.tStart) continue;
+            // getPenaltyForProtCoords  :84-106
+            int pen; if (diffAAs < 0) pen = gapO + gapE * (abs(diffAAs) - 1); else if (diffAAs <= 1) pen = 0; else pen = gapO + gapE * (diffAAs - 1);
+            size_t nEx = R[prev].nEx + 1; int bonus = (int)log2(nEx);
+            int sc = R[prev].score + pen + b.bitScore + bonus;
+            double cov = R[prev].cov + b.tCov; int aal = R[prev].aaLen + b.aaLen - (int)ov;
+            if (sc > R[cur].score) { R[cur].prev = prev; R[cur].score = sc; R[cur].nEx = nEx; R[cur].cov = cov; R[cur].aaLen = aal; }
+        }
+        if ((double)R[cur].aaLen / (double)targetLength >= tcovThr) if (R[cur].score > best) { last = cur; best = R[cur].score; }
+    }
+    if (best == 0) return 0;
+    size_t e = last;
+    while (R[e].prev != e) { opt.push_back(c[e]); c[e].used = true; e = R[e].prev; }
+    opt.push_back(c[e]); c[e].used = true;
+    std::reverse(opt.begin(), opt.end());
+    return best;
+}
+
+// returns number of calls; exons appended to exonsOut (caller sizes both to nCands*maxSets ; calls to 2*nTargets*maxSets)
+int mbo_chain(const mbo_cand *cands, uint32_t n, uint64_t totalTargetResidues, int minIntron, int maxIntron, int minExonAa, int maxOverlap,
+              int setGapOpen, int setGapExtend, double tcov, double evalThr, int maxSets, mbo_call *calls, mbo_exon *exonsOut, uint32_t *nExonsOut) {
+    uint32_t nCalls = 0, nEx = 0;
+    uint32_t i = 0;
+    while (i < n) {
+        uint32_t j = i; while (j < n && cands[j].targetKey == cands[i].targetKey) j++;
+        std::vector<PE> plus, minus;
+        for (uint32_t k = i; k < j; k++) {
+            const mbo_cand &c = cands[k]; PE e; e.cand = k; e.bitScore = c.bitScore; e.tStart = c.tStart; e.tEnd = c.tEnd; e.tLen = c.tLen; e.used = false;
+            if (c.fragFrom < c.fragTo) { e.cStart = c.fragFrom + c.qStart * 3; e.cEnd = c.fragFrom + c.qEnd * 3 + 2; e.strand = 1; }      // PredictionParser.h:40-51
+            else { e.cStart = -1 * (c.fragFrom - c.qStart * 3); e.cEnd = -1 * (c.fragFrom - c.qEnd * 3 - 2); e.strand = -1; }
+            e.nucLen = e.cEnd - e.cStart + 1; if (e.nucLen % 3 != 0) return -1; e.aaLen = e.nucLen / 3;
+            e.tCov = (double)(e.tEnd - e.tStart + 1) / e.tLen;
+            size_t aal = std::abs(e.nucLen) / 3;
+            if (aal >= (size_t)minExonAa) { if (e.strand == 1) plus.push_back(e); else minus.push_back(e); }                              // collectoptimalset.cpp:360-367
+        }
+        int it = 0;
+        while (it < maxSets && (plus.size() > 0 || minus.size() > 0)) {                                                                   // :313-317
+            std::vector<PE> op, om;
+            int sp = dp_find(plus, op, minIntron, maxIntron, maxOverlap, setGapOpen, setGapExtend, tcov);
+            int sm = dp_find(minus, om, minIntron, maxIntron, maxOverlap, setGapOpen, setGapExtend, tcov);
+            for (int s = 0; s < 2; s++) {
+                std::vector<PE> &os = s == 0 ? op : om; int tot = s == 0 ? sp : sm;
+                if (os.size() == 0) continue;
+                double l2 = log2(totalTargetResidues) + log2(2) - tot; double ev = pow(2, l2);                                            // :323-325
+                if (ev <= evalThr) {
+                    mbo_call &cl = calls[nCalls++]; cl.targetKey = cands[i].targetKey; cl.strand = s == 0 ? 1 : -1; cl.totalBitScore = tot; cl.nExons = (int)os.size();
+                    cl.exonBegin = nEx; cl.evalue = ev; cl.pad = 0;
+                    cl.lowCoord = (s == 0) ? os.front().cStart : (-1 * os.back().cEnd); cl.highCoord = (s == 0) ? os.back().cEnd : (-1 * os.front().cStart);   // PredictionParser.h:236-237
+                    for (auto &e : os) { mbo_exon &x = exonsOut[nEx++]; x.candIdx = e.cand; x.contigStart = e.cStart; x.contigEnd = e.cEnd; x.nucLen = e.nucLen; }
+                }
+            }
+            it++;
+        }
+        i = j;
+    }
+    *nExonsOut = nEx;
+    return (int)nCalls;
+}
+
+}  // extern "C"

@@ -129,14 +129,19 @@ def ref_index(tmp, db, mask, thr, log):
     nent = struct.unpack("<q", get(12)[:8])[0]
     entries = get(9)[:6 * nent]
     offsets = get(10)[:8 * (20 ** 6 + 1)]
+    import numpy as np
     sm3 = get(4)
-    nsc = 8000 * 8032
+    # ScoreMatrix::serialize: int16 score[8000][rowSize] then uint32 index[8000][rowSize]; rowSize is padded to the
+    # build's SIMD width (8064 on AVX2, 8032 on SSE) with -255/0 -- digest only the 8000 real columns.
+    row = (len(sm3) - 1) // 6 // 8000
+    sc = np.frombuffer(sm3[:2 * 8000 * row], dtype=np.int16).reshape(8000, row)[:, :8000]
+    ix = np.frombuffer(sm3[2 * 8000 * row:6 * 8000 * row], dtype=np.uint32).reshape(8000, row)[:, :8000]
     res = {
         "masked_targets": masked, "idx_n_entries": nent,
         "idx_entries_sha256": hashlib.sha256(entries).hexdigest(),
         "idx_offsets_u64_sha256": hashlib.sha256(offsets).hexdigest(),
-        "sim3_score_i16_sha256": hashlib.sha256(sm3[:2 * nsc]).hexdigest(),
-        "sim3_index_u32_sha256": hashlib.sha256(sm3[2 * nsc:2 * nsc + 4 * nsc]).hexdigest(),
+        "sim3_score_i16_sha256": hashlib.sha256(np.ascontiguousarray(sc).tobytes()).hexdigest(),
+        "sim3_index_u32_sha256": hashlib.sha256(np.ascontiguousarray(ix).tobytes()).hexdigest(),
         "idx_masked_residues": int(out.split("Masked residues: ")[1].split()[0]),
     }
     f.close()

@@ -1,0 +1,292 @@
+"""Test-side helpers: golden fixture loading, residue encoding, the ctypes binding of the CPU oracle
+(oracle/libmb200_oracle.so) and the reference's text formatters restated in Python so structured
+results can be compared byte-for-byte with the reference's result DBs.
+
+TEST INFRASTRUCTURE ONLY (the product never imports this)."""
+import ctypes as C
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libmb200_oracle.so")
+TABLE = 20 ** 6
+ROW3 = 8000
+
+# aa2num after SubstitutionMatrix::setupLetterMapping (reference/lib/mmseqs/src/commons/SubstitutionMatrix.cpp:262-304)
+_ORDER = "ACDEFGHIKLMNPQRSTVWYX"
+AA2NUM = np.full(256, 20, dtype=np.uint8)
+for _i, _c in enumerate(_ORDER):
+    AA2NUM[ord(_c)] = _i
+    AA2NUM[ord(_c.lower())] = _i
+for _a, _b in (("J", "L"), ("Z", "E"), ("B", "D")):
+    AA2NUM[ord(_a)] = AA2NUM[ord(_b)]
+    AA2NUM[ord(_a.lower())] = AA2NUM[ord(_b)]
+
+
+def encode(seq):
+    return AA2NUM[np.frombuffer(seq.encode(), dtype=np.uint8)]
+
+
+def pack(seqs):
+    """list of str -> (uint8 codes concatenated, uint64 offsets[n+1])"""
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    data = encode("".join(seqs)) if len(seqs) else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def load_case(name):
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rt") as f:
+        return json.load(f)
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "CXX=" + ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")])
+
+
+class Hit(C.Structure):
+    _fields_ = [("seqId", C.c_uint32), ("score", C.c_int32), ("diag", C.c_int32)]
+
+
+class Aln(C.Structure):
+    _fields_ = [("seqId", C.c_uint32), ("score", C.c_int32), ("bitScore", C.c_int32), ("qStart", C.c_int32), ("qEnd", C.c_int32),
+                ("dbStart", C.c_int32), ("dbEnd", C.c_int32), ("alnLen", C.c_int32), ("passed", C.c_int32), ("seqIdEst", C.c_float),
+                ("pad", C.c_float), ("evalue", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("kmers", "lookups", "dbMatches", "doubleHits", "diagCells", "results")]
+
+
+class Cand(C.Structure):
+    _fields_ = [("targetKey", C.c_uint32), ("bitScore", C.c_int32), ("qStart", C.c_int32), ("qEnd", C.c_int32), ("tStart", C.c_int32),
+                ("tEnd", C.c_int32), ("tLen", C.c_int32), ("orfKey", C.c_uint32), ("fragFrom", C.c_int32), ("fragTo", C.c_int32)]
+
+
+class Exon(C.Structure):
+    _fields_ = [("candIdx", C.c_uint32), ("contigStart", C.c_int32), ("contigEnd", C.c_int32), ("nucLen", C.c_int32)]
+
+
+class Call(C.Structure):
+    _fields_ = [("targetKey", C.c_uint32), ("strand", C.c_int32), ("totalBitScore", C.c_int32), ("nExons", C.c_int32), ("exonBegin", C.c_uint32),
+                ("lowCoord", C.c_int32), ("highCoord", C.c_int32), ("pad", C.c_int32), ("evalue", C.c_double)]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Oracle:
+    """ctypes binding of oracle/libmb200_oracle.so (the CPU restatement; the checker, never the product)."""
+
+    def __init__(self, need_sim3=True):
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        self.L = L
+        L.mbo_create.restype = C.c_void_p
+        L.mbo_sim3_score.restype = C.POINTER(C.c_int16)
+        L.mbo_sim3_index.restype = C.POINTER(C.c_uint32)
+        L.mbo_index_entries.restype = C.c_uint64
+        L.mbo_evalue.restype = C.c_double
+        L.mbo_evalue.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.mbo_bitscore.argtypes = [C.c_double]
+        self.h = C.c_void_p(L.mbo_create())
+        self.max_res = 300
+        self.nT = 0
+        if need_sim3:
+            L.mbo_build_sim3(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.mbo_destroy(self.h)
+            self.h = None
+
+    def set_params(self, kmerThr=127, maxResListLen=300, minDiagScore=15, binSize=2, gapOpen=11, gapExtend=1, evalThr=100.0, minAlnLen=11):
+        self.max_res = maxResListLen
+        self.L.mbo_set_params(self.h, kmerThr, maxResListLen, minDiagScore, binSize, gapOpen, gapExtend, C.c_double(evalThr), minAlnLen)
+
+    def matrices(self):
+        seed = np.zeros(441, np.int16); ung = np.zeros(441, np.int16); aln = np.zeros(441, np.int16)
+        sp = np.zeros(21, np.float64); ap = np.zeros(21, np.float64)
+        self.L.mbo_get_matrices(self.h, _p(seed, C.c_int16), _p(ung, C.c_int16), _p(aln, C.c_int16), _p(sp, C.c_double), _p(ap, C.c_double))
+        return seed, ung, aln, sp, ap
+
+    def sim3(self):
+        n = 8000 * ROW3
+        sc = np.ctypeslib.as_array(self.L.mbo_sim3_score(self.h), shape=(n,))
+        ix = np.ctypeslib.as_array(self.L.mbo_sim3_index(self.h), shape=(n,))
+        return sc, ix
+
+    def set_targets(self, masked, unmasked):
+        m, off = pack(masked)
+        u, off2 = pack(unmasked)
+        assert (off == off2).all()
+        self.nT = len(masked)
+        self.toff = off
+        rc = self.L.mbo_set_targets(self.h, _p(m, C.c_uint8), _p(u, C.c_uint8), _p(off, C.c_uint64), C.c_uint32(self.nT))
+        assert rc == 0, rc
+
+    def index(self):
+        n = self.L.mbo_index_entries(self.h)
+        offsets = np.zeros(TABLE + 1, np.uint64)
+        entries = np.zeros(6 * n, np.uint8)
+        self.L.mbo_index_copy(self.h, _p(offsets, C.c_uint64), _p(entries, C.c_uint8))
+        return offsets, entries
+
+    def comp_bias(self, which, seq):
+        q = encode(seq)
+        out = np.zeros(len(q), np.float32)
+        self.L.mbo_comp_bias(self.h, which, _p(q, C.c_uint8), len(q), _p(out, C.c_float))
+        return out
+
+    def prefilter(self, queries, threads=0):
+        q, off = pack(queries)
+        n = len(queries)
+        hits = (Hit * (n * self.max_res))()
+        cnt = np.zeros(n, np.uint32)
+        st = Stats()
+        rc = self.L.mbo_prefilter(self.h, _p(q, C.c_uint8), _p(off, C.c_uint64), C.c_uint32(n), hits, _p(cnt, C.c_uint32), C.byref(st), threads)
+        assert rc == 0, rc
+        out = []
+        for i in range(n):
+            out.append([(hits[i * self.max_res + k].seqId, hits[i * self.max_res + k].score, hits[i * self.max_res + k].diag) for k in range(cnt[i])])
+        return out, {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    def align(self, queries, hit_lists, threads=0):
+        """hit_lists[i] = list of target local ids for query i -> list of list of Aln-like dicts"""
+        q, off = pack(queries)
+        n = len(queries)
+        hoff = np.zeros(n + 1, np.uint64)
+        hoff[1:] = np.cumsum([len(h) for h in hit_lists], dtype=np.uint64)
+        flat = np.array([t for h in hit_lists for t in h], dtype=np.uint32)
+        if len(flat) == 0:
+            flat = np.zeros(1, np.uint32)
+        alns = (Aln * max(1, int(hoff[-1])))()
+        cells = C.c_uint64(0)
+        rc = self.L.mbo_align(self.h, _p(q, C.c_uint8), _p(off, C.c_uint64), C.c_uint32(n), _p(flat, C.c_uint32), _p(hoff, C.c_uint64), alns, C.byref(cells), threads)
+        assert rc == 0, rc
+        out = []
+        for i in range(n):
+            out.append([aln_to_dict(alns[k]) for k in range(int(hoff[i]), int(hoff[i + 1]))])
+        return out, cells.value
+
+    def chain(self, cands, total_residues, min_intron=15, max_intron=10000, min_exon_aa=11, max_overlap=10, gap_open=-1, gap_extend=-1,
+              tcov=0.5, eval_thr=0.001, max_sets=1):
+        return chain_call(self.L.mbo_chain, cands, total_residues, min_intron, max_intron, min_exon_aa, max_overlap, gap_open, gap_extend,
+                          tcov, eval_thr, max_sets)
+
+
+def aln_to_dict(a):
+    return dict(seqId=a.seqId, score=a.score, bitScore=a.bitScore, qStart=a.qStart, qEnd=a.qEnd, dbStart=a.dbStart, dbEnd=a.dbEnd,
+                alnLen=a.alnLen, passed=a.passed, seqIdEst=float(np.float32(a.seqIdEst)), evalue=a.evalue)
+
+
+def chain_call(fn, cands, total_residues, min_intron, max_intron, min_exon_aa, max_overlap, gap_open, gap_extend, tcov, eval_thr, max_sets):
+    """cands: list of dicts with the Cand fields, sorted by (targetKey, orfKey) -> list of calls (dict with 'exons')."""
+    n = len(cands)
+    arr = (Cand * max(1, n))()
+    for i, c in enumerate(cands):
+        for k, _ in Cand._fields_:
+            setattr(arr[i], k, c[k])
+    calls = (Call * max(1, 2 * n * max_sets))()
+    exons = (Exon * max(1, n * max_sets))()
+    nex = C.c_uint32(0)
+    fn.argtypes = [C.POINTER(Cand), C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                   C.c_int, C.POINTER(Call), C.POINTER(Exon), C.POINTER(C.c_uint32)]
+    fn.restype = C.c_int
+    nc = fn(arr, n, total_residues, min_intron, max_intron, min_exon_aa, max_overlap, gap_open, gap_extend, tcov, eval_thr, max_sets,
+            calls, exons, C.byref(nex))
+    assert nc >= 0, nc
+    out = []
+    for i in range(nc):
+        c = calls[i]
+        ex = [dict(candIdx=exons[k].candIdx, contigStart=exons[k].contigStart, contigEnd=exons[k].contigEnd, nucLen=exons[k].nucLen)
+              for k in range(c.exonBegin, c.exonBegin + c.nExons)]
+        out.append(dict(targetKey=c.targetKey, strand=c.strand, totalBitScore=c.totalBitScore, evalue=c.evalue, lowCoord=c.lowCoord,
+                        highCoord=c.highCoord, exons=ex))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference text formatters restated
+# ------------------------------------------------------------------------------------------------
+def fmt_pref(hits, keys):
+    """QueryMatcher::prefilterHitToBuffer (reference/lib/mmseqs/src/prefiltering/QueryMatcher.h:118-130)"""
+    return "".join("%d\t%d\t%d\n" % (keys[t], s, d) for t, s, d in hits)
+
+
+def fmt_seqid(x):
+    """Util::fastSeqIdToBuffer + the tab overwrite in Matcher::resultToBuffer
+    (reference/lib/mmseqs/src/commons/Util.cpp:222-251, alignment/Matcher.cpp:286-287): 1.0 prints as '1.00'."""
+    x = np.float32(x)
+    if x == np.float32(1.0):
+        return "1.00"
+    s = "0."
+    if x < 0.10:
+        s += "0"
+    if x < 0.01:
+        s += "0"
+    return s + str(int(np.float32(x * np.float32(1000))))
+
+
+def fmt_eval(e):
+    return "%.3E" % e
+
+
+def sort_alns(alns, keys, tlens):
+    """Matcher::compareHits (reference/lib/mmseqs/src/alignment/Matcher.h:157-168): eval asc, score desc, dbLen asc, dbKey asc"""
+    return sorted(alns, key=lambda a: (a["evalue"], -a["bitScore"], tlens[a["seqId"]], keys[a["seqId"]]))
+
+
+def fmt_aln(a, keys, qlen, tlens):
+    """Matcher::resultToBuffer, 10 columns (reference/lib/mmseqs/src/alignment/Matcher.cpp:280-327)"""
+    return "%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\n" % (keys[a["seqId"]], a["bitScore"], fmt_seqid(a["seqIdEst"]), fmt_eval(a["evalue"]),
+                                                         a["qStart"], a["qEnd"], qlen, a["dbStart"], a["dbEnd"], tlens[a["seqId"]])
+
+
+def parse_orf_header(h):
+    """Orf::parseOrfHeader (reference/lib/mmseqs/src/commons/Orf.cpp:351-438): 'contigKey\\tfrom+len' / 'from-len'"""
+    w = h.split()
+    contig = int(w[0])
+    loc = w[1]
+    if "+" in loc:
+        a, b = loc.split("+")
+        return contig, int(a), int(a) + int(b)
+    a, b = loc.split("-")
+    return contig, int(a), int(a) - int(b)
+
+
+def fmt_exon_seqid(text):
+    """PotentialExon::exonToBuffer seqId chain (reference/src/commons/PredictionParser.h:21,106-136):
+    text -> strtod -> double -> float -> *1000 -> int"""
+    f = np.float32(float(text))
+    if f == np.float32(1.0):
+        return "1.000"
+    s = "0."
+    if f < 0.10:
+        s += "0"
+    if f < 0.01:
+        s += "0"
+    return s + str(int(np.float32(f * np.float32(1000))))
+
+
+def fmt_dp(calls, cands):
+    """Prediction::predictionToBuffer, 19 columns per exon line (reference/src/commons/PredictionParser.h:368-396,97-163).
+    cands[i] needs the text fields 'seqIdText', 'evalText' of the search_res record it came from."""
+    out = ""
+    for c in calls:
+        head = "%d\t%d\t%d\t%s\t%d\t%d\t%d\t" % (c["targetKey"], c["strand"], c["totalBitScore"], fmt_eval(c["evalue"]), len(c["exons"]),
+                                                 c["lowCoord"], c["highCoord"])
+        for e in c["exons"]:
+            k = cands[e["candIdx"]]
+            out += head + "%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n" % (
+                k["orfKey"], k["bitScore"], fmt_exon_seqid(k["seqIdText"]), fmt_eval(float(k["evalText"])), k["tStart"], k["tEnd"], k["tLen"],
+                e["contigStart"], e["contigEnd"], e["nucLen"], k["fragFrom"], k["fragTo"])
+    return out
