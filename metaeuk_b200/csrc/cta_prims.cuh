@@ -1,0 +1,129 @@
+// cta_prims.cuh -- block-level ("CTA") programming primitives used by the prefilter / chain kernels.
+//
+// The kernels are written as a sequence of block-wide parallel-for regions separated by barriers
+// (CTA_FOR ... CTA_SYNC) plus three collective primitives (exclusive scan, 64-bit key sort, append).
+// Under nvcc these compile to the real sm_100a code.  Under a host compiler with -DMB200_EMULATE the
+// same source compiles to a serial single-"thread" execution (CTA_FOR = plain loop); that build exists
+// ONLY so tests/ can check the kernel logic against the oracle in a container without a GPU.  It is not
+// part of libmetaeuk_b200.so and is never used as a fallback.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MB200_EMULATE)
+#define MB_DEVICE_BUILD 1
+#define MB_DEV __device__ __forceinline__
+#define CTA_TID (threadIdx.x)
+#define CTA_NT (blockDim.x)
+#define CTA_FOR(i, n) for (uint32_t i = threadIdx.x, i##_end = (uint32_t)(n); i < i##_end; i += blockDim.x)
+#define CTA_SYNC() __syncthreads()
+#define CTA_SINGLE if (threadIdx.x == 0)
+MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+// IEEE double ops that must never be contracted into FMAs (composition-bias parity with the CPU path)
+MB_DEV double mb_dmul(double a, double b) { return __dmul_rn(a, b); }
+MB_DEV double mb_dadd(double a, double b) { return __dadd_rn(a, b); }
+MB_DEV double mb_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+MB_DEV float mb_fadd(float a, float b) { return __fadd_rn(a, b); }
+MB_DEV float mb_fmul(float a, float b) { return __fmul_rn(a, b); }
+MB_DEV float mb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+#else
+#define MB_DEVICE_BUILD 0
+#define MB_DEV static inline
+#define CTA_TID (0u)
+#define CTA_NT (1u)
+#define CTA_FOR(i, n) for (uint32_t i = 0, i##_end = (uint32_t)(n); i < i##_end; i++)
+#define CTA_SYNC() ((void)0)
+#define CTA_SINGLE if (true)
+#include <algorithm>
+struct uint2 { unsigned int x, y; };
+MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+MB_DEV double mb_dmul(double a, double b) { return a * b; }   // emulation is built with -ffp-contract=off
+MB_DEV double mb_dadd(double a, double b) { return a + b; }
+MB_DEV double mb_ddiv(double a, double b) { return a / b; }
+MB_DEV float mb_fadd(float a, float b) { return a + b; }
+MB_DEV float mb_fmul(float a, float b) { return a * b; }
+MB_DEV float mb_fdiv(float a, float b) { return a / b; }
+#endif
+
+#define MB_CTA_THREADS 256
+
+// Scratch every collective needs (lives in shared memory on the device).
+struct CtaScratch {
+    uint32_t part[MB_CTA_THREADS + 1];
+    uint32_t bcast[4];
+};
+
+// In-place exclusive prefix sum of a[0..n); also writes a[n] = total and returns the total to every thread.
+// a may live in shared or global memory.
+MB_DEV uint32_t cta_exclusive_scan(uint32_t *a, uint32_t n, CtaScratch *s) {
+#if MB_DEVICE_BUILD
+    const uint32_t T = blockDim.x, tid = threadIdx.x;
+    const uint32_t chunk = (n + T - 1) / T;
+    uint32_t begin = tid * chunk; if (begin > n) begin = n;
+    uint32_t end = begin + chunk; if (end > n) end = n;
+    uint32_t sum = 0;
+    for (uint32_t i = begin; i < end; i++) sum += a[i];
+    s->part[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {   // warp 0 scans the T partial sums, T/32 consecutive partials per lane
+        const uint32_t per = T / 32;
+        uint32_t loc = 0;
+        for (uint32_t k = 0; k < per; k++) loc += s->part[tid * per + k];
+        uint32_t inc = loc;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)tid >= d) inc += y; }
+        uint32_t run = inc - loc;
+        for (uint32_t k = 0; k < per; k++) { uint32_t v = s->part[tid * per + k]; s->part[tid * per + k] = run; run += v; }
+        if (tid == 31) s->part[T] = run;
+    }
+    __syncthreads();
+    uint32_t run = s->part[tid];
+    for (uint32_t i = begin; i < end; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+    const uint32_t total = s->part[T];
+    if (tid == 0) a[n] = total;
+    __syncthreads();
+    return total;
+#else
+    (void)s;
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < n; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+    a[n] = run;
+    return run;
+#endif
+}
+
+// largest idx in [0,n) with a[idx] <= x, for a non-decreasing a[0..n] with a[0] == 0 <= x < a[n]
+MB_DEV uint32_t cta_find_segment(const uint32_t *a, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;   // invariant: a[lo] <= x < a[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (a[mid] <= x) lo = mid; else hi = mid; }
+    return lo;
+}
+
+MB_DEV uint32_t mb_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
+
+// Ascending sort of 64-bit keys a[0..n).  The buffer must have room for next_pow2(n) elements (padding is
+// written as ~0).  Bitonic network with block barriers; fine for the few-hundred-element lists the prefilter sorts.
+MB_DEV void cta_sort_u64(uint64_t *a, uint32_t n) {
+#if MB_DEVICE_BUILD
+    const uint32_t n2 = mb_next_pow2(n);
+    for (uint32_t i = n + threadIdx.x; i < n2; i += blockDim.x) a[i] = ~0ull;
+    __syncthreads();
+    if (n2 < 2) return;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                const uint32_t l = ((t / j) * (j << 1)) + (t % j);   // j is a power of two
+                const uint32_t r = l + j;
+                const bool asc = ((l & k) == 0);
+                const uint64_t x = a[l], y = a[r];
+                if ((x > y) == asc) { a[l] = y; a[r] = x; }
+            }
+            __syncthreads();
+        }
+    }
+#else
+    std::sort(a, a + n);
+#endif
+}

@@ -1,0 +1,52 @@
+// host_tables.h -- host-side preprocessing for the B200 hot path (plain C++, no CUDA):
+// substitution matrices, 3-mer similarity tables, target k-mer index, e-value model.
+// These are the one-time "setup" steps the reference also does on the host before its query loop
+// (SURVEY.md section 8a rows a1-a3, a14); the per-query work is in the CUDA kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace mb200 {
+
+const int AL = 21;
+const int N3 = 8000;
+const size_t KMER_TABLE = 64000000;   // 20^6
+
+struct Matrices {
+    int16_t seed[441];   // VTML80  x8  bias -0.2  (k-mer similarity)
+    int16_t ung[441];    // BLOSUM62 x2 bias -0.2  (ungapped diagonal score)
+    int16_t aln[441];    // BLOSUM62 x2 bias  0.0  (gapped alignment)
+    double seedPBack[21];
+    double alnPBack[21];
+};
+// SubstitutionMatrix ctor semantics (reference/lib/mmseqs/src/commons/SubstitutionMatrix.cpp:12-57, BaseMatrix.cpp:110-159)
+void default_matrices(Matrices &m);
+
+// sim3[r][z] = (neighbour 3-mer index << 16) | (uint16_t)score, z-th best neighbour of 3-mer r in the reference's
+// order (ExtendedSubstitutionMatrix::calcScoreMatrix, reference/lib/mmseqs/src/prefiltering/ExtendedSubstitutionMatrix.cpp:20-69);
+// cnt3[r][x - cntMin] = number of neighbours of r scoring >= x.
+void build_sim3(const int16_t seed[441], std::vector<uint32_t> &sim3, std::vector<uint16_t> &cnt3, int cntMin, int cntW);
+
+struct TargetIndex {
+    std::vector<uint32_t> offsets;          // [20^6 + 1]
+    std::vector<uint64_t> entries;          // low 32 bits seqId, next 16 bits pos_j  (device layout uint2)
+};
+// IndexBuilder::fillDatabase semantics on ALREADY MASKED residues
+// (reference/lib/mmseqs/src/prefiltering/IndexBuilder.cpp:55-239, IndexTable.h:133-173,348-401,182-189)
+int build_index(const uint8_t *masked, const uint64_t *off, uint32_t nT, const int16_t seed[441], int kmerThr, TargetIndex &idx);
+// same layout from a reference IndexTable (offsets size_t[20^6+1], packed 6-byte IndexEntryLocal entries)
+int import_index(const uint64_t *offsets, const uint8_t *entries6, uint64_t nEntries, TargetIndex &idx);
+
+// Gumbel/finite-size e-value model of the reference for BLOSUM62 gap 11/1
+// (reference/lib/mmseqs/src/alignment/EvalueComputation.h:18-40,56-69 -> Sls::AlignmentEvaluer::area)
+struct EvalueModel {
+    double lambda, K, a1, b1, a2, b2, alpha1, beta1, alpha2, beta2, sigma, tau, viThr, vjThr, cThr, logK;
+    EvalueModel();
+    double evalue(double score, double qLen, double dbResidues) const;
+    int bitScore(double score) const;   // int(bits + 0.5)  (Matcher.cpp:130)
+    // smallest raw score whose e-value is <= evalThr for this query length (e-value is decreasing in score)
+    int minScoreFor(double evalThr, double qLen, double dbResidues) const;
+};
+
+}  // namespace mb200

@@ -1,0 +1,323 @@
+// prefilter_core.cuh -- the per-query k-mer prefilter, one CTA per query fragment.
+//
+// Reproduces, bit for bit, what the reference computes per query in
+//   QueryMatcher::matchQuery / match          reference/lib/mmseqs/src/prefiltering/QueryMatcher.cpp:85-211,213-346
+//   KmerGenerator::generateKmerList           .../KmerGenerator.cpp:107-183,186-216
+//   CacheFriendlyOperations::findDuplicates   .../CacheFriendlyOperations.cpp:185-274   (order-dependent double-hit rule)
+//   UngappedAlignment::computeScores          .../UngappedAlignment.cpp:30-43,331-362
+//   keepMaxScoreElementOnly / top-N / sort    .../CacheFriendlyOperations.cpp:350-380, QueryMatcher.cpp:153-209,363-420
+// but organised for a GPU: the reference's per-target byte array scan in *arrival order* becomes
+//   (1) a 2-bit-per-slot shared-memory occupancy map that separates targets hit once from targets hit >= 2 times,
+//   (2) a sort of the (few) multi-hit entries by (target, arrival index) and a per-target run walk.
+// Arrival index = position in the reference's databaseHits buffer: (query position, similar-k-mer rank, list order).
+#pragma once
+#include "cta_prims.cuh"
+
+#define MB_AL 21
+#define MB_XRES 20
+#define MB_N3 8000
+#define MB_CNT_MIN (-192)
+#define MB_CNT_W 384
+#define MB_NSLOT_LOG 18
+#define MB_NSLOT (1u << MB_NSLOT_LOG)
+
+// hit / candidate word:  seqId[27] | arrival[21] | diag16[16]
+#define MB_MAX_SEQID_BITS 27
+#define MB_MAX_ARRIVAL_BITS 21
+#define MB_W_SEQ(w) ((uint32_t)((w) >> 37))
+#define MB_W_ARR(w) ((uint32_t)(((w) >> 16) & 0x1FFFFFu))
+#define MB_W_DIAG(w) ((uint16_t)((w) & 0xFFFFu))
+
+enum { MB_ST_OK = 0, MB_ST_TOO_LONG = 1, MB_ST_OVERFLOW = 2 };
+
+struct MbPrefHit { uint32_t seqId; int32_t score; int32_t diag; };
+
+struct MbPrefTables {
+    const uint32_t *sim3;      // [8000][8000]  (neighbour 3-mer index << 16) | (uint16)score, descending score, reference order
+    const uint16_t *cnt3;      // [8000][MB_CNT_W]  #neighbours with score >= (x + MB_CNT_MIN)
+    const uint32_t *offsets;   // [20^6 + 1]
+    const uint2 *entries;      // (seqId, pos_j)
+    const uint8_t *tseq;       // masked target residues
+    const uint64_t *toff;      // [nT + 1]
+    uint32_t nT;
+    int kmerThr, maxHits, minDiag;
+    uint32_t binMask;          // BINSIZE - 1 of the reference's CacheFriendlyOperations<BINSIZE>
+    uint32_t capP, capI, capK, capM;
+};
+
+struct MbPrefScratch {        // per-CTA global scratch
+    uint32_t *itemOff;  // capP + 1
+    int16_t *wThr; uint16_t *wI0, *wI1;   // capP
+    uint32_t *kmerOff;  // capI + 1
+    uint32_t *itemInfo; // capI          p << 13 | i
+    uint32_t *hitOff;   // capK + 1
+    uint32_t *kmerLo;   // capK
+    uint16_t *kmerP;    // capK
+    uint64_t *A, *B, *C;   // capM each (power of two)
+    int32_t *S;            // capM
+};
+
+struct MbPrefShared {
+    CtaScratch cs;
+    uint32_t hist[256];
+    uint32_t cnt[8];       // 0 nMulti, 1 nCand, 2 nSurv, 3 thr, 4 nPass, 5 rescale, 6 status
+    int8_t ungMat[448];
+    uint32_t slots[MB_NSLOT / 16];
+};
+
+struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; };
+
+MB_DEV uint32_t mb_count_ge(const uint16_t *cnt3, uint32_t row, int x) {
+    if (x <= MB_CNT_MIN) return MB_N3;
+    if (x >= MB_CNT_MIN + MB_CNT_W) return 0;
+    return cnt3[(size_t)row * MB_CNT_W + (x - MB_CNT_MIN)];
+}
+
+// UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:30-43,416-430)
+MB_DEV int mb_diag_score(const int8_t *ungMat, const uint8_t *q, const int8_t *corr, uint32_t L, const uint8_t *t, uint32_t tLen, uint16_t diag16,
+                         uint32_t *cells) {
+    const int diagonal = (int16_t)diag16;
+    const uint16_t d1 = (uint16_t)(0 - diag16), d2 = diag16;
+    const uint32_t dist = d1 < d2 ? d1 : d2;
+    uint32_t n, qo, to;
+    if (diagonal >= 0 && dist < L) { n = (tLen < L - dist) ? tLen : (L - dist); qo = dist; to = 0; }
+    else if (diagonal < 0 && dist < tLen) { n = (tLen - dist < L) ? (tLen - dist) : L; qo = 0; to = dist; }
+    else { *cells = 0; return 0; }
+    int mx = 0, score = 0;
+    for (uint32_t pos = 0; pos < n; pos++) {
+        const int curr = (int8_t)(ungMat[q[qo + pos] * MB_AL + t[to + pos]] + corr[qo + pos]);
+        score += curr; score = score < 0 ? 0 : score; mx = score > mx ? score : mx;
+    }
+    *cells = n;
+    return mx;
+}
+
+// One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
+MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
+                               const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
+    const uint32_t P = (L >= 10) ? (L - 9) : 0;   // Sequence::hasNextKmer, spaced pattern length 10 (Sequence.h:23,92-94)
+    CTA_SINGLE { for (int i = 0; i < 8; i++) sh->cnt[i] = 0; }
+    CTA_FOR(i, 256) sh->hist[i] = 0;
+    CTA_FOR(i, MB_NSLOT / 16) sh->slots[i] = 0;
+    CTA_SYNC();
+    if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
+    if (P == 0) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OK; } return; }
+
+    // ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140)
+    CTA_FOR(p, P) {
+        const uint8_t *w = q + p;
+        const uint32_t r0 = w[0], r1 = w[1], r2 = w[3], r3 = w[5], r4 = w[8], r5 = w[9];
+        float b = 0.0f;
+        b = mb_fadd(b, bias[p + 0]); b = mb_fadd(b, bias[p + 1]); b = mb_fadd(b, bias[p + 3]);
+        b = mb_fadd(b, bias[p + 5]); b = mb_fadd(b, bias[p + 8]); b = mb_fadd(b, bias[p + 9]);
+        uint32_t n0 = 0; int thr = 0; uint32_t i0 = 0, i1 = 0;
+        const bool hasX = (r0 == MB_XRES) | (r1 == MB_XRES) | (r2 == MB_XRES) | (r3 == MB_XRES) | (r4 == MB_XRES) | (r5 == MB_XRES);
+        if (!hasX) {
+            const short bs = (short)((b < 0.0) ? (double)b - 0.5 : (double)b + 0.5);
+            thr = T.kmerThr - bs; if (thr < 0) thr = 0;
+            i0 = r0 + 20 * r1 + 400 * r2; i1 = r3 + 20 * r4 + 400 * r5;
+            const int top1 = (int16_t)(T.sim3[(size_t)i1 * MB_N3] & 0xFFFFu);
+            const short cutoff1 = (short)(thr - top1);
+            n0 = mb_count_ge(T.cnt3, i0, cutoff1);
+        }
+        W.itemOff[p] = n0; W.wThr[p] = (int16_t)thr; W.wI0[p] = (uint16_t)i0; W.wI1[p] = (uint16_t)i1;
+    }
+    CTA_SYNC();
+    const uint32_t I = cta_exclusive_scan(W.itemOff, P, &sh->cs);
+    if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+
+    // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216)
+    CTA_FOR(it, I) {
+        const uint32_t p = cta_find_segment(W.itemOff, P, it);
+        const uint32_t i = it - W.itemOff[p];
+        const int s0 = (int16_t)(T.sim3[(size_t)W.wI0[p] * MB_N3 + i] & 0xFFFFu);
+        const short cutoff2 = (short)((int)W.wThr[p] - s0);
+        W.kmerOff[it] = mb_count_ge(T.cnt3, W.wI1[p], cutoff2);
+        W.itemInfo[it] = (p << 13) | i;
+    }
+    CTA_SYNC();
+    const uint32_t K = cta_exclusive_scan(W.kmerOff, I, &sh->cs);
+    if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+
+    // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
+    CTA_FOR(k, K) {
+        const uint32_t it = cta_find_segment(W.kmerOff, I, k);
+        const uint32_t j = k - W.kmerOff[it];
+        const uint32_t info = W.itemInfo[it]; const uint32_t p = info >> 13, i = info & 0x1FFFu;
+        const uint32_t k0 = T.sim3[(size_t)W.wI0[p] * MB_N3 + i] >> 16;
+        const uint32_t k1 = T.sim3[(size_t)W.wI1[p] * MB_N3 + j] >> 16;
+        const uint32_t kmer = k0 + k1 * 8000u;
+        const uint32_t lo = T.offsets[kmer], hi = T.offsets[kmer + 1];
+        W.hitOff[k] = hi - lo; W.kmerLo[k] = lo; W.kmerP[k] = (uint16_t)p;
+    }
+    CTA_SYNC();
+    const uint32_t M = cta_exclusive_scan(W.hitOff, K, &sh->cs);
+    if (M > T.capM || M >= (1u << MB_MAX_ARRIVAL_BITS)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+
+    // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
+    CTA_FOR(h, M) {
+        const uint32_t k = cta_find_segment(W.hitOff, K, h);
+        const uint2 e = T.entries[(size_t)W.kmerLo[k] + (h - W.hitOff[k])];
+        const uint16_t diag16 = (uint16_t)((uint32_t)W.kmerP[k] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+        W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
+        const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+        const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+        if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+    }
+    CTA_SYNC();
+    // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
+    //               targets possibly seen more than once -> multi list
+    CTA_FOR(h, M) {
+        const uint64_t w = W.A[h];
+        const uint32_t slot = MB_W_SEQ(w) & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+        if ((sh->slots[slot >> 4] >> sft) & 2u) { W.B[mb_atomic_add(&sh->cnt[0], 1u)] = w; }
+        else if ((w & 0xFFu) == 0) { W.C[mb_atomic_add(&sh->cnt[1], 1u)] = w; }
+    }
+    CTA_SYNC();
+    const uint32_t nMulti = sh->cnt[0];
+    // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
+    cta_sort_u64(W.B, nMulti);
+    CTA_FOR(e, nMulti) {
+        const uint32_t id = MB_W_SEQ(W.B[e]);
+        if (e == 0 || MB_W_SEQ(W.B[e - 1]) != id) {
+            uint32_t last = 0; int prevCand = -1;
+            for (uint32_t x = e; x < nMulti && MB_W_SEQ(W.B[x]) == id; x++) {
+                const uint64_t w = W.B[x]; const uint32_t d8 = (uint32_t)(w & 0xFFu);
+                if (d8 == last) {                         // duplicate of the immediately preceding hit of this target
+                    if (prevCand != (int)d8) W.C[mb_atomic_add(&sh->cnt[1], 1u)] = w;   // runs of equal diagonals collapse to their first
+                    prevCand = (int)d8;
+                }
+                last = d8;
+            }
+        }
+    }
+    CTA_SYNC();
+    const uint32_t D = sh->cnt[1];
+    // ---- P8/P9 ungapped diagonal scores
+    cta_sort_u64(W.C, D);
+    uint32_t myCells = 0;
+    CTA_FOR(c, D) {
+        const uint64_t w = W.C[c]; const uint32_t id = MB_W_SEQ(w);
+        const uint64_t to = T.toff[id]; const uint32_t tLen = (uint32_t)(T.toff[id + 1] - to);
+        uint32_t cells;
+        W.S[c] = mb_diag_score(sh->ungMat, q, corr, L, T.tseq + to, tLen, MB_W_DIAG(w), &cells);
+        myCells += cells;
+    }
+    CTA_SYNC();
+    // ---- P10 best diagonal per target: first maximum in arrival order (keepMaxElement, CacheFriendlyOperations.cpp:350-380)
+    CTA_FOR(c, D) {
+        const uint32_t id = MB_W_SEQ(W.C[c]);
+        if (c == 0 || MB_W_SEQ(W.C[c - 1]) != id) {
+            uint32_t best = 0, bestIdx = c;
+            for (uint32_t x = c; x < D && MB_W_SEQ(W.C[x]) == id; x++) {
+                const int s = W.S[x]; const uint32_t cnt = s > 255 ? 255u : (uint32_t)s;
+                if (cnt > best) { best = cnt; bestIdx = x; }
+            }
+            if (best > 0) {   // count==0 entries never reach the output (threshold >= 1 is enforced by the host API)
+                const uint64_t bw = W.C[bestIdx];
+                W.B[mb_atomic_add(&sh->cnt[2], 1u)] = ((uint64_t)(255u - best) << 53) | ((uint64_t)(id & T.binMask) << 42) | ((uint64_t)MB_W_ARR(bw) << 21) | bestIdx;
+                mb_atomic_add(&sh->hist[best], 1u);
+            }
+        }
+    }
+    CTA_SYNC();
+    const uint32_t nSurv = sh->cnt[2];
+    // ---- P11 score threshold (computeScoreThreshold, QueryMatcher.h:206-216; QueryMatcher.cpp:153-155)
+    CTA_SINGLE {
+        const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
+        uint32_t found = 0, thr = 0;
+        for (thr = 255; thr > 0; thr--) { found += sh->hist[thr]; if (found >= maxHits) break; }
+        if (thr < (uint32_t)T.minDiag) thr = (uint32_t)T.minDiag;
+        uint32_t nPass = 0;
+        for (uint32_t s = thr; s < 256; s++) nPass += sh->hist[s];
+        sh->cnt[3] = thr; sh->cnt[4] = nPass;
+    }
+    // ---- P12 stable order of the reference's counting sort: score desc, then bin (seqId & (BINSIZE-1)), then arrival
+    cta_sort_u64(W.B, nSurv);
+    const uint32_t thr = sh->cnt[3];
+    uint32_t nPass = sh->cnt[4];
+    const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
+    const bool truncated = thr >= 255;
+    if (truncated) {
+        // ---- rescoreHits (QueryMatcher.cpp:160-170,525-544): >= maxHits targets saturate the 8-bit score
+        CTA_SINGLE {
+            uint32_t cells;
+            int self = mb_diag_score(sh->ungMat, q, corr, L, q, L, 0, &cells);
+            self -= 255; if (self < 1) self = 1; if (self > 65535) self = 65535;
+            sh->cnt[5] = (uint32_t)self;
+        }
+        CTA_SYNC();
+        const float fltMax = (float)(int)sh->cnt[5];
+        CTA_FOR(i, nPass) {
+            const uint32_t ci = (uint32_t)(W.B[i] & 0x1FFFFFu);
+            uint32_t ns = (uint32_t)W.S[ci] - 255u; if (ns > 65535u) ns = 65535u;
+            const float sc = (float)ns;
+            const uint32_t nc = (uint32_t)(unsigned char)((double)mb_fmul(mb_fdiv(sc, fltMax), 255.0f) + 0.5);
+            W.A[i] = ((uint64_t)(255u - nc) << 53) | ((uint64_t)i << 21) | ci;
+        }
+        CTA_SYNC();
+        CTA_FOR(i, nPass) W.B[i] = W.A[i];
+        CTA_SYNC();
+        cta_sort_u64(W.B, nPass);
+    }
+    const uint32_t nSel = nPass < maxHits ? nPass : maxHits;
+    // ---- P13 getResult<UNGAPPED_DIAGONAL_SCORE> (QueryMatcher.cpp:363-420): exact score when the 8-bit score saturated
+    CTA_FOR(i, nSel) {
+        const uint64_t w = W.B[i]; const uint32_t ci = (uint32_t)(w & 0x1FFFFFu);
+        const uint32_t cnt = 255u - (uint32_t)(w >> 53);
+        uint32_t score;
+        if (truncated) score = 255u + (cnt * sh->cnt[5] / 255u);
+        else score = (cnt >= 255u) ? (uint32_t)W.S[ci] : cnt;
+        const uint64_t cw = W.C[ci];
+        W.A[i] = ((uint64_t)(0xFFFFFu - (score & 0xFFFFFu)) << 43) | ((uint64_t)MB_W_SEQ(cw) << 16) | MB_W_DIAG(cw);
+    }
+    CTA_SYNC();
+    // ---- P14 final order: score desc, seqId asc (hit_t::compareHitsByScoreAndId, QueryMatcher.h:38-48)
+    cta_sort_u64(W.A, nSel);
+    CTA_FOR(i, nSel) {
+        const uint64_t w = W.A[i];
+        MbPrefHit hres; hres.seqId = (uint32_t)((w >> 16) & 0x7FFFFFFu); hres.score = (int32_t)(0xFFFFFu - (uint32_t)(w >> 43)); hres.diag = (int16_t)(w & 0xFFFFu);
+        out[i] = hres;
+    }
+    // stats (algorithmic-byte numerators for the roofline)
+#if MB_DEVICE_BUILD
+    if (stats) {
+        if (myCells) atomicAdd(&stats->diagCells, (unsigned long long)myCells);
+        if (threadIdx.x == 0) { atomicAdd(&stats->kmers, (unsigned long long)K); atomicAdd(&stats->lookups, (unsigned long long)K);
+            atomicAdd(&stats->dbMatches, (unsigned long long)M); atomicAdd(&stats->doubleHits, (unsigned long long)D); atomicAdd(&stats->results, (unsigned long long)nSel); }
+    }
+#else
+    if (stats) { stats->diagCells += myCells; stats->kmers += K; stats->lookups += K; stats->dbMatches += M; stats->doubleHits += D; stats->results += nSel; }
+#endif
+    CTA_SINGLE { *outCount = nSel; *outStatus = MB_ST_OK; }
+    CTA_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-residue preparation: float composition bias (SubstitutionMatrix::calcLocalAaBiasCorrection,
+// reference/lib/mmseqs/src/commons/SubstitutionMatrix.cpp:79-109) for the seed matrix and the alignment matrix,
+// the int8 ungapped-profile correction (UngappedAlignment.cpp:392-397) and the int8 SW composition bias
+// (StripedSmithWaterman.cpp:1229-1237).  Exact IEEE op order, no FMA contraction.
+// ---------------------------------------------------------------------------------------------------
+MB_DEV float mb_comp_bias_at(const int16_t *mat /*[441]*/, const double *pBack /*[21]*/, const uint8_t *seq, int N, int i) {
+    const int minPos = (i - 20) > 0 ? (i - 20) : 0;
+    const int maxPos = (i + 20) < N ? (i + 20) : N;
+    const int windowLength = maxPos - minPos;
+    int sum = 0;
+    const int16_t *row = mat + seq[i] * MB_AL;
+    for (int j = minPos; j < maxPos; j++) sum += row[seq[j]];
+    sum -= row[seq[i]];
+    float d = (float)sum;
+    d = (float)mb_ddiv((double)d, mb_dmul(-1.0, (double)(float)windowLength));
+    for (int a = 0; a < MB_AL; a++) d = (float)mb_dadd((double)d, mb_dmul(pBack[a], (double)(float)row[a]));
+    return d;   // scale == 1.0f
+}
+MB_DEV int8_t mb_round_bias_quarter(float b) {   // UngappedAlignment.cpp:394-396
+    float t = mb_fdiv(b, 4.0f);
+    t = (float)((b < 0.0) ? mb_dadd((double)t, -0.5) : mb_dadd((double)t, 0.5));
+    return (int8_t)t;
+}
+MB_DEV int8_t mb_round_bias(float b) {           // StripedSmithWaterman.cpp:1233
+    const double t = (b < 0.0) ? mb_dadd((double)b, -0.5) : mb_dadd((double)b, 0.5);
+    return (int8_t)t;
+}

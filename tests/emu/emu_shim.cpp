@@ -1,0 +1,76 @@
+// tests/emu/emu_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's kernel source (prefilter_core.cuh) with MB200_EMULATE (serial CTA emulation, see
+// cta_prims.cuh) plus the product's host preprocessing (host_tables.cpp) into a CPU library so the kernel
+// LOGIC can be diffed against the oracle in a container without a GPU.  Not shipped, not a fallback.
+#define MB200_EMULATE 1
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../metaeuk_b200/csrc/host_tables.h"
+#include "../../metaeuk_b200/csrc/prefilter_core.cuh"
+
+extern "C" {
+
+int emu_matrices(int16_t *seed, int16_t *ung, int16_t *aln, double *seedPBack, double *alnPBack) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    memcpy(seed, m.seed, 882); memcpy(ung, m.ung, 882); memcpy(aln, m.aln, 882); memcpy(seedPBack, m.seedPBack, 168); memcpy(alnPBack, m.alnPBack, 168);
+    return 0;
+}
+
+// sim3 unpacked for comparison with the oracle / reference digest
+int emu_sim3(int16_t *score, uint32_t *index) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
+    mb200::build_sim3(m.seed, sim3, cnt3, MB_CNT_MIN, MB_CNT_W);
+    for (size_t i = 0; i < sim3.size(); i++) { score[i] = (int16_t)(sim3[i] & 0xFFFF); index[i] = sim3[i] >> 16; }
+    // cnt3 self-check
+    for (int r = 0; r < 8000; r += 97) for (int x = -150; x < 180; x += 7) {
+        uint32_t c = 0; for (int z = 0; z < 8000; z++) c += ((int16_t)(sim3[(size_t)r * 8000 + z] & 0xFFFF) >= x);
+        if (c != mb_count_ge(cnt3.data(), r, x)) return -1;
+    }
+    return 0;
+}
+
+// index in the reference's serialised form (u64 offsets, packed 6-byte entries) for digest comparison
+int emu_index(const uint8_t *masked, const uint64_t *off, uint32_t nT, int kmerThr, uint64_t *offsets, uint8_t *entries6, uint64_t *nEntries) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, off, nT, m.seed, kmerThr, idx)) return -1;
+    *nEntries = idx.entries.size();
+    if (offsets) for (size_t k = 0; k <= mb200::KMER_TABLE; k++) offsets[k] = idx.offsets[k];
+    if (entries6) for (size_t i = 0; i < idx.entries.size(); i++) { uint32_t s = (uint32_t)idx.entries[i]; uint16_t p = (uint16_t)(idx.entries[i] >> 32); memcpy(entries6 + 6 * i, &s, 4); memcpy(entries6 + 6 * i + 4, &p, 2); }
+    return 0;
+}
+
+int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
+                  int kmerThr, int maxHits, int minDiag, int binSize, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, unsigned long long *statsOut) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
+    mb200::build_sim3(m.seed, sim3, cnt3, MB_CNT_MIN, MB_CNT_W);
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, toff, nT, m.seed, kmerThr, idx)) return -1;
+    MbPrefTables T; memset(&T, 0, sizeof(T));
+    T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
+    T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
+    T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
+    std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI), hitOff(T.capK + 1), kmerLo(T.capK);
+    std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP), kmerP(T.capK);
+    std::vector<uint64_t> A(T.capM), B(T.capM), C(T.capM); std::vector<int32_t> S(T.capM);
+    MbPrefScratch W; W.itemOff = itemOff.data(); W.wThr = wThr.data(); W.wI0 = wI0.data(); W.wI1 = wI1.data(); W.kmerOff = kmerOff.data();
+    W.itemInfo = itemInfo.data(); W.hitOff = hitOff.data(); W.kmerLo = kmerLo.data(); W.kmerP = kmerP.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
+    MbPrefShared *sh = new MbPrefShared();
+    for (int i = 0; i < 441; i++) sh->ungMat[i] = (int8_t)m.ung[i];
+    MbPrefStats st; memset(&st, 0, sizeof(st));
+    std::vector<float> bias; std::vector<int8_t> corr;
+    for (uint32_t i = 0; i < nQ; i++) {
+        const uint8_t *qs = q + qOff[i]; const uint32_t L = (uint32_t)(qOff[i + 1] - qOff[i]);
+        bias.resize(L + 1); corr.resize(L + 1);
+        for (uint32_t p = 0; p < L; p++) { bias[p] = mb_comp_bias_at(m.seed, m.seedPBack, qs, (int)L, (int)p); corr[p] = mb_round_bias_quarter(bias[p]); }
+        mb_prefilter_query(T, W, sh, qs, bias.data(), corr.data(), L, out + (size_t)i * maxHits, outCount + i, outStatus + i, &st);
+    }
+    delete sh;
+    if (statsOut) { statsOut[0] = st.kmers; statsOut[1] = st.lookups; statsOut[2] = st.dbMatches; statsOut[3] = st.doubleHits; statsOut[4] = st.diagCells; statsOut[5] = st.results; }
+    return 0;
+}
+
+}  // extern "C"
