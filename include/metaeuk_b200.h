@@ -1,0 +1,131 @@
+/* metaeuk_b200.h -- C ABI of libmetaeuk_b200.so: the B200-native predictexons hot path.
+ *
+ * One context per GPU.  Plain pointers and sizes only; every function returns 0 on success or a negative
+ * MB200_E_* code and records a message retrievable with mb200_last_error() (the reference's modules print
+ * via Debug(Debug::ERROR) and EXIT(EXIT_FAILURE); a caller keeps that convention by exiting on != 0).
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference, M/ = lib/mmseqs/):
+ *   mb200_matrices_*     SubstitutionMatrix ctor                M/src/commons/SubstitutionMatrix.cpp:12-57
+ *                        (Prefiltering.cpp:67-70 kmerSubMat/ungappedSubMat, Alignment.cpp:152 m)
+ *   mb200_index_build    IndexBuilder::fillDatabase             M/src/prefiltering/IndexBuilder.cpp:55-239
+ *   mb200_index_import   IndexTable::initTableByExternalData    M/src/prefiltering/IndexTable.h:223-240
+ *   mb200_prefilter      Prefiltering::runSplit query loop      M/src/prefiltering/Prefiltering.cpp:790-870
+ *                        = QueryMatcher::matchQuery per query   M/src/prefiltering/QueryMatcher.cpp:85-211
+ *   mb200_align          Alignment::run hot loop                M/src/alignment/Alignment.cpp:312-405
+ *                        = Matcher::getSWResult per hit         M/src/alignment/Matcher.cpp:60-142
+ *   mb200_chain          collectoptimalset per-contig loop      src/exonpredictor/collectoptimalset.cpp:273-418
+ *   mb200_search         blastp.sh prefilter -> align           M/data/workflow/blastp.sh:70,85
+ *
+ * Residues are the reference's numeric codes (Sequence::mapSequence): A C D E F G H I K L M N P Q R S T V W Y = 0..19, X = 20.
+ * Target ids are LOCAL ids (rank in the target DB as the reference's DBReader enumerates it); dbKeys map them back.
+ * Limits (checked, fail loudly): sequences < 32768 residues, < 2^27 targets, < 2^32 target residues, k = 6 spaced 1101010011.
+ */
+#ifndef METAEUK_B200_H
+#define METAEUK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_OK 0
+#define MB200_E_ARG (-1)
+#define MB200_E_CUDA (-2)
+#define MB200_E_LIMIT (-3)     /* an input exceeds a documented limit */
+#define MB200_E_OVERFLOW (-4)  /* a per-query work list exceeded its configured capacity */
+#define MB200_E_STATE (-5)     /* call order (e.g. prefilter before index) */
+#define MB200_E_INTERNAL (-6)
+
+typedef struct mb200_ctx mb200_ctx;
+
+typedef struct mb200_params {
+    /* prefilter (MetaEuk defaults) */
+    int32_t kmer_thr;          /* 127 = -s 4, k 6 (Prefiltering::getKmerThreshold) */
+    int32_t max_res_list_len;  /* --max-seqs 300 */
+    int32_t min_diag_score;    /* --min-ungapped-score 15 (must be >= 1) */
+    int32_t bin_size;          /* BINSIZE of CacheFriendlyOperations<BINSIZE>, 2 for <= 2.6 M targets (QueryMatcher.cpp:422-450) */
+    /* align */
+    int32_t gap_open, gap_extend;   /* 11, 1 */
+    int32_t min_aln_len;            /* --min-aln-len 11 */
+    int32_t pad0;
+    double eval_thr;                /* -e 100 */
+    /* exon chaining (LocalParameters.h:138-146) */
+    int32_t min_intron, max_intron, min_exon_aa, max_overlap, set_gap_open, set_gap_extend, max_exon_sets, pad1;
+    double tcov, metaeuk_eval;
+    /* capacities of the per-CTA work lists, log2 (0 = default) */
+    int32_t cap_items_log2, cap_kmers_log2, cap_hits_log2, pad2;
+} mb200_params;
+
+typedef struct mb200_hit { uint32_t seq_id; int32_t score; int32_t diag; } mb200_hit;       /* = hit_t written to pref_N */
+typedef struct mb200_aln {                                                                  /* = Matcher::result_t (SCORE_COV mode) */
+    uint32_t seq_id; int32_t raw_score; int32_t bit_score;
+    int32_t q_start, q_end, db_start, db_end, aln_len;
+    int32_t passed;            /* 1 = accepted by Alignment::checkCriteria (e-value, min-aln-len) */
+    float seq_id_est;          /* Matcher::estimateSeqIdByScorePerCol */
+    float q_cov, db_cov;
+    double evalue;
+} mb200_aln;
+typedef struct mb200_cand {   /* one 20-column search_res_by_contig line */
+    uint32_t target_key; int32_t bit_score; int32_t q_start, q_end; int32_t t_start, t_end, t_len; uint32_t orf_key; int32_t frag_from, frag_to;
+} mb200_cand;
+typedef struct mb200_exon { uint32_t cand_idx; int32_t contig_start, contig_end, nuc_len; } mb200_exon;
+typedef struct mb200_call {
+    uint32_t target_key; int32_t strand; int32_t total_bit_score; int32_t n_exons; uint32_t exon_begin; int32_t low_coord, high_coord, pad; double evalue;
+} mb200_call;
+typedef struct mb200_stats {   /* algorithmic work counters of the last prefilter / align call (roofline numerators) */
+    uint64_t kmers, lookups, db_matches, double_hits, diag_cells, pref_results;
+    uint64_t sw_pairs, sw_cells_fwd, sw_cells_rev, sw_target_bytes;
+    uint64_t query_residues, n_queries;
+    double ms_prep, ms_prefilter, ms_sw_fwd, ms_sw_rev, ms_chain, ms_h2d, ms_d2h, ms_host;
+    uint32_t launches, pad;
+} mb200_stats;
+
+int mb200_ctx_create(int device, mb200_ctx **out);
+void mb200_ctx_destroy(mb200_ctx *ctx);
+const char *mb200_last_error(void);
+void mb200_params_default(mb200_params *p);
+int mb200_params_set(mb200_ctx *ctx, const mb200_params *p);
+
+/* matrices: built like the reference builds them, or supplied by a caller that already holds the reference's BaseMatrix objects */
+int mb200_matrices_default(mb200_ctx *ctx);
+int mb200_matrices_set(mb200_ctx *ctx, const int16_t seed21x21[441], const int16_t ungapped21x21[441], const int16_t aln21x21[441],
+                       const double seed_pback[21], const double aln_pback[21]);
+int mb200_matrices_get(mb200_ctx *ctx, int16_t seed21x21[441], int16_t ungapped21x21[441], int16_t aln21x21[441]);
+
+/* target side.  masked = residues after the reference's tantan masking (Masker::maskSequence; masked positions = 20),
+ * unmasked = raw residues (the align stage reads the unmasked target, Alignment.cpp:346-367). off[n_targets+1]. */
+int mb200_index_build(mb200_ctx *ctx, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets);
+int mb200_index_import(mb200_ctx *ctx, const uint64_t *offsets, const uint8_t *entries6, uint64_t n_entries,
+                       const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets);
+/* multi-GPU: rank 0 builds, every rank allocates with mb200_index_alloc (sizes from rank 0), the caller broadcasts the
+ * device buffers listed by mb200_index_buffers (NCCL over NVLink), then each rank calls mb200_index_commit. */
+int mb200_index_sizes(mb200_ctx *ctx, uint64_t sizes[4] /* n_entries, n_targets, total_residues, reserved */);
+int mb200_index_alloc(mb200_ctx *ctx, const uint64_t sizes[4]);
+int mb200_index_buffers(mb200_ctx *ctx, void *dev_ptrs[8], uint64_t nbytes[8], int *n);
+int mb200_index_commit(mb200_ctx *ctx);
+
+/* query side: host buffers in, host buffers out (the call a module makes).  q_off[n_q+1]. */
+int mb200_prefilter(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, mb200_hit *hits /* n_q*max_res_list_len */, uint32_t *hit_count);
+int mb200_align(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, const uint32_t *hit_seq_id, const uint64_t *hit_off,
+                mb200_aln *alns /* hit_off[n_q] */);
+/* prefilter + align in one call: alns[i*max_res_list_len + k] for k < aln_count[i], in prefilter order */
+int mb200_search(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, mb200_aln *alns, uint32_t *aln_count);
+/* exon chaining for a batch of contigs: cands of contig c = cands[cand_off[c]..cand_off[c+1]) sorted by (target_key, orf_key).
+ * calls/exons are caller buffers sized 2*n_cands*max_exon_sets and n_cands*max_exon_sets; call_off/exon ranges are per contig. */
+int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_off, uint32_t n_contigs, uint64_t total_target_residues,
+                mb200_call *calls, uint32_t *call_count /* n_contigs */, mb200_exon *exons);
+
+/* device-resident variant used for kernel-only timing: upload once, run many times, download once */
+int mb200_queries_upload(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q);
+int mb200_prefilter_resident(mb200_ctx *ctx);
+int mb200_align_resident(mb200_ctx *ctx);             /* aligns the resident prefilter result */
+int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count, mb200_aln *alns, uint32_t *aln_count);
+
+int mb200_stats_get(mb200_ctx *ctx, mb200_stats *out);
+double mb200_evalue(mb200_ctx *ctx, int raw_score, int q_len);   /* EvalueComputation::computeEvalue with the ctx's target residues */
+int mb200_bit_score(mb200_ctx *ctx, int raw_score);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

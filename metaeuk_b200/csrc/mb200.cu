@@ -1,0 +1,654 @@
+// mb200.cu -- CUDA kernels (sm_100a) and the C ABI of libmetaeuk_b200.so.  See include/metaeuk_b200.h.
+//
+// Data layout in HBM (per context = per GPU), all resident for the life of the index:
+//   sim3     u32 [8000][8000]   3-mer neighbour lists (index<<16 | score), 256 MB, only row prefixes are touched
+//   cnt3     u16 [8000][384]    "how many neighbours score >= x", 6 MB, L2 resident
+//   offsets  u32 [20^6+1]       k-mer -> first index entry, 256 MB, random 8-byte reads
+//   entries  u32x2 [nEntries]   (target id, position), streamed per list
+//   tseqM/U  u8  [residues]     masked / unmasked target residues, read along diagonals / rows
+// Per-CTA scratch lists (window/item/k-mer/hit expansions) live in global memory but are sized to stay in L2.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/metaeuk_b200.h"
+#include "chain_core.cuh"
+#include "host_tables.h"
+#include "prefilter_core.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf; return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(MB200_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+
+// ---- per-residue preparation (one thread per query residue) ---------------------------------------
+__global__ void __launch_bounds__(256) k_prep(const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, uint32_t nQ, uint64_t total,
+                                              const int16_t *__restrict__ seedMat, const double *__restrict__ seedPBack,
+                                              const int16_t *__restrict__ alnMat, const double *__restrict__ alnPBack,
+                                              float *__restrict__ bias, int8_t *__restrict__ corr, int8_t *__restrict__ cb) {
+    __shared__ int16_t sSeed[441], sAln[441];
+    __shared__ double sPs[21], sPa[21];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) { sSeed[i] = seedMat[i]; sAln[i] = alnMat[i]; }
+    if (threadIdx.x < 21) { sPs[threadIdx.x] = seedPBack[threadIdx.x]; sPa[threadIdx.x] = alnPBack[threadIdx.x]; }
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= total) return;
+    uint32_t lo = 0, hi = nQ;   // qoff[lo] <= r < qoff[hi]
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (qoff[mid] <= r) lo = mid; else hi = mid; }
+    const uint64_t b = qoff[lo]; const int N = (int)(qoff[lo + 1] - b); const int i = (int)(r - b);
+    const float bs = mb_comp_bias_at(sSeed, sPs, qres + b, N, i);
+    bias[r] = bs; corr[r] = mb_round_bias_quarter(bs);
+    cb[r] = mb_round_bias(mb_comp_bias_at(sAln, sPa, qres + b, N, i));
+}
+
+// ---- prefilter: persistent CTAs, one query at a time, dynamic work distribution --------------------
+__global__ void __launch_bounds__(MB_CTA_THREADS) k_prefilter(MbPrefTables T, const MbPrefScratch *__restrict__ scratch, const uint8_t *__restrict__ qres,
+                                                              const uint64_t *__restrict__ qoff, const float *__restrict__ bias, const int8_t *__restrict__ corr,
+                                                              const uint32_t *__restrict__ order, uint32_t nQ, const int8_t *__restrict__ ungMat8,
+                                                              MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats, uint32_t *nextQ) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    MbPrefShared *sh = reinterpret_cast<MbPrefShared *>(smemRaw);
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sh->ungMat[i] = ungMat8[i];
+    const MbPrefScratch W = scratch[blockIdx.x];
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) sh->cs.bcast[0] = atomicAdd(nextQ, 1u);
+        __syncthreads();
+        const uint32_t slot = sh->cs.bcast[0];
+        if (slot >= nQ) break;
+        const uint32_t qi = order[slot];
+        const uint64_t b = qoff[qi]; const uint32_t L = (uint32_t)(qoff[qi + 1] - b);
+        mb_prefilter_query(T, W, sh, qres + b, bias + b, corr + b, L, out + (size_t)qi * T.maxHits, outCount + qi, outStatus + qi, stats);
+        __syncthreads();
+    }
+}
+
+// ---- gapped Smith-Waterman, one alignment per lane -------------------------------------------------
+// Exact affine-gap local alignment (what the reference's striped 8/16-bit kernels compute):
+//   H = max(0, Hdiag + s, E, F);  E' = max(E - ge, H - go);  F' = max(F - ge, H - go)
+// reporting the maximum, the FIRST target column that reaches it and the smallest query row holding it in that
+// column (StripedSmithWaterman.cpp:873-912); a reverse item walks the reversed query prefix / target prefix and stops
+// at the first column whose maximum equals the forward score (:900).
+struct SwItem { uint32_t q; uint32_t t; int32_t qn; int32_t tBegin; int32_t nCols; int32_t terminate; int32_t rev; int32_t pad; };
+struct SwOut { int32_t score, ref, read, pad; };
+
+__global__ void __launch_bounds__(128) k_sw(const SwItem *__restrict__ items, uint32_t nItems, const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff,
+                                            const int8_t *__restrict__ cb, const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff,
+                                            const int16_t *__restrict__ alnMat, int gapO, int gapE, uint32_t *__restrict__ he /* [warp][maxQn][32] */, uint32_t maxQn,
+                                            SwOut *__restrict__ outs, uint32_t *nextWarpItem, unsigned long long *cellCount) {
+    __shared__ int8_t sMat[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t *myHE = he + (size_t)warpGlobal * maxQn * 32u + lane;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(nextWarpItem, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nItems) break;
+        const uint32_t idx = base + lane;
+        const bool active = idx < nItems;
+        SwItem it; it.qn = 0; it.nCols = 0; it.q = 0; it.t = 0; it.tBegin = 0; it.terminate = 0; it.rev = 0;
+        if (active) it = items[idx];
+        const uint8_t *q = qres + qoff[it.q]; const int8_t *c = cb + qoff[it.q];
+        const uint8_t *t = tseq + toff[it.t];
+        const int qn = it.qn; const int qLast = qn - 1;   // reverse items read the query prefix backwards
+        for (int j = 0; j < qn; j++) myHE[(size_t)j * 32u] = 0u;
+        int mx = 0, endDb = -1, endQ = qn - 1;
+        int ti = it.tBegin; const int step = it.rev ? -1 : 1;
+        for (int col = 0; col < it.nCols; col++, ti += step) {
+            const int8_t *row = sMat + t[ti] * MB_AL;
+            int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
+            for (int j = 0; j < qn; j++) {
+                const int qj = it.rev ? (qLast - j) : j;
+                const int s = row[q[qj]] + c[qj];
+                const uint32_t w = myHE[(size_t)j * 32u];
+                const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
+                int f = F - gapE; const int f2 = hUp - gapO; f = f > f2 ? f : f2; f = f < 0 ? 0 : f;
+                int h = hDiag + s; h = h < 0 ? 0 : h; h = h > e ? h : e; h = h > f ? h : f;
+                hDiag = hPrev;
+                int en = e - gapE; const int e2 = h - gapO; en = en > e2 ? en : e2; en = en < 0 ? 0 : en;
+                myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
+                F = f; hUp = h;
+                if (h > cm) { cm = h; jm = j; }
+            }
+            cells += (unsigned long long)qn;
+            if (cm > mx) { mx = cm; endDb = ti; endQ = jm; }
+            if (it.terminate > 0 && cm == it.terminate) break;
+        }
+        if (active) { SwOut o; o.score = mx; o.ref = endDb; o.read = endQ; o.pad = (mx >= 65535) ? 1 : 0; outs[idx] = o; }
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
+// ---- exon chaining: one contig per thread -----------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chain(const MbCand *__restrict__ cands, const uint64_t *__restrict__ candOff, uint32_t nContigs, MbChainParams P,
+                                               MbPE *pe, int32_t *ordPlus, int32_t *ordMinus, MbRow *rows, MbCall *calls, MbExon *exons,
+                                               int32_t *callCount, uint32_t *exonCount) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nContigs) return;
+    const uint64_t b = candOff[c]; const uint32_t n = (uint32_t)(candOff[c + 1] - b);
+    uint32_t nEx = 0;
+    callCount[c] = mb_chain_contig(cands + b, n, P, pe + b, ordPlus + b, ordMinus + b, rows + b, calls + 2 * b, exons + b, &nEx);
+    exonCount[c] = nEx;
+}
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) return fail(MB200_E_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct mb200_ctx {
+    int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
+    mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
+    // tables
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets; DevBuf<uint2> dEntries;
+    DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
+    DevBuf<int16_t> dSeedMat, dAlnMat; DevBuf<double> dSeedPB, dAlnPB; DevBuf<int8_t> dUng8;
+    uint64_t nEntries = 0, totalRes = 0; uint32_t nT = 0; std::vector<uint64_t> hToff; bool haveIndex = false, haveSim3 = false;
+    // prefilter scratch
+    int nCta = 0; DevBuf<MbPrefScratch> dScratch; DevBuf<unsigned char> dScratchMem; uint32_t capP = 0, capI = 0, capK = 0, capM = 0;
+    // resident query batch
+    DevBuf<uint8_t> dQ; DevBuf<uint64_t> dQoff; DevBuf<float> dBias; DevBuf<int8_t> dCorr, dCb; DevBuf<uint32_t> dOrder;
+    std::vector<uint64_t> hQoff; uint32_t nQ = 0; uint64_t totalQ = 0; uint32_t maxQLen = 0;
+    DevBuf<MbPrefHit> dHits; DevBuf<uint32_t> dHitCount, dStatus, dCounter; DevBuf<MbPrefStats> dStats; DevBuf<unsigned long long> dCells;
+    bool havePref = false;
+    // align
+    DevBuf<SwItem> dItems; DevBuf<SwOut> dOuts; DevBuf<uint32_t> dHE; std::vector<int> minScore;   // per query length, -2 = not computed
+    std::vector<mb200_aln> hAlns; std::vector<uint32_t> hAlnCount; std::vector<MbPrefHit> hHits; std::vector<uint32_t> hHitCount;
+    mb200_stats st;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static int upload(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); return 0;
+}
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+static int ctx_upload_matrices(mb200_ctx *c) {
+    TRY(c->dSeedMat.alloc(441)); TRY(c->dAlnMat.alloc(441)); TRY(c->dSeedPB.alloc(21)); TRY(c->dAlnPB.alloc(21)); TRY(c->dUng8.alloc(448));
+    int8_t u8[448]; memset(u8, 0, sizeof(u8)); for (int i = 0; i < 441; i++) u8[i] = (int8_t)c->mat.ung[i];
+    TRY(upload(c->dSeedMat.p, c->mat.seed, 882, c->stream)); TRY(upload(c->dAlnMat.p, c->mat.aln, 882, c->stream));
+    TRY(upload(c->dSeedPB.p, c->mat.seedPBack, 168, c->stream)); TRY(upload(c->dAlnPB.p, c->mat.alnPBack, 168, c->stream)); TRY(upload(c->dUng8.p, u8, 448, c->stream));
+    // similarity tables depend on the seed matrix only
+    std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
+    mb200::build_sim3(c->mat.seed, sim3, cnt3, MB_CNT_MIN, MB_CNT_W);
+    TRY(c->dSim3.alloc(sim3.size())); TRY(c->dCnt3.alloc(cnt3.size()));
+    TRY(upload(c->dSim3.p, sim3.data(), sim3.size() * 4, c->stream)); TRY(upload(c->dCnt3.p, cnt3.data(), cnt3.size() * 2, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->haveMat = true; c->haveSim3 = true;
+    return 0;
+}
+
+static int ctx_alloc_scratch(mb200_ctx *c) {
+    const uint32_t capP = 32768, capI = 1u << (c->par.cap_items_log2 ? c->par.cap_items_log2 : 17), capK = 1u << (c->par.cap_kmers_log2 ? c->par.cap_kmers_log2 : 18),
+                   capM = 1u << (c->par.cap_hits_log2 ? c->par.cap_hits_log2 : 19);
+    if (capM > (1u << MB_MAX_ARRIVAL_BITS)) return fail(MB200_E_ARG, "cap_hits_log2 > %d", MB_MAX_ARRIVAL_BITS);
+    if (c->nCta && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
+    int smemBytes = (int)sizeof(MbPrefShared), perSM = 0;
+    CU(cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter, MB_CTA_THREADS, smemBytes));
+    if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
+    if (perSM > 3) perSM = 3;
+    c->nCta = c->nSM * perSM;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((capK + 1) * 4) + al(capK * 4) + al(capK * 2) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
+    TRY(c->dScratchMem.alloc(per * c->nCta)); TRY(c->dScratch.alloc(c->nCta));
+    std::vector<MbPrefScratch> hs(c->nCta);
+    for (int i = 0; i < c->nCta; i++) {
+        unsigned char *b = c->dScratchMem.p + per * i; MbPrefScratch &W = hs[i];
+        W.itemOff = (uint32_t *)b; b += al((capP + 1) * 4); W.wThr = (int16_t *)b; b += al(capP * 2); W.wI0 = (uint16_t *)b; b += al(capP * 2); W.wI1 = (uint16_t *)b; b += al(capP * 2);
+        W.kmerOff = (uint32_t *)b; b += al((capI + 1) * 4); W.itemInfo = (uint32_t *)b; b += al(capI * 4); W.hitOff = (uint32_t *)b; b += al((capK + 1) * 4);
+        W.kmerLo = (uint32_t *)b; b += al(capK * 4); W.kmerP = (uint16_t *)b; b += al(capK * 2);
+        W.A = (uint64_t *)b; b += al((size_t)capM * 8); W.B = (uint64_t *)b; b += al((size_t)capM * 8); W.C = (uint64_t *)b; b += al((size_t)capM * 8); W.S = (int32_t *)b;
+    }
+    TRY(upload(c->dScratch.p, hs.data(), hs.size() * sizeof(MbPrefScratch), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM;
+    return 0;
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *mb200_last_error(void) { return g_err.c_str(); }
+
+void mb200_params_default(mb200_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->kmer_thr = 127; p->max_res_list_len = 300; p->min_diag_score = 15; p->bin_size = 2;
+    p->gap_open = 11; p->gap_extend = 1; p->min_aln_len = 11; p->eval_thr = 100.0;
+    p->min_intron = 15; p->max_intron = 10000; p->min_exon_aa = 11; p->max_overlap = 10; p->set_gap_open = -1; p->set_gap_extend = -1; p->max_exon_sets = 1;
+    p->tcov = 0.5; p->metaeuk_eval = 0.001;
+}
+
+int mb200_ctx_create(int device, mb200_ctx **out) {
+    if (!out) return fail(MB200_E_ARG, "out == NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(MB200_E_CUDA, "no CUDA device (%s): libmetaeuk_b200 has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(MB200_E_ARG, "device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    mb200_ctx *c = new mb200_ctx();
+    c->device = device;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); c->nSM = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+    mb200_params_default(&c->par); memset(&c->st, 0, sizeof(c->st));
+    *out = c; return 0;
+}
+
+void mb200_ctx_destroy(mb200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
+    c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
+    c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
+    c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dItems.release(); c->dOuts.release(); c->dHE.release();
+    if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mb200_params_set(mb200_ctx *c, const mb200_params *p) {
+    if (!c || !p) return fail(MB200_E_ARG, "null argument");
+    if (p->min_diag_score < 1) return fail(MB200_E_ARG, "min_diag_score must be >= 1");
+    if (p->bin_size < 1 || (p->bin_size & (p->bin_size - 1)) || p->bin_size > 2048) return fail(MB200_E_ARG, "bin_size must be a power of two <= 2048");
+    if (p->max_res_list_len < 1 || p->max_res_list_len > 65535) return fail(MB200_E_ARG, "max_res_list_len out of range");
+    if (p->gap_open != c->par.gap_open || p->gap_extend != c->par.gap_extend || p->eval_thr != c->par.eval_thr) c->minScore.clear();
+    if ((p->gap_open != 11 || p->gap_extend != 1)) return fail(MB200_E_ARG, "only the reference's fixed BLOSUM62 11/1 e-value model is implemented");
+    c->par = *p; return 0;
+}
+
+int mb200_matrices_default(mb200_ctx *c) {
+    if (!c) return fail(MB200_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    mb200::default_matrices(c->mat); return ctx_upload_matrices(c);
+}
+int mb200_matrices_set(mb200_ctx *c, const int16_t *seed, const int16_t *ung, const int16_t *aln, const double *spb, const double *apb) {
+    if (!c || !seed || !ung || !aln || !spb || !apb) return fail(MB200_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    memcpy(c->mat.seed, seed, 882); memcpy(c->mat.ung, ung, 882); memcpy(c->mat.aln, aln, 882); memcpy(c->mat.seedPBack, spb, 168); memcpy(c->mat.alnPBack, apb, 168);
+    return ctx_upload_matrices(c);
+}
+int mb200_matrices_get(mb200_ctx *c, int16_t *seed, int16_t *ung, int16_t *aln) {
+    if (!c || !c->haveMat) return fail(MB200_E_STATE, "matrices not set");
+    memcpy(seed, c->mat.seed, 882); memcpy(ung, c->mat.ung, 882); memcpy(aln, c->mat.aln, 882); return 0;
+}
+
+static int check_targets(const uint64_t *off, uint32_t nT) {
+    if (nT == 0) return fail(MB200_E_ARG, "no targets");
+    if (nT >= (1u << MB_MAX_SEQID_BITS)) return fail(MB200_E_LIMIT, "more than 2^%d targets", MB_MAX_SEQID_BITS);
+    if (off[nT] >= (1ull << 32)) return fail(MB200_E_LIMIT, "more than 2^32 target residues");
+    for (uint32_t t = 0; t < nT; t++) if (off[t + 1] - off[t] >= 32768) return fail(MB200_E_LIMIT, "target %u has >= 32768 residues", t);
+    return 0;
+}
+static int upload_targets(mb200_ctx *c, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT) {
+    const uint64_t tot = off[nT];
+    TRY(c->dTseqM.alloc(tot + 16)); TRY(c->dTseqU.alloc(tot + 16)); TRY(c->dToff.alloc(nT + 1));
+    TRY(upload(c->dTseqM.p, masked, tot, c->stream)); TRY(upload(c->dTseqU.p, unmasked, tot, c->stream)); TRY(upload(c->dToff.p, off, (nT + 1) * 8, c->stream));
+    c->hToff.assign(off, off + nT + 1); c->nT = nT; c->totalRes = tot; c->minScore.clear();
+    return 0;
+}
+static int upload_index(mb200_ctx *c, const mb200::TargetIndex &idx) {
+    TRY(c->dOffsets.alloc(idx.offsets.size())); TRY(c->dEntries.alloc(idx.entries.size()));
+    TRY(upload(c->dOffsets.p, idx.offsets.data(), idx.offsets.size() * 4, c->stream));
+    TRY(upload(c->dEntries.p, idx.entries.data(), idx.entries.size() * 8, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->nEntries = idx.entries.size(); c->haveIndex = true; return 0;
+}
+
+int mb200_index_build(mb200_ctx *c, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT) {
+    if (!c || !masked || !unmasked || !off) return fail(MB200_E_ARG, "null argument");
+    if (!c->haveMat) return fail(MB200_E_STATE, "set the matrices before building the index");
+    CU(cudaSetDevice(c->device));
+    TRY(check_targets(off, nT));
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, off, nT, c->mat.seed, c->par.kmer_thr, idx)) return fail(MB200_E_LIMIT, "index build failed");
+    TRY(upload_targets(c, masked, unmasked, off, nT));
+    return upload_index(c, idx);
+}
+
+int mb200_index_import(mb200_ctx *c, const uint64_t *offsets, const uint8_t *entries6, uint64_t nEntries, const uint8_t *masked, const uint8_t *unmasked,
+                       const uint64_t *off, uint32_t nT) {
+    if (!c || !offsets || !entries6 || !masked || !unmasked || !off) return fail(MB200_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    TRY(check_targets(off, nT));
+    mb200::TargetIndex idx;
+    if (mb200::import_index(offsets, entries6, nEntries, idx)) return fail(MB200_E_LIMIT, "index has >= 2^32 entries");
+    TRY(upload_targets(c, masked, unmasked, off, nT));
+    return upload_index(c, idx);
+}
+
+int mb200_index_sizes(mb200_ctx *c, uint64_t sizes[4]) {
+    if (!c || !c->haveIndex) return fail(MB200_E_STATE, "no index");
+    sizes[0] = c->nEntries; sizes[1] = c->nT; sizes[2] = c->totalRes; sizes[3] = 0; return 0;
+}
+int mb200_index_alloc(mb200_ctx *c, const uint64_t sizes[4]) {
+    if (!c) return fail(MB200_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    c->nEntries = sizes[0]; c->nT = (uint32_t)sizes[1]; c->totalRes = sizes[2];
+    TRY(c->dOffsets.alloc(mb200::KMER_TABLE + 1)); TRY(c->dEntries.alloc(c->nEntries)); TRY(c->dTseqM.alloc(c->totalRes + 16)); TRY(c->dTseqU.alloc(c->totalRes + 16));
+    TRY(c->dToff.alloc(c->nT + 1));
+    return 0;
+}
+int mb200_index_buffers(mb200_ctx *c, void *ptrs[8], uint64_t nbytes[8], int *n) {
+    if (!c || !c->dOffsets.p) return fail(MB200_E_STATE, "index buffers not allocated");
+    ptrs[0] = c->dOffsets.p; nbytes[0] = (mb200::KMER_TABLE + 1) * 4;
+    ptrs[1] = c->dEntries.p; nbytes[1] = c->nEntries * 8;
+    ptrs[2] = c->dTseqM.p; nbytes[2] = c->totalRes;
+    ptrs[3] = c->dTseqU.p; nbytes[3] = c->totalRes;
+    ptrs[4] = c->dToff.p; nbytes[4] = (uint64_t)(c->nT + 1) * 8;
+    *n = 5; return 0;
+}
+int mb200_index_commit(mb200_ctx *c) {
+    if (!c || !c->dToff.p) return fail(MB200_E_STATE, "index buffers not allocated");
+    CU(cudaSetDevice(c->device));
+    c->hToff.resize(c->nT + 1);
+    CU(cudaMemcpy(c->hToff.data(), c->dToff.p, (size_t)(c->nT + 1) * 8, cudaMemcpyDeviceToHost));
+    c->haveIndex = true; c->minScore.clear(); return 0;
+}
+
+// ---- query upload + per-residue preparation ----------------------------------------------------------
+int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ) {
+    if (!c || !q || !qoff) return fail(MB200_E_ARG, "null argument");
+    if (!c->haveMat) return fail(MB200_E_STATE, "matrices not set");
+    CU(cudaSetDevice(c->device));
+    const uint64_t tot = qoff[nQ];
+    uint32_t maxL = 0;
+    for (uint32_t i = 0; i < nQ; i++) { const uint64_t l = qoff[i + 1] - qoff[i]; if (l >= 32768) return fail(MB200_E_LIMIT, "query %u has >= 32768 residues", i); if (l > maxL) maxL = (uint32_t)l; }
+    TRY(c->dQ.alloc(tot + 16)); TRY(c->dQoff.alloc(nQ + 1)); TRY(c->dBias.alloc(tot + 16)); TRY(c->dCorr.alloc(tot + 16)); TRY(c->dCb.alloc(tot + 16)); TRY(c->dOrder.alloc(nQ + 1));
+    // longest queries first: the persistent prefilter CTAs pull work from this order
+    std::vector<uint32_t> order(nQ);
+    for (uint32_t i = 0; i < nQ; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (qoff[a + 1] - qoff[a]) > (qoff[b + 1] - qoff[b]); });
+    CU(cudaEventRecord(c->ev0, c->stream));
+    TRY(upload(c->dQ.p, q, tot, c->stream)); TRY(upload(c->dQoff.p, qoff, (size_t)(nQ + 1) * 8, c->stream)); TRY(upload(c->dOrder.p, order.data(), (size_t)nQ * 4, c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_h2d = ms;
+    c->hQoff.assign(qoff, qoff + nQ + 1); c->nQ = nQ; c->totalQ = tot; c->maxQLen = maxL; c->havePref = false;
+    if (tot) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_prep<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->dQ.p, c->dQoff.p, nQ, tot, c->dSeedMat.p, c->dSeedPB.p, c->dAlnMat.p, c->dAlnPB.p, c->dBias.p, c->dCorr.p, c->dCb.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prep = ms; c->st.launches++;
+    }
+    c->st.query_residues = tot; c->st.n_queries = nQ;
+    return 0;
+}
+
+int mb200_prefilter_resident(mb200_ctx *c) {
+    if (!c) return fail(MB200_E_ARG, "null ctx");
+    if (!c->haveIndex || !c->haveSim3) return fail(MB200_E_STATE, "index / matrices not set");
+    CU(cudaSetDevice(c->device));
+    TRY(ctx_alloc_scratch(c));
+    const uint32_t nQ = c->nQ; const uint32_t maxHits = (uint32_t)c->par.max_res_list_len;
+    TRY(c->dHits.alloc((size_t)nQ * maxHits)); TRY(c->dHitCount.alloc(nQ + 1)); TRY(c->dStatus.alloc(nQ + 1)); TRY(c->dCounter.alloc(4)); TRY(c->dStats.alloc(1));
+    CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream)); CU(cudaMemsetAsync(c->dStats.p, 0, sizeof(MbPrefStats), c->stream));
+    CU(cudaMemsetAsync(c->dHitCount.p, 0, (size_t)(nQ + 1) * 4, c->stream)); CU(cudaMemsetAsync(c->dStatus.p, 0xFF, (size_t)(nQ + 1) * 4, c->stream));
+    MbPrefTables T; memset(&T, 0, sizeof(T));
+    T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
+    T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
+    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM;
+    if (nQ) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_prefilter<<<c->nCta, MB_CTA_THREADS, sizeof(MbPrefShared), c->stream>>>(T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p,
+                                                                                c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prefilter = ms; c->st.launches++;
+    }
+    // status check: any query that could not be processed is an error, never a silent drop
+    std::vector<uint32_t> status(nQ + 1);
+    CU(cudaMemcpy(status.data(), c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK)
+        return fail(status[i] == MB_ST_OVERFLOW ? MB200_E_OVERFLOW : MB200_E_LIMIT, "query %u: prefilter status %u (work list capacity exceeded or sequence too long)", i, status[i]);
+    MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    c->st.kmers = hs.kmers; c->st.lookups = hs.lookups; c->st.db_matches = hs.dbMatches; c->st.double_hits = hs.doubleHits; c->st.diag_cells = hs.diagCells; c->st.pref_results = hs.results;
+    c->havePref = true;
+    return 0;
+}
+
+// run a batch of SW items on the device; outs returned on the host
+static int run_sw(mb200_ctx *c, const std::vector<SwItem> &items, std::vector<SwOut> &outs, uint32_t maxQn, float *msOut, uint64_t *cellsOut) {
+    outs.resize(items.size());
+    *msOut = 0; *cellsOut = 0;
+    if (items.empty()) return 0;
+    const int warpsPerBlock = 4; const int blocks = c->nSM * 8;
+    const size_t nWarps = (size_t)blocks * warpsPerBlock;
+    if (maxQn == 0) maxQn = 1;
+    TRY(c->dItems.alloc(items.size())); TRY(c->dOuts.alloc(items.size())); TRY(c->dHE.alloc(nWarps * maxQn * 32)); TRY(c->dCounter.alloc(4)); TRY(c->dCells.alloc(1));
+    TRY(upload(c->dItems.p, items.data(), items.size() * sizeof(SwItem), c->stream));
+    CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 8, c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    k_sw<<<blocks, warpsPerBlock * 32, 0, c->stream>>>(c->dItems.p, (uint32_t)items.size(), c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                                                        c->par.gap_open, c->par.gap_extend, c->dHE.p, maxQn, c->dOuts.p, c->dCounter.p, c->dCells.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaMemcpyAsync(outs.data(), c->dOuts.p, items.size() * sizeof(SwOut), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long cells = 0;
+    CU(cudaMemcpyAsync(&cells, c->dCells.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(msOut, c->ev0, c->ev1)); *cellsOut = cells; c->st.launches++;
+    return 0;
+}
+
+static int min_score_for(mb200_ctx *c, uint32_t L) {
+    if (c->minScore.size() < 32769) c->minScore.assign(32769, -2);
+    if (c->minScore[L] == -2) c->minScore[L] = c->ev.minScoreFor(c->par.eval_thr, (double)L, (double)c->totalRes);
+    return c->minScore[L];
+}
+
+// align the lists hitSeq[hitOff[i]..hitOff[i+1]) of every resident query; alns has the same layout
+static int align_lists(mb200_ctx *c, const uint32_t *hitSeq, const uint64_t *hitOff, mb200_aln *alns) {
+    const uint32_t nQ = c->nQ;
+    const uint64_t nPairs = hitOff[nQ];
+    c->st.sw_pairs = nPairs; c->st.sw_cells_fwd = c->st.sw_cells_rev = 0; c->st.ms_sw_fwd = c->st.ms_sw_rev = 0; c->st.sw_target_bytes = 0;
+    if (nPairs == 0) return 0;
+    if (nPairs >= (1ull << 32)) return fail(MB200_E_LIMIT, "too many alignments in one call");
+    std::vector<SwItem> items(nPairs);
+    uint64_t tbytes = 0;
+    for (uint32_t i = 0; i < nQ; i++) {
+        const int L = (int)(c->hQoff[i + 1] - c->hQoff[i]);
+        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
+            const uint32_t t = hitSeq[k];
+            if (t >= c->nT) return fail(MB200_E_ARG, "hit target id %u out of range", t);
+            SwItem &it = items[k]; it.q = i; it.t = t; it.qn = L; it.tBegin = 0; it.nCols = (int)(c->hToff[t + 1] - c->hToff[t]); it.terminate = 0; it.rev = 0; it.pad = 0;
+            tbytes += (uint64_t)it.nCols;
+        }
+    }
+    std::vector<SwOut> fwd; float ms; uint64_t cells;
+    TRY(run_sw(c, items, fwd, c->maxQLen, &ms, &cells));
+    c->st.ms_sw_fwd = ms; c->st.sw_cells_fwd = cells; c->st.sw_target_bytes = tbytes;
+    // gate on the e-value (StripedSmithWaterman.cpp:389-398): only alignments that can pass -e get start coordinates
+    std::vector<SwItem> ritems; std::vector<uint64_t> rmap;
+    uint32_t maxRn = 0;
+    for (uint32_t i = 0; i < nQ; i++) {
+        if (hitOff[i + 1] == hitOff[i]) continue;
+        const uint32_t L = (uint32_t)(c->hQoff[i + 1] - c->hQoff[i]);
+        const int ms0 = min_score_for(c, L);
+        if (ms0 < 0) return fail(MB200_E_INTERNAL, "e-value not monotone in the score for query length %u", L);
+        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
+            const SwOut &f = fwd[k]; mb200_aln &a = alns[k];
+            if (f.pad) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
+            memset(&a, 0, sizeof(a));
+            a.seq_id = hitSeq[k]; a.raw_score = f.score; a.q_end = f.read; a.db_end = f.ref; a.q_start = -1; a.db_start = -1; a.passed = 0;
+            if (f.ref < 0) continue;
+            if (f.score >= ms0) {
+                SwItem it; it.q = i; it.t = hitSeq[k]; it.qn = f.read + 1; it.tBegin = f.ref; it.nCols = f.ref + 1; it.terminate = f.score; it.rev = 1; it.pad = 0;
+                ritems.push_back(it); rmap.push_back(k); if ((uint32_t)it.qn > maxRn) maxRn = (uint32_t)it.qn;
+            }
+        }
+    }
+    std::vector<SwOut> rev;
+    TRY(run_sw(c, ritems, rev, maxRn, &ms, &cells));
+    c->st.ms_sw_rev = ms; c->st.sw_cells_rev = cells;
+    for (size_t r = 0; r < ritems.size(); r++) {
+        mb200_aln &a = alns[rmap[r]];
+        if (rev[r].score != a.raw_score) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (%d vs %d)", a.raw_score, rev[r].score);
+        a.db_start = rev[r].ref; a.q_start = a.q_end - rev[r].read;
+    }
+    // host epilogue: e-value, bit score, coverage, estimated identity, acceptance (Matcher.cpp:100-142, Alignment.cpp:548-567)
+#pragma omp parallel for schedule(dynamic, 64)
+    for (uint32_t i = 0; i < nQ; i++) {
+        const uint32_t L = (uint32_t)(c->hQoff[i + 1] - c->hQoff[i]);
+        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
+            mb200_aln &a = alns[k];
+            if (a.db_end < 0) { a.q_end = (int)L - 1; continue; }
+            a.evalue = c->ev.evalue(a.raw_score, L, (double)c->totalRes);
+            a.bit_score = c->ev.bitScore(a.raw_score);
+            if (a.db_start < 0) continue;
+            const uint32_t tLen = (uint32_t)(c->hToff[a.seq_id + 1] - c->hToff[a.seq_id]);
+            a.q_cov = (std::min(L, (uint32_t)std::max(a.q_start, a.q_end)) - (uint32_t)std::min(a.q_start, a.q_end) + 1) / (float)L;
+            a.db_cov = (std::min(tLen, (uint32_t)std::max(a.db_start, a.db_end)) - (uint32_t)std::min(a.db_start, a.db_end) + 1) / (float)tLen;
+            a.aln_len = std::max(abs(a.q_end - a.q_start), abs(a.db_end - a.db_start)) + 1;
+            const unsigned qa = std::max((unsigned)(a.q_end - a.q_start), 1u), ta = std::max((unsigned)(a.db_end - a.db_start), 1u);
+            float sid = ((uint16_t)a.raw_score / static_cast<float>(std::max(qa, ta))) * 0.1656 + 0.1141;
+            sid = std::min(sid, 1.0f); a.seq_id_est = std::max(0.0f, sid);
+            a.passed = (a.evalue <= c->par.eval_thr && a.aln_len >= c->par.min_aln_len) ? 1 : 0;
+        }
+    }
+    return 0;
+}
+
+int mb200_align_resident(mb200_ctx *c) {
+    if (!c || !c->havePref) return fail(MB200_E_STATE, "no resident prefilter result");
+    CU(cudaSetDevice(c->device));
+    const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
+    c->hHits.resize((size_t)nQ * maxHits); c->hHitCount.resize(nQ);
+    CU(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaMemcpyAsync(c->hHits.data(), c->dHits.p, (size_t)nQ * maxHits * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->hHitCount.data(), c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_d2h = ms;
+    std::vector<uint64_t> off(nQ + 1, 0);
+    for (uint32_t i = 0; i < nQ; i++) off[i + 1] = off[i] + c->hHitCount[i];
+    std::vector<uint32_t> seq(off[nQ] ? off[nQ] : 1);
+    for (uint32_t i = 0; i < nQ; i++) for (uint32_t k = 0; k < c->hHitCount[i]; k++) seq[off[i] + k] = c->hHits[(size_t)i * maxHits + k].seqId;
+    std::vector<mb200_aln> flat(off[nQ] ? off[nQ] : 1);
+    TRY(align_lists(c, seq.data(), off.data(), flat.data()));
+    c->hAlns.assign((size_t)nQ * maxHits, mb200_aln()); c->hAlnCount.assign(nQ, 0);
+    for (uint32_t i = 0; i < nQ; i++) { c->hAlnCount[i] = c->hHitCount[i]; for (uint32_t k = 0; k < c->hHitCount[i]; k++) c->hAlns[(size_t)i * maxHits + k] = flat[off[i] + k]; }
+    return 0;
+}
+
+int mb200_results_download(mb200_ctx *c, mb200_hit *hits, uint32_t *hitCount, mb200_aln *alns, uint32_t *alnCount) {
+    if (!c || !c->havePref) return fail(MB200_E_STATE, "no resident result");
+    CU(cudaSetDevice(c->device));
+    const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
+    if (hits && hitCount) {
+        CU(cudaMemcpy(hits, c->dHits.p, (size_t)nQ * maxHits * sizeof(MbPrefHit), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hitCount, c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost));
+    }
+    if (alns && alnCount) {
+        if (c->hAlnCount.size() != nQ) return fail(MB200_E_STATE, "no resident alignment result");
+        memcpy(alns, c->hAlns.data(), c->hAlns.size() * sizeof(mb200_aln)); memcpy(alnCount, c->hAlnCount.data(), (size_t)nQ * 4);
+    }
+    return 0;
+}
+
+int mb200_prefilter(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, mb200_hit *hits, uint32_t *hitCount) {
+    if (!hits || !hitCount) return fail(MB200_E_ARG, "null output");
+    TRY(mb200_queries_upload(c, q, qoff, nQ));
+    TRY(mb200_prefilter_resident(c));
+    return mb200_results_download(c, hits, hitCount, nullptr, nullptr);
+}
+
+int mb200_align(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, const uint32_t *hitSeq, const uint64_t *hitOff, mb200_aln *alns) {
+    if (!hitSeq || !hitOff || !alns) return fail(MB200_E_ARG, "null argument");
+    if (!c || !c->haveIndex) return fail(MB200_E_STATE, "index not set");
+    TRY(mb200_queries_upload(c, q, qoff, nQ));
+    return align_lists(c, hitSeq, hitOff, alns);
+}
+
+int mb200_search(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, mb200_aln *alns, uint32_t *alnCount) {
+    if (!alns || !alnCount) return fail(MB200_E_ARG, "null output");
+    TRY(mb200_queries_upload(c, q, qoff, nQ));
+    TRY(mb200_prefilter_resident(c));
+    TRY(mb200_align_resident(c));
+    return mb200_results_download(c, nullptr, nullptr, alns, alnCount);
+}
+
+int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, uint32_t nContigs, uint64_t totalTargetResidues, mb200_call *calls,
+                uint32_t *callCount, mb200_exon *exons) {
+    if (!c || !cands || !candOff || !calls || !callCount || !exons) return fail(MB200_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = candOff[nContigs];
+    for (uint32_t i = 0; i < nContigs; i++) callCount[i] = 0;
+    if (n == 0) return 0;
+    DevBuf<MbCand> dC; DevBuf<uint64_t> dOff; DevBuf<MbPE> dPE; DevBuf<int32_t> dOp, dOm, dCallCnt; DevBuf<MbRow> dRows; DevBuf<MbCall> dCalls; DevBuf<MbExon> dEx; DevBuf<uint32_t> dExCnt;
+    int rc = 0;
+    do {
+        if ((rc = dC.alloc(n)) || (rc = dOff.alloc(nContigs + 1)) || (rc = dPE.alloc(n)) || (rc = dOp.alloc(n)) || (rc = dOm.alloc(n)) || (rc = dRows.alloc(n)) ||
+            (rc = dCalls.alloc(2 * n)) || (rc = dEx.alloc(n)) || (rc = dCallCnt.alloc(nContigs)) || (rc = dExCnt.alloc(nContigs))) break;
+        static_assert(sizeof(MbCand) == sizeof(mb200_cand) && sizeof(MbCall) == sizeof(mb200_call) && sizeof(MbExon) == sizeof(mb200_exon), "ABI structs");
+        if ((rc = upload(dC.p, cands, n * sizeof(MbCand), c->stream)) || (rc = upload(dOff.p, candOff, (size_t)(nContigs + 1) * 8, c->stream))) break;
+        MbChainParams P; P.minIntron = c->par.min_intron; P.maxIntron = c->par.max_intron; P.minExonAa = c->par.min_exon_aa; P.maxOverlap = c->par.max_overlap;
+        P.gapOpen = c->par.set_gap_open; P.gapExtend = c->par.set_gap_extend; P.maxSets = c->par.max_exon_sets; P.tcov = c->par.tcov;
+        cudaEventRecord(c->ev0, c->stream);
+        k_chain<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(dC.p, dOff.p, nContigs, P, dPE.p, dOp.p, dOm.p, dRows.p, dCalls.p, dEx.p, dCallCnt.p, dExCnt.p);
+        cudaEventRecord(c->ev1, c->stream);
+        std::vector<MbCall> hCalls(2 * n); std::vector<MbExon> hEx(n); std::vector<int32_t> hCnt(nContigs);
+        cudaMemcpyAsync(hCalls.data(), dCalls.p, 2 * n * sizeof(MbCall), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hEx.data(), dEx.p, n * sizeof(MbExon), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hCnt.data(), dCallCnt.p, (size_t)nContigs * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(MB200_E_CUDA, "chain kernel: %s", cudaGetErrorString(e)); break; }
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->st.ms_chain = ms; c->st.launches++;
+        // host epilogue: set e-value and --metaeuk-eval filter (collectoptimalset.cpp:323-330); compact per contig
+        for (uint32_t ci = 0; ci < nContigs; ci++) {
+            if (hCnt[ci] < 0) { rc = fail(MB200_E_ARG, "contig %u: illegal codon segment length", ci); break; }
+            const uint64_t b = candOff[ci]; uint32_t w = 0, we = 0;
+            for (int k = 0; k < hCnt[ci]; k++) {
+                MbCall cl = hCalls[2 * b + k];
+                const double l2 = log2(totalTargetResidues) + log2(2) - cl.totalBitScore; const double ev = pow(2, l2);
+                if (!(ev <= c->par.metaeuk_eval)) continue;
+                const uint32_t eb = cl.exonBegin;
+                cl.evalue = ev; cl.exonBegin = (uint32_t)(b + we);
+                for (int x = 0; x < cl.nExons; x++) { MbExon ex = hEx[b + eb + x]; memcpy(&exons[b + we + x], &ex, sizeof(ex)); }
+                we += cl.nExons;
+                memcpy(&calls[2 * b + w], &cl, sizeof(cl)); w++;
+            }
+            callCount[ci] = w;
+        }
+    } while (0);
+    dC.release(); dOff.release(); dPE.release(); dOp.release(); dOm.release(); dRows.release(); dCalls.release(); dEx.release(); dCallCnt.release(); dExCnt.release();
+    return rc;
+}
+
+int mb200_stats_get(mb200_ctx *c, mb200_stats *out) { if (!c || !out) return fail(MB200_E_ARG, "null argument"); *out = c->st; return 0; }
+double mb200_evalue(mb200_ctx *c, int rawScore, int qLen) { return c->ev.evalue(rawScore, qLen, (double)c->totalRes); }
+int mb200_bit_score(mb200_ctx *c, int rawScore) { return c->ev.bitScore(rawScore); }
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""ctypes binding of libmetaeuk_b200.so (C ABI: include/metaeuk_b200.h) and the build recipe for it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_PATH = os.path.join(PKG, "libmetaeuk_b200.so")
+CSRC = os.path.join(PKG, "csrc")
+
+HIT_DTYPE = np.dtype([("seq_id", "<u4"), ("score", "<i4"), ("diag", "<i4")])
+ALN_DTYPE = np.dtype([("seq_id", "<u4"), ("raw_score", "<i4"), ("bit_score", "<i4"), ("q_start", "<i4"), ("q_end", "<i4"), ("db_start", "<i4"),
+                      ("db_end", "<i4"), ("aln_len", "<i4"), ("passed", "<i4"), ("seq_id_est", "<f4"), ("q_cov", "<f4"), ("db_cov", "<f4"),
+                      ("evalue", "<f8")], align=True)
+CAND_DTYPE = np.dtype([("target_key", "<u4"), ("bit_score", "<i4"), ("q_start", "<i4"), ("q_end", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
+                       ("t_len", "<i4"), ("orf_key", "<u4"), ("frag_from", "<i4"), ("frag_to", "<i4")])
+EXON_DTYPE = np.dtype([("cand_idx", "<u4"), ("contig_start", "<i4"), ("contig_end", "<i4"), ("nuc_len", "<i4")])
+CALL_DTYPE = np.dtype([("target_key", "<u4"), ("strand", "<i4"), ("total_bit_score", "<i4"), ("n_exons", "<i4"), ("exon_begin", "<u4"),
+                       ("low_coord", "<i4"), ("high_coord", "<i4"), ("pad", "<i4"), ("evalue", "<f8")], align=True)
+
+
+class Params(C.Structure):
+    _fields_ = [("kmer_thr", C.c_int32), ("max_res_list_len", C.c_int32), ("min_diag_score", C.c_int32), ("bin_size", C.c_int32),
+                ("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("min_aln_len", C.c_int32), ("pad0", C.c_int32), ("eval_thr", C.c_double),
+                ("min_intron", C.c_int32), ("max_intron", C.c_int32), ("min_exon_aa", C.c_int32), ("max_overlap", C.c_int32),
+                ("set_gap_open", C.c_int32), ("set_gap_extend", C.c_int32), ("max_exon_sets", C.c_int32), ("pad1", C.c_int32),
+                ("tcov", C.c_double), ("metaeuk_eval", C.c_double),
+                ("cap_items_log2", C.c_int32), ("cap_kmers_log2", C.c_int32), ("cap_hits_log2", C.c_int32), ("pad2", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("kmers", "lookups", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd",
+                                           "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
+               [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
+               [("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class Mb200Error(RuntimeError):
+    pass
+
+
+def _gxx():
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
+    srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
+        [os.path.join(ROOT, "include", "metaeuk_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc", "-ccbin", _gxx(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-shared"] + srcs + ["-o", LIB_PATH, "-lgomp"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Load the in-tree library; fail loudly if it is missing (there is no CPU path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Mb200Error("libmetaeuk_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                             "metaeuk_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.mb200_last_error.restype = C.c_char_p
+        L.mb200_evalue.restype = C.c_double
+        L.mb200_evalue.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.mb200_bit_score.argtypes = [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+def pack_codes(seqs):
+    """list of uint8 code arrays -> (concatenated, uint64 offsets)"""
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    data = np.concatenate(seqs).astype(np.uint8, copy=False) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+class Context:
+    """One GPU context (mb200_ctx).  All inputs are numeric residue codes (see metaeuk_b200.modules.encode)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        self._check(self.L.mb200_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.params = Params()
+        self.L.mb200_params_default(C.byref(self.params))
+        self.n_targets = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Mb200Error("mb200 error %d: %s" % (rc, self.L.mb200_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise KeyError(k)
+            setattr(self.params, k, v)
+        self._check(self.L.mb200_params_set(self.h, C.byref(self.params)))
+
+    def matrices_default(self):
+        self._check(self.L.mb200_matrices_default(self.h))
+
+    def matrices_get(self):
+        s = np.zeros(441, np.int16); u = np.zeros(441, np.int16); a = np.zeros(441, np.int16)
+        self._check(self.L.mb200_matrices_get(self.h, _p(s), _p(u), _p(a)))
+        return s, u, a
+
+    def index_build(self, masked, unmasked, off):
+        """masked/unmasked: concatenated uint8 codes, off: uint64[n+1]"""
+        masked = np.ascontiguousarray(masked, np.uint8); unmasked = np.ascontiguousarray(unmasked, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+        self.n_targets = len(off) - 1
+        self.target_off = off
+        self._check(self.L.mb200_index_build(self.h, _p(masked), _p(unmasked), _p(off), C.c_uint32(self.n_targets)))
+
+    def index_import(self, offsets_u64, entries6, masked, unmasked, off):
+        offsets_u64 = np.ascontiguousarray(offsets_u64, np.uint64); entries6 = np.ascontiguousarray(entries6, np.uint8)
+        masked = np.ascontiguousarray(masked, np.uint8); unmasked = np.ascontiguousarray(unmasked, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+        self.n_targets = len(off) - 1
+        self.target_off = off
+        self._check(self.L.mb200_index_import(self.h, _p(offsets_u64), _p(entries6), C.c_uint64(len(entries6) // 6), _p(masked), _p(unmasked), _p(off),
+                                              C.c_uint32(self.n_targets)))
+
+    # ---- multi-GPU replication helpers (see bench.py: one NCCL broadcast of these buffers) ----
+    def index_sizes(self):
+        s = (C.c_uint64 * 4)()
+        self._check(self.L.mb200_index_sizes(self.h, s))
+        return [int(x) for x in s]
+
+    def index_alloc(self, sizes):
+        s = (C.c_uint64 * 4)(*sizes)
+        self._check(self.L.mb200_index_alloc(self.h, s))
+        self.n_targets = int(sizes[1])
+
+    def index_buffers(self):
+        ptrs = (C.c_void_p * 8)(); nb = (C.c_uint64 * 8)(); n = C.c_int(0)
+        self._check(self.L.mb200_index_buffers(self.h, ptrs, nb, C.byref(n)))
+        return [(int(ptrs[i] or 0), int(nb[i])) for i in range(n.value)]
+
+    def index_commit(self):
+        self._check(self.L.mb200_index_commit(self.h))
+
+    # ---- host-buffer API ----
+    def prefilter(self, q, qoff):
+        q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
+        n = len(qoff) - 1
+        m = self.params.max_res_list_len
+        hits = np.zeros((n, m), dtype=HIT_DTYPE); cnt = np.zeros(n, np.uint32)
+        self._check(self.L.mb200_prefilter(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(hits), _p(cnt)))
+        return hits, cnt
+
+    def align(self, q, qoff, hit_seq, hit_off):
+        q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
+        hit_seq = np.ascontiguousarray(hit_seq, np.uint32); hit_off = np.ascontiguousarray(hit_off, np.uint64)
+        n = len(qoff) - 1
+        alns = np.zeros(max(1, int(hit_off[-1])), dtype=ALN_DTYPE)
+        if len(hit_seq) == 0:
+            hit_seq = np.zeros(1, np.uint32)
+        self._check(self.L.mb200_align(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(hit_seq), _p(hit_off), _p(alns)))
+        return alns[:int(hit_off[-1])]
+
+    def search(self, q, qoff):
+        q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
+        n = len(qoff) - 1
+        m = self.params.max_res_list_len
+        alns = np.zeros((n, m), dtype=ALN_DTYPE); cnt = np.zeros(n, np.uint32)
+        self._check(self.L.mb200_search(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(alns), _p(cnt)))
+        return alns, cnt
+
+    def chain(self, cands, cand_off, total_target_residues):
+        cands = np.ascontiguousarray(cands, CAND_DTYPE); cand_off = np.ascontiguousarray(cand_off, np.uint64)
+        nc = len(cand_off) - 1
+        n = int(cand_off[-1])
+        calls = np.zeros(max(1, 2 * n), dtype=CALL_DTYPE); exons = np.zeros(max(1, n), dtype=EXON_DTYPE); cnt = np.zeros(max(1, nc), np.uint32)
+        self._check(self.L.mb200_chain(self.h, _p(cands), _p(cand_off), C.c_uint32(nc), C.c_uint64(total_target_residues), _p(calls), _p(cnt), _p(exons)))
+        return calls, cnt[:nc], exons
+
+    # ---- device-resident API (kernel-only timing) ----
+    def queries_upload(self, q, qoff):
+        q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
+        self._nq = len(qoff) - 1
+        self._check(self.L.mb200_queries_upload(self.h, _p(q), _p(qoff), C.c_uint32(self._nq)))
+
+    def prefilter_resident(self):
+        self._check(self.L.mb200_prefilter_resident(self.h))
+
+    def align_resident(self):
+        self._check(self.L.mb200_align_resident(self.h))
+
+    def results_download(self, want_alns=False):
+        n = self._nq; m = self.params.max_res_list_len
+        hits = np.zeros((n, m), dtype=HIT_DTYPE); cnt = np.zeros(n, np.uint32)
+        if want_alns:
+            alns = np.zeros((n, m), dtype=ALN_DTYPE); acnt = np.zeros(n, np.uint32)
+            self._check(self.L.mb200_results_download(self.h, _p(hits), _p(cnt), _p(alns), _p(acnt)))
+            return hits, cnt, alns, acnt
+        self._check(self.L.mb200_results_download(self.h, _p(hits), _p(cnt), None, None))
+        return hits, cnt
+
+    def stats(self):
+        s = Stats()
+        self._check(self.L.mb200_stats_get(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_ if not k.startswith("pad")}

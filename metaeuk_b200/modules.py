@@ -1,0 +1,193 @@
+"""Host-side mirror of the reference's module surface for the hot path, on in-memory DBs.
+
+Each function corresponds to one reference module (same inputs, same result-DB records, byte for byte):
+  prefilter          reference/lib/mmseqs/src/prefiltering/Main.cpp:13     -> pref DB      "tKey\\tscore\\tdiag"
+  align              reference/lib/mmseqs/src/alignment/Main.cpp:12        -> alignment DB 10 columns
+  resultspercontig   reference/src/exonpredictor/resultspercontig.cpp:34   -> 20 columns per contig
+  collectoptimalset  reference/src/exonpredictor/collectoptimalset.cpp:224 -> 19 columns per exon
+  predictexons       reference/data/predictexons.sh:42-87 (search -> resultspercontig -> collectoptimalset)
+A "DB" here is {key: entry-text}; sequence DBs are lists of (key, sequence) in the reference's local-id order.
+All arithmetic on scores/coordinates happens in libmetaeuk_b200 (GPU); this file only converts letters to codes,
+orders records and prints them with the reference's formatting rules."""
+import numpy as np
+
+from .lib import CAND_DTYPE, Context, pack_codes
+
+_ORDER = "ACDEFGHIKLMNPQRSTVWYX"
+AA2NUM = np.full(256, 20, dtype=np.uint8)   # SubstitutionMatrix::setupLetterMapping (SubstitutionMatrix.cpp:262-304)
+for _i, _c in enumerate(_ORDER):
+    AA2NUM[ord(_c)] = _i
+    AA2NUM[ord(_c.lower())] = _i
+for _a, _b in (("J", "L"), ("Z", "E"), ("B", "D")):
+    AA2NUM[ord(_a)] = AA2NUM[ord(_b)]
+    AA2NUM[ord(_a.lower())] = AA2NUM[ord(_b)]
+
+
+def encode(seq):
+    return AA2NUM[np.frombuffer(seq.encode(), dtype=np.uint8)]
+
+
+def encode_many(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    data = encode("".join(seqs)) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+class TargetDB:
+    """Target protein DB in local-id order.  `masked` = sequences after the reference's tantan masking (X at masked
+    positions); pass None for --mask 0 semantics.  Masking itself is host preprocessing outside the hot path."""
+
+    def __init__(self, entries, masked=None):
+        self.keys = [k for k, _ in entries]
+        self.seqs = [s for _, s in entries]
+        self.masked = list(masked) if masked is not None else self.seqs
+        self.lens = [len(s) for s in self.seqs]
+        self.total_residues = sum(self.lens)
+
+    def upload(self, ctx):
+        u, off = encode_many(self.seqs)
+        m, off2 = encode_many(self.masked)
+        assert (off == off2).all()
+        ctx.index_build(m, u, off)
+
+
+def make_context(tdb, device=0, **params):
+    ctx = Context(device)
+    if params:
+        ctx.set_params(**params)
+    ctx.matrices_default()
+    tdb.upload(ctx)
+    return ctx
+
+
+# ---- formatting (the reference's own rules) -----------------------------------------------------
+def fmt_seqid(x):
+    """Util::fastSeqIdToBuffer + Matcher::resultToBuffer's tab overwrite: 1.0 -> '1.00' (Util.cpp:222-251, Matcher.cpp:286-287)"""
+    x = np.float32(x)
+    if x == np.float32(1.0):
+        return "1.00"
+    s = "0."
+    if x < 0.10:
+        s += "0"
+    if x < 0.01:
+        s += "0"
+    return s + str(int(np.float32(x * np.float32(1000))))
+
+
+def fmt_exon_seqid(text):
+    """PotentialExon::exonToBuffer after strtod -> float (PredictionParser.h:21,106-136)"""
+    f = np.float32(float(text))
+    if f == np.float32(1.0):
+        return "1.000"
+    s = "0."
+    if f < 0.10:
+        s += "0"
+    if f < 0.01:
+        s += "0"
+    return s + str(int(np.float32(f * np.float32(1000))))
+
+
+def prefilter(ctx, queries, tdb):
+    """queries: list of (key, seq) -> {key: pref entry}  (QueryMatcher::prefilterHitToBuffer, QueryMatcher.h:118-130)"""
+    q, qoff = encode_many([s for _, s in queries])
+    hits, cnt = ctx.prefilter(q, qoff)
+    out = {}
+    for i, (k, _) in enumerate(queries):
+        out[k] = "".join("%d\t%d\t%d\n" % (tdb.keys[h["seq_id"]], h["score"], h["diag"]) for h in hits[i, :cnt[i]])
+    return out
+
+
+def _aln_lines(alns, tdb, qlen):
+    """accepted records sorted by Matcher::compareHits (Matcher.h:157-168), printed by Matcher::resultToBuffer (Matcher.cpp:280-327)"""
+    rows = [a for a in alns if a["passed"] == 1]
+    rows.sort(key=lambda a: (a["evalue"], -int(a["bit_score"]), tdb.lens[a["seq_id"]], tdb.keys[a["seq_id"]]))
+    return "".join("%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\n" % (tdb.keys[a["seq_id"]], a["bit_score"], fmt_seqid(a["seq_id_est"]), "%.3E" % a["evalue"],
+                                                                 a["q_start"], a["q_end"], qlen, a["db_start"], a["db_end"], tdb.lens[a["seq_id"]])
+                   for a in rows)
+
+
+def align(ctx, queries, tdb, pref):
+    """pref: {key: pref entry} as written by prefilter -> {key: alignment entry}"""
+    key2id = {k: i for i, k in enumerate(tdb.keys)}
+    lists = [[key2id[int(l.split("\t")[0])] for l in pref.get(k, "").splitlines()] for k, _ in queries]
+    q, qoff = encode_many([s for _, s in queries])
+    hoff = np.zeros(len(queries) + 1, np.uint64)
+    hoff[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
+    flat = np.array([t for x in lists for t in x], dtype=np.uint32)
+    alns = ctx.align(q, qoff, flat, hoff)
+    return {k: _aln_lines(alns[int(hoff[i]):int(hoff[i + 1])], tdb, len(s)) for i, (k, s) in enumerate(queries)}
+
+
+def search(ctx, queries, tdb):
+    """prefilter + align without the text round trip (blastp.sh:70,85)"""
+    q, qoff = encode_many([s for _, s in queries])
+    alns, cnt = ctx.search(q, qoff)
+    return {k: _aln_lines(alns[i, :cnt[i]], tdb, len(s)) for i, (k, s) in enumerate(queries)}
+
+
+def parse_orf_header(h):
+    """Orf::parseOrfHeader: 'contigKey\\tfrom+len' or 'from-len' (Orf.cpp:351-438)"""
+    w = h.split()
+    loc = w[1]
+    if "+" in loc:
+        a, b = loc.split("+")
+        return int(w[0]), int(a), int(a) + int(b)
+    a, b = loc.split("-")
+    return int(w[0]), int(a), int(a) - int(b)
+
+
+def resultspercontig(aln, orf_headers, contig_lens):
+    """Join fragment->target records with the fragment's contig coordinates, regroup per contig, stable order by
+    (target key, orf key).  Contigs without records still get an (empty) entry (resultspercontig.cpp:147-196)."""
+    per = {k: [] for k in contig_lens}
+    for orf, text in aln.items():
+        if not text:
+            continue
+        contig, frm, to = parse_orf_header(orf_headers[orf])
+        orf_len = max(frm, to) - min(frm, to) + 1
+        for l in text.splitlines():
+            w = l.split("\t")
+            w[2] = fmt_seqid(float(w[2]))   # parse -> re-print loses up to one unit
+            line = "\t".join(w) + "\t%d\t1\t1.00\t0.000E+00\t0\t%d\t%d\t%d\t%d\t%d\n" % (int(orf), orf_len - 1, orf_len, frm, to, contig_lens[contig])
+            per[contig].append((int(w[0]), int(orf), line))
+    return {c: "".join(r[2] for r in sorted(rows, key=lambda r: (r[0], r[1]))) for c, rows in per.items()}
+
+
+def collectoptimalset(ctx, bycontig, total_target_residues):
+    """{contig: 20-column lines} -> {contig: 19-column exon lines} (Prediction::predictionToBuffer, PredictionParser.h:368-396)"""
+    contigs = list(bycontig.keys())
+    texts = []
+    rows = []
+    off = [0]
+    for c in contigs:
+        for l in bycontig[c].splitlines():
+            w = l.split("\t")
+            rows.append((int(w[0]), int(w[1]), int(w[4]), int(w[5]), int(w[7]), int(w[8]), int(w[9]), int(w[10]), int(w[17]), int(w[18])))
+            texts.append((w[2], w[3]))
+        off.append(len(rows))
+    cands = np.array(rows, dtype=CAND_DTYPE) if rows else np.zeros(0, CAND_DTYPE)
+    calls, cnt, exons = ctx.chain(cands, np.array(off, np.uint64), total_target_residues)
+    out = {}
+    for ci, c in enumerate(contigs):
+        b = off[ci]
+        s = ""
+        for cl in calls[2 * b: 2 * b + cnt[ci]]:
+            head = "%d\t%d\t%d\t%s\t%d\t%d\t%d\t" % (cl["target_key"], cl["strand"], cl["total_bit_score"], "%.3E" % cl["evalue"], cl["n_exons"],
+                                                     cl["low_coord"], cl["high_coord"])
+            for e in exons[cl["exon_begin"]: cl["exon_begin"] + cl["n_exons"]]:
+                k = cands[b + e["cand_idx"]]
+                sid, ev = texts[b + e["cand_idx"]]
+                s += head + "%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n" % (
+                    k["orf_key"], k["bit_score"], fmt_exon_seqid(sid), "%.3E" % float(ev), k["t_start"], k["t_end"], k["t_len"],
+                    e["contig_start"], e["contig_end"], e["nuc_len"], k["frag_from"], k["frag_to"])
+        out[c] = s
+    return out
+
+
+def predictexons(ctx, fragments, orf_headers, contig_lens, tdb):
+    """search -> resultspercontig -> collectoptimalset (predictexons.sh:68-82) on already extracted/translated fragments."""
+    aln = search(ctx, fragments, tdb)
+    byc = resultspercontig(aln, orf_headers, contig_lens)
+    return aln, byc, collectoptimalset(ctx, byc, tdb.total_residues)

@@ -1,0 +1,157 @@
+"""GPU parity tests (run on the B200 box): the sm_100a kernels, called through the C ABI, must reproduce
+ (a) the reference's golden result DBs byte for byte, and
+ (b) the CPU oracle on seeded synthetic inputs larger than the golden cases, plus size-independent properties."""
+import random
+
+import numpy as np
+import pytest
+
+import reflib
+from metaeuk_b200 import modules as M
+
+pytestmark = pytest.mark.gpu
+
+FRAG = ["frag_small", "frag_family", "frag_nomask"]
+CONTIG = ["contigs_small", "contigs_sets"]
+
+
+def ctx_for(c, **kw):
+    tdb = M.TargetDB(c["targets"], c["masked_targets"])
+    ctx = M.make_context(tdb, kmer_thr=c["kmer_thr"], max_res_list_len=c.get("max_seqs", 300), **kw)
+    return ctx, tdb
+
+
+def strkeys(d):
+    return {str(k): v for k, v in d.items()}
+
+
+@pytest.mark.parametrize("name", FRAG + CONTIG)
+def test_prefilter_golden(name):
+    c = reflib.load_case(name)
+    ctx, tdb = ctx_for(c)
+    got = strkeys(M.prefilter(ctx, c["queries"], tdb))
+    bad = [k for k, _ in c["queries"] if got[str(k)] != c["pref"].get(str(k), "")]
+    assert not bad, (bad[:5], got[str(bad[0])][:300], c["pref"].get(str(bad[0]), "")[:300])
+    st = ctx.stats()
+    assert st["pref_results"] == sum(v.count("\n") for v in c["pref"].values())
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", FRAG + CONTIG)
+def test_align_golden(name):
+    c = reflib.load_case(name)
+    ctx, tdb = ctx_for(c)
+    pref = {k: c["pref"].get(str(k), "") for k, _ in c["queries"]}
+    got = strkeys(M.align(ctx, c["queries"], tdb, pref))
+    bad = [k for k, _ in c["queries"] if got[str(k)] != c["aln"].get(str(k), "")]
+    assert not bad, (bad[:5], got[str(bad[0])][:400], c["aln"].get(str(bad[0]), "")[:400])
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", CONTIG)
+def test_predictexons_golden(name):
+    c = reflib.load_case(name)
+    ctx, tdb = ctx_for(c, max_exon_sets=c["max_exon_sets"])
+    contig_lens = {int(k): v for k, v in c["contig_lens"].items()}
+    hdr = {int(k): v for k, v in c["orf_headers"].items()}
+    aln, byc, dp = M.predictexons(ctx, c["queries"], hdr, contig_lens, tdb)
+    assert strkeys(aln) == {k: v for k, v in c["aln"].items()}
+    assert strkeys(byc) == c["bycontig"]
+    assert strkeys(dp) == c["dp"]
+    assert sum(v.count("\n") for v in dp.values()) > 0
+    ctx.close()
+
+
+def synth(seed, nprot, nfrag):
+    rng = random.Random(seed)
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    W = [7.8, 1.9, 5.4, 6.3, 3.9, 7.4, 2.3, 5.1, 5.7, 9.0, 2.2, 4.5, 5.2, 4.3, 5.1, 7.1, 5.8, 6.4, 1.3, 3.2]
+    prots = ["".join(rng.choices(AA, weights=W, k=max(60, int(rng.gauss(330, 120))))) for _ in range(nprot)]
+    frags = []
+    for i in range(nfrag):
+        L = max(15, int(rng.gauss(100, 40)))
+        if i % 2 == 0:
+            p = rng.choice(prots)
+            a = rng.randrange(0, max(1, len(p) - L))
+            rate = rng.choice([0.1, 0.3, 0.5])
+            s = "".join(rng.choice(AA) if rng.random() < rate else ch for ch in p[a:a + L])
+        else:
+            s = "".join(rng.choices(AA, weights=W, k=L))
+        frags.append(s)
+    return prots, frags
+
+
+def test_search_matches_oracle_on_larger_synthetic():
+    """C2-shaped input scaled to what the scalar oracle finishes in seconds: 3000 proteins x 1500 fragments."""
+    prots, frags = synth(2024, 3000, 1500)
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb)
+    queries = list(enumerate(frags))
+    got_pref = M.prefilter(ctx, queries, tdb)
+    o = reflib.Oracle()
+    o.set_params()
+    o.set_targets(prots, prots)
+    res, stats = o.prefilter(frags)
+    keys = list(range(len(prots)))
+    for (k, _), hits in zip(queries, res):
+        assert got_pref[k] == reflib.fmt_pref(hits, keys), k
+    st = ctx.stats()
+    for a, b in (("kmers", "kmers"), ("db_matches", "dbMatches"), ("double_hits", "doubleHits"), ("diag_cells", "diagCells"), ("pref_results", "results")):
+        assert st[a] == stats[b], (a, st[a], stats[b])
+    got_aln = M.search(ctx, queries, tdb)
+    alns, _ = o.align(frags, [[t for t, _, _ in h] for h in res])
+    tlens = [len(p) for p in prots]
+    for (k, q), al in zip(queries, alns):
+        want = "".join(reflib.fmt_aln(a, keys, len(q), tlens) for a in reflib.sort_alns([a for a in al if a["passed"] == 1], keys, tlens))
+        assert got_aln[k] == want, k
+    o.close()
+    ctx.close()
+
+
+def test_prefilter_properties_at_scale():
+    """Size-independent properties on an input too large for the scalar oracle: lists are sorted by (score desc, id asc),
+    capped at max-seqs, scores >= min-ungapped-score, identical on a second run, and per-query results do not depend on
+    which other queries share the batch."""
+    prots, frags = synth(7, 20000, 20000)
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb)
+    q, qoff = M.encode_many(frags)
+    hits, cnt = ctx.prefilter(q, qoff)
+    assert cnt.max() <= 300 and cnt.sum() > 0
+    for i in range(0, len(frags), 37):
+        h = hits[i, :cnt[i]]
+        assert (h["score"] >= 15).all()
+        key = list(zip((-h["score"].astype(np.int64)).tolist(), h["seq_id"].tolist()))
+        assert key == sorted(key)
+        assert len(set(h["seq_id"].tolist())) == len(h)
+    hits2, cnt2 = ctx.prefilter(q, qoff)
+    assert (cnt == cnt2).all()
+    for i in range(len(frags)):
+        assert hits[i, :cnt[i]].tobytes() == hits2[i, :cnt[i]].tobytes()
+    sub = list(range(0, len(frags), 11))
+    q3, qoff3 = M.encode_many([frags[i] for i in sub])
+    hits3, cnt3 = ctx.prefilter(q3, qoff3)
+    for j, i in enumerate(sub):
+        assert cnt3[j] == cnt[i] and hits3[j, :cnt3[j]].tobytes() == hits[i, :cnt[i]].tobytes()
+    ctx.close()
+
+
+def test_edge_cases():
+    prots, frags = synth(3, 200, 10)
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb)
+    queries = [(0, "ACDEFGHIK"), (1, "ACDEFGHIKL"), (2, "XXXXXXXXXXXXXXXXXXXX"), (3, prots[5]), (4, prots[7][10:60] + "X" + prots[7][61:120])]
+    pref = M.prefilter(ctx, queries, tdb)
+    assert pref[0] == "" and pref[2] == ""
+    assert pref[3].split("\t")[0] == "5"
+    o = reflib.Oracle()
+    o.set_params()
+    o.set_targets(prots, prots)
+    res, _ = o.prefilter([s for _, s in queries])
+    for (k, _), hits in zip(queries, res):
+        assert pref[k] == reflib.fmt_pref(hits, list(range(len(prots))))
+    # empty batch
+    h, c = ctx.prefilter(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(c) == 0
+    o.close()
+    ctx.close()
