@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- predictexons hot-path throughput (query fragments / s) on B200, with the CPU path timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+
+A "step" = one pass of the hot path over one batch of synthetic fragments per GPU.
+Workload c2 (default, BASELINE.json configs[1]): 100 K fragments (len max(15,N(100,40)), half mutated protein
+slices, half background) x 50 K proteins (len max(60,N(330,120))), prefilter-only.  c3 = 1 M x 500 K, prefilter + align.
+Multi-GPU (torchrun, one rank per GPU): rank 0 builds the target index, ONE NCCL broadcast replicates it, every rank then
+searches its own shard of fragments (weak scaling, no further collectives).
+
+JSON keys: value = device-resident throughput (inputs already in HBM); e2e = same metric through the host-buffer C ABI call
+(H2D of the fragments + kernels + D2H of the hit lists inside the timed region); roofline for the dominant kernel with
+algorithmic bytes over the CUDA-event kernel time; cpu_baseline = the CPU oracle (port of the reference
+algorithm) on a bounded sample on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BG = np.array([7.8, 1.9, 5.4, 6.3, 3.9, 7.4, 2.3, 5.1, 5.7, 9.0, 2.2, 4.5, 5.2, 4.3, 5.1, 7.1, 5.8, 6.4, 1.3, 3.2])
+BG = BG / BG.sum()
+WORKLOADS = {
+    "c2": dict(n_prot=50_000, n_frag=100_000, align=False, desc="C2: 100K fragments (~100 aa) x 50K proteins (~330 aa), prefilter-only"),
+    "c3": dict(n_prot=500_000, n_frag=1_000_000, align=True, desc="C3: 1M fragments x 500K proteins, prefilter + gapped SW align"),
+    "tiny": dict(n_prot=2_000, n_frag=4_000, align=True, desc="tiny: 4K fragments x 2K proteins (plumbing check)"),
+}
+
+
+def gen_proteins(n, seed=1234):
+    rng = np.random.default_rng(seed)
+    lens = np.maximum(60, np.rint(rng.normal(330, 120, n))).astype(np.int64)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    res = rng.choice(20, size=int(off[-1]), p=BG).astype(np.uint8)
+    return res, off
+
+
+def gen_fragments(n, prot, poff, seed=4321):
+    """half: mutated slices of random proteins (substitution rate in {0.1,0.3,0.5}); half: background"""
+    rng = np.random.default_rng(seed)
+    lens = np.maximum(15, np.rint(rng.normal(100, 40, n))).astype(np.int64)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    tot = int(off[-1])
+    res = rng.choice(20, size=tot, p=BG).astype(np.uint8)
+    homolog = (np.arange(n) % 2) == 0
+    pidx = rng.integers(0, len(poff) - 1, n)
+    plen = (poff[1:] - poff[:-1]).astype(np.int64)[pidx]
+    use = np.minimum(lens, plen)
+    start = (rng.random(n) * np.maximum(1, plen - use)).astype(np.int64)
+    rate = rng.choice([0.1, 0.3, 0.5], n)
+    frag_id = np.repeat(np.arange(n), lens)
+    within = np.arange(tot) - np.repeat(off[:-1].astype(np.int64), lens)
+    src = poff[:-1].astype(np.int64)[pidx][frag_id] + start[frag_id] + np.minimum(within, use[frag_id] - 1)
+    take = homolog[frag_id] & (within < use[frag_id]) & (rng.random(tot) >= rate[frag_id])
+    res[take] = prot[src[take]]
+    return res, off
+
+
+def pinned(a):
+    """copy a numpy array into page-locked host memory (so the C ABI's cudaMemcpyAsync is a real DMA)"""
+    import torch
+    t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)) if a.dtype != np.uint64 else torch.int64, pin_memory=True)
+    v = t.numpy().view(a.dtype)
+    v[...] = a
+    return v, t
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.p = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        sm, mx, reasons = [], 0, set()
+        for l in self.lines:
+            w = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(w[1])); mx = max(mx, float(w[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), w[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_prefilter(st):
+    """L + 21 L (profile) + 16 per similar k-mer (two 8-byte offsets) + 6 per index entry
+    + per double-hit candidate (overlap length + 6) + 10 per result"""
+    return 22 * st["query_residues"] + 16 * st["kmers"] + 6 * st["db_matches"] + st["diag_cells"] + 6 * st["double_hits"] + 10 * st["pref_results"]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "prefilter_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch_c2")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_oracle_run(prot, poff, frag, foff, n_sample, align, threads):
+    """time the CPU oracle (port of the reference algorithm) on the first n_sample fragments of the workload"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reflib
+    o = reflib.Oracle()
+    o.set_params()
+    rc = o.L.mbo_set_targets(o.h, reflib._p(prot, C.c_uint8), reflib._p(prot, C.c_uint8), reflib._p(poff, C.c_uint64), C.c_uint32(len(poff) - 1))
+    assert rc == 0
+    n = min(n_sample, len(foff) - 1)
+    q = np.ascontiguousarray(frag[:int(foff[n])]); qo = np.ascontiguousarray(foff[:n + 1])
+    hits = (reflib.Hit * (n * 300))(); cnt = np.zeros(n, np.uint32); st = reflib.Stats()
+
+    def one():
+        t0 = time.perf_counter()
+        rc = o.L.mbo_prefilter(o.h, reflib._p(q, C.c_uint8), reflib._p(qo, C.c_uint64), C.c_uint32(n), hits, reflib._p(cnt, C.c_uint32), C.byref(st), threads)
+        assert rc == 0
+        if align:
+            hoff = np.zeros(n + 1, np.uint64); hoff[1:] = np.cumsum(cnt)
+            flat = np.zeros(max(1, int(hoff[-1])), np.uint32)
+            for i in range(n):
+                for k in range(cnt[i]):
+                    flat[int(hoff[i]) + k] = hits[i * 300 + k].seqId
+            alns = (reflib.Aln * max(1, int(hoff[-1])))(); cells = C.c_uint64(0)
+            rc = o.L.mbo_align(o.h, reflib._p(q, C.c_uint8), reflib._p(qo, C.c_uint64), C.c_uint32(n), reflib._p(flat, C.c_uint32), reflib._p(hoff, C.c_uint64), alns, C.byref(cells), threads)
+            assert rc == 0
+        return time.perf_counter() - t0
+    return o, one, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="fragments in the CPU-baseline sample (0 = auto)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    base = {"metric": "predictexons query-fragments/sec", "unit": "fragments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup) if args.impl == "b200" else args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (integer DP; float32+float64 only for the composition bias)",
+            "data": "synthetic (seeded; SURVEY.md 8d generator)", "config": {"workload": wl["desc"], "stages": "prefilter+align" if wl["align"] else "prefilter",
+                                                                               "fragments_per_gpu": wl["n_frag"], "proteins": wl["n_prot"], "parallelism": "fragment shards x%d, index replicated by one NCCL broadcast" % args.gpus,
+                                                                               "l2": "inputs exceed L2 (k-mer offsets 256 MB + index entries + similarity table >> 126 MB); no explicit flush"}}
+    # ------------------------------------------------------------------ reference arm: CPU path on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        prot, poff = gen_proteins(wl["n_prot"])
+        frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321)
+        n_sample = args.cpu_sample or (2000 if not wl["align"] else 1000)
+        o, one, n = cpu_oracle_run(prot, poff, frag, foff, n_sample, wl["align"], threads)
+        for _ in range(args.warmup):
+            one()
+        t = sum(one() for _ in range(args.steps))
+        v = n * args.steps / t
+        base.update({"impl": "reference", "value": v, "ms_per_step": 1000 * t / args.steps, "gpu_launches": 0,
+                     "cpu_baseline": {"value": v, "unit": "fragments/s", "cores": threads, "kind": "port",
+                                      "sample": "first %d fragments of the workload per step, all %d host threads (OpenMP over queries); index build excluded" % (n, threads)},
+                     "e2e": {"value": v, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base))
+        return
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from metaeuk_b200.lib import Context
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+    ctx.matrices_default()
+    t_idx0 = time.perf_counter()
+    prot, poff = gen_proteins(wl["n_prot"])
+    if rank == 0:
+        ctx.index_build(prot, prot, poff)   # synthetic background proteins: masked == unmasked (masking is a host preprocessing input)
+        sizes = ctx.index_sizes()
+    if world > 1:
+        sz = torch.tensor(sizes if rank == 0 else [0, 0, 0, 0], dtype=torch.int64, device="cuda")
+        dist.broadcast(sz, 0)
+        sizes = [int(x) for x in sz.tolist()]
+        if rank != 0:
+            ctx.index_alloc(sizes)
+        torch.cuda.synchronize()
+        t_b0 = time.perf_counter()
+        for ptr, nb in ctx.index_buffers():   # the single collective of the path: replicate the index over NVLink
+            class _V:
+                pass
+            v = _V()
+            v.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            dist.broadcast(torch.as_tensor(v, device="cuda"), 0)
+        torch.cuda.synchronize()
+        bcast_s = time.perf_counter() - t_b0
+        if rank != 0:
+            ctx.index_commit()
+    else:
+        bcast_s = 0.0
+    index_s = time.perf_counter() - t_idx0
+    frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321 + rank)
+    nq = len(foff) - 1
+    (fragP, _k1), (foffP, _k2) = pinned(frag), pinned(foff)
+    maxres = ctx.params.max_res_list_len
+
+    def step_resident():
+        ctx.prefilter_resident()
+        if wl["align"]:
+            ctx.align_resident()
+
+    from metaeuk_b200.lib import ALN_DTYPE, HIT_DTYPE, _p
+    hitsP_t = torch.empty((nq * maxres * HIT_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
+    cntP_t = torch.empty((nq,), dtype=torch.int32, pin_memory=True)
+    if wl["align"]:
+        alnP_t = torch.empty((nq * maxres * ALN_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        if wl["align"]:
+            ctx._check(ctx.L.mb200_search(ctx.h, _p(fragP), _p(foffP), C.c_uint32(nq), C.c_void_p(alnP_t.data_ptr()), C.c_void_p(cntP_t.data_ptr())))
+        else:
+            ctx._check(ctx.L.mb200_prefilter(ctx.h, _p(fragP), _p(foffP), C.c_uint32(nq), C.c_void_p(hitsP_t.data_ptr()), C.c_void_p(cntP_t.data_ptr())))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+    W = max(3, args.warmup)
+    ctx.queries_upload(fragP, foffP)
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.stats()["launches"]
+    kernel_ms = []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+        kernel_ms.append(ctx.stats()["ms_prefilter"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    launches = ctx.stats()["launches"] - l0
+    st = ctx.stats()
+    for _ in range(2):
+        step_e2e()
+    dt_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * nq * args.steps / dt
+    e2e = world * nq * args.steps / dt_e2e
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes_prefilter(st)
+    kms = float(np.mean(kernel_ms))
+    achieved = abytes / (kms * 1e-3) / 1e9
+    h2d = int(frag.nbytes + foff.nbytes)
+    d2h = int(nq * maxres * (ALN_DTYPE.itemsize if wl["align"] else HIT_DTYPE.itemsize) + nq * 4)
+    base.update({"value": value, "ms_per_step": 1000 * dt / args.steps, "clocks": clocks, "gpu_launches": int(launches),
+                 "e2e": {"value": e2e, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_e2e / args.steps},
+                 "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                              "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "traffic": ncu_traffic()},
+                 "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},
+                 "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev")},
+                 "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "entries": ctx.index_sizes()[0]}})
+    if wl["align"] and (st["ms_sw_fwd"] + st["ms_sw_rev"]) > 0:
+        base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
+    # CPU baseline (oracle port) on a bounded sample of the same workload, rank 0, N=1 only
+    if args.gpus == 1:
+        n_sample = args.cpu_sample or (2000 if not wl["align"] else 1000)
+        o, one, n = cpu_oracle_run(prot, poff, frag, foff, n_sample, wl["align"], threads)
+        one()
+        tcpu = one()
+        base["cpu_baseline"] = {"value": n / tcpu, "unit": "fragments/s", "cores": threads, "kind": "port",
+                                "sample": "first %d fragments of the workload, all %d host threads (OpenMP over queries); index build excluded" % (n, threads)}
+    print(json.dumps(base))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
