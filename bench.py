@@ -247,17 +247,17 @@ def main():
         if wl["align"]:
             ctx.align_resident()
 
-    from metaeuk_b200.lib import ALN_DTYPE, HIT_DTYPE, _p
-    hitsP_t = torch.empty((nq * maxres * HIT_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
-    cntP_t = torch.empty((nq,), dtype=torch.int32, pin_memory=True)
-    if wl["align"]:
-        alnP_t = torch.empty((nq * maxres * ALN_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
+    from metaeuk_b200.lib import ALN_DTYPE, HIT_DTYPE
+    e2e_out = {}
 
     def step_e2e():
+        # the call a module makes: host buffers in (pinned), compact host result out
         if wl["align"]:
-            ctx._check(ctx.L.mb200_search(ctx.h, _p(fragP), _p(foffP), C.c_uint32(nq), C.c_void_p(alnP_t.data_ptr()), C.c_void_p(cntP_t.data_ptr())))
+            res, off = ctx.search(fragP, foffP)
+            e2e_out["bytes"] = int(res.nbytes + off.nbytes)
         else:
-            ctx._check(ctx.L.mb200_prefilter(ctx.h, _p(fragP), _p(foffP), C.c_uint32(nq), C.c_void_p(hitsP_t.data_ptr()), C.c_void_p(cntP_t.data_ptr())))
+            res, off = ctx.prefilter_compact(fragP, foffP)
+            e2e_out["bytes"] = int(res.nbytes + off.nbytes)
 
     def barrier():
         torch.cuda.synchronize()
@@ -315,7 +315,7 @@ def main():
     kms = float(np.mean(kernel_ms))
     achieved = abytes / (kms * 1e-3) / 1e9
     h2d = int(frag.nbytes + foff.nbytes)
-    d2h = int(nq * maxres * (ALN_DTYPE.itemsize if wl["align"] else HIT_DTYPE.itemsize) + nq * 4)
+    d2h = e2e_out.get("bytes", 0)
     base.update({"value": value, "ms_per_step": 1000 * dt / args.steps, "clocks": clocks, "gpu_launches": int(launches),
                  "e2e": {"value": e2e, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_e2e / args.steps},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,

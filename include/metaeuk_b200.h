@@ -106,10 +106,17 @@ int mb200_index_commit(mb200_ctx *ctx);
 
 /* query side: host buffers in, host buffers out (the call a module makes).  q_off[n_q+1]. */
 int mb200_prefilter(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, mb200_hit *hits /* n_q*max_res_list_len */, uint32_t *hit_count);
+/* alns[k] for every listed hit k (<= max_res_list_len hits per query): hits whose score can pass -e carry all fields and `passed`;
+ * the others (which the reference rejects before computing start coordinates) only carry seq_id and passed = 0. */
 int mb200_align(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, const uint32_t *hit_seq_id, const uint64_t *hit_off,
                 mb200_aln *alns /* hit_off[n_q] */);
-/* prefilter + align in one call: alns[i*max_res_list_len + k] for k < aln_count[i], in prefilter order */
-int mb200_search(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, mb200_aln *alns, uint32_t *aln_count);
+/* same as mb200_prefilter with a compact result: hits of query i = (*hits)[hit_off[i]..hit_off[i+1]).  hit_off is a caller buffer of
+ * n_q+1; *hits is owned by the context and valid until the next call on it. */
+int mb200_prefilter_compact(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, uint64_t *hit_off, const mb200_hit **hits);
+/* prefilter + align in one call (what `search` writes to search_res): the ACCEPTED alignments of query i are
+ * (*alns)[aln_off[i]..aln_off[i+1]) in prefilter order (sort with Matcher::compareHits to print).  aln_off: caller buffer n_q+1;
+ * *alns is owned by the context and valid until the next call on it. */
+int mb200_search(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, uint64_t *aln_off, const mb200_aln **alns);
 /* exon chaining for a batch of contigs: cands of contig c = cands[cand_off[c]..cand_off[c+1]) sorted by (target_key, orf_key).
  * calls/exons are caller buffers sized 2*n_cands*max_exon_sets and n_cands*max_exon_sets; call_off/exon ranges are per contig. */
 int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_off, uint32_t n_contigs, uint64_t total_target_residues,
@@ -119,6 +126,7 @@ int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_of
 int mb200_queries_upload(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q);
 int mb200_prefilter_resident(mb200_ctx *ctx);
 int mb200_align_resident(mb200_ctx *ctx);             /* aligns the resident prefilter result */
+/* dense layouts [n_q][max_res_list_len]; alns holds accepted alignments only, aln_count[i] of them */
 int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count, mb200_aln *alns, uint32_t *aln_count);
 
 int mb200_stats_get(mb200_ctx *ctx, mb200_stats *out);

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -75,65 +76,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS) k_prefilter(MbPrefTables T, co
     }
 }
 
-// ---- gapped Smith-Waterman, one alignment per lane -------------------------------------------------
-// Exact affine-gap local alignment (what the reference's striped 8/16-bit kernels compute):
-//   H = max(0, Hdiag + s, E, F);  E' = max(E - ge, H - go);  F' = max(F - ge, H - go)
-// reporting the maximum, the FIRST target column that reaches it and the smallest query row holding it in that
-// column (StripedSmithWaterman.cpp:873-912); a reverse item walks the reversed query prefix / target prefix and stops
-// at the first column whose maximum equals the forward score (:900).
-struct SwItem { uint32_t q; uint32_t t; int32_t qn; int32_t tBegin; int32_t nCols; int32_t terminate; int32_t rev; int32_t pad; };
-struct SwOut { int32_t score, ref, read, pad; };
-
-__global__ void __launch_bounds__(128) k_sw(const SwItem *__restrict__ items, uint32_t nItems, const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff,
-                                            const int8_t *__restrict__ cb, const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff,
-                                            const int16_t *__restrict__ alnMat, int gapO, int gapE, uint32_t *__restrict__ he /* [warp][maxQn][32] */, uint32_t maxQn,
-                                            SwOut *__restrict__ outs, uint32_t *nextWarpItem, unsigned long long *cellCount) {
-    __shared__ int8_t sMat[448];
-    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat[i] = (int8_t)alnMat[i];
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t *myHE = he + (size_t)warpGlobal * maxQn * 32u + lane;
-    unsigned long long cells = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(nextWarpItem, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nItems) break;
-        const uint32_t idx = base + lane;
-        const bool active = idx < nItems;
-        SwItem it; it.qn = 0; it.nCols = 0; it.q = 0; it.t = 0; it.tBegin = 0; it.terminate = 0; it.rev = 0;
-        if (active) it = items[idx];
-        const uint8_t *q = qres + qoff[it.q]; const int8_t *c = cb + qoff[it.q];
-        const uint8_t *t = tseq + toff[it.t];
-        const int qn = it.qn; const int qLast = qn - 1;   // reverse items read the query prefix backwards
-        for (int j = 0; j < qn; j++) myHE[(size_t)j * 32u] = 0u;
-        int mx = 0, endDb = -1, endQ = qn - 1;
-        int ti = it.tBegin; const int step = it.rev ? -1 : 1;
-        for (int col = 0; col < it.nCols; col++, ti += step) {
-            const int8_t *row = sMat + t[ti] * MB_AL;
-            int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
-            for (int j = 0; j < qn; j++) {
-                const int qj = it.rev ? (qLast - j) : j;
-                const int s = row[q[qj]] + c[qj];
-                const uint32_t w = myHE[(size_t)j * 32u];
-                const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
-                int f = F - gapE; const int f2 = hUp - gapO; f = f > f2 ? f : f2; f = f < 0 ? 0 : f;
-                int h = hDiag + s; h = h < 0 ? 0 : h; h = h > e ? h : e; h = h > f ? h : f;
-                hDiag = hPrev;
-                int en = e - gapE; const int e2 = h - gapO; en = en > e2 ? en : e2; en = en < 0 ? 0 : en;
-                myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
-                F = f; hUp = h;
-                if (h > cm) { cm = h; jm = j; }
-            }
-            cells += (unsigned long long)qn;
-            if (cm > mx) { mx = cm; endDb = ti; endQ = jm; }
-            if (it.terminate > 0 && cm == it.terminate) break;
-        }
-        if (active) { SwOut o; o.score = mx; o.ref = endDb; o.read = endQ; o.pad = (mx >= 65535) ? 1 : 0; outs[idx] = o; }
-    }
-    if (cells) atomicAdd(cellCount, cells);
-}
+#include "sw_kernels.cuh"
 
 // ---- exon chaining: one contig per thread -----------------------------------------------------------
 __global__ void __launch_bounds__(128) k_chain(const MbCand *__restrict__ cands, const uint64_t *__restrict__ candOff, uint32_t nContigs, MbChainParams P,
@@ -180,8 +123,13 @@ struct mb200_ctx {
     DevBuf<MbPrefHit> dHits; DevBuf<uint32_t> dHitCount, dStatus, dCounter; DevBuf<MbPrefStats> dStats; DevBuf<unsigned long long> dCells;
     bool havePref = false;
     // align
-    DevBuf<SwItem> dItems; DevBuf<SwOut> dOuts; DevBuf<uint32_t> dHE; std::vector<int> minScore;   // per query length, -2 = not computed
-    std::vector<mb200_aln> hAlns; std::vector<uint32_t> hAlnCount; std::vector<MbPrefHit> hHits; std::vector<uint32_t> hHitCount;
+    DevBuf<uint32_t> dPairOff, dChunkOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
+    DevBuf<uint64_t> dHitOff64;
+    std::vector<int> minScore;   // per query length, -2 = not computed
+    std::vector<uint32_t> hOrder;   // queries by descending length
+    std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
+    std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<mb200_hit> hFlatHits; std::vector<uint64_t> hHitOff;
+    bool haveAln = false;
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -271,7 +219,8 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
-    c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dItems.release(); c->dOuts.release(); c->dHE.release();
+    c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
+    c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -393,7 +342,7 @@ int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, u
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_h2d = ms;
-    c->hQoff.assign(qoff, qoff + nQ + 1); c->nQ = nQ; c->totalQ = tot; c->maxQLen = maxL; c->havePref = false;
+    c->hQoff.assign(qoff, qoff + nQ + 1); c->nQ = nQ; c->totalQ = tot; c->maxQLen = maxL; c->havePref = false; c->haveAln = false; c->hOrder = order;
     if (tot) {
         CU(cudaEventRecord(c->ev0, c->stream));
         k_prep<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->dQ.p, c->dQoff.p, nQ, tot, c->dSeedMat.p, c->dSeedPB.p, c->dAlnMat.p, c->dAlnPB.p, c->dBias.p, c->dCorr.p, c->dCb.p);
@@ -439,127 +388,159 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     return 0;
 }
 
-// run a batch of SW items on the device; outs returned on the host
-static int run_sw(mb200_ctx *c, const std::vector<SwItem> &items, std::vector<SwOut> &outs, uint32_t maxQn, float *msOut, uint64_t *cellsOut) {
-    outs.resize(items.size());
-    *msOut = 0; *cellsOut = 0;
-    if (items.empty()) return 0;
-    const int warpsPerBlock = 4; const int blocks = c->nSM * 8;
-    const size_t nWarps = (size_t)blocks * warpsPerBlock;
-    if (maxQn == 0) maxQn = 1;
-    TRY(c->dItems.alloc(items.size())); TRY(c->dOuts.alloc(items.size())); TRY(c->dHE.alloc(nWarps * maxQn * 32)); TRY(c->dCounter.alloc(4)); TRY(c->dCells.alloc(1));
-    TRY(upload(c->dItems.p, items.data(), items.size() * sizeof(SwItem), c->stream));
-    CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 8, c->stream));
-    CU(cudaEventRecord(c->ev0, c->stream));
-    k_sw<<<blocks, warpsPerBlock * 32, 0, c->stream>>>(c->dItems.p, (uint32_t)items.size(), c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
-                                                        c->par.gap_open, c->par.gap_extend, c->dHE.p, maxQn, c->dOuts.p, c->dCounter.p, c->dCells.p);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaMemcpyAsync(outs.data(), c->dOuts.p, items.size() * sizeof(SwOut), cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long cells = 0;
-    CU(cudaMemcpyAsync(&cells, c->dCells.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaEventElapsedTime(msOut, c->ev0, c->ev1)); *cellsOut = cells; c->st.launches++;
-    return 0;
-}
-
 static int min_score_for(mb200_ctx *c, uint32_t L) {
     if (c->minScore.size() < 32769) c->minScore.assign(32769, -2);
     if (c->minScore[L] == -2) c->minScore[L] = c->ev.minScoreFor(c->par.eval_thr, (double)L, (double)c->totalRes);
     return c->minScore[L];
 }
 
-// align the lists hitSeq[hitOff[i]..hitOff[i+1]) of every resident query; alns has the same layout
-static int align_lists(mb200_ctx *c, const uint32_t *hitSeq, const uint64_t *hitOff, mb200_aln *alns) {
-    const uint32_t nQ = c->nQ;
-    const uint64_t nPairs = hitOff[nQ];
-    c->st.sw_pairs = nPairs; c->st.sw_cells_fwd = c->st.sw_cells_rev = 0; c->st.ms_sw_fwd = c->st.ms_sw_rev = 0; c->st.sw_target_bytes = 0;
-    if (nPairs == 0) return 0;
-    if (nPairs >= (1ull << 32)) return fail(MB200_E_LIMIT, "too many alignments in one call");
-    std::vector<SwItem> items(nPairs);
-    uint64_t tbytes = 0;
-    for (uint32_t i = 0; i < nQ; i++) {
-        const int L = (int)(c->hQoff[i + 1] - c->hQoff[i]);
-        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
-            const uint32_t t = hitSeq[k];
-            if (t >= c->nT) return fail(MB200_E_ARG, "hit target id %u out of range", t);
-            SwItem &it = items[k]; it.q = i; it.t = t; it.qn = L; it.tBegin = 0; it.nCols = (int)(c->hToff[t + 1] - c->hToff[t]); it.terminate = 0; it.rev = 0; it.pad = 0;
-            tbytes += (uint64_t)it.nCols;
-        }
-    }
-    std::vector<SwOut> fwd; float ms; uint64_t cells;
-    TRY(run_sw(c, items, fwd, c->maxQLen, &ms, &cells));
-    c->st.ms_sw_fwd = ms; c->st.sw_cells_fwd = cells; c->st.sw_target_bytes = tbytes;
-    // gate on the e-value (StripedSmithWaterman.cpp:389-398): only alignments that can pass -e get start coordinates
-    std::vector<SwItem> ritems; std::vector<uint64_t> rmap;
-    uint32_t maxRn = 0;
-    for (uint32_t i = 0; i < nQ; i++) {
-        if (hitOff[i + 1] == hitOff[i]) continue;
-        const uint32_t L = (uint32_t)(c->hQoff[i + 1] - c->hQoff[i]);
-        const int ms0 = min_score_for(c, L);
-        if (ms0 < 0) return fail(MB200_E_INTERNAL, "e-value not monotone in the score for query length %u", L);
-        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
-            const SwOut &f = fwd[k]; mb200_aln &a = alns[k];
-            if (f.pad) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
-            memset(&a, 0, sizeof(a));
-            a.seq_id = hitSeq[k]; a.raw_score = f.score; a.q_end = f.read; a.db_end = f.ref; a.q_start = -1; a.db_start = -1; a.passed = 0;
-            if (f.ref < 0) continue;
-            if (f.score >= ms0) {
-                SwItem it; it.q = i; it.t = hitSeq[k]; it.qn = f.read + 1; it.tBegin = f.ref; it.nCols = f.ref + 1; it.terminate = f.score; it.rev = 1; it.pad = 0;
-                ritems.push_back(it); rmap.push_back(k); if ((uint32_t)it.qn > maxRn) maxRn = (uint32_t)it.qn;
-            }
-        }
-    }
-    std::vector<SwOut> rev;
-    TRY(run_sw(c, ritems, rev, maxRn, &ms, &cells));
-    c->st.ms_sw_rev = ms; c->st.sw_cells_rev = cells;
-    for (size_t r = 0; r < ritems.size(); r++) {
-        mb200_aln &a = alns[rmap[r]];
-        if (rev[r].score != a.raw_score) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (%d vs %d)", a.raw_score, rev[r].score);
-        a.db_start = rev[r].ref; a.q_start = a.q_end - rev[r].read;
-    }
-    // host epilogue: e-value, bit score, coverage, estimated identity, acceptance (Matcher.cpp:100-142, Alignment.cpp:548-567)
-#pragma omp parallel for schedule(dynamic, 64)
-    for (uint32_t i = 0; i < nQ; i++) {
-        const uint32_t L = (uint32_t)(c->hQoff[i + 1] - c->hQoff[i]);
-        for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) {
-            mb200_aln &a = alns[k];
-            if (a.db_end < 0) { a.q_end = (int)L - 1; continue; }
-            a.evalue = c->ev.evalue(a.raw_score, L, (double)c->totalRes);
-            a.bit_score = c->ev.bitScore(a.raw_score);
-            if (a.db_start < 0) continue;
-            const uint32_t tLen = (uint32_t)(c->hToff[a.seq_id + 1] - c->hToff[a.seq_id]);
-            a.q_cov = (std::min(L, (uint32_t)std::max(a.q_start, a.q_end)) - (uint32_t)std::min(a.q_start, a.q_end) + 1) / (float)L;
-            a.db_cov = (std::min(tLen, (uint32_t)std::max(a.db_start, a.db_end)) - (uint32_t)std::min(a.db_start, a.db_end) + 1) / (float)tLen;
-            a.aln_len = std::max(abs(a.q_end - a.q_start), abs(a.db_end - a.db_start)) + 1;
-            const unsigned qa = std::max((unsigned)(a.q_end - a.q_start), 1u), ta = std::max((unsigned)(a.db_end - a.db_start), 1u);
-            float sid = ((uint16_t)a.raw_score / static_cast<float>(std::max(qa, ta))) * 0.1656 + 0.1141;
-            sid = std::min(sid, 1.0f); a.seq_id_est = std::max(0.0f, sid);
-            a.passed = (a.evalue <= c->par.eval_thr && a.aln_len >= c->par.min_aln_len) ? 1 : 0;
-        }
-    }
+static int sync_check(mb200_ctx *c, const char *what) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(MB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return 0;
 }
+
+// Gapped alignment of the resident hit lists (dHits / dHitCount).  Leaves c->hTrace = every alignment whose score passes the
+// e-value gate (score, start/end coordinates), sorted by slot = query * maxHits + rank.
+static int align_pipeline(mb200_ctx *c) {
+    const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
+    c->hTrace.clear(); c->haveAln = false;
+    c->st.sw_pairs = 0; c->st.sw_cells_fwd = c->st.sw_cells_rev = 0; c->st.ms_sw_fwd = c->st.ms_sw_rev = 0; c->st.sw_target_bytes = 0;
+    if (nQ == 0) { c->haveAln = true; return 0; }
+    if ((uint64_t)nQ * maxHits >= (1ull << 32)) return fail(MB200_E_LIMIT, "n_queries * max_res_list_len must be < 2^32 per call");
+    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(64)); TRY(c->dCells.alloc(2));
+    CU(cudaMemsetAsync(c->dCounter.p, 0, 64 * 4, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 16, c->stream));
+    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p);
+    CU(cudaGetLastError());
+    uint32_t nPairs = 0;
+    CU(cudaMemcpyAsync(&nPairs, c->dPairOff.p + nQ, 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "scan"));
+    c->st.launches++; c->st.sw_pairs = nPairs;
+    if (nPairs == 0) { c->haveAln = true; return 0; }
+    // e-value gate as a per-length minimum raw score (StripedSmithWaterman.cpp:389-398)
+    std::vector<int32_t> ms(c->maxQLen + 2, 0x7fffffff);
+    for (uint32_t i = 0; i < nQ; i++) {
+        const uint32_t L = (uint32_t)(c->hQoff[i + 1] - c->hQoff[i]);
+        if (ms[L] == 0x7fffffff) { const int v = min_score_for(c, L); if (v < 0) return fail(MB200_E_INTERNAL, "e-value not monotone in the score for query length %u", L); ms[L] = v; }
+    }
+    TRY(c->dMinScore.alloc(ms.size())); TRY(upload(c->dMinScore.p, ms.data(), ms.size() * 4, c->stream));
+    TRY(c->dScore.alloc((size_t)nQ * maxHits)); TRY(c->dPassList.alloc(nPairs));
+    uint32_t *dNPass = c->dCounter.p + 32, *dErr = c->dCounter.p + 33;
+    // length classes over the length-sorted query order (descending): one launch per class, shared-memory state sized to the class
+    static const uint32_t classPad[] = {32, 64, 96, 128, 160, 192, 224, 256, 384, 512, 768, 1024};
+    const int nClass = (int)(sizeof(classPad) / sizeof(classPad[0]));
+    std::vector<uint32_t> bound(nClass + 2, 0);   // bound[k] = first order position whose length <= classPad[k-1]... computed below
+    // order is descending: positions [0, pLong) have L > 1024
+    auto lenAt = [&](uint32_t p) { const uint32_t q = c->hOrder[p]; return (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]); };
+    auto firstLE = [&](uint32_t x) { uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lenAt(mid) <= x) hi = mid; else lo = mid + 1; } return lo; };
+    const uint32_t pLong = firstLE(1024);
+    CU(cudaEventRecord(c->ev0, c->stream));
+    for (int k = nClass - 1; k >= 0; k--) {
+        const uint32_t pB = firstLE(classPad[k]), pE = (k == 0) ? nQ : firstLE(classPad[k - 1]);
+        if (pB >= pE) continue;
+        const uint32_t Lpad = classPad[k];
+        int W = (int)(160 * 1024 / (Lpad * 33u * 4u)); if (W > MB_SW_WARPS) W = MB_SW_WARPS; if (W < 1) W = 1;
+        const size_t smem = (size_t)W * Lpad * 33u * 4u;
+        CU(cudaFuncSetAttribute(k_sw_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_score<4>, W * 32, smem)); if (perSM < 1) perSM = 1;
+        k_sw_score<4><<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p,
+                                                                  c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend, Lpad, c->dMinScore.p, c->dScore.p,
+                                                                  c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr);
+        CU(cudaGetLastError()); c->st.launches++;
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    uint32_t hn[2] = {0, 0};
+    CU(cudaMemcpyAsync(hn, dNPass, 8, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long hc[2] = {0, 0};
+    CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "k_sw_score"));
+    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
+    if (hn[1] == 1) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
+    if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
+    // queries longer than 1024 residues: every hit goes straight to the trace kernel (host applies the e-value test)
+    std::vector<uint32_t> extra;
+    if (pLong > 0) {
+        std::vector<uint32_t> hcnt(nQ);
+        CU(cudaMemcpy(hcnt.data(), c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t p = 0; p < pLong; p++) { const uint32_t q = c->hOrder[p]; for (uint32_t k = 0; k < hcnt[q]; k++) extra.push_back(q * maxHits + k); }
+    }
+    uint32_t nPass = hn[0];
+    if (!extra.empty()) {
+        if ((uint64_t)nPass + extra.size() > nPairs) return fail(MB200_E_INTERNAL, "pass list overflow");
+        TRY(upload(c->dPassList.p + nPass, extra.data(), extra.size() * 4, c->stream)); nPass += (uint32_t)extra.size();
+    }
+    if (nPass) {
+        const int blocks = c->nSM * 8; const size_t nWarps = (size_t)blocks * 4;
+        TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32)); TRY(c->dTrace.alloc(nPass));
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_sw_trace<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                                                  c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev1, c->stream));
+        c->hTrace.resize(nPass);
+        CU(cudaMemcpyAsync(c->hTrace.data(), c->dTrace.p, (size_t)nPass * sizeof(SwTraceOut), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        TRY(sync_check(c, "k_sw_trace"));
+        CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1]; c->st.launches++;
+        for (const SwTraceOut &o : c->hTrace) {
+            if (o.flag & 1) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (slot %u)", o.slot);
+            if (o.flag & 2) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
+        }
+        __gnu_parallel::sort(c->hTrace.begin(), c->hTrace.end(), [](const SwTraceOut &a, const SwTraceOut &b) { return a.slot < b.slot; });
+    }
+    c->haveAln = true;
+    return 0;
+}
+
+// host epilogue for one traced alignment: e-value, bit score, coverage, estimated identity, acceptance
+// (Matcher::getSWResult, Matcher.cpp:100-142; Alignment::checkCriteria, Alignment.cpp:548-567)
+static void finish_aln(const mb200_ctx *c, const SwTraceOut &o, uint32_t tid, uint32_t L, mb200_aln &a) {
+    memset(&a, 0, sizeof(a));
+    a.seq_id = tid; a.raw_score = o.score; a.q_end = o.qEnd; a.db_end = o.dbEnd; a.q_start = o.qStart; a.db_start = o.dbStart;
+    if (o.dbEnd < 0) { a.q_end = (int)L - 1; return; }
+    a.evalue = c->ev.evalue(a.raw_score, L, (double)c->totalRes);
+    a.bit_score = c->ev.bitScore(a.raw_score);
+    if (a.evalue > c->par.eval_thr) { a.q_start = a.db_start = -1; return; }   // the reference returns before the reverse pass
+    const uint32_t tLen = (uint32_t)(c->hToff[tid + 1] - c->hToff[tid]);
+    a.q_cov = (std::min(L, (uint32_t)std::max(a.q_start, a.q_end)) - (uint32_t)std::min(a.q_start, a.q_end) + 1) / (float)L;
+    a.db_cov = (std::min(tLen, (uint32_t)std::max(a.db_start, a.db_end)) - (uint32_t)std::min(a.db_start, a.db_end) + 1) / (float)tLen;
+    a.aln_len = std::max(abs(a.q_end - a.q_start), abs(a.db_end - a.db_start)) + 1;
+    const unsigned qa = std::max((unsigned)(a.q_end - a.q_start), 1u), ta = std::max((unsigned)(a.db_end - a.db_start), 1u);
+    float sid = ((uint16_t)a.raw_score / static_cast<float>(std::max(qa, ta))) * 0.1656 + 0.1141;
+    sid = std::min(sid, 1.0f); a.seq_id_est = std::max(0.0f, sid);
+    a.passed = (a.evalue <= c->par.eval_thr && a.aln_len >= c->par.min_aln_len) ? 1 : 0;
+}
+
+static int trace_tids(mb200_ctx *c, std::vector<uint32_t> &tids);
 
 int mb200_align_resident(mb200_ctx *c) {
     if (!c || !c->havePref) return fail(MB200_E_STATE, "no resident prefilter result");
     CU(cudaSetDevice(c->device));
+    return align_pipeline(c);
+}
+
+// compact device->host copy of the resident prefilter result: hit_off[n_q+1], hits in query order
+static int download_hits_compact(mb200_ctx *c) {
     const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
-    c->hHits.resize((size_t)nQ * maxHits); c->hHitCount.resize(nQ);
+    c->hHitOff.assign(nQ + 1, 0); c->hFlatHits.clear();
+    if (nQ == 0) return 0;
+    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1));
+    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> off(nQ + 1);
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemcpyAsync(c->hHits.data(), c->dHits.p, (size_t)nQ * maxHits * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->hHitCount.data(), c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(off.data(), c->dPairOff.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "scan"));
+    const uint32_t n = off[nQ];
+    TRY(c->dFlatHits.alloc(n));
+    k_compact_hits<<<nQ, 64, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dPairOff.p, nQ, maxHits, c->dFlatHits.p);
+    CU(cudaGetLastError());
+    c->hFlatHits.resize(n);
+    if (n) CU(cudaMemcpyAsync(c->hFlatHits.data(), c->dFlatHits.p, (size_t)n * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_d2h = ms;
-    std::vector<uint64_t> off(nQ + 1, 0);
-    for (uint32_t i = 0; i < nQ; i++) off[i + 1] = off[i] + c->hHitCount[i];
-    std::vector<uint32_t> seq(off[nQ] ? off[nQ] : 1);
-    for (uint32_t i = 0; i < nQ; i++) for (uint32_t k = 0; k < c->hHitCount[i]; k++) seq[off[i] + k] = c->hHits[(size_t)i * maxHits + k].seqId;
-    std::vector<mb200_aln> flat(off[nQ] ? off[nQ] : 1);
-    TRY(align_lists(c, seq.data(), off.data(), flat.data()));
-    c->hAlns.assign((size_t)nQ * maxHits, mb200_aln()); c->hAlnCount.assign(nQ, 0);
-    for (uint32_t i = 0; i < nQ; i++) { c->hAlnCount[i] = c->hHitCount[i]; for (uint32_t k = 0; k < c->hHitCount[i]; k++) c->hAlns[(size_t)i * maxHits + k] = flat[off[i] + k]; }
+    TRY(sync_check(c, "compact hits"));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_d2h = ms; c->st.launches += 2;
+    for (uint32_t i = 0; i <= nQ; i++) c->hHitOff[i] = off[i];
     return 0;
 }
 
@@ -572,8 +553,14 @@ int mb200_results_download(mb200_ctx *c, mb200_hit *hits, uint32_t *hitCount, mb
         CU(cudaMemcpy(hitCount, c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost));
     }
     if (alns && alnCount) {
-        if (c->hAlnCount.size() != nQ) return fail(MB200_E_STATE, "no resident alignment result");
-        memcpy(alns, c->hAlns.data(), c->hAlns.size() * sizeof(mb200_aln)); memcpy(alnCount, c->hAlnCount.data(), (size_t)nQ * 4);
+        if (!c->haveAln) return fail(MB200_E_STATE, "no resident alignment result");
+        for (uint32_t i = 0; i < nQ; i++) alnCount[i] = 0;
+        std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
+        for (size_t r = 0; r < c->hTrace.size(); r++) {
+            const uint32_t q = c->hTrace[r].slot / maxHits; const uint32_t L = (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]);
+            mb200_aln a; finish_aln(c, c->hTrace[r], tids[r], L, a);
+            if (a.passed) alns[(size_t)q * maxHits + alnCount[q]++] = a;
+        }
     }
     return 0;
 }
@@ -585,19 +572,81 @@ int mb200_prefilter(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32
     return mb200_results_download(c, hits, hitCount, nullptr, nullptr);
 }
 
+int mb200_prefilter_compact(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, uint64_t *hitOff, const mb200_hit **hits) {
+    if (!hitOff || !hits) return fail(MB200_E_ARG, "null output");
+    TRY(mb200_queries_upload(c, q, qoff, nQ));
+    TRY(mb200_prefilter_resident(c));
+    TRY(download_hits_compact(c));
+    memcpy(hitOff, c->hHitOff.data(), (size_t)(nQ + 1) * 8);
+    *hits = c->hFlatHits.empty() ? nullptr : c->hFlatHits.data();
+    return 0;
+}
+
+// accepted alignments of the resident pass, compact: fills c->hAlns / c->hAlnOff (prefilter order inside a query)
+static int collect_accepted(mb200_ctx *c, const std::vector<uint32_t> &tidOfTrace) {
+    const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
+    std::vector<mb200_aln> tmp(c->hTrace.size());
+#pragma omp parallel for schedule(dynamic, 256)
+    for (size_t r = 0; r < c->hTrace.size(); r++) {
+        const uint32_t q = c->hTrace[r].slot / maxHits; const uint32_t L = (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]);
+        finish_aln(c, c->hTrace[r], tidOfTrace[r], L, tmp[r]);
+    }
+    c->hAlnOff.assign(nQ + 1, 0); c->hAlns.clear();
+    for (size_t r = 0; r < tmp.size(); r++) if (tmp[r].passed) { c->hAlnOff[c->hTrace[r].slot / maxHits + 1]++; c->hAlns.push_back(tmp[r]); }
+    for (uint32_t i = 0; i < nQ; i++) c->hAlnOff[i + 1] += c->hAlnOff[i];
+    return 0;
+}
+
+// target ids of the traced slots, gathered on the device
+__global__ void k_gather_tid(const MbPrefHit *__restrict__ hits, const SwTraceOut *__restrict__ tr, uint32_t n, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hits[tr[i].slot].seqId;
+}
+static int trace_tids(mb200_ctx *c, std::vector<uint32_t> &tids) {
+    const size_t n = c->hTrace.size(); tids.resize(n);
+    if (!n) return 0;
+    // hTrace was sorted on the host; re-upload so the gather follows the same order
+    TRY(c->dTrace.alloc(n)); TRY(c->dFlatSeq.alloc(n));
+    TRY(upload(c->dTrace.p, c->hTrace.data(), n * sizeof(SwTraceOut), c->stream));
+    k_gather_tid<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->dHits.p, c->dTrace.p, (uint32_t)n, c->dFlatSeq.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(tids.data(), c->dFlatSeq.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "gather tid")); c->st.launches++;
+    return 0;
+}
+
 int mb200_align(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, const uint32_t *hitSeq, const uint64_t *hitOff, mb200_aln *alns) {
     if (!hitSeq || !hitOff || !alns) return fail(MB200_E_ARG, "null argument");
     if (!c || !c->haveIndex) return fail(MB200_E_STATE, "index not set");
     TRY(mb200_queries_upload(c, q, qoff, nQ));
-    return align_lists(c, hitSeq, hitOff, alns);
+    const uint32_t maxHits = (uint32_t)c->par.max_res_list_len;
+    const uint64_t n = hitOff[nQ];
+    for (uint32_t i = 0; i < nQ; i++) if (hitOff[i + 1] - hitOff[i] > maxHits) return fail(MB200_E_LIMIT, "query %u has more than max_res_list_len hits", i);
+    for (uint64_t k = 0; k < n; k++) if (hitSeq[k] >= c->nT) return fail(MB200_E_ARG, "hit target id %u out of range", hitSeq[k]);
+    TRY(c->dHits.alloc((size_t)nQ * maxHits)); TRY(c->dHitCount.alloc(nQ + 1)); TRY(c->dFlatSeq.alloc(n ? n : 1)); TRY(c->dHitOff64.alloc(nQ + 1));
+    if (n) TRY(upload(c->dFlatSeq.p, hitSeq, n * 4, c->stream));
+    TRY(upload(c->dHitOff64.p, hitOff, (size_t)(nQ + 1) * 8, c->stream));
+    if (nQ) { k_scatter_hits<<<nQ, 64, 0, c->stream>>>(c->dFlatSeq.p, c->dHitOff64.p, nQ, maxHits, c->dHits.p, c->dHitCount.p); CU(cudaGetLastError()); c->st.launches++; }
+    c->havePref = true;
+    TRY(align_pipeline(c));
+    for (uint32_t i = 0; i < nQ; i++) for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) { memset(&alns[k], 0, sizeof(mb200_aln)); alns[k].seq_id = hitSeq[k]; alns[k].q_start = alns[k].db_start = -1; }
+    for (const SwTraceOut &o : c->hTrace) {
+        const uint32_t qi = o.slot / maxHits, k = o.slot % maxHits; const uint64_t pos = hitOff[qi] + k;
+        finish_aln(c, o, hitSeq[pos], (uint32_t)(c->hQoff[qi + 1] - c->hQoff[qi]), alns[pos]);
+    }
+    return 0;
 }
 
-int mb200_search(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, mb200_aln *alns, uint32_t *alnCount) {
-    if (!alns || !alnCount) return fail(MB200_E_ARG, "null output");
+int mb200_search(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, uint64_t *alnOff, const mb200_aln **alns) {
+    if (!alnOff || !alns) return fail(MB200_E_ARG, "null output");
     TRY(mb200_queries_upload(c, q, qoff, nQ));
     TRY(mb200_prefilter_resident(c));
-    TRY(mb200_align_resident(c));
-    return mb200_results_download(c, nullptr, nullptr, alns, alnCount);
+    TRY(align_pipeline(c));
+    std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
+    TRY(collect_accepted(c, tids));
+    memcpy(alnOff, c->hAlnOff.data(), (size_t)(nQ + 1) * 8);
+    *alns = c->hAlns.empty() ? nullptr : c->hAlns.data();
+    return 0;
 }
 
 int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, uint32_t nContigs, uint64_t totalTargetResidues, mb200_call *calls,

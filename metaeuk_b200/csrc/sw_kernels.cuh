@@ -1,0 +1,218 @@
+// sw_kernels.cuh -- gapped Smith-Waterman on the device (sm_100a), exact affine-gap local alignment.
+//
+// What the reference computes per (query, target) hit (M/ = reference/lib/mmseqs/):
+//   SmithWaterman::ssw_align_private<SEQ_SEQ>   M/src/alignment/StripedSmithWaterman.cpp:309-545
+//     forward  sw_sse2_byte / sw_sse2_word (:638-940, :942-1214): score, FIRST target column reaching it, smallest query row
+//     e-value gate (:389-398) -- only alignments that can pass -e get start coordinates
+//     reverse  on the reversed query prefix / target prefix, stopping at the first column whose maximum == score (:400-476, :900)
+// Recurrence:  H = max(0, Hdiag + s, E, F);  E' = max(E - ge, H - go);  F' = max(F - ge, H - go);  s = mat[t][q_j] + compBias8[j].
+//
+// Two kernels:
+//   k_sw_score  all hits, score only.  One warp per (query, chunk of <= 32 hits): every lane aligns the SAME query against its
+//               own target, so the query row (residue, bias) is a shared-memory broadcast and the substitution lookup
+//               sMat[q_j][t] is bank-conflict free (row = 32 consecutive banks).  Per-lane DP state = one packed (H:16|E:16) word per
+//               query row in shared memory, laid out [row][lane]; NC target columns are processed per sweep over the query so the
+//               state is read/written once per NC cells.  Alignments whose score reaches the per-query-length e-value gate are
+//               appended to a pass list.
+//   k_sw_trace  pass list only (a few % of the hits): forward with end tracking, then the reverse pass; one alignment per lane,
+//               state in a lane-interleaved global scratch (any length).
+#pragma once
+#include <stdint.h>
+
+#define MB_SW_WARPS 4
+#define MB_SW_PADRES 21   // matrix row/column used for columns beyond the target end (very negative)
+
+struct SwTraceOut { uint32_t slot; int32_t score, qStart, qEnd, dbStart, dbEnd, flag, pad; };
+
+__device__ __forceinline__ int sw_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+
+template <int NC>
+__global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, uint32_t maxHits,
+    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
+    uint32_t Lpad, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag) {
+    extern __shared__ __align__(16) uint32_t dynSmem[];
+    __shared__ int32_t sMat[22 * 32];
+    for (int i = threadIdx.x; i < 22 * 32; i += blockDim.x) {
+        const int r = i >> 5, t = i & 31;
+        sMat[i] = (r < 21 && t < 21) ? (int)alnMat[t * 21 + r] : -30000;   // sMat[q][t] = mat[t][q] (Matcher tinySubMat, StripedSmithWaterman.cpp:1341)
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    uint32_t *HE = dynSmem + (size_t)wib * (Lpad * 33u);   // [Lpad][32] state words
+    uint32_t *sQcb = HE + Lpad * 32u;                       // [Lpad]  (q_j * 32) | (uint8)cb_j << 16
+    const uint32_t chunkBase = chunkOff[pBegin], chunkEnd = chunkOff[pEnd];
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = chunkBase + atomicAdd(counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= chunkEnd) break;
+        uint32_t lo = pBegin, hi = pEnd;   // chunkOff[lo] <= chunk < chunkOff[hi]
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunkOff[mid] <= chunk) lo = mid; else hi = mid; }
+        const uint32_t qi = order[lo];
+        const uint32_t k = (chunk - chunkOff[lo]) * 32u + lane;
+        const uint32_t cnt = hitCount[qi];
+        const bool active = k < cnt;
+        const uint64_t qb = qoff[qi]; const int L = (int)(qoff[qi + 1] - qb);
+        __syncwarp();
+        for (int j = lane; j < L; j += 32) sQcb[j] = ((uint32_t)qres[qb + j] << 5) | ((uint32_t)(uint8_t)cb[qb + j] << 16);
+        __syncwarp();
+        const size_t slot = (size_t)qi * maxHits + k;
+        uint32_t tid = 0; int tLen = 0; const uint8_t *t = tseq;
+        if (active) { tid = hits[slot].seqId; const uint64_t tb = toff[tid]; tLen = (int)(toff[tid + 1] - tb); t = tseq + tb; }
+        int mx = 0;
+        uint32_t *myHE = HE + lane;
+        for (int i0 = 0; i0 < tLen; i0 += NC) {
+            int tAddr[NC], hprev[NC], F[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) { tAddr[c] = (i0 + c < tLen) ? (int)t[i0 + c] : MB_SW_PADRES; hprev[c] = 0; F[c] = 0; }
+            int hleftPrev = 0;
+            const bool first = (i0 == 0);
+            for (int j = 0; j < L; j++) {
+                const uint32_t w = first ? 0u : myHE[j * 32];
+                const int hleft = (int)(w & 0xFFFFu);
+                int e = (int)(w >> 16);
+                const uint32_t qc = sQcb[j];
+                const int32_t *row = sMat + (qc & 0xFFFFu);
+                const int cbj = (int)(int8_t)(qc >> 16);
+                int diag = hleftPrev;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int s = row[tAddr[c]] + cbj;
+                    const int f = __viaddmax_s32(F[c], -gapE, hprev[c] - gapO);
+                    const int h = sw_max3(diag + s, e, f > 0 ? f : 0);
+                    diag = hprev[c]; hprev[c] = h; F[c] = f;
+                    e = sw_max3(e - gapE, h - gapO, 0);
+                    mx = h > mx ? h : mx;
+                }
+                hleftPrev = hleft;
+                myHE[j * 32] = (uint32_t)hprev[NC - 1] | ((uint32_t)e << 16);
+            }
+            cells += (unsigned long long)L * NC;
+        }
+        if (active) {
+            scoreOut[slot] = mx;
+            if (mx >= 65000) atomicExch(errFlag, 1u);
+            if (mx >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slot; else atomicExch(errFlag, 2u); }
+        }
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
+// one alignment per lane: forward with end tracking, then reverse to the start.  slot = query * maxHits + hit rank (slot < 2^32).
+__global__ void __launch_bounds__(128) k_sw_trace(const uint32_t *__restrict__ passList, uint32_t nPass, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
+                                                  const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+                                                  const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat,
+                                                  int gapO, int gapE, uint32_t *__restrict__ he /* [warp][maxQn][32] */, uint32_t maxQn,
+                                                  SwTraceOut *__restrict__ outs, uint32_t *counter, unsigned long long *cellCount) {
+    __shared__ int8_t sMat[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t *myHE = he + (size_t)warpGlobal * maxQn * 32u + lane;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nPass) break;
+        const uint32_t idx = base + lane;
+        if (idx >= nPass) continue;   // lanes are independent from here on (no warp collectives below)
+        const uint32_t slot = passList[idx];
+        const uint32_t qi = slot / maxHits;
+        const uint32_t tid = hits[slot].seqId;
+        const uint8_t *q = qres + qoff[qi]; const int8_t *c = cb + qoff[qi]; const int L = (int)(qoff[qi + 1] - qoff[qi]);
+        const uint8_t *t = tseq + toff[tid]; const int tLen = (int)(toff[tid + 1] - toff[tid]);
+        // ---- forward
+        for (int j = 0; j < L; j++) myHE[(size_t)j * 32u] = 0u;
+        int mx = 0, endDb = -1, endQ = L - 1;
+        for (int ti = 0; ti < tLen; ti++) {
+            const int8_t *row = sMat + t[ti] * 21;
+            int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
+            for (int j = 0; j < L; j++) {
+                const int s = row[q[j]] + c[j];
+                const uint32_t w = myHE[(size_t)j * 32u];
+                const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
+                int f = __viaddmax_s32(F, -gapE, hUp - gapO); f = f < 0 ? 0 : f;
+                const int h = sw_max3(hDiag + s, e, f);
+                hDiag = hPrev;
+                const int en = sw_max3(e - gapE, h - gapO, 0);
+                myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
+                F = f; hUp = h;
+                if (h > cm) { cm = h; jm = j; }
+            }
+            if (cm > mx) { mx = cm; endDb = ti; endQ = jm; }
+        }
+        cells += (unsigned long long)L * tLen;
+        SwTraceOut o; o.slot = slot; o.score = mx; o.qEnd = endQ; o.dbEnd = endDb; o.qStart = -1; o.dbStart = -1; o.flag = 0; o.pad = 0;
+        if (endDb >= 0) {
+            // ---- reverse: rows = query positions endQ, endQ-1, ... 0 ; columns = target positions endDb, endDb-1, ...
+            const int qn = endQ + 1;
+            for (int j = 0; j < qn; j++) myHE[(size_t)j * 32u] = 0u;
+            int rmx = 0, rDb = -1, rQ = qn - 1;
+            for (int ti = endDb; ti >= 0; ti--) {
+                const int8_t *row = sMat + t[ti] * 21;
+                int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
+                for (int j = 0; j < qn; j++) {
+                    const int qj = endQ - j;
+                    const int s = row[q[qj]] + c[qj];
+                    const uint32_t w = myHE[(size_t)j * 32u];
+                    const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
+                    int f = __viaddmax_s32(F, -gapE, hUp - gapO); f = f < 0 ? 0 : f;
+                    const int h = sw_max3(hDiag + s, e, f);
+                    hDiag = hPrev;
+                    const int en = sw_max3(e - gapE, h - gapO, 0);
+                    myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
+                    F = f; hUp = h;
+                    if (h > cm) { cm = h; jm = j; }
+                }
+                cells += (unsigned long long)qn;
+                if (cm > rmx) { rmx = cm; rDb = ti; rQ = jm; }
+                if (cm == mx) break;
+            }
+            o.dbStart = rDb; o.qStart = endQ - rQ;
+            if (rmx != mx) o.flag = 1;   // the reference EXITs on a forward/backward mismatch (StripedSmithWaterman.cpp:466-473)
+        }
+        if (mx >= 65000) o.flag |= 2;
+        outs[idx] = o;
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
+// exclusive scans over the prefilter result: pairOff[i] (natural query order) and chunkOff[p] (length-sorted order, 32 hits per chunk)
+__global__ void __launch_bounds__(MB_CTA_THREADS) k_scan_counts(const uint32_t *__restrict__ hitCount, const uint32_t *__restrict__ order, uint32_t nQ,
+                                                                uint32_t *pairOff, uint32_t *chunkOff) {
+    __shared__ CtaScratch cs;
+    if (blockIdx.x == 0) {
+        for (uint32_t i = threadIdx.x; i < nQ; i += blockDim.x) pairOff[i] = hitCount[i];
+        __syncthreads();
+        cta_exclusive_scan(pairOff, nQ, &cs);
+    } else {
+        for (uint32_t p = threadIdx.x; p < nQ; p += blockDim.x) chunkOff[p] = (hitCount[order[p]] + 31u) >> 5;
+        __syncthreads();
+        cta_exclusive_scan(chunkOff, nQ, &cs);
+    }
+}
+
+__global__ void k_compact_hits(const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint32_t *__restrict__ pairOff, uint32_t nQ,
+                               uint32_t maxHits, MbPrefHit *__restrict__ out) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nQ) return;
+    const uint32_t n = hitCount[q], b = pairOff[q];
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) out[b + k] = hits[(size_t)q * maxHits + k];
+}
+
+// caller-supplied hit lists -> the dense [query][maxHits] layout the SW kernels read
+__global__ void k_scatter_hits(const uint32_t *__restrict__ flatSeq, const uint64_t *__restrict__ hitOff, uint32_t nQ, uint32_t maxHits,
+                               MbPrefHit *__restrict__ hits, uint32_t *__restrict__ hitCount) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nQ) return;
+    const uint64_t b = hitOff[q]; const uint32_t n = (uint32_t)(hitOff[q + 1] - b);
+    if (threadIdx.x == 0) hitCount[q] = n;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { MbPrefHit h; h.seqId = flatSeq[b + k]; h.score = 0; h.diag = 0; hits[(size_t)q * maxHits + k] = h; }
+}

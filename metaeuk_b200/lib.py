@@ -48,7 +48,7 @@ def _gxx():
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
     srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
         [os.path.join(ROOT, "include", "metaeuk_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -188,12 +188,27 @@ class Context:
         return alns[:int(hit_off[-1])]
 
     def search(self, q, qoff):
+        """-> (accepted alignments as one flat array, uint64 offsets[n+1]); copies out of the context-owned buffer"""
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
         n = len(qoff) - 1
-        m = self.params.max_res_list_len
-        alns = np.zeros((n, m), dtype=ALN_DTYPE); cnt = np.zeros(n, np.uint32)
-        self._check(self.L.mb200_search(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(alns), _p(cnt)))
-        return alns, cnt
+        off = np.zeros(n + 1, np.uint64); ptr = C.c_void_p()
+        self._check(self.L.mb200_search(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(off), C.byref(ptr)))
+        tot = int(off[-1])
+        if tot == 0:
+            return np.zeros(0, ALN_DTYPE), off
+        buf = (C.c_char * (tot * ALN_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=ALN_DTYPE).copy(), off
+
+    def prefilter_compact(self, q, qoff):
+        q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
+        n = len(qoff) - 1
+        off = np.zeros(n + 1, np.uint64); ptr = C.c_void_p()
+        self._check(self.L.mb200_prefilter_compact(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(off), C.byref(ptr)))
+        tot = int(off[-1])
+        if tot == 0:
+            return np.zeros(0, HIT_DTYPE), off
+        buf = (C.c_char * (tot * HIT_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=HIT_DTYPE).copy(), off
 
     def chain(self, cands, cand_off, total_target_residues):
         cands = np.ascontiguousarray(cands, CAND_DTYPE); cand_off = np.ascontiguousarray(cand_off, np.uint64)

@@ -123,8 +123,8 @@ def align(ctx, queries, tdb, pref):
 def search(ctx, queries, tdb):
     """prefilter + align without the text round trip (blastp.sh:70,85)"""
     q, qoff = encode_many([s for _, s in queries])
-    alns, cnt = ctx.search(q, qoff)
-    return {k: _aln_lines(alns[i, :cnt[i]], tdb, len(s)) for i, (k, s) in enumerate(queries)}
+    alns, off = ctx.search(q, qoff)
+    return {k: _aln_lines(alns[int(off[i]):int(off[i + 1])], tdb, len(s)) for i, (k, s) in enumerate(queries)}
 
 
 def parse_orf_header(h):
