@@ -33,6 +33,7 @@ BG = BG / BG.sum()
 WORKLOADS = {
     "c2": dict(n_prot=50_000, n_frag=100_000, align=False, desc="C2: 100K fragments (~100 aa) x 50K proteins (~330 aa), prefilter-only"),
     "c3": dict(n_prot=500_000, n_frag=1_000_000, align=True, desc="C3: 1M fragments x 500K proteins, prefilter + gapped SW align"),
+    "c3s": dict(n_prot=500_000, n_frag=100_000, align=True, desc="C3/10: 100K fragments x 500K proteins, prefilter + gapped SW align (profiling size)"),
     "tiny": dict(n_prot=2_000, n_frag=4_000, align=True, desc="tiny: 4K fragments x 2K proteins (plumbing check)"),
 }
 

@@ -48,7 +48,7 @@ MB_DEV float mb_fmul(float a, float b) { return a * b; }
 MB_DEV float mb_fdiv(float a, float b) { return a / b; }
 #endif
 
-#define MB_CTA_THREADS 256
+#define MB_CTA_THREADS 512
 
 // Scratch every collective needs (lives in shared memory on the device).
 struct CtaScratch {

@@ -111,7 +111,7 @@ struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
-    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets; DevBuf<uint2> dEntries;
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
     DevBuf<int16_t> dSeedMat, dAlnMat; DevBuf<double> dSeedPB, dAlnPB; DevBuf<int8_t> dUng8;
     uint64_t nEntries = 0, totalRes = 0; uint32_t nT = 0; std::vector<uint64_t> hToff; bool haveIndex = false, haveSim3 = false;
@@ -163,7 +163,7 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
     CU(cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter, MB_CTA_THREADS, smemBytes));
     if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
-    if (perSM > 3) perSM = 3;
+    if (perSM > 2) perSM = 2;
     c->nCta = c->nSM * perSM;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((capK + 1) * 4) + al(capK * 4) + al(capK * 2) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
@@ -216,7 +216,7 @@ int mb200_ctx_create(int device, mb200_ctx **out) {
 void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
+    c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
@@ -265,12 +265,30 @@ static int upload_targets(mb200_ctx *c, const uint8_t *masked, const uint8_t *un
     c->hToff.assign(off, off + nT + 1); c->nT = nT; c->totalRes = tot; c->minScore.clear();
     return 0;
 }
+// bitmap of k-mers whose index list is non-empty: 8 MB, L2 resident; consulted before the random read of offsets[]
+__global__ void k_kmer_bits(const uint32_t *__restrict__ offsets, uint32_t nWords, uint32_t *__restrict__ bits) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nWords) return;
+    uint32_t m = 0;
+    for (uint32_t b = 0; b < 32; b++) { const uint32_t k = w * 32u + b; if (offsets[k + 1] != offsets[k]) m |= 1u << b; }
+    bits[w] = m;
+}
+static int build_kmer_bits(mb200_ctx *c) {
+    c->useBits = false;
+    if (c->nEntries >= mb200::KMER_TABLE) return 0;   // dense index: nearly every k-mer has a list, the extra lookup would not pay
+    const uint32_t nWords = (uint32_t)(mb200::KMER_TABLE / 32);
+    TRY(c->dKmerBits.alloc(nWords));
+    k_kmer_bits<<<(nWords + 255) / 256, 256, 0, c->stream>>>(c->dOffsets.p, nWords, c->dKmerBits.p);
+    CU(cudaGetLastError()); CU(cudaStreamSynchronize(c->stream));
+    c->useBits = true; return 0;
+}
 static int upload_index(mb200_ctx *c, const mb200::TargetIndex &idx) {
     TRY(c->dOffsets.alloc(idx.offsets.size())); TRY(c->dEntries.alloc(idx.entries.size()));
     TRY(upload(c->dOffsets.p, idx.offsets.data(), idx.offsets.size() * 4, c->stream));
     TRY(upload(c->dEntries.p, idx.entries.data(), idx.entries.size() * 8, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->nEntries = idx.entries.size(); c->haveIndex = true; return 0;
+    c->nEntries = idx.entries.size(); c->haveIndex = true;
+    return build_kmer_bits(c);
 }
 
 int mb200_index_build(mb200_ctx *c, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT) {
@@ -321,7 +339,8 @@ int mb200_index_commit(mb200_ctx *c) {
     CU(cudaSetDevice(c->device));
     c->hToff.resize(c->nT + 1);
     CU(cudaMemcpy(c->hToff.data(), c->dToff.p, (size_t)(c->nT + 1) * 8, cudaMemcpyDeviceToHost));
-    c->haveIndex = true; c->minScore.clear(); return 0;
+    c->haveIndex = true; c->minScore.clear();
+    return build_kmer_bits(c);
 }
 
 // ---- query upload + per-residue preparation ----------------------------------------------------------
@@ -365,7 +384,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream)); CU(cudaMemsetAsync(c->dStats.p, 0, sizeof(MbPrefStats), c->stream));
     CU(cudaMemsetAsync(c->dHitCount.p, 0, (size_t)(nQ + 1) * 4, c->stream)); CU(cudaMemsetAsync(c->dStatus.p, 0xFF, (size_t)(nQ + 1) * 4, c->stream));
     MbPrefTables T; memset(&T, 0, sizeof(T));
-    T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
+    T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
     T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
     T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM;
     if (nQ) {

@@ -18,7 +18,7 @@
 #define MB_N3 8000
 #define MB_CNT_MIN (-192)
 #define MB_CNT_W 384
-#define MB_NSLOT_LOG 18
+#define MB_NSLOT_LOG 17
 #define MB_NSLOT (1u << MB_NSLOT_LOG)
 
 // hit / candidate word:  seqId[27] | arrival[21] | diag16[16]
@@ -36,6 +36,7 @@ struct MbPrefTables {
     const uint32_t *sim3;      // [8000][8000]  (neighbour 3-mer index << 16) | (uint16)score, descending score, reference order
     const uint16_t *cnt3;      // [8000][MB_CNT_W]  #neighbours with score >= (x + MB_CNT_MIN)
     const uint32_t *offsets;   // [20^6 + 1]
+    const uint32_t *kmerBits;  // optional [20^6 / 32] bitmap of k-mers with a non-empty list (L2 resident), or NULL
     const uint2 *entries;      // (seqId, pos_j)
     const uint8_t *tseq;       // masked target residues
     const uint64_t *toff;      // [nT + 1]
@@ -57,13 +58,36 @@ struct MbPrefScratch {        // per-CTA global scratch
     int32_t *S;            // capM
 };
 
+// shared-memory homes of the expansion arrays (queries that exceed them use the global scratch instead)
+#define MB_SM_P 512
+#define MB_SM_I 4096
+#define MB_SM_K 8192
+#define MB_SM_S 1024
+
 struct MbPrefShared {
     CtaScratch cs;
     uint32_t hist[256];
     uint32_t cnt[8];       // 0 nMulti, 1 nCand, 2 nSurv, 3 thr, 4 nPass, 5 rescale, 6 status
     int8_t ungMat[448];
     uint32_t slots[MB_NSLOT / 16];
+    uint32_t sItemOff[MB_SM_P + 1]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P];
+    uint32_t sKmerOff[MB_SM_I + 1];
+    uint32_t sHitOff[MB_SM_K + 1];
+    uint64_t sSort[MB_SM_S];
 };
+
+// sort a (usually short) global list: through shared memory when it fits
+MB_DEV void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
+    if (n <= MB_SM_S) {
+        CTA_FOR(i, n) sh->sSort[i] = g[i];
+        CTA_SYNC();
+        cta_sort_u64(sh->sSort, n);
+        CTA_FOR(i, n) g[i] = sh->sSort[i];
+        CTA_SYNC();
+    } else {
+        cta_sort_u64(g, n);
+    }
+}
 
 struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; };
 
@@ -103,6 +127,10 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
     if (P == 0) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OK; } return; }
 
+    uint32_t *const itemOff = (P <= MB_SM_P) ? sh->sItemOff : W.itemOff;
+    int16_t *const wThr = (P <= MB_SM_P) ? sh->sThr : W.wThr;
+    uint16_t *const wI0 = (P <= MB_SM_P) ? sh->sI0 : W.wI0;
+    uint16_t *const wI1 = (P <= MB_SM_P) ? sh->sI1 : W.wI1;
     // ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140)
     CTA_FOR(p, P) {
         const uint8_t *w = q + p;
@@ -120,44 +148,47 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
             const short cutoff1 = (short)(thr - top1);
             n0 = mb_count_ge(T.cnt3, i0, cutoff1);
         }
-        W.itemOff[p] = n0; W.wThr[p] = (int16_t)thr; W.wI0[p] = (uint16_t)i0; W.wI1[p] = (uint16_t)i1;
+        itemOff[p] = n0; wThr[p] = (int16_t)thr; wI0[p] = (uint16_t)i0; wI1[p] = (uint16_t)i1;
     }
     CTA_SYNC();
-    const uint32_t I = cta_exclusive_scan(W.itemOff, P, &sh->cs);
+    const uint32_t I = cta_exclusive_scan(itemOff, P, &sh->cs);
     if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
     // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216)
+    uint32_t *const kmerOff = (I <= MB_SM_I) ? sh->sKmerOff : W.kmerOff;
     CTA_FOR(it, I) {
-        const uint32_t p = cta_find_segment(W.itemOff, P, it);
-        const uint32_t i = it - W.itemOff[p];
-        const int s0 = (int16_t)(T.sim3[(size_t)W.wI0[p] * MB_N3 + i] & 0xFFFFu);
-        const short cutoff2 = (short)((int)W.wThr[p] - s0);
-        W.kmerOff[it] = mb_count_ge(T.cnt3, W.wI1[p], cutoff2);
+        const uint32_t p = cta_find_segment(itemOff, P, it);
+        const uint32_t i = it - itemOff[p];
+        const int s0 = (int16_t)(T.sim3[(size_t)wI0[p] * MB_N3 + i] & 0xFFFFu);
+        const short cutoff2 = (short)((int)wThr[p] - s0);
+        kmerOff[it] = mb_count_ge(T.cnt3, wI1[p], cutoff2);
         W.itemInfo[it] = (p << 13) | i;
     }
     CTA_SYNC();
-    const uint32_t K = cta_exclusive_scan(W.kmerOff, I, &sh->cs);
+    const uint32_t K = cta_exclusive_scan(kmerOff, I, &sh->cs);
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
     // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
+    uint32_t *const hitOff = (K <= MB_SM_K) ? sh->sHitOff : W.hitOff;
     CTA_FOR(k, K) {
-        const uint32_t it = cta_find_segment(W.kmerOff, I, k);
-        const uint32_t j = k - W.kmerOff[it];
+        const uint32_t it = cta_find_segment(kmerOff, I, k);
+        const uint32_t j = k - kmerOff[it];
         const uint32_t info = W.itemInfo[it]; const uint32_t p = info >> 13, i = info & 0x1FFFu;
-        const uint32_t k0 = T.sim3[(size_t)W.wI0[p] * MB_N3 + i] >> 16;
-        const uint32_t k1 = T.sim3[(size_t)W.wI1[p] * MB_N3 + j] >> 16;
+        const uint32_t k0 = T.sim3[(size_t)wI0[p] * MB_N3 + i] >> 16;
+        const uint32_t k1 = T.sim3[(size_t)wI1[p] * MB_N3 + j] >> 16;
         const uint32_t kmer = k0 + k1 * 8000u;
-        const uint32_t lo = T.offsets[kmer], hi = T.offsets[kmer + 1];
-        W.hitOff[k] = hi - lo; W.kmerLo[k] = lo; W.kmerP[k] = (uint16_t)p;
+        uint32_t lo = 0, hi = 0;
+        if (!T.kmerBits || ((T.kmerBits[kmer >> 5] >> (kmer & 31u)) & 1u)) { lo = T.offsets[kmer]; hi = T.offsets[kmer + 1]; }
+        hitOff[k] = hi - lo; W.kmerLo[k] = lo; W.kmerP[k] = (uint16_t)p;
     }
     CTA_SYNC();
-    const uint32_t M = cta_exclusive_scan(W.hitOff, K, &sh->cs);
+    const uint32_t M = cta_exclusive_scan(hitOff, K, &sh->cs);
     if (M > T.capM || M >= (1u << MB_MAX_ARRIVAL_BITS)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
     // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
     CTA_FOR(h, M) {
-        const uint32_t k = cta_find_segment(W.hitOff, K, h);
-        const uint2 e = T.entries[(size_t)W.kmerLo[k] + (h - W.hitOff[k])];
+        const uint32_t k = cta_find_segment(hitOff, K, h);
+        const uint2 e = T.entries[(size_t)W.kmerLo[k] + (h - hitOff[k])];
         const uint16_t diag16 = (uint16_t)((uint32_t)W.kmerP[k] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
         W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
         const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
@@ -176,7 +207,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     CTA_SYNC();
     const uint32_t nMulti = sh->cnt[0];
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
-    cta_sort_u64(W.B, nMulti);
+    mb_sort_list(W.B, nMulti, sh);
     CTA_FOR(e, nMulti) {
         const uint32_t id = MB_W_SEQ(W.B[e]);
         if (e == 0 || MB_W_SEQ(W.B[e - 1]) != id) {
@@ -194,7 +225,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     CTA_SYNC();
     const uint32_t D = sh->cnt[1];
     // ---- P8/P9 ungapped diagonal scores
-    cta_sort_u64(W.C, D);
+    mb_sort_list(W.C, D, sh);
     uint32_t myCells = 0;
     CTA_FOR(c, D) {
         const uint64_t w = W.C[c]; const uint32_t id = MB_W_SEQ(w);
@@ -233,7 +264,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
         sh->cnt[3] = thr; sh->cnt[4] = nPass;
     }
     // ---- P12 stable order of the reference's counting sort: score desc, then bin (seqId & (BINSIZE-1)), then arrival
-    cta_sort_u64(W.B, nSurv);
+    mb_sort_list(W.B, nSurv, sh);
     const uint32_t thr = sh->cnt[3];
     uint32_t nPass = sh->cnt[4];
     const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
@@ -258,7 +289,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
         CTA_SYNC();
         CTA_FOR(i, nPass) W.B[i] = W.A[i];
         CTA_SYNC();
-        cta_sort_u64(W.B, nPass);
+        mb_sort_list(W.B, nPass, sh);
     }
     const uint32_t nSel = nPass < maxHits ? nPass : maxHits;
     // ---- P13 getResult<UNGAPPED_DIAGONAL_SCORE> (QueryMatcher.cpp:363-420): exact score when the 8-bit score saturated
@@ -273,7 +304,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     CTA_SYNC();
     // ---- P14 final order: score desc, seqId asc (hit_t::compareHitsByScoreAndId, QueryMatcher.h:38-48)
-    cta_sort_u64(W.A, nSel);
+    mb_sort_list(W.A, nSel, sh);
     CTA_FOR(i, nSel) {
         const uint64_t w = W.A[i];
         MbPrefHit hres; hres.seqId = (uint32_t)((w >> 16) & 0x7FFFFFFu); hres.score = (int32_t)(0xFFFFFu - (uint32_t)(w >> 43)); hres.diag = (int16_t)(w & 0xFFFFu);

@@ -50,6 +50,9 @@ int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, cons
     mb200::TargetIndex idx;
     if (mb200::build_index(masked, toff, nT, m.seed, kmerThr, idx)) return -1;
     MbPrefTables T; memset(&T, 0, sizeof(T));
+    std::vector<uint32_t> bits(mb200::KMER_TABLE / 32, 0);   // same bitmap k_kmer_bits builds on the device
+    for (size_t k = 0; k < mb200::KMER_TABLE; k++) if (idx.offsets[k + 1] != idx.offsets[k]) bits[k >> 5] |= 1u << (k & 31);
+    T.kmerBits = bits.data();
     T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
     T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
     T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
