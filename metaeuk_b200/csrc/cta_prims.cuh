@@ -17,6 +17,9 @@
 #define CTA_FOR(i, n) for (uint32_t i = threadIdx.x, i##_end = (uint32_t)(n); i < i##_end; i += blockDim.x)
 #define CTA_SYNC() __syncthreads()
 #define CTA_SINGLE if (threadIdx.x == 0)
+// one warp per work item / contiguous chunk of a range per thread
+#define CTA_WARP_FOR(i, n) for (uint32_t i = threadIdx.x >> 5, i##_end = (uint32_t)(n); i < i##_end; i += blockDim.x >> 5)
+#define CTA_CHUNK(b, e, n) uint32_t b, e; { const uint32_t n_ = (uint32_t)(n), c_ = (n_ + blockDim.x - 1) / blockDim.x; b = threadIdx.x * c_; if (b > n_) b = n_; e = b + c_; if (e > n_) e = n_; }
 MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
@@ -35,6 +38,8 @@ MB_DEV float mb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 #define CTA_FOR(i, n) for (uint32_t i = 0, i##_end = (uint32_t)(n); i < i##_end; i++)
 #define CTA_SYNC() ((void)0)
 #define CTA_SINGLE if (true)
+#define CTA_WARP_FOR(i, n) for (uint32_t i = 0, i##_end = (uint32_t)(n); i < i##_end; i++)
+#define CTA_CHUNK(b, e, n) uint32_t b = 0, e = (uint32_t)(n);
 #include <algorithm>
 struct uint2 { unsigned int x, y; };
 MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
@@ -60,28 +65,30 @@ struct CtaScratch {
 // a may live in shared or global memory.
 MB_DEV uint32_t cta_exclusive_scan(uint32_t *a, uint32_t n, CtaScratch *s) {
 #if MB_DEVICE_BUILD
-    const uint32_t T = blockDim.x, tid = threadIdx.x;
-    const uint32_t chunk = (n + T - 1) / T;
-    uint32_t begin = tid * chunk; if (begin > n) begin = n;
-    uint32_t end = begin + chunk; if (end > n) end = n;
-    uint32_t sum = 0;
-    for (uint32_t i = begin; i < end; i++) sum += a[i];
-    s->part[tid] = sum;
-    __syncthreads();
-    if (tid < 32) {   // warp 0 scans the T partial sums, T/32 consecutive partials per lane
-        const uint32_t per = T / 32;
-        uint32_t loc = 0;
-        for (uint32_t k = 0; k < per; k++) loc += s->part[tid * per + k];
-        uint32_t inc = loc;
-        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)tid >= d) inc += y; }
-        uint32_t run = inc - loc;
-        for (uint32_t k = 0; k < per; k++) { uint32_t v = s->part[tid * per + k]; s->part[tid * per + k] = run; run += v; }
-        if (tid == 31) s->part[T] = run;
+    // every warp owns one contiguous range and sweeps it 32 elements at a time (coalesced, shuffle scans, no block barrier
+    // inside the sweep); one barrier to exchange warp totals; a second sweep adds the warp's prefix.
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nW = blockDim.x >> 5;
+    const uint32_t per = ((n + nW - 1) / nW + 31u) & ~31u;
+    uint32_t rb = wid * per; if (rb > n) rb = n;
+    uint32_t re = rb + per; if (re > n) re = n;
+    uint32_t carry = 0;
+    for (uint32_t base = rb; base < re; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = (i < re) ? a[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
+        if (i < re) a[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
+    if (lane == 0) s->part[wid] = carry;
     __syncthreads();
-    uint32_t run = s->part[tid];
-    for (uint32_t i = begin; i < end; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
-    const uint32_t total = s->part[T];
+    uint32_t wt = (lane < nW) ? s->part[lane] : 0u, winc = wt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d); if ((int)lane >= d) winc += y; }
+    const uint32_t myPrefix = __shfl_sync(0xffffffffu, winc - wt, wid);
+    const uint32_t total = __shfl_sync(0xffffffffu, winc, nW - 1);
+    if (myPrefix) for (uint32_t i = rb + lane; i < re; i += 32) a[i] += myPrefix;
     if (tid == 0) a[n] = total;
     __syncthreads();
     return total;
@@ -108,9 +115,25 @@ MB_DEV uint32_t mb_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1
 MB_DEV void cta_sort_u64(uint64_t *a, uint32_t n) {
 #if MB_DEVICE_BUILD
     const uint32_t n2 = mb_next_pow2(n);
+    if (n2 <= 32) {   // short lists: one warp, keys in registers, compare-exchange through shuffles, a single block barrier
+        if (threadIdx.x < 32) {
+            const uint32_t lane = threadIdx.x;
+            uint64_t key = (lane < n) ? a[lane] : ~0ull;
+            for (uint32_t k = 2; k <= 32; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool asc = ((lane & k) == 0), lower = ((lane & j) == 0);
+                    const uint64_t mn = key < other ? key : other, mx = key < other ? other : key;
+                    key = (asc == lower) ? mn : mx;
+                }
+            }
+            if (lane < n) a[lane] = key;
+        }
+        __syncthreads();
+        return;
+    }
     for (uint32_t i = n + threadIdx.x; i < n2; i += blockDim.x) a[i] = ~0ull;
     __syncthreads();
-    if (n2 < 2) return;
     for (uint32_t k = 2; k <= n2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {

@@ -116,6 +116,42 @@ MB_DEV int mb_diag_score(const int8_t *ungMat, const uint8_t *q, const int8_t *c
     return mx;
 }
 
+#if MB_DEVICE_BUILD
+// The same recurrence evaluated by a whole warp: every lane folds a contiguous piece of the diagonal into the transfer
+// function of "running sum clamped at 0" -- (S, R, P, B): out(x) = max(x + S, R), best(x) = max(x + P, B) -- and the pieces are
+// combined left to right with the associative rule  S = Sa+Sb, R = max(Ra+Sb, Rb), P = max(Pa, Sa+Pb), B = max(Ba, Ra+Pb, Bb).
+__device__ __forceinline__ int mb_diag_score_warp(const int8_t *ungMat, const uint8_t *q, const int8_t *corr, uint32_t L, const uint8_t *t, uint32_t tLen,
+                                                  uint16_t diag16, uint32_t *cells) {
+    const int diagonal = (int16_t)diag16;
+    const uint16_t d1 = (uint16_t)(0 - diag16), d2 = diag16;
+    const uint32_t dist = d1 < d2 ? d1 : d2;
+    uint32_t n, qo, to;
+    if (diagonal >= 0 && dist < L) { n = (tLen < L - dist) ? tLen : (L - dist); qo = dist; to = 0; }
+    else if (diagonal < 0 && dist < tLen) { n = (tLen - dist < L) ? (tLen - dist) : L; qo = 0; to = dist; }
+    else { *cells = 0; return 0; }
+    const uint32_t lane = threadIdx.x & 31u, chunk = (n + 31u) >> 5;
+    uint32_t b = lane * chunk; if (b > n) b = n;
+    uint32_t e = b + chunk; if (e > n) e = n;
+    const int NEG = -(1 << 28);
+    int S = 0, R = 0, P = NEG, B = 0;
+    for (uint32_t pos = b; pos < e; pos++) {
+        const int v = (int8_t)(ungMat[q[qo + pos] * MB_AL + t[to + pos]] + corr[qo + pos]);
+        S += v; R += v; R = R < 0 ? 0 : R; P = S > P ? S : P; B = R > B ? R : B;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int Sb = __shfl_down_sync(0xffffffffu, S, d), Rb = __shfl_down_sync(0xffffffffu, R, d);
+        const int Pb = __shfl_down_sync(0xffffffffu, P, d), Bb = __shfl_down_sync(0xffffffffu, B, d);
+        if ((lane & (2 * d - 1)) == 0) {
+            const int nB = max(max(B, R + Pb), Bb), nP = max(P, S + Pb), nR = max(R + Sb, Rb);
+            B = nB; P = nP < NEG ? NEG : nP; R = nR; S += Sb;
+        }
+    }
+    *cells = n;
+    return __shfl_sync(0xffffffffu, B, 0);
+}
+#endif
+
 // One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
 MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
                                const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
@@ -170,8 +206,10 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
 
     // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
     uint32_t *const hitOff = (K <= MB_SM_K) ? sh->sHitOff : W.hitOff;
-    CTA_FOR(k, K) {
-        const uint32_t it = cta_find_segment(kmerOff, I, k);
+    CTA_CHUNK(kb, ke, K);
+    uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;   // one search per contiguous chunk, then walk forward
+    for (uint32_t k = kb; k < ke; k++) {
+        while (kmerOff[it + 1] <= k) it++;
         const uint32_t j = k - kmerOff[it];
         const uint32_t info = W.itemInfo[it]; const uint32_t p = info >> 13, i = info & 0x1FFFu;
         const uint32_t k0 = T.sim3[(size_t)wI0[p] * MB_N3 + i] >> 16;
@@ -186,8 +224,11 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     if (M > T.capM || M >= (1u << MB_MAX_ARRIVAL_BITS)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
     // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
-    CTA_FOR(h, M) {
-        const uint32_t k = cta_find_segment(hitOff, K, h);
+    CTA_CHUNK(hb, he, M);
+    uint32_t kk = (hb < he) ? cta_find_segment(hitOff, K, hb) : 0;
+    for (uint32_t h = hb; h < he; h++) {
+        while (hitOff[kk + 1] <= h) kk++;
+        const uint32_t k = kk;
         const uint2 e = T.entries[(size_t)W.kmerLo[k] + (h - hitOff[k])];
         const uint16_t diag16 = (uint16_t)((uint32_t)W.kmerP[k] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
         W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
@@ -227,12 +268,17 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     // ---- P8/P9 ungapped diagonal scores
     mb_sort_list(W.C, D, sh);
     uint32_t myCells = 0;
-    CTA_FOR(c, D) {
+    CTA_WARP_FOR(c, D) {   // one warp per candidate diagonal
         const uint64_t w = W.C[c]; const uint32_t id = MB_W_SEQ(w);
         const uint64_t to = T.toff[id]; const uint32_t tLen = (uint32_t)(T.toff[id + 1] - to);
         uint32_t cells;
+#if MB_DEVICE_BUILD
+        const int sc = mb_diag_score_warp(sh->ungMat, q, corr, L, T.tseq + to, tLen, MB_W_DIAG(w), &cells);
+        if ((threadIdx.x & 31u) == 0) { W.S[c] = sc; myCells += cells; }
+#else
         W.S[c] = mb_diag_score(sh->ungMat, q, corr, L, T.tseq + to, tLen, MB_W_DIAG(w), &cells);
         myCells += cells;
+#endif
     }
     CTA_SYNC();
     // ---- P10 best diagonal per target: first maximum in arrival order (keepMaxElement, CacheFriendlyOperations.cpp:350-380)
