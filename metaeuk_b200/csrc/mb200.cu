@@ -124,7 +124,7 @@ struct mb200_ctx {
     bool havePref = false;
     // align
     DevBuf<uint32_t> dPairOff, dChunkOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
-    DevBuf<uint64_t> dHitOff64;
+    DevBuf<uint64_t> dHitOff64; DevBuf<uint16_t> dPerm;
     std::vector<int> minScore;   // per query length, -2 = not computed
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
@@ -220,7 +220,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
-    c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release();
+    c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -444,6 +444,12 @@ static int align_pipeline(mb200_ctx *c) {
     }
     TRY(c->dMinScore.alloc(ms.size())); TRY(upload(c->dMinScore.p, ms.data(), ms.size() * 4, c->stream));
     TRY(c->dScore.alloc((size_t)nQ * maxHits)); TRY(c->dPassList.alloc(nPairs));
+    const bool usePerm = maxHits <= 1024;
+    if (usePerm) {
+        TRY(c->dPerm.alloc((size_t)nQ * maxHits));
+        k_perm_by_len<<<c->nSM * 8, 128, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dToff.p, nQ, maxHits, c->dPerm.p);
+        CU(cudaGetLastError()); c->st.launches++;
+    }
     uint32_t *dNPass = c->dCounter.p + 32, *dErr = c->dCounter.p + 33;
     // length classes over the length-sorted query order (descending): one launch per class, shared-memory state sized to the class
     static const uint32_t classPad[] = {32, 64, 96, 128, 160, 192, 224, 256, 384, 512, 768, 1024};
@@ -462,7 +468,7 @@ static int align_pipeline(mb200_ctx *c) {
         const size_t smem = (size_t)W * Lpad * 33u * 4u;
         CU(cudaFuncSetAttribute(k_sw_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_score<4>, W * 32, smem)); if (perSM < 1) perSM = 1;
-        k_sw_score<4><<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p,
+        k_sw_score<4><<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p,
                                                                   c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend, Lpad, c->dMinScore.p, c->dScore.p,
                                                                   c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr);
         CU(cudaGetLastError()); c->st.launches++;

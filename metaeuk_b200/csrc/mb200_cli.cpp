@@ -1,0 +1,293 @@
+// mb200_cli.cpp -- C++ host driver with MetaEuk's module surface over libmetaeuk_b200 (C ABI only).
+//
+//   mb200 gpuprefilter         <queryDB> <targetDB> <prefDB>            == prefilter          (M/src/prefiltering/Main.cpp:13)
+//   mb200 gpualign             <queryDB> <targetDB> <prefDB> <alnDB>    == align              (M/src/alignment/Main.cpp:12)
+//   mb200 gpusearch            <queryDB> <targetDB> <alnDB>             == search (blastp.sh:70,85 without the pref DB round trip)
+//   mb200 gpuresultspercontig  <contigsDB> <orfDB> <alnDB> <byContigDB> == resultspercontig   (src/exonpredictor/resultspercontig.cpp:34)
+//   mb200 gpucollectoptimalset <byContigDB> <targetDB> <predDB>         == collectoptimalset  (src/exonpredictor/collectoptimalset.cpp:224)
+//   mb200 gpupredictexons      <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>
+//                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
+// DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
+// Result DBs are written byte-compatible with the reference's (same records, same keys; one data file).
+// Options: --max-seqs N  --min-ungapped-score N  --k-score N  -e X  --min-aln-len N  --masked-db <db> (target residues after the
+// reference's tantan masking, lower case or X = masked; without it targets are used unmasked = --mask 0)  --metaeuk-eval X
+// --metaeuk-tcov X --max-intron N --min-intron N --min-exon-aa N --max-overlap N --max-exon-sets N --set-gap-open N --set-gap-extend N
+// --device N.  Everything numeric happens in the library (GPU); this file is DB I/O and the reference's text formatting.
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/metaeuk_b200.h"
+
+#define DIE(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); exit(EXIT_FAILURE); } while (0)
+#define MB(x) do { if ((x) != MB200_OK) DIE("mb200: %s", mb200_last_error()); } while (0)
+
+// ---------------------------------------------------------------- MMseqs DB I/O
+struct Db {
+    std::vector<char> data; std::vector<uint32_t> keys; std::vector<uint64_t> off, len;   // entries in data-offset order (= local id)
+    int dbtype = 0;
+    std::map<uint32_t, size_t> byKey;
+    const char *entry(size_t id) const { return data.data() + off[id]; }
+    size_t find(uint32_t key) const { auto it = byKey.find(key); return it == byKey.end() ? (size_t)-1 : it->second; }
+};
+static bool readFile(const std::string &p, std::vector<char> &out, bool append) {
+    FILE *f = fopen(p.c_str(), "rb"); if (!f) return false;
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    size_t o = append ? out.size() : 0; out.resize(o + n);
+    if (n && fread(out.data() + o, 1, n, f) != (size_t)n) DIE("short read on %s", p.c_str());
+    fclose(f); return true;
+}
+static Db openDb(const std::string &name) {
+    Db d;
+    if (!readFile(name, d.data, false)) {   // split data files name.0, name.1, ... concatenated in order (DBReader)
+        int i = 0; bool any = false;
+        while (readFile(name + "." + std::to_string(i), d.data, true)) { any = true; i++; }
+        if (!any) DIE("cannot open database %s", name.c_str());
+    }
+    std::vector<char> idx; if (!readFile(name + ".index", idx, false)) DIE("cannot open %s.index", name.c_str());
+    struct E { uint64_t off, len; uint32_t key; };
+    std::vector<E> es;
+    const char *p = idx.data(), *end = p + idx.size();
+    while (p < end) {
+        char *q; E e; e.key = (uint32_t)strtoul(p, &q, 10); e.off = strtoull(q, &q, 10); e.len = strtoull(q, &q, 10);
+        es.push_back(e); while (q < end && *q != '\n') q++; p = q + 1;
+    }
+    std::stable_sort(es.begin(), es.end(), [](const E &a, const E &b) { return a.off < b.off; });
+    for (auto &e : es) { d.byKey[e.key] = d.keys.size(); d.keys.push_back(e.key); d.off.push_back(e.off); d.len.push_back(e.len); }
+    std::vector<char> t; if (readFile(name + ".dbtype", t, false) && t.size() >= 4) memcpy(&d.dbtype, t.data(), 4);
+    return d;
+}
+struct DbOut {
+    FILE *f, *fi; uint64_t pos = 0; std::string name;
+    DbOut(const std::string &n, int dbtype) : name(n) {
+        f = fopen(n.c_str(), "wb"); fi = fopen((n + ".index").c_str(), "wb"); if (!f || !fi) DIE("cannot write %s", n.c_str());
+        FILE *t = fopen((n + ".dbtype").c_str(), "wb"); fwrite(&dbtype, 4, 1, t); fclose(t);
+    }
+    void write(uint32_t key, const std::string &s) { fwrite(s.data(), 1, s.size(), f); fputc('\0', f); fprintf(fi, "%u\t%llu\t%zu\n", key, (unsigned long long)pos, s.size() + 1); pos += s.size() + 1; }
+    ~DbOut() { fclose(f); fclose(fi); }
+};
+
+// ---------------------------------------------------------------- residue codes (SubstitutionMatrix::setupLetterMapping, SubstitutionMatrix.cpp:262-304)
+static uint8_t AA2NUM[256];
+static void initCodes() {
+    const char *order = "ACDEFGHIKLMNPQRSTVWYX";
+    for (int i = 0; i < 256; i++) AA2NUM[i] = 20;
+    for (int i = 0; order[i]; i++) { AA2NUM[(int)order[i]] = i; AA2NUM[tolower(order[i])] = i; }
+    const char *al[3][2] = {{"J", "L"}, {"Z", "E"}, {"B", "D"}};
+    for (auto &a : al) { AA2NUM[(int)a[0][0]] = AA2NUM[(int)a[1][0]]; AA2NUM[tolower(a[0][0])] = AA2NUM[(int)a[1][0]]; }
+}
+struct Seqs { std::vector<uint8_t> res; std::vector<uint64_t> off; };
+static Seqs encodeDb(const Db &d, bool lowerIsMasked) {
+    Seqs s; s.off.push_back(0);
+    for (size_t i = 0; i < d.keys.size(); i++) {
+        const char *e = d.entry(i); size_t n = d.len[i] >= 2 ? d.len[i] - 2 : 0;   // "residues\n\0" (DBReader.h:211-231)
+        for (size_t k = 0; k < n; k++) s.res.push_back((lowerIsMasked && islower((unsigned char)e[k])) ? 20 : AA2NUM[(unsigned char)e[k]]);
+        s.off.push_back(s.res.size());
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------- the reference's text formatting
+static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdToBuffer (Util.cpp:222-251); resultToBuffer overwrites the last 0 of "1.000"
+    char b[32];
+    if (x == 1.0f) return dropLastZero ? "1.00" : "1.000";
+    std::string s = "0."; if (x < 0.10) s += "0"; if (x < 0.01) s += "0";
+    snprintf(b, sizeof(b), "%d", (int)(x * 1000)); return s + b;
+}
+static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
+
+struct Opt {
+    mb200_params p; std::string maskedDb; int device = 0;
+};
+static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
+    Opt o; mb200_params_default(&o.p);
+    for (int i = first; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() { if (i + 1 >= argc) DIE("missing value for %s", a.c_str()); return std::string(argv[++i]); };
+        if (a == "--max-seqs") o.p.max_res_list_len = atoi(val().c_str());
+        else if (a == "--min-ungapped-score") o.p.min_diag_score = atoi(val().c_str());
+        else if (a == "--k-score") o.p.kmer_thr = atoi(val().c_str());
+        else if (a == "-e") o.p.eval_thr = atof(val().c_str());
+        else if (a == "--min-aln-len") o.p.min_aln_len = atoi(val().c_str());
+        else if (a == "--masked-db") o.maskedDb = val();
+        else if (a == "--metaeuk-eval") o.p.metaeuk_eval = atof(val().c_str());
+        else if (a == "--metaeuk-tcov") o.p.tcov = atof(val().c_str());
+        else if (a == "--max-intron") o.p.max_intron = atoi(val().c_str());
+        else if (a == "--min-intron") o.p.min_intron = atoi(val().c_str());
+        else if (a == "--min-exon-aa") o.p.min_exon_aa = atoi(val().c_str());
+        else if (a == "--max-overlap") o.p.max_overlap = atoi(val().c_str());
+        else if (a == "--max-exon-sets") o.p.max_exon_sets = atoi(val().c_str());
+        else if (a == "--set-gap-open") o.p.set_gap_open = atoi(val().c_str());
+        else if (a == "--set-gap-extend") o.p.set_gap_extend = atoi(val().c_str());
+        else if (a == "--device") o.device = atoi(val().c_str());
+        else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
+        else pos.push_back(a);
+    }
+    return o;
+}
+
+struct Session {
+    mb200_ctx *ctx = nullptr; Db tdb; Seqs t; std::vector<uint64_t> tlen;
+    void open(const Opt &o, const std::string &targetDb) {
+        MB(mb200_ctx_create(o.device, &ctx)); MB(mb200_params_set(ctx, &o.p)); MB(mb200_matrices_default(ctx));
+        tdb = openDb(targetDb); t = encodeDb(tdb, false);
+        Seqs m = t;
+        if (!o.maskedDb.empty()) {
+            Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
+            for (size_t i = 0; i < tdb.keys.size(); i++) {   // align by key
+                size_t j = md.find(tdb.keys[i]); if (j == (size_t)-1 || raw.off[j + 1] - raw.off[j] != t.off[i + 1] - t.off[i]) DIE("masked DB does not match target DB at key %u", tdb.keys[i]);
+                memcpy(&m.res[t.off[i]], &raw.res[raw.off[j]], t.off[i + 1] - t.off[i]);
+            }
+        }
+        MB(mb200_index_build(ctx, m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size()));
+        for (size_t i = 0; i < tdb.keys.size(); i++) tlen.push_back(t.off[i + 1] - t.off[i]);
+    }
+    ~Session() { if (ctx) mb200_ctx_destroy(ctx); }
+};
+
+static std::string prefEntry(const Session &s, const mb200_hit *h, uint64_t n) {   // QueryMatcher::prefilterHitToBuffer (QueryMatcher.h:118-130)
+    std::string e; char b[64];
+    for (uint64_t k = 0; k < n; k++) { snprintf(b, sizeof(b), "%u\t%d\t%d\n", s.tdb.keys[h[k].seq_id], h[k].score, h[k].diag); e += b; }
+    return e;
+}
+static std::string alnEntry(const Session &s, std::vector<mb200_aln> v, uint32_t qLen) {   // Matcher::compareHits + resultToBuffer (Matcher.h:157-168, Matcher.cpp:280-327)
+    v.erase(std::remove_if(v.begin(), v.end(), [](const mb200_aln &a) { return !a.passed; }), v.end());
+    std::sort(v.begin(), v.end(), [&](const mb200_aln &a, const mb200_aln &b) {
+        if (a.evalue != b.evalue) return a.evalue < b.evalue; if (a.bit_score != b.bit_score) return a.bit_score > b.bit_score;
+        if (s.tlen[a.seq_id] != s.tlen[b.seq_id]) return s.tlen[a.seq_id] < s.tlen[b.seq_id]; return s.tdb.keys[a.seq_id] < s.tdb.keys[b.seq_id]; });
+    std::string e; char b[256];
+    for (auto &a : v) {
+        snprintf(b, sizeof(b), "%u\t%d\t%s\t%s\t%d\t%d\t%u\t%d\t%d\t%llu\n", s.tdb.keys[a.seq_id], a.bit_score, fmtSeqId(a.seq_id_est, true).c_str(), fmtE(a.evalue).c_str(),
+                 a.q_start, a.q_end, qLen, a.db_start, a.db_end, (unsigned long long)s.tlen[a.seq_id]);
+        e += b;
+    }
+    return e;
+}
+
+static std::vector<std::string> splitTab(const std::string &l) { std::vector<std::string> w; size_t a = 0; for (;;) { size_t b = l.find('\t', a); if (b == std::string::npos) { w.push_back(l.substr(a)); break; } w.push_back(l.substr(a, b - a)); a = b + 1; } return w; }
+static std::vector<std::string> lines(const char *p) { std::vector<std::string> v; while (*p) { const char *q = strchr(p, '\n'); if (!q) { v.push_back(p); break; } v.push_back(std::string(p, q - p)); p = q + 1; } return v; }
+
+// resultspercontig (resultspercontig.cpp:64-196): ORF header "contigKey\tfrom+len" / "from-len" (Orf::parseOrfHeader, Orf.cpp:351-438)
+static std::map<uint32_t, std::string> byContig(const Db &contigs, const Db &orfHeaders, const std::map<uint32_t, std::string> &aln) {
+    struct Row { uint32_t t, orf; std::string line; };
+    std::map<uint32_t, std::vector<Row>> per;
+    for (size_t i = 0; i < contigs.keys.size(); i++) per[contigs.keys[i]];
+    for (auto &kv : aln) {
+        if (kv.second.empty()) continue;
+        size_t h = orfHeaders.find(kv.first); if (h == (size_t)-1) continue;
+        std::string hdr(orfHeaders.entry(h)); char *q; uint32_t contig = (uint32_t)strtoul(hdr.c_str(), &q, 10);
+        long from = strtol(q, &q, 10); char sign = *q; long len = strtol(q + 1, &q, 10); long to = sign == '+' ? from + len : from - len;
+        size_t c = contigs.find(contig); if (c == (size_t)-1) continue;
+        long orfLen = std::max(from, to) - std::min(from, to) + 1; unsigned long long contigLen = contigs.len[c] >= 2 ? contigs.len[c] - 2 : 0;
+        for (auto &l : lines(kv.second.c_str())) {
+            auto w = splitTab(l); w[2] = fmtSeqId(strtof(w[2].c_str(), nullptr), true);   // parse + re-print
+            std::string line; for (size_t x = 0; x < w.size(); x++) { line += w[x]; line += '\t'; }
+            char b[256]; snprintf(b, sizeof(b), "%u\t1\t1.00\t0.000E+00\t0\t%ld\t%ld\t%ld\t%ld\t%llu\n", kv.first, orfLen - 1, orfLen, from, to, contigLen);
+            per[contig].push_back({(uint32_t)strtoul(w[0].c_str(), nullptr, 10), kv.first, line + b});
+        }
+    }
+    std::map<uint32_t, std::string> out;
+    for (auto &kv : per) { auto &v = kv.second; std::stable_sort(v.begin(), v.end(), [](const Row &a, const Row &b) { return a.t != b.t ? a.t < b.t : a.orf < b.orf; }); std::string e; for (auto &r : v) e += r.line; out[kv.first] = e; }
+    return out;
+}
+
+// collectoptimalset on {contig: 20-column lines} (collectoptimalset.cpp:273-418 ; Prediction::predictionToBuffer PredictionParser.h:368-396)
+static std::map<uint32_t, std::string> chainAll(mb200_ctx *ctx, const std::map<uint32_t, std::string> &byc, uint64_t totalRes) {
+    std::vector<mb200_cand> cands; std::vector<uint64_t> off(1, 0); std::vector<std::pair<std::string, std::string>> txt; std::vector<uint32_t> keys;
+    for (auto &kv : byc) {
+        keys.push_back(kv.first);
+        for (auto &l : lines(kv.second.c_str())) {
+            auto w = splitTab(l); if (w.size() != 20) DIE("there should be 20 columns in the input file");
+            mb200_cand c; c.target_key = strtoul(w[0].c_str(), 0, 10); c.bit_score = atoi(w[1].c_str()); c.q_start = atoi(w[4].c_str()); c.q_end = atoi(w[5].c_str());
+            c.t_start = atoi(w[7].c_str()); c.t_end = atoi(w[8].c_str()); c.t_len = atoi(w[9].c_str()); c.orf_key = strtoul(w[10].c_str(), 0, 10); c.frag_from = atoi(w[17].c_str()); c.frag_to = atoi(w[18].c_str());
+            cands.push_back(c); txt.push_back({w[2], w[3]});
+        }
+        off.push_back(cands.size());
+    }
+    std::vector<mb200_call> calls(std::max<size_t>(1, 2 * cands.size())); std::vector<mb200_exon> exons(std::max<size_t>(1, cands.size())); std::vector<uint32_t> cnt(std::max<size_t>(1, keys.size()));
+    if (cands.empty()) cands.resize(1);
+    MB(mb200_chain(ctx, cands.data(), off.data(), (uint32_t)keys.size(), totalRes, calls.data(), cnt.data(), exons.data()));
+    std::map<uint32_t, std::string> out;
+    for (size_t ci = 0; ci < keys.size(); ci++) {
+        std::string e; char b[512]; const uint64_t base = off[ci];
+        for (uint32_t k = 0; k < cnt[ci]; k++) {
+            const mb200_call &cl = calls[2 * base + k];
+            for (int x = 0; x < cl.n_exons; x++) {
+                const mb200_exon &ex = exons[cl.exon_begin + x]; const mb200_cand &c = cands[base + ex.cand_idx]; auto &t = txt[base + ex.cand_idx];
+                snprintf(b, sizeof(b), "%u\t%d\t%d\t%s\t%d\t%d\t%d\t%u\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n", cl.target_key, cl.strand, cl.total_bit_score, fmtE(cl.evalue).c_str(),
+                         cl.n_exons, cl.low_coord, cl.high_coord, c.orf_key, c.bit_score, fmtSeqId((float)strtod(t.first.c_str(), nullptr), false).c_str(), fmtE(strtod(t.second.c_str(), nullptr)).c_str(),
+                         c.t_start, c.t_end, c.t_len, ex.contig_start, ex.contig_end, ex.nuc_len, c.frag_from, c.frag_to);
+                e += b;
+            }
+        }
+        out[keys[ci]] = e;
+    }
+    return out;
+}
+
+static std::map<uint32_t, std::string> searchAll(Session &s, const Db &qdb, const Seqs &q) {
+    std::vector<uint64_t> off(qdb.keys.size() + 1); const mb200_aln *alns = nullptr;
+    MB(mb200_search(s.ctx, q.res.data(), q.off.data(), (uint32_t)qdb.keys.size(), off.data(), &alns));
+    std::map<uint32_t, std::string> out;
+    for (size_t i = 0; i < qdb.keys.size(); i++) out[qdb.keys[i]] = alnEntry(s, std::vector<mb200_aln>(alns + off[i], alns + off[i + 1]), (uint32_t)(q.off[i + 1] - q.off[i]));
+    return out;
+}
+static void writeDb(const std::string &name, int dbtype, const std::map<uint32_t, std::string> &m) { DbOut o(name, dbtype); for (auto &kv : m) o.write(kv.first, kv.second); }
+
+int main(int argc, char **argv) {
+    if (argc < 2) DIE("usage: mb200 <gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
+    initCodes();
+    std::string cmd = argv[1]; std::vector<std::string> pos; Opt o = parseOpts(argc, argv, 2, pos);
+    if (cmd == "gpuprefilter") {
+        if (pos.size() != 3) DIE("gpuprefilter <queryDB> <targetDB> <prefDB>");
+        Session s; s.open(o, pos[1]); Db qdb = openDb(pos[0]); Seqs q = encodeDb(qdb, false);
+        std::vector<uint64_t> off(qdb.keys.size() + 1); const mb200_hit *hits = nullptr;
+        MB(mb200_prefilter_compact(s.ctx, q.res.data(), q.off.data(), (uint32_t)qdb.keys.size(), off.data(), &hits));
+        DbOut out(pos[2], 7);   // DBTYPE_PREFILTER_RES
+        for (size_t i = 0; i < qdb.keys.size(); i++) out.write(qdb.keys[i], prefEntry(s, hits + off[i], off[i + 1] - off[i]));
+    } else if (cmd == "gpualign") {
+        if (pos.size() != 4) DIE("gpualign <queryDB> <targetDB> <prefDB> <alnDB>");
+        Session s; s.open(o, pos[1]); Db qdb = openDb(pos[0]); Seqs q = encodeDb(qdb, false); Db pref = openDb(pos[2]);
+        std::vector<uint32_t> flat; std::vector<uint64_t> off(1, 0);
+        for (size_t i = 0; i < qdb.keys.size(); i++) {
+            size_t p = pref.find(qdb.keys[i]);
+            if (p != (size_t)-1) for (auto &l : lines(pref.entry(p))) { size_t t = s.tdb.find((uint32_t)strtoul(l.c_str(), nullptr, 10)); if (t == (size_t)-1) DIE("prefilter hit not in target DB"); flat.push_back((uint32_t)t); }
+            off.push_back(flat.size());
+        }
+        std::vector<mb200_aln> alns(std::max<size_t>(1, flat.size())); if (flat.empty()) flat.push_back(0);
+        MB(mb200_align(s.ctx, q.res.data(), q.off.data(), (uint32_t)qdb.keys.size(), flat.data(), off.data(), alns.data()));
+        DbOut out(pos[3], 5);   // DBTYPE_ALIGNMENT_RES
+        for (size_t i = 0; i < qdb.keys.size(); i++) out.write(qdb.keys[i], alnEntry(s, std::vector<mb200_aln>(alns.begin() + off[i], alns.begin() + off[i + 1]), (uint32_t)(q.off[i + 1] - q.off[i])));
+    } else if (cmd == "gpusearch") {
+        if (pos.size() != 3) DIE("gpusearch <queryDB> <targetDB> <alnDB>");
+        Session s; s.open(o, pos[1]); Db qdb = openDb(pos[0]); Seqs q = encodeDb(qdb, false);
+        writeDb(pos[2], 5, searchAll(s, qdb, q));
+    } else if (cmd == "gpuresultspercontig") {
+        if (pos.size() != 4) DIE("gpuresultspercontig <contigsDB> <orfDB> <alnDB> <byContigDB>");
+        Db contigs = openDb(pos[0]), hdr = openDb(pos[1] + "_h"), aln = openDb(pos[2]);
+        std::map<uint32_t, std::string> a; for (size_t i = 0; i < aln.keys.size(); i++) a[aln.keys[i]] = aln.entry(i);
+        writeDb(pos[3], 5, byContig(contigs, hdr, a));
+    } else if (cmd == "gpucollectoptimalset") {
+        if (pos.size() != 3) DIE("gpucollectoptimalset <byContigDB> <targetDB> <predDB>");
+        Db byc = openDb(pos[0]), tdb = openDb(pos[1]);
+        uint64_t total = 0; for (size_t i = 0; i < tdb.keys.size(); i++) total += tdb.len[i] >= 2 ? tdb.len[i] - 2 : 0;
+        mb200_ctx *ctx; MB(mb200_ctx_create(o.device, &ctx)); MB(mb200_params_set(ctx, &o.p));
+        std::map<uint32_t, std::string> m; for (size_t i = 0; i < byc.keys.size(); i++) m[byc.keys[i]] = byc.entry(i);
+        writeDb(pos[2], 12, chainAll(ctx, m, total));   // DBTYPE_GENERIC_DB
+        mb200_ctx_destroy(ctx);
+    } else if (cmd == "gpupredictexons") {
+        if (pos.size() != 5) DIE("gpupredictexons <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>");
+        Session s; s.open(o, pos[3]); Db contigs = openDb(pos[0]), qdb = openDb(pos[1]), hdr = openDb(pos[2] + "_h"); Seqs q = encodeDb(qdb, false);
+        auto aln = searchAll(s, qdb, q);
+        auto byc = byContig(contigs, hdr, aln);
+        writeDb(pos[4], 12, chainAll(s.ctx, byc, s.t.res.size()));
+    } else DIE("unknown command %s", cmd.c_str());
+    return EXIT_SUCCESS;
+}

@@ -62,7 +62,7 @@ struct MbPrefScratch {        // per-CTA global scratch
 #define MB_SM_P 512
 #define MB_SM_I 4096
 #define MB_SM_K 8192
-#define MB_SM_S 1024
+#define MB_SM_S 4096
 
 struct MbPrefShared {
     CtaScratch cs;
@@ -72,8 +72,10 @@ struct MbPrefShared {
     uint32_t slots[MB_NSLOT / 16];
     uint32_t sItemOff[MB_SM_P + 1]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P];
     uint32_t sKmerOff[MB_SM_I + 1];
-    uint32_t sHitOff[MB_SM_K + 1];
-    uint64_t sSort[MB_SM_S];
+    union {   // the k-mer -> hit offsets are dead once the hits are gathered; the sorts that follow reuse the space
+        uint32_t sHitOff[MB_SM_K + 2];
+        uint64_t sSort[MB_SM_S];
+    };
 };
 
 // sort a (usually short) global list: through shared memory when it fits

@@ -26,10 +26,37 @@ struct SwTraceOut { uint32_t slot; int32_t score, qStart, qEnd, dbStart, dbEnd, 
 
 __device__ __forceinline__ int sw_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
+// per-query permutation of the hit list by target length, so the 32 lanes of a chunk run for (nearly) the same number of columns
+__global__ void __launch_bounds__(128) k_perm_by_len(const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint64_t *__restrict__ toff,
+                                                     uint32_t nQ, uint32_t maxHits, uint16_t *__restrict__ perm) {
+    __shared__ uint32_t keys[1024];
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
+        const uint32_t n = hitCount[q];
+        uint32_t n2 = 1; while (n2 < n) n2 <<= 1;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < n2; k += blockDim.x) {
+            uint32_t key = 0xFFFFFFFFu;
+            if (k < n) { const uint32_t t = hits[(size_t)q * maxHits + k].seqId; key = ((uint32_t)(toff[t + 1] - toff[t]) << 16) | k; }
+            keys[k] = key;
+        }
+        __syncthreads();
+        for (uint32_t kk = 2; kk <= n2; kk <<= 1) for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                const uint32_t l = ((t / j) * (j << 1)) + (t % j), r = l + j;
+                const bool asc = ((l & kk) == 0);
+                const uint32_t x = keys[l], y = keys[r];
+                if ((x > y) == asc) { keys[l] = y; keys[r] = x; }
+            }
+            __syncthreads();
+        }
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) perm[(size_t)q * maxHits + k] = (uint16_t)(keys[k] & 0xFFFFu);
+    }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
     const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
-    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, uint32_t maxHits,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
     const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
     const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
     uint32_t Lpad, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
@@ -43,8 +70,10 @@ __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     uint32_t *HE = dynSmem + (size_t)wib * (Lpad * 33u);   // [Lpad][32] state words
-    uint32_t *sQcb = HE + Lpad * 32u;                       // [Lpad]  (q_j * 32) | (uint8)cb_j << 16
+    uint32_t *sQcb = HE + Lpad * 32u;                       // [Lpad]  byte offset of the matrix row of q_j (q_j*128) | (uint8)cb_j << 16
     const uint32_t chunkBase = chunkOff[pBegin], chunkEnd = chunkOff[pEnd];
+    const char *matBytes = reinterpret_cast<const char *>(sMat);
+    const int negE = -gapE;
     unsigned long long cells = 0;
     for (;;) {
         uint32_t chunk = 0;
@@ -54,22 +83,23 @@ __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
         uint32_t lo = pBegin, hi = pEnd;   // chunkOff[lo] <= chunk < chunkOff[hi]
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunkOff[mid] <= chunk) lo = mid; else hi = mid; }
         const uint32_t qi = order[lo];
-        const uint32_t k = (chunk - chunkOff[lo]) * 32u + lane;
+        const uint32_t kk = (chunk - chunkOff[lo]) * 32u + lane;
         const uint32_t cnt = hitCount[qi];
-        const bool active = k < cnt;
+        const bool active = kk < cnt;
         const uint64_t qb = qoff[qi]; const int L = (int)(qoff[qi + 1] - qb);
         __syncwarp();
-        for (int j = lane; j < L; j += 32) sQcb[j] = ((uint32_t)qres[qb + j] << 5) | ((uint32_t)(uint8_t)cb[qb + j] << 16);
+        for (int j = lane; j < L; j += 32) sQcb[j] = ((uint32_t)qres[qb + j] << 7) | ((uint32_t)(uint8_t)cb[qb + j] << 16);
         __syncwarp();
+        const uint32_t k = (active && perm) ? (uint32_t)perm[(size_t)qi * maxHits + kk] : kk;
         const size_t slot = (size_t)qi * maxHits + k;
         uint32_t tid = 0; int tLen = 0; const uint8_t *t = tseq;
         if (active) { tid = hits[slot].seqId; const uint64_t tb = toff[tid]; tLen = (int)(toff[tid + 1] - tb); t = tseq + tb; }
         int mx = 0;
         uint32_t *myHE = HE + lane;
         for (int i0 = 0; i0 < tLen; i0 += NC) {
-            int tAddr[NC], hprev[NC], F[NC];
+            int tA[NC], H[NC], G[NC], F[NC];   // column byte offset in a matrix row; H, H - gapOpen and F of the previous row
 #pragma unroll
-            for (int c = 0; c < NC; c++) { tAddr[c] = (i0 + c < tLen) ? (int)t[i0 + c] : MB_SW_PADRES; hprev[c] = 0; F[c] = 0; }
+            for (int c = 0; c < NC; c++) { tA[c] = ((i0 + c < tLen) ? (int)t[i0 + c] : MB_SW_PADRES) * 4; H[c] = 0; G[c] = -gapO; F[c] = 0; }
             int hleftPrev = 0;
             const bool first = (i0 == 0);
             for (int j = 0; j < L; j++) {
@@ -77,20 +107,22 @@ __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
                 const int hleft = (int)(w & 0xFFFFu);
                 int e = (int)(w >> 16);
                 const uint32_t qc = sQcb[j];
-                const int32_t *row = sMat + (qc & 0xFFFFu);
+                const int rowOff = (int)(qc & 0xFFFFu);
                 const int cbj = (int)(int8_t)(qc >> 16);
                 int diag = hleftPrev;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    const int s = row[tAddr[c]] + cbj;
-                    const int f = __viaddmax_s32(F[c], -gapE, hprev[c] - gapO);
-                    const int h = sw_max3(diag + s, e, f > 0 ? f : 0);
-                    diag = hprev[c]; hprev[c] = h; F[c] = f;
-                    e = sw_max3(e - gapE, h - gapO, 0);
-                    mx = h > mx ? h : mx;
+                    const int s = *reinterpret_cast<const int32_t *>(matBytes + (tA[c] + rowOff)) + cbj;
+                    const int f = __viaddmax_s32(F[c], negE, G[c]);          // max(F - ge, Hup - go)
+                    const int t1 = __viaddmax_s32(diag, s, e);               // max(Hdiag + s, E)
+                    const int h = __vimax_s32_relu(t1, f);                   // max(.., F, 0)
+                    diag = H[c]; H[c] = h; F[c] = f;
+                    const int g = h - gapO; G[c] = g;
+                    e = __viaddmax_s32_relu(e, negE, g);                     // E' = max(E - ge, H - go, 0)
+                    mx = max(mx, h);
                 }
                 hleftPrev = hleft;
-                myHE[j * 32] = (uint32_t)hprev[NC - 1] | ((uint32_t)e << 16);
+                myHE[j * 32] = (uint32_t)H[NC - 1] | ((uint32_t)e << 16);
             }
             cells += (unsigned long long)L * NC;
         }
