@@ -124,7 +124,7 @@ struct mb200_ctx {
     bool havePref = false;
     // align
     DevBuf<uint32_t> dPairOff, dChunkOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
-    DevBuf<uint64_t> dHitOff64; DevBuf<uint16_t> dPerm;
+    DevBuf<uint64_t> dHitOff64; DevBuf<uint16_t> dPerm; DevBuf<uint32_t> dBnd;
     std::vector<int> minScore;   // per query length, -2 = not computed
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
@@ -220,7 +220,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
-    c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release();
+    c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -451,26 +451,25 @@ static int align_pipeline(mb200_ctx *c) {
         CU(cudaGetLastError()); c->st.launches++;
     }
     uint32_t *dNPass = c->dCounter.p + 32, *dErr = c->dCounter.p + 33;
-    // length classes over the length-sorted query order (descending): one launch per class, shared-memory state sized to the class
-    static const uint32_t classPad[] = {32, 64, 96, 128, 160, 192, 224, 256, 384, 512, 768, 1024};
-    const int nClass = (int)(sizeof(classPad) / sizeof(classPad[0]));
-    std::vector<uint32_t> bound(nClass + 2, 0);   // bound[k] = first order position whose length <= classPad[k-1]... computed below
-    // order is descending: positions [0, pLong) have L > 1024
+    // two launches over the length-sorted query order (descending): queries <= 256 residues and 257..1024 (profile size differs)
     auto lenAt = [&](uint32_t p) { const uint32_t q = c->hOrder[p]; return (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]); };
     auto firstLE = [&](uint32_t x) { uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lenAt(mid) <= x) hi = mid; else lo = mid + 1; } return lo; };
     const uint32_t pLong = firstLE(1024);
+    uint32_t maxT = 1; for (uint32_t t = 0; t < c->nT; t++) maxT = std::max<uint32_t>(maxT, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
     CU(cudaEventRecord(c->ev0, c->stream));
-    for (int k = nClass - 1; k >= 0; k--) {
-        const uint32_t pB = firstLE(classPad[k]), pE = (k == 0) ? nQ : firstLE(classPad[k - 1]);
+    const uint32_t bounds[3] = {pLong, firstLE(256), nQ}; const uint32_t strides[2] = {1024 + 16, 256 + 16};
+    for (int k = 0; k < 2; k++) {
+        const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
-        const uint32_t Lpad = classPad[k];
-        int W = (int)(160 * 1024 / (Lpad * 33u * 4u)); if (W > MB_SW_WARPS) W = MB_SW_WARPS; if (W < 1) W = 1;
-        const size_t smem = (size_t)W * Lpad * 33u * 4u;
-        CU(cudaFuncSetAttribute(k_sw_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_score<4>, W * 32, smem)); if (perSM < 1) perSM = 1;
-        k_sw_score<4><<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p,
-                                                                  c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend, Lpad, c->dMinScore.p, c->dScore.p,
-                                                                  c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr);
+        const size_t smem = (size_t)MB_SWR_WARPS * 21u * strides[k];
+        CU(cudaFuncSetAttribute(k_sw_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
+        const int blocks = c->nSM * perSM;
+        TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u));
+        k_sw_rows<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                     c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                     strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
+                                                                     c->dBnd.p, maxT);
         CU(cudaGetLastError()); c->st.launches++;
     }
     CU(cudaEventRecord(c->ev1, c->stream));

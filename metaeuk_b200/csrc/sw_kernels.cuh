@@ -135,6 +135,102 @@ __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
     if (cells) atomicAdd(cellCount, cells);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_sw_rows: score-only SW with the DP state in REGISTERS.  One warp per (query, chunk of <= 32 hits), one alignment per lane.
+// The query is cut into blocks of RB rows; for one block a lane sweeps all target columns keeping H(previous column) and E for
+// the RB rows in registers and F / the diagonal in scalars.  The only state that leaves the registers is the block boundary
+// (H of the block's last row and the F entering the next block, one packed word per target column, lane-interleaved in global
+// memory, touched once per RB cells).  Substitution scores come from a per-warp query profile in shared memory,
+// P[t][j] = mat[t][q_j] + compBias8[j] as int8, fetched 16 rows at a time with 128-bit loads -> no per-cell shared-memory access.
+// ---------------------------------------------------------------------------------------------------------------------
+#define MB_SWR_WARPS 8
+template <int RB>
+__global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
+    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
+    uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint32_t *__restrict__ bnd, uint32_t maxT) {
+    extern __shared__ __align__(16) unsigned char dynProf[];
+    __shared__ int8_t sMat8[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)wib * 21u * profStride;
+    uint32_t *myBnd = bnd + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * maxT * 32u + lane;
+    const uint32_t chunkBase = chunkOff[pBegin], chunkEnd = chunkOff[pEnd];
+    const int negE = -gapE;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = chunkBase + atomicAdd(counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= chunkEnd) break;
+        uint32_t lo = pBegin, hi = pEnd;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunkOff[mid] <= chunk) lo = mid; else hi = mid; }
+        const uint32_t qi = order[lo];
+        const uint32_t kk = (chunk - chunkOff[lo]) * 32u + lane;
+        const uint32_t cnt = hitCount[qi];
+        const bool active = kk < cnt;
+        const uint64_t qb = qoff[qi]; const int L = (int)(qoff[qi + 1] - qb);
+        const int nb = (L + RB - 1) / RB;
+        __syncwarp();
+        for (uint32_t idx = lane; idx < 21u * profStride; idx += 32u) {
+            const uint32_t t = idx / profStride, j = idx - t * profStride;
+            prof[idx] = (j < (uint32_t)L) ? (int8_t)(sMat8[t * 21 + qres[qb + j]] + cb[qb + j]) : (int8_t)-64;   // rows past the query end can only lower scores
+        }
+        __syncwarp();
+        const uint32_t k = (active && perm) ? (uint32_t)perm[(size_t)qi * maxHits + kk] : kk;
+        const size_t slot = (size_t)qi * maxHits + k;
+        int tLen = 0; const uint8_t *t = tseq;
+        if (active) { const uint32_t tid = hits[slot].seqId; const uint64_t tb = toff[tid]; tLen = (int)(toff[tid + 1] - tb); t = tseq + tb; }
+        int mx = 0;
+        for (int b = 0; b < nb; b++) {
+            int Hp[RB], E[RB];
+#pragma unroll
+            for (int r = 0; r < RB; r++) { Hp[r] = 0; E[r] = 0; }
+            const int8_t *profB = prof + b * RB;
+            const bool hasTop = b > 0, hasBottom = b < nb - 1;
+            int prevTop = 0;
+            uint32_t topNext = (hasTop && tLen > 0) ? myBnd[0] : 0u;
+            uint32_t tcNext = tLen > 0 ? (uint32_t)t[0] : 0u;
+            for (int i = 0; i < tLen; i++) {
+                const uint32_t top = topNext, tc = tcNext;
+                if (i + 1 < tLen) { tcNext = (uint32_t)t[i + 1]; if (hasTop) topNext = myBnd[(size_t)(i + 1) * 32u]; }
+                const uint4 *pp = reinterpret_cast<const uint4 *>(profB + tc * profStride);
+                uint32_t pw[RB / 4];
+#pragma unroll
+                for (int v = 0; v < RB / 16; v++) { const uint4 x = pp[v]; pw[4 * v] = x.x; pw[4 * v + 1] = x.y; pw[4 * v + 2] = x.z; pw[4 * v + 3] = x.w; }
+                const int hTop = (int)(top & 0xFFFFu);
+                int F = (int)(top >> 16);          // F entering the block's first row (already max(F-ge, H-go, 0) of the row above)
+                int diag = prevTop; prevTop = hTop;
+                int gUp = 0;
+#pragma unroll
+                for (int r = 0; r < RB; r++) {
+                    const int s = (int)(int8_t)(pw[r >> 2] >> (8 * (r & 3)));
+                    const int f = (r == 0) ? F : __viaddmax_s32(F, negE, gUp);
+                    const int t1 = __viaddmax_s32(diag, s, E[r]);
+                    const int h = __vimax_s32_relu(t1, f);
+                    diag = Hp[r]; Hp[r] = h;
+                    const int g = h - gapO;
+                    E[r] = __viaddmax_s32_relu(E[r], negE, g);
+                    F = f; gUp = g;
+                    mx = max(mx, h);
+                }
+                if (hasBottom) myBnd[(size_t)i * 32u] = (uint32_t)Hp[RB - 1] | ((uint32_t)__viaddmax_s32_relu(F, negE, gUp) << 16);
+            }
+            cells += (unsigned long long)tLen * RB;
+        }
+        if (active) {
+            scoreOut[slot] = mx;
+            if (mx >= 65000) atomicExch(errFlag, 1u);
+            if (mx >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slot; else atomicExch(errFlag, 2u); }
+        }
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
 // one alignment per lane: forward with end tracking, then reverse to the start.  slot = query * maxHits + hit rank (slot < 2^32).
 __global__ void __launch_bounds__(128) k_sw_trace(const uint32_t *__restrict__ passList, uint32_t nPass, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
                                                   const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,

@@ -155,3 +155,57 @@ def test_edge_cases():
     assert len(c) == 0
     o.close()
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# C++ host driver (metaeuk_b200/bin/mb200): the reference's module surface on MMseqs database files
+# ------------------------------------------------------------------------------------------------
+def write_db(path, entries, dbtype):
+    import struct
+    pos = 0
+    with open(path, "wb") as f, open(path + ".index", "w") as fi:
+        for k, e in entries:
+            b = e.encode() + b"\0"
+            f.write(b)
+            fi.write("%d\t%d\t%d\n" % (k, pos, len(b)))
+            pos += len(b)
+    with open(path + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", dbtype))
+
+
+def read_db(path):
+    data = open(path, "rb").read()
+    out = {}
+    for line in open(path + ".index"):
+        k, o, l = line.split("\t")
+        out[k] = data[int(o):int(o) + int(l) - 1].decode()
+    return out
+
+
+def test_cli_modules_on_database_files(tmp_path):
+    import os
+    import subprocess
+    from metaeuk_b200 import lib as mlib
+    exe = os.path.join(mlib.PKG, "bin", "mb200")
+    assert os.path.exists(exe), "build the CLI first (__graft_entry__.build)"
+    c = reflib.load_case("contigs_sets")
+    d = str(tmp_path)
+    write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"]], 0)
+    write_db(d + "/proteins_masked", [(k, m + "\n") for (k, _), m in zip(c["targets"], c["masked_targets"])], 0)
+    write_db(d + "/aa_6f", [(k, s + "\n") for k, s in c["queries"]], 0)
+    write_db(d + "/nucl_6f_h", [(int(k), v) for k, v in c["orf_headers"].items()], 12)
+    write_db(d + "/contigs", [(int(k), "A" * v + "\n") for k, v in c["contig_lens"].items()], 1)
+    common = ["--masked-db", d + "/proteins_masked", "--k-score", str(c["kmer_thr"])]
+    subprocess.check_call([exe, "gpuprefilter", d + "/aa_6f", d + "/proteins", d + "/pref"] + common)
+    pref = read_db(d + "/pref")
+    assert all(pref[str(k)] == c["pref"].get(str(k), "") for k, _ in c["queries"])
+    subprocess.check_call([exe, "gpualign", d + "/aa_6f", d + "/proteins", d + "/pref", d + "/aln"] + common)
+    aln = read_db(d + "/aln")
+    assert all(aln[str(k)] == c["aln"].get(str(k), "") for k, _ in c["queries"])
+    subprocess.check_call([exe, "gpuresultspercontig", d + "/contigs", d + "/nucl_6f", d + "/aln", d + "/bycontig"])
+    assert read_db(d + "/bycontig") == c["bycontig"]
+    subprocess.check_call([exe, "gpucollectoptimalset", d + "/bycontig", d + "/proteins", d + "/dp", "--max-exon-sets", str(c["max_exon_sets"])])
+    assert read_db(d + "/dp") == c["dp"]
+    subprocess.check_call([exe, "gpupredictexons", d + "/contigs", d + "/aa_6f", d + "/nucl_6f", d + "/proteins", d + "/dp2", "--max-exon-sets",
+                           str(c["max_exon_sets"])] + common)
+    assert read_db(d + "/dp2") == c["dp"]
