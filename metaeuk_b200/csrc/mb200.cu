@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_prep(const uint8_t *__restrict__ qres, 
 }
 
 // ---- prefilter: persistent CTAs, one query at a time, dynamic work distribution --------------------
-__global__ void __launch_bounds__(MB_CTA_THREADS) k_prefilter(MbPrefTables T, const MbPrefScratch *__restrict__ scratch, const uint8_t *__restrict__ qres,
+__global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T, const MbPrefScratch *__restrict__ scratch, const uint8_t *__restrict__ qres,
                                                               const uint64_t *__restrict__ qoff, const float *__restrict__ bias, const int8_t *__restrict__ corr,
                                                               const uint32_t *__restrict__ order, uint32_t nQ, const int8_t *__restrict__ ungMat8,
                                                               MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats, uint32_t *nextQ) {

@@ -200,7 +200,6 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
         const int s0 = (int16_t)(T.sim3[(size_t)wI0[p] * MB_N3 + i] & 0xFFFFu);
         const short cutoff2 = (short)((int)wThr[p] - s0);
         kmerOff[it] = mb_count_ge(T.cnt3, wI1[p], cutoff2);
-        W.itemInfo[it] = (p << 13) | i;
     }
     CTA_SYNC();
     const uint32_t K = cta_exclusive_scan(kmerOff, I, &sh->cs);
@@ -208,18 +207,30 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
 
     // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
     uint32_t *const hitOff = (K <= MB_SM_K) ? sh->sHitOff : W.hitOff;
+    // Each thread owns a contiguous run of k-mers; it walks the (item, window) cursors forward instead of searching, and handles
+    // the run in batches of 4 so that the dependent global loads of a batch (sim3 rows -> bitmap -> offsets) are all in flight together.
     CTA_CHUNK(kb, ke, K);
-    uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;   // one search per contiguous chunk, then walk forward
-    for (uint32_t k = kb; k < ke; k++) {
-        while (kmerOff[it + 1] <= k) it++;
-        const uint32_t j = k - kmerOff[it];
-        const uint32_t info = W.itemInfo[it]; const uint32_t p = info >> 13, i = info & 0x1FFFu;
-        const uint32_t k0 = T.sim3[(size_t)wI0[p] * MB_N3 + i] >> 16;
-        const uint32_t k1 = T.sim3[(size_t)wI1[p] * MB_N3 + j] >> 16;
-        const uint32_t kmer = k0 + k1 * 8000u;
-        uint32_t lo = 0, hi = 0;
-        if (!T.kmerBits || ((T.kmerBits[kmer >> 5] >> (kmer & 31u)) & 1u)) { lo = T.offsets[kmer]; hi = T.offsets[kmer + 1]; }
-        hitOff[k] = hi - lo; W.kmerLo[k] = lo; W.kmerP[k] = (uint16_t)p;
+    uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;
+    uint32_t pw = (kb < ke) ? cta_find_segment(itemOff, P, it) : 0;
+    for (uint32_t k0 = kb; k0 < ke; k0 += 4) {
+        uint32_t pv[4], iv[4], jv[4], a0[4], a1[4], km[4], lo[4], hi[4]; bool ok[4], nz[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t k = k0 + u; ok[u] = k < ke; pv[u] = 0; iv[u] = 0; jv[u] = 0;
+            if (ok[u]) {
+                while (kmerOff[it + 1] <= k) it++;
+                while (itemOff[pw + 1] <= it) pw++;
+                pv[u] = pw; iv[u] = it - itemOff[pw]; jv[u] = k - kmerOff[it];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a0[u] = 0; a1[u] = 0; if (ok[u]) { a0[u] = T.sim3[(size_t)wI0[pv[u]] * MB_N3 + iv[u]]; a1[u] = T.sim3[(size_t)wI1[pv[u]] * MB_N3 + jv[u]]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { km[u] = (a0[u] >> 16) + (a1[u] >> 16) * 8000u; nz[u] = ok[u]; if (ok[u] && T.kmerBits) nz[u] = (T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lo[u] = 0; hi[u] = 0; if (nz[u]) { lo[u] = T.offsets[km[u]]; hi[u] = T.offsets[km[u] + 1]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) { const uint32_t k = k0 + u; hitOff[k] = hi[u] - lo[u]; W.kmerLo[k] = lo[u]; W.kmerP[k] = (uint16_t)pv[u]; }
     }
     CTA_SYNC();
     const uint32_t M = cta_exclusive_scan(hitOff, K, &sh->cs);
@@ -228,15 +239,23 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
     CTA_CHUNK(hb, he, M);
     uint32_t kk = (hb < he) ? cta_find_segment(hitOff, K, hb) : 0;
-    for (uint32_t h = hb; h < he; h++) {
-        while (hitOff[kk + 1] <= h) kk++;
-        const uint32_t k = kk;
-        const uint2 e = T.entries[(size_t)W.kmerLo[k] + (h - hitOff[k])];
-        const uint16_t diag16 = (uint16_t)((uint32_t)W.kmerP[k] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
-        W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
-        const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
-        const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
-        if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+    for (uint32_t h0 = hb; h0 < he; h0 += 4) {
+        uint32_t kv[4], ov[4], lov[4], ppv[4]; uint2 ev[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t h = h0 + u; ok[u] = h < he; kv[u] = 0; ov[u] = 0; if (ok[u]) { while (hitOff[kk + 1] <= h) kk++; kv[u] = kk; ov[u] = h - hitOff[kk]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lov[u] = 0; ppv[u] = 0; if (ok[u]) { lov[u] = W.kmerLo[kv[u]]; ppv[u] = W.kmerP[kv[u]]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { ev[u].x = 0; ev[u].y = 0; if (ok[u]) ev[u] = T.entries[(size_t)lov[u] + ov[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) {
+            const uint32_t h = h0 + u; const uint2 e = ev[u];
+            const uint16_t diag16 = (uint16_t)(ppv[u] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+            W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
+            const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+            const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+            if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+        }
     }
     CTA_SYNC();
     // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
