@@ -55,6 +55,25 @@ MB_DEV float mb_fdiv(float a, float b) { return a / b; }
 
 #define MB_CTA_THREADS 512
 
+// Reserve one slot of a list whose length lives at *ctr (shared memory) for every calling thread with pred == true and return its
+// index (~0u otherwise).  On the device the threads of a warp that append in the same instruction share ONE atomic.
+MB_DEV uint32_t cta_append_slot(uint32_t *ctr, bool pred) {
+#if MB_DEVICE_BUILD
+    const unsigned act = __activemask();
+    const unsigned b = __ballot_sync(act, pred);
+    if (!pred) return ~0u;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(b) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(b));
+    base = __shfl_sync(b, base, leader);
+    return base + (uint32_t)__popc(b & ((1u << lane) - 1u));
+#else
+    if (!pred) return ~0u;
+    const uint32_t o = *ctr; *ctr = o + 1; return o;
+#endif
+}
+
 // Scratch every collective needs (lives in shared memory on the device).
 struct CtaScratch {
     uint32_t part[MB_CTA_THREADS + 1];
@@ -137,7 +156,7 @@ MB_DEV void cta_sort_u64(uint64_t *a, uint32_t n) {
     for (uint32_t k = 2; k <= n2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-                const uint32_t l = ((t / j) * (j << 1)) + (t % j);   // j is a power of two
+                const uint32_t l = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two: (t / j) * 2j + t % j
                 const uint32_t r = l + j;
                 const bool asc = ((l & k) == 0);
                 const uint64_t x = a[l], y = a[r];

@@ -263,8 +263,12 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     CTA_FOR(h, M) {
         const uint64_t w = W.A[h];
         const uint32_t slot = MB_W_SEQ(w) & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
-        if ((sh->slots[slot >> 4] >> sft) & 2u) { W.B[mb_atomic_add(&sh->cnt[0], 1u)] = w; }
-        else if ((w & 0xFFu) == 0) { W.C[mb_atomic_add(&sh->cnt[1], 1u)] = w; }
+        const bool multi = (sh->slots[slot >> 4] >> sft) & 2u;
+        const uint32_t ib = cta_append_slot(&sh->cnt[0], multi);
+        if (multi) W.B[ib] = w;
+        const bool single0 = !multi && (w & 0xFFu) == 0;
+        const uint32_t ic = cta_append_slot(&sh->cnt[1], single0);
+        if (single0) W.C[ic] = w;
     }
     CTA_SYNC();
     const uint32_t nMulti = sh->cnt[0];

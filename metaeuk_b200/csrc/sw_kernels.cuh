@@ -144,6 +144,42 @@ __global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
 // P[t][j] = mat[t][q_j] + compBias8[j] as int8, fetched 16 rows at a time with 128-bit loads -> no per-cell shared-memory access.
 // ---------------------------------------------------------------------------------------------------------------------
 #define MB_SWR_WARPS 8
+// one block of RBK query rows against all columns of this lane's target; state in registers, block boundary through myBnd
+template <int RBK>
+__device__ __forceinline__ void sw_sweep_block(const int8_t *profB, uint32_t profStride, const uint8_t *__restrict__ t, int tLen, uint32_t *myBnd,
+                                               bool hasTop, bool hasBottom, int gapO, int negE, int &mx) {
+    int Hp[RBK], E[RBK];
+#pragma unroll
+    for (int r = 0; r < RBK; r++) { Hp[r] = 0; E[r] = 0; }
+    int prevTop = 0;
+    uint32_t topNext = (hasTop && tLen > 0) ? myBnd[0] : 0u;
+    uint32_t tcNext = tLen > 0 ? (uint32_t)t[0] : 0u;
+    for (int i = 0; i < tLen; i++) {
+        const uint32_t top = topNext, tc = tcNext;
+        if (i + 1 < tLen) { tcNext = (uint32_t)t[i + 1]; if (hasTop) topNext = myBnd[(size_t)(i + 1) * 32u]; }
+        const uint4 *pp = reinterpret_cast<const uint4 *>(profB + tc * profStride);
+        uint32_t pw[RBK / 4];
+#pragma unroll
+        for (int v = 0; v < RBK / 16; v++) { const uint4 x = pp[v]; pw[4 * v] = x.x; pw[4 * v + 1] = x.y; pw[4 * v + 2] = x.z; pw[4 * v + 3] = x.w; }
+        const int hTop = (int)(top & 0xFFFFu);
+        int F = (int)(top >> 16);          // F entering the block's first row (already max(F-ge, H-go, 0) of the row above)
+        int diag = prevTop; prevTop = hTop;
+        int gUp = 0;
+#pragma unroll
+        for (int r = 0; r < RBK; r++) {
+            const int s = (int)(int8_t)(pw[r >> 2] >> (8 * (r & 3)));
+            const int f = (r == 0) ? F : __viaddmax_s32(F, negE, gUp);
+            const int t1 = __viaddmax_s32(diag, s, E[r]);
+            const int h = __vimax_s32_relu(t1, f);
+            diag = Hp[r]; Hp[r] = h;
+            const int g = h - gapO;
+            E[r] = __viaddmax_s32_relu(E[r], negE, g);
+            F = f; gUp = g;
+            mx = max(mx, h);
+        }
+        if (hasBottom) myBnd[(size_t)i * 32u] = (uint32_t)Hp[RBK - 1] | ((uint32_t)__viaddmax_s32_relu(F, negE, gUp) << 16);
+    }
+}
 template <int RB>
 __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
     const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
@@ -187,40 +223,10 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
         if (active) { const uint32_t tid = hits[slot].seqId; const uint64_t tb = toff[tid]; tLen = (int)(toff[tid + 1] - tb); t = tseq + tb; }
         int mx = 0;
         for (int b = 0; b < nb; b++) {
-            int Hp[RB], E[RB];
-#pragma unroll
-            for (int r = 0; r < RB; r++) { Hp[r] = 0; E[r] = 0; }
-            const int8_t *profB = prof + b * RB;
             const bool hasTop = b > 0, hasBottom = b < nb - 1;
-            int prevTop = 0;
-            uint32_t topNext = (hasTop && tLen > 0) ? myBnd[0] : 0u;
-            uint32_t tcNext = tLen > 0 ? (uint32_t)t[0] : 0u;
-            for (int i = 0; i < tLen; i++) {
-                const uint32_t top = topNext, tc = tcNext;
-                if (i + 1 < tLen) { tcNext = (uint32_t)t[i + 1]; if (hasTop) topNext = myBnd[(size_t)(i + 1) * 32u]; }
-                const uint4 *pp = reinterpret_cast<const uint4 *>(profB + tc * profStride);
-                uint32_t pw[RB / 4];
-#pragma unroll
-                for (int v = 0; v < RB / 16; v++) { const uint4 x = pp[v]; pw[4 * v] = x.x; pw[4 * v + 1] = x.y; pw[4 * v + 2] = x.z; pw[4 * v + 3] = x.w; }
-                const int hTop = (int)(top & 0xFFFFu);
-                int F = (int)(top >> 16);          // F entering the block's first row (already max(F-ge, H-go, 0) of the row above)
-                int diag = prevTop; prevTop = hTop;
-                int gUp = 0;
-#pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    const int s = (int)(int8_t)(pw[r >> 2] >> (8 * (r & 3)));
-                    const int f = (r == 0) ? F : __viaddmax_s32(F, negE, gUp);
-                    const int t1 = __viaddmax_s32(diag, s, E[r]);
-                    const int h = __vimax_s32_relu(t1, f);
-                    diag = Hp[r]; Hp[r] = h;
-                    const int g = h - gapO;
-                    E[r] = __viaddmax_s32_relu(E[r], negE, g);
-                    F = f; gUp = g;
-                    mx = max(mx, h);
-                }
-                if (hasBottom) myBnd[(size_t)i * 32u] = (uint32_t)Hp[RB - 1] | ((uint32_t)__viaddmax_s32_relu(F, negE, gUp) << 16);
-            }
-            cells += (unsigned long long)tLen * RB;
+            if (L - b * RB <= RB / 2) sw_sweep_block<RB / 2>(prof + b * RB, profStride, t, tLen, myBnd, hasTop, hasBottom, gapO, negE, mx);   // short tail block
+            else sw_sweep_block<RB>(prof + b * RB, profStride, t, tLen, myBnd, hasTop, hasBottom, gapO, negE, mx);
+            cells += (unsigned long long)tLen * ((L - b * RB <= RB / 2) ? RB / 2 : RB);
         }
         if (active) {
             scoreOut[slot] = mx;
