@@ -23,6 +23,7 @@
 MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+MB_DEV uint32_t mb_atomic_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 // IEEE double ops that must never be contracted into FMAs (composition-bias parity with the CPU path)
 MB_DEV double mb_dmul(double a, double b) { return __dmul_rn(a, b); }
 MB_DEV double mb_dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -45,6 +46,7 @@ struct uint2 { unsigned int x, y; };
 MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+MB_DEV uint32_t mb_atomic_cas(uint32_t *p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
 MB_DEV double mb_dmul(double a, double b) { return a * b; }   // emulation is built with -ffp-contract=off
 MB_DEV double mb_dadd(double a, double b) { return a + b; }
 MB_DEV double mb_ddiv(double a, double b) { return a / b; }

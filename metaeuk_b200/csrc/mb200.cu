@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -458,18 +459,32 @@ static int align_pipeline(mb200_ctx *c) {
     uint32_t maxT = 1; for (uint32_t t = 0; t < c->nT; t++) maxT = std::max<uint32_t>(maxT, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
     CU(cudaEventRecord(c->ev0, c->stream));
     const uint32_t bounds[3] = {pLong, firstLE(256), nQ}; const uint32_t strides[2] = {1024 + 16, 256 + 16};
+    const char *swSel = getenv("MB200_SW_KERNEL");   // "rows" = one target per lane (32-bit), default "rows2" = two targets per lane (packed 16-bit)
+    const bool packed = !(swSel && strcmp(swSel, "rows") == 0);
     for (int k = 0; k < 2; k++) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
-        const size_t smem = (size_t)MB_SWR_WARPS * 21u * strides[k];
-        CU(cudaFuncSetAttribute(k_sw_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
-        const int blocks = c->nSM * perSM;
-        TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u));
-        k_sw_rows<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
-                                                                     c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
-                                                                     strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
-                                                                     c->dBnd.p, maxT);
+        if (packed) {
+            const size_t smem = (size_t)MB_SWR_WARPS * 2u * 22u * strides[k];
+            CU(cudaFuncSetAttribute(k_sw_rows2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows2<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
+            const int blocks = c->nSM * perSM;
+            TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u * 2u));
+            k_sw_rows2<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                          c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                          strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
+                                                                          reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
+        } else {
+            const size_t smem = (size_t)MB_SWR_WARPS * 21u * strides[k];
+            CU(cudaFuncSetAttribute(k_sw_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
+            const int blocks = c->nSM * perSM;
+            TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u));
+            k_sw_rows<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                         c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                         strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
+                                                                         c->dBnd.p, maxT);
+        }
         CU(cudaGetLastError()); c->st.launches++;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -479,7 +494,7 @@ static int align_pipeline(mb200_ctx *c) {
     CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "k_sw_score"));
     float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
-    if (hn[1] == 1) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
+    if (hn[1] == 1) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits (scores must stay below 32000)");
     if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
     // queries longer than 1024 residues: every hit goes straight to the trace kernel (host applies the e-value test)
     std::vector<uint32_t> extra;

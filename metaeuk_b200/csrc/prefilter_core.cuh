@@ -91,6 +91,14 @@ MB_DEV void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
     }
 }
 
+#define MB_HT_LOG 12
+#define MB_HT_N (1u << MB_HT_LOG)   // 2 x MB_HT_N words must fit in sHitOff
+MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t id1) {
+    uint32_t slot = (id1 * 2654435761u) >> (32 - MB_HT_LOG);
+    while (htKey[slot] != id1) slot = (slot + 1u) & (MB_HT_N - 1u);
+    return slot;
+}
+
 struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; };
 
 MB_DEV uint32_t mb_count_ge(const uint16_t *cnt3, uint32_t row, int x) {
@@ -273,6 +281,53 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     CTA_SYNC();
     const uint32_t nMulti = sh->cnt[0];
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
+    if (nMulti <= MB_HT_N / 2) {
+        // Sort-free: group the multi list by target with a shared-memory hash table (the hit offsets' space is free now), then every
+        // hit looks up its predecessor *of the same target* (largest smaller arrival index) inside its group.
+        uint32_t *htKey = sh->sHitOff, *htOff = sh->sHitOff + MB_HT_N;
+        CTA_FOR(i, 2 * MB_HT_N) sh->sHitOff[i] = 0;
+        CTA_SYNC();
+        CTA_FOR(e, nMulti) {
+            const uint32_t id1 = MB_W_SEQ(W.B[e]) + 1u;
+            uint32_t slot = (id1 * 2654435761u) >> (32 - MB_HT_LOG);
+            for (;;) {
+                const uint32_t old = mb_atomic_cas(&htKey[slot], 0u, id1);
+                if (old == 0u || old == id1) break;
+                slot = (slot + 1u) & (MB_HT_N - 1u);
+            }
+            mb_atomic_add(&htOff[slot], 1u);
+            W.S[e] = (int32_t)slot;
+        }
+        CTA_SYNC();
+        cta_exclusive_scan(htOff, MB_HT_N - 1, &sh->cs);   // (the last slot's count is covered by the total; offsets only need [0, N-1))
+        CTA_FOR(e, nMulti) { const uint32_t slot = (uint32_t)W.S[e]; W.A[mb_atomic_add(&htOff[slot], 1u)] = W.B[e]; }   // afterwards htOff[s] = END of group s
+        CTA_SYNC();
+        // pass X: is this hit a duplicate of the immediately preceding hit of its target?  (byte array starts at 0: CacheFriendlyOperations.cpp:213-218)
+        CTA_FOR(e, nMulti) {
+            const uint64_t w = W.A[e];
+            const uint32_t slot = mb_ht_find(htKey, MB_W_SEQ(w) + 1u);
+            const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
+            uint64_t pred = 0; bool has = false;
+            for (uint32_t x = gb; x < ge; x++) { const uint64_t y = W.A[x]; if (y < w && (!has || y > pred)) { pred = y; has = true; } }
+            const uint32_t d8 = (uint32_t)(w & 0xFFu), last = has ? (uint32_t)(pred & 0xFFu) : 0u;
+            W.B[e] = w | ((d8 == last) ? (1ull << 63) : 0ull);   // bit 63 = candidate flag (seqId uses 27 bits)
+        }
+        CTA_SYNC();
+        // pass Y: runs of candidates with equal 8-bit diagonal collapse to their first (phases 2/3, CacheFriendlyOperations.cpp:236-262)
+        CTA_FOR(e, nMulti) {
+            const uint64_t wf = W.B[e];
+            if (wf >> 63) {
+                const uint64_t w = wf & ~(1ull << 63);
+                const uint32_t slot = mb_ht_find(htKey, MB_W_SEQ(w) + 1u);
+                const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
+                uint64_t pc = 0; bool has = false;
+                for (uint32_t x = gb; x < ge; x++) { const uint64_t yf = W.B[x]; const uint64_t y = yf & ~(1ull << 63); if ((yf >> 63) && y < w && (!has || y > pc)) { pc = y; has = true; } }
+                const bool accept = !has || ((uint32_t)(pc & 0xFFu) != (uint32_t)(w & 0xFFu));
+                const uint32_t ic = cta_append_slot(&sh->cnt[1], accept);
+                if (accept) W.C[ic] = w;
+            } else { cta_append_slot(&sh->cnt[1], false); }
+        }
+    } else {
     mb_sort_list(W.B, nMulti, sh);
     CTA_FOR(e, nMulti) {
         const uint32_t id = MB_W_SEQ(W.B[e]);
@@ -287,6 +342,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
                 last = d8;
             }
         }
+    }
     }
     CTA_SYNC();
     const uint32_t D = sh->cnt[1];

@@ -237,6 +237,126 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
     if (cells) atomicAdd(cellCount, cells);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_sw_rows2: as k_sw_rows, but every lane aligns TWO targets at once in packed signed 16-bit halves (DPX s16x2 instructions:
+// VIADDMNMX.S16x2 etc.), and a warp serves two (query, chunk of 32 hits) work items, one per half-warp, so short hit lists
+// waste fewer lanes.  Hits k = 2*lane16, 2*lane16+1 of the length-sorted chunk share a lane (similar target lengths).
+// Scores must stay below 32000 (checked, fail loudly).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sw_pack_scores(uint32_t wa, uint32_t wb, int k) {
+    // halfword 0 = sign-extended byte k of wa, halfword 1 = sign-extended byte k of wb  (PRMT with msb replication)
+    const uint32_t sel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
+    return __byte_perm(wa, wb, sel);
+}
+
+template <int RBK>
+__device__ __forceinline__ void sw_sweep_block2(const int8_t *profB, uint32_t profStride, const uint8_t *__restrict__ tA, int lenA,
+                                                const uint8_t *__restrict__ tB, int lenB, uint2 *myBnd, bool hasTop, bool hasBottom,
+                                                uint32_t go2, uint32_t negE2, uint32_t &mx) {
+    uint32_t Hp[RBK], E[RBK];
+#pragma unroll
+    for (int r = 0; r < RBK; r++) { Hp[r] = 0; E[r] = 0; }
+    const int n = lenA > lenB ? lenA : lenB;
+    const uint32_t MIN2 = 0x80008000u;
+    uint32_t prevTop = 0;
+    uint2 topNext = make_uint2(0u, 0u);
+    if (hasTop && n > 0) topNext = myBnd[0];
+    uint32_t taNext = lenA > 0 ? (uint32_t)tA[0] : 21u, tbNext = lenB > 0 ? (uint32_t)tB[0] : 21u;
+    for (int i = 0; i < n; i++) {
+        const uint2 top = topNext; const uint32_t ta = taNext, tb = tbNext;
+        if (i + 1 < n) {
+            taNext = (i + 1 < lenA) ? (uint32_t)tA[i + 1] : 21u; tbNext = (i + 1 < lenB) ? (uint32_t)tB[i + 1] : 21u;
+            if (hasTop) topNext = myBnd[(size_t)(i + 1) * 32u];
+        }
+        const uint4 *pa = reinterpret_cast<const uint4 *>(profB + ta * profStride);
+        const uint4 *pb = reinterpret_cast<const uint4 *>(profB + tb * profStride);
+        uint32_t wa[RBK / 4], wb[RBK / 4];
+#pragma unroll
+        for (int v = 0; v < RBK / 16; v++) {
+            const uint4 x = pa[v], y = pb[v];
+            wa[4 * v] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
+            wb[4 * v] = y.x; wb[4 * v + 1] = y.y; wb[4 * v + 2] = y.z; wb[4 * v + 3] = y.w;
+        }
+        const uint32_t hTop = top.x;
+        uint32_t F = top.y;
+        uint32_t diag = prevTop; prevTop = hTop;
+        uint32_t gUp = 0;
+#pragma unroll
+        for (int r = 0; r < RBK; r++) {
+            const uint32_t s = sw_pack_scores(wa[r >> 2], wb[r >> 2], r & 3);
+            const uint32_t f = (r == 0) ? F : __viaddmax_s16x2(F, negE2, gUp);
+            const uint32_t t1 = __viaddmax_s16x2(diag, s, E[r]);
+            const uint32_t h = __vimax_s16x2_relu(t1, f);
+            diag = Hp[r]; Hp[r] = h;
+            const uint32_t g = __viaddmax_s16x2(h, go2, MIN2);      // h - gapOpen (go2 holds -gapOpen in both halves)
+            E[r] = __viaddmax_s16x2_relu(E[r], negE2, g);
+            F = f; gUp = g;
+            mx = __vmaxs2(mx, h);
+        }
+        if (hasBottom) myBnd[(size_t)i * 32u] = make_uint2(Hp[RBK - 1], __viaddmax_s16x2_relu(F, negE2, gUp));
+    }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows2(
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
+    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
+    uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
+    extern __shared__ __align__(16) unsigned char dynProf[];
+    __shared__ int8_t sMat8[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15u;
+    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)(wib * 2u + half) * 22u * profStride;   // row 21 = padding residue
+    uint2 *myBnd = bnd + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * maxT * 32u + lane;
+    const uint32_t chunkBase = chunkOff[pBegin], chunkEnd = chunkOff[pEnd];
+    const uint32_t negE2 = (uint32_t)(uint16_t)(int16_t)(-gapE) * 0x10001u, go2 = (uint32_t)(uint16_t)(int16_t)(-gapO) * 0x10001u;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = chunkBase + atomicAdd(counter, 2u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0) + half;          // half-warp 0 / 1 take consecutive work items
+        if (__all_sync(0xffffffffu, chunk >= chunkEnd)) break;
+        const bool haveItem = chunk < chunkEnd;
+        uint32_t qi = 0, kk0 = 0, cnt = 0; int L = 0; uint64_t qb = 0;
+        if (haveItem) {
+            uint32_t lo = pBegin, hi = pEnd;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunkOff[mid] <= chunk) lo = mid; else hi = mid; }
+            qi = order[lo]; kk0 = (chunk - chunkOff[lo]) * 32u + l16 * 2u; cnt = hitCount[qi];
+            qb = qoff[qi]; L = (int)(qoff[qi + 1] - qb);
+        }
+        const int nb = (L + RB - 1) / RB;
+        __syncwarp();
+        if (haveItem) for (uint32_t idx = l16; idx < 22u * profStride; idx += 16u) {
+            const uint32_t t = idx / profStride, j = idx - t * profStride;
+            prof[idx] = (t < 21u && j < (uint32_t)L) ? (int8_t)(sMat8[t * 21 + qres[qb + j]] + cb[qb + j]) : (int8_t)-64;
+        }
+        __syncwarp();
+        const bool actA = haveItem && kk0 < cnt, actB = haveItem && kk0 + 1 < cnt;
+        size_t slotA = 0, slotB = 0; int lenA = 0, lenB = 0; const uint8_t *tA = tseq, *tB = tseq;
+        if (actA) { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kk0] : kk0; slotA = (size_t)qi * maxHits + k;
+                    const uint32_t tid = hits[slotA].seqId; const uint64_t tb = toff[tid]; lenA = (int)(toff[tid + 1] - tb); tA = tseq + tb; }
+        if (actB) { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kk0 + 1] : kk0 + 1; slotB = (size_t)qi * maxHits + k;
+                    const uint32_t tid = hits[slotB].seqId; const uint64_t tb = toff[tid]; lenB = (int)(toff[tid + 1] - tb); tB = tseq + tb; }
+        uint32_t mx = 0;
+        for (int b = 0; b < nb; b++) {
+            const bool hasTop = b > 0, hasBottom = b < nb - 1;
+            if (L - b * RB <= RB / 2) sw_sweep_block2<RB / 2>(prof + b * RB, profStride, tA, lenA, tB, lenB, myBnd, hasTop, hasBottom, go2, negE2, mx);
+            else sw_sweep_block2<RB>(prof + b * RB, profStride, tA, lenA, tB, lenB, myBnd, hasTop, hasBottom, go2, negE2, mx);
+            cells += (unsigned long long)(lenA + lenB) * ((L - b * RB <= RB / 2) ? RB / 2 : RB);
+        }
+        const int sA = (int)(int16_t)(mx & 0xFFFFu), sB = (int)(int16_t)(mx >> 16);
+        if (actA) { scoreOut[slotA] = sA; if (sA >= 32000) atomicExch(errFlag, 1u);
+                    if (sA >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotA; else atomicExch(errFlag, 2u); } }
+        if (actB) { scoreOut[slotB] = sB; if (sB >= 32000) atomicExch(errFlag, 1u);
+                    if (sB >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotB; else atomicExch(errFlag, 2u); } }
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
 // one alignment per lane: forward with end tracking, then reverse to the start.  slot = query * maxHits + hit rank (slot < 2^32).
 __global__ void __launch_bounds__(128) k_sw_trace(const uint32_t *__restrict__ passList, uint32_t nPass, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
                                                   const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
