@@ -465,15 +465,16 @@ static int align_pipeline(mb200_ctx *c) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
         if (packed) {
-            const size_t smem = (size_t)MB_SWR_WARPS * 2u * 22u * strides[k];
+            int W = (int)((100u * 1024u) / (2u * 22u * strides[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
+            const size_t smem = (size_t)W * 2u * 22u * strides[k];
             CU(cudaFuncSetAttribute(k_sw_rows2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows2<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
+            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows2<32>, W * 32, smem)); if (perSM < 1) perSM = 1;
             const int blocks = c->nSM * perSM;
-            TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u * 2u));
-            k_sw_rows2<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
-                                                                          c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
-                                                                          strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
-                                                                          reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
+            TRY(c->dBnd.alloc((size_t)blocks * W * maxT * 32u * 2u));
+            k_sw_rows2<32><<<blocks, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                             c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                             strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
+                                                             reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
         } else {
             const size_t smem = (size_t)MB_SWR_WARPS * 21u * strides[k];
             CU(cudaFuncSetAttribute(k_sw_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
