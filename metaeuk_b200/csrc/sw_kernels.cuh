@@ -245,8 +245,11 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sw_pack_scores(uint32_t wa, uint32_t wb, int k) {
     // halfword 0 = sign-extended byte k of wa, halfword 1 = sign-extended byte k of wb  (PRMT with msb replication)
+    // (__byte_perm masks the selector nibbles to 3 bits, so the sign-replicating form needs the PTX instruction itself)
     const uint32_t sel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
-    return __byte_perm(wa, wb, sel);
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(wa), "r"(wb), "r"(sel));
+    return d;
 }
 
 template <int RBK>
