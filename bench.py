@@ -324,6 +324,11 @@ def main():
                  "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev")},
                  "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "entries": ctx.index_sizes()[0]}})
+    ph = st.get("pref_phase_cycles") or []
+    if sum(ph) > 0:
+        names = ["clear", "P1 windows+scan", "P2 items+scan", "P3 kmers/offsets+scan", "P4 gather hits", "P5 split", "P6-7 double hits", "P8-9 diag scores",
+                 "P10 best diag", "P11-12 threshold/sort", "P13-14 output", "", "", "", "", "between queries"]
+        base["prefilter_phase_pct"] = {names[i]: round(100.0 * ph[i] / sum(ph), 1) for i in range(16) if ph[i]}
     if wl["align"] and (st["ms_sw_fwd"] + st["ms_sw_rev"]) > 0:
         base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
     # CPU baseline (oracle port) on a bounded sample of the same workload, rank 0, N=1 only

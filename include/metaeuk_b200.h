@@ -78,6 +78,7 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     uint64_t query_residues, n_queries;
     double ms_prep, ms_prefilter, ms_sw_fwd, ms_sw_rev, ms_chain, ms_h2d, ms_d2h, ms_host;
     uint32_t launches, pad;
+    uint64_t pref_phase_cycles[16];   /* k_prefilter: CTA cycles summed over queries, per phase; [15] = between queries */
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T,
     extern __shared__ __align__(16) unsigned char smemRaw[];
     MbPrefShared *sh = reinterpret_cast<MbPrefShared *>(smemRaw);
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sh->ungMat[i] = ungMat8[i];
+    if (threadIdx.x == 0) { for (int i = 0; i < 16; i++) sh->phaseAcc[i] = 0; sh->phaseT = clock64(); }
     const MbPrefScratch W = scratch[blockIdx.x];
     __syncthreads();
     for (;;) {
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T,
         mb_prefilter_query(T, W, sh, qres + b, bias + b, corr + b, L, out + (size_t)qi * T.maxHits, outCount + qi, outStatus + qi, stats);
         __syncthreads();
     }
+    if (threadIdx.x == 0 && stats) for (int i = 0; i < 16; i++) atomicAdd(&stats->phase[i], sh->phaseAcc[i]);
 }
 
 #include "sw_kernels.cuh"
@@ -404,6 +406,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
         return fail(status[i] == MB_ST_OVERFLOW ? MB200_E_OVERFLOW : MB200_E_LIMIT, "query %u: prefilter status %u (work list capacity exceeded or sequence too long)", i, status[i]);
     MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
     c->st.kmers = hs.kmers; c->st.lookups = hs.lookups; c->st.db_matches = hs.dbMatches; c->st.double_hits = hs.doubleHits; c->st.diag_cells = hs.diagCells; c->st.pref_results = hs.results;
+    for (int i = 0; i < 16; i++) c->st.pref_phase_cycles[i] = hs.phase[i];
     c->havePref = true;
     return 0;
 }
@@ -510,11 +513,19 @@ static int align_pipeline(mb200_ctx *c) {
         TRY(upload(c->dPassList.p + nPass, extra.data(), extra.size() * 4, c->stream)); nPass += (uint32_t)extra.size();
     }
     if (nPass) {
-        const int blocks = c->nSM * 8; const size_t nWarps = (size_t)blocks * 4;
-        TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32)); TRY(c->dTrace.alloc(nPass));
+        const int blocks = c->nSM * 4; const size_t nWarps = (size_t)blocks * 4;
+        const char *trSel = getenv("MB200_TRACE_KERNEL");
         CU(cudaEventRecord(c->ev0, c->stream));
-        k_sw_trace<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
-                                                  c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
+        TRY(c->dTrace.alloc(nPass));
+        if (trSel && strcmp(trSel, "v1") == 0) {
+            TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32));
+            k_sw_trace<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                                                      c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
+        } else {
+            TRY(c->dHE.alloc(nWarps * maxT * 32));
+            k_sw_trace2<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                                                       c->par.gap_open, c->par.gap_extend, c->dHE.p, maxT, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
+        }
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         c->hTrace.resize(nPass);

@@ -68,10 +68,12 @@ struct MbPrefShared {
     CtaScratch cs;
     uint32_t hist[256];
     uint32_t cnt[8];       // 0 nMulti, 1 nCand, 2 nSurv, 3 thr, 4 nPass, 5 rescale, 6 status
+    long long phaseT; unsigned long long phaseAcc[16];
     int8_t ungMat[448];
     uint32_t slots[MB_NSLOT / 16];
-    uint32_t sItemOff[MB_SM_P + 2], sWinK[MB_SM_P + 2]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P], sN0[MB_SM_P];
-    union {   // work space of the phases after the hit gathering: hash grouping of the multi list / short sorts
+    uint32_t sItemOff[MB_SM_P + 1]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P];
+    uint32_t sKmerOff[MB_SM_I + 1];
+    union {   // the k-mer -> hit offsets are dead once the hits are gathered; the sorts that follow reuse the space
         uint32_t sHitOff[MB_SM_K + 2];
         uint64_t sSort[MB_SM_S];
     };
@@ -98,7 +100,7 @@ MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t id1) {
     return slot;
 }
 
-struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; };
+struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; unsigned long long phase[16]; };
 
 MB_DEV uint32_t mb_count_ge(const uint16_t *cnt3, uint32_t row, int x) {
     if (x <= MB_CNT_MIN) return MB_N3;
@@ -161,23 +163,30 @@ __device__ __forceinline__ int mb_diag_score_warp(const int8_t *ungMat, const ui
 }
 #endif
 
+// per-phase cycle accounting (thread 0 of the CTA; sums over all queries land in MbPrefStats::phase)
+#if MB_DEVICE_BUILD
+#define MB_PHASE(n) do { if (threadIdx.x == 0) { const long long t_ = clock64(); sh->phaseAcc[n] += (unsigned long long)(t_ - sh->phaseT); sh->phaseT = t_; } } while (0)
+#else
+#define MB_PHASE(n) ((void)0)
+#endif
+
 // One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
 MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
                                const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
     const uint32_t P = (L >= 10) ? (L - 9) : 0;   // Sequence::hasNextKmer, spaced pattern length 10 (Sequence.h:23,92-94)
+    MB_PHASE(15);   // time between queries (queue pop, previous epilogue)
     CTA_SINGLE { for (int i = 0; i < 8; i++) sh->cnt[i] = 0; }
     CTA_FOR(i, 256) sh->hist[i] = 0;
     CTA_FOR(i, MB_NSLOT / 16) sh->slots[i] = 0;
     CTA_SYNC();
+    MB_PHASE(0);    // clearing
     if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
     if (P == 0) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OK; } return; }
 
-    uint32_t *const winOff = (P <= MB_SM_P) ? sh->sItemOff : W.itemOff;   // per-window counts, then exclusive offsets (k-mers, later hits)
-    uint32_t *const winK = (P <= MB_SM_P) ? sh->sWinK : W.kmerOff;       // k-mer base of every window (kept while winOff is reused for hits)
+    uint32_t *const itemOff = (P <= MB_SM_P) ? sh->sItemOff : W.itemOff;
     int16_t *const wThr = (P <= MB_SM_P) ? sh->sThr : W.wThr;
     uint16_t *const wI0 = (P <= MB_SM_P) ? sh->sI0 : W.wI0;
     uint16_t *const wI1 = (P <= MB_SM_P) ? sh->sI1 : W.wI1;
-    uint16_t *const wN0 = (P <= MB_SM_P) ? sh->sN0 : W.kmerP;
     // ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140)
     CTA_FOR(p, P) {
         const uint8_t *w = q + p;
@@ -195,132 +204,83 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
             const short cutoff1 = (short)(thr - top1);
             n0 = mb_count_ge(T.cnt3, i0, cutoff1);
         }
-        wN0[p] = (uint16_t)n0; wThr[p] = (int16_t)thr; wI0[p] = (uint16_t)i0; wI1[p] = (uint16_t)i1;
+        itemOff[p] = n0; wThr[p] = (int16_t)thr; wI0[p] = (uint16_t)i0; wI1[p] = (uint16_t)i1;
     }
     CTA_SYNC();
-#if MB_DEVICE_BUILD
-    // ---- P2 (one warp per window): number of similar k-mers of the window = sum over first-half neighbours of the second-half count
-    //      (the staircase of calculateArrayProduct, KmerGenerator.cpp:186-216)
-    {
-        const uint32_t lane = threadIdx.x & 31u;
-        CTA_WARP_FOR(p, P) {
-            const uint32_t n0 = wN0[p]; const int thr = wThr[p]; const uint32_t i0 = wI0[p], i1 = wI1[p];
-            uint32_t sum = 0;
-            for (uint32_t i = lane; i < n0; i += 32) { const int s0 = (int16_t)(T.sim3[(size_t)i0 * MB_N3 + i] & 0xFFFFu); sum += mb_count_ge(T.cnt3, i1, (short)(thr - s0)); }
-            sum = __reduce_add_sync(0xffffffffu, sum);
-            if (lane == 0) winOff[p] = sum;
-        }
+    const uint32_t I = cta_exclusive_scan(itemOff, P, &sh->cs);
+    MB_PHASE(1);
+    if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+
+    // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216)
+    uint32_t *const kmerOff = (I <= MB_SM_I) ? sh->sKmerOff : W.kmerOff;
+    CTA_FOR(it, I) {
+        const uint32_t p = cta_find_segment(itemOff, P, it);
+        const uint32_t i = it - itemOff[p];
+        const int s0 = (int16_t)(T.sim3[(size_t)wI0[p] * MB_N3 + i] & 0xFFFFu);
+        const short cutoff2 = (short)((int)wThr[p] - s0);
+        kmerOff[it] = mb_count_ge(T.cnt3, wI1[p], cutoff2);
     }
     CTA_SYNC();
-    const uint32_t K = cta_exclusive_scan(winOff, P, &sh->cs);
+    const uint32_t K = cta_exclusive_scan(kmerOff, I, &sh->cs);
+    MB_PHASE(2);
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
-    // ---- P3 (one warp per window): enumerate the similar k-mers in the reference's nested-loop order, look up their index lists
-    {
-        const uint32_t lane = threadIdx.x & 31u;
-        CTA_WARP_FOR(p, P) {
-            const uint32_t n0 = wN0[p]; const int thr = wThr[p]; const uint32_t i0 = wI0[p], i1 = wI1[p];
-            const uint32_t kb = winOff[p];
-            uint32_t kw = 0, hits = 0;
-            for (uint32_t ib = 0; ib < n0; ib += 32) {
-                const uint32_t i = ib + lane; const bool valid = i < n0;
-                const uint32_t e0 = valid ? T.sim3[(size_t)i0 * MB_N3 + i] : 0u;
-                const uint32_t n1 = valid ? mb_count_ge(T.cnt3, i1, (short)(thr - (int)(int16_t)(e0 & 0xFFFFu))) : 0u;
-                uint32_t inc = n1;
+
+    // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
+    uint32_t *const hitOff = (K <= MB_SM_K) ? sh->sHitOff : W.hitOff;
+    // Each thread owns a contiguous run of k-mers; it walks the (item, window) cursors forward instead of searching, and handles
+    // the run in batches of 4 so that the dependent global loads of a batch (sim3 rows -> bitmap -> offsets) are all in flight together.
+    CTA_CHUNK(kb, ke, K);
+    uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;
+    uint32_t pw = (kb < ke) ? cta_find_segment(itemOff, P, it) : 0;
+    for (uint32_t k0 = kb; k0 < ke; k0 += 4) {
+        uint32_t pv[4], iv[4], jv[4], a0[4], a1[4], km[4], lo[4], hi[4]; bool ok[4], nz[4];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
-                const uint32_t o = inc - n1, Tb = __shfl_sync(0xffffffffu, inc, 31);
-                for (uint32_t c = 0; c < Tb; c += 32) {
-                    const bool inR = valid && o >= c && o < c + 32;
-                    const uint32_t mask = __reduce_or_sync(0xffffffffu, inR ? (1u << (o - c)) : 0u);
-                    const uint32_t prior = __popc(__ballot_sync(0xffffffffu, valid && o < c));
-                    const uint32_t kk = c + lane; const bool act = kk < Tb;
-                    const uint32_t item = (prior + __popc(mask & ((2u << lane) - 1u)) - 1u) & 31u;
-                    const uint32_t oItem = __shfl_sync(0xffffffffu, o, item), e0Item = __shfl_sync(0xffffffffu, e0, item);
-                    uint32_t lo = 0, hi = 0;
-                    if (act) {
-                        const uint32_t j = kk - oItem;
-                        const uint32_t kmer = (e0Item >> 16) + (T.sim3[(size_t)i1 * MB_N3 + j] >> 16) * 8000u;
-                        if (!T.kmerBits || ((T.kmerBits[kmer >> 5] >> (kmer & 31u)) & 1u)) { lo = T.offsets[kmer]; hi = T.offsets[kmer + 1]; }
-                        W.kmerLo[kb + kw + kk] = lo; W.hitOff[kb + kw + kk] = hi - lo;
-                    }
-                    hits += hi - lo;
-                }
-                kw += Tb;
+        for (int u = 0; u < 4; u++) {
+            const uint32_t k = k0 + u; ok[u] = k < ke; pv[u] = 0; iv[u] = 0; jv[u] = 0;
+            if (ok[u]) {
+                while (kmerOff[it + 1] <= k) it++;
+                while (itemOff[pw + 1] <= it) pw++;
+                pv[u] = pw; iv[u] = it - itemOff[pw]; jv[u] = k - kmerOff[it];
             }
-            hits = __reduce_add_sync(0xffffffffu, hits);
-            if (lane == 0) { winK[p] = kb; winOff[p] = hits; }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a0[u] = 0; a1[u] = 0; if (ok[u]) { a0[u] = T.sim3[(size_t)wI0[pv[u]] * MB_N3 + iv[u]]; a1[u] = T.sim3[(size_t)wI1[pv[u]] * MB_N3 + jv[u]]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { km[u] = (a0[u] >> 16) + (a1[u] >> 16) * 8000u; nz[u] = ok[u]; if (ok[u] && T.kmerBits) nz[u] = (T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lo[u] = 0; hi[u] = 0; if (nz[u]) { lo[u] = T.offsets[km[u]]; hi[u] = T.offsets[km[u] + 1]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) { const uint32_t k = k0 + u; hitOff[k] = hi[u] - lo[u]; W.kmerLo[k] = lo[u]; W.kmerP[k] = (uint16_t)pv[u]; }
     }
     CTA_SYNC();
-    CTA_SINGLE { winK[P] = K; }
-    const uint32_t M = cta_exclusive_scan(winOff, P, &sh->cs);
+    const uint32_t M = cta_exclusive_scan(hitOff, K, &sh->cs);
+    MB_PHASE(3);
     if (M > T.capM || M >= (1u << MB_MAX_ARRIVAL_BITS)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
-    // ---- P4 (one warp per window): gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
-    {
-        const uint32_t lane = threadIdx.x & 31u;
-        CTA_WARP_FOR(p, P) {
-            const uint32_t kb = winK[p], Sp = winK[p + 1] - kb, hb = winOff[p];
-            uint32_t hw = 0;
-            for (uint32_t kc = 0; kc < Sp; kc += 32) {
-                const bool actK = kc + lane < Sp;
-                const uint32_t lo = actK ? W.kmerLo[kb + kc + lane] : 0u, len = actK ? W.hitOff[kb + kc + lane] : 0u;
-                uint32_t inc = len;
+
+    // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
+    CTA_CHUNK(hb, he, M);
+    uint32_t kk = (hb < he) ? cta_find_segment(hitOff, K, hb) : 0;
+    for (uint32_t h0 = hb; h0 < he; h0 += 4) {
+        uint32_t kv[4], ov[4], lov[4], ppv[4]; uint2 ev[4]; bool ok[4];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
-                const uint32_t ho = inc - len, Tc = __shfl_sync(0xffffffffu, inc, 31);
-                const uint32_t nzmask = __ballot_sync(0xffffffffu, len > 0);
-                for (uint32_t h = 0; h < Tc; h += 32) {
-                    const bool inR = len > 0 && ho >= h && ho < h + 32;
-                    const uint32_t mask = __reduce_or_sync(0xffffffffu, inR ? (1u << (ho - h)) : 0u);
-                    const uint32_t prior = __popc(__ballot_sync(0xffffffffu, len > 0 && ho < h));
-                    const uint32_t hh = h + lane; const bool act = hh < Tc;
-                    const uint32_t r = prior + __popc(mask & ((2u << lane) - 1u));   // 1-based rank among the non-empty lists of this chunk
-                    const uint32_t src = __fns(nzmask, 0, (int)(act ? r : 1u)) & 31u;
-                    const uint32_t hoS = __shfl_sync(0xffffffffu, ho, src), loS = __shfl_sync(0xffffffffu, lo, src);
-                    if (act) {
-                        const uint2 e = T.entries[(size_t)loS + (hh - hoS)];
-                        const uint32_t arrival = hb + hw + hh;
-                        const uint16_t diag16 = (uint16_t)(p - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
-                        W.A[arrival] = ((uint64_t)e.x << 37) | ((uint64_t)arrival << 16) | diag16;
-                        const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
-                        const uint32_t old = atomicOr(&sh->slots[slot >> 4], 1u << sft);
-                        if ((old >> sft) & 1u) atomicOr(&sh->slots[slot >> 4], 2u << sft);
-                    }
-                }
-                hw += Tc;
-            }
+        for (int u = 0; u < 4; u++) { const uint32_t h = h0 + u; ok[u] = h < he; kv[u] = 0; ov[u] = 0; if (ok[u]) { while (hitOff[kk + 1] <= h) kk++; kv[u] = kk; ov[u] = h - hitOff[kk]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lov[u] = 0; ppv[u] = 0; if (ok[u]) { lov[u] = W.kmerLo[kv[u]]; ppv[u] = W.kmerP[kv[u]]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { ev[u].x = 0; ev[u].y = 0; if (ok[u]) ev[u] = T.entries[(size_t)lov[u] + ov[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) {
+            const uint32_t h = h0 + u; const uint2 e = ev[u];
+            const uint16_t diag16 = (uint16_t)(ppv[u] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+            W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
+            const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+            const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+            if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
         }
     }
-#else
-    // serial restatement of P2-P4 for the CPU emulation build (same lists, same arrival order)
-    uint32_t K = 0, M = 0;
-    for (uint32_t p = 0; p < P; p++) {
-        const uint32_t n0 = wN0[p]; const int thr = wThr[p]; const uint32_t i0 = wI0[p], i1 = wI1[p];
-        for (uint32_t i = 0; i < n0; i++) {
-            const uint32_t e0 = T.sim3[(size_t)i0 * MB_N3 + i];
-            const uint32_t n1 = mb_count_ge(T.cnt3, i1, (short)(thr - (int)(int16_t)(e0 & 0xFFFFu)));
-            for (uint32_t j = 0; j < n1; j++) {
-                const uint32_t kmer = (e0 >> 16) + (T.sim3[(size_t)i1 * MB_N3 + j] >> 16) * 8000u;
-                K++;
-                if (K > T.capK) { *outCount = 0; *outStatus = MB_ST_OVERFLOW; return; }
-                if (T.kmerBits && !((T.kmerBits[kmer >> 5] >> (kmer & 31u)) & 1u)) continue;
-                for (uint32_t x = T.offsets[kmer]; x < T.offsets[kmer + 1]; x++) {
-                    if (M >= T.capM || M + 1 >= (1u << MB_MAX_ARRIVAL_BITS)) { *outCount = 0; *outStatus = MB_ST_OVERFLOW; return; }
-                    const uint2 e = T.entries[x];
-                    const uint16_t diag16 = (uint16_t)(p - (e.y & 0xFFFFu));
-                    W.A[M] = ((uint64_t)e.x << 37) | ((uint64_t)M << 16) | diag16;
-                    const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
-                    const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
-                    if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
-                    M++;
-                }
-            }
-        }
-    }
-    (void)winOff; (void)winK;
-#endif
     CTA_SYNC();
     // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
+    MB_PHASE(4);
     //               targets possibly seen more than once -> multi list
     CTA_FOR(h, M) {
         const uint64_t w = W.A[h];
@@ -334,6 +294,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     CTA_SYNC();
     const uint32_t nMulti = sh->cnt[0];
+    MB_PHASE(5);
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
     if (nMulti <= MB_HT_N / 2) {
         // Sort-free: group the multi list by target with a shared-memory hash table (the hit offsets' space is free now), then every
@@ -400,6 +361,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     CTA_SYNC();
     const uint32_t D = sh->cnt[1];
+    MB_PHASE(6);
     // ---- P8/P9 ungapped diagonal scores
     mb_sort_list(W.C, D, sh);
     uint32_t myCells = 0;
@@ -417,6 +379,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     CTA_SYNC();
     // ---- P10 best diagonal per target: first maximum in arrival order (keepMaxElement, CacheFriendlyOperations.cpp:350-380)
+    MB_PHASE(7);
     CTA_FOR(c, D) {
         const uint32_t id = MB_W_SEQ(W.C[c]);
         if (c == 0 || MB_W_SEQ(W.C[c - 1]) != id) {
@@ -434,6 +397,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     CTA_SYNC();
     const uint32_t nSurv = sh->cnt[2];
+    MB_PHASE(8);
     // ---- P11 score threshold (computeScoreThreshold, QueryMatcher.h:206-216; QueryMatcher.cpp:153-155)
     CTA_SINGLE {
         const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
@@ -474,6 +438,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     }
     const uint32_t nSel = nPass < maxHits ? nPass : maxHits;
     // ---- P13 getResult<UNGAPPED_DIAGONAL_SCORE> (QueryMatcher.cpp:363-420): exact score when the 8-bit score saturated
+    MB_PHASE(9);
     CTA_FOR(i, nSel) {
         const uint64_t w = W.B[i]; const uint32_t ci = (uint32_t)(w & 0x1FFFFFu);
         const uint32_t cnt = 255u - (uint32_t)(w >> 53);
@@ -503,6 +468,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
 #endif
     CTA_SINGLE { *outCount = nSel; *outStatus = MB_ST_OK; }
     CTA_SYNC();
+    MB_PHASE(10);   // P13/P14 + output
 }
 
 // ---------------------------------------------------------------------------------------------------

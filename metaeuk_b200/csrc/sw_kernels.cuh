@@ -441,6 +441,103 @@ __global__ void __launch_bounds__(128) k_sw_trace(const uint32_t *__restrict__ p
     if (cells) atomicAdd(cellCount, cells);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_sw_trace2: end / start coordinates for the alignments on the pass list, one alignment per lane (every lane its own query and
+// target), same register-resident row-block sweep as k_sw_rows (16 rows per block).  A pass returns the best cell under the
+// reference's tie rule -- maximum score, then the FIRST column reaching it, then the smallest row in that column
+// (StripedSmithWaterman.cpp:873-912) -- tracked as a packed key (score << 16 | 0xFFFF - column).  The reverse pass is the same sweep
+// on the reversed query prefix / target prefix: the first reversed column holding the forward score is where the reference's
+// early termination stops (:900), so no early exit is needed for identical coordinates.
+// ---------------------------------------------------------------------------------------------------------------------
+#define MB_TR_RB 16
+__device__ __forceinline__ void sw_trace_pass(const int8_t *sMatT /* [22][32] : [q][t] */, const uint8_t *__restrict__ q, const int8_t *__restrict__ cb, int qFirst, int qStep,
+                                              int qn, const uint8_t *__restrict__ t, int tFirst, int tStep, int tn, uint32_t *myBnd, int gapO, int negE,
+                                              int &bestScore, int &bestCol, int &bestRow) {
+    uint32_t bestKey = 0; int bRow = 0;
+    const int nb = (qn + MB_TR_RB - 1) / MB_TR_RB;
+    for (int b = 0; b < nb; b++) {
+        uint32_t QR[MB_TR_RB];   // (q_r * 32) | cb_r << 16 ; rows past the end use the padding row 21
+#pragma unroll
+        for (int r = 0; r < MB_TR_RB; r++) {
+            const int row = b * MB_TR_RB + r;
+            uint32_t v = 21u * 32u;
+            if (row < qn) { const int qi = qFirst + qStep * row; v = ((uint32_t)q[qi] * 32u) | ((uint32_t)(uint8_t)cb[qi] << 16); }
+            QR[r] = v;
+        }
+        int Hp[MB_TR_RB], E[MB_TR_RB];
+#pragma unroll
+        for (int r = 0; r < MB_TR_RB; r++) { Hp[r] = 0; E[r] = 0; }
+        const bool hasTop = b > 0, hasBottom = b < nb - 1;
+        int prevTop = 0;
+        for (int i = 0; i < tn; i++) {
+            const uint32_t tc = (uint32_t)t[tFirst + tStep * i];
+            const uint32_t top = hasTop ? myBnd[(size_t)i * 32u] : 0u;
+            const int hTop = (int)(top & 0xFFFFu);
+            int F = (int)(top >> 16);
+            int diag = prevTop; prevTop = hTop;
+            int gUp = 0;
+            const uint32_t colKey = 0xFFFFu - (uint32_t)i;
+#pragma unroll
+            for (int r = 0; r < MB_TR_RB; r++) {
+                const int s = (int)sMatT[(QR[r] & 0xFFFFu) + tc] + (int)(int8_t)(QR[r] >> 16);
+                const int f = (r == 0) ? F : __viaddmax_s32(F, negE, gUp);
+                const int t1 = __viaddmax_s32(diag, s, E[r]);
+                const int h = __vimax_s32_relu(t1, f);
+                diag = Hp[r]; Hp[r] = h;
+                const int g = h - gapO;
+                E[r] = __viaddmax_s32_relu(E[r], negE, g);
+                F = f; gUp = g;
+                const uint32_t key = ((uint32_t)h << 16) | colKey;
+                if (key > bestKey) { bestKey = key; bRow = b * MB_TR_RB + r; }
+            }
+            if (hasBottom) myBnd[(size_t)i * 32u] = (uint32_t)Hp[MB_TR_RB - 1] | ((uint32_t)__viaddmax_s32_relu(F, negE, gUp) << 16);
+        }
+    }
+    bestScore = (int)(bestKey >> 16); bestCol = (int)(0xFFFFu - (bestKey & 0xFFFFu)); bestRow = bRow;
+}
+
+__global__ void __launch_bounds__(128) k_sw_trace2(const uint32_t *__restrict__ passList, uint32_t nPass, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
+                                                   const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+                                                   const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat,
+                                                   int gapO, int gapE, uint32_t *__restrict__ bnd /* [warp][maxT][32] */, uint32_t maxT,
+                                                   SwTraceOut *__restrict__ outs, uint32_t *counter, unsigned long long *cellCount) {
+    __shared__ int8_t sMatT[22 * 32];
+    for (int i = threadIdx.x; i < 22 * 32; i += blockDim.x) { const int qq = i >> 5, tt = i & 31; sMatT[i] = (qq < 21 && tt < 21) ? (int8_t)alnMat[tt * 21 + qq] : (int8_t)-64; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t *myBnd = bnd + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * maxT * 32u + lane;
+    const int negE = -gapE;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nPass) break;
+        const uint32_t idx = base + lane;
+        if (idx >= nPass) continue;
+        const uint32_t slot = passList[idx];
+        const uint32_t qi = slot / maxHits;
+        const uint32_t tid = hits[slot].seqId;
+        const uint8_t *q = qres + qoff[qi]; const int8_t *c = cb + qoff[qi]; const int L = (int)(qoff[qi + 1] - qoff[qi]);
+        const uint8_t *t = tseq + toff[tid]; const int tLen = (int)(toff[tid + 1] - toff[tid]);
+        int sc, col, row;
+        sw_trace_pass(sMatT, q, c, 0, 1, L, t, 0, 1, tLen, myBnd, gapO, negE, sc, col, row);
+        cells += (unsigned long long)L * tLen;
+        SwTraceOut o; o.slot = slot; o.score = sc; o.qEnd = row; o.dbEnd = col; o.qStart = -1; o.dbStart = -1; o.flag = 0; o.pad = 0;
+        if (sc <= 0) { o.dbEnd = -1; o.qEnd = L - 1; }
+        else {
+            int rs, rcol, rrow;
+            sw_trace_pass(sMatT, q, c, row, -1, row + 1, t, col, -1, col + 1, myBnd, gapO, negE, rs, rcol, rrow);
+            cells += (unsigned long long)(row + 1) * (col + 1);
+            o.dbStart = col - rcol; o.qStart = row - rrow;
+            if (rs != sc) o.flag = 1;
+        }
+        if (sc >= 32000) o.flag |= 2;
+        outs[idx] = o;
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
 // exclusive scans over the prefilter result: pairOff[i] (natural query order) and chunkOff[p] (length-sorted order, 32 hits per chunk)
 __global__ void __launch_bounds__(MB_CTA_THREADS) k_scan_counts(const uint32_t *__restrict__ hitCount, const uint32_t *__restrict__ order, uint32_t nQ,
                                                                 uint32_t *pairOff, uint32_t *chunkOff) {

@@ -34,7 +34,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kmers", "lookups", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd",
                                            "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
                [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
-               [("launches", C.c_uint32), ("pad", C.c_uint32)]
+               [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16)]
 
 
 class Mb200Error(RuntimeError):
@@ -243,4 +243,6 @@ class Context:
     def stats(self):
         s = Stats()
         self._check(self.L.mb200_stats_get(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in Stats._fields_ if not k.startswith("pad")}
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if not k.startswith("pad")}
+        d["pref_phase_cycles"] = [int(x) for x in s.pref_phase_cycles]
+        return d
