@@ -191,7 +191,7 @@ def main():
             return
         prot, poff = gen_proteins(wl["n_prot"])
         frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321)
-        n_sample = args.cpu_sample or (2000 if not wl["align"] else 1000)
+        n_sample = args.cpu_sample or (8192 if not wl["align"] else 2048)
         o, one, n = cpu_oracle_run(prot, poff, frag, foff, n_sample, wl["align"], threads)
         for _ in range(args.warmup):
             one()
@@ -216,27 +216,12 @@ def main():
     prot, poff = gen_proteins(wl["n_prot"])
     if rank == 0:
         ctx.index_build(prot, prot, poff)   # synthetic background proteins: masked == unmasked (masking is a host preprocessing input)
-        sizes = ctx.index_sizes()
-    if world > 1:
-        sz = torch.tensor(sizes if rank == 0 else [0, 0, 0, 0], dtype=torch.int64, device="cuda")
-        dist.broadcast(sz, 0)
-        sizes = [int(x) for x in sz.tolist()]
-        if rank != 0:
-            ctx.index_alloc(sizes)
-        torch.cuda.synchronize()
-        t_b0 = time.perf_counter()
-        for ptr, nb in ctx.index_buffers():   # the single collective of the path: replicate the index over NVLink
-            class _V:
-                pass
-            v = _V()
-            v.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-            dist.broadcast(torch.as_tensor(v, device="cuda"), 0)
-        torch.cuda.synchronize()
-        bcast_s = time.perf_counter() - t_b0
-        if rank != 0:
-            ctx.index_commit()
-    else:
-        bcast_s = 0.0
+    from metaeuk_b200 import multi
+    torch.cuda.synchronize()
+    t_b0 = time.perf_counter()
+    bcast_bytes = multi.replicate_index(ctx, rank, world)   # the single collective of the path: replicate the index over NVLink
+    torch.cuda.synchronize()
+    bcast_s = time.perf_counter() - t_b0 if world > 1 else 0.0
     index_s = time.perf_counter() - t_idx0
     frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321 + rank)
     nq = len(foff) - 1
@@ -288,16 +273,17 @@ def main():
     l0 = ctx.stats()["launches"]
     kernel_ms = []
     barrier()
+    ctx.timer_start()                      # CUDA events on the library's stream, around exactly K steps
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
         kernel_ms.append(ctx.stats()["ms_prefilter"])
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = ctx.timer_stop() * 1e-3
+    wall_dt = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, wall_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt, wall_dt = float(t[0].item()), float(t[1].item())
     launches = ctx.stats()["launches"] - l0
     st = ctx.stats()
     for _ in range(2):
@@ -323,8 +309,12 @@ def main():
                               "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "traffic": ncu_traffic()},
                  "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev")},
-                 "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "entries": ctx.index_sizes()[0]}})
-    ph = st.get("pref_phase_cycles") or []
+                 "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "broadcast_bytes": int(bcast_bytes), "entries": ctx.index_sizes()[0]},
+                 "timing": "value: CUDA events on the library stream around K steps, max over ranks (wall clock for the same region: %.3f ms/step); e2e: wall clock between device synchronisations (host post-processing is part of the call)" % (1000 * wall_dt / args.steps)})
+    ctx.option_set("phase_stats", 1)     # one extra, untimed, instrumented pass for the per-phase breakdown
+    ctx.prefilter_resident()
+    ph = ctx.stats().get("pref_phase_cycles") or []
+    ctx.option_set("phase_stats", 0)
     if sum(ph) > 0:
         names = ["clear", "P1 windows+scan", "P2 items+scan", "P3 kmers/offsets+scan", "P4 gather hits", "P5 split", "P6-7 double hits", "P8-9 diag scores",
                  "P10 best diag", "P11-12 threshold/sort", "P13-14 output", "", "", "", "", "between queries"]
@@ -333,7 +323,7 @@ def main():
         base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
     # CPU baseline (oracle port) on a bounded sample of the same workload, rank 0, N=1 only
     if args.gpus == 1:
-        n_sample = args.cpu_sample or (2000 if not wl["align"] else 1000)
+        n_sample = args.cpu_sample or (8192 if not wl["align"] else 2048)
         o, one, n = cpu_oracle_run(prot, poff, frag, foff, n_sample, wl["align"], threads)
         one()
         tcpu = one()

@@ -130,7 +130,13 @@ int mb200_align_resident(mb200_ctx *ctx);             /* aligns the resident pre
 /* dense layouts [n_q][max_res_list_len]; alns holds accepted alignments only, aln_count[i] of them */
 int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count, mb200_aln *alns, uint32_t *aln_count);
 
+/* tuning / diagnostic switches (results never depend on them): "phase_stats" 0|1 (per-phase cycle accounting in k_prefilter),
+ * "sw_kernel" 1|2 (one or two targets per lane), "trace_kernel" 1|2 */
+int mb200_option_set(mb200_ctx *ctx, const char *name, int64_t value);
 int mb200_stats_get(mb200_ctx *ctx, mb200_stats *out);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel and copy of this library is issued on) */
+int mb200_timer_start(mb200_ctx *ctx);
+int mb200_timer_stop(mb200_ctx *ctx, double *ms);
 double mb200_evalue(mb200_ctx *ctx, int raw_score, int q_len);   /* EvalueComputation::computeEvalue with the ctx's target residues */
 int mb200_bit_score(mb200_ctx *ctx, int raw_score);
 

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T,
     extern __shared__ __align__(16) unsigned char smemRaw[];
     MbPrefShared *sh = reinterpret_cast<MbPrefShared *>(smemRaw);
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sh->ungMat[i] = ungMat8[i];
-    if (threadIdx.x == 0) { for (int i = 0; i < 16; i++) sh->phaseAcc[i] = 0; sh->phaseT = clock64(); }
+    if (T.phaseStats && threadIdx.x == 0) { for (int i = 0; i < 16; i++) sh->phaseAcc[i] = 0; sh->phaseT = clock64(); }
     const MbPrefScratch W = scratch[blockIdx.x];
     __syncthreads();
     for (;;) {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T,
         mb_prefilter_query(T, W, sh, qres + b, bias + b, corr + b, L, out + (size_t)qi * T.maxHits, outCount + qi, outStatus + qi, stats);
         __syncthreads();
     }
-    if (threadIdx.x == 0 && stats) for (int i = 0; i < 16; i++) atomicAdd(&stats->phase[i], sh->phaseAcc[i]);
+    if (T.phaseStats && threadIdx.x == 0 && stats) for (int i = 0; i < 16; i++) atomicAdd(&stats->phase[i], sh->phaseAcc[i]);
 }
 
 #include "sw_kernels.cuh"
@@ -133,8 +133,9 @@ struct mb200_ctx {
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
     std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<mb200_hit> hFlatHits; std::vector<uint64_t> hHitOff;
     bool haveAln = false;
+    int optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
     mb200_stats st;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
 };
 
 static int upload(void *dst, const void *src, size_t bytes, cudaStream_t s) {
@@ -160,7 +161,8 @@ static int ctx_upload_matrices(mb200_ctx *c) {
 static int ctx_alloc_scratch(mb200_ctx *c) {
     const uint32_t capP = 32768, capI = 1u << (c->par.cap_items_log2 ? c->par.cap_items_log2 : 17), capK = 1u << (c->par.cap_kmers_log2 ? c->par.cap_kmers_log2 : 18),
                    capM = 1u << (c->par.cap_hits_log2 ? c->par.cap_hits_log2 : 19);
-    if (capM > (1u << MB_MAX_ARRIVAL_BITS)) return fail(MB200_E_ARG, "cap_hits_log2 > %d", MB_MAX_ARRIVAL_BITS);
+    if (capK > (1u << 18)) return fail(MB200_E_ARG, "cap_kmers_log2 > 18 (the k-mer ordinal is an 18-bit field)");
+    if (capM < capK || capM > (1u << 24)) return fail(MB200_E_ARG, "cap_hits_log2 must be in [cap_kmers_log2, 24]");
     if (c->nCta && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
     int smemBytes = (int)sizeof(MbPrefShared), perSM = 0;
     CU(cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
@@ -169,14 +171,13 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
     if (perSM > 2) perSM = 2;
     c->nCta = c->nSM * perSM;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((capK + 1) * 4) + al(capK * 4) + al(capK * 2) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
+    const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
     TRY(c->dScratchMem.alloc(per * c->nCta)); TRY(c->dScratch.alloc(c->nCta));
     std::vector<MbPrefScratch> hs(c->nCta);
     for (int i = 0; i < c->nCta; i++) {
         unsigned char *b = c->dScratchMem.p + per * i; MbPrefScratch &W = hs[i];
         W.itemOff = (uint32_t *)b; b += al((capP + 1) * 4); W.wThr = (int16_t *)b; b += al(capP * 2); W.wI0 = (uint16_t *)b; b += al(capP * 2); W.wI1 = (uint16_t *)b; b += al(capP * 2);
-        W.kmerOff = (uint32_t *)b; b += al((capI + 1) * 4); W.itemInfo = (uint32_t *)b; b += al(capI * 4); W.hitOff = (uint32_t *)b; b += al((capK + 1) * 4);
-        W.kmerLo = (uint32_t *)b; b += al(capK * 4); W.kmerP = (uint16_t *)b; b += al(capK * 2);
+        W.kmerOff = (uint32_t *)b; b += al((capI + 1) * 4); W.itemInfo = (uint32_t *)b; b += al(capI * 4);
         W.A = (uint64_t *)b; b += al((size_t)capM * 8); W.B = (uint64_t *)b; b += al((size_t)capM * 8); W.C = (uint64_t *)b; b += al((size_t)capM * 8); W.S = (int32_t *)b;
     }
     TRY(upload(c->dScratch.p, hs.data(), hs.size() * sizeof(MbPrefScratch), c->stream));
@@ -211,7 +212,7 @@ int mb200_ctx_create(int device, mb200_ctx **out) {
     c->device = device;
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); c->nSM = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->evT0)); CU(cudaEventCreate(&c->evT1));
     mb200_params_default(&c->par); memset(&c->st, 0, sizeof(c->st));
     *out = c; return 0;
 }
@@ -224,8 +225,29 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
-    if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
+    if (!c || !name) return fail(MB200_E_ARG, "null argument");
+    const std::string n(name);
+    if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
+    else if (n == "sw_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane) or 2 (two, packed 16-bit)"); c->optSwKernel = (int)value; }
+    else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
+    else return fail(MB200_E_ARG, "unknown option '%s'", name);
+    return 0;
+}
+
+int mb200_timer_start(mb200_ctx *c) {
+    if (!c) return fail(MB200_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); CU(cudaEventRecord(c->evT0, c->stream)); return 0;
+}
+
+int mb200_timer_stop(mb200_ctx *c, double *ms) {
+    if (!c || !ms) return fail(MB200_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device)); CU(cudaEventRecord(c->evT1, c->stream)); CU(cudaEventSynchronize(c->evT1));
+    float f = 0; CU(cudaEventElapsedTime(&f, c->evT0, c->evT1)); *ms = f; return 0;
 }
 
 int mb200_params_set(mb200_ctx *c, const mb200_params *p) {
@@ -389,7 +411,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     MbPrefTables T; memset(&T, 0, sizeof(T));
     T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
     T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
-    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM;
+    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM; T.phaseStats = c->optPhaseStats;
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
         k_prefilter<<<c->nCta, MB_CTA_THREADS, sizeof(MbPrefShared), c->stream>>>(T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p,
@@ -462,8 +484,7 @@ static int align_pipeline(mb200_ctx *c) {
     uint32_t maxT = 1; for (uint32_t t = 0; t < c->nT; t++) maxT = std::max<uint32_t>(maxT, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
     CU(cudaEventRecord(c->ev0, c->stream));
     const uint32_t bounds[3] = {pLong, firstLE(256), nQ}; const uint32_t strides[2] = {1024 + 16, 256 + 16};
-    const char *swSel = getenv("MB200_SW_KERNEL");   // "rows" = one target per lane (32-bit), default "rows2" = two targets per lane (packed 16-bit)
-    const bool packed = !(swSel && strcmp(swSel, "rows") == 0);
+    const bool packed = c->optSwKernel == 2;   // 1 = one target per lane (32-bit cells), 2 = two targets per lane (packed 16-bit cells)
     for (int k = 0; k < 2; k++) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
@@ -514,10 +535,9 @@ static int align_pipeline(mb200_ctx *c) {
     }
     if (nPass) {
         const int blocks = c->nSM * 4; const size_t nWarps = (size_t)blocks * 4;
-        const char *trSel = getenv("MB200_TRACE_KERNEL");
         CU(cudaEventRecord(c->ev0, c->stream));
         TRY(c->dTrace.alloc(nPass));
-        if (trSel && strcmp(trSel, "v1") == 0) {
+        if (c->optTraceKernel == 1) {
             TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32));
             k_sw_trace<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
                                                       c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);

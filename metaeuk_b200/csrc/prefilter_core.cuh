@@ -9,7 +9,9 @@
 // but organised for a GPU: the reference's per-target byte array scan in *arrival order* becomes
 //   (1) a 2-bit-per-slot shared-memory occupancy map that separates targets hit once from targets hit >= 2 times,
 //   (2) a sort of the (few) multi-hit entries by (target, arrival index) and a per-target run walk.
-// Arrival index = position in the reference's databaseHits buffer: (query position, similar-k-mer rank, list order).
+// Arrival order = order of the reference's databaseHits buffer: (query position, similar-k-mer rank, list order).  An index list holds
+// every target at most once and is sorted by target id, so that order is the lexicographic order of (k, seqId) with k = the ordinal of
+// the similar k-mer inside the query.  The hit word therefore carries k as its "arrival" field and no per-hit rank is ever computed.
 #pragma once
 #include "cta_prims.cuh"
 
@@ -44,6 +46,7 @@ struct MbPrefTables {
     int kmerThr, maxHits, minDiag;
     uint32_t binMask;          // BINSIZE - 1 of the reference's CacheFriendlyOperations<BINSIZE>
     uint32_t capP, capI, capK, capM;
+    uint32_t phaseStats;       // 1 = per-phase cycle accounting (diagnostic runs only)
 };
 
 struct MbPrefScratch {        // per-CTA global scratch
@@ -51,9 +54,6 @@ struct MbPrefScratch {        // per-CTA global scratch
     int16_t *wThr; uint16_t *wI0, *wI1;   // capP
     uint32_t *kmerOff;  // capI + 1
     uint32_t *itemInfo; // capI          p << 13 | i
-    uint32_t *hitOff;   // capK + 1
-    uint32_t *kmerLo;   // capK
-    uint16_t *kmerP;    // capK
     uint64_t *A, *B, *C;   // capM each (power of two)
     int32_t *S;            // capM
 };
@@ -61,7 +61,7 @@ struct MbPrefScratch {        // per-CTA global scratch
 // shared-memory homes of the expansion arrays (queries that exceed them use the global scratch instead)
 #define MB_SM_P 512
 #define MB_SM_I 4096
-#define MB_SM_K 8192
+#define MB_SM_NZ 4096
 #define MB_SM_S 4096
 
 struct MbPrefShared {
@@ -73,8 +73,10 @@ struct MbPrefShared {
     uint32_t slots[MB_NSLOT / 16];
     uint32_t sItemOff[MB_SM_P + 1]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P];
     uint32_t sKmerOff[MB_SM_I + 1];
-    union {   // the k-mer -> hit offsets are dead once the hits are gathered; the sorts that follow reuse the space
-        uint32_t sHitOff[MB_SM_K + 2];
+    uint16_t sItemIdx0[MB_SM_I];   // first-half neighbour 3-mer of every item (read once in P2, used by every k-mer of the item in P3)
+    union {   // the list of similar k-mers with a non-empty index list is dead once the hits are gathered; the sorts that follow reuse the space
+        uint64_t sNz[MB_SM_NZ];
+        uint32_t sHitOff[2 * MB_SM_NZ];   // hash table of the double-hit stage (keys | group offsets)
         uint64_t sSort[MB_SM_S];
     };
 };
@@ -92,11 +94,11 @@ MB_DEV void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
     }
 }
 
-#define MB_HT_LOG 12
-#define MB_HT_N (1u << MB_HT_LOG)   // 2 x MB_HT_N words must fit in sHitOff
-MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t id1) {
-    uint32_t slot = (id1 * 2654435761u) >> (32 - MB_HT_LOG);
-    while (htKey[slot] != id1) slot = (slot + 1u) & (MB_HT_N - 1u);
+#define MB_HT_LOG_MAX 12   // 2 x 2^12 words = sHitOff
+MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t htLog, uint32_t id1) {
+    const uint32_t mask = (1u << htLog) - 1u;
+    uint32_t slot = (id1 * 2654435761u) >> (32 - htLog);
+    while (htKey[slot] != id1) slot = (slot + 1u) & mask;
     return slot;
 }
 
@@ -165,7 +167,7 @@ __device__ __forceinline__ int mb_diag_score_warp(const int8_t *ungMat, const ui
 
 // per-phase cycle accounting (thread 0 of the CTA; sums over all queries land in MbPrefStats::phase)
 #if MB_DEVICE_BUILD
-#define MB_PHASE(n) do { if (threadIdx.x == 0) { const long long t_ = clock64(); sh->phaseAcc[n] += (unsigned long long)(t_ - sh->phaseT); sh->phaseT = t_; } } while (0)
+#define MB_PHASE(n) do { if (T.phaseStats && threadIdx.x == 0) { const long long t_ = clock64(); sh->phaseAcc[n] += (unsigned long long)(t_ - sh->phaseT); sh->phaseT = t_; } } while (0)
 #else
 #define MB_PHASE(n) ((void)0)
 #endif
@@ -213,74 +215,92 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
 
     // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216)
     uint32_t *const kmerOff = (I <= MB_SM_I) ? sh->sKmerOff : W.kmerOff;
-    CTA_FOR(it, I) {
-        const uint32_t p = cta_find_segment(itemOff, P, it);
-        const uint32_t i = it - itemOff[p];
-        const int s0 = (int16_t)(T.sim3[(size_t)wI0[p] * MB_N3 + i] & 0xFFFFu);
-        const short cutoff2 = (short)((int)wThr[p] - s0);
-        kmerOff[it] = mb_count_ge(T.cnt3, wI1[p], cutoff2);
+    uint16_t *const itemIdx0 = (I <= MB_SM_I) ? sh->sItemIdx0 : (uint16_t *)W.itemInfo;
+    for (uint32_t it0 = CTA_TID; it0 < I; it0 += 4 * CTA_NT) {   // 4 items per thread per round: the two dependent table loads of each are in flight together
+        uint32_t pv[4], a0[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t it = it0 + u * CTA_NT; ok[u] = it < I; pv[u] = ok[u] ? cta_find_segment(itemOff, P, it) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t it = it0 + u * CTA_NT; a0[u] = ok[u] ? T.sim3[(uint32_t)wI0[pv[u]] * MB_N3 + (it - itemOff[pv[u]])] : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) {
+            const uint32_t it = it0 + u * CTA_NT;
+            const short cutoff2 = (short)((int)wThr[pv[u]] - (int)(int16_t)(a0[u] & 0xFFFFu));
+            kmerOff[it] = mb_count_ge(T.cnt3, wI1[pv[u]], cutoff2);
+            itemIdx0[it] = (uint16_t)(a0[u] >> 16);
+        }
     }
     CTA_SYNC();
     const uint32_t K = cta_exclusive_scan(kmerOff, I, &sh->cs);
     MB_PHASE(2);
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
-    // ---- P3 similar k-mers in the reference's enumeration order; index list bounds (IndexTable::getDBSeqList, IndexTable.h:176-180)
-    uint32_t *const hitOff = (K <= MB_SM_K) ? sh->sHitOff : W.hitOff;
-    // Each thread owns a contiguous run of k-mers; it walks the (item, window) cursors forward instead of searching, and handles
-    // the run in batches of 4 so that the dependent global loads of a batch (sim3 rows -> bitmap -> offsets) are all in flight together.
-    CTA_CHUNK(kb, ke, K);
-    uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;
-    uint32_t pw = (kb < ke) ? cta_find_segment(itemOff, P, it) : 0;
-    for (uint32_t k0 = kb; k0 < ke; k0 += 4) {
-        uint32_t pv[4], iv[4], jv[4], a0[4], a1[4], km[4], lo[4], hi[4]; bool ok[4], nz[4];
+    // ---- P3 similar k-mers in the reference's enumeration order k = 0..K-1 (window, first-half rank, second-half rank); those whose
+    //      index list is non-empty (bitmap test, IndexTable::getDBSeqList, IndexTable.h:176-180) go to an unordered list of
+    //      (window | k | k-mer) words.  Each thread owns a contiguous run of k and walks items in the outer loop, so the inner loop over the
+    //      second-half rank touches consecutive sim3 entries of one row and nothing else.
+    {
+        CTA_CHUNK(kb, ke, K);
+        uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;
+        uint32_t pw = (kb < ke) ? cta_find_segment(itemOff, P, it) : 0;
+        uint32_t k = kb;
+        while (k < ke) {
+            while (itemOff[pw + 1] <= it) pw++;
+            const uint32_t o = kmerOff[it], oe = kmerOff[it + 1];
+            const uint32_t jEnd = ((ke < oe) ? ke : oe) - o;
+            const uint32_t idx0 = itemIdx0[it];
+            const uint32_t *row1 = T.sim3 + (uint32_t)wI1[pw] * MB_N3;
+            for (uint32_t j = k - o; j < jEnd; j++) {
+                const uint32_t km = idx0 + (row1[j] >> 16) * 8000u;
+                const bool nz = T.kmerBits ? ((T.kmerBits[km >> 5] >> (km & 31u)) & 1u) : (T.offsets[km + 1] != T.offsets[km]);
+                if (nz) {
+                    const uint32_t n = mb_atomic_add(&sh->cnt[7], 1u);
+                    const uint64_t w = ((uint64_t)pw << 44) | ((uint64_t)(o + j) << 26) | km;
+                    if (n < MB_SM_NZ) sh->sNz[n] = w; else W.B[n - MB_SM_NZ] = w;
+                }
+            }
+            k = o + jEnd; it++;
+        }
+    }
+    CTA_SYNC();
+    const uint32_t nNz = sh->cnt[7];
+    MB_PHASE(3);
+
+    // ---- P4 gather the index entries of the non-empty lists; mark slot occupancy (0 / 1 / >=2 hits)
+    for (uint32_t n0 = CTA_TID; n0 < nNz; n0 += 4 * CTA_NT) {
+        uint64_t wv[4]; uint32_t lo[4], len[4], base[4]; uint2 e0[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t n = n0 + u * CTA_NT; ok[u] = n < nNz; wv[u] = 0; if (ok[u]) wv[u] = (n < MB_SM_NZ) ? sh->sNz[n] : W.B[n - MB_SM_NZ]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lo[u] = 0; len[u] = 0; if (ok[u]) { const uint32_t km = (uint32_t)wv[u] & 0x3FFFFFFu; lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u]; } }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t k = k0 + u; ok[u] = k < ke; pv[u] = 0; iv[u] = 0; jv[u] = 0;
-            if (ok[u]) {
-                while (kmerOff[it + 1] <= k) it++;
-                while (itemOff[pw + 1] <= it) pw++;
-                pv[u] = pw; iv[u] = it - itemOff[pw]; jv[u] = k - kmerOff[it];
+            base[u] = 0;
+            if (len[u] && *(volatile uint32_t *)&sh->cnt[3] == 0u) {   // cnt[3] = overflow flag until P11 reuses it
+                base[u] = mb_atomic_add(&sh->cnt[6], len[u] <= T.capM ? len[u] : T.capM + 1u);
+                if (base[u] > T.capM || len[u] > T.capM - base[u]) { len[u] = 0; sh->cnt[3] = 1u; }
+            } else len[u] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { e0[u].x = 0; e0[u].y = 0; if (len[u]) e0[u] = T.entries[lo[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t pp = (uint32_t)(wv[u] >> 44), kk = (uint32_t)(wv[u] >> 26) & 0x3FFFFu;
+            for (uint32_t x = 0; x < len[u]; x++) {
+                const uint2 en = x ? T.entries[(size_t)lo[u] + x] : e0[u];
+                const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+                W.A[base[u] + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
+                const uint32_t slot = en.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+                const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+                if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { a0[u] = 0; a1[u] = 0; if (ok[u]) { a0[u] = T.sim3[(size_t)wI0[pv[u]] * MB_N3 + iv[u]]; a1[u] = T.sim3[(size_t)wI1[pv[u]] * MB_N3 + jv[u]]; } }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { km[u] = (a0[u] >> 16) + (a1[u] >> 16) * 8000u; nz[u] = ok[u]; if (ok[u] && T.kmerBits) nz[u] = (T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { lo[u] = 0; hi[u] = 0; if (nz[u]) { lo[u] = T.offsets[km[u]]; hi[u] = T.offsets[km[u] + 1]; } }
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (ok[u]) { const uint32_t k = k0 + u; hitOff[k] = hi[u] - lo[u]; W.kmerLo[k] = lo[u]; W.kmerP[k] = (uint16_t)pv[u]; }
     }
     CTA_SYNC();
-    const uint32_t M = cta_exclusive_scan(hitOff, K, &sh->cs);
-    MB_PHASE(3);
-    if (M > T.capM || M >= (1u << MB_MAX_ARRIVAL_BITS)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
-
-    // ---- P4 gather index entries in arrival order; mark slot occupancy (0 / 1 / >=2 hits)
-    CTA_CHUNK(hb, he, M);
-    uint32_t kk = (hb < he) ? cta_find_segment(hitOff, K, hb) : 0;
-    for (uint32_t h0 = hb; h0 < he; h0 += 4) {
-        uint32_t kv[4], ov[4], lov[4], ppv[4]; uint2 ev[4]; bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t h = h0 + u; ok[u] = h < he; kv[u] = 0; ov[u] = 0; if (ok[u]) { while (hitOff[kk + 1] <= h) kk++; kv[u] = kk; ov[u] = h - hitOff[kk]; } }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { lov[u] = 0; ppv[u] = 0; if (ok[u]) { lov[u] = W.kmerLo[kv[u]]; ppv[u] = W.kmerP[kv[u]]; } }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { ev[u].x = 0; ev[u].y = 0; if (ok[u]) ev[u] = T.entries[(size_t)lov[u] + ov[u]]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (ok[u]) {
-            const uint32_t h = h0 + u; const uint2 e = ev[u];
-            const uint16_t diag16 = (uint16_t)(ppv[u] - (e.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
-            W.A[h] = ((uint64_t)e.x << 37) | ((uint64_t)h << 16) | diag16;
-            const uint32_t slot = e.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
-            const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
-            if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
-        }
-    }
-    CTA_SYNC();
-    // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
+    const uint32_t M = sh->cnt[6];
     MB_PHASE(4);
+    if (sh->cnt[3]) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+    // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
     //               targets possibly seen more than once -> multi list
     CTA_FOR(h, M) {
         const uint64_t w = W.A[h];
@@ -296,31 +316,34 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     const uint32_t nMulti = sh->cnt[0];
     MB_PHASE(5);
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
-    if (nMulti <= MB_HT_N / 2) {
-        // Sort-free: group the multi list by target with a shared-memory hash table (the hit offsets' space is free now), then every
-        // hit looks up its predecessor *of the same target* (largest smaller arrival index) inside its group.
-        uint32_t *htKey = sh->sHitOff, *htOff = sh->sHitOff + MB_HT_N;
-        CTA_FOR(i, 2 * MB_HT_N) sh->sHitOff[i] = 0;
+    if (nMulti == 0) {
+    } else if (nMulti <= (1u << (MB_HT_LOG_MAX - 1))) {
+        // Sort-free: group the multi list by target with a shared-memory hash table (the k-mer list's space is free now), then every
+        // hit looks up its predecessor *of the same target* (largest smaller arrival key) inside its group.
+        uint32_t htLog = 6; while ((1u << htLog) < 2u * nMulti) htLog++;
+        const uint32_t htN = 1u << htLog;
+        uint32_t *htKey = sh->sHitOff, *htOff = sh->sHitOff + htN;
+        CTA_FOR(i, 2 * htN) sh->sHitOff[i] = 0;
         CTA_SYNC();
         CTA_FOR(e, nMulti) {
             const uint32_t id1 = MB_W_SEQ(W.B[e]) + 1u;
-            uint32_t slot = (id1 * 2654435761u) >> (32 - MB_HT_LOG);
+            uint32_t slot = (id1 * 2654435761u) >> (32 - htLog);
             for (;;) {
                 const uint32_t old = mb_atomic_cas(&htKey[slot], 0u, id1);
                 if (old == 0u || old == id1) break;
-                slot = (slot + 1u) & (MB_HT_N - 1u);
+                slot = (slot + 1u) & (htN - 1u);
             }
             mb_atomic_add(&htOff[slot], 1u);
             W.S[e] = (int32_t)slot;
         }
         CTA_SYNC();
-        cta_exclusive_scan(htOff, MB_HT_N - 1, &sh->cs);   // (the last slot's count is covered by the total; offsets only need [0, N-1))
+        cta_exclusive_scan(htOff, htN - 1, &sh->cs);   // (the last slot's count is covered by the total; offsets only need [0, N-1))
         CTA_FOR(e, nMulti) { const uint32_t slot = (uint32_t)W.S[e]; W.A[mb_atomic_add(&htOff[slot], 1u)] = W.B[e]; }   // afterwards htOff[s] = END of group s
         CTA_SYNC();
         // pass X: is this hit a duplicate of the immediately preceding hit of its target?  (byte array starts at 0: CacheFriendlyOperations.cpp:213-218)
         CTA_FOR(e, nMulti) {
             const uint64_t w = W.A[e];
-            const uint32_t slot = mb_ht_find(htKey, MB_W_SEQ(w) + 1u);
+            const uint32_t slot = mb_ht_find(htKey, htLog, MB_W_SEQ(w) + 1u);
             const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
             uint64_t pred = 0; bool has = false;
             for (uint32_t x = gb; x < ge; x++) { const uint64_t y = W.A[x]; if (y < w && (!has || y > pred)) { pred = y; has = true; } }
@@ -333,7 +356,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
             const uint64_t wf = W.B[e];
             if (wf >> 63) {
                 const uint64_t w = wf & ~(1ull << 63);
-                const uint32_t slot = mb_ht_find(htKey, MB_W_SEQ(w) + 1u);
+                const uint32_t slot = mb_ht_find(htKey, htLog, MB_W_SEQ(w) + 1u);
                 const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
                 uint64_t pc = 0; bool has = false;
                 for (uint32_t x = gb; x < ge; x++) { const uint64_t yf = W.B[x]; const uint64_t y = yf & ~(1ull << 63); if ((yf >> 63) && y < w && (!has || y > pc)) { pc = y; has = true; } }
@@ -399,6 +422,31 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     const uint32_t nSurv = sh->cnt[2];
     MB_PHASE(8);
     // ---- P11 score threshold (computeScoreThreshold, QueryMatcher.h:206-216; QueryMatcher.cpp:153-155)
+#if MB_DEVICE_BUILD
+    if (threadIdx.x < 32) {   // one warp: lane l owns score bins [8l, 8l+8); S(t) = number of targets with 8-bit score >= t
+        const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
+        const uint32_t lane = threadIdx.x;
+        uint32_t hb[8], mine = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) { hb[b] = sh->hist[lane * 8 + b]; mine += hb[b]; }
+        uint32_t incl = mine;   // sum over lanes >= lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, incl, d); if (lane + d < 32) incl += o; }
+        uint32_t run = incl - mine; int cand = 0;   // largest t in this lane's bins (t >= 1) with S(t) >= maxHits
+#pragma unroll
+        for (int b = 7; b >= 0; b--) { run += hb[b]; const int t = (int)lane * 8 + b; if (cand == 0 && t >= 1 && run >= maxHits) cand = t; }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, cand, d); cand = o > cand ? o : cand; }
+        uint32_t thr = (uint32_t)cand;
+        if (thr < (uint32_t)T.minDiag) thr = (uint32_t)T.minDiag;
+        uint32_t part = 0;   // S(thr)
+#pragma unroll
+        for (int b = 0; b < 8; b++) if (lane * 8 + b >= thr) part += hb[b];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0) { sh->cnt[3] = thr; sh->cnt[4] = part; }
+    }
+#else
     CTA_SINGLE {
         const uint32_t maxHits = (uint32_t)T.maxHits < T.nT ? (uint32_t)T.maxHits : T.nT;
         uint32_t found = 0, thr = 0;
@@ -408,6 +456,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
         for (uint32_t s = thr; s < 256; s++) nPass += sh->hist[s];
         sh->cnt[3] = thr; sh->cnt[4] = nPass;
     }
+#endif
     // ---- P12 stable order of the reference's counting sort: score desc, then bin (seqId & (BINSIZE-1)), then arrival
     mb_sort_list(W.B, nSurv, sh);
     const uint32_t thr = sh->cnt[3];

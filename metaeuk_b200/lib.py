@@ -240,6 +240,18 @@ class Context:
         self._check(self.L.mb200_results_download(self.h, _p(hits), _p(cnt), None, None))
         return hits, cnt
 
+    def option_set(self, name, value):
+        self._check(self.L.mb200_option_set(self.h, name.encode(), C.c_int64(int(value))))
+
+    def timer_start(self):
+        """CUDA-event stopwatch on the context's stream (where every kernel of the library is launched)"""
+        self._check(self.L.mb200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._check(self.L.mb200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def stats(self):
         s = Stats()
         self._check(self.L.mb200_stats_get(self.h, C.byref(s)))

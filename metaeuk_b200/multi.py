@@ -1,0 +1,88 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU (torch.distributed), fragments sharded across ranks, the target
+index built once on rank 0 and replicated with ONE broadcast per device buffer (NCCL over NVLink on GPUs; gloo in the CPU
+tests).  The search itself has no data-path collective: every fragment is independent of every other fragment
+(the reference gets the same independence from `#pragma omp for schedule(dynamic)` over queries, Prefiltering.cpp:790-870,
+Alignment.cpp:312-405, and from MPI splits of the query DB, Prefiltering.cpp:560-640).
+
+`ctx` is a metaeuk_b200.lib.Context (or anything with the same four index_* methods -- the gloo test drives this module with
+host buffers).
+"""
+import numpy as np
+
+
+def shard_bounds(off, world):
+    """Contiguous shards of the query batch with (nearly) equal residue counts: rank r owns queries [b[r], b[r+1]).
+    off = uint64 offsets[n+1] of the concatenated fragments."""
+    off = np.asarray(off, dtype=np.uint64)
+    n = len(off) - 1
+    if n <= 0:
+        return [0] * (world + 1)
+    total = int(off[-1]) - int(off[0])
+    b = [0]
+    for r in range(1, world):
+        want = int(off[0]) + (total * r) // world
+        i = int(np.searchsorted(off, want, side="left"))
+        b.append(min(max(i, b[-1]), n))
+    b.append(n)
+    return b
+
+
+def device_view(ptr, nbytes):
+    """uint8 torch tensor aliasing a device buffer owned by the library (no copy)"""
+    import torch
+
+    class _V:
+        pass
+    v = _V()
+    v.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(v, device="cuda")
+
+
+def replicate_index(ctx, rank, world, device="cuda", view=device_view):
+    """rank 0 has built (or imported) the index; afterwards every rank holds a bit-identical copy.
+    Returns the number of bytes broadcast."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return 0
+    sz = torch.tensor(ctx.index_sizes() if rank == 0 else [0, 0, 0, 0], dtype=torch.int64, device=device)
+    dist.broadcast(sz, 0)
+    sizes = [int(x) for x in sz.tolist()]
+    if rank != 0:
+        ctx.index_alloc(sizes)
+    total = 0
+    for ptr, nb in ctx.index_buffers():
+        if nb == 0:
+            continue
+        dist.broadcast(view(ptr, nb), 0)
+        total += nb
+    if rank != 0:
+        ctx.index_commit()
+    return total
+
+
+def gather_to_root(obj, rank, world):
+    """per-rank python results -> list on rank 0 (None elsewhere); results are small compared with the search itself"""
+    import torch.distributed as dist
+    if world == 1:
+        return [obj]
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(obj, out, dst=0)
+    return out
+
+
+def search_sharded(run_shard, queries, rank, world):
+    """queries: [(key, sequence)].  run_shard(list) -> {key: result text} on this rank's GPU.  Rank 0 returns the merged dict
+    (identical to the single-GPU result: per-query results do not depend on the batch they travel in)."""
+    off = np.zeros(len(queries) + 1, np.uint64)
+    if queries:
+        off[1:] = np.cumsum([len(s) for _, s in queries])
+    b = shard_bounds(off, world)
+    mine = run_shard(queries[b[rank]:b[rank + 1]])
+    parts = gather_to_root(mine, rank, world)
+    if rank != 0:
+        return None
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return merged

@@ -56,11 +56,11 @@ int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, cons
     T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
     T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
     T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
-    std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI), hitOff(T.capK + 1), kmerLo(T.capK);
-    std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP), kmerP(T.capK);
+    std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI);
+    std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP);
     std::vector<uint64_t> A(T.capM), B(T.capM), C(T.capM); std::vector<int32_t> S(T.capM);
     MbPrefScratch W; W.itemOff = itemOff.data(); W.wThr = wThr.data(); W.wI0 = wI0.data(); W.wI1 = wI1.data(); W.kmerOff = kmerOff.data();
-    W.itemInfo = itemInfo.data(); W.hitOff = hitOff.data(); W.kmerLo = kmerLo.data(); W.kmerP = kmerP.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
+    W.itemInfo = itemInfo.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
     MbPrefShared *sh = new MbPrefShared();
     for (int i = 0; i < 441; i++) sh->ungMat[i] = (int8_t)m.ung[i];
     MbPrefStats st; memset(&st, 0, sizeof(st));
