@@ -12,6 +12,7 @@
 #if defined(__CUDACC__) && !defined(MB200_EMULATE)
 #define MB_DEVICE_BUILD 1
 #define MB_DEV __device__ __forceinline__
+#define MB_DEV_CALL __device__ __noinline__   // block-wide collectives used at several sites: one copy of the code
 #define CTA_TID (threadIdx.x)
 #define CTA_NT (blockDim.x)
 #define CTA_FOR(i, n) for (uint32_t i = threadIdx.x, i##_end = (uint32_t)(n); i < i##_end; i += blockDim.x)
@@ -34,6 +35,7 @@ MB_DEV float mb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 #else
 #define MB_DEVICE_BUILD 0
 #define MB_DEV static inline
+#define MB_DEV_CALL static inline
 #define CTA_TID (0u)
 #define CTA_NT (1u)
 #define CTA_FOR(i, n) for (uint32_t i = 0, i##_end = (uint32_t)(n); i < i##_end; i++)
@@ -84,7 +86,7 @@ struct CtaScratch {
 
 // In-place exclusive prefix sum of a[0..n); also writes a[n] = total and returns the total to every thread.
 // a may live in shared or global memory.
-MB_DEV uint32_t cta_exclusive_scan(uint32_t *a, uint32_t n, CtaScratch *s) {
+MB_DEV_CALL uint32_t cta_exclusive_scan(uint32_t *a, uint32_t n, CtaScratch *s) {
 #if MB_DEVICE_BUILD
     // every warp owns one contiguous range and sweeps it 32 elements at a time (coalesced, shuffle scans, no block barrier
     // inside the sweep); one barrier to exchange warp totals; a second sweep adds the warp's prefix.
@@ -133,7 +135,7 @@ MB_DEV uint32_t mb_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1
 
 // Ascending sort of 64-bit keys a[0..n).  The buffer must have room for next_pow2(n) elements (padding is
 // written as ~0).  Bitonic network with block barriers; fine for the few-hundred-element lists the prefilter sorts.
-MB_DEV void cta_sort_u64(uint64_t *a, uint32_t n) {
+MB_DEV_CALL void cta_sort_u64(uint64_t *a, uint32_t n) {
 #if MB_DEVICE_BUILD
     const uint32_t n2 = mb_next_pow2(n);
     if (n2 <= 32) {   // short lists: one warp, keys in registers, compare-exchange through shuffles, a single block barrier

@@ -82,7 +82,7 @@ struct MbPrefShared {
 };
 
 // sort a (usually short) global list: through shared memory when it fits
-MB_DEV void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
+MB_DEV_CALL void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
     if (n <= MB_SM_S) {
         CTA_FOR(i, n) sh->sSort[i] = g[i];
         CTA_SYNC();
@@ -236,50 +236,94 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
 
     // ---- P3 similar k-mers in the reference's enumeration order k = 0..K-1 (window, first-half rank, second-half rank); those whose
-    //      index list is non-empty (bitmap test, IndexTable::getDBSeqList, IndexTable.h:176-180) go to an unordered list of
-    //      (window | k | k-mer) words.  Each thread owns a contiguous run of k and walks items in the outer loop, so the inner loop over the
-    //      second-half rank touches consecutive sim3 entries of one row and nothing else.
+    //      index list is non-empty (bitmap test; IndexTable::getDBSeqList, IndexTable.h:176-180) go to an unordered list of
+    //      (window | k | k-mer) words.  Each thread owns a contiguous run of k and keeps the (item, window) cursor in registers; the run is
+    //      handled in batches of 4 with uniform control flow, so the dependent loads of a batch (sim3 row -> bitmap) are in flight
+    //      together and the list append is one shared-memory atomic per warp and batch slot.
     {
         CTA_CHUNK(kb, ke, K);
-        uint32_t it = (kb < ke) ? cta_find_segment(kmerOff, I, kb) : 0;
-        uint32_t pw = (kb < ke) ? cta_find_segment(itemOff, P, it) : 0;
-        uint32_t k = kb;
-        while (k < ke) {
-            while (itemOff[pw + 1] <= it) pw++;
-            const uint32_t o = kmerOff[it], oe = kmerOff[it + 1];
-            const uint32_t jEnd = ((ke < oe) ? ke : oe) - o;
-            const uint32_t idx0 = itemIdx0[it];
-            const uint32_t *row1 = T.sim3 + (uint32_t)wI1[pw] * MB_N3;
-            for (uint32_t j = k - o; j < jEnd; j++) {
-                const uint32_t km = idx0 + (row1[j] >> 16) * 8000u;
-                const bool nz = T.kmerBits ? ((T.kmerBits[km >> 5] >> (km & 31u)) & 1u) : (T.offsets[km + 1] != T.offsets[km]);
-                if (nz) {
-                    const uint32_t n = mb_atomic_add(&sh->cnt[7], 1u);
-                    const uint64_t w = ((uint64_t)pw << 44) | ((uint64_t)(o + j) << 26) | km;
+        uint32_t it = 0, pw = 0, o = 0, oe = 0, idx0 = 0, rowBase = 0;
+        if (kb < ke) {
+            it = cta_find_segment(kmerOff, I, kb); pw = cta_find_segment(itemOff, P, it);
+            o = kmerOff[it]; oe = kmerOff[it + 1]; idx0 = itemIdx0[it]; rowBase = (uint32_t)wI1[pw] * MB_N3;
+        }
+        for (uint32_t k0 = kb; k0 < ke; k0 += 4) {
+            uint32_t ad[4], i0v[4], pv[4], a1[4], km[4]; bool ok[4], nz[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + u; ok[u] = k < ke; ad[u] = 0; i0v[u] = 0; pv[u] = 0;
+                if (ok[u]) {
+                    while (k >= oe) {
+                        it++; o = oe; oe = kmerOff[it + 1]; idx0 = itemIdx0[it];
+                        while (itemOff[pw + 1] <= it) pw++;
+                        rowBase = (uint32_t)wI1[pw] * MB_N3;
+                    }
+                    ad[u] = rowBase + (k - o); i0v[u] = idx0; pv[u] = pw;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) a1[u] = ok[u] ? T.sim3[ad[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                km[u] = i0v[u] + (a1[u] >> 16) * 8000u; nz[u] = false;
+                if (ok[u]) nz[u] = T.kmerBits ? ((T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u) : (T.offsets[km[u] + 1] != T.offsets[km[u]]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t n = cta_append_slot(&sh->cnt[7], nz[u]);
+                if (nz[u]) {
+                    const uint64_t w = ((uint64_t)pv[u] << 44) | ((uint64_t)(k0 + u) << 26) | km[u];
                     if (n < MB_SM_NZ) sh->sNz[n] = w; else W.B[n - MB_SM_NZ] = w;
                 }
             }
-            k = o + jEnd; it++;
         }
     }
     CTA_SYNC();
     const uint32_t nNz = sh->cnt[7];
     MB_PHASE(3);
 
-    // ---- P4 gather the index entries of the non-empty lists; mark slot occupancy (0 / 1 / >=2 hits)
-    for (uint32_t n0 = CTA_TID; n0 < nNz; n0 += 4 * CTA_NT) {
-        uint64_t wv[4]; uint32_t lo[4], len[4], base[4]; uint2 e0[4]; bool ok[4];
+    // ---- P4 gather the index entries of the non-empty lists (thread per list, 4 in flight); mark slot occupancy (0 / 1 / >=2 hits).
+    //      Output slots are reserved with one shared-memory atomic per warp and round.
+    for (uint32_t r0 = 0; r0 < nNz; r0 += 4 * CTA_NT) {
+        uint64_t wv[4]; uint32_t lo[4], len[4], base[4]; uint2 e0[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t n = n0 + u * CTA_NT; ok[u] = n < nNz; wv[u] = 0; if (ok[u]) wv[u] = (n < MB_SM_NZ) ? sh->sNz[n] : W.B[n - MB_SM_NZ]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) { lo[u] = 0; len[u] = 0; if (ok[u]) { const uint32_t km = (uint32_t)wv[u] & 0x3FFFFFFu; lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u]; } }
+        for (int u = 0; u < 4; u++) { const uint32_t n = r0 + u * CTA_NT + CTA_TID; wv[u] = 0; if (n < nNz) wv[u] = (n < MB_SM_NZ) ? sh->sNz[n] : W.B[n - MB_SM_NZ]; }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            base[u] = 0;
-            if (len[u] && *(volatile uint32_t *)&sh->cnt[3] == 0u) {   // cnt[3] = overflow flag until P11 reuses it
-                base[u] = mb_atomic_add(&sh->cnt[6], len[u] <= T.capM ? len[u] : T.capM + 1u);
-                if (base[u] > T.capM || len[u] > T.capM - base[u]) { len[u] = 0; sh->cnt[3] = 1u; }
-            } else len[u] = 0;
+            lo[u] = 0; len[u] = 0;
+            if (r0 + u * CTA_NT + CTA_TID < nNz) { const uint32_t km = (uint32_t)wv[u] & 0x3FFFFFFu; lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u]; }
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { base[u] = mine; mine += (len[u] <= T.capM) ? len[u] : T.capM + 1u; }
+        uint32_t b0 = 0; bool fits = true;
+#if MB_DEVICE_BUILD
+        {
+            const uint32_t lane = threadIdx.x & 31u;
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
+            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t wb = 0, wf = 1;
+            if (lane == 0 && wtot) {
+                if (*(volatile uint32_t *)&sh->cnt[3] == 0u) {   // cnt[3] = overflow flag until P11 reuses it
+                    wb = atomicAdd(&sh->cnt[6], wtot);
+                    wf = (wb <= T.capM && wtot <= T.capM - wb) ? 1u : 0u;
+                    if (!wf) sh->cnt[3] = 1u;
+                } else wf = 0;
+            }
+            wb = __shfl_sync(0xffffffffu, wb, 0); wf = __shfl_sync(0xffffffffu, wf, 0);
+            b0 = wb + inc - mine; fits = wf != 0u;
+        }
+#else
+        if (mine) {
+            if (sh->cnt[3] == 0u) { b0 = sh->cnt[6]; sh->cnt[6] += mine; fits = b0 <= T.capM && mine <= T.capM - b0; if (!fits) sh->cnt[3] = 1u; }
+            else fits = false;
+        }
+#endif
+        if (!fits) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) len[u] = 0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) { e0[u].x = 0; e0[u].y = 0; if (len[u]) e0[u] = T.entries[lo[u]]; }
@@ -289,7 +333,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
             for (uint32_t x = 0; x < len[u]; x++) {
                 const uint2 en = x ? T.entries[(size_t)lo[u] + x] : e0[u];
                 const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
-                W.A[base[u] + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
+                W.A[b0 + base[u] + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
                 const uint32_t slot = en.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
                 const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
                 if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
