@@ -289,6 +289,7 @@ def main():
     for _ in range(2):
         step_e2e()
     dt_e2e = timed(step_e2e, args.steps)
+    st_e2e = ctx.stats()
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         ctx.close()
@@ -304,7 +305,8 @@ def main():
     h2d = int(frag.nbytes + foff.nbytes)
     d2h = e2e_out.get("bytes", 0)
     base.update({"value": value, "ms_per_step": 1000 * dt / args.steps, "clocks": clocks, "gpu_launches": int(launches),
-                 "e2e": {"value": e2e, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_e2e / args.steps},
+                 "e2e": {"value": e2e, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_e2e / args.steps,
+                         "last_call_ms": {k: round(st_e2e[k], 3) for k in ("ms_h2d", "ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_d2h", "ms_host")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                               "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "traffic": ncu_traffic()},
                  "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/metaeuk_b200.h"
@@ -110,6 +111,21 @@ template <class T> struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+template <class T> struct PinBuf {   // grow-only page-locked host staging buffer
+    T *p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        if (count == 0) count = 1;
+        count += count / 4;
+        cudaError_t e = cudaHostAlloc((void **)&p, count * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(MB200_E_CUDA, "cudaHostAlloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count; return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
 struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
@@ -131,7 +147,8 @@ struct mb200_ctx {
     std::vector<int> minScore;   // per query length, -2 = not computed
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
-    std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<mb200_hit> hFlatHits; std::vector<uint64_t> hHitOff;
+    std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<uint64_t> hHitOff;
+    PinBuf<mb200_hit> pFlatHits; PinBuf<uint32_t> pOff, pStatus; size_t nFlatHits = 0;
     bool haveAln = false;
     int optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
     mb200_stats st;
@@ -225,6 +242,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
+    c->pFlatHits.release(); c->pOff.release(); c->pStatus.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -379,8 +397,12 @@ int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, u
     TRY(c->dQ.alloc(tot + 16)); TRY(c->dQoff.alloc(nQ + 1)); TRY(c->dBias.alloc(tot + 16)); TRY(c->dCorr.alloc(tot + 16)); TRY(c->dCb.alloc(tot + 16)); TRY(c->dOrder.alloc(nQ + 1));
     // longest queries first: the persistent prefilter CTAs pull work from this order
     std::vector<uint32_t> order(nQ);
-    for (uint32_t i = 0; i < nQ; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (qoff[a + 1] - qoff[a]) > (qoff[b + 1] - qoff[b]); });
+    {   // stable counting sort by descending length (lengths < 32768)
+        std::vector<uint32_t> start(maxL + 2, 0);
+        for (uint32_t i = 0; i < nQ; i++) start[maxL - (uint32_t)(qoff[i + 1] - qoff[i]) + 1]++;
+        for (uint32_t l = 0; l <= maxL; l++) start[l + 1] += start[l];
+        for (uint32_t i = 0; i < nQ; i++) order[start[maxL - (uint32_t)(qoff[i + 1] - qoff[i])]++] = i;
+    }
     CU(cudaEventRecord(c->ev0, c->stream));
     TRY(upload(c->dQ.p, q, tot, c->stream)); TRY(upload(c->dQoff.p, qoff, (size_t)(nQ + 1) * 8, c->stream)); TRY(upload(c->dOrder.p, order.data(), (size_t)nQ * 4, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -422,8 +444,10 @@ int mb200_prefilter_resident(mb200_ctx *c) {
         float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prefilter = ms; c->st.launches++;
     }
     // status check: any query that could not be processed is an error, never a silent drop
-    std::vector<uint32_t> status(nQ + 1);
-    CU(cudaMemcpy(status.data(), c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost));
+    TRY(c->pStatus.alloc(nQ + 1));
+    uint32_t *status = c->pStatus.p;
+    CU(cudaMemcpyAsync(status, c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK)
         return fail(status[i] == MB_ST_OVERFLOW ? MB200_E_OVERFLOW : MB200_E_LIMIT, "query %u: prefilter status %u (work list capacity exceeded or sequence too long)", i, status[i]);
     MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
@@ -593,25 +617,25 @@ int mb200_align_resident(mb200_ctx *c) {
 // compact device->host copy of the resident prefilter result: hit_off[n_q+1], hits in query order
 static int download_hits_compact(mb200_ctx *c) {
     const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
-    c->hHitOff.assign(nQ + 1, 0); c->hFlatHits.clear();
+    c->hHitOff.assign(nQ + 1, 0); c->nFlatHits = 0;
     if (nQ == 0) return 0;
-    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1));
+    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->pOff.alloc(nQ + 1));
     k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p);
     CU(cudaGetLastError());
-    std::vector<uint32_t> off(nQ + 1);
+    uint32_t *off = c->pOff.p;
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemcpyAsync(off.data(), c->dPairOff.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(off, c->dPairOff.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "scan"));
     const uint32_t n = off[nQ];
-    TRY(c->dFlatHits.alloc(n));
+    TRY(c->dFlatHits.alloc(n)); TRY(c->pFlatHits.alloc(n));
     k_compact_hits<<<nQ, 64, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dPairOff.p, nQ, maxHits, c->dFlatHits.p);
     CU(cudaGetLastError());
-    c->hFlatHits.resize(n);
-    if (n) CU(cudaMemcpyAsync(c->hFlatHits.data(), c->dFlatHits.p, (size_t)n * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
+    if (n) CU(cudaMemcpyAsync(c->pFlatHits.p, c->dFlatHits.p, (size_t)n * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
+    for (uint32_t i = 0; i <= nQ; i++) c->hHitOff[i] = off[i];
     TRY(sync_check(c, "compact hits"));
     float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_d2h = ms; c->st.launches += 2;
-    for (uint32_t i = 0; i <= nQ; i++) c->hHitOff[i] = off[i];
+    c->nFlatHits = n;
     return 0;
 }
 
@@ -645,11 +669,13 @@ int mb200_prefilter(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32
 
 int mb200_prefilter_compact(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ, uint64_t *hitOff, const mb200_hit **hits) {
     if (!hitOff || !hits) return fail(MB200_E_ARG, "null output");
+    const auto t0 = std::chrono::steady_clock::now();
     TRY(mb200_queries_upload(c, q, qoff, nQ));
     TRY(mb200_prefilter_resident(c));
     TRY(download_hits_compact(c));
     memcpy(hitOff, c->hHitOff.data(), (size_t)(nQ + 1) * 8);
-    *hits = c->hFlatHits.empty() ? nullptr : c->hFlatHits.data();
+    c->st.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *hits = c->nFlatHits ? c->pFlatHits.p : nullptr;
     return 0;
 }
 

@@ -172,24 +172,13 @@ __device__ __forceinline__ int mb_diag_score_warp(const int8_t *ungMat, const ui
 #define MB_PHASE(n) ((void)0)
 #endif
 
-// One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
-MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
-                               const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
-    const uint32_t P = (L >= 10) ? (L - 9) : 0;   // Sequence::hasNextKmer, spaced pattern length 10 (Sequence.h:23,92-94)
-    MB_PHASE(15);   // time between queries (queue pop, previous epilogue)
-    CTA_SINGLE { for (int i = 0; i < 8; i++) sh->cnt[i] = 0; }
-    CTA_FOR(i, 256) sh->hist[i] = 0;
-    CTA_FOR(i, MB_NSLOT / 16) sh->slots[i] = 0;
-    CTA_SYNC();
-    MB_PHASE(0);    // clearing
-    if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
-    if (P == 0) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OK; } return; }
-
-    uint32_t *const itemOff = (P <= MB_SM_P) ? sh->sItemOff : W.itemOff;
-    int16_t *const wThr = (P <= MB_SM_P) ? sh->sThr : W.wThr;
-    uint16_t *const wI0 = (P <= MB_SM_P) ? sh->sI0 : W.wI0;
-    uint16_t *const wI1 = (P <= MB_SM_P) ? sh->sI1 : W.wI1;
-    // ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140)
+// P1..P3 are instantiated per home of the expansion arrays (SMP: window arrays in shared memory, SMI: item arrays in shared memory) so that
+// every access compiles to a shared (LDS/STS) or a global (LDG/STG) instruction instead of a generic one.
+// ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140); returns #items
+template <bool SMP>
+MB_DEV uint32_t mb_pref_windows(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias, uint32_t P) {
+    uint32_t *const itemOff = SMP ? sh->sItemOff : W.itemOff; int16_t *const wThr = SMP ? sh->sThr : W.wThr;
+    uint16_t *const wI0 = SMP ? sh->sI0 : W.wI0; uint16_t *const wI1 = SMP ? sh->sI1 : W.wI1;
     CTA_FOR(p, P) {
         const uint8_t *w = q + p;
         const uint32_t r0 = w[0], r1 = w[1], r2 = w[3], r3 = w[5], r4 = w[8], r5 = w[9];
@@ -209,31 +198,39 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
         itemOff[p] = n0; wThr[p] = (int16_t)thr; wI0[p] = (uint16_t)i0; wI1[p] = (uint16_t)i1;
     }
     CTA_SYNC();
-    const uint32_t I = cta_exclusive_scan(itemOff, P, &sh->cs);
-    MB_PHASE(1);
-    if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+    return cta_exclusive_scan(itemOff, P, &sh->cs);
+}
 
-    // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216)
-    uint32_t *const kmerOff = (I <= MB_SM_I) ? sh->sKmerOff : W.kmerOff;
-    uint16_t *const itemIdx0 = (I <= MB_SM_I) ? sh->sItemIdx0 : (uint16_t *)W.itemInfo;
-    for (uint32_t it0 = CTA_TID; it0 < I; it0 += 4 * CTA_NT) {   // 4 items per thread per round: the two dependent table loads of each are in flight together
-        uint32_t pv[4], a0[4]; bool ok[4];
+// ---- P2 + P3; returns K (similar k-mers); the non-empty ones are listed in sh->sNz / W.B (count in sh->cnt[7]).  K > capK: nothing listed.
+template <bool SMP, bool SMI>
+MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, uint32_t P, uint32_t I) {
+    uint32_t *const itemOff = SMP ? sh->sItemOff : W.itemOff; int16_t *const wThr = SMP ? sh->sThr : W.wThr;
+    uint16_t *const wI0 = SMP ? sh->sI0 : W.wI0; uint16_t *const wI1 = SMP ? sh->sI1 : W.wI1;
+    uint32_t *const kmerOff = SMI ? sh->sKmerOff : W.kmerOff;
+    uint16_t *const itemIdx0 = SMI ? sh->sItemIdx0 : (uint16_t *)W.itemInfo;
+    // ---- P2 items (p, i): second-level neighbour count  (calculateArrayProduct, KmerGenerator.cpp:186-216).  Each thread owns a
+    //      contiguous run of items (one search for the first window, then a cursor); 4 per round so the two dependent table loads overlap.
+    {
+        CTA_CHUNK(ib, ie, I);
+        uint32_t pw = (ib < ie) ? cta_find_segment(itemOff, P, ib) : 0;
+        for (uint32_t i0 = ib; i0 < ie; i0 += 4) {
+            uint32_t pv[4], a0[4]; bool ok[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t it = it0 + u * CTA_NT; ok[u] = it < I; pv[u] = ok[u] ? cta_find_segment(itemOff, P, it) : 0; }
+            for (int u = 0; u < 4; u++) { const uint32_t it = i0 + u; ok[u] = it < ie; pv[u] = 0; if (ok[u]) { while (itemOff[pw + 1] <= it) pw++; pv[u] = pw; } }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t it = it0 + u * CTA_NT; a0[u] = ok[u] ? T.sim3[(uint32_t)wI0[pv[u]] * MB_N3 + (it - itemOff[pv[u]])] : 0; }
+            for (int u = 0; u < 4; u++) a0[u] = ok[u] ? T.sim3[(uint32_t)wI0[pv[u]] * MB_N3 + (i0 + u - itemOff[pv[u]])] : 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (ok[u]) {
-            const uint32_t it = it0 + u * CTA_NT;
-            const short cutoff2 = (short)((int)wThr[pv[u]] - (int)(int16_t)(a0[u] & 0xFFFFu));
-            kmerOff[it] = mb_count_ge(T.cnt3, wI1[pv[u]], cutoff2);
-            itemIdx0[it] = (uint16_t)(a0[u] >> 16);
+            for (int u = 0; u < 4; u++) if (ok[u]) {
+                const short cutoff2 = (short)((int)wThr[pv[u]] - (int)(int16_t)(a0[u] & 0xFFFFu));
+                kmerOff[i0 + u] = mb_count_ge(T.cnt3, wI1[pv[u]], cutoff2);
+                itemIdx0[i0 + u] = (uint16_t)(a0[u] >> 16);
+            }
         }
     }
     CTA_SYNC();
     const uint32_t K = cta_exclusive_scan(kmerOff, I, &sh->cs);
     MB_PHASE(2);
-    if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+    if (K > T.capK) return K;
 
     // ---- P3 similar k-mers in the reference's enumeration order k = 0..K-1 (window, first-half rank, second-half rank); those whose
     //      index list is non-empty (bitmap test; IndexTable::getDBSeqList, IndexTable.h:176-180) go to an unordered list of
@@ -278,6 +275,29 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
             }
         }
     }
+    return K;
+}
+
+// One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
+MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
+                               const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
+    const uint32_t P = (L >= 10) ? (L - 9) : 0;   // Sequence::hasNextKmer, spaced pattern length 10 (Sequence.h:23,92-94)
+    MB_PHASE(15);   // time between queries (queue pop, previous epilogue)
+    CTA_SINGLE { for (int i = 0; i < 8; i++) sh->cnt[i] = 0; }
+    CTA_FOR(i, 256) sh->hist[i] = 0;
+    CTA_FOR(i, MB_NSLOT / 16) sh->slots[i] = 0;
+    CTA_SYNC();
+    MB_PHASE(0);    // clearing
+    if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
+    if (P == 0) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OK; } return; }
+
+    const bool smP = P <= MB_SM_P;
+    const uint32_t I = smP ? mb_pref_windows<true>(T, W, sh, q, bias, P) : mb_pref_windows<false>(T, W, sh, q, bias, P);
+    MB_PHASE(1);
+    if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
+    const uint32_t K = (smP && I <= MB_SM_I) ? mb_pref_expand<true, true>(T, W, sh, P, I)
+                     : smP ? mb_pref_expand<true, false>(T, W, sh, P, I) : mb_pref_expand<false, false>(T, W, sh, P, I);
+    if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
     CTA_SYNC();
     const uint32_t nNz = sh->cnt[7];
     MB_PHASE(3);

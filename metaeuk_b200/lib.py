@@ -187,28 +187,30 @@ class Context:
         self._check(self.L.mb200_align(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(hit_seq), _p(hit_off), _p(alns)))
         return alns[:int(hit_off[-1])]
 
-    def search(self, q, qoff):
-        """-> (accepted alignments as one flat array, uint64 offsets[n+1]); copies out of the context-owned buffer"""
+    def search(self, q, qoff, copy=False):
+        """-> (accepted alignments as one flat array, uint64 offsets[n+1]).  The flat array is a view of the context-owned host buffer,
+        valid until the next call on this context (pass copy=True to keep it)."""
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
         n = len(qoff) - 1
-        off = np.zeros(n + 1, np.uint64); ptr = C.c_void_p()
+        off = np.empty(n + 1, np.uint64); ptr = C.c_void_p()
         self._check(self.L.mb200_search(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(off), C.byref(ptr)))
-        tot = int(off[-1])
-        if tot == 0:
-            return np.zeros(0, ALN_DTYPE), off
-        buf = (C.c_char * (tot * ALN_DTYPE.itemsize)).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=ALN_DTYPE).copy(), off
+        return self._view(ptr, int(off[-1]), ALN_DTYPE, copy), off
 
-    def prefilter_compact(self, q, qoff):
+    def prefilter_compact(self, q, qoff, copy=False):
+        """-> (hits as one flat array, uint64 offsets[n+1]); same ownership rule as search()"""
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
         n = len(qoff) - 1
-        off = np.zeros(n + 1, np.uint64); ptr = C.c_void_p()
+        off = np.empty(n + 1, np.uint64); ptr = C.c_void_p()
         self._check(self.L.mb200_prefilter_compact(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(off), C.byref(ptr)))
-        tot = int(off[-1])
-        if tot == 0:
-            return np.zeros(0, HIT_DTYPE), off
-        buf = (C.c_char * (tot * HIT_DTYPE.itemsize)).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=HIT_DTYPE).copy(), off
+        return self._view(ptr, int(off[-1]), HIT_DTYPE, copy), off
+
+    @staticmethod
+    def _view(ptr, count, dtype, copy):
+        if count == 0:
+            return np.zeros(0, dtype)
+        buf = (C.c_char * (count * dtype.itemsize)).from_address(ptr.value)
+        a = np.frombuffer(buf, dtype=dtype)
+        return a.copy() if copy else a
 
     def chain(self, cands, cand_off, total_target_residues):
         cands = np.ascontiguousarray(cands, CAND_DTYPE); cand_off = np.ascontiguousarray(cand_off, np.uint64)
