@@ -23,7 +23,12 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1; the host side of the library (index build, alignment epilogue) is OpenMP code: give every rank its
+# share of the cores (must happen before any OpenMP runtime is loaded)
+if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -168,7 +173,19 @@ def cpu_oracle_run(prot, poff, frag, foff, n_sample, align, threads):
     return o, one, n
 
 
+def emit(obj):
+    """the ONE JSON line on the real stdout (libraries that chat on fd 1, e.g. NCCL's version banner, were redirected to stderr)"""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -201,7 +218,7 @@ def main():
                      "cpu_baseline": {"value": v, "unit": "fragments/s", "cores": threads, "kind": "port",
                                       "sample": "first %d fragments of the workload per step, all %d host threads (OpenMP over queries); index build excluded" % (n, threads)},
                      "e2e": {"value": v, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base))
+        emit(base)
         return
     # ------------------------------------------------------------------ B200 arm
     import torch
@@ -331,7 +348,7 @@ def main():
         tcpu = one()
         base["cpu_baseline"] = {"value": n / tcpu, "unit": "fragments/s", "cores": threads, "kind": "port",
                                 "sample": "first %d fragments of the workload, all %d host threads (OpenMP over queries); index build excluded" % (n, threads)}
-    print(json.dumps(base))
+    emit(base)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -57,7 +57,9 @@ MB_DEV float mb_fmul(float a, float b) { return a * b; }
 MB_DEV float mb_fdiv(float a, float b) { return a / b; }
 #endif
 
+#ifndef MB_CTA_THREADS
 #define MB_CTA_THREADS 512
+#endif
 
 // Reserve one slot of a list whose length lives at *ctr (shared memory) for every calling thread with pred == true and return its
 // index (~0u otherwise).  On the device the threads of a warp that append in the same instruction share ONE atomic.

@@ -57,12 +57,13 @@ __global__ void __launch_bounds__(256) k_prep(const uint8_t *__restrict__ qres, 
 }
 
 // ---- prefilter: persistent CTAs, one query at a time, dynamic work distribution --------------------
-__global__ void __launch_bounds__(MB_CTA_THREADS, 2) k_prefilter(MbPrefTables T, const MbPrefScratch *__restrict__ scratch, const uint8_t *__restrict__ qres,
+template <class SH>
+__global__ void __launch_bounds__(SH::Cfg::NT, SH::Cfg::CTAS) k_prefilter(MbPrefTables T, const MbPrefScratch *__restrict__ scratch, const uint8_t *__restrict__ qres,
                                                               const uint64_t *__restrict__ qoff, const float *__restrict__ bias, const int8_t *__restrict__ corr,
                                                               const uint32_t *__restrict__ order, uint32_t nQ, const int8_t *__restrict__ ungMat8,
                                                               MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats, uint32_t *nextQ) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    MbPrefShared *sh = reinterpret_cast<MbPrefShared *>(smemRaw);
+    SH *sh = reinterpret_cast<SH *>(smemRaw);
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sh->ungMat[i] = ungMat8[i];
     if (T.phaseStats && threadIdx.x == 0) { for (int i = 0; i < 16; i++) sh->phaseAcc[i] = 0; sh->phaseT = clock64(); }
     const MbPrefScratch W = scratch[blockIdx.x];
@@ -150,7 +151,7 @@ struct mb200_ctx {
     std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<uint64_t> hHitOff;
     PinBuf<mb200_hit> pFlatHits; PinBuf<uint32_t> pOff, pStatus; size_t nFlatHits = 0;
     bool haveAln = false;
-    int optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
+    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
 };
@@ -180,12 +181,20 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
                    capM = 1u << (c->par.cap_hits_log2 ? c->par.cap_hits_log2 : 19);
     if (capK > (1u << 18)) return fail(MB200_E_ARG, "cap_kmers_log2 > 18 (the k-mer ordinal is an 18-bit field)");
     if (capM < capK || capM > (1u << 24)) return fail(MB200_E_ARG, "cap_hits_log2 must be in [cap_kmers_log2, 24]");
-    if (c->nCta && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
-    int smemBytes = (int)sizeof(MbPrefShared), perSM = 0;
-    CU(cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter, MB_CTA_THREADS, smemBytes));
+    // dense config for indexes with long k-mer lists (>= 1 entry per k-mer slot on average), sparse config otherwise
+    const int cfg = c->optPrefCfg ? c->optPrefCfg : ((double)c->nEntries >= 1.0 * (double)mb200::KMER_TABLE ? 1 : 2);
+    if (c->nCta && cfg == c->prefCfg && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
+    int perSM = 0;
+    if (cfg == 1) {
+        CU(cudaFuncSetAttribute(k_prefilter<MbPrefSharedT<MbPrefCfgDense>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbPrefSharedT<MbPrefCfgDense>)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter<MbPrefSharedT<MbPrefCfgDense>>, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>)));
+        if (perSM > (int)MbPrefCfgDense::CTAS) perSM = MbPrefCfgDense::CTAS;
+    } else {
+        CU(cudaFuncSetAttribute(k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbPrefSharedT<MbPrefCfgSparse>)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>)));
+        if (perSM > (int)MbPrefCfgSparse::CTAS) perSM = MbPrefCfgSparse::CTAS;
+    }
     if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
-    if (perSM > 2) perSM = 2;
     c->nCta = c->nSM * perSM;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
@@ -199,7 +208,7 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
     }
     TRY(upload(c->dScratch.p, hs.data(), hs.size() * sizeof(MbPrefScratch), c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM;
+    c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM; c->prefCfg = cfg;
     return 0;
 }
 
@@ -251,6 +260,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return fail(MB200_E_ARG, "null argument");
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
+    else if (n == "prefilter_config") { if (value < 0 || value > 2) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense) or 2 (sparse)"); c->optPrefCfg = (int)value; }
     else if (n == "sw_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane) or 2 (two, packed 16-bit)"); c->optSwKernel = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
@@ -436,8 +446,12 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM; T.phaseStats = c->optPhaseStats;
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
-        k_prefilter<<<c->nCta, MB_CTA_THREADS, sizeof(MbPrefShared), c->stream>>>(T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p,
-                                                                                c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+        if (c->prefCfg == 1)
+            k_prefilter<MbPrefSharedT<MbPrefCfgDense>><<<c->nCta, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream>>>(
+                T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+        else
+            k_prefilter<MbPrefSharedT<MbPrefCfgSparse>><<<c->nCta, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream>>>(
+                T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));

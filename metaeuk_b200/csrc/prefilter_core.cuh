@@ -20,8 +20,6 @@
 #define MB_N3 8000
 #define MB_CNT_MIN (-192)
 #define MB_CNT_W 384
-#define MB_NSLOT_LOG 17
-#define MB_NSLOT (1u << MB_NSLOT_LOG)
 
 // hit / candidate word:  seqId[27] | arrival[21] | diag16[16]
 #define MB_MAX_SEQID_BITS 27
@@ -60,30 +58,43 @@ struct MbPrefScratch {        // per-CTA global scratch
 
 // shared-memory homes of the expansion arrays (queries that exceed them use the global scratch instead)
 #define MB_SM_P 512
-#define MB_SM_I 4096
-#define MB_SM_NZ 4096
-#define MB_SM_S 4096
 
-struct MbPrefShared {
+// Kernel configuration: threads per CTA, CTAs per SM and the shared-memory homes of the per-query work lists.  Two are instantiated
+// (mb200.cu): "dense" for indexes whose k-mer lists are long (many hits per query: big occupancy map, big lists) and "sparse" for
+// small / sparse indexes (half the threads, twice the CTAs per SM: block barriers of one query overlap with work of three others).
+template <int NT_, int CTAS_, int NSLOT_LOG_, int SM_I_, int SM_NZ_LOG_> struct MbPrefCfg {
+    static constexpr uint32_t NT = NT_, CTAS = CTAS_;
+    static constexpr uint32_t NSLOT = 1u << NSLOT_LOG_;     // 2-bit occupancy slots (target & (NSLOT - 1))
+    static constexpr uint32_t SM_I = SM_I_;                 // items (window, first-half neighbour)
+    static constexpr uint32_t SM_NZ = 1u << SM_NZ_LOG_;     // non-empty similar k-mers; the same space then holds the hash table / sort buffer
+    static constexpr uint32_t SM_S = SM_NZ, HT_LOG_MAX = SM_NZ_LOG_;
+};
+typedef MbPrefCfg<512, 2, 17, 4096, 12> MbPrefCfgDense;
+typedef MbPrefCfg<256, 4, 15, 2048, 10> MbPrefCfgSparse;
+
+template <class CFG> struct MbPrefSharedT {
+    typedef CFG Cfg;
     CtaScratch cs;
     uint32_t hist[256];
-    uint32_t cnt[8];       // 0 nMulti, 1 nCand, 2 nSurv, 3 thr, 4 nPass, 5 rescale, 6 status
+    uint32_t cnt[8];       // 0 nMulti, 1 nCand, 2 nSurv, 3 thr (overflow flag before P11), 4 nPass, 5 rescale, 6 hits, 7 non-empty k-mers
     long long phaseT; unsigned long long phaseAcc[16];
     int8_t ungMat[448];
-    uint32_t slots[MB_NSLOT / 16];
+    uint32_t slots[CFG::NSLOT / 16];
     uint32_t sItemOff[MB_SM_P + 1]; int16_t sThr[MB_SM_P]; uint16_t sI0[MB_SM_P], sI1[MB_SM_P];
-    uint32_t sKmerOff[MB_SM_I + 1];
-    uint16_t sItemIdx0[MB_SM_I];   // first-half neighbour 3-mer of every item (read once in P2, used by every k-mer of the item in P3)
+    uint32_t sKmerOff[CFG::SM_I + 1];
+    uint16_t sItemIdx0[CFG::SM_I];   // first-half neighbour 3-mer of every item (read once in P2, used by every k-mer of the item in P3)
     union {   // the list of similar k-mers with a non-empty index list is dead once the hits are gathered; the sorts that follow reuse the space
-        uint64_t sNz[MB_SM_NZ];
-        uint32_t sHitOff[2 * MB_SM_NZ];   // hash table of the double-hit stage (keys | group offsets)
-        uint64_t sSort[MB_SM_S];
+        uint64_t sNz[CFG::SM_NZ];
+        uint32_t sHitOff[2 * CFG::SM_NZ];   // hash table of the double-hit stage (keys | group offsets)
+        uint64_t sSort[CFG::SM_S];
     };
 };
+typedef MbPrefSharedT<MbPrefCfgDense> MbPrefShared;
 
 // sort a (usually short) global list: through shared memory when it fits
-MB_DEV_CALL void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
-    if (n <= MB_SM_S) {
+template <class SH>
+MB_DEV_CALL void mb_sort_list(uint64_t *g, uint32_t n, SH *sh) {
+    if (n <= SH::Cfg::SM_S) {
         CTA_FOR(i, n) sh->sSort[i] = g[i];
         CTA_SYNC();
         cta_sort_u64(sh->sSort, n);
@@ -94,7 +105,6 @@ MB_DEV_CALL void mb_sort_list(uint64_t *g, uint32_t n, MbPrefShared *sh) {
     }
 }
 
-#define MB_HT_LOG_MAX 12   // 2 x 2^12 words = sHitOff
 MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t htLog, uint32_t id1) {
     const uint32_t mask = (1u << htLog) - 1u;
     uint32_t slot = (id1 * 2654435761u) >> (32 - htLog);
@@ -175,8 +185,8 @@ __device__ __forceinline__ int mb_diag_score_warp(const int8_t *ungMat, const ui
 // P1..P3 are instantiated per home of the expansion arrays (SMP: window arrays in shared memory, SMI: item arrays in shared memory) so that
 // every access compiles to a shared (LDS/STS) or a global (LDG/STG) instruction instead of a generic one.
 // ---- P1 windows: threshold and first-level neighbour count  (QueryMatcher.cpp:225-244, KmerGenerator.cpp:107-140); returns #items
-template <bool SMP>
-MB_DEV uint32_t mb_pref_windows(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias, uint32_t P) {
+template <bool SMP, class SH>
+MB_DEV uint32_t mb_pref_windows(const MbPrefTables &T, const MbPrefScratch &W, SH *sh, const uint8_t *q, const float *bias, uint32_t P) {
     uint32_t *const itemOff = SMP ? sh->sItemOff : W.itemOff; int16_t *const wThr = SMP ? sh->sThr : W.wThr;
     uint16_t *const wI0 = SMP ? sh->sI0 : W.wI0; uint16_t *const wI1 = SMP ? sh->sI1 : W.wI1;
     CTA_FOR(p, P) {
@@ -202,8 +212,8 @@ MB_DEV uint32_t mb_pref_windows(const MbPrefTables &T, const MbPrefScratch &W, M
 }
 
 // ---- P2 + P3; returns K (similar k-mers); the non-empty ones are listed in sh->sNz / W.B (count in sh->cnt[7]).  K > capK: nothing listed.
-template <bool SMP, bool SMI>
-MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, uint32_t P, uint32_t I) {
+template <bool SMP, bool SMI, class SH>
+MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, SH *sh, uint32_t P, uint32_t I) {
     uint32_t *const itemOff = SMP ? sh->sItemOff : W.itemOff; int16_t *const wThr = SMP ? sh->sThr : W.wThr;
     uint16_t *const wI0 = SMP ? sh->sI0 : W.wI0; uint16_t *const wI1 = SMP ? sh->sI1 : W.wI1;
     uint32_t *const kmerOff = SMI ? sh->sKmerOff : W.kmerOff;
@@ -270,7 +280,7 @@ MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, Mb
                 const uint32_t n = cta_append_slot(&sh->cnt[7], nz[u]);
                 if (nz[u]) {
                     const uint64_t w = ((uint64_t)pv[u] << 44) | ((uint64_t)(k0 + u) << 26) | km[u];
-                    if (n < MB_SM_NZ) sh->sNz[n] = w; else W.B[n - MB_SM_NZ] = w;
+                    if (n < SH::Cfg::SM_NZ) sh->sNz[n] = w; else W.B[n - SH::Cfg::SM_NZ] = w;
                 }
             }
         }
@@ -279,13 +289,14 @@ MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, Mb
 }
 
 // One query.  q/bias/corr point at this query's residues, float composition bias (seed matrix) and int8 profile correction.
-MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, MbPrefShared *sh, const uint8_t *q, const float *bias,
+template <class SH>
+MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH *sh, const uint8_t *q, const float *bias,
                                const int8_t *corr, uint32_t L, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats) {
     const uint32_t P = (L >= 10) ? (L - 9) : 0;   // Sequence::hasNextKmer, spaced pattern length 10 (Sequence.h:23,92-94)
     MB_PHASE(15);   // time between queries (queue pop, previous epilogue)
     CTA_SINGLE { for (int i = 0; i < 8; i++) sh->cnt[i] = 0; }
     CTA_FOR(i, 256) sh->hist[i] = 0;
-    CTA_FOR(i, MB_NSLOT / 16) sh->slots[i] = 0;
+    CTA_FOR(i, SH::Cfg::NSLOT / 16) sh->slots[i] = 0;
     CTA_SYNC();
     MB_PHASE(0);    // clearing
     if (L >= 32768 || P > T.capP) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_TOO_LONG; } return; }
@@ -295,7 +306,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     const uint32_t I = smP ? mb_pref_windows<true>(T, W, sh, q, bias, P) : mb_pref_windows<false>(T, W, sh, q, bias, P);
     MB_PHASE(1);
     if (I > T.capI) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
-    const uint32_t K = (smP && I <= MB_SM_I) ? mb_pref_expand<true, true>(T, W, sh, P, I)
+    const uint32_t K = (smP && I <= SH::Cfg::SM_I) ? mb_pref_expand<true, true>(T, W, sh, P, I)
                      : smP ? mb_pref_expand<true, false>(T, W, sh, P, I) : mb_pref_expand<false, false>(T, W, sh, P, I);
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
     CTA_SYNC();
@@ -307,7 +318,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     for (uint32_t r0 = 0; r0 < nNz; r0 += 4 * CTA_NT) {
         uint64_t wv[4]; uint32_t lo[4], len[4], base[4]; uint2 e0[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t n = r0 + u * CTA_NT + CTA_TID; wv[u] = 0; if (n < nNz) wv[u] = (n < MB_SM_NZ) ? sh->sNz[n] : W.B[n - MB_SM_NZ]; }
+        for (int u = 0; u < 4; u++) { const uint32_t n = r0 + u * CTA_NT + CTA_TID; wv[u] = 0; if (n < nNz) wv[u] = (n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]; }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             lo[u] = 0; len[u] = 0;
@@ -354,7 +365,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
                 const uint2 en = x ? T.entries[(size_t)lo[u] + x] : e0[u];
                 const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
                 W.A[b0 + base[u] + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
-                const uint32_t slot = en.x & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+                const uint32_t slot = en.x & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
                 const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
                 if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
             }
@@ -368,7 +379,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     //               targets possibly seen more than once -> multi list
     CTA_FOR(h, M) {
         const uint64_t w = W.A[h];
-        const uint32_t slot = MB_W_SEQ(w) & (MB_NSLOT - 1), sft = (slot & 15u) * 2u;
+        const uint32_t slot = MB_W_SEQ(w) & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
         const bool multi = (sh->slots[slot >> 4] >> sft) & 2u;
         const uint32_t ib = cta_append_slot(&sh->cnt[0], multi);
         if (multi) W.B[ib] = w;
@@ -381,10 +392,10 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, Mb
     MB_PHASE(5);
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
     if (nMulti == 0) {
-    } else if (nMulti <= (1u << (MB_HT_LOG_MAX - 1))) {
+    } else if (nMulti <= (1u << (SH::Cfg::HT_LOG_MAX - 1))) {
         // Sort-free: group the multi list by target with a shared-memory hash table (the k-mer list's space is free now), then every
         // hit looks up its predecessor *of the same target* (largest smaller arrival key) inside its group.
-        uint32_t htLog = 6; while ((1u << htLog) < 2u * nMulti) htLog++;
+        uint32_t htLog = SH::Cfg::HT_LOG_MAX < 6u ? SH::Cfg::HT_LOG_MAX : 6u; while ((1u << htLog) < 2u * nMulti) htLog++;
         const uint32_t htN = 1u << htLog;
         uint32_t *htKey = sh->sHitOff, *htOff = sh->sHitOff + htN;
         CTA_FOR(i, 2 * htN) sh->sHitOff[i] = 0;

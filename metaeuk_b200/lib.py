@@ -67,10 +67,11 @@ def load_library():
     """Load the in-tree library; fail loudly if it is missing (there is no CPU path)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("MB200_LIB_PATH", LIB_PATH)   # (tuning experiments load an alternative build of the same sources)
+        if not os.path.exists(path):
             raise Mb200Error("libmetaeuk_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                              "metaeuk_b200 has no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.mb200_last_error.restype = C.c_char_p
         L.mb200_evalue.restype = C.c_double
         L.mb200_evalue.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -9,6 +9,43 @@
 #include "../../metaeuk_b200/csrc/host_tables.h"
 #include "../../metaeuk_b200/csrc/prefilter_core.cuh"
 
+template <class SH>
+static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
+                           int kmerThr, int maxHits, int minDiag, int binSize, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, unsigned long long *statsOut) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
+    mb200::build_sim3(m.seed, sim3, cnt3, MB_CNT_MIN, MB_CNT_W);
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, toff, nT, m.seed, kmerThr, idx)) return -1;
+    MbPrefTables T; memset(&T, 0, sizeof(T));
+    std::vector<uint32_t> bits(mb200::KMER_TABLE / 32, 0);   // same bitmap k_kmer_bits builds on the device
+    for (size_t k = 0; k < mb200::KMER_TABLE; k++) if (idx.offsets[k + 1] != idx.offsets[k]) bits[k >> 5] |= 1u << (k & 31);
+    T.kmerBits = bits.data();
+    T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
+    T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
+    T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
+    std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI);
+    std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP);
+    std::vector<uint64_t> A(T.capM), B(T.capM), C(T.capM); std::vector<int32_t> S(T.capM);
+    MbPrefScratch W; W.itemOff = itemOff.data(); W.wThr = wThr.data(); W.wI0 = wI0.data(); W.wI1 = wI1.data(); W.kmerOff = kmerOff.data();
+    W.itemInfo = itemInfo.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
+    SH *sh = new SH();
+    for (int i = 0; i < 441; i++) sh->ungMat[i] = (int8_t)m.ung[i];
+    MbPrefStats st; memset(&st, 0, sizeof(st));
+    std::vector<float> bias; std::vector<int8_t> corr;
+    for (uint32_t i = 0; i < nQ; i++) {
+        const uint8_t *qs = q + qOff[i]; const uint32_t L = (uint32_t)(qOff[i + 1] - qOff[i]);
+        bias.resize(L + 1); corr.resize(L + 1);
+        for (uint32_t p = 0; p < L; p++) { bias[p] = mb_comp_bias_at(m.seed, m.seedPBack, qs, (int)L, (int)p); corr[p] = mb_round_bias_quarter(bias[p]); }
+        mb_prefilter_query(T, W, sh, qs, bias.data(), corr.data(), L, out + (size_t)i * maxHits, outCount + i, outStatus + i, &st);
+    }
+    delete sh;
+    if (statsOut) { statsOut[0] = st.kmers; statsOut[1] = st.lookups; statsOut[2] = st.dbMatches; statsOut[3] = st.doubleHits; statsOut[4] = st.diagCells; statsOut[5] = st.results; }
+    return 0;
+}
+
+
+
 extern "C" {
 
 int emu_matrices(int16_t *seed, int16_t *ung, int16_t *aln, double *seedPBack, double *alnPBack) {
@@ -42,38 +79,13 @@ int emu_index(const uint8_t *masked, const uint64_t *off, uint32_t nT, int kmerT
     return 0;
 }
 
-int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
-                  int kmerThr, int maxHits, int minDiag, int binSize, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, unsigned long long *statsOut) {
-    mb200::Matrices m; mb200::default_matrices(m);
-    std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
-    mb200::build_sim3(m.seed, sim3, cnt3, MB_CNT_MIN, MB_CNT_W);
-    mb200::TargetIndex idx;
-    if (mb200::build_index(masked, toff, nT, m.seed, kmerThr, idx)) return -1;
-    MbPrefTables T; memset(&T, 0, sizeof(T));
-    std::vector<uint32_t> bits(mb200::KMER_TABLE / 32, 0);   // same bitmap k_kmer_bits builds on the device
-    for (size_t k = 0; k < mb200::KMER_TABLE; k++) if (idx.offsets[k + 1] != idx.offsets[k]) bits[k >> 5] |= 1u << (k & 31);
-    T.kmerBits = bits.data();
-    T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
-    T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
-    T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
-    std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI);
-    std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP);
-    std::vector<uint64_t> A(T.capM), B(T.capM), C(T.capM); std::vector<int32_t> S(T.capM);
-    MbPrefScratch W; W.itemOff = itemOff.data(); W.wThr = wThr.data(); W.wI0 = wI0.data(); W.wI1 = wI1.data(); W.kmerOff = kmerOff.data();
-    W.itemInfo = itemInfo.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
-    MbPrefShared *sh = new MbPrefShared();
-    for (int i = 0; i < 441; i++) sh->ungMat[i] = (int8_t)m.ung[i];
-    MbPrefStats st; memset(&st, 0, sizeof(st));
-    std::vector<float> bias; std::vector<int8_t> corr;
-    for (uint32_t i = 0; i < nQ; i++) {
-        const uint8_t *qs = q + qOff[i]; const uint32_t L = (uint32_t)(qOff[i + 1] - qOff[i]);
-        bias.resize(L + 1); corr.resize(L + 1);
-        for (uint32_t p = 0; p < L; p++) { bias[p] = mb_comp_bias_at(m.seed, m.seedPBack, qs, (int)L, (int)p); corr[p] = mb_round_bias_quarter(bias[p]); }
-        mb_prefilter_query(T, W, sh, qs, bias.data(), corr.data(), L, out + (size_t)i * maxHits, outCount + i, outStatus + i, &st);
-    }
-    delete sh;
-    if (statsOut) { statsOut[0] = st.kmers; statsOut[1] = st.lookups; statsOut[2] = st.dbMatches; statsOut[3] = st.doubleHits; statsOut[4] = st.diagCells; statsOut[5] = st.results; }
-    return 0;
+// cfg 1 = dense, 2 = sparse (the two device configurations), 3 = a deliberately tiny one that pushes every list through its
+// global-memory fallback (items, non-empty k-mers, hash table -> sort path, sorts in global memory)
+int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ, int kmerThr, int maxHits,
+                  int minDiag, int binSize, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, unsigned long long *statsOut, int cfg) {
+    if (cfg == 2) return emu_prefilter_t<MbPrefSharedT<MbPrefCfgSparse>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
+    if (cfg == 3) return emu_prefilter_t<MbPrefSharedT<MbPrefCfg<64, 1, 8, 64, 5>>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
+    return emu_prefilter_t<MbPrefSharedT<MbPrefCfgDense>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
 }
 
 }  // extern "C"

@@ -25,10 +25,13 @@ def strkeys(d):
     return {str(k): v for k, v in d.items()}
 
 
+@pytest.mark.parametrize("cfg", [1, 2], ids=["dense", "sparse"])
 @pytest.mark.parametrize("name", FRAG + CONTIG)
-def test_prefilter_golden(name):
+def test_prefilter_golden(name, cfg):
+    """both kernel configurations (the library picks one from the index density; here each is forced)"""
     c = reflib.load_case(name)
     ctx, tdb = ctx_for(c)
+    ctx.option_set("prefilter_config", cfg)
     got = strkeys(M.prefilter(ctx, c["queries"], tdb))
     bad = [k for k, _ in c["queries"] if got[str(k)] != c["pref"].get(str(k), "")]
     assert not bad, (bad[:5], got[str(bad[0])][:300], c["pref"].get(str(bad[0]), "")[:300])
@@ -81,11 +84,13 @@ def synth(seed, nprot, nfrag):
     return prots, frags
 
 
-def test_search_matches_oracle_on_larger_synthetic():
+@pytest.mark.parametrize("cfg", [1, 2], ids=["dense", "sparse"])
+def test_search_matches_oracle_on_larger_synthetic(cfg):
     """C2-shaped input scaled to what the scalar oracle finishes in seconds: 3000 proteins x 1500 fragments."""
     prots, frags = synth(2024, 3000, 1500)
     tdb = M.TargetDB(list(enumerate(prots)))
     ctx = M.make_context(tdb)
+    ctx.option_set("prefilter_config", cfg)
     queries = list(enumerate(frags))
     got_pref = M.prefilter(ctx, queries, tdb)
     o = reflib.Oracle()
@@ -154,6 +159,47 @@ def test_edge_cases():
     h, c = ctx.prefilter(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert len(c) == 0
     o.close()
+    ctx.close()
+
+
+def test_long_queries_take_the_32bit_alignment_path():
+    """queries longer than 1024 residues skip the packed 16-bit kernel; longer than 512 windows spill the window arrays"""
+    prots, _ = synth(11, 300, 1)
+    rng = random.Random(5)
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    def mutate(s, r):
+        return "".join(rng.choice(AA) if rng.random() < r else ch for ch in s)
+    queries = [(0, mutate(prots[3] + prots[17] + prots[40] + prots[41], 0.2)), (1, mutate(prots[8], 0.3)), (2, mutate(prots[100] + prots[101] + prots[102] + prots[103] + prots[104], 0.1))]
+    assert len(queries[0][1]) > 1024 and len(queries[2][1]) > 1024
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb)
+    got_pref = M.prefilter(ctx, queries, tdb)
+    got_aln = M.search(ctx, queries, tdb)
+    o = reflib.Oracle()
+    o.set_params()
+    o.set_targets(prots, prots)
+    res, _ = o.prefilter([s for _, s in queries])
+    keys = list(range(len(prots))); tlens = [len(p) for p in prots]
+    alns, _ = o.align([s for _, s in queries], [[t for t, _, _ in h] for h in res])
+    for (k, q), hits, al in zip(queries, res, alns):
+        assert got_pref[k] == reflib.fmt_pref(hits, keys), k
+        want = "".join(reflib.fmt_aln(a, keys, len(q), tlens) for a in reflib.sort_alns([a for a in al if a["passed"] == 1], keys, tlens))
+        assert got_aln[k] == want and want, k
+    o.close()
+    ctx.close()
+
+
+def test_limits_fail_loudly():
+    from metaeuk_b200.lib import Mb200Error
+    prots, _ = synth(12, 50, 1)
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb)
+    with pytest.raises(Mb200Error):   # >= 32768 residues
+        M.prefilter(ctx, [(0, "ACDEFGHIKL" * 3300)], tdb)
+    ctx.close()
+    ctx = M.make_context(tdb, cap_items_log2=6, cap_kmers_log2=8, cap_hits_log2=8)   # work lists far too small: error, never a silent drop
+    with pytest.raises(Mb200Error):
+        M.prefilter(ctx, [(0, prots[0])], tdb)
     ctx.close()
 
 

@@ -55,8 +55,11 @@ def test_host_index_matches_reference_digest(emu, name):
     assert hashlib.sha256(offsets.tobytes()).hexdigest() == c["idx_offsets_u64_sha256"]
 
 
+@pytest.mark.parametrize("cfg", [1, 2, 3], ids=["dense", "sparse", "tiny-all-fallbacks"])
 @pytest.mark.parametrize("name", ["frag_small", "frag_family", "frag_nomask", "contigs_small", "contigs_sets"])
-def test_prefilter_kernel_logic_matches_reference(emu, name):
+def test_prefilter_kernel_logic_matches_reference(emu, name, cfg):
+    """cfg 1/2 = the two kernel configurations of the library; 3 = a tiny configuration whose shared-memory homes overflow on every
+    query, so the global-memory fallbacks of every list (and the sort-based double-hit path) are diffed against the reference too"""
     c = reflib.load_case(name)
     keys = [k for k, _ in c["targets"]]
     m, toff = reflib.pack(c["masked_targets"])
@@ -69,7 +72,7 @@ def test_prefilter_kernel_logic_matches_reference(emu, name):
     cnt = np.zeros(nQ, np.uint32); st = np.zeros(nQ, np.uint32); stats = np.zeros(6, np.uint64)
     p = reflib._p
     rc = emu.emu_prefilter(p(m, C.c_uint8), p(toff, C.c_uint64), len(keys), p(q, C.c_uint8), p(qoff, C.c_uint64), nQ, c["kmer_thr"], maxres, 15, 2,
-                           hits, p(cnt, C.c_uint32), p(st, C.c_uint32), p(stats, C.c_uint64))
+                           hits, p(cnt, C.c_uint32), p(st, C.c_uint32), p(stats, C.c_uint64), cfg)
     assert rc == 0
     assert (st == 0).all()
     bad = 0
