@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="fragments in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--sw-kernel", type=int, default=0, help="forward alignment kernel variant (diagnostic; 0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,6 +230,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     ctx.matrices_default()
+    if args.sw_kernel:
+        ctx.option_set("sw_kernel", args.sw_kernel)
     t_idx0 = time.perf_counter()
     prot, poff = gen_proteins(wl["n_prot"])
     if rank == 0:

@@ -40,10 +40,13 @@ def test_prefilter_golden(name, cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("sw", [1, 2, 3], ids=["rows", "rows2-packed", "rows3-state-machine"])
 @pytest.mark.parametrize("name", FRAG + CONTIG)
-def test_align_golden(name):
+def test_align_golden(name, sw):
+    """every forward alignment kernel variant (mb200_option_set "sw_kernel") must give the reference's result DB"""
     c = reflib.load_case(name)
     ctx, tdb = ctx_for(c)
+    ctx.option_set("sw_kernel", sw)
     pref = {k: c["pref"].get(str(k), "") for k, _ in c["queries"]}
     got = strkeys(M.align(ctx, c["queries"], tdb, pref))
     bad = [k for k, _ in c["queries"] if got[str(k)] != c["aln"].get(str(k), "")]
