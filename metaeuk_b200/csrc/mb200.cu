@@ -261,7 +261,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
     else if (n == "prefilter_config") { if (value < 0 || value > 2) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense) or 2 (sparse)"); c->optPrefCfg = (int)value; }
-    else if (n == "sw_kernel") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit) or 3 (packed, per-lane state machine)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_kernel") { if (value < 1 || value > 3) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit) or 3 (packed, per-lane state machine)"); c->optSwKernel = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
     return 0;
@@ -526,12 +526,11 @@ static int align_pipeline(mb200_ctx *c) {
     for (int k = 0; k < 2; k++) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
-        if (c->optSwKernel >= 3) {
+        if (c->optSwKernel == 3) {
             int W = (int)((100u * 1024u) / (2u * 22u * strides[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
             const size_t smem = (size_t)W * 2u * 22u * strides[k];
             CU(cudaFuncSetAttribute(k_sw_rows3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows3, W * 32, smem)); if (perSM < 1) perSM = 1;
-            if (c->optSwKernel == 4) perSM = 1;   // experiment: one CTA per SM leaves ~130 KB of L1 for the per-lane streams
             const int blocks = c->nSM * perSM;
             TRY(c->dBnd.alloc((size_t)blocks * W * maxT * 32u * 2u));
             k_sw_rows3<<<blocks, W * 32, smem, c->stream>>>(c->dOrder.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
