@@ -287,6 +287,7 @@ def case_contigs(name, seed, nprot, nc, cl, mask=1, sets=1, thr=8):
         "case": name, "kind": "contigs", "seed": seed, "mask": mask, "max_exon_sets": sets,
         "targets": seqdb(tmp + "/proteins"),
         "contig_lens": {str(k): len(s) for k, s in seqdb(tmp + "/contigs")},
+        "contigs": seqdb(tmp + "/contigs"),            # nucleotide contigs: input of extractorfs + translatenucs
         "queries": seqdb(tmp + "/aa_6f"),
         "orf_headers": {str(k): e[:-1].decode() for k, e in read_db(tmp + "/nucl_6f_h")},
         "pref": resdb(tmp + "/pref"), "aln": resdb(tmp + "/aln"),
