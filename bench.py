@@ -40,6 +40,8 @@ WORKLOADS = {
     "c3": dict(n_prot=500_000, n_frag=1_000_000, align=True, desc="C3: 1M fragments x 500K proteins, prefilter + gapped SW align"),
     "c3s": dict(n_prot=500_000, n_frag=100_000, align=True, desc="C3/10: 100K fragments x 500K proteins, prefilter + gapped SW align (profiling size)"),
     "tiny": dict(n_prot=2_000, n_frag=4_000, align=True, desc="tiny: 4K fragments x 2K proteins (plumbing check)"),
+    "orf": dict(n_contigs=4_000, contig_len=50_000, orf=True, n_prot=0, n_frag=0, align=False,
+                desc="ORF stage (SURVEY 8f-1): 4000 contigs x 50 kb random DNA -> six-frame fragments >= 15 codons, translated"),
 }
 
 
@@ -72,6 +74,83 @@ def gen_fragments(n, prot, poff, seed=4321):
     take = homolog[frag_id] & (within < use[frag_id]) & (rng.random(tot) >= rate[frag_id])
     res[take] = prot[src[take]]
     return res, off
+
+
+def gen_contigs(n, length, seed=1234):
+    rng = np.random.default_rng(seed)
+    nuc = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * length, dtype=np.uint8)]
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
+    return np.ascontiguousarray(nuc), off
+
+
+def bench_orf(args, wl, base, rank, world, local, threads):
+    """the step before the path: contigs -> six-frame fragments -> residues.  value = fragments/s of the kernels with the contigs resident
+    (CUDA events), e2e = the C-ABI call with host buffers (H2D of the contigs, kernels, D2H of records + residues)."""
+    import torch
+    import torch.distributed as dist
+    from metaeuk_b200.lib import Context
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+    nuc, off = gen_contigs(wl["n_contigs"], wl["contig_len"], seed=1234 + rank)
+    (nucP, _k1), (offP, _k2) = pinned(nuc), pinned(off)
+    W = max(3, args.warmup)
+    for _ in range(W):
+        ctx.extract_orfs(nucP, offP)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.stats()["launches"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    kms = []; out_bytes = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        recs, aa = ctx.extract_orfs(nucP, offP)
+        kms.append(ctx.stats()["ms_orf"]); out_bytes = int(recs.nbytes + aa.nbytes)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = ctx.stats()
+    vals = [dt, float(np.sum(kms)) * 1e-3]
+    if world > 1:
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in t.tolist()]
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    nfrag = int(st["orf_fragments"])
+    peak, peak_src = measured_peak()
+    abytes = 2 * int(st["orf_nucleotides"]) + 2 * int(st["orf_residues"]) + 32 * nfrag   # both strands read once, residues + codes written, one record per fragment
+    kernel_ms = float(np.mean(kms))
+    base["config"].update({"fragments_per_gpu": nfrag, "contigs_per_gpu": wl["n_contigs"], "nucleotides_per_gpu": int(st["orf_nucleotides"]), "stages": "extractorfs+translatenucs",
+                           "l2": "contigs (%d MB) exceed L2; no explicit flush" % (int(st["orf_nucleotides"]) >> 20)})
+    base.update({"value": world * nfrag * args.steps / vals[1], "ms_per_step": 1000 * vals[1] / args.steps, "clocks": clocks, "gpu_launches": int(st["launches"] - l0),
+                 "e2e": {"value": world * nfrag * args.steps / vals[0], "unit": "fragments/s", "h2d_bytes_per_step": int(nuc.nbytes + off.nbytes), "d2h_bytes_per_step": out_bytes,
+                         "ms_per_step": 1000 * vals[0] / args.steps},
+                 "roofline": {"kernel": "k_orf_scan x2 + k_orf_translate", "bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kernel_ms, "traffic": None},
+                 "work": {"nucleotides": int(st["orf_nucleotides"]), "fragments": nfrag, "residues": int(st["orf_residues"])}})
+    if args.gpus == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import reflib
+        nsample = min(wl["n_contigs"], 16 * threads)
+        sseq = nuc[:int(off[nsample])].tobytes(); soff = np.ascontiguousarray(off[:nsample + 1])
+        reflib.oracle_extract_orfs_raw(sseq[:int(off[2])], np.ascontiguousarray(off[:3]))
+        t0 = time.perf_counter()
+        ncpu, _r, _a = reflib.oracle_extract_orfs_raw(sseq, soff, threads=threads)
+        tcpu = time.perf_counter() - t0
+        base["cpu_baseline"] = {"value": ncpu / tcpu, "unit": "fragments/s", "cores": threads, "kind": "port",
+                                "sample": "first %d contigs of the workload, all %d host threads (OpenMP over contigs)" % (nsample, threads)}
+    emit(base)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def pinned(a):
@@ -207,6 +286,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if wl.get("orf"):
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import reflib
+            nuc, off = gen_contigs(wl["n_contigs"], wl["contig_len"])
+            nsample = min(wl["n_contigs"], 16 * threads)
+            sseq = nuc[:int(off[nsample])].tobytes(); soff = np.ascontiguousarray(off[:nsample + 1])
+            t0 = time.perf_counter(); nfr = 0
+            for _ in range(max(1, args.steps)):
+                nfr += reflib.oracle_extract_orfs_raw(sseq, soff, threads=threads)[0]
+            t = time.perf_counter() - t0
+            base.update({"impl": "reference", "value": nfr / t, "ms_per_step": 1000 * t / max(1, args.steps), "gpu_launches": 0,
+                         "cpu_baseline": {"value": nfr / t, "unit": "fragments/s", "cores": threads, "kind": "port", "sample": "first %d contigs per step, all %d host threads (OpenMP over contigs)" % (nsample, threads)},
+                         "e2e": {"value": nfr / t, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            emit(base)
+            return
         prot, poff = gen_proteins(wl["n_prot"])
         frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321)
         n_sample = args.cpu_sample or (8192 if not wl["align"] else 2048)
@@ -222,6 +316,8 @@ def main():
         emit(base)
         return
     # ------------------------------------------------------------------ B200 arm
+    if wl.get("orf"):
+        return bench_orf(args, wl, base, rank, world, local, threads)
     import torch
     import torch.distributed as dist
     from metaeuk_b200.lib import Context

@@ -72,6 +72,13 @@ typedef struct mb200_exon { uint32_t cand_idx; int32_t contig_start, contig_end,
 typedef struct mb200_call {
     uint32_t target_key; int32_t strand; int32_t total_bit_score; int32_t n_exons; uint32_t exon_begin; int32_t low_coord, high_coord, pad; double evalue;
 } mb200_call;
+typedef struct mb200_orf {   /* one six-frame fragment = one entry of the reference's nucl_6f_h / aa_6f DBs (key = index in the array) */
+    uint32_t contig;           /* index of the contig in the input batch */
+    uint32_t from, to;         /* header coordinates on the contig (Orf::writeOrfHeader): from > to on the minus strand */
+    uint32_t flags;            /* 1 = incomplete start, 2 = incomplete end (header column 3), 4 = minus strand */
+    uint64_t aa_off; uint32_t aa_len;   /* residues aa[aa_off .. aa_off + aa_len) */
+    uint32_t strand_from;      /* first nucleotide on the strand the fragment was read from */
+} mb200_orf;
 typedef struct mb200_stats {   /* algorithmic work counters of the last prefilter / align call (roofline numerators) */
     uint64_t kmers, lookups, db_matches, double_hits, diag_cells, pref_results;
     uint64_t sw_pairs, sw_cells_fwd, sw_cells_rev, sw_target_bytes;
@@ -79,6 +86,8 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     double ms_prep, ms_prefilter, ms_sw_fwd, ms_sw_rev, ms_chain, ms_h2d, ms_d2h, ms_host;
     uint32_t launches, pad;
     uint64_t pref_phase_cycles[16];   /* k_prefilter: CTA cycles summed over queries, per phase; [15] = between queries */
+    double ms_orf, ms_orf_host;       /* mb200_extract_orfs: kernels with the contigs resident (CUDA events) / whole call incl. H2D and D2H (wall clock) */
+    uint64_t orf_nucleotides, orf_fragments, orf_residues;
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);
@@ -122,6 +131,16 @@ int mb200_search(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32
  * calls/exons are caller buffers sized 2*n_cands*max_exon_sets and n_cands*max_exon_sets; call_off/exon ranges are per contig. */
 int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_off, uint32_t n_contigs, uint64_t total_target_residues,
                 mb200_call *calls, uint32_t *call_count /* n_contigs */, mb200_exon *exons);
+
+/* Six-frame ORF fragments of nucleotide contigs and their translation = `extractorfs` + `translatenucs` with the flags of
+ * `metaeuk predictexons` (M/src/util/extractorfs.cpp:19-159, M/src/commons/Orf.cpp:230-349, M/src/util/translatenucs.cpp:13-118,
+ * M/src/commons/TranslateNucl.h:383-503).  nuc = concatenated ASCII nucleotides (as stored in the contig DB, any case, IUPAC codes),
+ * off[n_contigs+1]; min_len / max_len in codons (15 / 32734), start_mode 1.  Fragments come back in the reference's key order;
+ * *orfs and *aa are owned by the context (valid until the next call).  mb200_queries_from_orfs() then makes the fragments the resident
+ * query batch without a host round trip (follow with mb200_prefilter_resident / mb200_align_resident). */
+int mb200_extract_orfs(mb200_ctx *ctx, const char *nuc, const uint64_t *off, uint32_t n_contigs, int min_len, int max_len, int start_mode,
+                       uint64_t *n_orfs, const mb200_orf **orfs, uint64_t *n_aa, const char **aa);
+int mb200_queries_from_orfs(mb200_ctx *ctx);
 
 /* device-resident variant used for kernel-only timing: upload once, run many times, download once */
 int mb200_queries_upload(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q);

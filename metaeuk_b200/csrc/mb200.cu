@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(SH::Cfg::NT, SH::Cfg::CTAS) k_prefilter(MbPref
 }
 
 #include "sw_kernels.cuh"
+#include "orf_kernels.cuh"
 
 // ---- exon chaining: one contig per thread -----------------------------------------------------------
 __global__ void __launch_bounds__(128) k_chain(const MbCand *__restrict__ cands, const uint64_t *__restrict__ candOff, uint32_t nContigs, MbChainParams P,
@@ -149,6 +150,9 @@ struct mb200_ctx {
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
     std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<uint64_t> hHitOff;
+    // ORF extraction
+    DevBuf<unsigned char> dNuc; DevBuf<uint64_t> dNucOff, dOrfAaCnt, dOrfRecBase, dOrfAaBase; DevBuf<uint32_t> dOrfCnt; DevBuf<MbOrfTables> dOrfTab; bool haveOrfTab = false;
+    DevBuf<MbOrfRec> dOrfRecs; DevBuf<char> dOrfAa; DevBuf<uint8_t> dOrfCodes; PinBuf<MbOrfRec> pOrfRecs; PinBuf<char> pOrfAa; uint64_t nOrfs = 0, nOrfAa = 0;
     PinBuf<mb200_hit> pFlatHits; PinBuf<uint32_t> pOff, pStatus; size_t nFlatHits = 0;
     bool haveAln = false;
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
@@ -212,6 +216,12 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
     return 0;
 }
 
+static int sync_check(mb200_ctx *c, const char *what) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(MB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -251,7 +261,8 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
-    c->pFlatHits.release(); c->pOff.release(); c->pStatus.release();
+    c->pFlatHits.release(); c->pOff.release(); c->pStatus.release(); c->pOrfRecs.release(); c->pOrfAa.release();
+    c->dNuc.release(); c->dNucOff.release(); c->dOrfAaCnt.release(); c->dOrfRecBase.release(); c->dOrfAaBase.release(); c->dOrfCnt.release(); c->dOrfTab.release(); c->dOrfRecs.release(); c->dOrfAa.release(); c->dOrfCodes.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -397,8 +408,9 @@ int mb200_index_commit(mb200_ctx *c) {
 }
 
 // ---- query upload + per-residue preparation ----------------------------------------------------------
-int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ) {
-    if (!c || !q || !qoff) return fail(MB200_E_ARG, "null argument");
+// q: host residues, or NULL with qDev = residues already in device memory (fragments produced by mb200_extract_orfs)
+static int queries_install(mb200_ctx *c, const uint8_t *q, const uint8_t *qDev, const uint64_t *qoff, uint32_t nQ) {
+    if (!c || (!q && !qDev) || !qoff) return fail(MB200_E_ARG, "null argument");
     if (!c->haveMat) return fail(MB200_E_STATE, "matrices not set");
     CU(cudaSetDevice(c->device));
     const uint64_t tot = qoff[nQ];
@@ -414,7 +426,8 @@ int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, u
         for (uint32_t i = 0; i < nQ; i++) order[start[maxL - (uint32_t)(qoff[i + 1] - qoff[i])]++] = i;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
-    TRY(upload(c->dQ.p, q, tot, c->stream)); TRY(upload(c->dQoff.p, qoff, (size_t)(nQ + 1) * 8, c->stream)); TRY(upload(c->dOrder.p, order.data(), (size_t)nQ * 4, c->stream));
+    if (q) { TRY(upload(c->dQ.p, q, tot, c->stream)); } else if (tot) { CU(cudaMemcpyAsync(c->dQ.p, qDev, tot, cudaMemcpyDeviceToDevice, c->stream)); }
+    TRY(upload(c->dQoff.p, qoff, (size_t)(nQ + 1) * 8, c->stream)); TRY(upload(c->dOrder.p, order.data(), (size_t)nQ * 4, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_h2d = ms;
@@ -429,6 +442,111 @@ int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, u
     }
     c->st.query_residues = tot; c->st.n_queries = nQ;
     return 0;
+}
+
+int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t nQ) {
+    if (!q) return fail(MB200_E_ARG, "null argument");
+    return queries_install(c, q, nullptr, qoff, nQ);
+}
+
+
+// ---- ORF extraction + translation (the step before the path: extractorfs + translatenucs) ----------------
+static void orf_build_tables(MbOrfTables &T) {
+    // complement (Orf::iupacReverseComplementTable, Orf.cpp:47-51) with "no complement" -> 'N' (Orf.cpp:146-150)
+    const char *from = "ATUGCYRSWKMBDHVN", *to = "TAACGRYSWMKVHDBN";
+    for (int c = 0; c < 256; c++) T.comp[c] = 'N';
+    for (int i = 0; from[i]; i++) { T.comp[(unsigned char)from[i]] = (unsigned char)to[i]; T.comp[(unsigned char)tolower(from[i])] = (unsigned char)tolower(to[i]); }
+    // IUPAC letter -> base set (TranslateNucl::initConversionTable, TranslateNucl.h:334-362); illegal characters -> gap
+    const char *bases = "-ACMGRSVTWYHKDBN";
+    for (int c = 0; c < 256; c++) T.base[c] = 0;
+    for (int i = 0; i < 16; i++) { T.base[(unsigned char)bases[i]] = (unsigned char)i; T.base[(unsigned char)tolower(bases[i])] = (unsigned char)i; T.base[i] = (unsigned char)i; }
+    T.base['U'] = T.base['u'] = 8; T.base['X'] = T.base['x'] = 15;
+    // codon table of genetic code 1 over base sets (TranslateNucl::initTranslationTable, TranslateNucl.h:383-485)
+    const char *code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    const int ex[4] = {1, 2, 4, 8}; const int tcag[9] = {0, 2, 1, 0, 3, 0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) for (int j = 0; j < 16; j++) for (int k = 0; k < 16; k++) {
+        char aa = 0; bool go = true;
+        for (int p = 0; p < 4 && go; p++) if (ex[p] & i) for (int q = 0; q < 4 && go; q++) if (ex[q] & j) for (int r = 0; r < 4 && go; r++) if (ex[r] & k) {
+            const char ch = code[16 * tcag[ex[p]] + 4 * tcag[ex[q]] + tcag[ex[r]]];
+            if (!aa) aa = ch;
+            else if (aa != ch) {
+                if ((aa == 'B' || aa == 'D' || aa == 'N') && (ch == 'D' || ch == 'N')) aa = 'B';
+                else if ((aa == 'Z' || aa == 'E' || aa == 'Q') && (ch == 'E' || ch == 'Q')) aa = 'Z';
+                else if ((aa == 'J' || aa == 'I' || aa == 'L') && (ch == 'I' || ch == 'L')) aa = 'J';
+                else { aa = 'X'; go = false; }
+            }
+        }
+        T.aaOf[256 * i + 16 * j + k] = aa ? aa : 'X';
+    }
+    // residue letter -> prefilter alphabet (SubstitutionMatrix::setupLetterMapping, SubstitutionMatrix.cpp:262-304)
+    const char *order = "ACDEFGHIKLMNPQRSTVWYX";
+    for (int c = 0; c < 256; c++) T.aa2num[c] = 20;
+    for (int i = 0; order[i]; i++) { T.aa2num[(unsigned char)order[i]] = (unsigned char)i; T.aa2num[(unsigned char)tolower(order[i])] = (unsigned char)i; }
+    const char *alias = "JLZEBD";
+    for (int i = 0; i < 6; i += 2) { T.aa2num[(unsigned char)alias[i]] = T.aa2num[(unsigned char)alias[i + 1]]; T.aa2num[(unsigned char)tolower(alias[i])] = T.aa2num[(unsigned char)alias[i + 1]]; }
+}
+
+int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
+                       uint64_t *nOrfs, const mb200_orf **orfs, uint64_t *nAa, const char **aa) {
+    if (!c || !nuc || !off || !nOrfs || !orfs || !nAa || !aa) return fail(MB200_E_ARG, "null argument");
+    if (startMode != 1) return fail(MB200_E_ARG, "only --orf-start-mode 1 (any-to-stop, what metaeuk predictexons uses) is implemented");
+    if (minLen < 4 || maxLen < minLen) return fail(MB200_E_ARG, "need 4 <= min_len <= max_len (codons)");
+    if (nContigs >= (1u << 31)) return fail(MB200_E_LIMIT, "too many contigs");
+    static_assert(sizeof(MbOrfRec) == sizeof(mb200_orf), "ABI struct");
+    const auto t0 = std::chrono::steady_clock::now();
+    CU(cudaSetDevice(c->device));
+    const uint64_t total = off[nContigs] - off[0];
+    for (uint32_t i = 0; i < nContigs; i++) if (off[i + 1] - off[i] >= (1ull << 31)) return fail(MB200_E_LIMIT, "contig %u has >= 2^31 nucleotides", i);
+    if (!c->haveOrfTab) { MbOrfTables T; orf_build_tables(T); TRY(c->dOrfTab.alloc(1)); TRY(upload(c->dOrfTab.p, &T, sizeof(T), c->stream)); CU(cudaStreamSynchronize(c->stream)); c->haveOrfTab = true; }
+    const uint32_t units = 2u * nContigs;
+    TRY(c->dNuc.alloc(total + 16)); TRY(c->dNucOff.alloc(nContigs + 1)); TRY(c->dOrfCnt.alloc(units + 1)); TRY(c->dOrfAaCnt.alloc(units + 1));
+    TRY(c->dOrfRecBase.alloc(units + 1)); TRY(c->dOrfAaBase.alloc(units + 1));
+    std::vector<uint64_t> rel(nContigs + 1);
+    for (uint32_t i = 0; i <= nContigs; i++) rel[i] = off[i] - off[0];
+    TRY(upload(c->dNuc.p, nuc + off[0], total, c->stream)); TRY(upload(c->dNucOff.p, rel.data(), (size_t)(nContigs + 1) * 8, c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));   // ms_orf = the two scan passes + translation (inputs resident), incl. the host scan between them
+    c->nOrfs = 0; c->nOrfAa = 0; *nOrfs = 0; *nAa = 0; *orfs = nullptr; *aa = nullptr;
+    if (nContigs == 0) return 0;
+    const int grid = (int)std::min<uint32_t>(units, (uint32_t)c->nSM * 8u);
+    k_orf_scan<false><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen,
+                                                              c->dOrfCnt.p, c->dOrfAaCnt.p, nullptr, nullptr, nullptr);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> cnt(units); std::vector<uint64_t> acnt(units), rb(units + 1, 0), ab(units + 1, 0);
+    CU(cudaMemcpyAsync(cnt.data(), c->dOrfCnt.p, (size_t)units * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(acnt.data(), c->dOrfAaCnt.p, (size_t)units * 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "k_orf_scan (count)"));
+    for (uint32_t u = 0; u < units; u++) { rb[u + 1] = rb[u] + cnt[u]; ab[u + 1] = ab[u] + acnt[u]; }   // key order: contig, plus strand, minus strand
+    const uint64_t n = rb[units], na = ab[units];
+    TRY(c->dOrfRecs.alloc(n + 1)); TRY(c->dOrfAa.alloc(na + 16)); TRY(c->dOrfCodes.alloc(na + 16)); TRY(c->pOrfRecs.alloc(n + 1)); TRY(c->pOrfAa.alloc(na + 16));
+    TRY(upload(c->dOrfRecBase.p, rb.data(), (size_t)(units + 1) * 8, c->stream)); TRY(upload(c->dOrfAaBase.p, ab.data(), (size_t)(units + 1) * 8, c->stream));
+    if (n) {
+        k_orf_scan<true><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen,
+                                                                 nullptr, nullptr, c->dOrfRecBase.p, c->dOrfAaBase.p, c->dOrfRecs.p);
+        CU(cudaGetLastError());
+        k_orf_translate<<<c->nSM * 8, 256, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, c->dOrfTab.p, c->dOrfRecs.p, n, c->dOrfAa.p, c->dOrfCodes.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaMemcpyAsync(c->pOrfRecs.p, c->dOrfRecs.p, (size_t)n * sizeof(MbOrfRec), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->pOrfAa.p, c->dOrfAa.p, (size_t)na, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaEventRecord(c->ev1, c->stream));
+    }
+    TRY(sync_check(c, "k_orf_scan (emit) / k_orf_translate"));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->st.ms_orf = ms; c->st.orf_nucleotides = total; c->st.orf_fragments = n; c->st.orf_residues = na; c->st.launches += 3;
+    c->st.ms_orf_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->nOrfs = n; c->nOrfAa = na;
+    *nOrfs = n; *nAa = na; *orfs = reinterpret_cast<const mb200_orf *>(c->pOrfRecs.p); *aa = c->pOrfAa.p;
+    return 0;
+}
+
+int mb200_queries_from_orfs(mb200_ctx *c) {
+    if (!c) return fail(MB200_E_ARG, "null ctx");
+    if (c->nOrfs >= (1ull << 32)) return fail(MB200_E_LIMIT, "more than 2^32 fragments in one batch");
+    std::vector<uint64_t> qoff(c->nOrfs + 1);
+    for (uint64_t i = 0; i < c->nOrfs; i++) qoff[i] = c->pOrfRecs.p[i].aaOff;
+    qoff[c->nOrfs] = c->nOrfAa;
+    return queries_install(c, nullptr, c->dOrfCodes.p, qoff.data(), (uint32_t)c->nOrfs);
 }
 
 int mb200_prefilter_resident(mb200_ctx *c) {
@@ -477,11 +595,6 @@ static int min_score_for(mb200_ctx *c, uint32_t L) {
     return c->minScore[L];
 }
 
-static int sync_check(mb200_ctx *c, const char *what) {
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) return fail(MB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
-    return 0;
-}
 
 // Gapped alignment of the resident hit lists (dHits / dHitCount).  Leaves c->hTrace = every alignment whose score passes the
 // e-value gate (score, start/end coordinates), sorted by slot = query * maxHits + rank.

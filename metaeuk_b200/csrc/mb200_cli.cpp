@@ -1,5 +1,6 @@
 // mb200_cli.cpp -- C++ host driver with MetaEuk's module surface over libmetaeuk_b200 (C ABI only).
 //
+//   mb200 gpuextractorfs       <contigsDB> <orfHeaderDB> <orfAaDB>      == extractorfs + translatenucs (M/src/util/extractorfs.cpp:19, translatenucs.cpp:13)
 //   mb200 gpuprefilter         <queryDB> <targetDB> <prefDB>            == prefilter          (M/src/prefiltering/Main.cpp:13)
 //   mb200 gpualign             <queryDB> <targetDB> <prefDB> <alnDB>    == align              (M/src/alignment/Main.cpp:12)
 //   mb200 gpusearch            <queryDB> <targetDB> <alnDB>             == search (blastp.sh:70,85 without the pref DB round trip)
@@ -242,7 +243,7 @@ static std::map<uint32_t, std::string> searchAll(Session &s, const Db &qdb, cons
 static void writeDb(const std::string &name, int dbtype, const std::map<uint32_t, std::string> &m) { DbOut o(name, dbtype); for (auto &kv : m) o.write(kv.first, kv.second); }
 
 int main(int argc, char **argv) {
-    if (argc < 2) DIE("usage: mb200 <gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
+    if (argc < 2) DIE("usage: mb200 <gpuextractorfs|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
     initCodes();
     std::string cmd = argv[1]; std::vector<std::string> pos; Opt o = parseOpts(argc, argv, 2, pos);
     if (cmd == "gpuprefilter") {
@@ -288,6 +289,30 @@ int main(int argc, char **argv) {
         auto aln = searchAll(s, qdb, q);
         auto byc = byContig(contigs, hdr, aln);
         writeDb(pos[4], 12, chainAll(s.ctx, byc, s.t.res.size()));
+    } else if (cmd == "gpuextractorfs") {
+        // extractorfs + translatenucs in one step (data/predictexons.sh: contigs -> nucl_6f(_h) -> aa_6f): writes the ORF header DB and the
+        // translated fragment DB with the reference's renumbered keys
+        if (pos.size() != 3) DIE("gpuextractorfs <contigsDB> <o:orfHeaderDB (nucl_6f_h)> <o:aaDB (aa_6f)>");
+        Db contigs = openDb(pos[0]);
+        // the reference processes contigs in index order and renumbers by (contig key, offset): feed them sorted by key
+        std::vector<size_t> order(contigs.keys.size()); for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return contigs.keys[a] < contigs.keys[b]; });
+        std::string nuc; std::vector<uint64_t> off(1, 0);
+        for (size_t id : order) { const size_t n = contigs.len[id] >= 2 ? contigs.len[id] - 2 : 0; nuc.append(contigs.entry(id), n); off.push_back(nuc.size()); }
+        mb200_ctx *ctx; MB(mb200_ctx_create(o.device, &ctx));
+        uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+        MB(mb200_extract_orfs(ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
+        DbOut hdr(pos[1], 12), seq(pos[2], 0);   // DBTYPE_GENERIC_DB, DBTYPE_AMINO_ACIDS
+        char buf[96];
+        for (uint64_t i = 0; i < n; i++) {
+            const mb200_orf &r = orfs[i]; const long long d = (long long)r.from - (long long)r.to;
+            int w = snprintf(buf, sizeof(buf), "%u\t%u%c%lld", contigs.keys[order[r.contig]], r.from, r.from < r.to ? '+' : '-', d < 0 ? -d : d);   // Orf::writeOrfHeader (Orf.cpp:440-457)
+            if (r.flags & 3u) w += snprintf(buf + w, sizeof(buf) - w, "\t%u", r.flags & 3u);
+            buf[w++] = '\n';
+            hdr.write((uint32_t)i, std::string(buf, w));
+            seq.write((uint32_t)i, std::string(aa + r.aa_off, r.aa_len) + "\n");
+        }
+        mb200_ctx_destroy(ctx);
     } else DIE("unknown command %s", cmd.c_str());
     return EXIT_SUCCESS;
 }

@@ -1,0 +1,167 @@
+// orf_kernels.cuh -- six-frame ORF fragments of nucleotide contigs and their translation, the step that feeds the
+// prefilter: what `extractorfs` + `translatenucs` do with the flags `metaeuk predictexons` passes
+//   --min-length 15 --max-length 32734 --orf-start-mode 1 (ANY_TO_STOP) --contig-start-mode 2 --contig-end-mode 2 --translation-table 1
+// Reference behaviour reproduced (not its code):
+//   Orf::setSequence / findForward     reference/lib/mmseqs/src/commons/Orf.cpp:125-157,230-349   (stop-to-stop fragments per frame,
+//                                      first fragment of a frame has an incomplete start, a fragment cut by the contig end an incomplete end)
+//   extractorfs header coordinates     reference/lib/mmseqs/src/util/extractorfs.cpp:82-87, Orf.cpp:440-457
+//   TranslateNucl::translate           reference/lib/mmseqs/src/commons/TranslateNucl.h:383-503  (IUPAC-aware codon table, case preserved)
+//   key order                          DBWriter::createRenumberedDB (DBWriter.cpp:690-738): contig, then plus strand before minus, then
+//                                      the order in which fragments END along the strand (all three frames interleaved)
+// GPU organisation: in ANY_TO_STOP mode a fragment is fully determined by its terminating codon (a stop, or the last complete codon of
+// its frame) and the previous terminator of the same frame, so one CTA per (contig, strand) streams the strand in tiles, finds
+// terminators with one thread per 12 positions, and gets "previous terminator" and the output rank from two block scans.  Pass 1 counts,
+// a scan over (contig, strand) gives every CTA its output base, pass 2 writes the records in the reference's order, and a third
+// kernel translates with one thread per residue.
+#pragma once
+#include <stdint.h>
+
+#define MB_ORF_THREADS 256
+#define MB_ORF_PER_THREAD 12                      // 4 codons of each frame
+#define MB_ORF_TILE (MB_ORF_THREADS * MB_ORF_PER_THREAD)
+
+struct MbOrfRec { uint32_t contig, from, to, flags; uint64_t aaOff; uint32_t aaLen; uint32_t strandFrom; };   // from/to: header coordinates
+
+struct MbOrfTables {
+    unsigned char comp[256];     // complement with '.' -> 'N' (Orf.cpp:47-51,146-150)
+    unsigned char base[256];     // IUPAC letter -> 4-bit base set (TranslateNucl.h:334-362)
+    char aaOf[4096];             // codon (three 4-bit codes) -> residue
+    unsigned char aa2num[256];   // residue letter -> prefilter alphabet code (Sequence::mapSequence)
+};
+
+// character p of strand s of a contig (s = 0 plus, 1 minus); positions >= L read as 127 (the reference pads with CHAR_MAX)
+__device__ __forceinline__ int orf_char(const unsigned char *seq, uint32_t L, int s, uint32_t p, const unsigned char *comp) {
+    if (p >= L) return 127;
+    unsigned char c = s ? seq[L - 1u - p] : seq[p];
+    if (c == 'u') c = 't';                        // (only the lower-case branch survives in Orf::setSequence, Orf.cpp:141-144)
+    return s ? comp[c] : c;
+}
+
+__device__ __forceinline__ uint32_t orf_block_scan_add(uint32_t v, uint32_t *sm, uint32_t *total) {   // exclusive; 256 threads
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    uint32_t wp = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[i]; if (i < (int)w) wp += x; tot += x; }
+    __syncthreads();
+    *total = tot;
+    return wp + inc - v;
+}
+
+// exclusive "last terminator seen so far" per frame: max-scan of (position + 1), 0 = none
+__device__ __forceinline__ uint32_t orf_block_scan_max(uint32_t v, uint32_t *sm, uint32_t *total) {
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc = max(inc, y); }
+    uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1); if (lane == 0) excl = 0;
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    uint32_t wp = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[i]; if (i < (int)w) wp = max(wp, x); tot = max(tot, x); }
+    __syncthreads();
+    *total = tot;
+    return max(wp, excl);
+}
+
+// EMIT = false: counts[(contig, strand)] = (#fragments, #residues).  EMIT = true: writes the records at recBase / aaBase.
+template <bool EMIT>
+__global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char *__restrict__ nuc, const uint64_t *__restrict__ off, uint32_t nContigs,
+                                                             const MbOrfTables *__restrict__ tab, uint32_t minLen, uint32_t maxLen,
+                                                             uint32_t *__restrict__ cntOut, uint64_t *__restrict__ aaOut,
+                                                             const uint64_t *__restrict__ recBase, const uint64_t *__restrict__ aaBase, MbOrfRec *__restrict__ recs) {
+    __shared__ unsigned char tile[MB_ORF_TILE + 8];
+    __shared__ unsigned char comp[256];
+    __shared__ uint32_t sm[MB_ORF_THREADS / 32];
+    comp[threadIdx.x] = tab->comp[threadIdx.x];
+    for (uint32_t unit = blockIdx.x; unit < 2u * nContigs; unit += gridDim.x) {
+        const uint32_t c = unit >> 1; const int s = (int)(unit & 1u);
+        const unsigned char *seq = nuc + off[c]; const uint64_t L64 = off[c + 1] - off[c]; const uint32_t L = (uint32_t)L64;
+        uint32_t carryTerm[3] = {0, 0, 0};      // (position + 1) of the last terminator of each frame in earlier tiles
+        uint32_t carryCnt = 0; uint64_t carryAa = 0;
+        __syncthreads();
+        if (L >= 3) for (uint32_t tb = 0; tb < L; tb += MB_ORF_TILE) {
+            for (uint32_t i = threadIdx.x; i < MB_ORF_TILE + 8; i += MB_ORF_THREADS) tile[i] = (unsigned char)orf_char(seq, L, s, tb + i, comp);
+            __syncthreads();
+            // ---- terminators among my 12 positions
+            const uint32_t lb = threadIdx.x * MB_ORF_PER_THREAD;
+            uint32_t termMask = 0, stopMask = 0, myLast[3] = {0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < MB_ORF_PER_THREAD; j++) {
+                const uint32_t p = tb + lb + j;
+                const int c0 = tile[lb + j], c1 = tile[lb + j + 1], c2 = tile[lb + j + 2];
+                const bool complete = p + 2 < L;            // (127 never occurs inside a contig: createdb stores printable characters)
+                const int u0 = c0 & ~0x20, u1 = c1 & ~0x20, u2 = c2 & ~0x20;
+                const bool stop = complete && u0 == 'T' && ((u1 == 'A' && (u2 == 'A' || u2 == 'G')) || (u1 == 'G' && u2 == 'A'));
+                const bool isLast = complete && (p + 5 >= L);
+                if (stop) stopMask |= 1u << j;
+                if (stop || isLast) { termMask |= 1u << j; myLast[j % 3] = p + 1; }
+            }
+            uint32_t prev[3], tot;
+#pragma unroll
+            for (int f = 0; f < 3; f++) { prev[f] = max(orf_block_scan_max(myLast[f], sm, &tot), carryTerm[f]); carryTerm[f] = max(carryTerm[f], tot); }
+            // ---- fragments that end in my positions
+            uint32_t myCnt = 0, myAa = 0;
+            uint32_t eFrom[4], eLen[4], eInfo[4];     // at most 4 terminators of one frame... up to 12 in total, but >= minLen apart per frame
+            int ne = 0;
+#pragma unroll
+            for (int j = 0; j < MB_ORF_PER_THREAD; j++) if ((termMask >> j) & 1u) {
+                const int f = j % 3; const uint32_t p = tb + lb + j;
+                const bool stop = (stopMask >> j) & 1u;
+                const uint32_t from = prev[f] ? prev[f] - 1u + 3u : (uint32_t)f;
+                const uint32_t len = (p - from) / 3u + (stop ? 0u : 1u);
+                if (len >= minLen && len <= maxLen && len > 0) {
+                    if (ne < 4) { eFrom[ne] = from; eLen[ne] = len; eInfo[ne] = (prev[f] ? 0u : 1u) | (stop ? 0u : 2u) | ((uint32_t)j << 8); ne++; }
+                    myCnt++; myAa += len;
+                }
+                prev[f] = p + 1;
+            }
+            uint32_t totCnt, totAa;
+            const uint32_t rank = orf_block_scan_add(myCnt, sm, &totCnt);
+            const uint32_t aaRank = orf_block_scan_add(myAa, sm, &totAa);
+            if (EMIT) {
+                uint64_t a = aaBase[unit] + carryAa + aaRank;
+                for (int e = 0; e < ne; e++) {
+                    MbOrfRec r; r.contig = c; r.flags = (eInfo[e] & 3u) | (s ? 4u : 0u); r.aaOff = a; r.aaLen = eLen[e]; r.strandFrom = eFrom[e];
+                    const uint32_t to = eFrom[e] + 3u * eLen[e] - 1u;   // last nucleotide of the last counted codon
+                    r.from = s ? (L - 1u) - eFrom[e] : eFrom[e]; r.to = s ? (L - 1u) - to : to;
+                    recs[recBase[unit] + carryCnt + rank + e] = r;
+                    a += eLen[e];
+                }
+            }
+            carryCnt += totCnt; carryAa += totAa;
+            __syncthreads();
+        }
+        if (!EMIT && threadIdx.x == 0) { cntOut[unit] = carryCnt; aaOut[unit] = carryAa; }
+    }
+}
+
+// one warp per fragment, lanes over its residues: codon -> amino acid letter (case preserved) and prefilter alphabet code
+__global__ void __launch_bounds__(256) k_orf_translate(const unsigned char *__restrict__ nuc, const uint64_t *__restrict__ off, const MbOrfTables *__restrict__ tab,
+                                                       const MbOrfRec *__restrict__ recs, uint64_t nRecs, char *__restrict__ aa, uint8_t *__restrict__ codes) {
+    __shared__ char aaOf[4096];
+    __shared__ unsigned char comp[256], base[256], a2n[256];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) aaOf[i] = tab->aaOf[i];
+    comp[threadIdx.x] = tab->comp[threadIdx.x]; base[threadIdx.x] = tab->base[threadIdx.x]; a2n[threadIdx.x] = tab->aa2num[threadIdx.x];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nWarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < nRecs; w += nWarps) {
+        const MbOrfRec r = recs[w];
+        const unsigned char *seq = nuc + off[r.contig]; const uint32_t L = (uint32_t)(off[r.contig + 1] - off[r.contig]);
+        const int s = (r.flags & 4u) ? 1 : 0;
+        for (uint32_t k = lane; k < r.aaLen; k += 32u) {
+            const uint32_t p = r.strandFrom + 3u * k;
+            const int c0 = orf_char(seq, L, s, p, comp), c1 = orf_char(seq, L, s, p + 1, comp), c2 = orf_char(seq, L, s, p + 2, comp);
+            char res = aaOf[256 * base[c0 & 255] + 16 * base[c1 & 255] + base[c2 & 255]];
+            const bool lower = (c0 >= 'a' && c0 <= 'z') || (c1 >= 'a' && c1 <= 'z') || (c2 >= 'a' && c2 <= 'z');
+            if (lower && res >= 'A' && res <= 'Z') res = (char)(res + 32);
+            aa[r.aaOff + k] = res; codes[r.aaOff + k] = a2n[(unsigned char)res];
+        }
+    }
+}

@@ -34,7 +34,9 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kmers", "lookups", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd",
                                            "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
                [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
-               [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16)]
+               [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16), ("ms_orf", C.c_double), ("ms_orf_host", C.c_double),
+                ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64)]
+ORF_DTYPE = np.dtype([("contig", "<u4"), ("from", "<u4"), ("to", "<u4"), ("flags", "<u4"), ("aa_off", "<u8"), ("aa_len", "<u4"), ("strand_from", "<u4")])
 
 
 class Mb200Error(RuntimeError):
@@ -220,6 +222,25 @@ class Context:
         calls = np.zeros(max(1, 2 * n), dtype=CALL_DTYPE); exons = np.zeros(max(1, n), dtype=EXON_DTYPE); cnt = np.zeros(max(1, nc), np.uint32)
         self._check(self.L.mb200_chain(self.h, _p(cands), _p(cand_off), C.c_uint32(nc), C.c_uint64(total_target_residues), _p(calls), _p(cnt), _p(exons)))
         return calls, cnt[:nc], exons
+
+    # ---- ORF extraction + translation (extractorfs + translatenucs) ----
+    def extract_orfs(self, nuc, off, min_len=15, max_len=32734, start_mode=1, copy=False):
+        """nuc: concatenated ASCII nucleotides (bytes / uint8 array), off: uint64[n+1] -> (records ORF_DTYPE[n_orfs], residues as a bytes-like
+        uint8 array); views of context-owned buffers unless copy=True"""
+        nuc = np.ascontiguousarray(np.frombuffer(nuc, dtype=np.uint8) if isinstance(nuc, (bytes, bytearray)) else nuc, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        n = C.c_uint64(0); na = C.c_uint64(0); precs = C.c_void_p(); paa = C.c_void_p()
+        self._check(self.L.mb200_extract_orfs(self.h, _p(nuc), _p(off), C.c_uint32(len(off) - 1), int(min_len), int(max_len), int(start_mode),
+                                              C.byref(n), C.byref(precs), C.byref(na), C.byref(paa)))
+        self._n_orfs = int(n.value)
+        recs = self._view(precs, n.value, ORF_DTYPE, copy)
+        aa = self._view(paa, na.value, np.dtype(np.uint8), copy)
+        return recs, aa
+
+    def queries_from_orfs(self):
+        """the fragments of the last extract_orfs call become the resident query batch (no host round trip)"""
+        self._check(self.L.mb200_queries_from_orfs(self.h))
+        self._nq = self._n_orfs
 
     # ---- device-resident API (kernel-only timing) ----
     def queries_upload(self, q, qoff):

@@ -127,6 +127,27 @@ def search(ctx, queries, tdb):
     return {k: _aln_lines(alns[int(off[i]):int(off[i + 1])], tdb, len(s)) for i, (k, s) in enumerate(queries)}
 
 
+def extractorfs(ctx, contigs, min_len=15, max_len=32734):
+    """extractorfs + translatenucs with the flags of `metaeuk predictexons` (extractorfs.cpp:19-159, translatenucs.cpp:13-118):
+    contigs [(key, nucleotides)] -> (queries [(orfKey, aa)], orf_headers {orfKey: 'contigKey\\tfrom+len[\\tflags]\\n'}) in the reference's key
+    order.  The fragments stay on the device: ctx.queries_from_orfs() makes them the resident query batch."""
+    seq = "".join(s for _, s in contigs).encode()
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    if contigs:
+        off[1:] = np.cumsum([len(s) for _, s in contigs], dtype=np.uint64)
+    recs, aa = ctx.extract_orfs(seq, off, min_len, max_len, 1)
+    aab = aa.tobytes()
+    queries, headers = [], {}
+    for i, r in enumerate(recs):
+        frm, to = int(r["from"]), int(r["to"])
+        h = "%d\t%d%s%d" % (contigs[int(r["contig"])][0], frm, "+" if frm < to else "-", abs(frm - to))   # Orf::writeOrfHeader (Orf.cpp:440-457)
+        if int(r["flags"]) & 3:
+            h += "\t%d" % (int(r["flags"]) & 3)
+        headers[i] = h + "\n"
+        queries.append((i, aab[int(r["aa_off"]):int(r["aa_off"]) + int(r["aa_len"])].decode()))
+    return queries, headers
+
+
 def parse_orf_header(h):
     """Orf::parseOrfHeader: 'contigKey\\tfrom+len' or 'from-len' (Orf.cpp:351-438)"""
     w = h.split()

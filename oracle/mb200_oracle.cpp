@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
+#include <cctype>
+#include <string>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -641,4 +644,128 @@ int mbo_chain(const mbo_cand *cands, uint32_t n, uint64_t totalTargetResidues, i
     return (int)nCalls;
 }
 
+}  // extern "C"
+
+// =====================================================================================================
+// extractorfs + translatenucs: six-frame ORF fragments of a contig and their translation.
+//   Orf::setSequence / findAll / findForward      reference/lib/mmseqs/src/commons/Orf.cpp:125-157,171-190,230-349
+//   extractorfs driver, header coordinates        reference/lib/mmseqs/src/util/extractorfs.cpp:70-100, Orf.cpp:440-457
+//   TranslateNucl (NCBI state machine)            reference/lib/mmseqs/src/commons/TranslateNucl.h:334-503
+//   translatenucs driver                          reference/lib/mmseqs/src/util/translatenucs.cpp:47-104
+// =====================================================================================================
+static const char *IUPAC_BASES = "-ACMGRSVTWYHKDBN";   // 4-bit code = bit set of {A=1, C=2, G=4, T=8}
+static int base_code(unsigned char c) {                  // TranslateNucl::initConversionTable (TranslateNucl.h:334-362)
+    if (c < 16) return c;                                // ncbi4na values map to themselves
+    const char *u = strchr(IUPAC_BASES, toupper(c));
+    if (c == 'U' || c == 'u') return 8;
+    if (c == 'X' || c == 'x') return 15;
+    if (c == '-' ) return 0;
+    return (u && *u) ? (int)(u - IUPAC_BASES) : 0;       // illegal characters -> gap
+}
+static char iupac_complement(char c) {                   // Orf::iupacReverseComplementTable (Orf.cpp:47-51); '.' = no complement
+    static const char *from = "ATUGCYRSWKMBDHVN", *to = "TAACGRYSWMKVHDBN";
+    const char *p = strchr(from, toupper((unsigned char)c));
+    if (!p || !*p || !isalpha((unsigned char)c)) return '.';
+    return islower((unsigned char)c) ? (char)tolower(to[p - from]) : to[p - from];
+}
+// amino acid of every (possibly ambiguous) codon: consensus over the expansions, with B/Z/J merging (TranslateNucl.h:383-485)
+static void build_codon_table(char aaOf[4096]) {
+    static const char *code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";   // genetic code 1, TCAG order
+    const int exp[4] = {1, 2, 4, 8}; const int tcag[9] = {0, 2, 1, 0, 3, 0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) for (int j = 0; j < 16; j++) for (int k = 0; k < 16; k++) {
+        char aa = 0; bool go = true;
+        for (int p = 0; p < 4 && go; p++) if (exp[p] & i) for (int q = 0; q < 4 && go; q++) if (exp[q] & j) for (int r = 0; r < 4 && go; r++) if (exp[r] & k) {
+            const char ch = code[16 * tcag[exp[p]] + 4 * tcag[exp[q]] + tcag[exp[r]]];
+            if (!aa) aa = ch;
+            else if (aa != ch) {
+                if ((aa == 'B' || aa == 'D' || aa == 'N') && (ch == 'D' || ch == 'N')) aa = 'B';
+                else if ((aa == 'Z' || aa == 'E' || aa == 'Q') && (ch == 'E' || ch == 'Q')) aa = 'Z';
+                else if ((aa == 'J' || aa == 'I' || aa == 'L') && (ch == 'I' || ch == 'L')) aa = 'J';
+                else { aa = 'X'; go = false; }
+            }
+        }
+        aaOf[256 * i + 16 * j + k] = aa ? aa : 'X';
+    }
+}
+struct mbo_orf { uint32_t contig; uint32_t from, to; uint32_t flags; uint64_t aaOff; uint32_t aaLen; uint32_t pad; };   // from/to = header coordinates; flags: 1 incomplete start, 2 incomplete end, 4 minus strand
+
+static void find_forward(const std::string &seq, int strand, size_t minLen, size_t maxLen, size_t maxGaps, int startMode, std::vector<std::array<size_t, 4>> &res) {
+    const size_t L = seq.size();
+    auto at = [&](size_t p) -> int { return p < L ? (unsigned char)seq[p] : 127; };   // CHAR_MAX padding (Orf.cpp:151-154)
+    auto up = [&](int c) { return c == 127 ? 127 : (c & ~0x20); };
+    auto isStop = [&](int a, int b, int c) { return a == 'T' && ((b == 'A' && (c == 'A' || c == 'G')) || (b == 'G' && c == 'A')); };   // table 1
+    auto isStart = [&](int a, int b, int c) { return a == 'A' && b == 'T' && c == 'G'; };
+    auto gapOrN = [&](int c) { return c == 'N' || c == 127 || iupac_complement((char)c) == '.'; };
+    bool inside[3] = {true, true, true}, hasStart[3] = {false, false, false};
+    size_t gaps[3] = {0, 0, 0}, len[3] = {0, 0, 0}, from[3] = {0, 1, 2};
+    for (size_t i = 0; i + 2 < L; i += 3) for (size_t pos = i; pos < i + 3; pos++) {      // Orf.cpp:263-264
+        const int c0 = up(at(pos)), c1 = up(at(pos + 1)), c2 = up(at(pos + 2));
+        const size_t f = pos % 3;
+        const bool incomplete = c0 == 127 || c1 == 127 || c2 == 127;
+        const bool isLast = !incomplete && (at(pos + 3) == 127 || at(pos + 4) == 127 || at(pos + 5) == 127);
+        bool shouldStart;
+        if (startMode == 0) shouldStart = !inside[f] && isStart(c0, c1, c2);
+        else if (startMode == 1) shouldStart = !inside[f];
+        else shouldStart = isStart(c0, c1, c2);
+        if (shouldStart) { inside[f] = true; hasStart[f] = true; from[f] = pos; gaps[f] = 0; len[f] = 0; }
+        const bool stop = isStop(c0, c1, c2);
+        if (inside[f]) { if (!stop) len[f]++; if (gapOrN(c0) || gapOrN(c1) || gapOrN(c2)) gaps[f]++; }
+        if (inside[f] && (stop || isLast)) {
+            inside[f] = false;
+            if (len[f] == 0 && stop) continue;
+            const size_t to = (isLast && !stop) ? pos + 2 : pos - 1;
+            if (gaps[f] > maxGaps || len[f] > maxLen || len[f] < minLen) continue;
+            res.push_back({from[f], to, (size_t)((hasStart[f] ? 0 : 1) | (stop ? 0 : 2)), (size_t)strand});
+        }
+    }
+}
+
+extern "C" {
+// Contigs: concatenated ASCII nucleotides.  Output in the reference's key order: contigs ascending, plus-strand ORFs in emission order,
+// then minus-strand ORFs (DBWriter::createRenumberedDB sorts by (contig key, data offset), DBWriter.cpp:690-738).  aa = ASCII residues.
+// Returns the number of ORFs or -1 if a capacity is exceeded.
+long long mbo_extract_orfs_mt(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
+                              mbo_orf *recs, uint64_t capRecs, char *aa, uint64_t capAa, uint64_t *aaUsed, int threads) {
+    char aaOf[4096]; build_codon_table(aaOf);
+    std::vector<std::vector<mbo_orf>> perRec(nContigs); std::vector<std::string> perAa(nContigs);
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (uint32_t c = 0; c < nContigs; c++) {
+        const size_t L = off[c + 1] - off[c];
+        if (L < 3) continue;                                                              // Orf::setSequence (Orf.cpp:126-128)
+        std::string fwd(nuc + off[c], L), rev(L, 'N');
+        for (size_t i = 0; i < L; i++) if (fwd[i] == 'u') fwd[i] = 't';                  // (the 'U' branch is overwritten, Orf.cpp:141-144)
+        for (size_t i = 0; i < L; i++) { char x = iupac_complement(fwd[L - 1 - i]); rev[i] = (x == '.') ? 'N' : x; }
+        std::vector<std::array<size_t, 4>> res;
+        find_forward(fwd, +1, minLen, maxLen, (size_t)-1, startMode, res);
+        find_forward(rev, -1, minLen, maxLen, (size_t)-1, startMode, res);
+        for (auto &o : res) {
+            const std::string &s = (int)o[3] > 0 ? fwd : rev;
+            size_t nucLen = o[1] - o[0] + 1;
+            if (nucLen < 3) continue;                                                     // translatenucs.cpp:75-78
+            mbo_orf r; r.contig = c; r.flags = (uint32_t)o[2] | ((int)o[3] < 0 ? 4u : 0u); r.pad = 0;
+            r.from = (uint32_t)((int)o[3] > 0 ? o[0] : (L - 1) - o[0]); r.to = (uint32_t)((int)o[3] > 0 ? o[1] : (L - 1) - o[1]);   // extractorfs.cpp:82-87
+            r.aaOff = perAa[c].size(); r.aaLen = (uint32_t)(nucLen / 3);
+            for (size_t k = 0; k + 2 < nucLen; k += 3) {                                  // TranslateNucl::translate (TranslateNucl.h:488-503)
+                const unsigned char a = s[o[0] + k], b = s[o[0] + k + 1], d = s[o[0] + k + 2];
+                char res1 = aaOf[256 * base_code(a) + 16 * base_code(b) + base_code(d)];
+                if (islower(a) || islower(b) || islower(d)) res1 = (char)tolower(res1);
+                perAa[c].push_back(res1);
+            }
+            perRec[c].push_back(r);
+        }
+    }
+    uint64_t n = 0, na = 0;
+    for (uint32_t c = 0; c < nContigs; c++) {
+        if (n + perRec[c].size() > capRecs || na + perAa[c].size() > capAa) return -1;
+        for (auto r : perRec[c]) { r.aaOff += na; recs[n++] = r; }
+        memcpy(aa + na, perAa[c].data(), perAa[c].size()); na += perAa[c].size();
+    }
+    *aaUsed = na;
+    return (long long)n;
+}
+long long mbo_extract_orfs(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
+                           mbo_orf *recs, uint64_t capRecs, char *aa, uint64_t capAa, uint64_t *aaUsed) {
+    return mbo_extract_orfs_mt(nuc, off, nContigs, minLen, maxLen, startMode, recs, capRecs, aa, capAa, aaUsed, 1);
+}
 }  // extern "C"

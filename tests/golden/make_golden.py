@@ -308,6 +308,38 @@ def case_contigs(name, seed, nprot, nc, cl, mask=1, sets=1, thr=8):
           "dp lines", sum(v.count("\n") for v in out["dp"].values()))
 
 
+def case_orfs(name, seed, thr=4):
+    """extractorfs + translatenucs only on contigs with the characters the synthetic genes never contain:
+    N runs, lower case, IUPAC ambiguity codes, U, and contigs too short to hold a codon / an ORF"""
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    contigs = []
+    for i in range(10):
+        s = list("".join(rng.choices("ACGT", k=rng.randint(1500, 4000))))
+        for _ in range(rng.randint(0, 6)):      # N runs
+            a = rng.randrange(len(s)); b = min(len(s), a + rng.randint(1, 40))
+            s[a:b] = "N" * (b - a)
+        for _ in range(rng.randint(0, 6)):      # soft-masked stretches
+            a = rng.randrange(len(s)); b = min(len(s), a + rng.randint(1, 200))
+            s[a:b] = [x.lower() for x in s[a:b]]
+        for _ in range(rng.randint(0, 60)):     # ambiguity codes, U
+            s[rng.randrange(len(s))] = rng.choice("RYKMSWBDHVUnrykmswbdhvu")
+        contigs.append("".join(s))
+    contigs += ["AC", "ACG", "ATGAAATAG", "A" * 44, "ACGTTGCAAGGCTTAACC" * 3, "TAA" * 20, "GCT" * 15 + "TGA", "GCT" * 15, "G" + "GCT" * 16 + "TA"]
+    write_fasta(tmp + "/contigs.fna", contigs, "C")
+    run("%s createdb %s/contigs.fna %s/contigs --dbtype 2 -v 3" % (REF, tmp, tmp), log)
+    run("%s extractorfs %s/contigs %s/nucl_6f %s" % (REF, tmp, tmp, ORF_FLAGS.format(thr=thr)), log)
+    run("%s translatenucs %s/nucl_6f %s/aa_6f --translation-table 1 --add-orf-stop 0 -v 3 --compressed 0 --threads %d" % (REF, tmp, tmp, thr), log)
+    out = {"case": name, "kind": "orfs", "seed": seed, "contigs": seqdb(tmp + "/contigs"), "queries": seqdb(tmp + "/aa_6f"),
+           "orf_headers": {str(k): e[:-1].decode() for k, e in read_db(tmp + "/nucl_6f_h")},
+           "ref_version": run("%s version" % REF, log).strip()}
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+    print(name, "contigs", len(out["contigs"]), "fragments", len(out["queries"]))
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("reference binary not found: " + REF)
@@ -322,3 +354,5 @@ if __name__ == "__main__":
         case_contigs("contigs_small", 1234, nprot=400, nc=24, cl=9000)
     if "contigs_sets" in which:
         case_contigs("contigs_sets", 77, nprot=200, nc=12, cl=9000, sets=3)
+    if "orf_edge" in which:
+        case_orfs("orf_edge", 31)

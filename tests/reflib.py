@@ -183,6 +183,48 @@ class Oracle:
                           tcov, eval_thr, max_sets)
 
 
+class OrfRec(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("frm", C.c_uint32), ("to", C.c_uint32), ("flags", C.c_uint32), ("aaOff", C.c_uint64), ("aaLen", C.c_uint32), ("pad", C.c_uint32)]
+
+
+def fmt_orf_header(contig_key, frm, to, flags):
+    """Orf::writeOrfHeader (Orf.cpp:440-457): 'key\tfrom+len' / 'from-len', third column only when a side is incomplete"""
+    frm, to = int(frm), int(to)
+    h = "%d\t%d%s%d" % (contig_key, frm, "+" if frm < to else "-", abs(frm - to))
+    if flags & 3:
+        h += "\t%d" % (flags & 3)
+    return h + "\n"
+
+
+def oracle_extract_orfs_raw(seq, off, min_len=15, max_len=32734, start_mode=1, threads=1):
+    """seq: bytes of concatenated contigs, off: uint64[n+1] -> (n_orfs, records, residues buffer); the C call only"""
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    L = C.CDLL(ORACLE_SO)
+    L.mbo_extract_orfs_mt.restype = C.c_longlong
+    cap = max(16, len(seq) // 8)
+    recs = (OrfRec * cap)(); aa = C.create_string_buffer(2 * len(seq) + 16); used = C.c_uint64(0)
+    n = L.mbo_extract_orfs_mt(seq, _p(off, C.c_uint64), C.c_uint32(len(off) - 1), min_len, max_len, start_mode, recs, C.c_uint64(cap), aa, C.c_uint64(2 * len(seq) + 16), C.byref(used),
+                              int(threads))
+    assert n >= 0
+    return n, recs, aa
+
+
+def oracle_extract_orfs(contigs, min_len=15, max_len=32734, start_mode=1):
+    """contigs: [(key, nucleotides)] -> ({orfKey: header}, {orfKey: aa}) through the CPU oracle (extractorfs + translatenucs)"""
+    seq = "".join(s for _, s in contigs).encode()
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    if contigs:
+        off[1:] = np.cumsum([len(s) for _, s in contigs])
+    n, recs, aa = oracle_extract_orfs_raw(seq, off, min_len, max_len, start_mode)
+    hdr, seqs = {}, {}
+    for i in range(n):
+        r = recs[i]
+        hdr[i] = fmt_orf_header(contigs[r.contig][0], r.frm, r.to, r.flags)
+        seqs[i] = aa.raw[r.aaOff:r.aaOff + r.aaLen].decode()
+    return hdr, seqs
+
+
 def aln_to_dict(a):
     return dict(seqId=a.seqId, score=a.score, bitScore=a.bitScore, qStart=a.qStart, qEnd=a.qEnd, dbStart=a.dbStart, dbEnd=a.dbEnd,
                 alnLen=a.alnLen, passed=a.passed, seqIdEst=float(np.float32(a.seqIdEst)), evalue=a.evalue)

@@ -165,6 +165,60 @@ def test_edge_cases():
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["contigs_small", "contigs_sets", "orf_edge"])
+def test_extractorfs_golden(name):
+    """six-frame ORF fragments + translation on the device == the reference's nucl_6f_h / aa_6f DBs, key for key"""
+    c = reflib.load_case(name)
+    from metaeuk_b200.lib import Context
+    ctx = Context(0)
+    queries, headers = M.extractorfs(ctx, [tuple(x) for x in c["contigs"]])
+    assert {k: v for k, v in queries} == {int(k): s for k, s in c["queries"]}
+    assert headers == {int(k): v for k, v in c["orf_headers"].items()}
+    st = ctx.stats()
+    assert st["orf_fragments"] == len(c["queries"]) and st["orf_residues"] == sum(len(s) for _, s in c["queries"])
+    ctx.close()
+
+
+def test_extractorfs_matches_oracle_on_larger_contigs():
+    """contigs that span many tiles of the scan kernel (tile = 3072 nt), incl. lengths around the tile size and frames cut by the contig end"""
+    rng = random.Random(17)
+    contigs = []
+    for i, L in enumerate([3071, 3072, 3073, 3074, 3075, 6143, 6144, 6149, 50000, 123457, 40, 44, 47, 48, 2]):
+        s = "".join(rng.choices("ACGT", k=L))
+        if i % 3 == 0:
+            s = s[: L // 2] + "N" * min(30, L // 4) + s[L // 2 + min(30, L // 4):].lower()
+        contigs.append((100 + i, s))
+    from metaeuk_b200.lib import Context
+    ctx = Context(0)
+    queries, headers = M.extractorfs(ctx, contigs)
+    hdr, seqs = reflib.oracle_extract_orfs(contigs)
+    assert len(queries) == len(seqs) > 1000
+    assert headers == hdr
+    assert {k: v for k, v in queries} == seqs
+    with pytest.raises(Exception):
+        ctx.extract_orfs(b"ACGT" * 10, np.array([0, 40], np.uint64), 15, 32734, 0)   # other start modes are not implemented: loud
+    ctx.close()
+
+
+def test_contigs_to_exon_calls_without_host_round_trip():
+    """contigs -> ORF fragments (device) -> resident prefilter + alignment -> exon chaining == the reference's dp_predictions"""
+    c = reflib.load_case("contigs_sets")
+    ctx, tdb = ctx_for(c, max_exon_sets=c["max_exon_sets"])
+    contigs = [tuple(x) for x in c["contigs"]]
+    queries, headers = M.extractorfs(ctx, contigs)
+    ctx.queries_from_orfs()                      # fragments never leave the GPU
+    ctx.prefilter_resident()
+    hits, cnt = ctx.results_download()
+    keys = tdb.keys
+    for (k, _), h, n in zip(queries, hits, cnt):
+        got = reflib.fmt_pref([(int(x["seq_id"]), int(x["score"]), int(x["diag"])) for x in h[:n]], keys)
+        assert got == c["pref"].get(str(k), ""), k
+    contig_lens = {k: len(s) for k, s in contigs}
+    aln, byc, dp = M.predictexons(ctx, queries, headers, contig_lens, tdb)
+    assert strkeys(dp) == c["dp"]
+    ctx.close()
+
+
 def test_long_queries_take_the_32bit_alignment_path():
     """queries longer than 1024 residues skip the packed 16-bit kernel; longer than 512 windows spill the window arrays"""
     prots, _ = synth(11, 300, 1)
@@ -258,3 +312,8 @@ def test_cli_modules_on_database_files(tmp_path):
     subprocess.check_call([exe, "gpupredictexons", d + "/contigs", d + "/aa_6f", d + "/nucl_6f", d + "/proteins", d + "/dp2", "--max-exon-sets",
                            str(c["max_exon_sets"])] + common)
     assert read_db(d + "/dp2") == c["dp"]
+    # the step before: contigs -> ORF header DB + translated fragment DB, then the whole chain from those
+    write_db(d + "/contigs_nt", [(k, s + "\n") for k, s in c["contigs"]], 1)
+    subprocess.check_call([exe, "gpuextractorfs", d + "/contigs_nt", d + "/orf_h", d + "/orf_aa"])
+    assert read_db(d + "/orf_h") == {str(k): v for k, v in c["orf_headers"].items()}
+    assert read_db(d + "/orf_aa") == {str(k): s + "\n" for k, s in c["queries"]}
