@@ -40,6 +40,8 @@ WORKLOADS = {
     "c3": dict(n_prot=500_000, n_frag=1_000_000, align=True, desc="C3: 1M fragments x 500K proteins, prefilter + gapped SW align"),
     "c3s": dict(n_prot=500_000, n_frag=100_000, align=True, desc="C3/10: 100K fragments x 500K proteins, prefilter + gapped SW align (profiling size)"),
     "tiny": dict(n_prot=2_000, n_frag=4_000, align=True, desc="tiny: 4K fragments x 2K proteins (plumbing check)"),
+    "reduce": dict(n_contigs=200_000, reduce=True, n_prot=0, n_frag=0, align=False,
+                   desc="reduceredundancy stage (SURVEY 8f-2): 200 K contigs x ~24 calls (1-4 exons, exon keys shared inside a contig)"),
     "orf": dict(n_contigs=4_000, contig_len=50_000, orf=True, n_prot=0, n_frag=0, align=False,
                 desc="ORF stage (SURVEY 8f-1): 4000 contigs x 50 kb random DNA -> six-frame fragments >= 15 codons, translated"),
 }
@@ -81,6 +83,87 @@ def gen_contigs(n, length, seed=1234):
     nuc = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * length, dtype=np.uint8)]
     off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
     return np.ascontiguousarray(nuc), off
+
+
+def gen_calls(n_contigs, seed=99):
+    """synthetic calledExons content: per contig 4..44 calls on both strands; exon keys drawn from a small per-contig pool so calls share exons"""
+    from metaeuk_b200.lib import PRED_DTYPE
+    rng = np.random.default_rng(seed)
+    ncall = rng.integers(4, 45, n_contigs)
+    off = np.zeros(n_contigs + 1, np.uint64); off[1:] = np.cumsum(ncall)
+    n = int(off[-1])
+    P = np.zeros(n, PRED_DTYPE)
+    P["target_key"] = rng.integers(0, 500_000, n); P["strand"] = rng.choice(np.array([1, -1], np.int32), n)
+    P["total_bit_score"] = rng.integers(40, 900, n); P["n_exons"] = rng.integers(1, 5, n)
+    low = rng.integers(0, 48_000, n); P["low_coord"] = low; P["high_coord"] = low + rng.integers(200, 3000, n)
+    P["evalue"] = np.float64(10.0) ** (-rng.integers(3, 120, n).astype(np.float64)) * rng.integers(1000, 9999, n) / 1000.0
+    eb = np.zeros(n + 1, np.uint64); eb[1:] = np.cumsum(P["n_exons"]); P["exon_begin"] = eb[:-1]
+    contig_of = np.repeat(np.arange(n_contigs), ncall)
+    pool = np.maximum(2, ncall // 2)
+    keys = (np.repeat(contig_of, P["n_exons"]).astype(np.uint64) * 64 + rng.integers(0, 1 << 30, int(eb[-1])) % np.repeat(pool[contig_of], P["n_exons"])).astype(np.uint32)
+    return P, off, keys
+
+
+def bench_reduce(args, wl, base, rank, world, local, threads):
+    """the step after the path.  value = calls/s of k_reduce (CUDA events), e2e = the C-ABI call with host buffers."""
+    import torch
+    import torch.distributed as dist
+    from metaeuk_b200.lib import Context
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+    P, off, keys = gen_calls(wl["n_contigs"], seed=99 + rank)
+    n = len(P)
+    for _ in range(max(3, args.warmup)):
+        ctx.reduce_redundancy(P, off, keys)
+    l0 = ctx.stats()["launches"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    kms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, mo, ro, cnt = ctx.reduce_redundancy(P, off, keys)
+        kms.append(ctx.stats()["ms_reduce"])
+    dt = time.perf_counter() - t0
+    vals = [dt, float(np.sum(kms)) * 1e-3]
+    if world > 1:
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in t.tolist()]
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    abytes = int(P.nbytes + keys.nbytes + out.nbytes + mo.nbytes + ro.nbytes)   # every call read once, every result written once
+    kernel_ms = float(np.mean(kms))
+    base.update({"metric": "reduceredundancy calls/sec", "unit": "calls/s", "value": world * n * args.steps / vals[1], "ms_per_step": 1000 * vals[1] / args.steps,
+                 "gpu_launches": int(ctx.stats()["launches"] - l0), "clocks": None,
+                 "e2e": {"value": world * n * args.steps / vals[0], "unit": "calls/s", "h2d_bytes_per_step": int(P.nbytes + off.nbytes + keys.nbytes),
+                         "d2h_bytes_per_step": int(out.nbytes + mo.nbytes + ro.nbytes + cnt.nbytes), "ms_per_step": 1000 * vals[0] / args.steps},
+                 "roofline": {"kernel": "k_reduce", "bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak,
+                              "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms, "traffic": None},
+                 "work": {"contigs": wl["n_contigs"], "calls": n, "representatives": int(cnt.sum())}})
+    base["config"].update({"fragments_per_gpu": 0, "calls_per_gpu": n, "stages": "reduceredundancy"})
+    if args.gpus == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import reflib
+        L = C.CDLL(reflib.ORACLE_SO)
+        o2 = np.zeros(n, out.dtype); m2 = np.zeros(n, np.uint32); r2 = np.zeros(n, np.uint32); c2 = np.zeros(wl["n_contigs"], np.uint32)
+        t0 = time.perf_counter()
+        L.mbo_reduce_redundancy_batch(C.c_void_p(P.ctypes.data), C.c_void_p(off.ctypes.data), C.c_uint32(wl["n_contigs"]), C.c_void_p(keys.ctypes.data), C.c_void_p(o2.ctypes.data),
+                                      C.c_void_p(m2.ctypes.data), C.c_void_p(r2.ctypes.data), C.c_void_p(c2.ctypes.data), threads)
+        tcpu = time.perf_counter() - t0
+        same = bool((o2 == out).all() and (m2 == mo).all() and (c2 == cnt).all())
+        base["cpu_baseline"] = {"value": n / tcpu, "unit": "calls/s", "cores": threads, "kind": "port", "sample": "the whole batch, all %d host threads (OpenMP over contigs)" % threads,
+                                "identical_to_gpu_result": same}
+    emit(base)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def bench_orf(args, wl, base, rank, world, local, threads):
@@ -318,6 +401,8 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     if wl.get("orf"):
         return bench_orf(args, wl, base, rank, world, local, threads)
+    if wl.get("reduce"):
+        return bench_reduce(args, wl, base, rank, world, local, threads)
     import torch
     import torch.distributed as dist
     from metaeuk_b200.lib import Context

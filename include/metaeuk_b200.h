@@ -72,6 +72,12 @@ typedef struct mb200_exon { uint32_t cand_idx; int32_t contig_start, contig_end,
 typedef struct mb200_call {
     uint32_t target_key; int32_t strand; int32_t total_bit_score; int32_t n_exons; uint32_t exon_begin; int32_t low_coord, high_coord, pad; double evalue;
 } mb200_call;
+typedef struct mb200_pred {   /* one call of collectoptimalset = Prediction::setByDPRes (PredictionParser.h:253-272) */
+    uint32_t target_key; int32_t strand; uint32_t total_bit_score, n_exons, low_coord, high_coord;
+    uint32_t exon_begin, pad;  /* exon keys of the call: exon_keys[exon_begin .. exon_begin + n_exons) */
+    double evalue;             /* atof of the printed %.3E value, as the reference parses it */
+} mb200_pred;
+typedef struct mb200_pred_out { uint32_t cluster_id, cluster_low_coord, no_overlap_cluster_id, is_rep; } mb200_pred_out;
 typedef struct mb200_orf {   /* one six-frame fragment = one entry of the reference's nucl_6f_h / aa_6f DBs (key = index in the array) */
     uint32_t contig;           /* index of the contig in the input batch */
     uint32_t from, to;         /* header coordinates on the contig (Orf::writeOrfHeader): from > to on the minus strand */
@@ -88,6 +94,7 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     uint64_t pref_phase_cycles[16];   /* k_prefilter: CTA cycles summed over queries, per phase; [15] = between queries */
     double ms_orf, ms_orf_host;       /* mb200_extract_orfs: kernels with the contigs resident (CUDA events) / whole call incl. H2D and D2H (wall clock) */
     uint64_t orf_nucleotides, orf_fragments, orf_residues;
+    double ms_reduce;                 /* k_reduce (mb200_reduce_redundancy) */
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);
@@ -141,6 +148,14 @@ int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_of
 int mb200_extract_orfs(mb200_ctx *ctx, const char *nuc, const uint64_t *off, uint32_t n_contigs, int min_len, int max_len, int start_mode,
                        uint64_t *n_orfs, const mb200_orf **orfs, uint64_t *n_aa, const char **aa);
 int mb200_queries_from_orfs(mb200_ctx *ctx);
+
+/* reduceredundancy (src/exonpredictor/reduceredundancy.cpp:24-147,273-296) for a batch of contigs: calls of contig c =
+ * preds[pred_off[c] .. pred_off[c+1]) in the order of the calledExons entry.  Per call: cluster representative (target key, low coordinate),
+ * the winner of the same-strand overlap exclusion, and whether the call is a representative.  member_order (per contig, same ranges) = the
+ * order of the call -> representative DB; rep_order[pred_off[c] .. + rep_count[c]) = the representatives in output order (a representative is
+ * printed when overlaps are allowed or its no_overlap_cluster_id equals its own target key).  Indices are relative to the contig's range. */
+int mb200_reduce_redundancy(mb200_ctx *ctx, const mb200_pred *preds, const uint64_t *pred_off, uint32_t n_contigs, const uint32_t *exon_keys, uint64_t n_exon_keys,
+                            mb200_pred_out *out, uint32_t *member_order, uint32_t *rep_order, uint32_t *rep_count);
 
 /* device-resident variant used for kernel-only timing: upload once, run many times, download once */
 int mb200_queries_upload(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q);

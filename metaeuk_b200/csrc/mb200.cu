@@ -22,6 +22,7 @@
 
 #include "../../include/metaeuk_b200.h"
 #include "chain_core.cuh"
+#include "reduce_core.cuh"
 #include "host_tables.h"
 #include "prefilter_core.cuh"
 
@@ -94,6 +95,15 @@ __global__ void __launch_bounds__(128) k_chain(const MbCand *__restrict__ cands,
     uint32_t nEx = 0;
     callCount[c] = mb_chain_contig(cands + b, n, P, pe + b, ordPlus + b, ordMinus + b, rows + b, calls + 2 * b, exons + b, &nEx);
     exonCount[c] = nEx;
+}
+
+// ---- reduceredundancy: one contig per thread ---------------------------------------------------------
+__global__ void __launch_bounds__(128) k_reduce(const MbPred *__restrict__ preds, const uint64_t *__restrict__ predOff, uint32_t nContigs, const uint32_t *__restrict__ exonKeys,
+                                                MbPredOut *out, uint32_t *memberOrder, uint32_t *repOrder, uint32_t *repCount, uint32_t *flag, uint32_t *tmp) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nContigs) return;
+    const uint64_t b = predOff[c]; const uint32_t n = (uint32_t)(predOff[c + 1] - b);
+    repCount[c] = mb_reduce_contig(preds + b, n, exonKeys, out + b, memberOrder + b, repOrder + b, flag + b, tmp + b);
 }
 
 // =====================================================================================================
@@ -547,6 +557,38 @@ int mb200_queries_from_orfs(mb200_ctx *c) {
     for (uint64_t i = 0; i < c->nOrfs; i++) qoff[i] = c->pOrfRecs.p[i].aaOff;
     qoff[c->nOrfs] = c->nOrfAa;
     return queries_install(c, nullptr, c->dOrfCodes.p, qoff.data(), (uint32_t)c->nOrfs);
+}
+
+
+// ---- reduceredundancy (the step after the path) ---------------------------------------------------------
+int mb200_reduce_redundancy(mb200_ctx *c, const mb200_pred *preds, const uint64_t *predOff, uint32_t nContigs, const uint32_t *exonKeys, uint64_t nExonKeys,
+                            mb200_pred_out *out, uint32_t *memberOrder, uint32_t *repOrder, uint32_t *repCount) {
+    if (!c || !preds || !predOff || !exonKeys || !out || !memberOrder || !repOrder || !repCount) return fail(MB200_E_ARG, "null argument");
+    static_assert(sizeof(MbPred) == sizeof(mb200_pred) && sizeof(MbPredOut) == sizeof(mb200_pred_out), "ABI structs");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = predOff[nContigs];
+    if (nContigs == 0 || n == 0) { for (uint32_t i = 0; i < nContigs; i++) repCount[i] = 0; return 0; }
+    for (uint64_t i = 0; i < n; i++) if ((uint64_t)preds[i].exon_begin + preds[i].n_exons > nExonKeys) return fail(MB200_E_ARG, "call %llu: exon range outside exon_keys", (unsigned long long)i);
+    for (uint32_t i = 0; i < nContigs; i++) if (predOff[i + 1] - predOff[i] >= (1ull << 31)) return fail(MB200_E_LIMIT, "too many calls on contig %u", i);
+    DevBuf<MbPred> dP; DevBuf<uint64_t> dOff; DevBuf<uint32_t> dKeys, dMem, dRep, dCnt, dFlag, dTmp; DevBuf<MbPredOut> dOut;
+    int rc = 0;
+    auto done = [&](int r) { dP.release(); dOff.release(); dKeys.release(); dMem.release(); dRep.release(); dCnt.release(); dFlag.release(); dTmp.release(); dOut.release(); return r; };
+    if ((rc = dP.alloc(n)) || (rc = dOff.alloc(nContigs + 1)) || (rc = dKeys.alloc(nExonKeys + 1)) || (rc = dMem.alloc(n)) || (rc = dRep.alloc(n)) || (rc = dCnt.alloc(nContigs)) ||
+        (rc = dFlag.alloc(n)) || (rc = dTmp.alloc(n)) || (rc = dOut.alloc(n))) return done(rc);
+    if ((rc = upload(dP.p, preds, n * sizeof(MbPred), c->stream)) || (rc = upload(dOff.p, predOff, (size_t)(nContigs + 1) * 8, c->stream)) ||
+        (rc = upload(dKeys.p, exonKeys, (size_t)nExonKeys * 4, c->stream))) return done(rc);
+    cudaEventRecord(c->ev0, c->stream);
+    k_reduce<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(dP.p, dOff.p, nContigs, dKeys.p, dOut.p, dMem.p, dRep.p, dCnt.p, dFlag.p, dTmp.p);
+    cudaEventRecord(c->ev1, c->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut.p, n * sizeof(MbPredOut), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(memberOrder, dMem.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(repOrder, dRep.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(repCount, dCnt.p, (size_t)nContigs * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(MB200_E_CUDA, "k_reduce: %s", cudaGetErrorString(e)));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->st.ms_reduce = ms; c->st.launches++;
+    return done(0);
 }
 
 int mb200_prefilter_resident(mb200_ctx *c) {

@@ -6,6 +6,7 @@
 //   mb200 gpusearch            <queryDB> <targetDB> <alnDB>             == search (blastp.sh:70,85 without the pref DB round trip)
 //   mb200 gpuresultspercontig  <contigsDB> <orfDB> <alnDB> <byContigDB> == resultspercontig   (src/exonpredictor/resultspercontig.cpp:34)
 //   mb200 gpucollectoptimalset <byContigDB> <targetDB> <predDB>         == collectoptimalset  (src/exonpredictor/collectoptimalset.cpp:224)
+//   mb200 gpureduceredundancy  <calledExonsDB> <predsDB> <predToCallDB> == reduceredundancy   (src/exonpredictor/reduceredundancy.cpp:162)
 //   mb200 gpupredictexons      <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>
 //                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
 // DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
@@ -105,7 +106,7 @@ static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdTo
 static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
 
 struct Opt {
-    mb200_params p; std::string maskedDb; int device = 0;
+    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0;
 };
 static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
     Opt o; mb200_params_default(&o.p);
@@ -128,6 +129,7 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--set-gap-open") o.p.set_gap_open = atoi(val().c_str());
         else if (a == "--set-gap-extend") o.p.set_gap_extend = atoi(val().c_str());
         else if (a == "--device") o.device = atoi(val().c_str());
+        else if (a == "--overlap") o.overlap = atoi(val().c_str());
         else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
         else pos.push_back(a);
     }
@@ -243,7 +245,7 @@ static std::map<uint32_t, std::string> searchAll(Session &s, const Db &qdb, cons
 static void writeDb(const std::string &name, int dbtype, const std::map<uint32_t, std::string> &m) { DbOut o(name, dbtype); for (auto &kv : m) o.write(kv.first, kv.second); }
 
 int main(int argc, char **argv) {
-    if (argc < 2) DIE("usage: mb200 <gpuextractorfs|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
+    if (argc < 2) DIE("usage: mb200 <gpuextractorfs|gpureduceredundancy|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
     initCodes();
     std::string cmd = argv[1]; std::vector<std::string> pos; Opt o = parseOpts(argc, argv, 2, pos);
     if (cmd == "gpuprefilter") {
@@ -289,6 +291,55 @@ int main(int argc, char **argv) {
         auto aln = searchAll(s, qdb, q);
         auto byc = byContig(contigs, hdr, aln);
         writeDb(pos[4], 12, chainAll(s.ctx, byc, s.t.res.size()));
+    } else if (cmd == "gpureduceredundancy") {
+        // reduceredundancy: calledExonsDB -> representative calls (DP format) + call -> representative DB
+        if (pos.size() != 3) DIE("gpureduceredundancy <i:calledExonsDB> <o:predictionsExonsDB> <o:predToCall> [--overlap 0|1]");
+        Db dp = openDb(pos[0]);
+        std::vector<mb200_pred> preds; std::vector<uint32_t> exonKeys; std::vector<std::vector<std::vector<std::string>>> exonCols; std::vector<uint64_t> off(1, 0);
+        for (size_t id = 0; id < dp.keys.size(); id++) {
+            long prevIdx[2] = {-1, -1};
+            for (auto &l : lines(dp.entry(id))) {
+                if (l.empty()) continue;
+                auto w = splitTab(l); if (w.size() != 19) DIE("There should be 19 columns in the input file");
+                const uint32_t t = (uint32_t)atoi(w[0].c_str()), low = (uint32_t)atoi(w[5].c_str()); const int s = atoi(w[1].c_str()); const int si = s == 1 ? 0 : 1;
+                long j = prevIdx[si];
+                if (j < 0 || preds[j].target_key != t || preds[j].low_coord != low) {   // reduceredundancy.cpp:237-262
+                    mb200_pred p; memset(&p, 0, sizeof(p)); p.target_key = t; p.strand = s; p.total_bit_score = (uint32_t)atoi(w[2].c_str()); p.evalue = atof(w[3].c_str());
+                    p.low_coord = low; p.high_coord = (uint32_t)atoi(w[6].c_str()); p.exon_begin = (uint32_t)exonKeys.size();
+                    preds.push_back(p); exonCols.emplace_back(); prevIdx[si] = j = (long)preds.size() - 1;
+                }
+                preds[j].n_exons++; exonKeys.push_back((uint32_t)atoi(w[7].c_str())); exonCols[j].push_back(std::vector<std::string>(w.begin() + 7, w.end()));
+            }
+            off.push_back(preds.size());
+        }
+        mb200_ctx *ctx; MB(mb200_ctx_create(o.device, &ctx));
+        std::vector<mb200_pred_out> out(preds.size() + 1); std::vector<uint32_t> mo(preds.size() + 1), ro(preds.size() + 1), cnt(dp.keys.size() + 1), keys1(exonKeys); keys1.push_back(0);
+        mb200_pred dummy; memset(&dummy, 0, sizeof(dummy));
+        MB(mb200_reduce_redundancy(ctx, preds.empty() ? &dummy : preds.data(), off.data(), (uint32_t)dp.keys.size(), keys1.data(), exonKeys.size(), out.data(), mo.data(), ro.data(), cnt.data()));
+        DbOut grouped(pos[1], 12), clusters(pos[2], 12);
+        char buf[256];
+        for (size_t id = 0; id < dp.keys.size(); id++) {
+            const uint64_t b = off[id], e = off[id + 1]; std::string g, cl;
+            for (uint32_t r = 0; r < cnt[id]; r++) {
+                const uint64_t i = b + ro[b + r]; const mb200_pred &p = preds[i];
+                if (!o.overlap && out[i].no_overlap_cluster_id != p.target_key) continue;
+                for (auto &ex : exonCols[i]) {       // Prediction::predictionToBuffer + PotentialExon::exonToBuffer (PredictionParser.h:368-396,99-150)
+                    snprintf(buf, sizeof(buf), "%u\t%d\t%u\t%.3E\t%u\t%u\t%u\t", p.target_key, p.strand, p.total_bit_score, p.evalue, p.n_exons, p.low_coord, p.high_coord); g += buf;
+                    const float sid = (float)strtod(ex[2].c_str(), NULL);
+                    std::string sidTxt;
+                    if (sid == 1.0f) sidTxt = "1.000"; else { sidTxt = "0."; if (sid < 0.10f) sidTxt += "0"; if (sid < 0.01f) sidTxt += "0"; sidTxt += std::to_string((int)(sid * 1000)); }
+                    snprintf(buf, sizeof(buf), "%.3E", strtod(ex[3].c_str(), NULL));
+                    g += ex[0] + "\t" + ex[1] + "\t" + sidTxt + "\t" + buf;
+                    for (size_t k = 4; k < ex.size(); k++) g += "\t" + ex[k];
+                    g += "\n";
+                }
+            }
+            for (uint64_t m = b; m < e; m++) {
+                const uint64_t i = b + mo[m]; snprintf(buf, sizeof(buf), "%u\t%d\t%u\t%u\t%d\t%u\n", out[i].cluster_id, preds[i].strand, out[i].cluster_low_coord, preds[i].target_key, preds[i].strand, preds[i].low_coord); cl += buf;
+            }
+            grouped.write(dp.keys[id], g); clusters.write(dp.keys[id], cl);
+        }
+        mb200_ctx_destroy(ctx);
     } else if (cmd == "gpuextractorfs") {
         // extractorfs + translatenucs in one step (data/predictexons.sh: contigs -> nucl_6f(_h) -> aa_6f): writes the ORF header DB and the
         // translated fragment DB with the reference's renumbered keys

@@ -35,7 +35,10 @@ class Stats(C.Structure):
                                            "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
                [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
                [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16), ("ms_orf", C.c_double), ("ms_orf_host", C.c_double),
-                ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64)]
+                ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64), ("ms_reduce", C.c_double)]
+PRED_DTYPE = np.dtype([("target_key", "<u4"), ("strand", "<i4"), ("total_bit_score", "<u4"), ("n_exons", "<u4"), ("low_coord", "<u4"), ("high_coord", "<u4"),
+                       ("exon_begin", "<u4"), ("pad", "<u4"), ("evalue", "<f8")])
+PRED_OUT_DTYPE = np.dtype([("cluster_id", "<u4"), ("cluster_low_coord", "<u4"), ("no_overlap_cluster_id", "<u4"), ("is_rep", "<u4")])
 ORF_DTYPE = np.dtype([("contig", "<u4"), ("from", "<u4"), ("to", "<u4"), ("flags", "<u4"), ("aa_off", "<u8"), ("aa_len", "<u4"), ("strand_from", "<u4")])
 
 
@@ -50,7 +53,7 @@ def _gxx():
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
     srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
         [os.path.join(ROOT, "include", "metaeuk_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -222,6 +225,16 @@ class Context:
         calls = np.zeros(max(1, 2 * n), dtype=CALL_DTYPE); exons = np.zeros(max(1, n), dtype=EXON_DTYPE); cnt = np.zeros(max(1, nc), np.uint32)
         self._check(self.L.mb200_chain(self.h, _p(cands), _p(cand_off), C.c_uint32(nc), C.c_uint64(total_target_residues), _p(calls), _p(cnt), _p(exons)))
         return calls, cnt[:nc], exons
+
+    # ---- reduceredundancy ----
+    def reduce_redundancy(self, preds, pred_off, exon_keys):
+        preds = np.ascontiguousarray(preds, PRED_DTYPE); pred_off = np.ascontiguousarray(pred_off, np.uint64); exon_keys = np.ascontiguousarray(exon_keys, np.uint32)
+        nc = len(pred_off) - 1; n = int(pred_off[-1])
+        out = np.zeros(max(1, n), PRED_OUT_DTYPE); mo = np.zeros(max(1, n), np.uint32); ro = np.zeros(max(1, n), np.uint32); cnt = np.zeros(max(1, nc), np.uint32)
+        keys = exon_keys if len(exon_keys) else np.zeros(1, np.uint32)
+        self._check(self.L.mb200_reduce_redundancy(self.h, _p(preds if n else np.zeros(1, PRED_DTYPE)), _p(pred_off), C.c_uint32(nc), _p(keys), C.c_uint64(len(exon_keys)),
+                                                   _p(out), _p(mo), _p(ro), _p(cnt)))
+        return out[:n], mo[:n], ro[:n], cnt[:nc]
 
     # ---- ORF extraction + translation (extractorfs + translatenucs) ----
     def extract_orfs(self, nuc, off, min_len=15, max_len=32734, start_mode=1, copy=False):

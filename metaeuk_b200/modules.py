@@ -148,6 +148,61 @@ def extractorfs(ctx, contigs, min_len=15, max_len=32734):
     return queries, headers
 
 
+def _reprint_exon(cols):
+    """PotentialExon::setByDPRes -> exonToBuffer (PredictionParser.h:66-150): the identity is parsed to double, narrowed to float and
+    re-truncated to three digits; the E-value goes through %.3E again; every other column is an integer"""
+    f = np.float32(float(cols[2]))
+    if f == np.float32(1.0):
+        sid = "1.000"
+    else:
+        sid = "0." + ("0" if f < np.float32(0.10) else "") + ("0" if f < np.float32(0.01) else "") + str(int(np.float32(f * np.float32(1000))))
+    return "\t".join([cols[0], cols[1], sid, "%.3E" % float(cols[3])] + list(cols[4:]))
+
+
+def reduceredundancy(ctx, dp_by_contig, allow_overlaps=False):
+    """reduceredundancy (src/exonpredictor/reduceredundancy.cpp:162-317): {contigKey: calledExons entry} ->
+    ({contigKey: representative calls in DP format}, {contigKey: 'repT repS repLow memberT memberS memberLow' lines})"""
+    from .lib import PRED_DTYPE
+    keys = list(dp_by_contig.keys())
+    preds, exon_keys, exon_lines, off = [], [], [], [0]
+    for k in keys:
+        prev = {1: None, -1: None}
+        for line in dp_by_contig[k].split("\n"):
+            if not line:
+                continue
+            w = line.split("\t")
+            if len(w) != 19:
+                raise ValueError("There should be 19 columns in the input file")
+            t, s, low = int(w[0]), int(w[1]), int(w[5])
+            j = prev[s]
+            if j is None or preds[j][0] != t or preds[j][4] != low:      # a new call per strand when target or low coordinate changes (:237-262)
+                preds.append([t, s, int(w[2]), 0, low, int(w[6]), len(exon_keys), 0, float(w[3])])
+                exon_lines.append([])
+                prev[s] = j = len(preds) - 1
+            preds[j][3] += 1
+            exon_keys.append(int(w[7])); exon_lines[j].append(w[7:])
+        off.append(len(preds))
+    P = np.zeros(len(preds), PRED_DTYPE)
+    for i, p in enumerate(preds):
+        P[i] = tuple(p)
+    out, mo, ro, cnt = ctx.reduce_redundancy(P, np.array(off, np.uint64), np.array(exon_keys, np.uint32))
+    grouped, clusters = {}, {}
+    for c, k in enumerate(keys):
+        b, e = off[c], off[c + 1]
+        g = ""
+        for r in ro[b:b + int(cnt[c])]:
+            i = b + int(r); p = preds[i]
+            if not allow_overlaps and int(out[i]["no_overlap_cluster_id"]) != p[0]:
+                continue
+            head = "%d\t%d\t%d\t%s\t%d\t%d\t%d" % (p[0], p[1], p[2], "%.3E" % p[8], p[3], p[4], p[5])      # Prediction::predictionToBuffer (PredictionParser.h:368-396)
+            for ex in exon_lines[i]:
+                g += head + "\t" + _reprint_exon(ex) + "\n"
+        grouped[k] = g
+        clusters[k] = "".join("%d\t%d\t%d\t%d\t%d\t%d\n" % (int(out[b + int(m)]["cluster_id"]), preds[b + int(m)][1], int(out[b + int(m)]["cluster_low_coord"]),
+                                                              preds[b + int(m)][0], preds[b + int(m)][1], preds[b + int(m)][4]) for m in mo[b:e])
+    return grouped, clusters
+
+
 def parse_orf_header(h):
     """Orf::parseOrfHeader: 'contigKey\\tfrom+len' or 'from-len' (Orf.cpp:351-438)"""
     w = h.split()

@@ -769,3 +769,91 @@ long long mbo_extract_orfs(const char *nuc, const uint64_t *off, uint32_t nConti
     return mbo_extract_orfs_mt(nuc, off, nContigs, minLen, maxLen, startMode, recs, capRecs, aa, capAa, aaUsed, 1);
 }
 }  // extern "C"
+
+// =====================================================================================================
+// reduceredundancy: greedy clustering of the calls of one contig + same-strand overlap exclusion
+//   clusterPredictions / excludeSameStrandOverlaps   reference/src/exonpredictor/reduceredundancy.cpp:24-109,111-147
+//   comparators                                      reference/src/commons/PredictionParser.h:318-366
+//   driver (per contig, plus then minus, final order) reference/src/exonpredictor/reduceredundancy.cpp:273-296
+// =====================================================================================================
+struct mbo_pred { uint32_t targetKey; int32_t strand; uint32_t totalBitscore, nExons, lowCoord, highCoord, exonBegin, pad; double evalue; };
+struct mbo_pred_out { uint32_t clusterId, clusterLowCoord, noOverlapClusterId, isRep; };
+
+static void rr_strand(const mbo_pred *P, const uint32_t *exonKeys, std::vector<uint32_t> &idx, mbo_pred_out *out, std::vector<uint32_t> &reps) {
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {                // comparePredictionsByContigStart
+        if (P[a].lowCoord != P[b].lowCoord) return P[a].lowCoord < P[b].lowCoord;
+        if (P[a].highCoord != P[b].highCoord) return P[a].highCoord > P[b].highCoord;
+        if (P[a].totalBitscore != P[b].totalBitscore) return P[a].totalBitscore > P[b].totalBitscore;
+        return P[a].targetKey < P[b].targetKey; });
+    std::vector<char> clustered(idx.size(), 0);
+    for (size_t i = 0; i < idx.size(); i++) {
+        if (clustered[i]) continue;
+        const mbo_pred &pi = P[idx[i]];
+        uint32_t finalId = pi.targetKey, finalLow = pi.lowCoord, maxScore = pi.totalBitscore;
+        clustered[i] = 1;
+        std::vector<size_t> members(1, i);
+        for (size_t j = i + 1; j < idx.size(); j++) {
+            const mbo_pred &pj = P[idx[j]];
+            if (pj.lowCoord >= pi.highCoord) break;                                       // reduceredundancy.cpp:52-55
+            bool share = false;
+            for (uint32_t a = 0; a < pi.nExons && !share; a++) for (uint32_t b = 0; b < pj.nExons; b++)
+                if (exonKeys[pi.exonBegin + a] == exonKeys[pj.exonBegin + b]) { share = true; break; }
+            if (share && !clustered[j]) {
+                clustered[j] = 1;
+                if (pj.totalBitscore > maxScore) { maxScore = pj.totalBitscore; finalId = pj.targetKey; finalLow = pj.lowCoord; }
+                members.push_back(j);
+            }
+        }
+        for (size_t m : members) {
+            mbo_pred_out &o = out[idx[m]]; o.clusterId = finalId; o.clusterLowCoord = finalLow;
+            if (P[idx[m]].targetKey == finalId && P[idx[m]].lowCoord == finalLow) { o.isRep = 1; reps.push_back(idx[m]); }   // :93-97
+        }
+    }
+}
+static void rr_overlaps(const mbo_pred *P, std::vector<uint32_t> &reps, mbo_pred_out *out) {
+    std::stable_sort(reps.begin(), reps.end(), [&](uint32_t a, uint32_t b) {              // comparePredictionsByEvalue
+        if (P[a].evalue != P[b].evalue) return P[a].evalue < P[b].evalue;
+        return P[a].lowCoord < P[b].lowCoord; });
+    std::vector<char> done(reps.size(), 0);
+    for (size_t i = 0; i < reps.size(); i++) {
+        if (done[i]) continue;
+        done[i] = 1; const mbo_pred &a = P[reps[i]]; out[reps[i]].noOverlapClusterId = a.targetKey;
+        for (size_t j = i + 1; j < reps.size(); j++) {
+            const mbo_pred &b = P[reps[j]];
+            if ((b.highCoord < a.highCoord && b.highCoord > a.lowCoord) || (b.lowCoord < a.highCoord && b.lowCoord > a.lowCoord) ||
+                (b.highCoord < a.highCoord && b.lowCoord > a.lowCoord) || (b.highCoord > a.highCoord && b.lowCoord < a.lowCoord)) {
+                done[j] = 1; out[reps[j]].noOverlapClusterId = a.targetKey;               // :139-141 (assigned even if already assigned)
+            }
+        }
+    }
+}
+extern "C" {
+// one contig: preds in the order of the calledExons entry.  memberOrder = every call, plus strand (sorted by contig start) then minus;
+// repOrder = the representatives in output order (stable by (target, strand) over [plus reps by E-value, minus reps by E-value]).
+int mbo_reduce_redundancy(const mbo_pred *P, uint32_t n, const uint32_t *exonKeys, mbo_pred_out *out, uint32_t *memberOrder, uint32_t *repOrder, uint32_t *nRep) {
+    for (uint32_t i = 0; i < n; i++) { out[i].clusterId = 0; out[i].clusterLowCoord = 0; out[i].noOverlapClusterId = 0; out[i].isRep = 0; }
+    std::vector<uint32_t> plus, minus, rp, rm;
+    for (uint32_t i = 0; i < n; i++) (P[i].strand == 1 ? plus : minus).push_back(i);
+    rr_strand(P, exonKeys, plus, out, rp); rr_overlaps(P, rp, out);
+    rr_strand(P, exonKeys, minus, out, rm); rr_overlaps(P, rm, out);
+    uint32_t k = 0;
+    for (uint32_t x : plus) memberOrder[k++] = x;
+    for (uint32_t x : minus) memberOrder[k++] = x;
+    std::vector<uint32_t> reps(rp); reps.insert(reps.end(), rm.begin(), rm.end());
+    std::stable_sort(reps.begin(), reps.end(), [&](uint32_t a, uint32_t b) {              // comparePredictionsByTarget
+        if (P[a].targetKey != P[b].targetKey) return P[a].targetKey < P[b].targetKey;
+        return P[a].strand < P[b].strand; });
+    for (size_t i = 0; i < reps.size(); i++) repOrder[i] = reps[i];
+    *nRep = (uint32_t)reps.size();
+    return 0;
+}
+// batch form (same layout as mb200_reduce_redundancy: exon ranges are absolute, orders are relative to the contig's range); OpenMP over contigs
+int mbo_reduce_redundancy_batch(const mbo_pred *P, const uint64_t *off, uint32_t nContigs, const uint32_t *exonKeys, mbo_pred_out *out, uint32_t *memberOrder,
+                                uint32_t *repOrder, uint32_t *repCount, int threads) {
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (uint32_t c = 0; c < nContigs; c++)
+        mbo_reduce_redundancy(P + off[c], (uint32_t)(off[c + 1] - off[c]), exonKeys, out + off[c], memberOrder + off[c], repOrder + off[c], repCount + c);
+    return 0;
+}
+}  // extern "C"

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../metaeuk_b200/csrc/host_tables.h"
 #include "../../metaeuk_b200/csrc/prefilter_core.cuh"
+#include "../../metaeuk_b200/csrc/reduce_core.cuh"
 
 template <class SH>
 static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
@@ -86,6 +87,12 @@ int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, cons
     if (cfg == 2) return emu_prefilter_t<MbPrefSharedT<MbPrefCfgSparse>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
     if (cfg == 3) return emu_prefilter_t<MbPrefSharedT<MbPrefCfg<64, 1, 8, 64, 5>>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
     return emu_prefilter_t<MbPrefSharedT<MbPrefCfgDense>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);
+}
+
+int emu_reduce(const MbPred *P, uint32_t n, const uint32_t *exonKeys, MbPredOut *out, uint32_t *memberOrder, uint32_t *repOrder, uint32_t *nRep) {
+    std::vector<uint32_t> flag(n + 1), tmp(n + 1);
+    *nRep = mb_reduce_contig(P, n, exonKeys, out, memberOrder, repOrder, flag.data(), tmp.data());
+    return 0;
 }
 
 }  // extern "C"

@@ -308,6 +308,60 @@ def case_contigs(name, seed, nprot, nc, cl, mask=1, sets=1, thr=8):
           "dp lines", sum(v.count("\n") for v in out["dp"].values()))
 
 
+def case_redundancy(name, seed, nfam=8, famsize=6, nc=10, cl=12000, sets=2, thr=4):
+    """reduceredundancy needs calls that share exons: protein FAMILIES as targets, genes planted from family members,
+    so every gene is called once per homologous target (and --max-exon-sets 2 adds same-target sub-optimal sets)"""
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    prots = [rand_prot(rng) for _ in range(60)]
+    fams = []
+    for _ in range(nfam):
+        base = rand_prot(rng, 260, 40)
+        fam = [mutate(rng, base, rng.choice([0.05, 0.1, 0.2, 0.3])) for _ in range(famsize)]
+        fams.append(fam); prots += fam
+    rng.shuffle(prots)
+    famprots = [p for fam in fams for p in fam]
+    contigs = make_contigs(rng, famprots, nc, cl)
+    # genes of two different families overlapping on the same strand (one sits inside the other's intron, or they interleave):
+    # these are the calls excludeSameStrandOverlaps has to choose between
+    def enc(p):
+        return "".join(rng.choice(CODON[x]) for x in p)
+    def spacer(a, b):
+        return "".join(rng.choices("ACGT", k=rng.randint(a, b)))
+    for t in range(8):
+        fa, fb = rng.sample(range(nfam), 2)
+        pa = mutate(rng, rng.choice(fams[fa]), 0.15); pb = mutate(rng, rng.choice(fams[fb]), rng.choice([0.1, 0.4]))
+        h = len(pa) // 2
+        if t % 2 == 0:      # B inside A's intron
+            gene = enc(pa[:h]) + spacer(60, 200) + "TAA" + enc(pb) + "TAG" + spacer(60, 200) + enc(pa[h:])
+        else:               # interleaved: A1 B1 A2 B2
+            hb = len(pb) // 2
+            gene = enc(pa[:h]) + spacer(50, 120) + enc(pb[:hb]) + spacer(50, 120) + enc(pa[h:]) + spacer(50, 120) + enc(pb[hb:])
+        if t % 3 == 0:
+            gene = rc(gene)
+        contigs.append(spacer(300, 900) + gene + spacer(300, 900))
+    write_fasta(tmp + "/proteins.faa", prots, "P")
+    write_fasta(tmp + "/contigs.fna", contigs, "C")
+    run("%s createdb %s/proteins.faa %s/proteins -v 3" % (REF, tmp, tmp), log)
+    run("%s createdb %s/contigs.fna %s/contigs -v 3" % (REF, tmp, tmp), log)
+    run("%s extractorfs %s/contigs %s/nucl_6f %s" % (REF, tmp, tmp, ORF_FLAGS.format(thr=thr)), log)
+    run("%s translatenucs %s/nucl_6f %s/aa_6f --translation-table 1 --add-orf-stop 0 -v 3 --compressed 0 --threads %d" % (REF, tmp, tmp, thr), log)
+    run("%s prefilter %s/aa_6f %s/proteins %s/pref %s" % (REF, tmp, tmp, tmp, PREF_FLAGS.format(mask=1, thr=thr, maxseqs=300)), log)
+    run("%s align %s/aa_6f %s/proteins %s/pref %s/aln %s" % (REF, tmp, tmp, tmp, tmp, ALN_FLAGS.format(thr=thr)), log)
+    run("%s resultspercontig %s/contigs %s/nucl_6f %s/aln %s/bycontig --threads %d --compressed 0 -v 3" % (REF, tmp, tmp, tmp, tmp, thr), log)
+    run("%s collectoptimalset %s/bycontig %s/proteins %s/dp %s" % (REF, tmp, tmp, tmp, DP_FLAGS.format(thr=thr, sets=sets)), log)
+    run("%s reduceredundancy %s/dp %s/grouped %s/clusters --overlap 0 --threads %d --compressed 0 -v 3" % (REF, tmp, tmp, tmp, thr), log)
+    run("%s reduceredundancy %s/dp %s/grouped_ov %s/clusters_ov --overlap 1 --threads %d --compressed 0 -v 3" % (REF, tmp, tmp, tmp, thr), log)
+    out = {"case": name, "kind": "redundancy", "seed": seed, "dp": resdb(tmp + "/dp"), "grouped": resdb(tmp + "/grouped"), "clusters": resdb(tmp + "/clusters"),
+           "grouped_overlap_allowed": resdb(tmp + "/grouped_ov"), "ref_version": run("%s version" % REF, log).strip()}
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+    print(name, "dp lines", sum(v.count("\n") for v in out["dp"].values()), "grouped lines", sum(v.count("\n") for v in out["grouped"].values()),
+          "grouped(overlap ok) lines", sum(v.count("\n") for v in out["grouped_overlap_allowed"].values()), "cluster lines", sum(v.count("\n") for v in out["clusters"].values()))
+
+
 def case_orfs(name, seed, thr=4):
     """extractorfs + translatenucs only on contigs with the characters the synthetic genes never contain:
     N runs, lower case, IUPAC ambiguity codes, U, and contigs too short to hold a codon / an ORF"""
@@ -356,3 +410,5 @@ if __name__ == "__main__":
         case_contigs("contigs_sets", 77, nprot=200, nc=12, cl=9000, sets=3)
     if "orf_edge" in which:
         case_orfs("orf_edge", 31)
+    if "redundancy_family" in which:
+        case_redundancy("redundancy_family", 2025)

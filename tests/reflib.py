@@ -225,6 +225,84 @@ def oracle_extract_orfs(contigs, min_len=15, max_len=32734, start_mode=1):
     return hdr, seqs
 
 
+class Pred(C.Structure):
+    _fields_ = [("targetKey", C.c_uint32), ("strand", C.c_int32), ("totalBitscore", C.c_uint32), ("nExons", C.c_uint32), ("lowCoord", C.c_uint32),
+                ("highCoord", C.c_uint32), ("exonBegin", C.c_uint32), ("pad", C.c_uint32), ("evalue", C.c_double)]
+
+
+class PredOut(C.Structure):
+    _fields_ = [("clusterId", C.c_uint32), ("clusterLowCoord", C.c_uint32), ("noOverlapClusterId", C.c_uint32), ("isRep", C.c_uint32)]
+
+
+def parse_calls(entry):
+    """one calledExons (dp) DB entry -> (preds [dict], exon lines per pred) as reduceredundancy collects them (reduceredundancy.cpp:222-268):
+    a new call starts, per strand, whenever the target key or the low contig coordinate changes"""
+    preds, prev = [], {1: None, -1: None}
+    for line in entry.split("\n"):
+        if not line:
+            continue
+        w = line.split("\t")
+        assert len(w) == 19
+        t, s, low = int(w[0]), int(w[1]), int(w[5])
+        if prev[s] is None or preds[prev[s]]["targetKey"] != t or preds[prev[s]]["lowCoord"] != low:
+            preds.append({"targetKey": t, "strand": s, "totalBitscore": int(w[2]), "evalue": float(w[3]), "evalue_txt": w[3], "nExons": int(w[4]), "lowCoord": low,
+                          "highCoord": int(w[6]), "exons": []})
+            prev[s] = len(preds) - 1
+        preds[prev[s]]["exons"].append(w[7:])
+    return preds
+
+
+def reprint_exon(cols):
+    """PotentialExon::setByDPRes -> exonToBuffer (PredictionParser.h:66-150): every field survives except the sequence identity, which is
+    parsed to a double, narrowed to float and re-truncated to three digits"""
+    f = np.float32(float(cols[2]))
+    if f == np.float32(1.0):
+        sid = "1.000"
+    else:
+        sid = "0." + ("0" if f < np.float32(0.10) else "") + ("0" if f < np.float32(0.01) else "") + str(int(np.float32(f * np.float32(1000))))
+    ev = "%.3E" % float(cols[3])
+    return "\t".join([cols[0], cols[1], sid, ev] + list(cols[4:]))
+
+
+def fmt_grouped(preds, outs, rep_order, allow_overlaps=False):
+    """writeRepPredsInDPFormat + Prediction::predictionToBuffer (reduceredundancy.cpp:149-160, PredictionParser.h:368-396)"""
+    s = ""
+    for i in rep_order:
+        p = preds[i]
+        if not allow_overlaps and outs[i]["noOverlapClusterId"] != p["targetKey"]:
+            continue
+        head = "%d\t%d\t%d\t%s\t%d\t%d\t%d" % (p["targetKey"], p["strand"], p["totalBitscore"], "%.3E" % p["evalue"], p["nExons"], p["lowCoord"], p["highCoord"])
+        for e in p["exons"]:
+            s += head + "\t" + reprint_exon(e) + "\n"
+    return s
+
+
+def fmt_clusters(preds, outs, member_order):
+    """Prediction::predictionClusterToBuffer (PredictionParser.h:398-423)"""
+    return "".join("%d\t%d\t%d\t%d\t%d\t%d\n" % (outs[i]["clusterId"], preds[i]["strand"], outs[i]["clusterLowCoord"], preds[i]["targetKey"], preds[i]["strand"],
+                                                   preds[i]["lowCoord"]) for i in member_order)
+
+
+def oracle_reduce_redundancy(entry):
+    """dp entry text -> (preds, outs, member_order, rep_order) through the CPU oracle"""
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    L = C.CDLL(ORACLE_SO)
+    preds = parse_calls(entry)
+    n = len(preds)
+    P = (Pred * max(1, n))(); keys = []
+    for i, p in enumerate(preds):
+        P[i].targetKey = p["targetKey"]; P[i].strand = p["strand"]; P[i].totalBitscore = p["totalBitscore"]; P[i].nExons = len(p["exons"]); P[i].lowCoord = p["lowCoord"]
+        P[i].highCoord = p["highCoord"]; P[i].exonBegin = len(keys); P[i].evalue = p["evalue"]
+        keys += [int(e[0]) for e in p["exons"]]
+    K = np.array(keys + [0], np.uint32)
+    O = (PredOut * max(1, n))(); mo = np.zeros(max(1, n), np.uint32); ro = np.zeros(max(1, n), np.uint32); nrep = C.c_uint32(0)
+    rc = L.mbo_reduce_redundancy(P, C.c_uint32(n), _p(K, C.c_uint32), O, _p(mo, C.c_uint32), _p(ro, C.c_uint32), C.byref(nrep))
+    assert rc == 0
+    outs = [{"clusterId": O[i].clusterId, "clusterLowCoord": O[i].clusterLowCoord, "noOverlapClusterId": O[i].noOverlapClusterId, "isRep": O[i].isRep} for i in range(n)]
+    return preds, outs, [int(x) for x in mo[:n]], [int(x) for x in ro[:nrep.value]]
+
+
 def aln_to_dict(a):
     return dict(seqId=a.seqId, score=a.score, bitScore=a.bitScore, qStart=a.qStart, qEnd=a.qEnd, dbStart=a.dbStart, dbEnd=a.dbEnd,
                 alnLen=a.alnLen, passed=a.passed, seqIdEst=float(np.float32(a.seqIdEst)), evalue=a.evalue)

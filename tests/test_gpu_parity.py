@@ -219,6 +219,33 @@ def test_contigs_to_exon_calls_without_host_round_trip():
     ctx.close()
 
 
+def test_cli_reduceredundancy_on_database_files(tmp_path):
+    import os
+    import subprocess
+    from metaeuk_b200 import lib as mlib
+    exe = os.path.join(mlib.PKG, "bin", "mb200")
+    c = reflib.load_case("redundancy_family")
+    d = str(tmp_path)
+    write_db(d + "/dp", [(int(k), v) for k, v in c["dp"].items()], 12)
+    subprocess.check_call([exe, "gpureduceredundancy", d + "/dp", d + "/grouped", d + "/clusters"])
+    assert read_db(d + "/grouped") == c["grouped"] and read_db(d + "/clusters") == c["clusters"]
+    subprocess.check_call([exe, "gpureduceredundancy", d + "/dp", d + "/grouped_ov", d + "/clusters_ov", "--overlap", "1"])
+    assert read_db(d + "/grouped_ov") == c["grouped_overlap_allowed"]
+
+
+def test_reduceredundancy_golden():
+    """the step after the path on the device: representatives (with and without same-strand overlaps) and the call -> representative DB"""
+    c = reflib.load_case("redundancy_family")
+    from metaeuk_b200.lib import Context
+    ctx = Context(0)
+    grouped, clusters = M.reduceredundancy(ctx, c["dp"])
+    assert grouped == c["grouped"] and clusters == c["clusters"]
+    grouped_ov, _ = M.reduceredundancy(ctx, c["dp"], allow_overlaps=True)
+    assert grouped_ov == c["grouped_overlap_allowed"] and grouped_ov != grouped
+    assert M.reduceredundancy(ctx, {}) == ({}, {})
+    ctx.close()
+
+
 def test_long_queries_take_the_32bit_alignment_path():
     """queries longer than 1024 residues skip the packed 16-bit kernel; longer than 512 windows spill the window arrays"""
     prots, _ = synth(11, 300, 1)

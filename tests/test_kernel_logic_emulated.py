@@ -84,3 +84,23 @@ def test_prefilter_kernel_logic_matches_reference(emu, name, cfg):
             if bad < 3:
                 print("query", k, "\nwant:\n", want[:300], "\ngot:\n", got[:300])
     assert bad == 0
+
+
+def test_reduceredundancy_kernel_logic_matches_reference(emu):
+    """reduce_core.cuh (one contig per thread on the device) compiled for the host: clustering, overlap exclusion and both output orders"""
+    c = reflib.load_case("redundancy_family")
+    for k, entry in c["dp"].items():
+        preds = reflib.parse_calls(entry)
+        n = len(preds)
+        P = (reflib.Pred * max(1, n))(); keys = []
+        for i, p in enumerate(preds):
+            P[i].targetKey = p["targetKey"]; P[i].strand = p["strand"]; P[i].totalBitscore = p["totalBitscore"]; P[i].nExons = len(p["exons"]); P[i].lowCoord = p["lowCoord"]
+            P[i].highCoord = p["highCoord"]; P[i].exonBegin = len(keys); P[i].evalue = p["evalue"]
+            keys += [int(e[0]) for e in p["exons"]]
+        K = np.array(keys + [0], np.uint32)
+        O = (reflib.PredOut * max(1, n))(); mo = np.zeros(max(1, n), np.uint32); ro = np.zeros(max(1, n), np.uint32); nrep = C.c_uint32(0)
+        assert emu.emu_reduce(P, C.c_uint32(n), reflib._p(K, C.c_uint32), O, reflib._p(mo, C.c_uint32), reflib._p(ro, C.c_uint32), C.byref(nrep)) == 0
+        outs = [{"clusterId": O[i].clusterId, "clusterLowCoord": O[i].clusterLowCoord, "noOverlapClusterId": O[i].noOverlapClusterId} for i in range(n)]
+        assert reflib.fmt_grouped(preds, outs, [int(x) for x in ro[:nrep.value]]) == c["grouped"][k], k
+        assert reflib.fmt_grouped(preds, outs, [int(x) for x in ro[:nrep.value]], allow_overlaps=True) == c["grouped_overlap_allowed"][k], k
+        assert reflib.fmt_clusters(preds, outs, [int(x) for x in mo[:n]]) == c["clusters"][k], k
