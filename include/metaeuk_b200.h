@@ -148,6 +148,8 @@ int mb200_chain(mb200_ctx *ctx, const mb200_cand *cands, const uint64_t *cand_of
 int mb200_extract_orfs(mb200_ctx *ctx, const char *nuc, const uint64_t *off, uint32_t n_contigs, int min_len, int max_len, int start_mode,
                        uint64_t *n_orfs, const mb200_orf **orfs, uint64_t *n_aa, const char **aa);
 int mb200_queries_from_orfs(mb200_ctx *ctx);
+/* mb200_search on the resident query batch (mb200_queries_upload or mb200_queries_from_orfs); aln_off: caller buffer of n_queries + 1 */
+int mb200_search_resident(mb200_ctx *ctx, uint64_t *aln_off, const mb200_aln **alns);
 
 /* reduceredundancy (src/exonpredictor/reduceredundancy.cpp:24-147,273-296) for a batch of contigs: calls of contig c =
  * preds[pred_off[c] .. pred_off[c+1]) in the order of the calledExons entry.  Per call: cluster representative (target key, low coordinate),

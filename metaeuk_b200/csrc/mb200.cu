@@ -721,7 +721,7 @@ static int align_pipeline(mb200_ctx *c) {
     CU(cudaMemcpyAsync(hn, dNPass, 8, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long hc[2] = {0, 0};
     CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
-    TRY(sync_check(c, "k_sw_score"));
+    TRY(sync_check(c, "forward alignment kernel"));
     float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
     if (hn[1] == 1) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits (scores must stay below 32000)");
     if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
@@ -922,6 +922,17 @@ int mb200_search(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t 
     std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
     TRY(collect_accepted(c, tids));
     memcpy(alnOff, c->hAlnOff.data(), (size_t)(nQ + 1) * 8);
+    *alns = c->hAlns.empty() ? nullptr : c->hAlns.data();
+    return 0;
+}
+
+int mb200_search_resident(mb200_ctx *c, uint64_t *alnOff, const mb200_aln **alns) {
+    if (!c || !alnOff || !alns) return fail(MB200_E_ARG, "null argument");
+    TRY(mb200_prefilter_resident(c));
+    TRY(align_pipeline(c));
+    std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
+    TRY(collect_accepted(c, tids));
+    memcpy(alnOff, c->hAlnOff.data(), (size_t)(c->nQ + 1) * 8);
     *alns = c->hAlns.empty() ? nullptr : c->hAlns.data();
     return 0;
 }

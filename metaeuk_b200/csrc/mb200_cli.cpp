@@ -7,6 +7,7 @@
 //   mb200 gpuresultspercontig  <contigsDB> <orfDB> <alnDB> <byContigDB> == resultspercontig   (src/exonpredictor/resultspercontig.cpp:34)
 //   mb200 gpucollectoptimalset <byContigDB> <targetDB> <predDB>         == collectoptimalset  (src/exonpredictor/collectoptimalset.cpp:224)
 //   mb200 gpureduceredundancy  <calledExonsDB> <predsDB> <predToCallDB> == reduceredundancy   (src/exonpredictor/reduceredundancy.cpp:162)
+//   mb200 gpupredictexons      <contigsDB> <targetDB> <predDB>          == predictexons.sh:40-82 with the contigs as the only input (ORFs stay on the GPU)
 //   mb200 gpupredictexons      <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>
 //                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
 // DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
@@ -285,8 +286,35 @@ int main(int argc, char **argv) {
         std::map<uint32_t, std::string> m; for (size_t i = 0; i < byc.keys.size(); i++) m[byc.keys[i]] = byc.entry(i);
         writeDb(pos[2], 12, chainAll(ctx, m, total));   // DBTYPE_GENERIC_DB
         mb200_ctx_destroy(ctx);
+    } else if (cmd == "gpupredictexons" && pos.size() == 3) {
+        // contigs are the only input: ORF fragments are extracted and translated on the device, become the resident query batch
+        // (no aa_6f / nucl_6f DBs, no host round trip), are searched, regrouped per contig and chained
+        Session s; s.open(o, pos[1]); Db contigs = openDb(pos[0]);
+        std::vector<size_t> order(contigs.keys.size()); for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return contigs.keys[a] < contigs.keys[b]; });
+        std::string nuc; std::vector<uint64_t> off(1, 0);
+        for (size_t id : order) { const size_t n = contigs.len[id] >= 2 ? contigs.len[id] - 2 : 0; nuc.append(contigs.entry(id), n); off.push_back(nuc.size()); }
+        uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+        MB(mb200_extract_orfs(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
+        Db hdr; hdr.dbtype = 12; char buf[96];
+        for (uint64_t i = 0; i < n; i++) {          // in-memory nucl_6f_h (Orf::writeOrfHeader, Orf.cpp:440-457)
+            const mb200_orf &r = orfs[i]; const long long d = (long long)r.from - (long long)r.to;
+            int w = snprintf(buf, sizeof(buf), "%u\t%u%c%lld", contigs.keys[order[r.contig]], r.from, r.from < r.to ? '+' : '-', d < 0 ? -d : d);
+            if (r.flags & 3u) w += snprintf(buf + w, sizeof(buf) - w, "\t%u", r.flags & 3u);
+            buf[w++] = '\n'; buf[w++] = '\0';
+            hdr.byKey[(uint32_t)i] = hdr.keys.size(); hdr.keys.push_back((uint32_t)i); hdr.off.push_back(hdr.data.size()); hdr.len.push_back(w);
+            hdr.data.insert(hdr.data.end(), buf, buf + w);
+        }
+        std::vector<uint32_t> qlen(n); for (uint64_t i = 0; i < n; i++) qlen[i] = orfs[i].aa_len;   // (the record buffer is reused by later calls)
+        MB(mb200_queries_from_orfs(s.ctx));
+        std::vector<uint64_t> aoff(n + 1); const mb200_aln *alns = nullptr;
+        MB(mb200_search_resident(s.ctx, aoff.data(), &alns));
+        std::map<uint32_t, std::string> aln;
+        for (uint64_t i = 0; i < n; i++) aln[(uint32_t)i] = alnEntry(s, std::vector<mb200_aln>(alns + aoff[i], alns + aoff[i + 1]), qlen[i]);
+        auto byc = byContig(contigs, hdr, aln);
+        writeDb(pos[2], 12, chainAll(s.ctx, byc, s.t.res.size()));
     } else if (cmd == "gpupredictexons") {
-        if (pos.size() != 5) DIE("gpupredictexons <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>");
+        if (pos.size() != 5) DIE("gpupredictexons <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>   |   gpupredictexons <contigsDB> <targetDB> <predDB>");
         Session s; s.open(o, pos[3]); Db contigs = openDb(pos[0]), qdb = openDb(pos[1]), hdr = openDb(pos[2] + "_h"); Seqs q = encodeDb(qdb, false);
         auto aln = searchAll(s, qdb, q);
         auto byc = byContig(contigs, hdr, aln);

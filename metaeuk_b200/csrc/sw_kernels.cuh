@@ -7,19 +7,15 @@
 //     reverse  on the reversed query prefix / target prefix, stopping at the first column whose maximum == score (:400-476, :900)
 // Recurrence:  H = max(0, Hdiag + s, E, F);  E' = max(E - ge, H - go);  F' = max(F - ge, H - go);  s = mat[t][q_j] + compBias8[j].
 //
-// Two kernels:
-//   k_sw_score  all hits, score only.  One warp per (query, chunk of <= 32 hits): every lane aligns the SAME query against its
-//               own target, so the query row (residue, bias) is a shared-memory broadcast and the substitution lookup
-//               sMat[q_j][t] is bank-conflict free (row = 32 consecutive banks).  Per-lane DP state = one packed (H:16|E:16) word per
-//               query row in shared memory, laid out [row][lane]; NC target columns are processed per sweep over the query so the
-//               state is read/written once per NC cells.  Alignments whose score reaches the per-query-length e-value gate are
-//               appended to a pass list.
-//   k_sw_trace  pass list only (a few % of the hits): forward with end tracking, then the reverse pass; one alignment per lane,
-//               state in a lane-interleaved global scratch (any length).
+// Kernels (forward = score + e-value gate for all hits; trace = start coordinates for the few % that pass):
+//   k_sw_rows   forward, one target per lane, 32-bit cells, register-resident 32-row blocks (also used for queries > 1024 residues)
+//   k_sw_rows2  forward, two targets per lane in packed s16x2 cells (DPX), one (query, chunk of 32 hits) per half-warp  [default]
+//   k_sw_rows3  forward, the packed arithmetic as a per-lane state machine over (pair, block) units                   [option]
+//   k_sw_trace  pass list, forward with end tracking + reverse pass, state in a lane-interleaved global scratch         [option]
+//   k_sw_trace2 pass list, the same with 16-row register blocks                                                         [default]
 #pragma once
 #include <stdint.h>
 
-#define MB_SW_WARPS 4
 #define MB_SW_PADRES 21   // matrix row/column used for columns beyond the target end (very negative)
 
 struct SwTraceOut { uint32_t slot; int32_t score, qStart, qEnd, dbStart, dbEnd, flag, pad; };
@@ -51,88 +47,6 @@ __global__ void __launch_bounds__(128) k_perm_by_len(const MbPrefHit *__restrict
         }
         for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) perm[(size_t)q * maxHits + k] = (uint16_t)(keys[k] & 0xFFFFu);
     }
-}
-
-template <int NC>
-__global__ void __launch_bounds__(MB_SW_WARPS * 32) k_sw_score(
-    const uint32_t *__restrict__ order, const uint32_t *__restrict__ chunkOff, uint32_t pBegin, uint32_t pEnd,
-    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
-    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
-    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
-    uint32_t Lpad, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
-    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag) {
-    extern __shared__ __align__(16) uint32_t dynSmem[];
-    __shared__ int32_t sMat[22 * 32];
-    for (int i = threadIdx.x; i < 22 * 32; i += blockDim.x) {
-        const int r = i >> 5, t = i & 31;
-        sMat[i] = (r < 21 && t < 21) ? (int)alnMat[t * 21 + r] : -30000;   // sMat[q][t] = mat[t][q] (Matcher tinySubMat, StripedSmithWaterman.cpp:1341)
-    }
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    uint32_t *HE = dynSmem + (size_t)wib * (Lpad * 33u);   // [Lpad][32] state words
-    uint32_t *sQcb = HE + Lpad * 32u;                       // [Lpad]  byte offset of the matrix row of q_j (q_j*128) | (uint8)cb_j << 16
-    const uint32_t chunkBase = chunkOff[pBegin], chunkEnd = chunkOff[pEnd];
-    const char *matBytes = reinterpret_cast<const char *>(sMat);
-    const int negE = -gapE;
-    unsigned long long cells = 0;
-    for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = chunkBase + atomicAdd(counter, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= chunkEnd) break;
-        uint32_t lo = pBegin, hi = pEnd;   // chunkOff[lo] <= chunk < chunkOff[hi]
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (chunkOff[mid] <= chunk) lo = mid; else hi = mid; }
-        const uint32_t qi = order[lo];
-        const uint32_t kk = (chunk - chunkOff[lo]) * 32u + lane;
-        const uint32_t cnt = hitCount[qi];
-        const bool active = kk < cnt;
-        const uint64_t qb = qoff[qi]; const int L = (int)(qoff[qi + 1] - qb);
-        __syncwarp();
-        for (int j = lane; j < L; j += 32) sQcb[j] = ((uint32_t)qres[qb + j] << 7) | ((uint32_t)(uint8_t)cb[qb + j] << 16);
-        __syncwarp();
-        const uint32_t k = (active && perm) ? (uint32_t)perm[(size_t)qi * maxHits + kk] : kk;
-        const size_t slot = (size_t)qi * maxHits + k;
-        uint32_t tid = 0; int tLen = 0; const uint8_t *t = tseq;
-        if (active) { tid = hits[slot].seqId; const uint64_t tb = toff[tid]; tLen = (int)(toff[tid + 1] - tb); t = tseq + tb; }
-        int mx = 0;
-        uint32_t *myHE = HE + lane;
-        for (int i0 = 0; i0 < tLen; i0 += NC) {
-            int tA[NC], H[NC], G[NC], F[NC];   // column byte offset in a matrix row; H, H - gapOpen and F of the previous row
-#pragma unroll
-            for (int c = 0; c < NC; c++) { tA[c] = ((i0 + c < tLen) ? (int)t[i0 + c] : MB_SW_PADRES) * 4; H[c] = 0; G[c] = -gapO; F[c] = 0; }
-            int hleftPrev = 0;
-            const bool first = (i0 == 0);
-            for (int j = 0; j < L; j++) {
-                const uint32_t w = first ? 0u : myHE[j * 32];
-                const int hleft = (int)(w & 0xFFFFu);
-                int e = (int)(w >> 16);
-                const uint32_t qc = sQcb[j];
-                const int rowOff = (int)(qc & 0xFFFFu);
-                const int cbj = (int)(int8_t)(qc >> 16);
-                int diag = hleftPrev;
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    const int s = *reinterpret_cast<const int32_t *>(matBytes + (tA[c] + rowOff)) + cbj;
-                    const int f = __viaddmax_s32(F[c], negE, G[c]);          // max(F - ge, Hup - go)
-                    const int t1 = __viaddmax_s32(diag, s, e);               // max(Hdiag + s, E)
-                    const int h = __vimax_s32_relu(t1, f);                   // max(.., F, 0)
-                    diag = H[c]; H[c] = h; F[c] = f;
-                    const int g = h - gapO; G[c] = g;
-                    e = __viaddmax_s32_relu(e, negE, g);                     // E' = max(E - ge, H - go, 0)
-                    mx = max(mx, h);
-                }
-                hleftPrev = hleft;
-                myHE[j * 32] = (uint32_t)H[NC - 1] | ((uint32_t)e << 16);
-            }
-            cells += (unsigned long long)L * NC;
-        }
-        if (active) {
-            scoreOut[slot] = mx;
-            if (mx >= 65000) atomicExch(errFlag, 1u);
-            if (mx >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slot; else atomicExch(errFlag, 2u); }
-        }
-    }
-    if (cells) atomicAdd(cellCount, cells);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -202,6 +202,13 @@ class Context:
         self._check(self.L.mb200_search(self.h, _p(q), _p(qoff), C.c_uint32(n), _p(off), C.byref(ptr)))
         return self._view(ptr, int(off[-1]), ALN_DTYPE, copy), off
 
+    def search_resident(self, copy=False):
+        """search() on the resident query batch (queries_upload / queries_from_orfs)"""
+        n = self._nq
+        off = np.empty(n + 1, np.uint64); ptr = C.c_void_p()
+        self._check(self.L.mb200_search_resident(self.h, _p(off), C.byref(ptr)))
+        return self._view(ptr, int(off[-1]), ALN_DTYPE, copy), off
+
     def prefilter_compact(self, q, qoff, copy=False):
         """-> (hits as one flat array, uint64 offsets[n+1]); same ownership rule as search()"""
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)

@@ -344,3 +344,6 @@ def test_cli_modules_on_database_files(tmp_path):
     subprocess.check_call([exe, "gpuextractorfs", d + "/contigs_nt", d + "/orf_h", d + "/orf_aa"])
     assert read_db(d + "/orf_h") == {str(k): v for k, v in c["orf_headers"].items()}
     assert read_db(d + "/orf_aa") == {str(k): s + "\n" for k, s in c["queries"]}
+    # ... and the whole chain with the contigs as the only input (fragments never leave the GPU between extraction and search)
+    subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp3", "--max-exon-sets", str(c["max_exon_sets"])] + common)
+    assert read_db(d + "/dp3") == c["dp"]
