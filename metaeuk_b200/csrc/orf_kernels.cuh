@@ -10,14 +10,14 @@
 //                                      the order in which fragments END along the strand (all three frames interleaved)
 // GPU organisation: in ANY_TO_STOP mode a fragment is fully determined by its terminating codon (a stop, or the last complete codon of
 // its frame) and the previous terminator of the same frame, so one CTA per (contig, strand) streams the strand in tiles, finds
-// terminators with one thread per 12 positions, and gets "previous terminator" and the output rank from two block scans.  Pass 1 counts,
+// terminators with one thread per 24 positions, and gets "previous terminator" (three frames at once) and the output rank from two block scans.  Pass 1 counts,
 // a scan over (contig, strand) gives every CTA its output base, pass 2 writes the records in the reference's order, and a third
 // kernel translates with one thread per residue.
 #pragma once
 #include <stdint.h>
 
 #define MB_ORF_THREADS 256
-#define MB_ORF_PER_THREAD 12                      // 4 codons of each frame
+#define MB_ORF_PER_THREAD 24                      // 8 codons of each frame
 #define MB_ORF_TILE (MB_ORF_THREADS * MB_ORF_PER_THREAD)
 
 struct MbOrfRec { uint32_t contig, from, to, flags; uint64_t aaOff; uint32_t aaLen; uint32_t strandFrom; };   // from/to: header coordinates
@@ -37,36 +37,57 @@ __device__ __forceinline__ int orf_char(const unsigned char *seq, uint32_t L, in
     return s ? comp[c] : c;
 }
 
-__device__ __forceinline__ uint32_t orf_block_scan_add(uint32_t v, uint32_t *sm, uint32_t *total) {   // exclusive; 256 threads
+// exclusive block scans over MB_ORF_THREADS threads, several values per call so that one pair of barriers serves all of them
+template <int N> __device__ __forceinline__ void orf_block_scan_add(uint32_t (&v)[N], uint32_t *sm /* N * warps */, uint32_t (&total)[N]) {
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    uint32_t inc = v;
+    uint32_t inc[N];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
-    if (lane == 31) sm[w] = inc;
-    __syncthreads();
-    uint32_t wp = 0, tot = 0;
+    for (int k = 0; k < N; k++) inc[k] = v[k];
 #pragma unroll
-    for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[i]; if (i < (int)w) wp += x; tot += x; }
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < N; k++) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc[k], d); if ((int)lane >= d) inc[k] += y; }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < N; k++) sm[k * (MB_ORF_THREADS / 32) + w] = inc[k];
+    }
     __syncthreads();
-    *total = tot;
-    return wp + inc - v;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        uint32_t wp = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[k * (MB_ORF_THREADS / 32) + i]; if (i < (int)w) wp += x; tot += x; }
+        total[k] = tot; v[k] = wp + inc[k] - v[k];
+    }
+    __syncthreads();
 }
 
-// exclusive "last terminator seen so far" per frame: max-scan of (position + 1), 0 = none
-__device__ __forceinline__ uint32_t orf_block_scan_max(uint32_t v, uint32_t *sm, uint32_t *total) {
+// exclusive "last terminator seen so far" for the three frames at once: max-scan of (position + 1), 0 = none
+__device__ __forceinline__ void orf_block_scan_max3(uint32_t (&v)[3], uint32_t *sm /* 3 * warps */, uint32_t (&total)[3]) {
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    uint32_t inc = v;
+    uint32_t inc[3] = {v[0], v[1], v[2]};
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc = max(inc, y); }
-    uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1); if (lane == 0) excl = 0;
-    if (lane == 31) sm[w] = inc;
-    __syncthreads();
-    uint32_t wp = 0, tot = 0;
+    for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-    for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[i]; if (i < (int)w) wp = max(wp, x); tot = max(tot, x); }
+        for (int k = 0; k < 3; k++) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc[k], d); if ((int)lane >= d) inc[k] = max(inc[k], y); }
+    }
+    uint32_t excl[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { excl[k] = __shfl_up_sync(0xffffffffu, inc[k], 1); if (lane == 0) excl[k] = 0; }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) sm[k * (MB_ORF_THREADS / 32) + w] = inc[k];
+    }
     __syncthreads();
-    *total = tot;
-    return max(wp, excl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t wp = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < MB_ORF_THREADS / 32; i++) { const uint32_t x = sm[k * (MB_ORF_THREADS / 32) + i]; if (i < (int)w) wp = max(wp, x); tot = max(tot, x); }
+        total[k] = tot; v[k] = max(wp, excl[k]);
+    }
+    __syncthreads();
 }
 
 // EMIT = false: counts[(contig, strand)] = (#fragments, #residues).  EMIT = true: writes the records at recBase / aaBase.
@@ -77,7 +98,7 @@ __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char
                                                              const uint64_t *__restrict__ recBase, const uint64_t *__restrict__ aaBase, MbOrfRec *__restrict__ recs) {
     __shared__ unsigned char tile[MB_ORF_TILE + 8];
     __shared__ unsigned char comp[256];
-    __shared__ uint32_t sm[MB_ORF_THREADS / 32];
+    __shared__ uint32_t sm[3 * (MB_ORF_THREADS / 32)];
     comp[threadIdx.x] = tab->comp[threadIdx.x];
     for (uint32_t unit = blockIdx.x; unit < 2u * nContigs; unit += gridDim.x) {
         const uint32_t c = unit >> 1; const int s = (int)(unit & 1u);
@@ -102,12 +123,13 @@ __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char
                 if (stop) stopMask |= 1u << j;
                 if (stop || isLast) { termMask |= 1u << j; myLast[j % 3] = p + 1; }
             }
-            uint32_t prev[3], tot;
+            uint32_t prev[3] = {myLast[0], myLast[1], myLast[2]}, tot3[3];
+            orf_block_scan_max3(prev, sm, tot3);
 #pragma unroll
-            for (int f = 0; f < 3; f++) { prev[f] = max(orf_block_scan_max(myLast[f], sm, &tot), carryTerm[f]); carryTerm[f] = max(carryTerm[f], tot); }
+            for (int f = 0; f < 3; f++) { prev[f] = max(prev[f], carryTerm[f]); carryTerm[f] = max(carryTerm[f], tot3[f]); }
             // ---- fragments that end in my positions
             uint32_t myCnt = 0, myAa = 0;
-            uint32_t eFrom[4], eLen[4], eInfo[4];     // at most 4 terminators of one frame... up to 12 in total, but >= minLen apart per frame
+            uint32_t eFrom[6], eLen[6], eInfo[6];     // fragments of one frame end >= 3 * minLen nucleotides apart: with minLen >= 4 at most 2 per frame in 24 positions
             int ne = 0;
 #pragma unroll
             for (int j = 0; j < MB_ORF_PER_THREAD; j++) if ((termMask >> j) & 1u) {
@@ -116,14 +138,14 @@ __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char
                 const uint32_t from = prev[f] ? prev[f] - 1u + 3u : (uint32_t)f;
                 const uint32_t len = (p - from) / 3u + (stop ? 0u : 1u);
                 if (len >= minLen && len <= maxLen && len > 0) {
-                    if (ne < 4) { eFrom[ne] = from; eLen[ne] = len; eInfo[ne] = (prev[f] ? 0u : 1u) | (stop ? 0u : 2u) | ((uint32_t)j << 8); ne++; }
+                    if (ne < 6) { eFrom[ne] = from; eLen[ne] = len; eInfo[ne] = (prev[f] ? 0u : 1u) | (stop ? 0u : 2u) | ((uint32_t)j << 8); ne++; }
                     myCnt++; myAa += len;
                 }
                 prev[f] = p + 1;
             }
-            uint32_t totCnt, totAa;
-            const uint32_t rank = orf_block_scan_add(myCnt, sm, &totCnt);
-            const uint32_t aaRank = orf_block_scan_add(myAa, sm, &totAa);
+            uint32_t ranks[2] = {myCnt, myAa}, tots[2];
+            orf_block_scan_add<2>(ranks, sm, tots);
+            const uint32_t rank = ranks[0], aaRank = ranks[1], totCnt = tots[0], totAa = tots[1];
             if (EMIT) {
                 uint64_t a = aaBase[unit] + carryAa + aaRank;
                 for (int e = 0; e < ne; e++) {

@@ -2,7 +2,8 @@
 //
 // TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
 // Scalar CPU restatement of the reference's predictexons hot path:
-// MMseqs2 k-mer prefilter -> gapped Smith-Waterman -> MetaEuk exon-chaining DP.
+// MMseqs2 k-mer prefilter -> gapped Smith-Waterman -> MetaEuk exon-chaining DP, plus the two neighbouring steps of section 8f:
+// extractorfs + translatenucs (six-frame ORF fragments) before it and reduceredundancy after it.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
 // Parity: PINNED.  tests/test_oracle_golden.py checks every stage of this file against outputs of the
 // unmodified reference (tests/golden/*.json.gz, produced by tests/golden/make_golden.py).
