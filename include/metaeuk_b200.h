@@ -15,6 +15,9 @@
  *                        = Matcher::getSWResult per hit         M/src/alignment/Matcher.cpp:60-142
  *   mb200_chain          collectoptimalset per-contig loop      src/exonpredictor/collectoptimalset.cpp:273-418
  *   mb200_search         blastp.sh prefilter -> align           M/data/workflow/blastp.sh:70,85
+ *   mb200_predict_exons  predictexons.sh:40-82 (extractorfs, translatenucs, search, resultspercontig, collectoptimalset)
+ *                        with binary records handed from stage to stage instead of text DBs
+ *   mb200_index_save / mb200_index_load   the persisted index of `createindex` (M/src/prefiltering/PrefilteringIndexReader.cpp:60-330)
  *
  * Residues are the reference's numeric codes (Sequence::mapSequence): A C D E F G H I K L M N P Q R S T V W Y = 0..19, X = 20.
  * Target ids are LOCAL ids (rank in the target DB as the reference's DBReader enumerates it); dbKeys map them back.
@@ -72,6 +75,11 @@ typedef struct mb200_exon { uint32_t cand_idx; int32_t contig_start, contig_end,
 typedef struct mb200_call {
     uint32_t target_key; int32_t strand; int32_t total_bit_score; int32_t n_exons; uint32_t exon_begin; int32_t low_coord, high_coord, pad; double evalue;
 } mb200_call;
+typedef struct mb200_pexon {  /* one exon of a call = columns 8-19 of a dp_predictions line (PotentialExon::exonToBuffer, PredictionParser.h:97-163) */
+    uint32_t orf_key; int32_t bit_score; float seq_id_est;   /* seq_id_est / evalue as `align` computed them; the text columns derive from them */
+    int32_t t_start, t_end, t_len, contig_start, contig_end, nuc_len, frag_from, frag_to, pad;
+    double evalue;
+} mb200_pexon;
 typedef struct mb200_pred {   /* one call of collectoptimalset = Prediction::setByDPRes (PredictionParser.h:253-272) */
     uint32_t target_key; int32_t strand; uint32_t total_bit_score, n_exons, low_coord, high_coord;
     uint32_t exon_begin, pad;  /* exon keys of the call: exon_keys[exon_begin .. exon_begin + n_exons) */
@@ -95,6 +103,9 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     double ms_orf, ms_orf_host;       /* mb200_extract_orfs: kernels with the contigs resident (CUDA events) / whole call incl. H2D and D2H (wall clock) */
     uint64_t orf_nucleotides, orf_fragments, orf_residues;
     double ms_reduce;                 /* k_reduce (mb200_reduce_redundancy) */
+    /* mb200_predict_exons: sums over its contig batches (the ms_* and counter fields above are then sums too) */
+    double ms_join, ms_predict;       /* host join of alignments and fragments per contig / the whole call (wall clock) */
+    uint64_t pe_batches, pe_contigs, pe_fragments, pe_alignments, pe_calls, pe_exons;
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);
@@ -150,6 +161,20 @@ int mb200_extract_orfs(mb200_ctx *ctx, const char *nuc, const uint64_t *off, uin
 int mb200_queries_from_orfs(mb200_ctx *ctx);
 /* mb200_search on the resident query batch (mb200_queries_upload or mb200_queries_from_orfs); aln_off: caller buffer of n_queries + 1 */
 int mb200_search_resident(mb200_ctx *ctx, uint64_t *aln_off, const mb200_aln **alns);
+
+/* predictexons with the contigs as the only input and binary records between the stages (data/predictexons.sh:40-82):
+ * six-frame fragments (device) -> resident query batch -> prefilter -> gapped alignment -> join per contig (resultspercontig.cpp:64-196,
+ * as a binary join) -> exon chaining -> calls.  Contigs are processed in batches of about "predict_batch_nt" nucleotides (mb200_option_set;
+ * results do not depend on it).  Fragment keys (orf_key) count over the whole call in the reference's key order.  Target keys are the
+ * keys given to mb200_target_keys_set (default: local ids).  Calls of contig c = (*calls)[call_off[c] .. call_off[c+1]) in the order of the
+ * reference's dp_predictions entry; the exons of a call = (*exons)[exon_begin .. exon_begin + n_exons).  call_off: caller buffer of
+ * n_contigs + 1; *calls and *exons are owned by the context (valid until the next call on it). */
+int mb200_predict_exons(mb200_ctx *ctx, const char *nuc, const uint64_t *off, uint32_t n_contigs, int min_len, int max_len,
+                        uint64_t *call_off, const mb200_call **calls, const mb200_pexon **exons, uint64_t *n_exons);
+int mb200_target_keys_set(mb200_ctx *ctx, const uint32_t *keys, uint32_t n_targets);   /* DB keys of the targets in local-id order */
+/* one 19-column dp_predictions line (Prediction::predictionToBuffer, PredictionParser.h:368-396) from the binary records, with the
+ * digits the reference's text round trips leave; returns the length written (without the NUL) or MB200_E_ARG if cap is too small */
+int mb200_text_exon_line(const mb200_call *call, const mb200_pexon *exon, char *buf, size_t cap);
 
 /* reduceredundancy (src/exonpredictor/reduceredundancy.cpp:24-147,273-296) for a batch of contigs: calls of contig c =
  * preds[pred_off[c] .. pred_off[c+1]) in the order of the calledExons entry.  Per call: cluster representative (target key, low coordinate),

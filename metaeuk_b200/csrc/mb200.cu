@@ -24,6 +24,7 @@
 #include "chain_core.cuh"
 #include "reduce_core.cuh"
 #include "host_tables.h"
+#include "host_join.h"
 #include "prefilter_core.cuh"
 
 static thread_local std::string g_err;
@@ -165,6 +166,8 @@ struct mb200_ctx {
     DevBuf<MbOrfRec> dOrfRecs; DevBuf<char> dOrfAa; DevBuf<uint8_t> dOrfCodes; PinBuf<MbOrfRec> pOrfRecs; PinBuf<char> pOrfAa; uint64_t nOrfs = 0, nOrfAa = 0;
     PinBuf<mb200_hit> pFlatHits; PinBuf<uint32_t> pOff, pStatus; size_t nFlatHits = 0;
     bool haveAln = false;
+    // predictexons with binary hand-off
+    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20;
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -284,6 +287,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "prefilter_config") { if (value < 0 || value > 2) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense) or 2 (sparse)"); c->optPrefCfg = (int)value; }
     else if (n == "sw_kernel") { if (value < 1 || value > 3) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit) or 3 (packed, per-lane state machine)"); c->optSwKernel = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
+    else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
     return 0;
 }
@@ -966,22 +970,95 @@ int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, 
         // host epilogue: set e-value and --metaeuk-eval filter (collectoptimalset.cpp:323-330); compact per contig
         for (uint32_t ci = 0; ci < nContigs; ci++) {
             if (hCnt[ci] < 0) { rc = fail(MB200_E_ARG, "contig %u: illegal codon segment length", ci); break; }
-            const uint64_t b = candOff[ci]; uint32_t w = 0, we = 0;
-            for (int k = 0; k < hCnt[ci]; k++) {
-                MbCall cl = hCalls[2 * b + k];
-                const double l2 = log2(totalTargetResidues) + log2(2) - cl.totalBitScore; const double ev = pow(2, l2);
-                if (!(ev <= c->par.metaeuk_eval)) continue;
-                const uint32_t eb = cl.exonBegin;
-                cl.evalue = ev; cl.exonBegin = (uint32_t)(b + we);
-                for (int x = 0; x < cl.nExons; x++) { MbExon ex = hEx[b + eb + x]; memcpy(&exons[b + we + x], &ex, sizeof(ex)); }
-                we += cl.nExons;
-                memcpy(&calls[2 * b + w], &cl, sizeof(cl)); w++;
-            }
-            callCount[ci] = w;
+            const uint64_t b = candOff[ci];
+            callCount[ci] = mb200::finish_calls(reinterpret_cast<const mb200_call *>(&hCalls[2 * b]), (uint32_t)hCnt[ci], reinterpret_cast<const mb200_exon *>(&hEx[b]), b, totalTargetResidues,
+                                                c->par.metaeuk_eval, calls + 2 * b, exons + b);
         }
     } while (0);
     dC.release(); dOff.release(); dPE.release(); dOp.release(); dOm.release(); dRows.release(); dCalls.release(); dEx.release(); dCallCnt.release(); dExCnt.release();
     return rc;
+}
+
+// ---- predictexons from contigs, binary records between the stages -----------------------------------------
+int mb200_target_keys_set(mb200_ctx *c, const uint32_t *keys, uint32_t nT) {
+    if (!c || (!keys && nT)) return fail(MB200_E_ARG, "null argument");
+    if (c->haveIndex && nT != c->nT && nT != 0) return fail(MB200_E_ARG, "%u keys for %u targets", nT, c->nT);
+    c->tKeys.assign(keys, keys + nT);
+    return 0;
+}
+
+int mb200_text_exon_line(const mb200_call *call, const mb200_pexon *exon, char *buf, size_t cap) {
+    if (!call || !exon || !buf) return fail(MB200_E_ARG, "null argument");
+    const std::string l = mb200::text_exon_line(*call, *exon);
+    if (l.size() + 1 > cap) return fail(MB200_E_ARG, "buffer too small for one exon line (%zu bytes needed)", l.size() + 1);
+    memcpy(buf, l.c_str(), l.size() + 1);
+    return (int)l.size();
+}
+
+int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen,
+                        uint64_t *callOff, const mb200_call **calls, const mb200_pexon **exons, uint64_t *nExons) {
+    if (!c || !nuc || !off || !callOff || !calls || !exons || !nExons) return fail(MB200_E_ARG, "null argument");
+    if (!c->haveIndex || !c->haveSim3) return fail(MB200_E_STATE, "index / matrices not set");
+    if (!c->tKeys.empty() && c->tKeys.size() != c->nT) return fail(MB200_E_STATE, "mb200_target_keys_set: %zu keys for %u targets", c->tKeys.size(), c->nT);
+    const auto t0 = std::chrono::steady_clock::now();
+    c->peCalls.clear(); c->peExons.clear(); callOff[0] = 0; *calls = nullptr; *exons = nullptr; *nExons = 0;
+    mb200_stats acc; memset(&acc, 0, sizeof(acc));
+    const uint32_t launches0 = c->st.launches;
+    uint64_t orfBase = 0;
+    std::vector<mb200_cand> cands; std::vector<uint64_t> candOff, candAln; std::vector<mb200_call> bCalls; std::vector<mb200_exon> bExons; std::vector<uint32_t> bCnt;
+    for (uint32_t b0 = 0; b0 < nContigs;) {
+        uint32_t b1 = b0 + 1;
+        while (b1 < nContigs && off[b1 + 1] - off[b0] <= c->optBatchNt) b1++;
+        const uint32_t nb = b1 - b0;
+        uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+        TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa));
+        TRY(mb200_queries_from_orfs(c));
+        TRY(mb200_prefilter_resident(c));
+        TRY(align_pipeline(c));
+        std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
+        TRY(collect_accepted(c, tids));
+        const auto tj = std::chrono::steady_clock::now();
+        if (mb200::join_by_contig(orfs, n, nb, orfBase, c->hAlnOff.data(), c->hAlns.data(), c->tKeys.empty() ? nullptr : c->tKeys.data(), c->hToff.data(), cands, candOff, candAln))
+            return fail(MB200_E_LIMIT, "more than 2^32 fragments in one mb200_predict_exons call");
+        acc.ms_join += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count();
+        const uint64_t nc = candOff[nb];
+        bCalls.resize(std::max<uint64_t>(1, 2 * nc)); bExons.resize(std::max<uint64_t>(1, nc)); bCnt.assign(nb, 0);
+        c->st.ms_chain = 0;
+        if (nc) TRY(mb200_chain(c, cands.data(), candOff.data(), nb, c->totalRes, bCalls.data(), bCnt.data(), bExons.data()));
+        for (uint32_t ci = 0; ci < nb; ci++) {
+            const uint64_t base = candOff[ci];
+            for (uint32_t k = 0; k < bCnt[ci]; k++) {
+                mb200_call cl = bCalls[2 * base + k]; const uint32_t eb = cl.exon_begin;
+                if (c->peExons.size() + (size_t)cl.n_exons >= (1ull << 32)) return fail(MB200_E_LIMIT, "more than 2^32 exons in one mb200_predict_exons call");
+                cl.exon_begin = (uint32_t)c->peExons.size();
+                for (int x = 0; x < cl.n_exons; x++) {
+                    const mb200_exon &ex = bExons[eb + x]; const mb200_cand &k2 = cands[base + ex.cand_idx]; const mb200_aln &al = c->hAlns[candAln[base + ex.cand_idx]];
+                    mb200_pexon pe; memset(&pe, 0, sizeof(pe));
+                    pe.orf_key = k2.orf_key; pe.bit_score = k2.bit_score; pe.seq_id_est = al.seq_id_est; pe.t_start = k2.t_start; pe.t_end = k2.t_end; pe.t_len = k2.t_len;
+                    pe.contig_start = ex.contig_start; pe.contig_end = ex.contig_end; pe.nuc_len = ex.nuc_len; pe.frag_from = k2.frag_from; pe.frag_to = k2.frag_to; pe.evalue = al.evalue;
+                    c->peExons.push_back(pe);
+                }
+                c->peCalls.push_back(cl);
+            }
+            callOff[b0 + ci + 1] = c->peCalls.size();
+        }
+        // sums over the batches
+        const mb200_stats &s = c->st;
+        acc.kmers += s.kmers; acc.lookups += s.lookups; acc.db_matches += s.db_matches; acc.double_hits += s.double_hits; acc.diag_cells += s.diag_cells; acc.pref_results += s.pref_results;
+        acc.sw_pairs += s.sw_pairs; acc.sw_cells_fwd += s.sw_cells_fwd; acc.sw_cells_rev += s.sw_cells_rev; acc.sw_target_bytes += s.sw_target_bytes;
+        acc.query_residues += s.query_residues; acc.n_queries += s.n_queries;
+        acc.ms_prep += s.ms_prep; acc.ms_prefilter += s.ms_prefilter; acc.ms_sw_fwd += s.ms_sw_fwd; acc.ms_sw_rev += s.ms_sw_rev; acc.ms_chain += s.ms_chain; acc.ms_h2d += s.ms_h2d;
+        acc.ms_orf += s.ms_orf; acc.ms_orf_host += s.ms_orf_host; acc.orf_nucleotides += s.orf_nucleotides; acc.orf_fragments += s.orf_fragments; acc.orf_residues += s.orf_residues;
+        for (int i = 0; i < 16; i++) acc.pref_phase_cycles[i] += s.pref_phase_cycles[i];
+        acc.pe_batches++; acc.pe_contigs += nb; acc.pe_fragments += n; acc.pe_alignments += c->hAlns.size();
+        orfBase += n; b0 = b1;
+    }
+    acc.pe_calls = c->peCalls.size(); acc.pe_exons = c->peExons.size();
+    acc.launches = c->st.launches; acc.ms_reduce = c->st.ms_reduce; acc.ms_d2h = c->st.ms_d2h; acc.ms_host = c->st.ms_host;
+    acc.ms_predict = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->st = acc; (void)launches0;
+    *calls = c->peCalls.empty() ? nullptr : c->peCalls.data(); *exons = c->peExons.empty() ? nullptr : c->peExons.data(); *nExons = c->peExons.size();
+    return 0;
 }
 
 int mb200_stats_get(mb200_ctx *c, mb200_stats *out) { if (!c || !out) return fail(MB200_E_ARG, "null argument"); *out = c->st; return 0; }

@@ -107,7 +107,7 @@ static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdTo
 static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
 
 struct Opt {
-    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0;
+    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0;
 };
 static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
     Opt o; mb200_params_default(&o.p);
@@ -131,6 +131,8 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--set-gap-extend") o.p.set_gap_extend = atoi(val().c_str());
         else if (a == "--device") o.device = atoi(val().c_str());
         else if (a == "--overlap") o.overlap = atoi(val().c_str());
+        else if (a == "--text-stages") o.textStages = atoi(val().c_str());
+        else if (a == "--batch-nt") o.batchNt = atoll(val().c_str());
         else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
         else pos.push_back(a);
     }
@@ -294,25 +296,42 @@ int main(int argc, char **argv) {
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return contigs.keys[a] < contigs.keys[b]; });
         std::string nuc; std::vector<uint64_t> off(1, 0);
         for (size_t id : order) { const size_t n = contigs.len[id] >= 2 ? contigs.len[id] - 2 : 0; nuc.append(contigs.entry(id), n); off.push_back(nuc.size()); }
-        uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
-        MB(mb200_extract_orfs(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
-        Db hdr; hdr.dbtype = 12; char buf[96];
-        for (uint64_t i = 0; i < n; i++) {          // in-memory nucl_6f_h (Orf::writeOrfHeader, Orf.cpp:440-457)
-            const mb200_orf &r = orfs[i]; const long long d = (long long)r.from - (long long)r.to;
-            int w = snprintf(buf, sizeof(buf), "%u\t%u%c%lld", contigs.keys[order[r.contig]], r.from, r.from < r.to ? '+' : '-', d < 0 ? -d : d);
-            if (r.flags & 3u) w += snprintf(buf + w, sizeof(buf) - w, "\t%u", r.flags & 3u);
-            buf[w++] = '\n'; buf[w++] = '\0';
-            hdr.byKey[(uint32_t)i] = hdr.keys.size(); hdr.keys.push_back((uint32_t)i); hdr.off.push_back(hdr.data.size()); hdr.len.push_back(w);
-            hdr.data.insert(hdr.data.end(), buf, buf + w);
+        if (o.textStages) {
+            // the same chain with the reference's text DBs between the stages (in memory), for parity checks of the binary hand-off
+            uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+            MB(mb200_extract_orfs(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
+            Db hdr; hdr.dbtype = 12; char buf[96];
+            for (uint64_t i = 0; i < n; i++) {          // in-memory nucl_6f_h (Orf::writeOrfHeader, Orf.cpp:440-457)
+                const mb200_orf &r = orfs[i]; const long long d = (long long)r.from - (long long)r.to;
+                int w = snprintf(buf, sizeof(buf), "%u\t%u%c%lld", contigs.keys[order[r.contig]], r.from, r.from < r.to ? '+' : '-', d < 0 ? -d : d);
+                if (r.flags & 3u) w += snprintf(buf + w, sizeof(buf) - w, "\t%u", r.flags & 3u);
+                buf[w++] = '\n'; buf[w++] = '\0';
+                hdr.byKey[(uint32_t)i] = hdr.keys.size(); hdr.keys.push_back((uint32_t)i); hdr.off.push_back(hdr.data.size()); hdr.len.push_back(w);
+                hdr.data.insert(hdr.data.end(), buf, buf + w);
+            }
+            std::vector<uint32_t> qlen(n); for (uint64_t i = 0; i < n; i++) qlen[i] = orfs[i].aa_len;   // (the record buffer is reused by later calls)
+            MB(mb200_queries_from_orfs(s.ctx));
+            std::vector<uint64_t> aoff(n + 1); const mb200_aln *alns = nullptr;
+            MB(mb200_search_resident(s.ctx, aoff.data(), &alns));
+            std::map<uint32_t, std::string> aln;
+            for (uint64_t i = 0; i < n; i++) aln[(uint32_t)i] = alnEntry(s, std::vector<mb200_aln>(alns + aoff[i], alns + aoff[i + 1]), qlen[i]);
+            auto byc = byContig(contigs, hdr, aln);
+            writeDb(pos[2], 12, chainAll(s.ctx, byc, s.t.res.size()));
+        } else {
+            // binary records from stage to stage (mb200_predict_exons); only the final dp_predictions entries are printed
+            MB(mb200_target_keys_set(s.ctx, s.tdb.keys.data(), (uint32_t)s.tdb.keys.size()));
+            if (o.batchNt > 0) MB(mb200_option_set(s.ctx, "predict_batch_nt", o.batchNt));
+            std::vector<uint64_t> coff(order.size() + 1); const mb200_call *calls = nullptr; const mb200_pexon *ex = nullptr; uint64_t nEx = 0;
+            MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, coff.data(), &calls, &ex, &nEx));
+            std::map<uint32_t, std::string> out; char line[512];
+            for (size_t ci = 0; ci < order.size(); ci++) {
+                std::string e;
+                for (uint64_t k = coff[ci]; k < coff[ci + 1]; k++)
+                    for (int x = 0; x < calls[k].n_exons; x++) { if (mb200_text_exon_line(&calls[k], &ex[calls[k].exon_begin + x], line, sizeof(line)) < 0) DIE("%s", mb200_last_error()); e += line; }
+                out[contigs.keys[order[ci]]] = e;
+            }
+            writeDb(pos[2], 12, out);
         }
-        std::vector<uint32_t> qlen(n); for (uint64_t i = 0; i < n; i++) qlen[i] = orfs[i].aa_len;   // (the record buffer is reused by later calls)
-        MB(mb200_queries_from_orfs(s.ctx));
-        std::vector<uint64_t> aoff(n + 1); const mb200_aln *alns = nullptr;
-        MB(mb200_search_resident(s.ctx, aoff.data(), &alns));
-        std::map<uint32_t, std::string> aln;
-        for (uint64_t i = 0; i < n; i++) aln[(uint32_t)i] = alnEntry(s, std::vector<mb200_aln>(alns + aoff[i], alns + aoff[i + 1]), qlen[i]);
-        auto byc = byContig(contigs, hdr, aln);
-        writeDb(pos[2], 12, chainAll(s.ctx, byc, s.t.res.size()));
     } else if (cmd == "gpupredictexons") {
         if (pos.size() != 5) DIE("gpupredictexons <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>   |   gpupredictexons <contigsDB> <targetDB> <predDB>");
         Session s; s.open(o, pos[3]); Db contigs = openDb(pos[0]), qdb = openDb(pos[1]), hdr = openDb(pos[2] + "_h"); Seqs q = encodeDb(qdb, false);

@@ -35,7 +35,11 @@ class Stats(C.Structure):
                                            "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
                [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
                [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16), ("ms_orf", C.c_double), ("ms_orf_host", C.c_double),
-                ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64), ("ms_reduce", C.c_double)]
+                ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64), ("ms_reduce", C.c_double),
+                ("ms_join", C.c_double), ("ms_predict", C.c_double)] + \
+               [(n, C.c_uint64) for n in ("pe_batches", "pe_contigs", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons")]
+PEXON_DTYPE = np.dtype([("orf_key", "<u4"), ("bit_score", "<i4"), ("seq_id_est", "<f4"), ("t_start", "<i4"), ("t_end", "<i4"), ("t_len", "<i4"),
+                        ("contig_start", "<i4"), ("contig_end", "<i4"), ("nuc_len", "<i4"), ("frag_from", "<i4"), ("frag_to", "<i4"), ("pad", "<i4"), ("evalue", "<f8")])
 PRED_DTYPE = np.dtype([("target_key", "<u4"), ("strand", "<i4"), ("total_bit_score", "<u4"), ("n_exons", "<u4"), ("low_coord", "<u4"), ("high_coord", "<u4"),
                        ("exon_begin", "<u4"), ("pad", "<u4"), ("evalue", "<f8")])
 PRED_OUT_DTYPE = np.dtype([("cluster_id", "<u4"), ("cluster_low_coord", "<u4"), ("no_overlap_cluster_id", "<u4"), ("is_rep", "<u4")])
@@ -52,8 +56,8 @@ def _gxx():
 
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "submat_data.h")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp", "host_join.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "host_join.h", "submat_data.h")] + \
         [os.path.join(ROOT, "include", "metaeuk_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -232,6 +236,29 @@ class Context:
         calls = np.zeros(max(1, 2 * n), dtype=CALL_DTYPE); exons = np.zeros(max(1, n), dtype=EXON_DTYPE); cnt = np.zeros(max(1, nc), np.uint32)
         self._check(self.L.mb200_chain(self.h, _p(cands), _p(cand_off), C.c_uint32(nc), C.c_uint64(total_target_residues), _p(calls), _p(cnt), _p(exons)))
         return calls, cnt[:nc], exons
+
+    # ---- predictexons from contigs, binary records between the stages ----
+    def target_keys_set(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        self._check(self.L.mb200_target_keys_set(self.h, _p(keys), C.c_uint32(len(keys))))
+
+    def predict_exons(self, nuc, off, min_len=15, max_len=32734, copy=True):
+        """nuc: concatenated ASCII nucleotides, off: uint64[n_contigs+1] -> (call_off uint64[n_contigs+1], calls CALL_DTYPE, exons PEXON_DTYPE)"""
+        nuc = np.ascontiguousarray(np.frombuffer(nuc, dtype=np.uint8) if isinstance(nuc, (bytes, bytearray)) else nuc, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        nc = len(off) - 1
+        call_off = np.zeros(nc + 1, np.uint64); pc = C.c_void_p(); pe = C.c_void_p(); ne = C.c_uint64(0)
+        self._check(self.L.mb200_predict_exons(self.h, _p(nuc if len(nuc) else np.zeros(1, np.uint8)), _p(off), C.c_uint32(nc), int(min_len), int(max_len),
+                                               _p(call_off), C.byref(pc), C.byref(pe), C.byref(ne)))
+        return call_off, self._view(pc, int(call_off[-1]), CALL_DTYPE, copy), self._view(pe, int(ne.value), PEXON_DTYPE, copy)
+
+    def text_exon_line(self, call, exon):
+        buf = C.create_string_buffer(512)
+        c = np.ascontiguousarray(call, CALL_DTYPE).reshape(1); e = np.ascontiguousarray(exon, PEXON_DTYPE).reshape(1)
+        n = self.L.mb200_text_exon_line(_p(c), _p(e), buf, C.c_size_t(512))
+        if n < 0:
+            self._check(n)
+        return buf.raw[:n].decode()
 
     # ---- reduceredundancy ----
     def reduce_redundancy(self, preds, pred_off, exon_keys):

@@ -148,6 +148,26 @@ def extractorfs(ctx, contigs, min_len=15, max_len=32734):
     return queries, headers
 
 
+def predictexons_contigs(ctx, contigs, tdb, min_len=15, max_len=32734):
+    """predictexons.sh:40-82 with the contigs as the only input and no text DB between the stages:
+    contigs [(key, nucleotides)] -> {contigKey: dp_predictions entry} (19 columns per exon, Prediction::predictionToBuffer).
+    Fragment keys are the ranks extractorfs would assign (the key order of nucl_6f / aa_6f)."""
+    seq = "".join(s for _, s in contigs).encode()
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    if contigs:
+        off[1:] = np.cumsum([len(s) for _, s in contigs], dtype=np.uint64)
+    ctx.target_keys_set(np.array(tdb.keys, np.uint32))
+    call_off, calls, exons = ctx.predict_exons(seq, off, min_len, max_len)
+    out = {}
+    for ci, (k, _) in enumerate(contigs):
+        s = ""
+        for cl in calls[int(call_off[ci]):int(call_off[ci + 1])]:
+            for e in exons[int(cl["exon_begin"]):int(cl["exon_begin"]) + int(cl["n_exons"])]:
+                s += ctx.text_exon_line(cl, e)
+        out[k] = s
+    return out
+
+
 def _reprint_exon(cols):
     """PotentialExon::setByDPRes -> exonToBuffer (PredictionParser.h:66-150): the identity is parsed to double, narrowed to float and
     re-truncated to three digits; the E-value goes through %.3E again; every other column is an integer"""

@@ -9,6 +9,8 @@
 #include "../../metaeuk_b200/csrc/host_tables.h"
 #include "../../metaeuk_b200/csrc/prefilter_core.cuh"
 #include "../../metaeuk_b200/csrc/reduce_core.cuh"
+#include "../../metaeuk_b200/csrc/chain_core.cuh"
+#include "../../metaeuk_b200/csrc/host_join.h"
 
 template <class SH>
 static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
@@ -94,5 +96,33 @@ int emu_reduce(const MbPred *P, uint32_t n, const uint32_t *exonKeys, MbPredOut 
     *nRep = mb_reduce_contig(P, n, exonKeys, out, memberOrder, repOrder, flag.data(), tmp.data());
     return 0;
 }
+
+// ---- binary hand-off between the stages (host_join.cpp) and the chaining kernel logic (chain_core.cuh) ----
+// cands / candAln: caller buffers of alnOff[nOrfs] entries, candOff of nContigs + 1
+int emu_join(const mb200_orf *orfs, uint64_t nOrfs, uint32_t nContigs, uint64_t orfKeyBase, const uint64_t *alnOff, const mb200_aln *alns, const uint32_t *tKeys,
+             const uint64_t *tOff, mb200_cand *cands, uint64_t *candOff, uint64_t *candAln) {
+    std::vector<mb200_cand> c; std::vector<uint64_t> co, ca;
+    const int rc = mb200::join_by_contig(orfs, nOrfs, nContigs, orfKeyBase, alnOff, alns, tKeys, tOff, c, co, ca);
+    if (rc) return rc;
+    memcpy(candOff, co.data(), co.size() * 8);
+    if (!c.empty()) { memcpy(cands, c.data(), c.size() * sizeof(mb200_cand)); memcpy(candAln, ca.data(), ca.size() * 8); }
+    return 0;
+}
+
+// one contig through mb_chain_contig (what one thread of k_chain runs) + the host epilogue; calls: 2n entries, exons: n entries
+int emu_chain(const mb200_cand *cands, uint32_t n, int minIntron, int maxIntron, int minExonAa, int maxOverlap, int gapOpen, int gapExtend, int maxSets, double tcov,
+              uint64_t totalTargetResidues, double evalThr, mb200_call *calls, mb200_exon *exons) {
+    static_assert(sizeof(MbCand) == sizeof(mb200_cand) && sizeof(MbCall) == sizeof(mb200_call) && sizeof(MbExon) == sizeof(mb200_exon), "ABI structs");
+    MbChainParams P; P.minIntron = minIntron; P.maxIntron = maxIntron; P.minExonAa = minExonAa; P.maxOverlap = maxOverlap; P.gapOpen = gapOpen; P.gapExtend = gapExtend;
+    P.maxSets = maxSets; P.tcov = tcov;
+    std::vector<MbPE> pe(n + 1); std::vector<int32_t> op(n + 1), om(n + 1); std::vector<MbRow> rows(n + 1); std::vector<MbCall> cl(2 * n + 2); std::vector<MbExon> ex(n + 1);
+    uint32_t nEx = 0;
+    const int nc = mb_chain_contig(reinterpret_cast<const MbCand *>(cands), n, P, pe.data(), op.data(), om.data(), rows.data(), cl.data(), ex.data(), &nEx);
+    if (nc < 0) return nc;
+    return (int)mb200::finish_calls(reinterpret_cast<const mb200_call *>(cl.data()), (uint32_t)nc, reinterpret_cast<const mb200_exon *>(ex.data()), 0, totalTargetResidues, evalThr, calls, exons);
+}
+
+int emu_text_bycontig_line(const mb200_cand *k, const mb200_aln *a, uint32_t qLen, uint64_t contigLen, char *buf) { const std::string l = mb200::text_bycontig_line(*k, *a, qLen, contigLen); memcpy(buf, l.c_str(), l.size() + 1); return (int)l.size(); }
+int emu_text_exon_line(const mb200_call *c, const mb200_pexon *e, char *buf) { const std::string l = mb200::text_exon_line(*c, *e); memcpy(buf, l.c_str(), l.size() + 1); return (int)l.size(); }
 
 }  // extern "C"

@@ -219,6 +219,89 @@ def test_contigs_to_exon_calls_without_host_round_trip():
     ctx.close()
 
 
+@pytest.mark.parametrize("batch_nt", [0, 9000, 30000], ids=["one-batch", "contig-per-batch", "three-per-batch"])
+@pytest.mark.parametrize("name", CONTIG)
+def test_predict_exons_binary_handoff_golden(name, batch_nt):
+    """mb200_predict_exons: contigs in, call/exon records out, no text between the stages; printed with the reference's
+    rules the records must be the reference's dp_predictions DB, whatever the batching"""
+    c = reflib.load_case(name)
+    ctx, tdb = ctx_for(c, max_exon_sets=c["max_exon_sets"])
+    if batch_nt:
+        ctx.option_set("predict_batch_nt", batch_nt)
+    contigs = [tuple(x) for x in c["contigs"]]
+    dp = M.predictexons_contigs(ctx, contigs, tdb)
+    assert strkeys(dp) == c["dp"]
+    st = ctx.stats()
+    assert st["pe_contigs"] == len(contigs) and st["pe_fragments"] == len(c["queries"])
+    assert st["pe_batches"] == {0: 1, 9000: len(contigs), 30000: (len(contigs) + 2) // 3}[batch_nt]
+    assert st["pe_alignments"] == sum(v.count("\n") for v in c["aln"].values())
+    assert st["pe_exons"] == sum(v.count("\n") for v in c["dp"].values())
+    ctx.close()
+
+
+def planted_contigs(seed, prots, n_contigs, length):
+    """SURVEY 8d contig generator at test size: random ACGT with planted genes = mutated proteins back-translated, split into 1-4 exons,
+    introns of 40-600 nt, half of them reverse-complemented"""
+    rng = random.Random(seed)
+    codon = {"A": "GCT", "C": "TGT", "D": "GAT", "E": "GAA", "F": "TTT", "G": "GGT", "H": "CAT", "I": "ATT", "K": "AAA", "L": "CTG", "M": "ATG", "N": "AAT",
+             "P": "CCT", "Q": "CAA", "R": "CGT", "S": "TCT", "T": "ACT", "V": "GTT", "W": "TGG", "Y": "TAT"}
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    out = []
+    for ci in range(n_contigs):
+        parts, total = [], 0
+        while total < length:
+            gap = "".join(rng.choice("ACGT") for _ in range(rng.randrange(300, 1500)))
+            parts.append(gap); total += len(gap)
+            if rng.random() < 0.7:
+                p = rng.choice(prots)
+                rate = rng.choice([0.05, 0.2, 0.4])
+                p = "".join(rng.choice(AA) if rng.random() < rate else ch for ch in p)
+                nex = rng.randrange(1, 5)
+                cuts = sorted(rng.sample(range(20, max(21, len(p) - 20)), nex - 1)) if len(p) > 60 and nex > 1 else []
+                gene = ""
+                for a, b in zip([0] + cuts, cuts + [len(p)]):
+                    if gene:
+                        gene += "GT" + "".join(rng.choice("ACGT") for _ in range(rng.randrange(40, 600))) + "AG"
+                    gene += "".join(codon[ch] for ch in p[a:b])
+                if rng.random() < 0.5:
+                    gene = "".join(comp[ch] for ch in reversed(gene))
+                parts.append(gene); total += len(gene)
+        out.append((ci, "".join(parts)[:length]))
+    return out
+
+
+def test_predict_exons_matches_oracle_stage_by_stage_on_planted_genes():
+    """contigs with planted multi-exon genes on both strands, larger than the golden cases: the oracle's stages (ORF extraction, prefilter,
+    alignment, exon chaining) composed through the reference's text formats must equal the device pipeline's binary hand-off"""
+    prots, _ = synth(99, 300, 0)
+    contigs = planted_contigs(5, prots, 10, 30000)
+    tdb = M.TargetDB(list(enumerate(prots)))
+    ctx = M.make_context(tdb, max_exon_sets=2)
+    ctx.option_set("predict_batch_nt", 100000)
+    got = M.predictexons_contigs(ctx, contigs, tdb)
+    hdr, seqs = reflib.oracle_extract_orfs(contigs)
+    o = reflib.Oracle(); o.set_params(); o.set_targets(prots, prots)
+    frags = [seqs[i] for i in range(len(seqs))]
+    res, _ = o.prefilter(frags)
+    alns, _ = o.align(frags, [[t for t, _, _ in h] for h in res])
+    keys = list(range(len(prots))); tlens = [len(p) for p in prots]
+    aln_txt = {i: "".join(reflib.fmt_aln(a, keys, len(frags[i]), tlens) for a in reflib.sort_alns([a for a in al if a["passed"] == 1], keys, tlens)) for i, al in enumerate(alns)}
+    byc = M.resultspercontig(aln_txt, hdr, {k: len(s) for k, s in contigs})
+    want = {}
+    for ck, text in byc.items():
+        cands = []
+        for l in text.splitlines():
+            w = l.split("\t")
+            cands.append(dict(targetKey=int(w[0]), bitScore=int(w[1]), qStart=int(w[4]), qEnd=int(w[5]), tStart=int(w[7]), tEnd=int(w[8]), tLen=int(w[9]), orfKey=int(w[10]),
+                              fragFrom=int(w[17]), fragTo=int(w[18]), seqIdText=w[2], evalText=w[3]))
+        want[ck] = reflib.fmt_dp(o.chain(cands, tdb.total_residues, max_sets=2), cands)
+    assert sum(v.count("\n") for v in want.values()) > 20, "the planted genes must produce calls"
+    assert any(int(l.split("\t")[4]) > 1 for v in want.values() for l in v.splitlines()), "multi-exon calls expected"
+    assert got == want
+    o.close(); ctx.close()
+
+
 def test_cli_reduceredundancy_on_database_files(tmp_path):
     import os
     import subprocess
@@ -347,3 +430,8 @@ def test_cli_modules_on_database_files(tmp_path):
     # ... and the whole chain with the contigs as the only input (fragments never leave the GPU between extraction and search)
     subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp3", "--max-exon-sets", str(c["max_exon_sets"])] + common)
     assert read_db(d + "/dp3") == c["dp"]
+    # same, in batches of about 20 kb of contigs, and with the reference's text DBs between the stages instead of the binary records
+    subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp4", "--max-exon-sets", str(c["max_exon_sets"]), "--batch-nt", "20000"] + common)
+    assert read_db(d + "/dp4") == c["dp"]
+    subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp5", "--max-exon-sets", str(c["max_exon_sets"]), "--text-stages", "1"] + common)
+    assert read_db(d + "/dp5") == c["dp"]

@@ -104,3 +104,102 @@ def test_reduceredundancy_kernel_logic_matches_reference(emu):
         assert reflib.fmt_grouped(preds, outs, [int(x) for x in ro[:nrep.value]]) == c["grouped"][k], k
         assert reflib.fmt_grouped(preds, outs, [int(x) for x in ro[:nrep.value]], allow_overlaps=True) == c["grouped_overlap_allowed"][k], k
         assert reflib.fmt_clusters(preds, outs, [int(x) for x in mo[:n]]) == c["clusters"][k], k
+
+
+# ---- binary hand-off between the stages and the chaining kernel logic ------------------------------------
+class _Orf(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("frm", C.c_uint32), ("to", C.c_uint32), ("flags", C.c_uint32), ("aa_off", C.c_uint64), ("aa_len", C.c_uint32), ("strand_from", C.c_uint32)]
+
+
+class _Aln(C.Structure):
+    _fields_ = [("seq_id", C.c_uint32), ("raw_score", C.c_int32), ("bit_score", C.c_int32), ("q_start", C.c_int32), ("q_end", C.c_int32), ("db_start", C.c_int32),
+                ("db_end", C.c_int32), ("aln_len", C.c_int32), ("passed", C.c_int32), ("seq_id_est", C.c_float), ("q_cov", C.c_float), ("db_cov", C.c_float), ("evalue", C.c_double)]
+
+
+class _PExon(C.Structure):
+    _fields_ = [("orf_key", C.c_uint32), ("bit_score", C.c_int32), ("seq_id_est", C.c_float), ("t_start", C.c_int32), ("t_end", C.c_int32), ("t_len", C.c_int32),
+                ("contig_start", C.c_int32), ("contig_end", C.c_int32), ("nuc_len", C.c_int32), ("frag_from", C.c_int32), ("frag_to", C.c_int32), ("pad", C.c_int32),
+                ("evalue", C.c_double)]
+
+
+@pytest.mark.parametrize("key_stride", [1, 7], ids=["keys=ids", "keys!=ids"])
+@pytest.mark.parametrize("name", ["contigs_small", "contigs_sets"])
+def test_binary_handoff_and_chain_logic_match_reference_text(emu, name, key_stride):
+    """accepted alignments (binary) + fragment records -> join_by_contig -> mb_chain_contig -> call/exon records must print to the
+    reference's search_res_by_contig and dp_predictions entries byte for byte (the product's host_join.cpp + chain_core.cuh on the CPU).
+    With key_stride 7 the target DB keys differ from the local ids and their order is reversed, so the (key, ORF) ordering is exercised."""
+    c = reflib.load_case(name)
+    nT = len(c["targets"])
+    keyof = lambda t: t if key_stride == 1 else (nT - 1 - t) * key_stride + 3      # noqa: E731  (local id -> DB key)
+    rekey = {k: keyof(i) for i, (k, _) in enumerate(c["targets"])}
+    local = {k: i for i, (k, _) in enumerate(c["targets"])}
+    tkeys = np.array([keyof(i) for i in range(nT)], np.uint32)
+    toff = np.zeros(nT + 1, np.uint64); toff[1:] = np.cumsum([len(s) for _, s in c["targets"]])
+    contig_keys = [k for k, _ in c["contigs"]]
+    cidx = {k: i for i, k in enumerate(contig_keys)}
+    orf_keys = sorted(int(k) for k in c["orf_headers"])
+    assert orf_keys == list(range(len(orf_keys)))
+    n = len(orf_keys)
+    orfs = (_Orf * n)(); qlen = {}
+    for k, s in c["queries"]:
+        qlen[int(k)] = len(s)
+    aln_rows = []; aln_off = np.zeros(n + 1, np.uint64)
+    for i in orf_keys:
+        ck, frm, to = reflib.parse_orf_header(c["orf_headers"][str(i)])
+        orfs[i].contig = cidx[ck]; orfs[i].frm = frm; orfs[i].to = to; orfs[i].aa_len = qlen[i]
+        for line in c["aln"].get(str(i), "").splitlines():
+            w = line.split("\t")
+            assert int(w[6]) == qlen[i]
+            aln_rows.append(w)
+        aln_off[i + 1] = len(aln_rows)
+    alns = (_Aln * max(1, len(aln_rows)))()
+    for a, w in zip(alns, aln_rows):
+        a.seq_id = local[int(w[0])]; a.bit_score = int(w[1]); a.q_start = int(w[4]); a.q_end = int(w[5]); a.db_start = int(w[7]); a.db_end = int(w[8]); a.passed = 1
+        a.seq_id_est = 1.0 if w[2] == "1.00" else (int(w[2][2:]) + 0.5) / 1000.0      # any float the `align` stage prints as w[2]
+        a.evalue = float(w[3])
+        assert int(w[9]) == int(toff[a.seq_id + 1] - toff[a.seq_id])
+    ncand = len(aln_rows)
+    cands = (reflib.Cand * max(1, ncand))(); cand_off = np.zeros(len(contig_keys) + 1, np.uint64); cand_aln = np.zeros(max(1, ncand), np.uint64)
+    p = reflib._p
+    assert emu.emu_join(orfs, C.c_uint64(n), C.c_uint32(len(contig_keys)), C.c_uint64(0), p(aln_off, C.c_uint64), alns, p(tkeys, C.c_uint32), p(toff, C.c_uint64),
+                        cands, p(cand_off, C.c_uint64), p(cand_aln, C.c_uint64)) == 0
+    assert int(cand_off[-1]) == ncand
+
+    def rekey_lines(text, cols, resort):
+        """golden text with the target keys replaced; entries are ordered by (target key, ...) so re-sort stably by the new key"""
+        rows = [l.split("\t") for l in text.splitlines()]
+        for w in rows:
+            for col in cols:
+                w[col] = str(rekey[int(w[col])])
+        if resort and key_stride != 1:
+            rows.sort(key=lambda w: int(w[0]))
+        return "".join("\t".join(w) + "\n" for w in rows)
+
+    buf = C.create_string_buffer(1024)
+    total_res = int(toff[-1])
+    for ci, ck in enumerate(contig_keys):
+        b, e = int(cand_off[ci]), int(cand_off[ci + 1])
+        got = ""
+        for k in range(b, e):
+            nb = emu.emu_text_bycontig_line(C.byref(cands[k]), C.byref(alns[int(cand_aln[k])]), C.c_uint32(qlen[cands[k].orfKey]), C.c_uint64(c["contig_lens"][str(ck)]), buf)
+            got += buf.raw[:nb].decode()
+        assert got == rekey_lines(c["bycontig"][str(ck)], [0], True), ck
+        calls = (reflib.Call * max(1, 2 * (e - b)))(); exons = (reflib.Exon * max(1, e - b))()
+        sub = (reflib.Cand * max(1, e - b))(*[cands[k] for k in range(b, e)])
+        emu.emu_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]
+        nc = emu.emu_chain(sub, e - b, 15, 10000, 11, 10, -1, -1, c["max_exon_sets"], 0.5, total_res, 0.001, calls, exons)
+        assert nc >= 0
+        got = ""
+        for k in range(nc):
+            cl = calls[k]
+            for x in range(cl.nExons):
+                ex = exons[cl.exonBegin + x]; kd = cands[b + ex.candIdx]; al = alns[int(cand_aln[b + ex.candIdx])]
+                pe = _PExon(kd.orfKey, kd.bitScore, al.seq_id_est, kd.tStart, kd.tEnd, kd.tLen, ex.contigStart, ex.contigEnd, ex.nucLen, kd.fragFrom, kd.fragTo, 0, al.evalue)
+                nb = emu.emu_text_exon_line(C.byref(cl), C.byref(pe), buf)
+                got += buf.raw[:nb].decode()
+        if key_stride == 1:
+            assert got == c["dp"][str(ck)], ck
+        else:   # the calls come in target-key order: compare as multisets of re-keyed lines and check the order of the keys
+            assert sorted(got.splitlines()) == sorted(rekey_lines(c["dp"][str(ck)], [0], False).splitlines()), ck
+            ks = [int(l.split("\t")[0]) for l in got.splitlines()]
+            assert ks == sorted(ks)
