@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- predictexons hot-path throughput (query fragments / s) on B200, with the CPU path timed beside it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c4s|orf|reduce] [--impl reference]
 
 A "step" = one pass of the hot path over one batch of synthetic fragments per GPU.
 Workload c2 (default, BASELINE.json configs[1]): 100 K fragments (len max(15,N(100,40)), half mutated protein
@@ -39,6 +39,10 @@ WORKLOADS = {
     "c2": dict(n_prot=50_000, n_frag=100_000, align=False, desc="C2: 100K fragments (~100 aa) x 50K proteins (~330 aa), prefilter-only"),
     "c3": dict(n_prot=500_000, n_frag=1_000_000, align=True, desc="C3: 1M fragments x 500K proteins, prefilter + gapped SW align"),
     "c3s": dict(n_prot=500_000, n_frag=100_000, align=True, desc="C3/10: 100K fragments x 500K proteins, prefilter + gapped SW align (profiling size)"),
+    "c4": dict(n_prot=500_000, n_contigs=10_000, contig_len=50_000, predict=True, n_frag=0, align=True,
+               desc="C4: full predictexons (ORFs + prefilter + align + exon chaining) on 10K contigs x 50 kb with planted genes vs 500K proteins"),
+    "c4s": dict(n_prot=50_000, n_contigs=500, contig_len=50_000, predict=True, n_frag=0, align=True,
+                desc="C4/20: full predictexons on 500 contigs x 50 kb with planted genes vs 50K proteins (profiling size)"),
     "tiny": dict(n_prot=2_000, n_frag=4_000, align=True, desc="tiny: 4K fragments x 2K proteins (plumbing check)"),
     "reduce": dict(n_contigs=200_000, reduce=True, n_prot=0, n_frag=0, align=False,
                    desc="reduceredundancy stage (SURVEY 8f-2): 200 K contigs x ~24 calls (1-4 exons, exon keys shared inside a contig)"),
@@ -83,6 +87,168 @@ def gen_contigs(n, length, seed=1234):
     nuc = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * length, dtype=np.uint8)]
     off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
     return np.ascontiguousarray(nuc), off
+
+
+_CODON = np.frombuffer(b"GCTTGTGATGAATTTGGTCATATTAAACTGATGAATCCTCAACGTTCTACTGTTTGGTAT", dtype=np.uint8).reshape(20, 3)   # one codon per residue, A..Y in matrix order
+_COMP = np.zeros(256, np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+
+def gen_planted_contigs(n, length, prot, poff, seed=1234):
+    """SURVEY.md 8d contigs: i.i.d. ACGT; after 70 % of the inter-genic gaps (300-1500 nt) a gene = a random protein with per-residue
+    substitution rate in {0.1, 0.3, 0.5}, back-translated, split into 1-4 exons by introns of 40-600 nt, 50 % reverse-complemented"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    nuc = acgt[rng.integers(0, 4, size=n * length, dtype=np.uint8)]
+    nprot = len(poff) - 1
+    genes = 0
+    for c in range(n):
+        base = c * length; pos = 0
+        while True:
+            pos += int(rng.integers(300, 1500))
+            if rng.random() >= 0.7:
+                if pos >= length:
+                    break
+                continue
+            pi = int(rng.integers(0, nprot)); p = prot[int(poff[pi]):int(poff[pi + 1])].copy()
+            mut = rng.random(len(p)) < rng.choice([0.1, 0.3, 0.5])
+            p[mut] = rng.choice(20, size=int(mut.sum()), p=BG)
+            nex = int(rng.integers(1, 5))
+            cuts = np.sort(rng.choice(np.arange(20, len(p) - 20), size=nex - 1, replace=False)) if (nex > 1 and len(p) > 60 + nex) else np.zeros(0, np.int64)
+            pieces = []
+            for a, b in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [len(p)]))):
+                if pieces:
+                    pieces.append(acgt[rng.integers(0, 4, size=int(rng.integers(40, 600)), dtype=np.uint8)])
+                pieces.append(_CODON[p[int(a):int(b)]].reshape(-1))
+            g = np.concatenate(pieces)
+            if pos + len(g) > length:
+                break
+            if rng.random() < 0.5:
+                g = _COMP[g[::-1]]
+            nuc[base + pos: base + pos + len(g)] = g
+            pos += len(g); genes += 1
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
+    return np.ascontiguousarray(nuc), off, genes
+
+
+def cpu_predict_run(prot, poff, nuc, off, n_contigs, threads):
+    """the CPU oracle (port of the reference algorithm) on the first n_contigs contigs: ORF extraction + translation, prefilter, gapped alignment
+    (the exon-chaining DP, microseconds per contig in the reference too, is left out of the CPU timing)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reflib
+    o = reflib.Oracle()
+    o.set_params()
+    assert o.L.mbo_set_targets(o.h, reflib._p(prot, C.c_uint8), reflib._p(prot, C.c_uint8), reflib._p(poff, C.c_uint64), C.c_uint32(len(poff) - 1)) == 0
+    sseq = nuc[:int(off[n_contigs])].tobytes(); soff = np.ascontiguousarray(off[:n_contigs + 1])
+    from metaeuk_b200.modules import AA2NUM
+
+    def one():
+        t0 = time.perf_counter()
+        n, recs, aa = reflib.oracle_extract_orfs_raw(sseq, soff, threads=threads)
+        ra = np.ctypeslib.as_array(recs)[:n] if n else np.zeros(0, reflib.OrfRec)
+        qo = np.zeros(n + 1, np.uint64); qo[:n] = ra["aaOff"]; qo[n] = (int(ra["aaOff"][-1]) + int(ra["aaLen"][-1])) if n else 0
+        q = AA2NUM[np.frombuffer(aa, dtype=np.uint8, count=int(qo[n]))]
+        hits = (reflib.Hit * (max(1, n) * 300))(); cnt = np.zeros(max(1, n), np.uint32); st = reflib.Stats()
+        assert o.L.mbo_prefilter(o.h, reflib._p(q, C.c_uint8), reflib._p(qo, C.c_uint64), C.c_uint32(n), hits, reflib._p(cnt, C.c_uint32), C.byref(st), threads) == 0
+        hoff = np.zeros(n + 1, np.uint64); hoff[1:] = np.cumsum(cnt[:n])
+        ha = np.ctypeslib.as_array(hits)["seqId"].reshape(-1, 300)[:n]
+        mask = np.arange(300)[None, :] < cnt[:n, None]
+        flat = np.ascontiguousarray(ha[mask], np.uint32) if n else np.zeros(1, np.uint32)
+        if len(flat) == 0:
+            flat = np.zeros(1, np.uint32)
+        alns = (reflib.Aln * max(1, int(hoff[-1])))(); cells = C.c_uint64(0)
+        assert o.L.mbo_align(o.h, reflib._p(q, C.c_uint8), reflib._p(qo, C.c_uint64), C.c_uint32(n), reflib._p(flat, C.c_uint32), reflib._p(hoff, C.c_uint64), alns, C.byref(cells), threads) == 0
+        return time.perf_counter() - t0, n
+    return o, one
+
+
+def bench_predict(args, wl, base, rank, world, local, threads):
+    """BASELINE configs[3]/[4]: full predictexons from nucleotide contigs, contigs sharded across ranks (weak scaling: every rank gets
+    n_contigs of its own), index replicated by one NCCL broadcast.  value = fragments / sum of the CUDA-event stage times (contigs resident per
+    batch), e2e = fragments / wall clock of the C-ABI call mb200_predict_exons with HOST contigs in and HOST call records out."""
+    import torch
+    import torch.distributed as dist
+    from metaeuk_b200.lib import Context
+    from metaeuk_b200 import multi
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+    ctx.matrices_default()
+    t_idx0 = time.perf_counter()
+    prot, poff = gen_proteins(wl["n_prot"])
+    if rank == 0:
+        ctx.index_build(prot, prot, poff)
+    torch.cuda.synchronize()
+    t_b0 = time.perf_counter()
+    bcast_bytes = multi.replicate_index(ctx, rank, world)
+    torch.cuda.synchronize()
+    bcast_s = time.perf_counter() - t_b0 if world > 1 else 0.0
+    index_s = time.perf_counter() - t_idx0
+    nuc, off, genes = gen_planted_contigs(wl["n_contigs"], wl["contig_len"], prot, poff, seed=1234 + rank)
+    (nucP, _k1), (offP, _k2) = pinned(nuc), pinned(off)
+    STAGES = ("ms_orf", "ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain")
+    W = max(3, args.warmup) if wl["n_contigs"] <= 1000 else max(1, min(3, args.warmup))
+    for _ in range(W):
+        ctx.predict_exons(nucP, offP, copy=False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.stats()["launches"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = 0.0; pre_ms = 0.0; sts = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call_off, calls, exons = ctx.predict_exons(nucP, offP, copy=False)
+        st = ctx.stats(); sts.append(st)
+        dev_ms += sum(st[k] for k in STAGES); pre_ms += st["ms_prefilter"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st = sts[-1]
+    vals = [dev_ms * 1e-3, wall]
+    if world > 1:
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in t.tolist()]
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    nfrag = int(st["pe_fragments"])
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes_prefilter(st); kms = pre_ms / args.steps
+    base["config"].update({"fragments_per_gpu": nfrag, "contigs_per_gpu": wl["n_contigs"], "nucleotides_per_gpu": int(nuc.nbytes), "planted_genes_per_gpu": genes,
+                           "stages": "extractorfs+translatenucs+prefilter+align+resultspercontig+collectoptimalset", "contig_batches": int(st["pe_batches"]),
+                           "parallelism": "contig shards x%d, index replicated by one NCCL broadcast" % args.gpus,
+                           "warmup_used": W})
+    base["warmup"] = W
+    base.update({"value": world * nfrag * args.steps / vals[0], "ms_per_step": 1000 * vals[0] / args.steps, "clocks": clocks, "gpu_launches": int(st["launches"] - l0),
+                 "e2e": {"value": world * nfrag * args.steps / vals[1], "unit": "fragments/s", "h2d_bytes_per_step": int(nuc.nbytes + off.nbytes),
+                         "d2h_bytes_per_step": int(calls.nbytes + exons.nbytes + call_off.nbytes), "ms_per_step": 1000 * vals[1] / args.steps,
+                         "last_call_ms": {k: round(st[k], 3) for k in STAGES + ("ms_join", "ms_predict")}},
+                 "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": abytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kms * 1e-3) / 1e9 / peak,
+                              "peak_source": peak_src, "algorithmic_bytes_per_launch": int(abytes // max(1, int(st["pe_batches"]))), "kernel_ms": kms / max(1, int(st["pe_batches"])), "traffic": None},
+                 "stages_ms": {k: st[k] for k in STAGES + ("ms_join",)},
+                 "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons")},
+                 "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "broadcast_bytes": int(bcast_bytes), "entries": ctx.index_sizes()[0]},
+                 "timing": "value: sum of the CUDA-event stage times of the library stream (contigs of a batch resident), max over ranks; e2e: wall clock of mb200_predict_exons (host contigs in, host call records out) between device synchronisations"})
+    if st["ms_sw_fwd"] + st["ms_sw_rev"] > 0:
+        base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
+    if args.gpus == 1:
+        nsample = min(wl["n_contigs"], args.cpu_sample or 8)
+        o, one = cpu_predict_run(prot, poff, nuc, off, nsample, threads)
+        tcpu, ncpu = one()
+        base["cpu_baseline"] = {"value": ncpu / tcpu, "unit": "fragments/s", "cores": threads, "kind": "port",
+                                "sample": "first %d contigs (%d fragments) of the workload: ORF extraction + prefilter + alignment on all %d host threads; index build and the chaining DP excluded" % (nsample, ncpu, threads)}
+    emit(base)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def gen_calls(n_contigs, seed=99):
@@ -385,6 +551,22 @@ def main():
             emit(base)
             return
         prot, poff = gen_proteins(wl["n_prot"])
+        if wl.get("predict"):
+            nsample = min(wl["n_contigs"], args.cpu_sample or 8)
+            nuc, off, _g = gen_planted_contigs(nsample, wl["contig_len"], prot, poff)
+            o, one = cpu_predict_run(prot, poff, nuc, off, nsample, threads)
+            for _ in range(args.warmup):
+                one()
+            t = 0.0; nfr = 0
+            for _ in range(max(1, args.steps)):
+                dt, n = one(); t += dt; nfr += n
+            base["config"]["stages"] = "extractorfs+translatenucs+prefilter+align (chaining DP excluded from the CPU timing)"
+            base.update({"impl": "reference", "value": nfr / t, "ms_per_step": 1000 * t / max(1, args.steps), "gpu_launches": 0,
+                         "cpu_baseline": {"value": nfr / t, "unit": "fragments/s", "cores": threads, "kind": "port",
+                                          "sample": "first %d contigs per step, all %d host threads; index build excluded" % (nsample, threads)},
+                         "e2e": {"value": nfr / t, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            emit(base)
+            return
         frag, foff = gen_fragments(wl["n_frag"], prot, poff, seed=4321)
         n_sample = args.cpu_sample or (8192 if not wl["align"] else 2048)
         o, one, n = cpu_oracle_run(prot, poff, frag, foff, n_sample, wl["align"], threads)
@@ -403,6 +585,8 @@ def main():
         return bench_orf(args, wl, base, rank, world, local, threads)
     if wl.get("reduce"):
         return bench_reduce(args, wl, base, rank, world, local, threads)
+    if wl.get("predict"):
+        return bench_predict(args, wl, base, rank, world, local, threads)
     import torch
     import torch.distributed as dist
     from metaeuk_b200.lib import Context

@@ -86,3 +86,24 @@ def search_sharded(run_shard, queries, rank, world):
     for p in parts:
         merged.update(p)
     return merged
+
+
+def predict_sharded(predict, contig_off, rank, world):
+    """predictexons over contigs sharded by nucleotide count (BASELINE configs[4]; the reference's unit of independence is the contig,
+    collectoptimalset.cpp:274-418).  predict(c0, c1) runs contigs [c0, c1) on this rank's GPU (lib.Context.predict_exons on that slice) and
+    returns (call_off, calls, exons, n_fragments).  Rank 0 returns the merged (call_off, calls, exons), identical to the single-GPU result:
+    fragment keys count over the whole contig set in the reference, so every shard's orf_key is shifted by the number of fragments of the
+    contigs before it, and exon_begin by the exons before it.  No data-path collective; the gather moves call records only."""
+    b = shard_bounds(contig_off, world)
+    call_off, calls, exons, nfrag = predict(b[rank], b[rank + 1])
+    parts = gather_to_root((np.asarray(call_off, np.uint64), calls, exons, int(nfrag)), rank, world)
+    if rank != 0:
+        return None
+    offs, cs, es = [np.zeros(1, np.uint64)], [], []
+    frag_base = call_base = exon_base = 0
+    for co, c, e, nf in parts:
+        c = c.copy(); e = e.copy()
+        c["exon_begin"] += np.uint32(exon_base); e["orf_key"] += np.uint32(frag_base)
+        offs.append(co[1:] + np.uint64(call_base)); cs.append(c); es.append(e)
+        frag_base += nf; call_base += len(c); exon_base += len(e)
+    return np.concatenate(offs), np.concatenate(cs), np.concatenate(es)
