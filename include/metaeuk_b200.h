@@ -132,6 +132,18 @@ int mb200_index_alloc(mb200_ctx *ctx, const uint64_t sizes[4]);
 int mb200_index_buffers(mb200_ctx *ctx, void *dev_ptrs[8], uint64_t nbytes[8], int *n);
 int mb200_index_commit(mb200_ctx *ctx);
 
+/* persisted index: an MMseqs index database in the layout `createindex` / `indexdb` write (<path>, <path>.index, <path>.dbtype;
+ * entries keyed as in M/src/prefiltering/PrefilteringIndexReader.cpp:10-34).  mb200_index_load mmaps such a DB -- written by
+ * mb200_index_save / mb200_index_file_write or by the reference itself -- checks its META entry (k = 6, alphabet 21, spaced pattern, one split,
+ * amino acids, k-mer threshold equal to params.kmer_thr), uploads k-mer table, masked and unmasked residues and takes the DB keys
+ * (mb200_target_keys_set).  mb200_index_file_write builds the index on the host (no GPU needed; default seed matrix) and writes it. */
+int mb200_index_save(mb200_ctx *ctx, const char *path);
+int mb200_index_load(mb200_ctx *ctx, const char *path);
+int mb200_index_file_write(const char *path, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets,
+                           const uint32_t *keys /* NULL = local ids */, int kmer_thr, int mask_mode);
+/* copies the DB keys of the targets (identity if none were set); keys: caller buffer of n_targets */
+int mb200_target_keys_get(mb200_ctx *ctx, uint32_t *keys);
+
 /* query side: host buffers in, host buffers out (the call a module makes).  q_off[n_q+1]. */
 int mb200_prefilter(mb200_ctx *ctx, const uint8_t *q, const uint64_t *q_off, uint32_t n_q, mb200_hit *hits /* n_q*max_res_list_len */, uint32_t *hit_count);
 /* alns[k] for every listed hit k (<= max_res_list_len hits per query): hits whose score can pass -e carry all fields and `passed`;

@@ -25,6 +25,7 @@
 #include "reduce_core.cuh"
 #include "host_tables.h"
 #include "host_join.h"
+#include "host_indexdb.h"
 #include "prefilter_core.cuh"
 
 static thread_local std::string g_err;
@@ -389,6 +390,52 @@ int mb200_index_import(mb200_ctx *c, const uint64_t *offsets, const uint8_t *ent
     if (mb200::import_index(offsets, entries6, nEntries, idx)) return fail(MB200_E_LIMIT, "index has >= 2^32 entries");
     TRY(upload_targets(c, masked, unmasked, off, nT));
     return upload_index(c, idx);
+}
+
+// ---- persisted index ----
+int mb200_index_file_write(const char *path, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT, const uint32_t *keys, int kmerThr, int maskMode) {
+    if (!path || !masked || !unmasked || !off) return fail(MB200_E_ARG, "null argument");
+    TRY(check_targets(off, nT));
+    mb200::Matrices m; mb200::default_matrices(m);
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, off, nT, m.seed, kmerThr, idx)) return fail(MB200_E_LIMIT, "index build failed");
+    std::string err;
+    if (mb200::write_index_db(path, idx, masked, unmasked, off, nT, keys, kmerThr, maskMode, err)) return fail(MB200_E_ARG, "%s", err.c_str());
+    return 0;
+}
+
+int mb200_index_save(mb200_ctx *c, const char *path) {
+    if (!c || !path) return fail(MB200_E_ARG, "null argument");
+    if (!c->haveIndex) return fail(MB200_E_STATE, "no index");
+    CU(cudaSetDevice(c->device));
+    mb200::TargetIndex idx; idx.offsets.resize(mb200::KMER_TABLE + 1); idx.entries.resize(c->nEntries);
+    std::vector<uint8_t> m(c->totalRes + 1), u(c->totalRes + 1);
+    CU(cudaMemcpy(idx.offsets.data(), c->dOffsets.p, idx.offsets.size() * 4, cudaMemcpyDeviceToHost));
+    if (c->nEntries) CU(cudaMemcpy(idx.entries.data(), c->dEntries.p, c->nEntries * 8, cudaMemcpyDeviceToHost));
+    if (c->totalRes) { CU(cudaMemcpy(m.data(), c->dTseqM.p, c->totalRes, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(u.data(), c->dTseqU.p, c->totalRes, cudaMemcpyDeviceToHost)); }
+    bool masked = false; for (uint64_t i = 0; i < c->totalRes && !masked; i++) masked = m[i] != u[i];
+    std::string err;
+    if (mb200::write_index_db(path, idx, m.data(), u.data(), c->hToff.data(), c->nT, c->tKeys.size() == c->nT ? c->tKeys.data() : nullptr, c->par.kmer_thr, masked ? 1 : 0, err))
+        return fail(MB200_E_ARG, "%s", err.c_str());
+    return 0;
+}
+
+int mb200_index_load(mb200_ctx *c, const char *path) {
+    if (!c || !path) return fail(MB200_E_ARG, "null argument");
+    mb200::IndexDb db; std::string err;
+    if (mb200::open_index_db(path, db, err)) return fail(MB200_E_ARG, "%s: %s", path, err.c_str());
+    if (db.meta.kmerThr != c->par.kmer_thr) return fail(MB200_E_ARG, "%s was built with k-mer threshold %d, the context uses %d", path, db.meta.kmerThr, c->par.kmer_thr);
+    if (db.nSeq >= (1ull << 27)) return fail(MB200_E_LIMIT, "too many targets");
+    TRY(mb200_index_import(c, db.offsets, db.entries6, db.nEntries, db.masked, db.unmasked.data(), db.seqOff, (uint32_t)db.nSeq));
+    c->tKeys = db.keys;
+    return 0;
+}
+
+int mb200_target_keys_get(mb200_ctx *c, uint32_t *keys) {
+    if (!c || !keys) return fail(MB200_E_ARG, "null argument");
+    if (!c->haveIndex) return fail(MB200_E_STATE, "no index");
+    for (uint32_t i = 0; i < c->nT; i++) keys[i] = c->tKeys.size() == c->nT ? c->tKeys[i] : i;
+    return 0;
 }
 
 int mb200_index_sizes(mb200_ctx *c, uint64_t sizes[4]) {

@@ -9,6 +9,7 @@
 //   mb200 gpureduceredundancy  <calledExonsDB> <predsDB> <predToCallDB> == reduceredundancy   (src/exonpredictor/reduceredundancy.cpp:162)
 //   mb200 gpupredictexons      <contigsDB> <targetDB> <predDB>          == predictexons.sh:40-82 with the contigs as the only input (ORFs stay on the GPU)
 //   mb200 gpupredictexons      <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>
+//   mb200 gpucreateindex       <targetDB> <indexDB>                     == createindex / indexdb (M/src/util/indexdb.cpp); every search module takes --index-db <indexDB>
 //                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
 // DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
 // Result DBs are written byte-compatible with the reference's (same records, same keys; one data file).
@@ -107,7 +108,7 @@ static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdTo
 static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
 
 struct Opt {
-    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0;
+    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb;
 };
 static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
     Opt o; mb200_params_default(&o.p);
@@ -131,6 +132,7 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--set-gap-extend") o.p.set_gap_extend = atoi(val().c_str());
         else if (a == "--device") o.device = atoi(val().c_str());
         else if (a == "--overlap") o.overlap = atoi(val().c_str());
+        else if (a == "--index-db") o.indexDb = val();
         else if (a == "--text-stages") o.textStages = atoi(val().c_str());
         else if (a == "--batch-nt") o.batchNt = atoll(val().c_str());
         else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
@@ -152,7 +154,16 @@ struct Session {
                 memcpy(&m.res[t.off[i]], &raw.res[raw.off[j]], t.off[i + 1] - t.off[i]);
             }
         }
-        MB(mb200_index_build(ctx, m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size()));
+        if (!o.indexDb.empty()) {
+            // persisted index (written by gpucreateindex or by the reference's createindex / indexdb): mmap + upload instead of a rebuild
+            MB(mb200_index_load(ctx, o.indexDb.c_str()));
+            uint64_t sz[4]; MB(mb200_index_sizes(ctx, sz));
+            if (sz[1] != tdb.keys.size() || sz[2] != t.res.size()) DIE("index DB %s does not belong to target DB %s", o.indexDb.c_str(), targetDb.c_str());
+            std::vector<uint32_t> k(tdb.keys.size() + 1); MB(mb200_target_keys_get(ctx, k.data()));
+            for (size_t i = 0; i < tdb.keys.size(); i++) if (k[i] != tdb.keys[i]) DIE("index DB %s lists the targets in another order than %s", o.indexDb.c_str(), targetDb.c_str());
+        } else {
+            MB(mb200_index_build(ctx, m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size()));
+        }
         for (size_t i = 0; i < tdb.keys.size(); i++) tlen.push_back(t.off[i + 1] - t.off[i]);
     }
     ~Session() { if (ctx) mb200_ctx_destroy(ctx); }
@@ -248,7 +259,7 @@ static std::map<uint32_t, std::string> searchAll(Session &s, const Db &qdb, cons
 static void writeDb(const std::string &name, int dbtype, const std::map<uint32_t, std::string> &m) { DbOut o(name, dbtype); for (auto &kv : m) o.write(kv.first, kv.second); }
 
 int main(int argc, char **argv) {
-    if (argc < 2) DIE("usage: mb200 <gpuextractorfs|gpureduceredundancy|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
+    if (argc < 2) DIE("usage: mb200 <gpucreateindex|gpuextractorfs|gpureduceredundancy|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
     initCodes();
     std::string cmd = argv[1]; std::vector<std::string> pos; Opt o = parseOpts(argc, argv, 2, pos);
     if (cmd == "gpuprefilter") {
@@ -387,6 +398,19 @@ int main(int argc, char **argv) {
             grouped.write(dp.keys[id], g); clusters.write(dp.keys[id], cl);
         }
         mb200_ctx_destroy(ctx);
+    } else if (cmd == "gpucreateindex") {
+        // createindex / indexdb (M/src/util/indexdb.cpp): build the k-mer index on the host and persist it in the reference's index-DB layout
+        if (pos.size() != 2) DIE("gpucreateindex <targetDB> <o:indexDB> [--masked-db <DB>] [--k-score N]");
+        initCodes();
+        Db tdb = openDb(pos[0]); Seqs t = encodeDb(tdb, false); Seqs m = t;
+        if (!o.maskedDb.empty()) {
+            Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
+            for (size_t i = 0; i < tdb.keys.size(); i++) {
+                size_t j = md.find(tdb.keys[i]); if (j == (size_t)-1 || raw.off[j + 1] - raw.off[j] != t.off[i + 1] - t.off[i]) DIE("masked DB does not match target DB at key %u", tdb.keys[i]);
+                memcpy(&m.res[t.off[i]], &raw.res[raw.off[j]], t.off[i + 1] - t.off[i]);
+            }
+        }
+        MB(mb200_index_file_write(pos[1].c_str(), m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), tdb.keys.data(), o.p.kmer_thr, o.maskedDb.empty() ? 0 : 1));
     } else if (cmd == "gpuextractorfs") {
         // extractorfs + translatenucs in one step (data/predictexons.sh: contigs -> nucl_6f(_h) -> aa_6f): writes the ORF header DB and the
         // translated fragment DB with the reference's renumbered keys

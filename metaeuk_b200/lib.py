@@ -56,8 +56,8 @@ def _gxx():
 
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp", "host_join.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "host_join.h", "submat_data.h")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp", "host_join.cpp", "host_indexdb.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "host_join.h", "host_indexdb.h", "submat_data.h")] + \
         [os.path.join(ROOT, "include", "metaeuk_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -100,6 +100,16 @@ def pack_codes(seqs):
         off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
     data = np.concatenate(seqs).astype(np.uint8, copy=False) if len(seqs) else np.zeros(0, np.uint8)
     return np.ascontiguousarray(data), off
+
+
+def index_file_write(path, masked, unmasked, off, keys=None, kmer_thr=127, mask_mode=1):
+    """build the target index on the host and persist it in the reference's index-DB layout (no GPU needed)"""
+    L = load_library()
+    masked = np.ascontiguousarray(masked, np.uint8); unmasked = np.ascontiguousarray(unmasked, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+    k = np.ascontiguousarray(keys, np.uint32) if keys is not None else None
+    rc = L.mb200_index_file_write(os.fsencode(path), _p(masked), _p(unmasked), _p(off), C.c_uint32(len(off) - 1), _p(k) if k is not None else None, int(kmer_thr), int(mask_mode))
+    if rc != 0:
+        raise Mb200Error("mb200 error %d: %s" % (rc, L.mb200_last_error().decode()))
 
 
 class Context:
@@ -158,6 +168,19 @@ class Context:
         self.target_off = off
         self._check(self.L.mb200_index_import(self.h, _p(offsets_u64), _p(entries6), C.c_uint64(len(entries6) // 6), _p(masked), _p(unmasked), _p(off),
                                               C.c_uint32(self.n_targets)))
+
+    # ---- persisted index (createindex layout) ----
+    def index_save(self, path):
+        self._check(self.L.mb200_index_save(self.h, os.fsencode(path)))
+
+    def index_load(self, path):
+        self._check(self.L.mb200_index_load(self.h, os.fsencode(path)))
+        self.n_targets = self.index_sizes()[1]
+
+    def target_keys_get(self):
+        keys = np.zeros(max(1, self.index_sizes()[1]), np.uint32)
+        self._check(self.L.mb200_target_keys_get(self.h, _p(keys)))
+        return keys[:self.index_sizes()[1]]
 
     # ---- multi-GPU replication helpers (see bench.py: one NCCL broadcast of these buffers) ----
     def index_sizes(self):

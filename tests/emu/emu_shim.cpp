@@ -11,6 +11,7 @@
 #include "../../metaeuk_b200/csrc/reduce_core.cuh"
 #include "../../metaeuk_b200/csrc/chain_core.cuh"
 #include "../../metaeuk_b200/csrc/host_join.h"
+#include "../../metaeuk_b200/csrc/host_indexdb.h"
 
 template <class SH>
 static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
@@ -124,5 +125,28 @@ int emu_chain(const mb200_cand *cands, uint32_t n, int minIntron, int maxIntron,
 
 int emu_text_bycontig_line(const mb200_cand *k, const mb200_aln *a, uint32_t qLen, uint64_t contigLen, char *buf) { const std::string l = mb200::text_bycontig_line(*k, *a, qLen, contigLen); memcpy(buf, l.c_str(), l.size() + 1); return (int)l.size(); }
 int emu_text_exon_line(const mb200_call *c, const mb200_pexon *e, char *buf) { const std::string l = mb200::text_exon_line(*c, *e); memcpy(buf, l.c_str(), l.size() + 1); return (int)l.size(); }
+
+// ---- persisted index DB (host_indexdb.cpp) ----
+int emu_indexdb_write(const char *path, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT, const uint32_t *keys, int kmerThr, int maskMode) {
+    mb200::Matrices m; mb200::default_matrices(m);
+    mb200::TargetIndex idx;
+    if (mb200::build_index(masked, off, nT, m.seed, kmerThr, idx)) return -1;
+    std::string err;
+    const int rc = mb200::write_index_db(path, idx, masked, unmasked, off, nT, keys, kmerThr, maskMode, err);
+    if (rc) fprintf(stderr, "emu_indexdb_write: %s\n", err.c_str());
+    return rc;
+}
+void *emu_indexdb_open(const char *path, char *errOut, size_t errCap) {
+    mb200::IndexDb *db = new mb200::IndexDb(); std::string err;
+    if (mb200::open_index_db(path, *db, err)) { if (errOut && errCap) { strncpy(errOut, err.c_str(), errCap - 1); errOut[errCap - 1] = 0; } delete db; return nullptr; }
+    return db;
+}
+void emu_indexdb_info(void *h, uint64_t out[3], int meta[12]) { auto *db = (mb200::IndexDb *)h; out[0] = db->nEntries; out[1] = db->nSeq; out[2] = db->seqOff[db->nSeq]; memcpy(meta, &db->meta, 48); }
+const void *emu_indexdb_ptr(void *h, int which) {
+    auto *db = (mb200::IndexDb *)h;
+    switch (which) { case 0: return db->offsets; case 1: return db->entries6; case 2: return db->masked; case 3: return db->seqOff; case 4: return db->keys.data(); case 5: return db->unmasked.data(); }
+    return nullptr;
+}
+void emu_indexdb_close(void *h) { delete (mb200::IndexDb *)h; }
 
 }  // extern "C"

@@ -394,6 +394,50 @@ def case_orfs(name, seed, thr=4):
     print(name, "contigs", len(out["contigs"]), "fragments", len(out["queries"]))
 
 
+REF_TESTS = [("minus_strand", -1, 0), ("multi_exon", -1, 0), ("two_contigs", -1, 0), ("target_overlap", -3, 0), ("cluster_rep", -3, 0), ("target_cov", -1, 0.7)]
+
+
+def case_reference_tests(name="ref_tests", thr=8):
+    """The reference's OWN end-to-end fixtures (reference/tests/run.sh -> test.sh: six data sets with the flags listed there).  For each one:
+    the input FASTA files as the reference's createdb stored them, the `predictexons` workflow's intermediate DBs (kept with
+    --remove-tmp-files 0), `reduceredundancy`'s outputs, the tantan-masked targets, and -- verbatim -- the header lines of the checked-in
+    known answers as_should_final_united_exons_aa.fas / as_should_final_grouped_predictions_rep.fas (target|contig|strand|bit score|E-value|
+    #exons|low|high|exon coordinates...), which tests/ rebuild from the call records (unitesetstofasta.cpp:114-190)."""
+    tests_dir = os.environ.get("METAEUK_REF_TESTS", "/root/reference/tests")
+    out = {"case": name, "kind": "reference_tests", "sets": {}}
+    for ds, sge, tcov in REF_TESTS:
+        tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+        log = []
+        src = os.path.join(tests_dir, ds)
+        run("%s createdb %s/contigs.fna %s/contigs --dbtype 2 -v 3" % (REF, src, tmp), log)
+        run("%s createdb %s/proteins.faa %s/proteins --dbtype 1 -v 3" % (REF, src, tmp), log)
+        wf = run("%s predictexons %s/contigs %s/proteins %s/predEx %s/tmp --set-gap-extend %s --metaeuk-tcov %s --remove-tmp-files 0 --threads %d -v 3"
+                 % (REF, tmp, tmp, tmp, tmp, sge, tcov, thr), log)
+        run("%s reduceredundancy %s/predEx %s/predRed %s/predClust --threads %d -v 3" % (REF, tmp, tmp, tmp, thr), log)
+        lt = tmp + "/tmp/latest"
+        heads = {}
+        for f in ("as_should_final_united_exons_aa.fas", "as_should_final_grouped_predictions_rep.fas"):
+            heads[f] = [l[1:].rstrip("\n") for l in open(os.path.join(src, f)) if l.startswith(">")]
+        d = {"set_gap_extend": sge, "tcov": tcov, "targets": seqdb(tmp + "/proteins"), "contigs": seqdb(tmp + "/contigs"),
+             "target_acc": {str(k): e.decode().split()[0] for k, e in read_db(tmp + "/proteins_h")},
+             "contig_acc": {str(k): e.decode().split()[0] for k, e in read_db(tmp + "/contigs_h")},
+             "queries": seqdb(lt + "/aa_6f"), "orf_headers": {str(k): e[:-1].decode() for k, e in read_db(lt + "/nucl_6f_h")},
+             "aln": resdb(lt + "/search_res"), "bycontig": resdb(lt + "/search_res_by_contig"), "dp": resdb(tmp + "/predEx"),
+             "grouped": resdb(tmp + "/predRed"), "clusters": resdb(tmp + "/predClust"),
+             "kmer_thr": int(wf.split("k-mer similarity threshold: ")[1].split()[0]),
+             "masked_residues": int(wf.split("Masked residues: ")[1].split()[0]), "as_should": heads}
+        idx = ref_index(tmp, "proteins", 1, thr, log)
+        assert idx["idx_masked_residues"] == d["masked_residues"]
+        d["masked_targets"] = idx["masked_targets"]
+        out["sets"][ds] = d
+        shutil.rmtree(tmp)
+        print(ds, "targets", len(d["targets"]), "contigs", len(d["contigs"]), "fragments", len(d["queries"]), "aln lines", sum(v.count("\n") for v in d["aln"].values()),
+              "dp lines", sum(v.count("\n") for v in d["dp"].values()), "known answers", len(heads["as_should_final_united_exons_aa.fas"]), len(heads["as_should_final_grouped_predictions_rep.fas"]))
+    out["ref_version"] = run("%s version" % REF, []).strip()
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("reference binary not found: " + REF)
@@ -412,3 +456,5 @@ if __name__ == "__main__":
         case_orfs("orf_edge", 31)
     if "redundancy_family" in which:
         case_redundancy("redundancy_family", 2025)
+    if "ref_tests" in which:
+        case_reference_tests()

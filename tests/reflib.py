@@ -410,3 +410,100 @@ def fmt_dp(calls, cands):
                 k["orfKey"], k["bitScore"], fmt_exon_seqid(k["seqIdText"]), fmt_eval(float(k["evalText"])), k["tStart"], k["tEnd"], k["tLen"],
                 e["contigStart"], e["contigEnd"], e["nucLen"], k["fragFrom"], k["fragTo"])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# MMseqs database files (data + .index + .dbtype), as the reference's DBWriter / DBReader lay them out
+# ------------------------------------------------------------------------------------------------
+def write_db(path, entries, dbtype):
+    import struct
+    pos = 0
+    with open(path, "wb") as f, open(path + ".index", "w") as fi:
+        for k, e in entries:
+            b = e.encode() + b"\0"
+            f.write(b)
+            fi.write("%d\t%d\t%d\n" % (k, pos, len(b)))
+            pos += len(b)
+    with open(path + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", dbtype))
+
+
+def read_db(path):
+    data = open(path, "rb").read()
+    out = {}
+    for line in open(path + ".index"):
+        k, o, l = line.split("\t")
+        out[k] = data[int(o):int(o) + int(l) - 1].decode()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# The whole predictexons chain on the CPU oracle, stage by stage through the reference's text formats
+# ------------------------------------------------------------------------------------------------
+def bycontig_join(aln, orf_headers, contig_lens):
+    """resultspercontig restated (reference/src/exonpredictor/resultspercontig.cpp:64-196): {orfKey: aln entry} -> {contigKey: 20-column lines}"""
+    per = {k: [] for k in contig_lens}
+    for orf, text in aln.items():
+        if not text:
+            continue
+        contig, frm, to = parse_orf_header(orf_headers[orf])
+        orf_len = max(frm, to) - min(frm, to) + 1
+        for l in text.splitlines():
+            w = l.split("\t")
+            w[2] = fmt_seqid(float(w[2]))   # parse -> re-print can lose one unit (SURVEY.md App. E)
+            line = "\t".join(w) + "\t%d\t1\t1.00\t0.000E+00\t0\t%d\t%d\t%d\t%d\t%d\n" % (int(orf), orf_len - 1, orf_len, frm, to, contig_lens[contig])
+            per[contig].append((int(w[0]), int(orf), line))
+    return {c: "".join(r[2] for r in sorted(rows, key=lambda r: (r[0], r[1]))) for c, rows in per.items()}
+
+
+def cands_of(text):
+    out = []
+    for l in text.splitlines():
+        w = l.split("\t")
+        out.append(dict(targetKey=int(w[0]), bitScore=int(w[1]), qStart=int(w[4]), qEnd=int(w[5]), tStart=int(w[7]), tEnd=int(w[8]), tLen=int(w[9]), orfKey=int(w[10]),
+                        fragFrom=int(w[17]), fragTo=int(w[18]), seqIdText=w[2], evalText=w[3]))
+    return out
+
+
+def oracle_pipeline(o, contigs, target_keys, target_lens, max_sets=1, gap_open=-1, gap_extend=-1, tcov=0.5, threads=0):
+    """contigs [(key, nucleotides)] -> dict(orf_headers, queries, aln, bycontig, dp) as the reference's DBs (o: Oracle with params and targets set)"""
+    hdr, seqs = oracle_extract_orfs(contigs)
+    frags = [seqs[i] for i in range(len(seqs))]
+    res, _ = o.prefilter(frags, threads=threads)
+    alns, _ = o.align(frags, [[t for t, _, _ in h] for h in res], threads=threads)
+    aln = {i: "".join(fmt_aln(a, target_keys, len(frags[i]), target_lens) for a in sort_alns([a for a in al if a["passed"] == 1], target_keys, target_lens))
+           for i, al in enumerate(alns)}
+    byc = bycontig_join(aln, hdr, {k: len(s) for k, s in contigs})
+    dp = {}
+    for ck, text in byc.items():
+        cands = cands_of(text)
+        dp[ck] = fmt_dp(o.chain(cands, sum(target_lens), max_sets=max_sets, gap_open=gap_open, gap_extend=gap_extend, tcov=tcov), cands)
+    return dict(orf_headers=hdr, queries=seqs, aln=aln, bycontig=byc, dp=dp)
+
+
+def fmt_fasta_headers(dp, target_acc, contig_acc):
+    """{contigKey: dp_predictions entry} -> the FASTA header of every call as `unitesetstofasta` writes it (default flags; reference/src/
+    exonpredictor/unitesetstofasta.cpp:114-190): T|C|strand|bit score|E-value|#exons|low|high|start[adjusted]:end[end]:len[adjusted] per exon.
+    The E-value is the dp text parsed to double and printed by an ostream with its default 6 significant digits (= %g)."""
+    out = []
+    for ck, entry in dp.items():
+        calls = []
+        for l in entry.splitlines():
+            w = l.split("\t")
+            head = tuple(w[:7])
+            if not calls or calls[-1][0] != head:
+                calls.append((head, []))
+            calls[-1][1].append(w[7:])
+        for (t, s, score, ev, nex, low, high), exons in calls:
+            h = "%s|%s|%s|%s|%s|%s|%s|%s" % (target_acc[str(t)], contig_acc[str(ck)], "+" if int(s) == 1 else "-", score, "%g" % float(ev), nex, low, high)
+            last = -1
+            for e in exons:
+                t_start, t_end, c_start, c_end, nlen = int(e[4]), int(e[5]), int(e[7]), int(e[8]), int(e[9])
+                adj_start, adj_len = c_start, nlen
+                if last >= t_start:
+                    d = last - t_start + 1
+                    adj_start += 3 * d; adj_len -= 3 * d
+                last = t_end
+                h += "|%d[%d]:%d[%d]:%d[%d]" % (abs(c_start), abs(adj_start), abs(c_end), abs(c_end), nlen, adj_len)
+            out.append(h)
+    return out

@@ -239,6 +239,29 @@ def test_predict_exons_binary_handoff_golden(name, batch_nt):
     ctx.close()
 
 
+@pytest.mark.parametrize("ds", ["minus_strand", "multi_exon", "two_contigs", "target_overlap", "cluster_rep", "target_cov"])
+def test_reference_own_end_to_end_fixtures(ds):
+    """the data sets of the reference's own test suite (reference/tests/run.sh; BASELINE configs[0] = two_contigs) with run.sh's flags, contigs in:
+    the device pipeline must give the reference's dp_predictions and reduceredundancy DBs, and the calls must print to the CHECKED-IN known
+    answers of the reference (header lines of as_should_final_*.fas: bit scores, E-values, exon counts and coordinates)"""
+    c = reflib.load_case("ref_tests")["sets"][ds]
+    ctx, tdb = ctx_for(c, set_gap_extend=c["set_gap_extend"], tcov=c["tcov"])
+    contigs = [tuple(x) for x in c["contigs"]]
+    dp = strkeys(M.predictexons_contigs(ctx, contigs, tdb))
+    assert dp == c["dp"]
+    assert sorted(reflib.fmt_fasta_headers(dp, c["target_acc"], c["contig_acc"])) == sorted(c["as_should"]["as_should_final_united_exons_aa.fas"])
+    grouped, clusters = M.reduceredundancy(ctx, {int(k): v for k, v in dp.items()})
+    assert strkeys(grouped) == c["grouped"] and strkeys(clusters) == c["clusters"]
+    assert sorted(reflib.fmt_fasta_headers(strkeys(grouped), c["target_acc"], c["contig_acc"])) == sorted(c["as_should"]["as_should_final_grouped_predictions_rep.fas"])
+    # the stage-by-stage route (text DBs between the stages) agrees too
+    queries, headers = M.extractorfs(ctx, contigs)
+    assert {str(k): v for k, v in headers.items()} == c["orf_headers"] and queries == [(int(k), s) for k, s in c["queries"]]
+    aln, byc, dp2 = M.predictexons(ctx, queries, headers, {k: len(s) for k, s in contigs}, tdb)
+    assert {str(k): v for k, v in aln.items() if v} == {k: v for k, v in c["aln"].items() if v}
+    assert strkeys(byc) == c["bycontig"] and strkeys(dp2) == c["dp"]
+    ctx.close()
+
+
 def planted_contigs(seed, prots, n_contigs, length):
     """SURVEY 8d contig generator at test size: random ACGT with planted genes = mutated proteins back-translated, split into 1-4 exons,
     introns of 40-600 nt, half of them reverse-complemented"""
@@ -280,22 +303,8 @@ def test_predict_exons_matches_oracle_stage_by_stage_on_planted_genes():
     ctx = M.make_context(tdb, max_exon_sets=2)
     ctx.option_set("predict_batch_nt", 100000)
     got = M.predictexons_contigs(ctx, contigs, tdb)
-    hdr, seqs = reflib.oracle_extract_orfs(contigs)
     o = reflib.Oracle(); o.set_params(); o.set_targets(prots, prots)
-    frags = [seqs[i] for i in range(len(seqs))]
-    res, _ = o.prefilter(frags)
-    alns, _ = o.align(frags, [[t for t, _, _ in h] for h in res])
-    keys = list(range(len(prots))); tlens = [len(p) for p in prots]
-    aln_txt = {i: "".join(reflib.fmt_aln(a, keys, len(frags[i]), tlens) for a in reflib.sort_alns([a for a in al if a["passed"] == 1], keys, tlens)) for i, al in enumerate(alns)}
-    byc = M.resultspercontig(aln_txt, hdr, {k: len(s) for k, s in contigs})
-    want = {}
-    for ck, text in byc.items():
-        cands = []
-        for l in text.splitlines():
-            w = l.split("\t")
-            cands.append(dict(targetKey=int(w[0]), bitScore=int(w[1]), qStart=int(w[4]), qEnd=int(w[5]), tStart=int(w[7]), tEnd=int(w[8]), tLen=int(w[9]), orfKey=int(w[10]),
-                              fragFrom=int(w[17]), fragTo=int(w[18]), seqIdText=w[2], evalText=w[3]))
-        want[ck] = reflib.fmt_dp(o.chain(cands, tdb.total_residues, max_sets=2), cands)
+    want = reflib.oracle_pipeline(o, contigs, list(range(len(prots))), [len(p) for p in prots], max_sets=2)["dp"]
     assert sum(v.count("\n") for v in want.values()) > 20, "the planted genes must produce calls"
     assert any(int(l.split("\t")[4]) > 1 for v in want.values() for l in v.splitlines()), "multi-exon calls expected"
     assert got == want
@@ -370,29 +379,45 @@ def test_limits_fail_loudly():
     ctx.close()
 
 
+def test_persisted_index_save_load_round_trip(tmp_path):
+    """the resident index written in the reference's index-DB layout and loaded into a fresh context (mmap + upload, no rebuild)
+    must give the reference's prefilter and exon calls; a DB written on the host alone (mb200_index_file_write) must load to the same index"""
+    from metaeuk_b200 import lib as mlib
+    c = reflib.load_case("contigs_sets")
+    ctx, tdb = ctx_for(c, max_exon_sets=c["max_exon_sets"])
+    ctx.target_keys_set(np.array(tdb.keys, np.uint32))
+    path = str(tmp_path / "targets.idx")
+    ctx.index_save(path)
+    sizes = ctx.index_sizes()
+    ctx.close()
+    m, off = M.encode_many(tdb.masked); u, _ = M.encode_many(tdb.seqs)
+    path2 = str(tmp_path / "targets_host.idx")
+    mlib.index_file_write(path2, m, u, off, keys=np.array(tdb.keys, np.uint32), kmer_thr=c["kmer_thr"], mask_mode=1)
+    for pth in (path, path2):
+        ctx2 = mlib.Context(0)
+        ctx2.set_params(kmer_thr=c["kmer_thr"], max_exon_sets=c["max_exon_sets"])
+        ctx2.matrices_default()
+        ctx2.index_load(pth)
+        assert ctx2.index_sizes() == sizes
+        assert list(ctx2.target_keys_get()) == tdb.keys
+        got = strkeys(M.prefilter(ctx2, c["queries"][:800], tdb))
+        assert all(got[str(k)] == c["pref"].get(str(k), "") for k, _ in c["queries"][:800])
+        dp = M.predictexons_contigs(ctx2, [tuple(x) for x in c["contigs"]], tdb)
+        assert strkeys(dp) == c["dp"]
+        ctx2.close()
+    # a context with another k-mer threshold must refuse the file
+    ctx3 = mlib.Context(0)
+    ctx3.set_params(kmer_thr=c["kmer_thr"] + 5)
+    ctx3.matrices_default()
+    with pytest.raises(Exception):
+        ctx3.index_load(path)
+    ctx3.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # C++ host driver (metaeuk_b200/bin/mb200): the reference's module surface on MMseqs database files
 # ------------------------------------------------------------------------------------------------
-def write_db(path, entries, dbtype):
-    import struct
-    pos = 0
-    with open(path, "wb") as f, open(path + ".index", "w") as fi:
-        for k, e in entries:
-            b = e.encode() + b"\0"
-            f.write(b)
-            fi.write("%d\t%d\t%d\n" % (k, pos, len(b)))
-            pos += len(b)
-    with open(path + ".dbtype", "wb") as f:
-        f.write(struct.pack("<i", dbtype))
-
-
-def read_db(path):
-    data = open(path, "rb").read()
-    out = {}
-    for line in open(path + ".index"):
-        k, o, l = line.split("\t")
-        out[k] = data[int(o):int(o) + int(l) - 1].decode()
-    return out
+write_db, read_db = reflib.write_db, reflib.read_db
 
 
 def test_cli_modules_on_database_files(tmp_path):
@@ -433,5 +458,11 @@ def test_cli_modules_on_database_files(tmp_path):
     # same, in batches of about 20 kb of contigs, and with the reference's text DBs between the stages instead of the binary records
     subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp4", "--max-exon-sets", str(c["max_exon_sets"]), "--batch-nt", "20000"] + common)
     assert read_db(d + "/dp4") == c["dp"]
+    # persisted index: built on the host (no GPU), then every search module takes it instead of rebuilding
+    subprocess.check_call([exe, "gpucreateindex", d + "/proteins", d + "/proteins.idx"] + common)
+    subprocess.check_call([exe, "gpuprefilter", d + "/aa_6f", d + "/proteins", d + "/pref_idx", "--index-db", d + "/proteins.idx"] + common)
+    assert read_db(d + "/pref_idx") == pref
+    subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp6", "--max-exon-sets", str(c["max_exon_sets"]), "--index-db", d + "/proteins.idx"] + common)
+    assert read_db(d + "/dp6") == c["dp"]
     subprocess.check_call([exe, "gpupredictexons", d + "/contigs_nt", d + "/proteins", d + "/dp5", "--max-exon-sets", str(c["max_exon_sets"]), "--text-stages", "1"] + common)
     assert read_db(d + "/dp5") == c["dp"]

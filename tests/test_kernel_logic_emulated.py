@@ -123,12 +123,19 @@ class _PExon(C.Structure):
 
 
 @pytest.mark.parametrize("key_stride", [1, 7], ids=["keys=ids", "keys!=ids"])
-@pytest.mark.parametrize("name", ["contigs_small", "contigs_sets"])
+@pytest.mark.parametrize("name", ["contigs_small", "contigs_sets", "ref:minus_strand", "ref:multi_exon", "ref:two_contigs", "ref:target_overlap", "ref:cluster_rep", "ref:target_cov"])
 def test_binary_handoff_and_chain_logic_match_reference_text(emu, name, key_stride):
     """accepted alignments (binary) + fragment records -> join_by_contig -> mb_chain_contig -> call/exon records must print to the
     reference's search_res_by_contig and dp_predictions entries byte for byte (the product's host_join.cpp + chain_core.cuh on the CPU).
-    With key_stride 7 the target DB keys differ from the local ids and their order is reversed, so the (key, ORF) ordering is exercised."""
-    c = reflib.load_case(name)
+    With key_stride 7 the target DB keys differ from the local ids and their order is reversed, so the (key, ORF) ordering is exercised.
+    "ref:*" = the data sets of the reference's own test suite with run.sh's flags (--set-gap-extend, --metaeuk-tcov)."""
+    if name.startswith("ref:"):
+        c = reflib.load_case("ref_tests")["sets"][name[4:]]
+        c["max_exon_sets"] = 1
+        c["contig_lens"] = {str(k): len(s) for k, s in c["contigs"]}
+    else:
+        c = reflib.load_case(name)
+    gap_extend, tcov = c.get("set_gap_extend", -1), c.get("tcov", 0.5)
     nT = len(c["targets"])
     keyof = lambda t: t if key_stride == 1 else (nT - 1 - t) * key_stride + 3      # noqa: E731  (local id -> DB key)
     rekey = {k: keyof(i) for i, (k, _) in enumerate(c["targets"])}
@@ -187,7 +194,7 @@ def test_binary_handoff_and_chain_logic_match_reference_text(emu, name, key_stri
         calls = (reflib.Call * max(1, 2 * (e - b)))(); exons = (reflib.Exon * max(1, e - b))()
         sub = (reflib.Cand * max(1, e - b))(*[cands[k] for k in range(b, e)])
         emu.emu_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]
-        nc = emu.emu_chain(sub, e - b, 15, 10000, 11, 10, -1, -1, c["max_exon_sets"], 0.5, total_res, 0.001, calls, exons)
+        nc = emu.emu_chain(sub, e - b, 15, 10000, 11, 10, -1, gap_extend, c["max_exon_sets"], tcov, total_res, 0.001, calls, exons)
         assert nc >= 0
         got = ""
         for k in range(nc):
@@ -203,3 +210,59 @@ def test_binary_handoff_and_chain_logic_match_reference_text(emu, name, key_stri
             assert sorted(got.splitlines()) == sorted(rekey_lines(c["dp"][str(ck)], [0], False).splitlines()), ck
             ks = [int(l.split("\t")[0]) for l in got.splitlines()]
             assert ks == sorted(ks)
+
+
+# ---- persisted index DB ---------------------------------------------------------------------------------------
+def _open_indexdb(emu, path):
+    emu.emu_indexdb_open.restype = C.c_void_p
+    emu.emu_indexdb_ptr.restype = C.c_void_p
+    err = C.create_string_buffer(512)
+    h = emu.emu_indexdb_open(os.fsencode(path), err, C.c_size_t(512))
+    if not h:
+        return None, err.value.decode()
+    h = C.c_void_p(h)
+    info = (C.c_uint64 * 3)(); meta = (C.c_int * 12)()
+    emu.emu_indexdb_info(h, info, meta)
+    nent, nseq, nres = (int(x) for x in info)
+
+    def view(which, dtype, count):
+        n = count * np.dtype(dtype).itemsize
+        if n == 0:
+            return np.zeros(0, dtype)
+        return np.frombuffer((C.c_char * n).from_address(emu.emu_indexdb_ptr(h, which)), dtype=dtype).copy()
+    d = dict(h=h, meta=list(meta), n_entries=nent, n_seq=nseq, offsets=view(0, np.uint64, reflib.TABLE + 1), entries6=view(1, np.uint8, 6 * nent), masked=view(2, np.uint8, nres),
+             seq_off=view(3, np.uint64, nseq + 1), keys=view(4, np.uint32, nseq), unmasked=view(5, np.uint8, nres))
+    emu.emu_indexdb_close(h)
+    return d, ""
+
+
+@pytest.mark.parametrize("name", ["frag_small", "contigs_sets"])
+def test_persisted_index_db_round_trip_and_reference_digests(emu, name, tmp_path):
+    """write the index in the reference's index-DB layout, read it back: ENTRIES / ENTRIESOFFSETS must be the bytes the reference's indexdb
+    wrote for the same targets (golden digests), masked / unmasked residues, offsets and DB keys must survive, META must say what was built"""
+    c = reflib.load_case(name)
+    m, off = reflib.pack(c["masked_targets"]); u, _ = reflib.pack([s for _, s in c["targets"]])
+    keys = np.array([3 * k + 11 for k, _ in c["targets"]], np.uint32)
+    path = str(tmp_path / "targets.idx")
+    p = reflib._p
+    assert emu.emu_indexdb_write(os.fsencode(path), p(m, C.c_uint8), p(u, C.c_uint8), p(off, C.c_uint64), C.c_uint32(len(keys)), p(keys, C.c_uint32), c["kmer_thr"], c["mask"]) == 0
+    assert open(path + ".dbtype", "rb").read() == (9).to_bytes(4, "little")
+    d, err = _open_indexdb(emu, path)
+    assert d is not None, err
+    assert d["n_entries"] == c["idx_n_entries"] and d["n_seq"] == len(keys)
+    assert hashlib.sha256(d["entries6"].tobytes()).hexdigest() == c["idx_entries_sha256"]
+    assert hashlib.sha256(d["offsets"].tobytes()).hexdigest() == c["idx_offsets_u64_sha256"]
+    assert (d["masked"] == m).all() and (d["unmasked"] == u).all() and (d["seq_off"] == off).all() and (d["keys"] == keys).all()
+    assert d["meta"][1:7] == [6, 1, 21, 1 if c["mask"] else 0, 1, c["kmer_thr"]] and d["meta"][11] == 1
+    # every entry starts on a page boundary and ends with the writer's NUL, as DBWriter::writeData + alignToPageSize leave it
+    data = open(path, "rb").read()
+    for line in open(path + ".index"):
+        k, o, l = (int(x) for x in line.split("\t"))
+        if k not in (7, 8):
+            assert o % 4096 == 0 and data[o + l - 1] == 0, k
+    # damaged / foreign files fail loudly
+    with open(path + ".index") as f:
+        lines = [l for l in f if not l.startswith("9\t")]
+    open(path + ".index", "w").writelines(lines)
+    d2, err = _open_indexdb(emu, path)
+    assert d2 is None and "ENTRIES" in err
