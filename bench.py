@@ -176,6 +176,10 @@ def bench_predict(args, wl, base, rank, world, local, threads):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     ctx.matrices_default()
+    if args.sw_kernel:
+        ctx.option_set("sw_kernel", args.sw_kernel)
+    if args.lane_max_hits:
+        ctx.option_set("sw_lane_max_hits", args.lane_max_hits)
     t_idx0 = time.perf_counter()
     prot, poff = gen_proteins(wl["n_prot"])
     if rank == 0:
@@ -522,6 +526,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="fragments in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--sw-kernel", type=int, default=0, help="forward alignment kernel variant (diagnostic; 0 = library default)")
+    ap.add_argument("--lane-max-hits", type=int, default=0, help="sw_lane_max_hits (diagnostic; 0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -597,6 +602,8 @@ def main():
     ctx.matrices_default()
     if args.sw_kernel:
         ctx.option_set("sw_kernel", args.sw_kernel)
+    if args.lane_max_hits:
+        ctx.option_set("sw_lane_max_hits", args.lane_max_hits)
     t_idx0 = time.perf_counter()
     prot, poff = gen_proteins(wl["n_prot"])
     if rank == 0:

@@ -156,7 +156,7 @@ struct mb200_ctx {
     DevBuf<MbPrefHit> dHits; DevBuf<uint32_t> dHitCount, dStatus, dCounter; DevBuf<MbPrefStats> dStats; DevBuf<unsigned long long> dCells;
     bool havePref = false;
     // align
-    DevBuf<uint32_t> dPairOff, dChunkOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
+    DevBuf<uint32_t> dPairOff, dChunkOff, dLaneOff, dWaveOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
     DevBuf<uint64_t> dHitOff64; DevBuf<uint16_t> dPerm; DevBuf<uint32_t> dBnd;
     std::vector<int> minScore;   // per query length, -2 = not computed
     std::vector<uint32_t> hOrder;   // queries by descending length
@@ -169,7 +169,7 @@ struct mb200_ctx {
     bool haveAln = false;
     // predictexons with binary hand-off
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20;
-    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 2, optTraceKernel = 2;   // mb200_option_set
+    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
 };
@@ -273,7 +273,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
-    c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dPassList.release();
+    c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
     c->pFlatHits.release(); c->pOff.release(); c->pStatus.release(); c->pOrfRecs.release(); c->pOrfAa.release();
     c->dNuc.release(); c->dNucOff.release(); c->dOrfAaCnt.release(); c->dOrfRecBase.release(); c->dOrfAaBase.release(); c->dOrfCnt.release(); c->dOrfTab.release(); c->dOrfRecs.release(); c->dOrfAa.release(); c->dOrfCodes.release();
@@ -286,7 +286,8 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
     else if (n == "prefilter_config") { if (value < 0 || value > 2) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense) or 2 (sparse)"); c->optPrefCfg = (int)value; }
-    else if (n == "sw_kernel") { if (value < 1 || value > 3) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit) or 3 (packed, per-lane state machine)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_kernel") { if (value < 1 || value > 5) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane) or 5 (4 + row blocks of an alignment spread over lanes)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
@@ -697,9 +698,13 @@ static int align_pipeline(mb200_ctx *c) {
     c->st.sw_pairs = 0; c->st.sw_cells_fwd = c->st.sw_cells_rev = 0; c->st.ms_sw_fwd = c->st.ms_sw_rev = 0; c->st.sw_target_bytes = 0;
     if (nQ == 0) { c->haveAln = true; return 0; }
     if ((uint64_t)nQ * maxHits >= (1ull << 32)) return fail(MB200_E_LIMIT, "n_queries * max_res_list_len must be < 2^32 per call");
-    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(64)); TRY(c->dCells.alloc(2));
+    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dLaneOff.alloc(nQ + 1)); TRY(c->dWaveOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(64)); TRY(c->dCells.alloc(2));
     CU(cudaMemsetAsync(c->dCounter.p, 0, 64 * 4, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 16, c->stream));
-    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p);
+    // sw_kernel 4: queries of at most 64 residues with at most sw_lane_max_hits hits go to k_sw_lanes (one (query, 2 hits) item per lane), the rest to k_sw_rows2
+    // sw_kernel 5: the other queries of at most 512 residues go to k_sw_wave (the row blocks of one alignment on neighbouring lanes)
+    const bool laneMode = c->optSwKernel >= 4 && maxHits <= 1024, waveMode = c->optSwKernel == 5 && maxHits <= 1024;
+    k_scan_counts<<<4, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 64u,
+                                                       laneMode ? (uint32_t)c->optLaneMaxHits : 0u, waveMode ? 512u : 0u);
     CU(cudaGetLastError());
     uint32_t nPairs = 0;
     CU(cudaMemcpyAsync(&nPairs, c->dPairOff.p + nQ, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -728,7 +733,7 @@ static int align_pipeline(mb200_ctx *c) {
     uint32_t maxT = 1; for (uint32_t t = 0; t < c->nT; t++) maxT = std::max<uint32_t>(maxT, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
     CU(cudaEventRecord(c->ev0, c->stream));
     const uint32_t bounds[3] = {pLong, firstLE(256), nQ}; const uint32_t strides[2] = {1024 + 16, 256 + 16};
-    const bool packed = c->optSwKernel >= 2;   // 1 = one target per lane (32-bit cells), 2 = two targets per lane (packed 16-bit cells)
+    const bool packed = c->optSwKernel >= 2;   // (4 = 2 for the queries that stay with the chunk kernel)   // 1 = one target per lane (32-bit cells), 2 = two targets per lane (packed 16-bit cells)
     for (int k = 0; k < 2; k++) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
@@ -766,6 +771,48 @@ static int align_pipeline(mb200_ctx *c) {
                                                                          c->dBnd.p, maxT);
         }
         CU(cudaGetLastError()); c->st.launches++;
+    }
+    if (waveMode) {
+        // positions [firstLE(512), firstLE(256)) hold the queries of 257..512 residues (profile stride 528), [firstLE(256), nQ) those of <= 256 (stride 272)
+        const uint32_t wbnd[3] = {firstLE(512), firstLE(256), nQ}; const uint32_t wstr[2] = {512 + 16, 256 + 16};
+        for (int k = 0; k < 2; k++) {
+            if (wbnd[k] >= wbnd[k + 1]) continue;
+            int W = (int)((100u * 1024u) / (2u * 22u * wstr[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
+            const size_t smem = (size_t)W * 2u * 22u * wstr[k];
+            CU(cudaFuncSetAttribute(k_sw_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_wave, W * 32, smem)); if (perSM < 1) perSM = 1;
+            k_sw_wave<<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dWaveOff.p, wbnd[k], wbnd[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                 c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                 wstr[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 4 + k, c->dCells.p, dErr);
+            CU(cudaGetLastError()); c->st.launches++;
+        }
+    }
+    if (laneMode) {
+        // positions [firstLE(64), firstLE(32)) hold the queries of 33..64 residues (two row blocks), [firstLE(32), nQ) those of <= 32 (one block)
+        const uint32_t lb[3] = {firstLE(64), firstLE(32), nQ};
+        for (int k = 0; k < 2; k++) {
+            if (lb[k] >= lb[k + 1]) continue;
+            const int threads = k == 0 ? 128 : 256; const size_t smem = (size_t)threads * (22u * (k == 0 ? 64u : 32u) + 16u);
+            if (k == 0) CU(cudaFuncSetAttribute(k_sw_lanes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU(cudaFuncSetAttribute(k_sw_lanes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int perSM = 1;
+            if (k == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_lanes<64>, threads, smem));
+            else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_lanes<32>, threads, smem));
+            if (perSM < 1) perSM = 1;
+            const int blocks = c->nSM * perSM;
+            TRY(c->dBnd.alloc((size_t)blocks * (threads / 32) * maxT * 32u * 2u));
+            if (k == 0)
+                k_sw_lanes<64><<<blocks, threads, smem, c->stream>>>(c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                   c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                   c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 2 + k, c->dCells.p, dErr,
+                                                                   reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
+            else
+                k_sw_lanes<32><<<blocks, threads, smem, c->stream>>>(c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                                                                   c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
+                                                                   c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 2 + k, c->dCells.p, dErr,
+                                                                   reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
+            CU(cudaGetLastError()); c->st.launches++;
+        }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     uint32_t hn[2] = {0, 0};
@@ -851,7 +898,7 @@ static int download_hits_compact(mb200_ctx *c) {
     c->hHitOff.assign(nQ + 1, 0); c->nFlatHits = 0;
     if (nQ == 0) return 0;
     TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->pOff.alloc(nQ + 1));
-    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p);
+    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, nullptr, nullptr, c->dQoff.p, 0u, 0u, 0u);
     CU(cudaGetLastError());
     uint32_t *off = c->pOff.p;
     CU(cudaEventRecord(c->ev0, c->stream));

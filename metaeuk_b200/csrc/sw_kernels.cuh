@@ -275,6 +275,198 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows2(
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// k_sw_lanes: the packed arithmetic of k_sw_rows2 with ONE work item per LANE: (query, two of its hits).  Six-frame fragments of
+// metagenomic contigs are short (mean 37 residues) and most of them have a handful of hits, so a half-warp per query leaves 14 of 16 lanes
+// idle (C4: 2 hits per fragment on average).  Here every lane builds its own query profile in shared memory (22 x STRIDE bytes, STRIDE = 32
+// or 64 rows) and sweeps its own pair of targets; a warp takes 32 consecutive items of the length-sorted item list, so its lanes run the
+// same number of row blocks.  Queries with more than laneMaxHits hits or more than 64 residues stay with k_sw_rows2.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(STRIDE == 32 ? 256 : 128) k_sw_lanes(
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ laneOff, uint32_t pBegin, uint32_t pEnd,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
+    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
+    const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
+    constexpr int RB = 32;
+    constexpr uint32_t LANE_BYTES = 22u * STRIDE + 16u;       // an odd multiple of 16 bytes: the 128-bit profile loads of 8 neighbouring lanes fall into 8 different bank groups
+    extern __shared__ __align__(16) unsigned char dynProf[];
+    __shared__ int8_t sMat8[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)threadIdx.x * LANE_BYTES;
+    uint2 *myBnd = bnd + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * maxT * 32u + lane;
+    const uint32_t itemBase = laneOff[pBegin], itemEnd = laneOff[pEnd];
+    const uint32_t negE2 = (uint32_t)(uint16_t)(int16_t)(-gapE) * 0x10001u, go2 = (uint32_t)(uint16_t)(int16_t)(-gapO) * 0x10001u;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = itemBase + atomicAdd(counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= itemEnd) break;
+        const uint32_t item = base + lane;
+        if (item < itemEnd) {
+            uint32_t lo = pBegin, hi = pEnd;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (laneOff[mid] <= item) lo = mid; else hi = mid; }
+            const uint32_t qi = order[lo], kk0 = (item - laneOff[lo]) * 2u, cnt = hitCount[qi];
+            const uint64_t qb = qoff[qi]; const int L = (int)(qoff[qi + 1] - qb);
+            // this lane's profile: prof[t][j] = mat[t][q_j] + compBias8[j]; rows past the query end and the padding residue can only lower scores
+            for (int j4 = 0; j4 < STRIDE; j4 += 4) {
+                uint32_t qv[4]; int cv[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) { const bool in = j4 + x < L; qv[x] = in ? (uint32_t)qres[qb + j4 + x] : 0u; cv[x] = in ? (int)cb[qb + j4 + x] : 0; }
+                for (uint32_t t = 0; t < 22u; t++) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const int v = (t < 21u && j4 + x < L) ? (int)(int8_t)(sMat8[t * 21u + qv[x]] + cv[x]) : -64;
+                        w |= (uint32_t)(uint8_t)(int8_t)v << (8 * x);
+                    }
+                    *reinterpret_cast<uint32_t *>(prof + t * STRIDE + j4) = w;
+                }
+            }
+            const bool actB = kk0 + 1 < cnt;
+            size_t slotA, slotB = 0; int lenA, lenB = 0; const uint8_t *tA, *tB = tseq;
+            { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kk0] : kk0; slotA = (size_t)qi * maxHits + k;
+              const uint32_t tid = hits[slotA].seqId; const uint64_t tb = toff[tid]; lenA = (int)(toff[tid + 1] - tb); tA = tseq + tb; }
+            if (actB) { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kk0 + 1] : kk0 + 1; slotB = (size_t)qi * maxHits + k;
+                        const uint32_t tid = hits[slotB].seqId; const uint64_t tb = toff[tid]; lenB = (int)(toff[tid + 1] - tb); tB = tseq + tb; }
+            uint32_t mx = 0;
+            const int nb = (L + RB - 1) / RB;
+            for (int b = 0; b < nb; b++) {
+                const bool hasTop = b > 0, hasBottom = b < nb - 1;
+                if (L - b * RB <= RB / 2) sw_sweep_block2<RB / 2>(prof + b * RB, STRIDE, tA, lenA, tB, lenB, myBnd, hasTop, hasBottom, go2, negE2, mx);
+                else sw_sweep_block2<RB>(prof + b * RB, STRIDE, tA, lenA, tB, lenB, myBnd, hasTop, hasBottom, go2, negE2, mx);
+                cells += (unsigned long long)(lenA + lenB) * ((L - b * RB <= RB / 2) ? RB / 2 : RB);
+            }
+            const int sA = (int)(int16_t)(mx & 0xFFFFu), sB = (int)(int16_t)(mx >> 16);
+            { scoreOut[slotA] = sA; if (sA >= 32000) atomicExch(errFlag, 1u);
+              if (sA >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotA; else atomicExch(errFlag, 2u); } }
+            if (actB) { scoreOut[slotB] = sB; if (sB >= 32000) atomicExch(errFlag, 1u);
+                        if (sB >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotB; else atomicExch(errFlag, 2u); } }
+        }
+        __syncwarp();
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_sw_wave: the packed arithmetic with the ROW BLOCKS of one alignment spread over neighbouring lanes.  k_sw_rows2 gives a lane one pair of
+// targets and lets it sweep the query's 32-row blocks one after the other (block boundaries through global memory); a query with few hits then
+// occupies few of the 16 lanes of its half-warp.  Here a pair of targets is aligned by nb = ceil(L / 32) lanes at once: lane b owns rows
+// [32 b, 32 b + 32) and runs b columns behind lane b - 1, whose bottom row (H, F) of the column it needs arrives by one shuffle per step -- a
+// systolic wavefront along the query.  A half-warp (one query profile in shared memory) therefore carries 16 / nb pairs = 2 * (16 / nb) hits per
+// item: 16 pairs for L <= 32 (the k_sw_rows2 layout), 4 pairs for L = 100, one pair for L in (256, 512].  No boundary traffic to global memory.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ waveOff, uint32_t pBegin, uint32_t pEnd,
+    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
+    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
+    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
+    uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag) {
+    constexpr int RB = 32;
+    extern __shared__ __align__(16) unsigned char dynProf[];
+    __shared__ int8_t sMat8[448];
+    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15u;
+    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)(wib * 2u + half) * 22u * profStride;   // row 21 = padding residue
+    const uint32_t itemBase = waveOff[pBegin], itemEnd = waveOff[pEnd];
+    const uint32_t negE2 = (uint32_t)(uint16_t)(int16_t)(-gapE) * 0x10001u, go2 = (uint32_t)(uint16_t)(int16_t)(-gapO) * 0x10001u;
+    const uint32_t MIN2 = 0x80008000u;
+    unsigned long long cells = 0;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = itemBase + atomicAdd(counter, 2u);
+        item = __shfl_sync(0xffffffffu, item, 0) + half;           // half-warp 0 / 1 take consecutive work items
+        if (__all_sync(0xffffffffu, item >= itemEnd)) break;
+        const bool haveItem = item < itemEnd;
+        uint32_t qi = 0, cnt = 0, nb = 1, kk0 = 0; int L = 0; uint64_t qb = 0;
+        if (haveItem) {
+            uint32_t lo = pBegin, hi = pEnd;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (waveOff[mid] <= item) lo = mid; else hi = mid; }
+            qi = order[lo]; cnt = hitCount[qi]; qb = qoff[qi]; L = (int)(qoff[qi + 1] - qb);
+            nb = (uint32_t)(L + RB - 1) / RB; if (nb == 0) nb = 1;
+            kk0 = (item - waveOff[lo]) * 2u * (16u / nb);
+        }
+        __syncwarp();
+        if (haveItem) for (uint32_t idx = l16; idx < 22u * profStride; idx += 16u) {
+            const uint32_t t = idx / profStride, j = idx - t * profStride;
+            prof[idx] = (t < 21u && j < (uint32_t)L) ? (int8_t)(sMat8[t * 21 + qres[qb + j]] + cb[qb + j]) : (int8_t)-64;
+        }
+        __syncwarp();
+        const uint32_t slotInItem = l16 / nb, b = l16 - slotInItem * nb;     // which pair of the item, which row block of the pair
+        const bool valid = haveItem && slotInItem < 16u / nb;
+        const uint32_t kA = kk0 + 2u * slotInItem;
+        const bool actA = valid && kA < cnt, actB = valid && kA + 1 < cnt;
+        size_t slotA = 0, slotB = 0; int lenA = 0, lenB = 0; const uint8_t *tA = tseq, *tB = tseq;
+        if (actA) { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kA] : kA; slotA = (size_t)qi * maxHits + k;
+                    const uint32_t tid = hits[slotA].seqId; const uint64_t tb = toff[tid]; lenA = (int)(toff[tid + 1] - tb); tA = tseq + tb; }
+        if (actB) { const uint32_t k = perm ? (uint32_t)perm[(size_t)qi * maxHits + kA + 1] : kA + 1; slotB = (size_t)qi * maxHits + k;
+                    const uint32_t tid = hits[slotB].seqId; const uint64_t tb = toff[tid]; lenB = (int)(toff[tid + 1] - tb); tB = tseq + tb; }
+        const int n = lenA > lenB ? lenA : lenB;
+        const int nSteps = __reduce_max_sync(0xffffffffu, n > 0 ? n + (int)nb - 1 : 0);
+        const int8_t *profB = prof + b * RB;
+        uint32_t Hp[RB], E[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) { Hp[r] = 0; E[r] = 0; }
+        uint32_t prevTop = 0, mx = 0; uint2 bottom = make_uint2(0u, 0u);
+        uint32_t taNext = 21u, tbNext = 21u;
+        if (b == 0 && n > 0) { taNext = lenA > 0 ? (uint32_t)tA[0] : 21u; tbNext = lenB > 0 ? (uint32_t)tB[0] : 21u; }
+        for (int s = 0; s < nSteps; s++) {
+            uint2 top;
+            top.x = __shfl_up_sync(0xffffffffu, bottom.x, 1); top.y = __shfl_up_sync(0xffffffffu, bottom.y, 1);
+            if (b == 0) top = make_uint2(0u, 0u);
+            const int i = s - (int)b;
+            if (i >= 0 && i < n) {
+                const uint32_t ta = taNext, tb = tbNext;
+                taNext = (i + 1 < lenA) ? (uint32_t)tA[i + 1] : 21u; tbNext = (i + 1 < lenB) ? (uint32_t)tB[i + 1] : 21u;
+                const uint4 *pa = reinterpret_cast<const uint4 *>(profB + ta * profStride);
+                const uint4 *pb = reinterpret_cast<const uint4 *>(profB + tb * profStride);
+                uint32_t wa[RB / 4], wb[RB / 4];
+#pragma unroll
+                for (int v = 0; v < RB / 16; v++) {
+                    const uint4 x = pa[v], y = pb[v];
+                    wa[4 * v] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
+                    wb[4 * v] = y.x; wb[4 * v + 1] = y.y; wb[4 * v + 2] = y.z; wb[4 * v + 3] = y.w;
+                }
+                uint32_t F = top.y, diag = prevTop, gUp = 0; prevTop = top.x;
+#pragma unroll
+                for (int r = 0; r < RB; r++) {
+                    const uint32_t sc = sw_pack_scores(wa[r >> 2], wb[r >> 2], r & 3);
+                    const uint32_t f = (r == 0) ? F : __viaddmax_s16x2(F, negE2, gUp);
+                    const uint32_t t1 = __viaddmax_s16x2(diag, sc, E[r]);
+                    const uint32_t h = __vimax_s16x2_relu(t1, f);
+                    diag = Hp[r]; Hp[r] = h;
+                    const uint32_t g = __viaddmax_s16x2(h, go2, MIN2);
+                    E[r] = __viaddmax_s16x2_relu(E[r], negE2, g);
+                    F = f; gUp = g;
+                    mx = __vmaxs2(mx, h);
+                }
+                bottom = make_uint2(Hp[RB - 1], __viaddmax_s16x2_relu(F, negE2, gUp));
+            } else if (i == -1 && n > 0) {      // the step before this lane's first column: fetch its first residues
+                taNext = lenA > 0 ? (uint32_t)tA[0] : 21u; tbNext = lenB > 0 ? (uint32_t)tB[0] : 21u;
+            }
+        }
+        if (n > 0) { const int rows = L - (int)b * RB; cells += (unsigned long long)(lenA + lenB) * (unsigned)(rows > RB ? RB : (rows > 0 ? rows : 0)); }
+        // maximum over the row blocks of the pair -> the lane of block 0
+#pragma unroll
+        for (int d = 1; d < 16; d++) { const uint32_t y = __shfl_down_sync(0xffffffffu, mx, d); if (b + (uint32_t)d < nb) mx = __vmaxs2(mx, y); }
+        if (b == 0) {
+            const int sA = (int)(int16_t)(mx & 0xFFFFu), sB = (int)(int16_t)(mx >> 16);
+            if (actA) { scoreOut[slotA] = sA; if (sA >= 32000) atomicExch(errFlag, 1u);
+                        if (sA >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotA; else atomicExch(errFlag, 2u); } }
+            if (actB) { scoreOut[slotB] = sB; if (sB >= 32000) atomicExch(errFlag, 1u);
+                        if (sB >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotB; else atomicExch(errFlag, 2u); } }
+        }
+    }
+    if (cells) atomicAdd(cellCount, cells);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // k_sw_rows3: the packed kernel reorganised as a per-lane state machine.  A half-warp owns one QUERY at a time (its profile sits in
 // shared memory); the query's hits, sorted by target length, are dealt to the 16 lanes two at a time in snake order (longest pairs
 // first, direction alternating per round) so every lane gets nearly the same number of columns.  Each lane walks its own sequence of
@@ -599,18 +791,41 @@ __global__ void __launch_bounds__(128) k_sw_trace2(const uint32_t *__restrict__ 
     if (cells) atomicAdd(cellCount, cells);
 }
 
-// exclusive scans over the prefilter result: pairOff[i] (natural query order) and chunkOff[p] (length-sorted order, 32 hits per chunk)
+// exclusive scans over the prefilter result: pairOff[i] (natural query order) and, in length-sorted order, the work lists of the three
+// forward kernels.  A query with L residues and n hits goes to
+//   k_sw_lanes  (laneOff, items of 2 hits)                     when laneMaxHits != 0, n <= laneMaxHits and L <= laneMaxL,
+//   k_sw_wave   (waveOff, items of 2 * (16 / ceil(L/32)) hits) when L <= waveMaxL (0 = never),
+//   k_sw_rows*  (chunkOff, chunks of 32 hits)                  otherwise.            laneOff / waveOff may be NULL.
+__device__ __forceinline__ int sw_query_class(uint32_t L, uint32_t n, uint32_t laneMaxL, uint32_t laneMaxHits, uint32_t waveMaxL) {
+    if (laneMaxHits && n <= laneMaxHits && L <= laneMaxL) return 1;
+    if (L <= waveMaxL) return 2;
+    return 0;
+}
 __global__ void __launch_bounds__(MB_CTA_THREADS) k_scan_counts(const uint32_t *__restrict__ hitCount, const uint32_t *__restrict__ order, uint32_t nQ,
-                                                                uint32_t *pairOff, uint32_t *chunkOff) {
+                                                                uint32_t *pairOff, uint32_t *chunkOff, uint32_t *laneOff, uint32_t *waveOff, const uint64_t *__restrict__ qoff,
+                                                                uint32_t laneMaxL, uint32_t laneMaxHits, uint32_t waveMaxL) {
     __shared__ CtaScratch cs;
     if (blockIdx.x == 0) {
         for (uint32_t i = threadIdx.x; i < nQ; i += blockDim.x) pairOff[i] = hitCount[i];
         __syncthreads();
         cta_exclusive_scan(pairOff, nQ, &cs);
     } else {
-        for (uint32_t p = threadIdx.x; p < nQ; p += blockDim.x) chunkOff[p] = (hitCount[order[p]] + 31u) >> 5;
+        const int which = (int)blockIdx.x - 1;      // 0 chunk, 1 lane, 2 wave
+        uint32_t *out = which == 0 ? chunkOff : (which == 1 ? laneOff : waveOff);
+        if (!out) return;
+        for (uint32_t p = threadIdx.x; p < nQ; p += blockDim.x) {
+            const uint32_t q = order[p], n = hitCount[q], L = (uint32_t)(qoff[q + 1] - qoff[q]);
+            const int cls = sw_query_class(L, n, laneMaxL, laneMaxHits, waveMaxL);
+            uint32_t v = 0;
+            if (cls == which) {
+                if (which == 0) v = (n + 31u) >> 5;
+                else if (which == 1) v = (n + 1u) >> 1;
+                else { const uint32_t nb = (L + 31u) >> 5, per = 2u * (16u / (nb ? nb : 1u)); v = (n + per - 1u) / per; }
+            }
+            out[p] = v;
+        }
         __syncthreads();
-        cta_exclusive_scan(chunkOff, nQ, &cs);
+        cta_exclusive_scan(out, nQ, &cs);
     }
 }
 

@@ -40,12 +40,18 @@ def test_prefilter_golden(name, cfg):
     ctx.close()
 
 
-@pytest.mark.parametrize("sw", [1, 2, 3], ids=["rows", "rows2-packed", "rows3-state-machine"])
+@pytest.mark.parametrize("sw", [1, 2, 3, 4, (4, 1), (4, 1024), 5, (5, 1)],
+                         ids=["rows", "rows2-packed", "rows3-state-machine", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2"])
 @pytest.mark.parametrize("name", FRAG + CONTIG)
 def test_align_golden(name, sw):
-    """every forward alignment kernel variant (mb200_option_set "sw_kernel") must give the reference's result DB"""
+    """every forward alignment kernel variant (mb200_option_set "sw_kernel") must give the reference's result DB; 4 = queries of at most 64
+    residues with at most sw_lane_max_hits hits take the one-item-per-lane kernel, the others the chunk kernel; 5 (default) = as 4, and the other
+    queries of at most 512 residues take the wavefront kernel (row blocks of one alignment on neighbouring lanes)"""
     c = reflib.load_case(name)
     ctx, tdb = ctx_for(c)
+    if isinstance(sw, tuple):
+        ctx.option_set("sw_lane_max_hits", sw[1])
+        sw = sw[0]
     ctx.option_set("sw_kernel", sw)
     pref = {k: c["pref"].get(str(k), "") for k, _ in c["queries"]}
     got = strkeys(M.align(ctx, c["queries"], tdb, pref))
@@ -255,7 +261,7 @@ def test_reference_own_end_to_end_fixtures(ds):
     assert sorted(reflib.fmt_fasta_headers(strkeys(grouped), c["target_acc"], c["contig_acc"])) == sorted(c["as_should"]["as_should_final_grouped_predictions_rep.fas"])
     # the stage-by-stage route (text DBs between the stages) agrees too
     queries, headers = M.extractorfs(ctx, contigs)
-    assert {str(k): v for k, v in headers.items()} == c["orf_headers"] and queries == [(int(k), s) for k, s in c["queries"]]
+    assert {str(k): v for k, v in headers.items()} == c["orf_headers"] and dict(queries) == {int(k): s for k, s in c["queries"]}   # (fixture lists are in data-file order)
     aln, byc, dp2 = M.predictexons(ctx, queries, headers, {k: len(s) for k, s in contigs}, tdb)
     assert {str(k): v for k, v in aln.items() if v} == {k: v for k, v in c["aln"].items() if v}
     assert strkeys(byc) == c["bycontig"] and strkeys(dp2) == c["dp"]
