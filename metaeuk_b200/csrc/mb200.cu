@@ -168,6 +168,8 @@ struct mb200_ctx {
     PinBuf<mb200_hit> pFlatHits; PinBuf<uint32_t> pOff, pStatus; size_t nFlatHits = 0;
     bool haveAln = false;
     // predictexons with binary hand-off
+    DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
+    DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20;
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
@@ -276,6 +278,8 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
     c->pFlatHits.release(); c->pOff.release(); c->pStatus.release(); c->pOrfRecs.release(); c->pOrfAa.release();
+    c->dChCand.release(); c->dChOff.release(); c->dChPE.release(); c->dChOp.release(); c->dChOm.release(); c->dChCallCnt.release(); c->dChRows.release(); c->dChCalls.release();
+    c->dChEx.release(); c->dChExCnt.release(); c->pChCalls.release(); c->pChEx.release(); c->pChCnt.release();
     c->dNuc.release(); c->dNucOff.release(); c->dOrfAaCnt.release(); c->dOrfRecBase.release(); c->dOrfAaBase.release(); c->dOrfCnt.release(); c->dOrfTab.release(); c->dOrfRecs.release(); c->dOrfAa.release(); c->dOrfCodes.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -701,10 +705,10 @@ static int align_pipeline(mb200_ctx *c) {
     TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dLaneOff.alloc(nQ + 1)); TRY(c->dWaveOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(64)); TRY(c->dCells.alloc(2));
     CU(cudaMemsetAsync(c->dCounter.p, 0, 64 * 4, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 16, c->stream));
     // sw_kernel 4: queries of at most 64 residues with at most sw_lane_max_hits hits go to k_sw_lanes (one (query, 2 hits) item per lane), the rest to k_sw_rows2
-    // sw_kernel 5: the other queries of at most 512 residues go to k_sw_wave (the row blocks of one alignment on neighbouring lanes)
+    // sw_kernel 5: the other queries of at most 1024 residues go to k_sw_wave (the row blocks of one alignment on neighbouring lanes)
     const bool laneMode = c->optSwKernel >= 4 && maxHits <= 1024, waveMode = c->optSwKernel == 5 && maxHits <= 1024;
     k_scan_counts<<<4, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 64u,
-                                                       laneMode ? (uint32_t)c->optLaneMaxHits : 0u, waveMode ? 512u : 0u);
+                                                       laneMode ? (uint32_t)c->optLaneMaxHits : 0u, waveMode ? 1024u : 0u);
     CU(cudaGetLastError());
     uint32_t nPairs = 0;
     CU(cudaMemcpyAsync(&nPairs, c->dPairOff.p + nQ, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -720,6 +724,7 @@ static int align_pipeline(mb200_ctx *c) {
     TRY(c->dMinScore.alloc(ms.size())); TRY(upload(c->dMinScore.p, ms.data(), ms.size() * 4, c->stream));
     TRY(c->dScore.alloc((size_t)nQ * maxHits)); TRY(c->dPassList.alloc(nPairs));
     const bool usePerm = maxHits <= 1024;
+    CU(cudaEventRecord(c->ev0, c->stream));   // ms_sw_fwd = hit permutation + forward kernels
     if (usePerm) {
         TRY(c->dPerm.alloc((size_t)nQ * maxHits));
         k_perm_by_len<<<c->nSM * 8, 128, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dToff.p, nQ, maxHits, c->dPerm.p);
@@ -731,7 +736,6 @@ static int align_pipeline(mb200_ctx *c) {
     auto firstLE = [&](uint32_t x) { uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lenAt(mid) <= x) hi = mid; else lo = mid + 1; } return lo; };
     const uint32_t pLong = firstLE(1024);
     uint32_t maxT = 1; for (uint32_t t = 0; t < c->nT; t++) maxT = std::max<uint32_t>(maxT, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
-    CU(cudaEventRecord(c->ev0, c->stream));
     const uint32_t bounds[3] = {pLong, firstLE(256), nQ}; const uint32_t strides[2] = {1024 + 16, 256 + 16};
     const bool packed = c->optSwKernel >= 2;   // (4 = 2 for the queries that stay with the chunk kernel)   // 1 = one target per lane (32-bit cells), 2 = two targets per lane (packed 16-bit cells)
     for (int k = 0; k < 2; k++) {
@@ -773,17 +777,19 @@ static int align_pipeline(mb200_ctx *c) {
         CU(cudaGetLastError()); c->st.launches++;
     }
     if (waveMode) {
-        // positions [firstLE(512), firstLE(256)) hold the queries of 257..512 residues (profile stride 528), [firstLE(256), nQ) those of <= 256 (stride 272)
-        const uint32_t wbnd[3] = {firstLE(512), firstLE(256), nQ}; const uint32_t wstr[2] = {512 + 16, 256 + 16};
-        for (int k = 0; k < 2; k++) {
+        // by profile stride: positions [pLong, firstLE(512)) hold the queries of 513..1024 residues (one item per warp), [firstLE(512), firstLE(256)) those of
+        // 257..512, [firstLE(256), nQ) those of <= 256 (one item per half-warp)
+        const uint32_t wbnd[4] = {pLong, firstLE(512), firstLE(256), nQ}; const uint32_t wstr[3] = {1024 + 16, 512 + 16, 256 + 16}, wG[3] = {32, 16, 16};
+        for (int k = 0; k < 3; k++) {
             if (wbnd[k] >= wbnd[k + 1]) continue;
-            int W = (int)((100u * 1024u) / (2u * 22u * wstr[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
-            const size_t smem = (size_t)W * 2u * 22u * wstr[k];
+            const uint32_t perWarpBytes = (32u / wG[k]) * 22u * wstr[k];
+            int W = (int)((100u * 1024u) / perWarpBytes); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
+            const size_t smem = (size_t)W * perWarpBytes;
             CU(cudaFuncSetAttribute(k_sw_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_wave, W * 32, smem)); if (perSM < 1) perSM = 1;
             k_sw_wave<<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dWaveOff.p, wbnd[k], wbnd[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                                  c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
-                                                                 wstr[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 4 + k, c->dCells.p, dErr);
+                                                                 wstr[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 4 + k, c->dCells.p, dErr, wG[k]);
             CU(cudaGetLastError()); c->st.launches++;
         }
     }
@@ -1042,35 +1048,35 @@ int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, 
     const uint64_t n = candOff[nContigs];
     for (uint32_t i = 0; i < nContigs; i++) callCount[i] = 0;
     if (n == 0) return 0;
-    DevBuf<MbCand> dC; DevBuf<uint64_t> dOff; DevBuf<MbPE> dPE; DevBuf<int32_t> dOp, dOm, dCallCnt; DevBuf<MbRow> dRows; DevBuf<MbCall> dCalls; DevBuf<MbExon> dEx; DevBuf<uint32_t> dExCnt;
-    int rc = 0;
-    do {
-        if ((rc = dC.alloc(n)) || (rc = dOff.alloc(nContigs + 1)) || (rc = dPE.alloc(n)) || (rc = dOp.alloc(n)) || (rc = dOm.alloc(n)) || (rc = dRows.alloc(n)) ||
-            (rc = dCalls.alloc(2 * n)) || (rc = dEx.alloc(n)) || (rc = dCallCnt.alloc(nContigs)) || (rc = dExCnt.alloc(nContigs))) break;
-        static_assert(sizeof(MbCand) == sizeof(mb200_cand) && sizeof(MbCall) == sizeof(mb200_call) && sizeof(MbExon) == sizeof(mb200_exon), "ABI structs");
-        if ((rc = upload(dC.p, cands, n * sizeof(MbCand), c->stream)) || (rc = upload(dOff.p, candOff, (size_t)(nContigs + 1) * 8, c->stream))) break;
-        MbChainParams P; P.minIntron = c->par.min_intron; P.maxIntron = c->par.max_intron; P.minExonAa = c->par.min_exon_aa; P.maxOverlap = c->par.max_overlap;
-        P.gapOpen = c->par.set_gap_open; P.gapExtend = c->par.set_gap_extend; P.maxSets = c->par.max_exon_sets; P.tcov = c->par.tcov;
-        cudaEventRecord(c->ev0, c->stream);
-        k_chain<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(dC.p, dOff.p, nContigs, P, dPE.p, dOp.p, dOm.p, dRows.p, dCalls.p, dEx.p, dCallCnt.p, dExCnt.p);
-        cudaEventRecord(c->ev1, c->stream);
-        std::vector<MbCall> hCalls(2 * n); std::vector<MbExon> hEx(n); std::vector<int32_t> hCnt(nContigs);
-        cudaMemcpyAsync(hCalls.data(), dCalls.p, 2 * n * sizeof(MbCall), cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(hEx.data(), dEx.p, n * sizeof(MbExon), cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(hCnt.data(), dCallCnt.p, (size_t)nContigs * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { rc = fail(MB200_E_CUDA, "chain kernel: %s", cudaGetErrorString(e)); break; }
-        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->st.ms_chain = ms; c->st.launches++;
-        // host epilogue: set e-value and --metaeuk-eval filter (collectoptimalset.cpp:323-330); compact per contig
-        for (uint32_t ci = 0; ci < nContigs; ci++) {
-            if (hCnt[ci] < 0) { rc = fail(MB200_E_ARG, "contig %u: illegal codon segment length", ci); break; }
-            const uint64_t b = candOff[ci];
-            callCount[ci] = mb200::finish_calls(reinterpret_cast<const mb200_call *>(&hCalls[2 * b]), (uint32_t)hCnt[ci], reinterpret_cast<const mb200_exon *>(&hEx[b]), b, totalTargetResidues,
-                                                c->par.metaeuk_eval, calls + 2 * b, exons + b);
-        }
-    } while (0);
-    dC.release(); dOff.release(); dPE.release(); dOp.release(); dOm.release(); dRows.release(); dCalls.release(); dEx.release(); dCallCnt.release(); dExCnt.release();
-    return rc;
+    static_assert(sizeof(MbCand) == sizeof(mb200_cand) && sizeof(MbCall) == sizeof(mb200_call) && sizeof(MbExon) == sizeof(mb200_exon), "ABI structs");
+    // grow-only buffers owned by the context (a cudaMalloc / cudaFree pair per call costs more than the kernel)
+    TRY(c->dChCand.alloc(n)); TRY(c->dChOff.alloc(nContigs + 1)); TRY(c->dChPE.alloc(n)); TRY(c->dChOp.alloc(n)); TRY(c->dChOm.alloc(n)); TRY(c->dChRows.alloc(n));
+    TRY(c->dChCalls.alloc(2 * n)); TRY(c->dChEx.alloc(n)); TRY(c->dChCallCnt.alloc(nContigs)); TRY(c->dChExCnt.alloc(nContigs));
+    TRY(c->pChCalls.alloc(2 * n)); TRY(c->pChEx.alloc(n)); TRY(c->pChCnt.alloc(nContigs));
+    TRY(upload(c->dChCand.p, cands, n * sizeof(MbCand), c->stream)); TRY(upload(c->dChOff.p, candOff, (size_t)(nContigs + 1) * 8, c->stream));
+    MbChainParams P; P.minIntron = c->par.min_intron; P.maxIntron = c->par.max_intron; P.minExonAa = c->par.min_exon_aa; P.maxOverlap = c->par.max_overlap;
+    P.gapOpen = c->par.set_gap_open; P.gapExtend = c->par.set_gap_extend; P.maxSets = c->par.max_exon_sets; P.tcov = c->par.tcov;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    k_chain<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(c->dChCand.p, c->dChOff.p, nContigs, P, c->dChPE.p, c->dChOp.p, c->dChOm.p, c->dChRows.p, c->dChCalls.p, c->dChEx.p,
+                                                           c->dChCallCnt.p, c->dChExCnt.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, c->stream));
+    // only the used prefix of every contig's call / exon range is meaningful, but the ranges are interleaved with unused slots: copy whole arrays
+    CU(cudaMemcpyAsync(c->pChCalls.p, c->dChCalls.p, 2 * n * sizeof(MbCall), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->pChEx.p, c->dChEx.p, n * sizeof(MbExon), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->pChCnt.p, c->dChCallCnt.p, (size_t)nContigs * 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "chain kernel"));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_chain = ms; c->st.launches++;
+    // host epilogue: set e-value and --metaeuk-eval filter (collectoptimalset.cpp:323-330); compact per contig
+    const MbCall *hCalls = c->pChCalls.p; const MbExon *hEx = c->pChEx.p; const int32_t *hCnt = c->pChCnt.p;
+    for (uint32_t ci = 0; ci < nContigs; ci++) if (hCnt[ci] < 0) return fail(MB200_E_ARG, "contig %u: illegal codon segment length", ci);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (uint32_t ci = 0; ci < nContigs; ci++) {
+        const uint64_t b = candOff[ci];
+        callCount[ci] = mb200::finish_calls(reinterpret_cast<const mb200_call *>(&hCalls[2 * b]), (uint32_t)hCnt[ci], reinterpret_cast<const mb200_exon *>(&hEx[b]), b, totalTargetResidues,
+                                            c->par.metaeuk_eval, calls + 2 * b, exons + b);
+    }
+    return 0;
 }
 
 // ---- predictexons from contigs, binary records between the stages -----------------------------------------
@@ -1099,18 +1105,22 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     mb200_stats acc; memset(&acc, 0, sizeof(acc));
     const uint32_t launches0 = c->st.launches;
     uint64_t orfBase = 0;
+    // wall-clock per host phase, printed when MB200_TRACE is set (diagnostic)
+    double ph[9] = {0}; auto tp = std::chrono::steady_clock::now();
+    auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double, std::milli>(now - tp).count(); tp = now; };
     std::vector<mb200_cand> cands; std::vector<uint64_t> candOff, candAln; std::vector<mb200_call> bCalls; std::vector<mb200_exon> bExons; std::vector<uint32_t> bCnt;
     for (uint32_t b0 = 0; b0 < nContigs;) {
         uint32_t b1 = b0 + 1;
         while (b1 < nContigs && off[b1 + 1] - off[b0] <= c->optBatchNt) b1++;
         const uint32_t nb = b1 - b0;
         uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
-        TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa));
-        TRY(mb200_queries_from_orfs(c));
-        TRY(mb200_prefilter_resident(c));
-        TRY(align_pipeline(c));
-        std::vector<uint32_t> tids; TRY(trace_tids(c, tids));
-        TRY(collect_accepted(c, tids));
+        tp = std::chrono::steady_clock::now();
+        TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa)); lap(0);
+        TRY(mb200_queries_from_orfs(c)); lap(1);
+        TRY(mb200_prefilter_resident(c)); lap(2);
+        TRY(align_pipeline(c)); lap(3);
+        std::vector<uint32_t> tids; TRY(trace_tids(c, tids)); lap(4);
+        TRY(collect_accepted(c, tids)); lap(5);
         const auto tj = std::chrono::steady_clock::now();
         if (mb200::join_by_contig(orfs, n, nb, orfBase, c->hAlnOff.data(), c->hAlns.data(), c->tKeys.empty() ? nullptr : c->tKeys.data(), c->hToff.data(), cands, candOff, candAln))
             return fail(MB200_E_LIMIT, "more than 2^32 fragments in one mb200_predict_exons call");
@@ -1118,7 +1128,9 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         const uint64_t nc = candOff[nb];
         bCalls.resize(std::max<uint64_t>(1, 2 * nc)); bExons.resize(std::max<uint64_t>(1, nc)); bCnt.assign(nb, 0);
         c->st.ms_chain = 0;
+        lap(6);
         if (nc) TRY(mb200_chain(c, cands.data(), candOff.data(), nb, c->totalRes, bCalls.data(), bCnt.data(), bExons.data()));
+        lap(7);
         for (uint32_t ci = 0; ci < nb; ci++) {
             const uint64_t base = candOff[ci];
             for (uint32_t k = 0; k < bCnt[ci]; k++) {
@@ -1145,8 +1157,11 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         acc.ms_orf += s.ms_orf; acc.ms_orf_host += s.ms_orf_host; acc.orf_nucleotides += s.orf_nucleotides; acc.orf_fragments += s.orf_fragments; acc.orf_residues += s.orf_residues;
         for (int i = 0; i < 16; i++) acc.pref_phase_cycles[i] += s.pref_phase_cycles[i];
         acc.pe_batches++; acc.pe_contigs += nb; acc.pe_fragments += n; acc.pe_alignments += c->hAlns.size();
-        orfBase += n; b0 = b1;
+        orfBase += n; b0 = b1; lap(8);
     }
+    if (getenv("MB200_TRACE"))
+        fprintf(stderr, "mb200_predict_exons host phases (ms, wall): orfs %.1f install %.1f prefilter %.1f align %.1f tids %.1f accept %.1f join %.1f chain %.1f output %.1f\n",
+                ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7], ph[8]);
     acc.pe_calls = c->peCalls.size(); acc.pe_exons = c->peExons.size();
     acc.launches = c->st.launches; acc.ms_reduce = c->st.ms_reduce; acc.ms_d2h = c->st.ms_d2h; acc.ms_host = c->st.ms_host;
     acc.ms_predict = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

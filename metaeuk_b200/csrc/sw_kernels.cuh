@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(STRIDE == 32 ? 256 : 128) k_sw_lanes(
 // occupies few of the 16 lanes of its half-warp.  Here a pair of targets is aligned by nb = ceil(L / 32) lanes at once: lane b owns rows
 // [32 b, 32 b + 32) and runs b columns behind lane b - 1, whose bottom row (H, F) of the column it needs arrives by one shuffle per step -- a
 // systolic wavefront along the query.  A half-warp (one query profile in shared memory) therefore carries 16 / nb pairs = 2 * (16 / nb) hits per
-// item: 16 pairs for L <= 32 (the k_sw_rows2 layout), 4 pairs for L = 100, one pair for L in (256, 512].  No boundary traffic to global memory.
+// item: 16 pairs for L <= 32 (the k_sw_rows2 layout), 4 pairs for L = 100, one pair for L in (256, 512]; queries of 513..1024 residues take a whole warp
+// per item (G = 32 lanes, one pair).  No boundary traffic to global memory.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
     const uint32_t *__restrict__ order, const uint32_t *__restrict__ waveOff, uint32_t pBegin, uint32_t pEnd,
@@ -366,22 +367,22 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
     const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
     const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
     uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
-    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag) {
+    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint32_t G /* lanes per item: 16 (L <= 512) or 32 */) {
     constexpr int RB = 32;
     extern __shared__ __align__(16) unsigned char dynProf[];
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15u;
-    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)(wib * 2u + half) * 22u * profStride;   // row 21 = padding residue
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, perWarp = 32u / G, half = G == 16u ? lane >> 4 : 0u, l16 = lane & (G - 1u);   // l16: lane within its group
+    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)(wib * perWarp + half) * 22u * profStride;   // row 21 = padding residue
     const uint32_t itemBase = waveOff[pBegin], itemEnd = waveOff[pEnd];
     const uint32_t negE2 = (uint32_t)(uint16_t)(int16_t)(-gapE) * 0x10001u, go2 = (uint32_t)(uint16_t)(int16_t)(-gapO) * 0x10001u;
     const uint32_t MIN2 = 0x80008000u;
     unsigned long long cells = 0;
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = itemBase + atomicAdd(counter, 2u);
-        item = __shfl_sync(0xffffffffu, item, 0) + half;           // half-warp 0 / 1 take consecutive work items
+        if (lane == 0) item = itemBase + atomicAdd(counter, perWarp);
+        item = __shfl_sync(0xffffffffu, item, 0) + half;           // half-warp 0 / 1 take consecutive work items (G = 16)
         if (__all_sync(0xffffffffu, item >= itemEnd)) break;
         const bool haveItem = item < itemEnd;
         uint32_t qi = 0, cnt = 0, nb = 1, kk0 = 0; int L = 0; uint64_t qb = 0;
@@ -390,16 +391,16 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (waveOff[mid] <= item) lo = mid; else hi = mid; }
             qi = order[lo]; cnt = hitCount[qi]; qb = qoff[qi]; L = (int)(qoff[qi + 1] - qb);
             nb = (uint32_t)(L + RB - 1) / RB; if (nb == 0) nb = 1;
-            kk0 = (item - waveOff[lo]) * 2u * (16u / nb);
+            kk0 = (item - waveOff[lo]) * 2u * (G / nb);
         }
         __syncwarp();
-        if (haveItem) for (uint32_t idx = l16; idx < 22u * profStride; idx += 16u) {
+        if (haveItem) for (uint32_t idx = l16; idx < 22u * profStride; idx += G) {
             const uint32_t t = idx / profStride, j = idx - t * profStride;
             prof[idx] = (t < 21u && j < (uint32_t)L) ? (int8_t)(sMat8[t * 21 + qres[qb + j]] + cb[qb + j]) : (int8_t)-64;
         }
         __syncwarp();
         const uint32_t slotInItem = l16 / nb, b = l16 - slotInItem * nb;     // which pair of the item, which row block of the pair
-        const bool valid = haveItem && slotInItem < 16u / nb;
+        const bool valid = haveItem && slotInItem < G / nb;
         const uint32_t kA = kk0 + 2u * slotInItem;
         const bool actA = valid && kA < cnt, actB = valid && kA + 1 < cnt;
         size_t slotA = 0, slotB = 0; int lenA = 0, lenB = 0; const uint8_t *tA = tseq, *tB = tseq;
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
         if (n > 0) { const int rows = L - (int)b * RB; cells += (unsigned long long)(lenA + lenB) * (unsigned)(rows > RB ? RB : (rows > 0 ? rows : 0)); }
         // maximum over the row blocks of the pair -> the lane of block 0
 #pragma unroll
-        for (int d = 1; d < 16; d++) { const uint32_t y = __shfl_down_sync(0xffffffffu, mx, d); if (b + (uint32_t)d < nb) mx = __vmaxs2(mx, y); }
+        for (int d = 1; d < 32; d++) { const uint32_t y = __shfl_down_sync(0xffffffffu, mx, d); if (b + (uint32_t)d < nb) mx = __vmaxs2(mx, y); }
         if (b == 0) {
             const int sA = (int)(int16_t)(mx & 0xFFFFu), sB = (int)(int16_t)(mx >> 16);
             if (actA) { scoreOut[slotA] = sA; if (sA >= 32000) atomicExch(errFlag, 1u);
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(128) k_sw_trace2(const uint32_t *__restrict__ 
 // exclusive scans over the prefilter result: pairOff[i] (natural query order) and, in length-sorted order, the work lists of the three
 // forward kernels.  A query with L residues and n hits goes to
 //   k_sw_lanes  (laneOff, items of 2 hits)                     when laneMaxHits != 0, n <= laneMaxHits and L <= laneMaxL,
-//   k_sw_wave   (waveOff, items of 2 * (16 / ceil(L/32)) hits) when L <= waveMaxL (0 = never),
+//   k_sw_wave   (waveOff, items of 2 * (G / ceil(L/32)) hits, G = 16 lanes for L <= 512, else 32) when L <= waveMaxL (0 = never; <= 1024),
 //   k_sw_rows*  (chunkOff, chunks of 32 hits)                  otherwise.            laneOff / waveOff may be NULL.
 __device__ __forceinline__ int sw_query_class(uint32_t L, uint32_t n, uint32_t laneMaxL, uint32_t laneMaxHits, uint32_t waveMaxL) {
     if (laneMaxHits && n <= laneMaxHits && L <= laneMaxL) return 1;
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(MB_CTA_THREADS) k_scan_counts(const uint32_t *
             if (cls == which) {
                 if (which == 0) v = (n + 31u) >> 5;
                 else if (which == 1) v = (n + 1u) >> 1;
-                else { const uint32_t nb = (L + 31u) >> 5, per = 2u * (16u / (nb ? nb : 1u)); v = (n + per - 1u) / per; }
+                else { const uint32_t nb = L ? (L + 31u) >> 5 : 1u, per = 2u * ((nb <= 16u ? 16u : 32u) / nb); v = (n + per - 1u) / per; }
             }
             out[p] = v;
         }

@@ -353,6 +353,12 @@ def test_long_queries_take_the_32bit_alignment_path():
         return "".join(rng.choice(AA) if rng.random() < r else ch for ch in s)
     queries = [(0, mutate(prots[3] + prots[17] + prots[40] + prots[41], 0.2)), (1, mutate(prots[8], 0.3)), (2, mutate(prots[100] + prots[101] + prots[102] + prots[103] + prots[104], 0.1))]
     assert len(queries[0][1]) > 1024 and len(queries[2][1]) > 1024
+    # every profile class of the wavefront kernel: 257..512 (one pair per half-warp), 513..1024 (one pair per warp), and block-edge lengths
+    long = mutate(prots[20] + prots[21] + prots[22] + prots[23], 0.15)
+    for n in (257, 300, 449, 512, 513, 640, 800, 992, 1000, 1024):
+        if len(long) >= n:
+            queries.append((len(queries), long[:n]))
+    assert len(queries) >= 10
     tdb = M.TargetDB(list(enumerate(prots)))
     ctx = M.make_context(tdb)
     got_pref = M.prefilter(ctx, queries, tdb)
