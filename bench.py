@@ -700,7 +700,7 @@ def main():
                  "e2e": {"value": e2e, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_e2e / args.steps,
                          "last_call_ms": {k: round(st_e2e[k], 3) for k in ("ms_h2d", "ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_d2h", "ms_host")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                              "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "traffic": ncu_traffic()},
+                              "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "traffic": ncu_traffic() if args.workload == "c2" else None},
                  "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev")},
                  "index": {"build_plus_broadcast_s": index_s, "broadcast_s": bcast_s, "broadcast_bytes": int(bcast_bytes), "entries": ctx.index_sizes()[0]},
