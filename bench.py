@@ -213,10 +213,14 @@ def bench_predict(args, wl, base, rank, world, local, threads):
     wall = time.perf_counter() - t0
     st = sts[-1]
     vals = [dev_ms * 1e-3, wall]
+    total_frag = int(st["pe_fragments"])
     if world > 1:
         t = torch.tensor(vals, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = [float(x) for x in t.tolist()]
+        t = torch.tensor([total_frag], dtype=torch.int64, device="cuda")     # every rank has its own contigs (seed + rank): sum the fragments actually processed
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_frag = int(t.item())
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         ctx.close()
@@ -231,8 +235,8 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                            "parallelism": "contig shards x%d, index replicated by one NCCL broadcast" % args.gpus,
                            "warmup_used": W})
     base["warmup"] = W
-    base.update({"value": world * nfrag * args.steps / vals[0], "ms_per_step": 1000 * vals[0] / args.steps, "clocks": clocks, "gpu_launches": int(st["launches"] - l0),
-                 "e2e": {"value": world * nfrag * args.steps / vals[1], "unit": "fragments/s", "h2d_bytes_per_step": int(nuc.nbytes + off.nbytes),
+    base.update({"value": total_frag * args.steps / vals[0], "ms_per_step": 1000 * vals[0] / args.steps, "clocks": clocks, "gpu_launches": int(st["launches"] - l0),
+                 "e2e": {"value": total_frag * args.steps / vals[1], "unit": "fragments/s", "h2d_bytes_per_step": int(nuc.nbytes + off.nbytes),
                          "d2h_bytes_per_step": int(calls.nbytes + exons.nbytes + call_off.nbytes), "ms_per_step": 1000 * vals[1] / args.steps,
                          "last_call_ms": {k: round(st[k], 3) for k in STAGES + ("ms_join", "ms_predict")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": abytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kms * 1e-3) / 1e9 / peak,
