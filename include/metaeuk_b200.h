@@ -7,6 +7,7 @@
  * What each entry point replaces in the reference (paths relative to /root/reference, M/ = lib/mmseqs/):
  *   mb200_matrices_*     SubstitutionMatrix ctor                M/src/commons/SubstitutionMatrix.cpp:12-57
  *                        (Prefiltering.cpp:67-70 kmerSubMat/ungappedSubMat, Alignment.cpp:152 m)
+ *   mb200_mask_targets   Masker::maskSequence (tantan)          M/src/commons/Masker.cpp:14-58, M/lib/tantan/tantan.cpp:401-540
  *   mb200_index_build    IndexBuilder::fillDatabase             M/src/prefiltering/IndexBuilder.cpp:55-239
  *   mb200_index_import   IndexTable::initTableByExternalData    M/src/prefiltering/IndexTable.h:223-240
  *   mb200_prefilter      Prefiltering::runSplit query loop      M/src/prefiltering/Prefiltering.cpp:790-870
@@ -131,6 +132,12 @@ int mb200_index_sizes(mb200_ctx *ctx, uint64_t sizes[4] /* n_entries, n_targets,
 int mb200_index_alloc(mb200_ctx *ctx, const uint64_t sizes[4]);
 int mb200_index_buffers(mb200_ctx *ctx, void *dev_ptrs[8], uint64_t nbytes[8], int *n);
 int mb200_index_commit(mb200_ctx *ctx);
+
+/* Repeat masking of the targets before indexing = Masker::maskSequence with the prefilter's default flags (--mask 1 --mask-prob 0.9;
+ * M/src/commons/Masker.cpp:14-58 -> tantan, M/lib/tantan/tantan.cpp:401-433,478-540; called from IndexBuilder::fillDatabase, IndexBuilder.cpp:84-131).
+ * Host only (no GPU, no context): unmasked / masked are numeric residue codes with the same offsets off[n_targets+1]; masked letters become X (20).
+ * simd_width 4 reproduces the summation order of the reference's AVX2 build, 2 that of its SSE4.1 / NEON build (0 = 4). */
+int mb200_mask_targets(const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets, double mask_prob, int simd_width, uint8_t *masked, uint64_t *n_masked);
 
 /* persisted index: an MMseqs index database in the layout `createindex` / `indexdb` write (<path>, <path>.index, <path>.dbtype;
  * entries keyed as in M/src/prefiltering/PrefilteringIndexReader.cpp:10-34).  mb200_index_load mmaps such a DB -- written by

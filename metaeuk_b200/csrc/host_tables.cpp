@@ -40,6 +40,88 @@ void default_matrices(Matrices &m) {
     make_matrix(MB200_BLOSUM62_HALFBITS, MB200_BLOSUM62_BACKGROUND, MB200_BLOSUM62_LAMBDA, 2.0f, 0.0f, m.aln, m.alnPBack); // Alignment.cpp:152
 }
 
+// ---- target masking (tantan) --------------------------------------------------------------------------
+namespace {
+// The HMM: one background state and W = 50 repeat states (state k copies the letter k + 1 positions back).  Per letter the reference does
+// transition + emission in one pass over the states, in double precision, rescaling all states by 1 / background every 16 letters.
+class RepeatHmm {
+public:
+    static const int W = 50;
+    explicit RepeatHmm(int simdWidth) : width(simdWidth) {
+        // likelihood ratios P(a,b) / (f_a f_b), P rebuilt from the shipped half-bit table as in make_matrix
+        double f[21]; bool xPositive = false;
+        for (int a = 0; a < AL; a++) { f[a] = MB200_VTML80_BACKGROUND[a]; if (MB200_VTML80_HALFBITS[AL - 1][a] > 0 || MB200_VTML80_HALFBITS[a][AL - 1] > 0) xPositive = true; }
+        if (!xPositive) for (int a = 0; a < AL - 1; a++) f[a] = f[a] * (1.0 - f[AL - 1]);
+        for (int a = 0; a < AL; a++) for (int b = 0; b < AL; b++)
+            ratio[a][b] = (std::exp(MB200_VTML80_LAMBDA * MB200_VTML80_HALFBITS[a][b]) * f[a] * f[b]) / (f[a] * f[b]);
+        const double repeatProb = 0.005, decay = 0.9;
+        stay = 1 - repeatProb; leave = 0.05; keep = 1 - leave;
+        double p = repeatProb * ((1 - decay) / (1 - std::pow(decay, W)));
+        for (int k = 0; k < W; k++) { enter[k] = p; p *= decay; }
+    }
+    // posterior P(letter i is in a repeat) for one sequence
+    void posteriors(const uint8_t *x, int n, std::vector<float> &post, std::vector<double> &scales) const {
+        post.resize(n); scales.assign(n / 16 + 1, 1.0);
+        double rep[W], bg = 1.0;
+        std::fill(rep, rep + W, 0.0);
+        for (int i = 0; i < n; i++) {
+            const double from = forward(x, i, rep, bg);
+            bg = bg * stay + from * leave;
+            if ((i & 15) == 15) { const double sc = 1 / bg; scales[i >> 4] = sc; bg *= sc; for (int k = 0; k < W; k++) rep[k] *= sc; }
+            post[i] = static_cast<float>(bg);
+        }
+        double tail = 0.0; for (int k = 0; k < W; k++) tail += rep[k];
+        const double total = bg * stay + tail * leave;
+        bg = stay; std::fill(rep, rep + W, leave);
+        for (int i = n - 1; i >= 0; i--) {
+            const double notRepeat = post[i] * bg / total;
+            post[i] = 1 - static_cast<float>(notRepeat);
+            if ((i & 15) == 15) { const double sc = scales[i >> 4]; bg *= sc; for (int k = 0; k < W; k++) rep[k] *= sc; }
+            const double to = backward(x, i, rep, leave * bg);
+            bg = stay * bg + to;
+        }
+    }
+private:
+    int width; double ratio[21][21], enter[W], stay, leave, keep;
+    double fold(const double *part) const { return width == 4 ? (part[0] + part[2]) + (part[1] + part[3]) : part[0] + part[1]; }
+    // one letter of the forward pass over the reachable states; returns the probability mass that was in repeat states
+    double forward(const uint8_t *x, int i, double *rep, double bg) const {
+        const double *r = ratio[x[i]]; const int reach = i < W ? i : W;
+        double part[4] = {0, 0, 0, 0}; int k = 0;
+        for (; k + width <= reach; k += width)
+            for (int j = 0; j < width; j++) { const double v = rep[k + j]; part[j] += v; rep[k + j] = (bg * enter[k + j] + v * keep) * r[x[i - 1 - k - j]]; }
+        double sum = fold(part);
+        for (; k < reach; k++) { const double v = rep[k]; sum += v; rep[k] = (bg * enter[k] + v * keep) * r[x[i - 1 - k]]; }
+        return sum;
+    }
+    double backward(const uint8_t *x, int i, double *rep, double toBg) const {
+        const double *r = ratio[x[i]]; const int reach = i < W ? i : W;
+        double part[4] = {0, 0, 0, 0}; int k = 0;
+        for (; k + width <= reach; k += width)
+            for (int j = 0; j < width; j++) { const double v = rep[k + j] * r[x[i - 1 - k - j]]; part[j] += enter[k + j] * v; rep[k + j] = toBg + keep * v; }
+        double sum = fold(part);
+        for (; k < reach; k++) { const double v = rep[k] * r[x[i - 1 - k]]; sum += enter[k] * v; rep[k] = toBg + keep * v; }
+        return sum;
+    }
+};
+}  // namespace
+
+uint64_t mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, double maskProb, uint8_t *out, int simdWidth) {
+    const RepeatHmm hmm(simdWidth == 2 ? 2 : 4);
+    uint64_t masked = 0;
+#pragma omp parallel reduction(+ : masked)
+    {
+        std::vector<float> post; std::vector<double> scales;
+#pragma omp for schedule(dynamic, 64)
+        for (uint32_t t = 0; t < nT; t++) {
+            const uint64_t b = off[t]; const int n = (int)(off[t + 1] - b);
+            hmm.posteriors(res + b, n, post, scales);
+            for (int i = 0; i < n; i++) { const bool m = post[i] >= maskProb; out[b + i] = m ? (uint8_t)(AL - 1) : res[b + i]; masked += m; }
+        }
+    }
+    return masked;
+}
+
 // ---- 3-mer similarity table -----------------------------------------------------------------------
 // Stable descending order w.r.t. the cartesian enumeration (first letter outermost) == a counting sort over the
 // (small) score range that visits neighbours in cartesian order.

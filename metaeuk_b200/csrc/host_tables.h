@@ -38,6 +38,14 @@ int build_index(const uint8_t *masked, const uint64_t *off, uint32_t nT, const i
 // same layout from a reference IndexTable (offsets size_t[20^6+1], packed 6-byte IndexEntryLocal entries)
 int import_index(const uint64_t *offsets, const uint8_t *entries6, uint64_t nEntries, TargetIndex &idx);
 
+// Repeat / low-complexity masking of the targets before indexing = Masker::maskSequence with the prefilter's flags (--mask 1, --mask-lower-case 0,
+// --mask-n-repeat 0; reference/lib/mmseqs/src/commons/Masker.cpp:14-58 -> tantan::maskSequences, reference/lib/mmseqs/lib/tantan/tantan.cpp:478-540):
+// posterior repeat probability of every letter under tantan's gap-free repeat HMM (window 50, repeatProb 0.005, repeatEndProb 0.05, offset decay 0.9),
+// likelihood ratios from the SEED matrix (ProbabilityMatrix, BaseMatrix.h:85-96); letters with P(repeat) >= maskProb become X (code 20).
+// res / out: numeric residue codes, off[nT + 1].  simdWidth = number of doubles the reference build's tantan loops add side by side (4 = AVX2 build,
+// 2 = SSE4.1 / NEON build): it fixes the summation order, so the double-precision sums -- and the result -- are those of that build.  Returns #masked.
+uint64_t mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, double maskProb, uint8_t *out, int simdWidth = 4);
+
 // Gumbel/finite-size e-value model of the reference for BLOSUM62 gap 11/1
 // (reference/lib/mmseqs/src/alignment/EvalueComputation.h:18-40,56-69 -> Sls::AlignmentEvaluer::area)
 struct EvalueModel {

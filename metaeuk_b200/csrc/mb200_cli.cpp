@@ -13,8 +13,8 @@
 //                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
 // DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
 // Result DBs are written byte-compatible with the reference's (same records, same keys; one data file).
-// Options: --max-seqs N  --min-ungapped-score N  --k-score N  -e X  --min-aln-len N  --masked-db <db> (target residues after the
-// reference's tantan masking, lower case or X = masked; without it targets are used unmasked = --mask 0)  --metaeuk-eval X
+// Options: --max-seqs N  --min-ungapped-score N  --k-score N  -e X  --min-aln-len N  --mask 0|1 (default 1: tantan masking of the targets as the reference's
+// index builder does it, --mask-prob 0.9)  --masked-db <db> (take the masked target residues from a DB instead: lower case or X = masked)  --metaeuk-eval X
 // --metaeuk-tcov X --max-intron N --min-intron N --min-exon-aa N --max-overlap N --max-exon-sets N --set-gap-open N --set-gap-extend N
 // --device N.  Everything numeric happens in the library (GPU); this file is DB I/O and the reference's text formatting.
 #include <algorithm>
@@ -108,7 +108,7 @@ static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdTo
 static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
 
 struct Opt {
-    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb;
+    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb; int mask = 1; double maskProb = 0.9;
 };
 static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
     Opt o; mb200_params_default(&o.p);
@@ -133,6 +133,8 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--device") o.device = atoi(val().c_str());
         else if (a == "--overlap") o.overlap = atoi(val().c_str());
         else if (a == "--index-db") o.indexDb = val();
+        else if (a == "--mask") o.mask = atoi(val().c_str());
+        else if (a == "--mask-prob") o.maskProb = atof(val().c_str());
         else if (a == "--text-stages") o.textStages = atoi(val().c_str());
         else if (a == "--batch-nt") o.batchNt = atoll(val().c_str());
         else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
@@ -147,6 +149,10 @@ struct Session {
         MB(mb200_ctx_create(o.device, &ctx)); MB(mb200_params_set(ctx, &o.p)); MB(mb200_matrices_default(ctx));
         tdb = openDb(targetDb); t = encodeDb(tdb, false);
         Seqs m = t;
+        if (o.maskedDb.empty() && o.mask && o.indexDb.empty()) {
+            // --mask 1 (the reference's default): tantan masking on the host, as IndexBuilder::fillDatabase does before it indexes (IndexBuilder.cpp:84-131)
+            MB(mb200_mask_targets(t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), o.maskProb, 0, m.res.data(), nullptr));
+        }
         if (!o.maskedDb.empty()) {
             Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
             for (size_t i = 0; i < tdb.keys.size(); i++) {   // align by key
@@ -403,6 +409,7 @@ int main(int argc, char **argv) {
         if (pos.size() != 2) DIE("gpucreateindex <targetDB> <o:indexDB> [--masked-db <DB>] [--k-score N]");
         initCodes();
         Db tdb = openDb(pos[0]); Seqs t = encodeDb(tdb, false); Seqs m = t;
+        if (o.maskedDb.empty() && o.mask) MB(mb200_mask_targets(t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), o.maskProb, 0, m.res.data(), nullptr));
         if (!o.maskedDb.empty()) {
             Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
             for (size_t i = 0; i < tdb.keys.size(); i++) {
@@ -410,7 +417,7 @@ int main(int argc, char **argv) {
                 memcpy(&m.res[t.off[i]], &raw.res[raw.off[j]], t.off[i + 1] - t.off[i]);
             }
         }
-        MB(mb200_index_file_write(pos[1].c_str(), m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), tdb.keys.data(), o.p.kmer_thr, o.maskedDb.empty() ? 0 : 1));
+        MB(mb200_index_file_write(pos[1].c_str(), m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), tdb.keys.data(), o.p.kmer_thr, (o.maskedDb.empty() && !o.mask) ? 0 : 1));
     } else if (cmd == "gpuextractorfs") {
         // extractorfs + translatenucs in one step (data/predictexons.sh: contigs -> nucl_6f(_h) -> aa_6f): writes the ORF header DB and the
         // translated fragment DB with the reference's renumbered keys

@@ -102,6 +102,17 @@ def pack_codes(seqs):
     return np.ascontiguousarray(data), off
 
 
+def mask_targets(unmasked, off, mask_prob=0.9, simd_width=4):
+    """tantan masking of the targets as the reference's index builder does it (host only): -> (masked codes, number of masked residues)"""
+    L = load_library()
+    unmasked = np.ascontiguousarray(unmasked, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+    out = np.zeros(max(1, len(unmasked)), np.uint8); n = C.c_uint64(0)
+    rc = L.mb200_mask_targets(_p(unmasked if len(unmasked) else np.zeros(1, np.uint8)), _p(off), C.c_uint32(len(off) - 1), C.c_double(mask_prob), int(simd_width), _p(out), C.byref(n))
+    if rc != 0:
+        raise Mb200Error("mb200 error %d: %s" % (rc, L.mb200_last_error().decode()))
+    return out[:len(unmasked)], int(n.value)
+
+
 def index_file_write(path, masked, unmasked, off, keys=None, kmer_thr=127, mask_mode=1):
     """build the target index on the host and persist it in the reference's index-DB layout (no GPU needed)"""
     L = load_library()

@@ -46,6 +46,15 @@ class TargetDB:
         self.lens = [len(s) for s in self.seqs]
         self.total_residues = sum(self.lens)
 
+    @classmethod
+    def masked_like_the_reference(cls, entries, mask_prob=0.9):
+        """entries [(key, sequence)] -> TargetDB whose masked residues come from mb200_mask_targets (tantan, the reference's --mask 1 default)"""
+        from .lib import mask_targets
+        u, off = encode_many([s for _, s in entries])
+        m, _ = mask_targets(u, off, mask_prob)
+        masked = ["".join(_ORDER[c] for c in m[int(off[i]):int(off[i + 1])]) for i in range(len(entries))]
+        return cls(entries, masked)
+
     def upload(self, ctx):
         u, off = encode_many(self.seqs)
         m, off2 = encode_many(self.masked)

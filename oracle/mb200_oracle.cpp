@@ -858,3 +858,85 @@ int mbo_reduce_redundancy_batch(const mbo_pred *P, const uint64_t *off, uint32_t
     return 0;
 }
 }  // extern "C"
+
+// =============================================================================================
+//  a3 (masking)  Masker::maskSequence with the prefilter's flags (--mask 1 --mask-prob 0.9 --mask-lower-case 0 --mask-n-repeat 0)
+//     M/src/commons/Masker.cpp:14-58,121-128  ->  tantan::maskSequences  M/lib/tantan/tantan.cpp:478-523
+//     (repeat HMM without gap states: maxCycleLength 50, repeatProb 0.005, repeatEndProb 0.05, repeatOffsetProbDecay 0.9; forward-backward in
+//      double with a rescale every 16 letters, calcRepeatProbs :401-433); likelihood ratios from the SEED matrix (IndexBuilder.cpp:84-86):
+//      ProbabilityMatrix, BaseMatrix.h:85-96 = P(a,b) / (pBack[a] * pBack[b]).  A letter is masked (-> X) when P(repeat) >= maskProb.
+//  The reference's inner loops run over 4 (AVX2) or 2 (SSE4.1/NEON) doubles at a time; `lanes` restates their summation order
+//  (tantan.cpp:300-335,347-382, mcf_simd.h:175-179).
+// =============================================================================================
+namespace {
+void tantan_lr(double lr[21][21]) {
+    double pBack[21];
+    for (int i = 0; i < AL; i++) pBack[i] = MB200_VTML80_BACKGROUND[i];
+    bool xIsPositive = false;
+    for (int j = 0; j < AL; j++) if (MB200_VTML80_HALFBITS[XRES][j] > 0 || MB200_VTML80_HALFBITS[j][XRES] > 0) { xIsPositive = true; break; }
+    if (!xIsPositive) for (int i = 0; i < AL - 1; i++) pBack[i] = pBack[i] * (1.0 - pBack[XRES]);
+    for (int i = 0; i < AL; i++) for (int j = 0; j < AL; j++) {
+        const double prob = std::exp(MB200_VTML80_LAMBDA * MB200_VTML80_HALFBITS[i][j]) * pBack[i] * pBack[j];   // SubstitutionMatrix.cpp:410-416
+        lr[i][j] = prob / (pBack[i] * pBack[j]);                                                                  // BaseMatrix.h:93
+    }
+}
+double lane_sum(const double *s, int lanes) { return lanes == 4 ? (s[0] + s[2]) + (s[1] + s[3]) : s[0] + s[1]; }   // simdHorizontalAddDbl
+
+int tantan_mask(uint8_t *seq, int n, const double lr[21][21], double minMaskProb, int lanes) {
+    const int W = 50; const double repeatProb = 0.005, repeatEndProb = 0.05, decay = 0.9;
+    const double b2b = 1 - repeatProb, f2b = repeatEndProb, f2f0 = 1 - repeatEndProb;
+    const double b2fFirst = repeatProb * ((1 - decay) / (1 - std::pow(decay, W)));       // firstRepeatOffsetProb, tantan.cpp:26-31
+    double b2f[W], fg[W];
+    { double p = b2fFirst; for (int i = 0; i < W; i++) { b2f[i] = p; p *= decay; } }
+    std::vector<double> scale(n / 16 + 1, 1.0);
+    std::vector<float> prob(n > 0 ? n : 1);
+    double bg = 1.0;
+    for (int i = 0; i < W; i++) fg[i] = 0.0;
+    for (int pos = 0; pos < n; pos++) {                                                  // forward, tantan.cpp:404-410
+        const double *row = lr[seq[pos]]; const int maxOffset = pos < W ? pos : W; const double b = bg;
+        double s[4] = {0, 0, 0, 0}; int i = 0;
+        for (; i <= maxOffset - lanes; i += lanes)
+            for (int j = 0; j < lanes; j++) { const double f = fg[i + j]; s[j] += f; fg[i + j] = (b * b2f[i + j] + f * f2f0) * row[seq[pos - i - j - 1]]; }
+        double fromFg = lane_sum(s, lanes);
+        for (; i < maxOffset; i++) { const double f = fg[i]; fromFg += f; fg[i] = (b * b2f[i] + f * f2f0) * row[seq[pos - i - 1]]; }
+        bg = b * b2b + fromFg * f2b;
+        if (pos % 16 == 15) { const double sc = 1 / bg; scale[pos / 16] = sc; bg *= sc; for (int k = 0; k < W; k++) fg[k] *= sc; }
+        prob[pos] = static_cast<float>(bg);
+    }
+    double acc = 0.0; for (int k = 0; k < W; k++) acc += fg[k];
+    const double z = bg * b2b + acc * f2b;                                               // forwardTotal
+    bg = b2b; for (int k = 0; k < W; k++) fg[k] = f2b;                                   // initializeBackwardAlgorithm
+    for (int pos = n - 1; pos >= 0; pos--) {                                             // backward, :416-426
+        const double nonRepeat = prob[pos] * bg / z;
+        prob[pos] = 1 - static_cast<float>(nonRepeat);
+        if (pos % 16 == 15) { const double sc = scale[pos / 16]; bg *= sc; for (int k = 0; k < W; k++) fg[k] *= sc; }
+        const double *row = lr[seq[pos]]; const int maxOffset = pos < W ? pos : W; const double toBg = f2b * bg;
+        double s[4] = {0, 0, 0, 0}; int i = 0;
+        for (; i <= maxOffset - lanes; i += lanes)
+            for (int j = 0; j < lanes; j++) { const double f = fg[i + j] * row[seq[pos - i - j - 1]]; s[j] += b2f[i + j] * f; fg[i + j] = toBg + f2f0 * f; }
+        double toFg = lane_sum(s, lanes);
+        for (; i < maxOffset; i++) { const double f = fg[i] * row[seq[pos - i - 1]]; toFg += b2f[i] * f; fg[i] = toBg + f2f0 * f; }
+        bg = b2b * bg + toFg;
+    }
+    int masked = 0;
+    for (int pos = 0; pos < n; pos++) if (prob[pos] >= minMaskProb) { seq[pos] = XRES; masked++; }   // maskProbableLetters :525-540; finalizeMasking keeps X
+    return masked;
+}
+}  // namespace
+
+extern "C" {
+// out = residues after masking; returns the number of masked residues (the reference's "Masked residues:" line) or -1
+long long mbo_mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, double maskProb, uint8_t *out, int lanes, int threads) {
+    if (lanes != 2 && lanes != 4) return -1;
+    double lr[21][21]; tantan_lr(lr);
+    long long total = 0;
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total) num_threads(threads)
+    for (uint32_t t = 0; t < nT; t++) {
+        const uint64_t b = off[t]; const int n = (int)(off[t + 1] - b);
+        for (int i = 0; i < n; i++) out[b + i] = res[b + i];
+        total += tantan_mask(out + b, n, lr, maskProb, lanes);
+    }
+    return total;
+}
+}

@@ -394,6 +394,49 @@ def case_orfs(name, seed, thr=4):
     print(name, "contigs", len(out["contigs"]), "fragments", len(out["queries"]))
 
 
+def case_masking(name="mask_repeats", seed=606, thr=8):
+    """tantan masking of the targets (Masker::maskSequence, SURVEY.md 8a row a3) on proteins built to be masked: tandem repeats with unit lengths 1..60
+    (beyond the 50-letter window too), 2-12 copies, 0-30 % divergence per copy, low-complexity stretches, X runs, and sequences around the
+    16-letter rescaling step; the masked residues are read back from the reference's `indexdb` output"""
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    prots = []
+    for i in range(420):
+        kind = i % 6
+        if kind == 0:
+            p = rand_prot(rng)
+        elif kind in (1, 2, 3):
+            p = rand_prot(rng, 200, 80, 30)
+            for _ in range(rng.randint(1, 3)):
+                unit = "".join(rng.choices(AA, weights=W, k=rng.choice([1, 2, 3, 4, 5, 7, 10, 15, 24, 33, 49, 50, 51, 60])))
+                rep = "".join(mutate(rng, unit, rng.choice([0.0, 0.05, 0.1, 0.2, 0.3])) for _ in range(rng.randint(2, 12)))
+                a = rng.randrange(len(p) + 1)
+                p = p[:a] + rep + p[a:]
+        elif kind == 4:
+            p = rand_prot(rng, 150, 50, 30)
+            a = rng.randrange(len(p))
+            p = p[:a] + "".join(rng.choices(rng.sample(AA, rng.randint(2, 3)), k=rng.randint(10, 80))) + p[a:]
+            if rng.random() < 0.5:
+                b = rng.randrange(len(p))
+                p = p[:b] + "X" * rng.randint(1, 12) + p[b:]
+        else:
+            p = "".join(rng.choices(AA, weights=W, k=rng.choice([1, 5, 15, 16, 17, 31, 32, 33, 48, 49, 50, 51, 52, 64, 2000])))
+            if rng.random() < 0.5 and len(p) > 8:
+                p = p[:len(p) // 2] + p[:len(p) // 2]
+        prots.append(p)
+    write_fasta(tmp + "/proteins.faa", prots, "P")
+    run("%s createdb %s/proteins.faa %s/proteins --shuffle 0 -v 3" % (REF, tmp, tmp), log)
+    out = {"case": name, "kind": "masking", "seed": seed, "targets": seqdb(tmp + "/proteins")}
+    idx = ref_index(tmp, "proteins", 1, thr, log)
+    out["masked_targets"] = idx["masked_targets"]; out["masked_residues"] = idx["idx_masked_residues"]
+    out["ref_version"] = run("%s version" % REF, log).strip()
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+    print(name, "targets", len(out["targets"]), "residues", sum(len(s) for _, s in out["targets"]), "masked", out["masked_residues"])
+
+
 REF_TESTS = [("minus_strand", -1, 0), ("multi_exon", -1, 0), ("two_contigs", -1, 0), ("target_overlap", -3, 0), ("cluster_rep", -3, 0), ("target_cov", -1, 0.7)]
 
 
@@ -458,3 +501,5 @@ if __name__ == "__main__":
         case_redundancy("redundancy_family", 2025)
     if "ref_tests" in which:
         case_reference_tests()
+    if "mask_repeats" in which:
+        case_masking()

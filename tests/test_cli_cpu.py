@@ -49,3 +49,32 @@ def test_device_commands_fail_loudly_without_a_gpu(exe, tmp_path):
     r = subprocess.run([exe, "gpuprefilter", d + "/q", d + "/proteins", d + "/pref"], capture_output=True, text=True)
     assert r.returncode != 0 and not os.path.exists(d + "/pref")
     assert "mb200" in (r.stderr + r.stdout)
+
+
+@pytest.mark.parametrize("name", ["mask_repeats", "frag_small", "frag_family", "contigs_small", "contigs_sets"])
+def test_product_target_masking_matches_reference(name):
+    """mb200_mask_targets (host only, product code in host_tables.cpp) against the masked residues the reference stored in its index"""
+    c = reflib.load_case(name)
+    u, off = reflib.pack([s for _, s in c["targets"]]); m, _ = reflib.pack(c["masked_targets"])
+    for width in (4, 2):
+        got, n = mlib.mask_targets(u, off, 0.9, width)
+        assert n == c["masked_residues"] and (got == m).all(), width
+    with pytest.raises(mlib.Mb200Error):
+        mlib.mask_targets(np.array([3, 21, 4], np.uint8), np.array([0, 3], np.uint64))
+
+
+def test_gpucreateindex_masks_like_the_reference_by_default(exe, emu, tmp_path):  # noqa: F811
+    """no --masked-db: the driver masks the targets itself (--mask 1, the reference's default) and must arrive at the reference's index"""
+    c = reflib.load_case("contigs_small")
+    d = str(tmp_path)
+    reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"]], 0)
+    subprocess.check_call([exe, "gpucreateindex", d + "/proteins", d + "/proteins.idx", "--k-score", str(c["kmer_thr"])])
+    x, err = _open_indexdb(emu, d + "/proteins.idx")
+    assert x is not None, err
+    m, _ = reflib.pack(c["masked_targets"])
+    assert (x["masked"] == m).all() and x["meta"][4] == 1
+    assert hashlib.sha256(x["entries6"].tobytes()).hexdigest() == c["idx_entries_sha256"]
+    subprocess.check_call([exe, "gpucreateindex", d + "/proteins", d + "/unmasked.idx", "--k-score", str(c["kmer_thr"]), "--mask", "0"])
+    y, err = _open_indexdb(emu, d + "/unmasked.idx")
+    u, _ = reflib.pack([s for _, s in c["targets"]])
+    assert (y["masked"] == u).all() and y["meta"][4] == 0 and y["n_entries"] > x["n_entries"]

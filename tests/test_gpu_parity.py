@@ -268,6 +268,17 @@ def test_reference_own_end_to_end_fixtures(ds):
     ctx.close()
 
 
+def test_targets_masked_by_the_library_give_the_reference_calls():
+    """raw (unmasked) targets in: mb200_mask_targets (tantan, --mask 1) -> index -> contigs to calls == the reference's dp_predictions"""
+    c = reflib.load_case("contigs_small")
+    tdb = M.TargetDB.masked_like_the_reference(c["targets"])
+    assert tdb.masked == c["masked_targets"]
+    ctx = M.make_context(tdb, kmer_thr=c["kmer_thr"], max_exon_sets=c["max_exon_sets"])
+    dp = M.predictexons_contigs(ctx, [tuple(x) for x in c["contigs"]], tdb)
+    assert strkeys(dp) == c["dp"]
+    ctx.close()
+
+
 def planted_contigs(seed, prots, n_contigs, length):
     """SURVEY 8d contig generator at test size: random ACGT with planted genes = mutated proteins back-translated, split into 1-4 exons,
     introns of 40-600 nt, half of them reverse-complemented"""
