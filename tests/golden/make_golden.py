@@ -234,12 +234,46 @@ def write_fasta(path, seqs, prefix):
             f.write(">%s%d\n%s\n" % (prefix, i, s))
 
 
-def case_fragments(name, seed, nprot, nfrag, family=0, lowcomplex=0, mask=1, maxseqs=300, thr=8):
+def adversarial_sets(rng):
+    """targets and queries chosen to hit the corners of the path: > 300 near-identical targets (ties at the saturated 8-bit diagonal score -> exact re-score,
+    top-300 cut among equals), exact copies (maximal scores), homopolymers / short-period repeats / low complexity (masking, huge k-mer lists, many double hits on
+    neighbouring diagonals), X runs, sequences around the window length, very long sequences"""
+    base = rand_prot(rng, 180, 10)
+    prots = [mutate(rng, base, rng.choice([0.0, 0.0, 0.01, 0.02])) for _ in range(340)]
+    prots += [rand_prot(rng) for _ in range(120)]
+    for _ in range(30):
+        unit = "".join(rng.choices(AA, k=rng.randint(1, 6)))
+        p = rand_prot(rng, 120, 30, 40)
+        a = rng.randrange(len(p))
+        prots.append(p[:a] + unit * rng.randint(5, 40) + p[a:])
+    for _ in range(12):
+        p = rand_prot(rng, 200, 40)
+        a = rng.randrange(len(p) - 20)
+        prots.append(p[:a] + "X" * rng.randint(1, 25) + p[a:])
+    prots += ["".join(rng.choices(AA, weights=W, k=n)) for n in (10, 11, 12, 15, 20, 1500, 3000)]
+    prots += ["A" * 60, "AC" * 40, "ACD" * 30, "W" * 25 + rand_prot(rng, 80, 5)]
+    rng.shuffle(prots)
+    frags = [base, mutate(rng, base, 0.1), base[:40], base[100:], base + base]
+    frags += [p for p in rng.sample(prots, 25)]                                     # exact copies (incl. repeats, X runs, long, short)
+    frags += [mutate(rng, p, 0.15) for p in rng.sample(prots, 25)]
+    frags += ["A" * 50, "AC" * 30, "ACD" * 25, "ACDE" * 20, "W" * 40, "X" * 30, "ACDEFGHIKX" * 6, "XACDEFGHIKLMNX" * 4]
+    frags += ["ACDEFGHIK", "ACDEFGHIKL", "ACDEFGHIKLM", "MKV", "M"]
+    frags += ["".join(rng.choices(AA, weights=W, k=n)) for n in (15, 16, 31, 32, 33, 64, 65, 255, 256, 257, 512, 513, 1023, 1024, 1025, 2000)]
+    frags += [mutate(rng, "".join(rng.sample(prots, 1)[0] for _ in range(3)), 0.1)[:n] for n in (300, 520, 900)]
+    for _ in range(40):
+        frags.append("".join(rng.choices(AA, weights=W, k=max(15, int(rng.gauss(100, 40))))))
+    return prots, frags
+
+
+def case_fragments(name, seed, nprot, nfrag, family=0, lowcomplex=0, mask=1, maxseqs=300, thr=8, adversarial=False):
     rng = random.Random(seed)
     tmp = tempfile.mkdtemp(prefix="mb200_golden_")
     log = []
-    prots = make_proteins(rng, nprot, family, lowcomplex)
-    frags = make_fragments(rng, prots, nfrag)
+    if adversarial:
+        prots, frags = adversarial_sets(rng)
+    else:
+        prots = make_proteins(rng, nprot, family, lowcomplex)
+        frags = make_fragments(rng, prots, nfrag)
     write_fasta(tmp + "/proteins.faa", prots, "P")
     write_fasta(tmp + "/frags.faa", frags, "F")
     run("%s createdb %s/proteins.faa %s/proteins -v 3" % (REF, tmp, tmp), log)
@@ -491,6 +525,8 @@ if __name__ == "__main__":
         case_fragments("frag_family", 99, nprot=300, nfrag=60, family=700)
     if "frag_nomask" in which:   # low-complexity targets with --mask 0
         case_fragments("frag_nomask", 7, nprot=300, nfrag=200, lowcomplex=30, mask=0)
+    if "frag_adversarial" in which:
+        case_fragments("frag_adversarial", 515, 0, 0, adversarial=True)
     if "contigs_small" in which:
         case_contigs("contigs_small", 1234, nprot=400, nc=24, cl=9000)
     if "contigs_sets" in which:

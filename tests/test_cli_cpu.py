@@ -51,7 +51,7 @@ def test_device_commands_fail_loudly_without_a_gpu(exe, tmp_path):
     assert "mb200" in (r.stderr + r.stdout)
 
 
-@pytest.mark.parametrize("name", ["mask_repeats", "frag_small", "frag_family", "contigs_small", "contigs_sets"])
+@pytest.mark.parametrize("name", ["mask_repeats", "frag_adversarial", "frag_small", "frag_family", "contigs_small", "contigs_sets"])
 def test_product_target_masking_matches_reference(name):
     """mb200_mask_targets (host only, product code in host_tables.cpp) against the masked residues the reference stored in its index"""
     c = reflib.load_case(name)

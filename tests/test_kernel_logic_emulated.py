@@ -56,7 +56,7 @@ def test_host_index_matches_reference_digest(emu, name):
 
 
 @pytest.mark.parametrize("cfg", [1, 2, 3], ids=["dense", "sparse", "tiny-all-fallbacks"])
-@pytest.mark.parametrize("name", ["frag_small", "frag_family", "frag_nomask", "contigs_small", "contigs_sets"])
+@pytest.mark.parametrize("name", ["frag_small", "frag_family", "frag_nomask", "frag_adversarial", "contigs_small", "contigs_sets"])
 def test_prefilter_kernel_logic_matches_reference(emu, name, cfg):
     """cfg 1/2 = the two kernel configurations of the library; 3 = a tiny configuration whose shared-memory homes overflow on every
     query, so the global-memory fallbacks of every list (and the sort-based double-hit path) are diffed against the reference too"""
