@@ -119,6 +119,7 @@ struct Oracle {
     // parameters (MetaEuk defaults)
     int kmerThr = 127; int maxResListLen = 300; int minDiagScore = 15; int binSize = 2;
     int gapOpen = 11, gapExtend = 1; double evalThr = 100; int minAlnLen = 11;
+    bool compBiasCorr = true;    // --comp-bias-corr (Prefiltering.cpp:52, Alignment.cpp:26)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -186,7 +187,8 @@ int prefilter_query(const Oracle &o, const uint8_t *q, int L, std::vector<PrefHi
     out.clear();
     if (L >= 32768) return -2;
     std::vector<float> bias(L > 0 ? L : 1);
-    comp_bias(o.seedMat, o.seedPBack, q, L, bias.data(), 1.0f);                 // QueryMatcher.cpp:91-93 (kmerSubMat)
+    if (o.compBiasCorr) comp_bias(o.seedMat, o.seedPBack, q, L, bias.data(), 1.0f);   // QueryMatcher.cpp:91-93 (kmerSubMat)
+    else std::fill(bias.begin(), bias.end(), 0.0f);                             // QueryMatcher.cpp:97-99
     // UngappedAlignment::createProfile  UngappedAlignment.cpp:385-414
     std::vector<int8_t> prof((size_t)(L > 0 ? L : 1) * AL);
     for (int pos = 0; pos < L; pos++) {
@@ -442,6 +444,7 @@ void align_pair(const Oracle &o, const Alp &alp, const uint8_t *q, int qLen, con
 // int8 composition bias for the align stage  StripedSmithWaterman.cpp:1229-1237
 void aln_comp_bias(const Oracle &o, const uint8_t *q, int L, int8_t *cb) {
     std::vector<float> tmp(L > 0 ? L : 1);
+    if (!o.compBiasCorr) { memset(cb, 0, (size_t)(L > 0 ? L : 0)); return; }               // StripedSmithWaterman.cpp:1238-1240
     comp_bias(o.alnMat, o.alnPBack, q, L, tmp.data(), 1.0f);
     for (int i = 0; i < L; i++) cb[i] = (int8_t)((tmp[i] < 0.0) ? tmp[i] - 0.5 : tmp[i] + 0.5);
 }
@@ -469,6 +472,7 @@ void mbo_set_params(void *h, int kmerThr, int maxResListLen, int minDiagScore, i
     Oracle *o = (Oracle *)h; o->kmerThr = kmerThr; o->maxResListLen = maxResListLen; o->minDiagScore = minDiagScore; o->binSize = binSize;
     o->gapOpen = gapOpen; o->gapExtend = gapExtend; o->evalThr = evalThr; o->minAlnLen = minAlnLen;
 }
+void mbo_set_comp_bias_corr(void *h, int on) { ((Oracle *)h)->compBiasCorr = on != 0; }
 void mbo_get_matrices(void *h, int16_t *seed, int16_t *ung, int16_t *aln, double *seedPBack, double *alnPBack) {
     Oracle *o = (Oracle *)h; memcpy(seed, o->seedMat, 882); memcpy(ung, o->ungMat, 882); memcpy(aln, o->alnMat, 882);
     memcpy(seedPBack, o->seedPBack, 168); memcpy(alnPBack, o->alnPBack, 168);
@@ -670,8 +674,36 @@ static char iupac_complement(char c) {                   // Orf::iupacReverseCom
     return islower((unsigned char)c) ? (char)tolower(to[p - from]) : to[p - from];
 }
 // amino acid of every (possibly ambiguous) codon: consensus over the expansions, with B/Z/J merging (TranslateNucl.h:383-485)
-static void build_codon_table(char aaOf[4096]) {
-    static const char *code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";   // genetic code 1, TCAG order
+// NCBI genetic codes (amino acid per codon, TCAG order) as TranslateNucl's constructor lists them (TranslateNucl.h:110-246); NULL = not a table id
+static const char *genetic_code(int table) {
+    switch (table) {
+    case 1: case 11: return "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 2:  return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSS**VVVVAAAADDEEGGGG";
+    case 3:  return "FFLLSSSSYY**CCWWTTTTPPPPHHQQRRRRIIMMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 4:  return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 5:  return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSSSVVVVAAAADDEEGGGG";
+    case 6:  return "FFLLSSSSYYQQCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 9:  return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG";
+    case 10: return "FFLLSSSSYY**CCCWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 12: return "FFLLSSSSYY**CC*WLLLSPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 13: return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSGGVVVVAAAADDEEGGGG";
+    case 14: return "FFLLSSSSYYY*CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG";
+    case 15: return "FFLLSSSSYY*QCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 16: return "FFLLSSSSYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 21: return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNNKSSSSVVVVAAAADDEEGGGG";
+    case 22: return "FFLLSS*SYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 23: return "FF*LSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 24: return "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSSKVVVVAAAADDEEGGGG";
+    case 25: return "FFLLSSSSYY**CCGWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 26: return "FFLLSSSSYY**CC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 27: case 28: return "FFLLSSSSYYQQCCWWLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 29: return "FFLLSSSSYYYYCC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 30: return "FFLLSSSSYYEECC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    case 31: return "FFLLSSSSYYEECCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    default: return nullptr;
+    }
+}
+static void build_codon_table(char aaOf[4096], const char *code) {
     const int exp[4] = {1, 2, 4, 8}; const int tcag[9] = {0, 2, 1, 0, 3, 0, 0, 0, 0};
     for (int i = 0; i < 16; i++) for (int j = 0; j < 16; j++) for (int k = 0; k < 16; k++) {
         char aa = 0; bool go = true;
@@ -690,11 +722,14 @@ static void build_codon_table(char aaOf[4096]) {
 }
 struct mbo_orf { uint32_t contig; uint32_t from, to; uint32_t flags; uint64_t aaOff; uint32_t aaLen; uint32_t pad; };   // from/to = header coordinates; flags: 1 incomplete start, 2 incomplete end, 4 minus strand
 
-static void find_forward(const std::string &seq, int strand, size_t minLen, size_t maxLen, size_t maxGaps, int startMode, std::vector<std::array<size_t, 4>> &res) {
+static void find_forward(const std::string &seq, int strand, size_t minLen, size_t maxLen, size_t maxGaps, int startMode, const char *code, std::vector<std::array<size_t, 4>> &res) {
     const size_t L = seq.size();
+    // stop codons of the table = the '*' entries of its amino-acid string (TranslateNucl.h:428-434 -> Orf::Orf, Orf.cpp:54-64), compared letter by letter with the
+    // upper-cased sequence (Orf.cpp:266-269, isInCodons :206-228): ambiguity codes never match
+    auto tcag = [](int c) { return c == 'T' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'G' ? 3 : -1; };
     auto at = [&](size_t p) -> int { return p < L ? (unsigned char)seq[p] : 127; };   // CHAR_MAX padding (Orf.cpp:151-154)
     auto up = [&](int c) { return c == 127 ? 127 : (c & ~0x20); };
-    auto isStop = [&](int a, int b, int c) { return a == 'T' && ((b == 'A' && (c == 'A' || c == 'G')) || (b == 'G' && c == 'A')); };   // table 1
+    auto isStop = [&](int a, int b, int c) { const int x = tcag(a), y = tcag(b), z = tcag(c); return x >= 0 && y >= 0 && z >= 0 && code[16 * x + 4 * y + z] == '*'; };
     auto isStart = [&](int a, int b, int c) { return a == 'A' && b == 'T' && c == 'G'; };
     auto gapOrN = [&](int c) { return c == 'N' || c == 127 || iupac_complement((char)c) == '.'; };
     bool inside[3] = {true, true, true}, hasStart[3] = {false, false, false};
@@ -725,9 +760,10 @@ extern "C" {
 // Contigs: concatenated ASCII nucleotides.  Output in the reference's key order: contigs ascending, plus-strand ORFs in emission order,
 // then minus-strand ORFs (DBWriter::createRenumberedDB sorts by (contig key, data offset), DBWriter.cpp:690-738).  aa = ASCII residues.
 // Returns the number of ORFs or -1 if a capacity is exceeded.
-long long mbo_extract_orfs_mt(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
+long long mbo_extract_orfs_tt(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode, int table,
                               mbo_orf *recs, uint64_t capRecs, char *aa, uint64_t capAa, uint64_t *aaUsed, int threads) {
-    char aaOf[4096]; build_codon_table(aaOf);
+    const char *code = genetic_code(table); if (!code) return -2;
+    char aaOf[4096]; build_codon_table(aaOf, code);
     std::vector<std::vector<mbo_orf>> perRec(nContigs); std::vector<std::string> perAa(nContigs);
     if (threads < 1) threads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
@@ -738,8 +774,8 @@ long long mbo_extract_orfs_mt(const char *nuc, const uint64_t *off, uint32_t nCo
         for (size_t i = 0; i < L; i++) if (fwd[i] == 'u') fwd[i] = 't';                  // (the 'U' branch is overwritten, Orf.cpp:141-144)
         for (size_t i = 0; i < L; i++) { char x = iupac_complement(fwd[L - 1 - i]); rev[i] = (x == '.') ? 'N' : x; }
         std::vector<std::array<size_t, 4>> res;
-        find_forward(fwd, +1, minLen, maxLen, (size_t)-1, startMode, res);
-        find_forward(rev, -1, minLen, maxLen, (size_t)-1, startMode, res);
+        find_forward(fwd, +1, minLen, maxLen, (size_t)-1, startMode, code, res);
+        find_forward(rev, -1, minLen, maxLen, (size_t)-1, startMode, code, res);
         for (auto &o : res) {
             const std::string &s = (int)o[3] > 0 ? fwd : rev;
             size_t nucLen = o[1] - o[0] + 1;
@@ -764,6 +800,10 @@ long long mbo_extract_orfs_mt(const char *nuc, const uint64_t *off, uint32_t nCo
     }
     *aaUsed = na;
     return (long long)n;
+}
+long long mbo_extract_orfs_mt(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
+                              mbo_orf *recs, uint64_t capRecs, char *aa, uint64_t capAa, uint64_t *aaUsed, int threads) {
+    return mbo_extract_orfs_tt(nuc, off, nContigs, minLen, maxLen, startMode, 1, recs, capRecs, aa, capAa, aaUsed, threads);
 }
 long long mbo_extract_orfs(const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen, int startMode,
                            mbo_orf *recs, uint64_t capRecs, char *aa, uint64_t capAa, uint64_t *aaUsed) {

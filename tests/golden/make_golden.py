@@ -514,6 +514,68 @@ def case_reference_tests(name="ref_tests", thr=8):
     with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
         json.dump(out, f)
 
+FLAG_VARIANTS = [
+    # name, flags handed to `metaeuk predictexons` on top of its defaults
+    ("default", ""),
+    ("s6", "-s 6"),
+    ("s1", "-s 1"),
+    ("s7.5", "-s 7.5"),
+    ("kscore", "--k-score seq:140,prof:140"),
+    ("maxseqs10", "--max-seqs 10"),
+    ("eval", "-e 0.001"),
+    ("minexon", "--min-exon-aa 20 --min-length 30"),
+    ("maxlen", "--max-length 120"),
+    ("nocomp", "--comp-bias-corr 0"),
+    ("reverse", "--reverse-fragments 1"),
+    ("table4", "--translation-table 4"),
+    ("table6", "--translation-table 6"),
+    ("nomask", "--mask 0"),
+    ("minungapped", "--min-ungapped-score 30"),
+    ("dp", "--max-intron 400 --min-intron 60 --max-overlap 4 --set-gap-open -3 --set-gap-extend -2 --metaeuk-eval 1e-6 --metaeuk-tcov 0.3 --max-exon-sets 2"),
+]
+
+
+def case_flags(name="flags", seed=808, thr=8):
+    """One small contig set through the reference's `predictexons` WORKFLOW (data/predictexons.sh) once per entry of FLAG_VARIANTS: the flags a user of
+    `metaeuk predictexons` can change on this path (sensitivity -> k-mer threshold, list length, E-value, ORF length limits, genetic code, composition bias off,
+    reversed fragments = the null model, masking off, exon-chaining parameters).  Stored per variant: the k-mer threshold the reference logged, the six-frame
+    fragments and their headers (only if they differ from the default run), search_res and the calls."""
+    rng = random.Random(seed)
+    prots = make_proteins(rng, 150, family=40, lowcomplex=4)
+    contigs = make_contigs(rng, prots, 4, 8000)
+    out = {"case": name, "kind": "flags", "seed": seed, "variants": {}}
+    base_q = None
+    for vn, flags in FLAG_VARIANTS:
+        tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+        log = []
+        write_fasta(tmp + "/proteins.faa", prots, "P")
+        write_fasta(tmp + "/contigs.fna", contigs, "C")
+        run("%s createdb %s/proteins.faa %s/proteins -v 3" % (REF, tmp, tmp), log)
+        run("%s createdb %s/contigs.fna %s/contigs -v 3" % (REF, tmp, tmp), log)
+        wf = run("%s predictexons %s/contigs %s/proteins %s/predEx %s/tmp %s --remove-tmp-files 0 --threads %d -v 3" % (REF, tmp, tmp, tmp, tmp, flags, thr), log)
+        lt = tmp + "/tmp/latest"
+        aa = "/aa_6f_reverse" if "--reverse-fragments 1" in flags else "/aa_6f"
+        d = {"flags": flags, "kmer_thr": int(wf.split("k-mer similarity threshold: ")[1].split()[0]),
+             "aln": {k: t for k, t in resdb(lt + "/search_res").items() if t}, "dp": resdb(tmp + "/predEx")}          # (only the non-empty search_res entries)
+        q = {"queries": sorted(seqdb(lt + aa)), "orf_headers": {str(k): e[:-1].decode() for k, e in read_db(lt + "/nucl_6f_h")}}
+        if aa.endswith("_reverse"):      # reverseseq = every fragment back to front, headers unchanged: stored as a flag
+            assert q["orf_headers"] == base_q["orf_headers"] and q["queries"] == [(k, t[::-1]) for k, t in base_q["queries"]]
+            q = base_q; d["reversed"] = True
+        if vn == "default":
+            base_q = q
+            out["targets"] = seqdb(tmp + "/proteins"); out["contigs"] = seqdb(tmp + "/contigs")
+            out["masked_targets"] = ref_index(tmp, "proteins", 1, thr, log)["masked_targets"]
+            d.update(q)
+        elif q != base_q:
+            d.update(q)
+        out["variants"][vn] = d
+        shutil.rmtree(tmp)
+        print(vn, "kmer_thr", d["kmer_thr"], "fragments", len(q["queries"]), "aln lines", sum(v.count("\n") for v in d["aln"].values()),
+              "dp lines", sum(v.count("\n") for v in d["dp"].values()), "own fragments" if "queries" in d and vn != "default" else "")
+    out["ref_version"] = run("%s version" % REF, []).strip()
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+
 
 if __name__ == "__main__":
     if not os.path.exists(REF):
@@ -539,3 +601,5 @@ if __name__ == "__main__":
         case_reference_tests()
     if "mask_repeats" in which:
         case_masking()
+    if "flags" in which:
+        case_flags()

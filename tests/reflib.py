@@ -112,6 +112,9 @@ class Oracle:
         self.max_res = maxResListLen
         self.L.mbo_set_params(self.h, kmerThr, maxResListLen, minDiagScore, binSize, gapOpen, gapExtend, C.c_double(evalThr), minAlnLen)
 
+    def set_comp_bias_corr(self, on):
+        self.L.mbo_set_comp_bias_corr(self.h, int(bool(on)))
+
     def matrices(self):
         seed = np.zeros(441, np.int16); ung = np.zeros(441, np.int16); aln = np.zeros(441, np.int16)
         sp = np.zeros(21, np.float64); ap = np.zeros(21, np.float64)
@@ -196,27 +199,27 @@ def fmt_orf_header(contig_key, frm, to, flags):
     return h + "\n"
 
 
-def oracle_extract_orfs_raw(seq, off, min_len=15, max_len=32734, start_mode=1, threads=1):
+def oracle_extract_orfs_raw(seq, off, min_len=15, max_len=32734, start_mode=1, threads=1, table=1):
     """seq: bytes of concatenated contigs, off: uint64[n+1] -> (n_orfs, records, residues buffer); the C call only"""
     if not os.path.exists(ORACLE_SO):
         build_oracle()
     L = C.CDLL(ORACLE_SO)
-    L.mbo_extract_orfs_mt.restype = C.c_longlong
+    L.mbo_extract_orfs_tt.restype = C.c_longlong
     cap = max(16, len(seq) // 8)
     recs = (OrfRec * cap)(); aa = C.create_string_buffer(2 * len(seq) + 16); used = C.c_uint64(0)
-    n = L.mbo_extract_orfs_mt(seq, _p(off, C.c_uint64), C.c_uint32(len(off) - 1), min_len, max_len, start_mode, recs, C.c_uint64(cap), aa, C.c_uint64(2 * len(seq) + 16), C.byref(used),
-                              int(threads))
+    n = L.mbo_extract_orfs_tt(seq, _p(off, C.c_uint64), C.c_uint32(len(off) - 1), min_len, max_len, start_mode, int(table), recs, C.c_uint64(cap), aa, C.c_uint64(2 * len(seq) + 16),
+                              C.byref(used), int(threads))
     assert n >= 0
     return n, recs, aa
 
 
-def oracle_extract_orfs(contigs, min_len=15, max_len=32734, start_mode=1):
+def oracle_extract_orfs(contigs, min_len=15, max_len=32734, start_mode=1, table=1):
     """contigs: [(key, nucleotides)] -> ({orfKey: header}, {orfKey: aa}) through the CPU oracle (extractorfs + translatenucs)"""
     seq = "".join(s for _, s in contigs).encode()
     off = np.zeros(len(contigs) + 1, np.uint64)
     if contigs:
         off[1:] = np.cumsum([len(s) for _, s in contigs])
-    n, recs, aa = oracle_extract_orfs_raw(seq, off, min_len, max_len, start_mode)
+    n, recs, aa = oracle_extract_orfs_raw(seq, off, min_len, max_len, start_mode, table=table)
     hdr, seqs = {}, {}
     for i in range(n):
         r = recs[i]
@@ -465,9 +468,12 @@ def cands_of(text):
     return out
 
 
-def oracle_pipeline(o, contigs, target_keys, target_lens, max_sets=1, gap_open=-1, gap_extend=-1, tcov=0.5, threads=0):
+def oracle_pipeline(o, contigs, target_keys, target_lens, max_sets=1, gap_open=-1, gap_extend=-1, tcov=0.5, threads=0, min_len=15, max_len=32734, table=1,
+                    reverse_fragments=False, **chain_kw):
     """contigs [(key, nucleotides)] -> dict(orf_headers, queries, aln, bycontig, dp) as the reference's DBs (o: Oracle with params and targets set)"""
-    hdr, seqs = oracle_extract_orfs(contigs)
+    hdr, seqs = oracle_extract_orfs(contigs, min_len=min_len, max_len=max_len, table=table)
+    if reverse_fragments:       # data/predictexons.sh:52-62 (reverseseq: the null model)
+        seqs = {k: v[::-1] for k, v in seqs.items()}
     frags = [seqs[i] for i in range(len(seqs))]
     res, _ = o.prefilter(frags, threads=threads)
     alns, _ = o.align(frags, [[t for t, _, _ in h] for h in res], threads=threads)
@@ -477,8 +483,35 @@ def oracle_pipeline(o, contigs, target_keys, target_lens, max_sets=1, gap_open=-
     dp = {}
     for ck, text in byc.items():
         cands = cands_of(text)
-        dp[ck] = fmt_dp(o.chain(cands, sum(target_lens), max_sets=max_sets, gap_open=gap_open, gap_extend=gap_extend, tcov=tcov), cands)
+        dp[ck] = fmt_dp(o.chain(cands, sum(target_lens), max_sets=max_sets, gap_open=gap_open, gap_extend=gap_extend, tcov=tcov, **chain_kw), cands)
     return dict(orf_headers=hdr, queries=seqs, aln=aln, bycontig=byc, dp=dp)
+
+
+def sensitivity_to_kmer_thr(s):
+    """Prefiltering::getKmerThreshold for sequence searches with k = 6 (Prefiltering.cpp:1049-1055,1063): float base 163.2, the product s * 8.917 in double,
+    the difference stored in a float and truncated"""
+    return int(np.float32(float(np.float32(163.2)) - float(np.float32(s)) * 8.917))
+
+
+# `metaeuk predictexons` flags of tests/golden/flags.json.gz -> (oracle parameters, ORF / pipeline options, exon-chaining options)
+FLAG_VARIANTS = {
+    "default": ({}, {}),
+    "s6": (dict(kmerThr=sensitivity_to_kmer_thr(6)), {}),
+    "s1": (dict(kmerThr=sensitivity_to_kmer_thr(1)), {}),
+    "s7.5": (dict(kmerThr=sensitivity_to_kmer_thr(7.5)), {}),
+    "kscore": (dict(kmerThr=140), {}),
+    "maxseqs10": (dict(maxResListLen=10), {}),
+    "eval": (dict(evalThr=0.001), {}),
+    "minexon": (dict(minAlnLen=20), dict(min_len=30, min_exon_aa=20)),        # PredictExons.cpp:44: the align stage's --min-aln-len follows --min-exon-aa
+    "maxlen": ({}, dict(max_len=120)),
+    "nocomp": (dict(comp_bias_corr=False), {}),
+    "reverse": ({}, dict(reverse_fragments=True)),
+    "table4": ({}, dict(table=4)),
+    "table6": ({}, dict(table=6)),
+    "nomask": (dict(nomask=True), {}),
+    "minungapped": (dict(minDiagScore=30), {}),
+    "dp": ({}, dict(max_intron=400, min_intron=60, max_overlap=4, gap_open=-3, gap_extend=-2, eval_thr=1e-6, tcov=0.3, max_sets=2)),
+}
 
 
 def fmt_fasta_headers(dp, target_acc, contig_acc):
