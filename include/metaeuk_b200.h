@@ -58,6 +58,14 @@ typedef struct mb200_params {
     double tcov, metaeuk_eval;
     /* capacities of the per-CTA work lists, log2 (0 = default) */
     int32_t cap_items_log2, cap_kmers_log2, cap_hits_log2, pad2;
+    /* flags of `metaeuk predictexons` that change what the path computes (defaults 1, 0, 1) */
+    int32_t comp_bias_corr;     /* --comp-bias-corr: 0 = no composition-bias correction in the prefilter and the alignment (QueryMatcher.cpp:91-99,
+                                   StripedSmithWaterman.cpp:1228-1240) */
+    int32_t reverse_fragments;  /* --reverse-fragments 1: every six-frame fragment is searched back to front (the null model; data/predictexons.sh:52-62,
+                                   `reverseseq`); headers and coordinates stay those of the forward fragment */
+    int32_t translation_table;  /* --translation-table: NCBI genetic code of the ORF scan (its stop codons, Orf.cpp:54-64) and of the translation
+                                   (TranslateNucl.h:110-246): 1-6, 9-16, 21-31 */
+    int32_t pad3;
 } mb200_params;
 
 typedef struct mb200_hit { uint32_t seq_id; int32_t score; int32_t diag; } mb200_hit;       /* = hit_t written to pref_N */
@@ -113,6 +121,9 @@ int mb200_ctx_create(int device, mb200_ctx **out);
 void mb200_ctx_destroy(mb200_ctx *ctx);
 const char *mb200_last_error(void);
 void mb200_params_default(mb200_params *p);
+/* what `-s <sensitivity>` means for kmer_thr: Prefiltering::getKmerThreshold for a sequence search with k = 6 (M/src/prefiltering/Prefiltering.cpp:1005-1064);
+ * -s 4 (MetaEuk's default) -> 127 */
+int mb200_kmer_threshold(float sensitivity);
 int mb200_params_set(mb200_ctx *ctx, const mb200_params *p);
 
 /* matrices: built like the reference builds them, or supplied by a caller that already holds the reference's BaseMatrix objects */

@@ -57,4 +57,11 @@ struct EvalueModel {
     int minScoreFor(double evalThr, double qLen, double dbResidues) const;
 };
 
+// NCBI genetic code `table` as the amino acid of each codon in TCAG order ('*' = stop), NULL if the reference does not know the id
+// (TranslateNucl's constructor, TranslateNucl.h:110-246: 1-6, 9-16, 21-31).  The ORF scan takes its stop codons from it, the translation its residues.
+const char *genetic_code(int table);
+
+// Prefiltering::getKmerThreshold for a sequence search with k = 6 (Prefiltering.cpp:1049-1055,1063): what `-s` means for the k-mer similarity threshold
+int kmer_threshold_for_sensitivity(float sensitivity);
+
 }  // namespace mb200

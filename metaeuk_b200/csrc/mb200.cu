@@ -150,6 +150,8 @@ struct mb200_ctx {
     uint64_t nEntries = 0, totalRes = 0; uint32_t nT = 0; std::vector<uint64_t> hToff; bool haveIndex = false, haveSim3 = false;
     // prefilter scratch
     int nCta = 0; DevBuf<MbPrefScratch> dScratch; DevBuf<unsigned char> dScratchMem; uint32_t capP = 0, capI = 0, capK = 0, capM = 0;
+    int nCtaRescue = 0; DevBuf<MbPrefScratch> dScratchRescue; DevBuf<unsigned char> dScratchRescueMem; DevBuf<uint32_t> dOrderRescue; uint32_t rescueCapM = 0;   // second pass for queries whose work lists overflowed
+    uint64_t rescuedQueries = 0;
     // resident query batch
     DevBuf<uint8_t> dQ; DevBuf<uint64_t> dQoff; DevBuf<float> dBias; DevBuf<int8_t> dCorr, dCb; DevBuf<uint32_t> dOrder;
     std::vector<uint64_t> hQoff; uint32_t nQ = 0; uint64_t totalQ = 0; uint32_t maxQLen = 0;
@@ -196,11 +198,28 @@ static int ctx_upload_matrices(mb200_ctx *c) {
     return 0;
 }
 
+// per-CTA work lists of k_prefilter for `n` CTAs with the given capacities, carved out of one allocation
+static int pref_scratch_build(mb200_ctx *c, int n, uint32_t capP, uint32_t capI, uint32_t capM, DevBuf<unsigned char> &mem, DevBuf<MbPrefScratch> &dS) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al(((size_t)capI + 1) * 4) + al((size_t)capI * 4) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
+    TRY(mem.alloc(per * n)); TRY(dS.alloc(n));
+    std::vector<MbPrefScratch> hs(n);
+    for (int i = 0; i < n; i++) {
+        unsigned char *b = mem.p + per * i; MbPrefScratch &W = hs[i];
+        W.itemOff = (uint32_t *)b; b += al((capP + 1) * 4); W.wThr = (int16_t *)b; b += al(capP * 2); W.wI0 = (uint16_t *)b; b += al(capP * 2); W.wI1 = (uint16_t *)b; b += al(capP * 2);
+        W.kmerOff = (uint32_t *)b; b += al(((size_t)capI + 1) * 4); W.itemInfo = (uint32_t *)b; b += al((size_t)capI * 4);
+        W.A = (uint64_t *)b; b += al((size_t)capM * 8); W.B = (uint64_t *)b; b += al((size_t)capM * 8); W.C = (uint64_t *)b; b += al((size_t)capM * 8); W.S = (int32_t *)b;
+    }
+    TRY(upload(dS.p, hs.data(), hs.size() * sizeof(MbPrefScratch), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 static int ctx_alloc_scratch(mb200_ctx *c) {
     const uint32_t capP = 32768, capI = 1u << (c->par.cap_items_log2 ? c->par.cap_items_log2 : 17), capK = 1u << (c->par.cap_kmers_log2 ? c->par.cap_kmers_log2 : 18),
                    capM = 1u << (c->par.cap_hits_log2 ? c->par.cap_hits_log2 : 19);
-    if (capK > (1u << 18)) return fail(MB200_E_ARG, "cap_kmers_log2 > 18 (the k-mer ordinal is an 18-bit field)");
-    if (capM < capK || capM > (1u << 24)) return fail(MB200_E_ARG, "cap_hits_log2 must be in [cap_kmers_log2, 24]");
+    if (capK > (1u << 21)) return fail(MB200_E_ARG, "cap_kmers_log2 > 21 (the k-mer ordinal is a 21-bit field)");
+    if (capI > (1u << 24) || capM > (1u << 24)) return fail(MB200_E_ARG, "cap_items_log2 / cap_hits_log2 must be <= 24");
     // dense config for indexes with long k-mer lists (>= 1 entry per k-mer slot on average), sparse config otherwise
     const int cfg = c->optPrefCfg ? c->optPrefCfg : ((double)c->nEntries >= 1.0 * (double)mb200::KMER_TABLE ? 1 : 2);
     if (c->nCta && cfg == c->prefCfg && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
@@ -216,18 +235,7 @@ static int ctx_alloc_scratch(mb200_ctx *c) {
     }
     if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
     c->nCta = c->nSM * perSM;
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t per = al((capP + 1) * 4) + al(capP * 2) * 3 + al((capI + 1) * 4) + al(capI * 4) + al((size_t)capM * 8) * 3 + al((size_t)capM * 4);
-    TRY(c->dScratchMem.alloc(per * c->nCta)); TRY(c->dScratch.alloc(c->nCta));
-    std::vector<MbPrefScratch> hs(c->nCta);
-    for (int i = 0; i < c->nCta; i++) {
-        unsigned char *b = c->dScratchMem.p + per * i; MbPrefScratch &W = hs[i];
-        W.itemOff = (uint32_t *)b; b += al((capP + 1) * 4); W.wThr = (int16_t *)b; b += al(capP * 2); W.wI0 = (uint16_t *)b; b += al(capP * 2); W.wI1 = (uint16_t *)b; b += al(capP * 2);
-        W.kmerOff = (uint32_t *)b; b += al((capI + 1) * 4); W.itemInfo = (uint32_t *)b; b += al(capI * 4);
-        W.A = (uint64_t *)b; b += al((size_t)capM * 8); W.B = (uint64_t *)b; b += al((size_t)capM * 8); W.C = (uint64_t *)b; b += al((size_t)capM * 8); W.S = (int32_t *)b;
-    }
-    TRY(upload(c->dScratch.p, hs.data(), hs.size() * sizeof(MbPrefScratch), c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    TRY(pref_scratch_build(c, c->nCta, capP, capI, capM, c->dScratchMem, c->dScratch));
     c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM; c->prefCfg = cfg;
     return 0;
 }
@@ -251,7 +259,10 @@ void mb200_params_default(mb200_params *p) {
     p->gap_open = 11; p->gap_extend = 1; p->min_aln_len = 11; p->eval_thr = 100.0;
     p->min_intron = 15; p->max_intron = 10000; p->min_exon_aa = 11; p->max_overlap = 10; p->set_gap_open = -1; p->set_gap_extend = -1; p->max_exon_sets = 1;
     p->tcov = 0.5; p->metaeuk_eval = 0.001;
+    p->comp_bias_corr = 1; p->reverse_fragments = 0; p->translation_table = 1;
 }
+
+int mb200_kmer_threshold(float sensitivity) { return mb200::kmer_threshold_for_sensitivity(sensitivity); }
 
 int mb200_ctx_create(int device, mb200_ctx **out) {
     if (!out) return fail(MB200_E_ARG, "out == NULL");
@@ -273,7 +284,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
-    c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release();
+    c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
@@ -316,6 +327,8 @@ int mb200_params_set(mb200_ctx *c, const mb200_params *p) {
     if (p->max_res_list_len < 1 || p->max_res_list_len > 65535) return fail(MB200_E_ARG, "max_res_list_len out of range");
     if (p->gap_open != c->par.gap_open || p->gap_extend != c->par.gap_extend || p->eval_thr != c->par.eval_thr) c->minScore.clear();
     if ((p->gap_open != 11 || p->gap_extend != 1)) return fail(MB200_E_ARG, "only the reference's fixed BLOSUM62 11/1 e-value model is implemented");
+    if (!mb200::genetic_code(p->translation_table)) return fail(MB200_E_ARG, "translation_table %d is not an NCBI genetic code the reference knows (1-6, 9-16, 21-31)", p->translation_table);
+    if (p->translation_table != c->par.translation_table) c->haveOrfTab = false;
     c->par = *p; return 0;
 }
 
@@ -508,7 +521,11 @@ static int queries_install(mb200_ctx *c, const uint8_t *q, const uint8_t *qDev, 
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_h2d = ms;
     c->hQoff.assign(qoff, qoff + nQ + 1); c->nQ = nQ; c->totalQ = tot; c->maxQLen = maxL; c->havePref = false; c->haveAln = false; c->hOrder = order;
-    if (tot) {
+    if (tot && !c->par.comp_bias_corr) {
+        // --comp-bias-corr 0: the reference zeroes all three arrays (QueryMatcher.cpp:97-99, StripedSmithWaterman.cpp:1238-1240)
+        CU(cudaMemsetAsync(c->dBias.p, 0, tot * sizeof(float), c->stream)); CU(cudaMemsetAsync(c->dCorr.p, 0, tot, c->stream)); CU(cudaMemsetAsync(c->dCb.p, 0, tot, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); c->st.ms_prep = 0;
+    } else if (tot) {
         CU(cudaEventRecord(c->ev0, c->stream));
         k_prep<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->dQ.p, c->dQoff.p, nQ, tot, c->dSeedMat.p, c->dSeedPB.p, c->dAlnMat.p, c->dAlnPB.p, c->dBias.p, c->dCorr.p, c->dCb.p);
         CU(cudaGetLastError());
@@ -527,7 +544,7 @@ int mb200_queries_upload(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, u
 
 
 // ---- ORF extraction + translation (the step before the path: extractorfs + translatenucs) ----------------
-static void orf_build_tables(MbOrfTables &T) {
+static void orf_build_tables(MbOrfTables &T, const char *code) {
     // complement (Orf::iupacReverseComplementTable, Orf.cpp:47-51) with "no complement" -> 'N' (Orf.cpp:146-150)
     const char *from = "ATUGCYRSWKMBDHVN", *to = "TAACGRYSWMKVHDBN";
     for (int c = 0; c < 256; c++) T.comp[c] = 'N';
@@ -537,8 +554,7 @@ static void orf_build_tables(MbOrfTables &T) {
     for (int c = 0; c < 256; c++) T.base[c] = 0;
     for (int i = 0; i < 16; i++) { T.base[(unsigned char)bases[i]] = (unsigned char)i; T.base[(unsigned char)tolower(bases[i])] = (unsigned char)i; T.base[i] = (unsigned char)i; }
     T.base['U'] = T.base['u'] = 8; T.base['X'] = T.base['x'] = 15;
-    // codon table of genetic code 1 over base sets (TranslateNucl::initTranslationTable, TranslateNucl.h:383-485)
-    const char *code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    // codon table of the genetic code over base sets (TranslateNucl::initTranslationTable, TranslateNucl.h:383-485)
     const int ex[4] = {1, 2, 4, 8}; const int tcag[9] = {0, 2, 1, 0, 3, 0, 0, 0, 0};
     for (int i = 0; i < 16; i++) for (int j = 0; j < 16; j++) for (int k = 0; k < 16; k++) {
         char aa = 0; bool go = true;
@@ -573,7 +589,10 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     CU(cudaSetDevice(c->device));
     const uint64_t total = off[nContigs] - off[0];
     for (uint32_t i = 0; i < nContigs; i++) if (off[i + 1] - off[i] >= (1ull << 31)) return fail(MB200_E_LIMIT, "contig %u has >= 2^31 nucleotides", i);
-    if (!c->haveOrfTab) { MbOrfTables T; orf_build_tables(T); TRY(c->dOrfTab.alloc(1)); TRY(upload(c->dOrfTab.p, &T, sizeof(T), c->stream)); CU(cudaStreamSynchronize(c->stream)); c->haveOrfTab = true; }
+    const char *code = mb200::genetic_code(c->par.translation_table);
+    if (!code) return fail(MB200_E_ARG, "unknown translation table %d", c->par.translation_table);
+    const unsigned long long stopSet = orf_stop_set(code);
+    if (!c->haveOrfTab) { MbOrfTables T; orf_build_tables(T, code); TRY(c->dOrfTab.alloc(1)); TRY(upload(c->dOrfTab.p, &T, sizeof(T), c->stream)); CU(cudaStreamSynchronize(c->stream)); c->haveOrfTab = true; }
     const uint32_t units = 2u * nContigs;
     TRY(c->dNuc.alloc(total + 16)); TRY(c->dNucOff.alloc(nContigs + 1)); TRY(c->dOrfCnt.alloc(units + 1)); TRY(c->dOrfAaCnt.alloc(units + 1));
     TRY(c->dOrfRecBase.alloc(units + 1)); TRY(c->dOrfAaBase.alloc(units + 1));
@@ -584,7 +603,7 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     c->nOrfs = 0; c->nOrfAa = 0; *nOrfs = 0; *nAa = 0; *orfs = nullptr; *aa = nullptr;
     if (nContigs == 0) return 0;
     const int grid = (int)std::min<uint32_t>(units, (uint32_t)c->nSM * 8u);
-    k_orf_scan<false><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen,
+    k_orf_scan<false><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
                                                               c->dOrfCnt.p, c->dOrfAaCnt.p, nullptr, nullptr, nullptr);
     CU(cudaGetLastError());
     std::vector<uint32_t> cnt(units); std::vector<uint64_t> acnt(units), rb(units + 1, 0), ab(units + 1, 0);
@@ -596,10 +615,10 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     TRY(c->dOrfRecs.alloc(n + 1)); TRY(c->dOrfAa.alloc(na + 16)); TRY(c->dOrfCodes.alloc(na + 16)); TRY(c->pOrfRecs.alloc(n + 1)); TRY(c->pOrfAa.alloc(na + 16));
     TRY(upload(c->dOrfRecBase.p, rb.data(), (size_t)(units + 1) * 8, c->stream)); TRY(upload(c->dOrfAaBase.p, ab.data(), (size_t)(units + 1) * 8, c->stream));
     if (n) {
-        k_orf_scan<true><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen,
+        k_orf_scan<true><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
                                                                  nullptr, nullptr, c->dOrfRecBase.p, c->dOrfAaBase.p, c->dOrfRecs.p);
         CU(cudaGetLastError());
-        k_orf_translate<<<c->nSM * 8, 256, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, c->dOrfTab.p, c->dOrfRecs.p, n, c->dOrfAa.p, c->dOrfCodes.p);
+        k_orf_translate<<<c->nSM * 8, 256, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, c->dOrfTab.p, c->dOrfRecs.p, n, c->par.reverse_fragments ? 1 : 0, c->dOrfAa.p, c->dOrfCodes.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaMemcpyAsync(c->pOrfRecs.p, c->dOrfRecs.p, (size_t)n * sizeof(MbOrfRec), cudaMemcpyDeviceToHost, c->stream));
@@ -669,7 +688,8 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     MbPrefTables T; memset(&T, 0, sizeof(T));
     T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
     T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
-    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.capM = c->capM; T.phaseStats = c->optPhaseStats;
+    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.phaseStats = c->optPhaseStats;
+    T.capM = (uint32_t)std::min<uint64_t>(c->capM, 2ull * std::max<uint64_t>(1000000ull, c->nT) - 1);   // beyond that the reference switches to its own overflow path (QueryMatcher.cpp:43,280-305)
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
         if (c->prefCfg == 1)
@@ -688,6 +708,40 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     uint32_t *status = c->pStatus.p;
     CU(cudaMemcpyAsync(status, c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    // Queries whose work lists overflowed the default per-CTA capacities (long fragments at a high sensitivity, low-complexity queries against dense indexes)
+    // take a second pass on a few CTAs with the largest capacities the kernel's word layouts allow: 2^22 (window, neighbour) items, 2^21 similar k-mers,
+    // and as many index hits as the reference itself can hold before ITS overflow path starts (maxDbMatches = 2 max(10^6, #targets), QueryMatcher.cpp:43,
+    // 280-305 -- that path changes the result and is not reproduced, so reaching it stays an error).  Capacities set explicitly by the caller are hard limits.
+    if (nQ && !c->par.cap_items_log2 && !c->par.cap_kmers_log2 && !c->par.cap_hits_log2) {
+        std::vector<uint32_t> again;
+        for (uint32_t i = 0; i < nQ; i++) if (status[i] == MB_ST_OVERFLOW) again.push_back(i);
+        if (!again.empty()) {
+            const uint64_t refMax = 2ull * std::max<uint64_t>(1000000ull, c->nT);
+            uint32_t allocM = 1u << 21; while (allocM < (1u << 24) && allocM < refMax) allocM <<= 1;          // the lists are sorted in place: power-of-two room
+            const uint32_t capI2 = 1u << 22, capK2 = 1u << 21, capM2 = (uint32_t)std::min<uint64_t>(allocM, refMax - 1);
+            const int nR = (int)std::min<size_t>(again.size(), 32);
+            if (c->nCtaRescue < nR || c->rescueCapM != allocM) {
+                TRY(pref_scratch_build(c, nR, 32768, capI2, allocM, c->dScratchRescueMem, c->dScratchRescue)); c->nCtaRescue = nR; c->rescueCapM = allocM;
+            }
+            TRY(c->dOrderRescue.alloc(again.size()));
+            TRY(upload(c->dOrderRescue.p, again.data(), again.size() * 4, c->stream));
+            CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream));
+            MbPrefTables T2 = T; T2.capI = capI2; T2.capK = capK2; T2.capM = capM2;
+            CU(cudaEventRecord(c->ev0, c->stream));
+            if (c->prefCfg == 1)
+                k_prefilter<MbPrefSharedT<MbPrefCfgDense>><<<nR, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream>>>(
+                    T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+            else
+                k_prefilter<MbPrefSharedT<MbPrefCfgSparse>><<<nR, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream>>>(
+                    T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(c->ev1, c->stream));
+            CU(cudaMemcpyAsync(status, c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            float ms2 = 0; CU(cudaEventElapsedTime(&ms2, c->ev0, c->ev1)); c->st.ms_prefilter += ms2; c->st.launches++;
+            c->rescuedQueries += again.size();
+        }
+    }
     for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK)
         return fail(status[i] == MB_ST_OVERFLOW ? MB200_E_OVERFLOW : MB200_E_LIMIT, "query %u: prefilter status %u (work list capacity exceeded or sequence too long)", i, status[i]);
     MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));

@@ -13,7 +13,8 @@
 //                                                   == predictexons.sh:68-82 (search -> resultspercontig -> collectoptimalset)
 // DBs are MMseqs databases: data file(s) name[.N], name.index "key\toffset\tlength", name.dbtype.
 // Result DBs are written byte-compatible with the reference's (same records, same keys; one data file).
-// Options: --max-seqs N  --min-ungapped-score N  --k-score N  -e X  --min-aln-len N  --mask 0|1 (default 1: tantan masking of the targets as the reference's
+// Options: -s X (sensitivity -> k-mer threshold as Prefiltering::getKmerThreshold)  --k-score N  --max-seqs N  --min-ungapped-score N  -e X  --min-aln-len N
+// --comp-bias-corr 0|1  --min-length N --max-length N --translation-table N (ORF extraction)  --reverse-fragments 0|1 (null model)  --mask 0|1 (default 1: tantan masking of the targets as the reference's
 // index builder does it, --mask-prob 0.9)  --masked-db <db> (take the masked target residues from a DB instead: lower case or X = masked)  --metaeuk-eval X
 // --metaeuk-tcov X --max-intron N --min-intron N --min-exon-aa N --max-overlap N --max-exon-sets N --set-gap-open N --set-gap-extend N
 // --device N.  Everything numeric happens in the library (GPU); this file is DB I/O and the reference's text formatting.
@@ -109,17 +110,54 @@ static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e
 
 struct Opt {
     mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb; int mask = 1; double maskProb = 0.9;
+    int minLen = 15, maxLen = 32734;   // --min-length / --max-length of extractorfs in codons (setPredictExonsDefaults, src/workflow/PredictExons.cpp:8-16)
 };
+
+// Flags of the reference's modules that this driver takes.  Three groups: flags that change what the path computes and are implemented (parseOpts); flags that
+// never change a result (threads, verbosity, ...), accepted and ignored; flags of behaviour that is NOT implemented, accepted only with the value `metaeuk
+// predictexons` itself passes -- anything else stops the run instead of silently computing something different.  Unknown flags stop it too.
+static const char *IGNORED_FLAGS[] = {"--threads", "-v", "--compressed", "--remove-tmp-files", "--db-load-mode", "--split-memory-limit", "--force-reuse", "--mpi-runner",
+                                      "--local-tmp", "--disk-space-limit", "--pca", "--pcb", "--zdrop", "--strand", "--realign-score-bias", "--realign-max-seqs",
+                                      "--e-profile", "--mask-profile", "--filter-msa", "--max-seq-id", "--qid", "--qsc", "--cov", "--diff", "--pseudo-cnt-mode", "--wg", nullptr};
+struct FixedFlag { const char *name; const char *ok[4]; };
+static const FixedFlag FIXED_FLAGS[] = {
+    {"--alignment-mode", {"2"}}, {"--alignment-output-mode", {"0"}}, {"-a", {"0"}}, {"--gap-open", {"11", "aa:11,nucl:5"}}, {"--gap-extend", {"1", "aa:1,nucl:2"}},
+    {"--sub-mat", {"blosum62.out", "aa:blosum62.out,nucl:nucleotide.out"}}, {"--seed-sub-mat", {"VTML80.out", "aa:VTML80.out,nucl:nucleotide.out"}},
+    {"-k", {"0", "6"}}, {"--spaced-kmer-mode", {"1"}}, {"--alph-size", {"21", "aa:21,nucl:5"}}, {"--max-seq-len", {"65535"}}, {"--split", {"0", "1"}}, {"--split-mode", {"2"}},
+    {"-c", {"0"}}, {"--cov-mode", {"0"}}, {"--comp-bias-corr-scale", {"1"}}, {"--diag-score", {"1"}}, {"--exact-kmer-matching", {"0"}}, {"--mask-lower-case", {"0"}},
+    {"--mask-n-repeat", {"0"}}, {"--add-self-matches", {"0"}}, {"--min-seq-id", {"0"}}, {"--seq-id-mode", {"0"}}, {"--alt-ali", {"0"}}, {"--max-rejected", {"2147483647"}},
+    {"--max-accept", {"2147483647"}}, {"--score-bias", {"0"}}, {"--realign", {"0"}}, {"--wrapped-scoring", {"0"}}, {"--corr-score-weight", {"0"}},
+    {"--orf-start-mode", {"1"}}, {"--contig-start-mode", {"2"}}, {"--contig-end-mode", {"2"}}, {"--forward-frames", {"1,2,3"}}, {"--reverse-frames", {"1,2,3"}},
+    {"--max-gaps", {"2147483647"}}, {"--translate", {"0"}}, {"--use-all-table-starts", {"0"}}, {"--id-offset", {"0"}}, {"--create-lookup", {"0"}}, {"--add-orf-stop", {"0"}},
+    {"--num-iterations", {"1"}}, {"--exhaustive-search", {"0"}}, {"--target-search-mode", {"0"}}, {"--gpu", {"0"}}, {"--gpu-server", {"0"}}, {"--prefilter-mode", {"0"}},
+    {"--sens-steps", {"1"}}, {"--lca-search", {"0"}}, {"--slice-search", {"0"}}, {"--rescore-mode", {"0"}}, {"--chain-alignments", {"0"}}, {"--merge-query", {"1"}},
+    {"--taxon-list", {""}}, {"--spaced-kmer-pattern", {""}}, {nullptr, {}}};
+static bool sameValue(const std::string &v, const char *ok) {
+    if (v == ok) return true;
+    char *e1, *e2; const double a = strtod(v.c_str(), &e1), b = strtod(ok, &e2);
+    return *v.c_str() && *ok && !*e1 && !*e2 && a == b;
+}
+static int seqValue(const std::string &v) {   // "140" or the reference's printed form "seq:140,prof:140" (MultiParam)
+    const size_t p = v.find("seq:"); return atoi(v.c_str() + (p == std::string::npos ? 0 : p + 4));
+}
+
 static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> &pos) {
     Opt o; mb200_params_default(&o.p);
+    float sens = 4.0f; int kScore = 2147483647;     // -s 4: MetaEuk's default; --k-score INT_MAX = derive the threshold from -s
     for (int i = first; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&]() { if (i + 1 >= argc) DIE("missing value for %s", a.c_str()); return std::string(argv[++i]); };
         if (a == "--max-seqs") o.p.max_res_list_len = atoi(val().c_str());
         else if (a == "--min-ungapped-score") o.p.min_diag_score = atoi(val().c_str());
-        else if (a == "--k-score") o.p.kmer_thr = atoi(val().c_str());
+        else if (a == "--k-score") kScore = seqValue(val());
+        else if (a == "-s") sens = strtof(val().c_str(), nullptr);
         else if (a == "-e") o.p.eval_thr = atof(val().c_str());
         else if (a == "--min-aln-len") o.p.min_aln_len = atoi(val().c_str());
+        else if (a == "--min-length") o.minLen = atoi(val().c_str());
+        else if (a == "--max-length") o.maxLen = atoi(val().c_str());
+        else if (a == "--comp-bias-corr") o.p.comp_bias_corr = atoi(val().c_str());
+        else if (a == "--reverse-fragments") o.p.reverse_fragments = atoi(val().c_str());
+        else if (a == "--translation-table") o.p.translation_table = atoi(val().c_str());
         else if (a == "--masked-db") o.maskedDb = val();
         else if (a == "--metaeuk-eval") o.p.metaeuk_eval = atof(val().c_str());
         else if (a == "--metaeuk-tcov") o.p.tcov = atof(val().c_str());
@@ -137,9 +175,20 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--mask-prob") o.maskProb = atof(val().c_str());
         else if (a == "--text-stages") o.textStages = atoi(val().c_str());
         else if (a == "--batch-nt") o.batchNt = atoll(val().c_str());
-        else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }   // other reference flags are accepted and ignored
+        else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) {
+            bool known = false;
+            for (int k = 0; IGNORED_FLAGS[k] && !known; k++) if (a == IGNORED_FLAGS[k]) { val(); known = true; }
+            for (int k = 0; FIXED_FLAGS[k].name && !known; k++) if (a == FIXED_FLAGS[k].name) {
+                const std::string v = val(); bool ok = false;
+                for (const char *alt : FIXED_FLAGS[k].ok) if (alt && sameValue(v, alt)) ok = true;
+                if (!ok) DIE("%s %s: only the value `metaeuk predictexons` uses (%s) is implemented on the GPU path", a.c_str(), v.c_str(), FIXED_FLAGS[k].ok[0]);
+                known = true;
+            }
+            if (!known) DIE("unknown option %s", a.c_str());
+        }
         else pos.push_back(a);
     }
+    o.p.kmer_thr = kScore != 2147483647 ? kScore : mb200_kmer_threshold(sens);     // Prefiltering::getKmerThreshold (Prefiltering.cpp:1005-1011)
     return o;
 }
 
@@ -306,6 +355,7 @@ int main(int argc, char **argv) {
         writeDb(pos[2], 12, chainAll(ctx, m, total));   // DBTYPE_GENERIC_DB
         mb200_ctx_destroy(ctx);
     } else if (cmd == "gpupredictexons" && pos.size() == 3) {
+        o.p.min_aln_len = o.p.min_exon_aa;      // "align module should return alignments of at least a minimal exon length" (src/workflow/PredictExons.cpp:43-44)
         // contigs are the only input: ORF fragments are extracted and translated on the device, become the resident query batch
         // (no aa_6f / nucl_6f DBs, no host round trip), are searched, regrouped per contig and chained
         Session s; s.open(o, pos[1]); Db contigs = openDb(pos[0]);
@@ -316,7 +366,7 @@ int main(int argc, char **argv) {
         if (o.textStages) {
             // the same chain with the reference's text DBs between the stages (in memory), for parity checks of the binary hand-off
             uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
-            MB(mb200_extract_orfs(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
+            MB(mb200_extract_orfs(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), o.minLen, o.maxLen, 1, &n, &orfs, &na, &aa));
             Db hdr; hdr.dbtype = 12; char buf[96];
             for (uint64_t i = 0; i < n; i++) {          // in-memory nucl_6f_h (Orf::writeOrfHeader, Orf.cpp:440-457)
                 const mb200_orf &r = orfs[i]; const long long d = (long long)r.from - (long long)r.to;
@@ -339,7 +389,7 @@ int main(int argc, char **argv) {
             MB(mb200_target_keys_set(s.ctx, s.tdb.keys.data(), (uint32_t)s.tdb.keys.size()));
             if (o.batchNt > 0) MB(mb200_option_set(s.ctx, "predict_batch_nt", o.batchNt));
             std::vector<uint64_t> coff(order.size() + 1); const mb200_call *calls = nullptr; const mb200_pexon *ex = nullptr; uint64_t nEx = 0;
-            MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, coff.data(), &calls, &ex, &nEx));
+            MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), o.minLen, o.maxLen, coff.data(), &calls, &ex, &nEx));
             std::map<uint32_t, std::string> out; char line[512];
             for (size_t ci = 0; ci < order.size(); ci++) {
                 std::string e;
@@ -351,6 +401,7 @@ int main(int argc, char **argv) {
         }
     } else if (cmd == "gpupredictexons") {
         if (pos.size() != 5) DIE("gpupredictexons <contigsDB> <orfAaDB> <orfNuclDB> <targetDB> <predDB>   |   gpupredictexons <contigsDB> <targetDB> <predDB>");
+        o.p.min_aln_len = o.p.min_exon_aa;      // src/workflow/PredictExons.cpp:43-44
         Session s; s.open(o, pos[3]); Db contigs = openDb(pos[0]), qdb = openDb(pos[1]), hdr = openDb(pos[2] + "_h"); Seqs q = encodeDb(qdb, false);
         auto aln = searchAll(s, qdb, q);
         auto byc = byContig(contigs, hdr, aln);
@@ -428,9 +479,9 @@ int main(int argc, char **argv) {
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return contigs.keys[a] < contigs.keys[b]; });
         std::string nuc; std::vector<uint64_t> off(1, 0);
         for (size_t id : order) { const size_t n = contigs.len[id] >= 2 ? contigs.len[id] - 2 : 0; nuc.append(contigs.entry(id), n); off.push_back(nuc.size()); }
-        mb200_ctx *ctx; MB(mb200_ctx_create(o.device, &ctx));
+        mb200_ctx *ctx; MB(mb200_ctx_create(o.device, &ctx)); MB(mb200_params_set(ctx, &o.p));
         uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
-        MB(mb200_extract_orfs(ctx, nuc.data(), off.data(), (uint32_t)order.size(), 15, 32734, 1, &n, &orfs, &na, &aa));
+        MB(mb200_extract_orfs(ctx, nuc.data(), off.data(), (uint32_t)order.size(), o.minLen, o.maxLen, 1, &n, &orfs, &na, &aa));
         DbOut hdr(pos[1], 12), seq(pos[2], 0);   // DBTYPE_GENERIC_DB, DBTYPE_AMINO_ACIDS
         char buf[96];
         for (uint64_t i = 0; i < n; i++) {

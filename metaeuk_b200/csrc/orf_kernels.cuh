@@ -1,6 +1,7 @@
 // orf_kernels.cuh -- six-frame ORF fragments of nucleotide contigs and their translation, the step that feeds the
 // prefilter: what `extractorfs` + `translatenucs` do with the flags `metaeuk predictexons` passes
 //   --min-length 15 --max-length 32734 --orf-start-mode 1 (ANY_TO_STOP) --contig-start-mode 2 --contig-end-mode 2 --translation-table 1
+// (--min-length, --max-length and --translation-table are parameters; the other three are fixed)
 // Reference behaviour reproduced (not its code):
 //   Orf::setSequence / findForward     reference/lib/mmseqs/src/commons/Orf.cpp:125-157,230-349   (stop-to-stop fragments per frame,
 //                                      first fragment of a frame has an incomplete start, a fragment cut by the contig end an incomplete end)
@@ -16,6 +17,28 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define MB_ORF_HD __host__ __device__ __forceinline__
+#else
+#define MB_ORF_HD inline
+#endif
+
+// Stop codons of the genetic code in use (--translation-table; Orf::Orf takes them from the table's amino-acid string, Orf.cpp:54-64) as a 64-bit set.
+// The reference compares the upper-cased letters with the codon strings (Orf.cpp:266-269, isInCodons :206-228), so only plain A/C/G/T codons can match.
+// Letter code m(u) = (u >> 1) & 3 for u in {A, C, G, T}: A 0, C 1, T 2, G 3; bit 16 m(u0) + 4 m(u1) + m(u2) of the set.
+MB_ORF_HD bool orf_is_acgt(int u) { const unsigned d = (unsigned)(u - 'A'); return d < 20u && ((0x80045u >> d) & 1u); }   // bits 0 (A), 2 (C), 6 (G), 19 (T)
+MB_ORF_HD unsigned orf_codon_bit(int u0, int u1, int u2) { return (((unsigned)u0 >> 1) & 3u) * 16u + (((unsigned)u1 >> 1) & 3u) * 4u + (((unsigned)u2 >> 1) & 3u); }
+MB_ORF_HD bool orf_is_stop(int u0, int u1, int u2, unsigned long long stopSet) {   // u* = upper-cased letters (c & ~0x20)
+    return orf_is_acgt(u0) && orf_is_acgt(u1) && orf_is_acgt(u2) && ((stopSet >> orf_codon_bit(u0, u1, u2)) & 1ull);
+}
+// the set from an NCBI amino-acid string in TCAG order (64 letters, '*' = stop)
+inline unsigned long long orf_stop_set(const char *ncbieaa) {
+    const char L[4] = {'T', 'C', 'A', 'G'}; unsigned long long m = 0;
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4; c++) if (ncbieaa[16 * a + 4 * b + c] == '*') m |= 1ull << orf_codon_bit(L[a], L[b], L[c]);
+    return m;
+}
+
+#if defined(__CUDACC__)    // everything below is device code (the helpers above also compile for the host: tests/emu checks them exhaustively)
 #define MB_ORF_THREADS 256
 #define MB_ORF_PER_THREAD 24                      // 8 codons of each frame
 #define MB_ORF_TILE (MB_ORF_THREADS * MB_ORF_PER_THREAD)
@@ -93,7 +116,7 @@ __device__ __forceinline__ void orf_block_scan_max3(uint32_t (&v)[3], uint32_t *
 // EMIT = false: counts[(contig, strand)] = (#fragments, #residues).  EMIT = true: writes the records at recBase / aaBase.
 template <bool EMIT>
 __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char *__restrict__ nuc, const uint64_t *__restrict__ off, uint32_t nContigs,
-                                                             const MbOrfTables *__restrict__ tab, uint32_t minLen, uint32_t maxLen,
+                                                             const MbOrfTables *__restrict__ tab, uint32_t minLen, uint32_t maxLen, unsigned long long stopSet,
                                                              uint32_t *__restrict__ cntOut, uint64_t *__restrict__ aaOut,
                                                              const uint64_t *__restrict__ recBase, const uint64_t *__restrict__ aaBase, MbOrfRec *__restrict__ recs) {
     __shared__ unsigned char tile[MB_ORF_TILE + 8];
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char
                 const int c0 = tile[lb + j], c1 = tile[lb + j + 1], c2 = tile[lb + j + 2];
                 const bool complete = p + 2 < L;            // (127 never occurs inside a contig: createdb stores printable characters)
                 const int u0 = c0 & ~0x20, u1 = c1 & ~0x20, u2 = c2 & ~0x20;
-                const bool stop = complete && u0 == 'T' && ((u1 == 'A' && (u2 == 'A' || u2 == 'G')) || (u1 == 'G' && u2 == 'A'));
+                const bool stop = complete && orf_is_stop(u0, u1, u2, stopSet);
                 const bool isLast = complete && (p + 5 >= L);
                 if (stop) stopMask |= 1u << j;
                 if (stop || isLast) { termMask |= 1u << j; myLast[j % 3] = p + 1; }
@@ -165,7 +188,7 @@ __global__ void __launch_bounds__(MB_ORF_THREADS) k_orf_scan(const unsigned char
 
 // one warp per fragment, lanes over its residues: codon -> amino acid letter (case preserved) and prefilter alphabet code
 __global__ void __launch_bounds__(256) k_orf_translate(const unsigned char *__restrict__ nuc, const uint64_t *__restrict__ off, const MbOrfTables *__restrict__ tab,
-                                                       const MbOrfRec *__restrict__ recs, uint64_t nRecs, char *__restrict__ aa, uint8_t *__restrict__ codes) {
+                                                       const MbOrfRec *__restrict__ recs, uint64_t nRecs, int reversed, char *__restrict__ aa, uint8_t *__restrict__ codes) {
     __shared__ char aaOf[4096];
     __shared__ unsigned char comp[256], base[256], a2n[256];
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) aaOf[i] = tab->aaOf[i];
@@ -183,7 +206,9 @@ __global__ void __launch_bounds__(256) k_orf_translate(const unsigned char *__re
             char res = aaOf[256 * base[c0 & 255] + 16 * base[c1 & 255] + base[c2 & 255]];
             const bool lower = (c0 >= 'a' && c0 <= 'z') || (c1 >= 'a' && c1 <= 'z') || (c2 >= 'a' && c2 <= 'z');
             if (lower && res >= 'A' && res <= 'Z') res = (char)(res + 32);
-            aa[r.aaOff + k] = res; codes[r.aaOff + k] = a2n[(unsigned char)res];
+            const uint64_t o = r.aaOff + (reversed ? r.aaLen - 1u - k : k);   // --reverse-fragments: the fragment back to front (reverseseq)
+            aa[o] = res; codes[o] = a2n[(unsigned char)res];
         }
     }
 }
+#endif  // __CUDACC__

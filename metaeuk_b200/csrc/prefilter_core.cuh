@@ -279,8 +279,10 @@ MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, SH
             for (int u = 0; u < 4; u++) {
                 const uint32_t n = cta_append_slot(&sh->cnt[7], nz[u]);
                 if (nz[u]) {
-                    const uint64_t w = ((uint64_t)pv[u] << 44) | ((uint64_t)(k0 + u) << 26) | km[u];
-                    if (n < SH::Cfg::SM_NZ) sh->sNz[n] = w; else W.B[n - SH::Cfg::SM_NZ] = w;
+                    const uint64_t w = ((uint64_t)pv[u] << 47) | ((uint64_t)(k0 + u) << 26) | km[u];   // window[17] | k[21] | k-mer[26]
+                    if (n < SH::Cfg::SM_NZ) sh->sNz[n] = w;
+                    else if (n - SH::Cfg::SM_NZ < T.capM) W.B[n - SH::Cfg::SM_NZ] = w;
+                    else sh->cnt[3] = 1u;                                                               // list capacity exhausted (checked by the caller)
                 }
             }
         }
@@ -312,6 +314,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
     CTA_SYNC();
     const uint32_t nNz = sh->cnt[7];
     MB_PHASE(3);
+    if (sh->cnt[3]) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }   // more non-empty k-mers than the list holds
 
     // ---- P4 gather the index entries of the non-empty lists (thread per list, 4 in flight); mark slot occupancy (0 / 1 / >=2 hits).
     //      Output slots are reserved with one shared-memory atomic per warp and round.
@@ -360,7 +363,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
         for (int u = 0; u < 4; u++) { e0[u].x = 0; e0[u].y = 0; if (len[u]) e0[u] = T.entries[lo[u]]; }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t pp = (uint32_t)(wv[u] >> 44), kk = (uint32_t)(wv[u] >> 26) & 0x3FFFFu;
+            const uint32_t pp = (uint32_t)(wv[u] >> 47), kk = (uint32_t)(wv[u] >> 26) & 0x1FFFFFu;
             for (uint32_t x = 0; x < len[u]; x++) {
                 const uint2 en = x ? T.entries[(size_t)lo[u] + x] : e0[u];
                 const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
@@ -460,6 +463,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
     CTA_SYNC();
     const uint32_t D = sh->cnt[1];
     MB_PHASE(6);
+    if (D > (1u << 21)) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }   // candidate indices are 21-bit fields of the sort keys below
     // ---- P8/P9 ungapped diagonal scores
     mb_sort_list(W.C, D, sh);
     uint32_t myCells = 0;

@@ -27,7 +27,8 @@ class Params(C.Structure):
                 ("min_intron", C.c_int32), ("max_intron", C.c_int32), ("min_exon_aa", C.c_int32), ("max_overlap", C.c_int32),
                 ("set_gap_open", C.c_int32), ("set_gap_extend", C.c_int32), ("max_exon_sets", C.c_int32), ("pad1", C.c_int32),
                 ("tcov", C.c_double), ("metaeuk_eval", C.c_double),
-                ("cap_items_log2", C.c_int32), ("cap_kmers_log2", C.c_int32), ("cap_hits_log2", C.c_int32), ("pad2", C.c_int32)]
+                ("cap_items_log2", C.c_int32), ("cap_kmers_log2", C.c_int32), ("cap_hits_log2", C.c_int32), ("pad2", C.c_int32),
+                ("comp_bias_corr", C.c_int32), ("reverse_fragments", C.c_int32), ("translation_table", C.c_int32), ("pad3", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -71,6 +71,52 @@ def make_context(tdb, device=0, **params):
     return ctx
 
 
+def kmer_threshold(sensitivity):
+    """`-s` -> k-mer similarity threshold (Prefiltering::getKmerThreshold, sequence search, k = 6); -s 4 -> 127"""
+    import ctypes as C
+    from .lib import load_library
+    L = load_library()
+    L.mb200_kmer_threshold.argtypes = [C.c_float]
+    return int(L.mb200_kmer_threshold(float(sensitivity)))
+
+
+_FLAG_PARAMS = {"--max-seqs": ("max_res_list_len", int), "--min-ungapped-score": ("min_diag_score", int), "-e": ("eval_thr", float), "--comp-bias-corr": ("comp_bias_corr", int),
+                "--reverse-fragments": ("reverse_fragments", int), "--translation-table": ("translation_table", int), "--metaeuk-eval": ("metaeuk_eval", float),
+                "--metaeuk-tcov": ("tcov", float), "--max-intron": ("max_intron", int), "--min-intron": ("min_intron", int), "--min-exon-aa": ("min_exon_aa", int),
+                "--max-overlap": ("max_overlap", int), "--max-exon-sets": ("max_exon_sets", int), "--set-gap-open": ("set_gap_open", int), "--set-gap-extend": ("set_gap_extend", int)}
+
+
+def predictexons_flags(flags):
+    """The flags of a `metaeuk predictexons` command line that change what this path computes -> (context parameters for make_context, ORF options for
+    extractorfs / predictexons_contigs, mask 0|1).  Same rules as the C++ driver (mb200_cli.cpp:parseOpts): -s or --k-score give the k-mer threshold, the align
+    stage's minimal alignment length follows --min-exon-aa (src/workflow/PredictExons.cpp:43-44); a flag this path does not implement raises."""
+    w = flags.split() if isinstance(flags, str) else list(flags)
+    if len(w) % 2:
+        raise ValueError("flags come in (name, value) pairs: %r" % (flags,))
+    par, orf, mask, sens, kscore = {}, {}, 1, 4.0, None
+    for name, val in zip(w[0::2], w[1::2]):
+        if name in _FLAG_PARAMS:
+            par[_FLAG_PARAMS[name][0]] = _FLAG_PARAMS[name][1](val)
+        elif name == "-s":
+            sens = float(val)
+        elif name == "--k-score":
+            k = int(val.split("seq:")[1].split(",")[0]) if "seq:" in val else int(val)
+            kscore = None if k == 2147483647 else k
+        elif name == "--min-length":
+            orf["min_len"] = int(val)
+        elif name == "--max-length":
+            orf["max_len"] = int(val)
+        elif name == "--mask":
+            mask = int(val)
+        elif name in ("--threads", "-v", "--compressed", "--remove-tmp-files"):
+            pass
+        else:
+            raise ValueError("flag %s is not implemented on the GPU path" % name)
+    par["kmer_thr"] = kscore if kscore is not None else kmer_threshold(sens)
+    par["min_aln_len"] = par.get("min_exon_aa", 11)
+    return par, orf, mask
+
+
 # ---- formatting (the reference's own rules) -----------------------------------------------------
 def fmt_seqid(x):
     """Util::fastSeqIdToBuffer + Matcher::resultToBuffer's tab overwrite: 1.0 -> '1.00' (Util.cpp:222-251, Matcher.cpp:286-287)"""

@@ -12,6 +12,10 @@
 #include "../../metaeuk_b200/csrc/chain_core.cuh"
 #include "../../metaeuk_b200/csrc/host_join.h"
 #include "../../metaeuk_b200/csrc/host_indexdb.h"
+#include "../../metaeuk_b200/csrc/orf_kernels.cuh"    // (host-callable parts only: the stop-codon set of a genetic code)
+
+static uint32_t g_capI = 1u << 17, g_capK = 1u << 18, g_capMAlloc = 1u << 19, g_capM = 1u << 19;   // the library's default per-CTA capacities (mb200.cu: ctx_alloc_scratch)
+static int g_compBiasCorr = 1;   // --comp-bias-corr: the product zeroes the per-residue arrays instead of running k_prep (mb200.cu: queries_install)
 
 template <class SH>
 static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ,
@@ -27,10 +31,10 @@ static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t
     T.kmerBits = bits.data();
     T.sim3 = sim3.data(); T.cnt3 = cnt3.data(); T.offsets = idx.offsets.data(); T.entries = (const uint2 *)idx.entries.data();
     T.tseq = masked; T.toff = toff; T.nT = nT; T.kmerThr = kmerThr; T.maxHits = maxHits; T.minDiag = minDiag; T.binMask = (uint32_t)binSize - 1;
-    T.capP = 32768; T.capI = 1u << 17; T.capK = 1u << 18; T.capM = 1u << 19;
+    T.capP = 32768; T.capI = g_capI; T.capK = g_capK; T.capM = g_capM;
     std::vector<uint32_t> itemOff(T.capP + 1), kmerOff(T.capI + 1), itemInfo(T.capI);
     std::vector<int16_t> wThr(T.capP); std::vector<uint16_t> wI0(T.capP), wI1(T.capP);
-    std::vector<uint64_t> A(T.capM), B(T.capM), C(T.capM); std::vector<int32_t> S(T.capM);
+    std::vector<uint64_t> A(g_capMAlloc), B(g_capMAlloc), C(g_capMAlloc); std::vector<int32_t> S(g_capMAlloc);
     MbPrefScratch W; W.itemOff = itemOff.data(); W.wThr = wThr.data(); W.wI0 = wI0.data(); W.wI1 = wI1.data(); W.kmerOff = kmerOff.data();
     W.itemInfo = itemInfo.data(); W.A = A.data(); W.B = B.data(); W.C = C.data(); W.S = S.data();
     SH *sh = new SH();
@@ -40,7 +44,7 @@ static int emu_prefilter_t(const uint8_t *masked, const uint64_t *toff, uint32_t
     for (uint32_t i = 0; i < nQ; i++) {
         const uint8_t *qs = q + qOff[i]; const uint32_t L = (uint32_t)(qOff[i + 1] - qOff[i]);
         bias.resize(L + 1); corr.resize(L + 1);
-        for (uint32_t p = 0; p < L; p++) { bias[p] = mb_comp_bias_at(m.seed, m.seedPBack, qs, (int)L, (int)p); corr[p] = mb_round_bias_quarter(bias[p]); }
+        for (uint32_t p = 0; p < L; p++) { bias[p] = g_compBiasCorr ? mb_comp_bias_at(m.seed, m.seedPBack, qs, (int)L, (int)p) : 0.0f; corr[p] = g_compBiasCorr ? mb_round_bias_quarter(bias[p]) : 0; }
         mb_prefilter_query(T, W, sh, qs, bias.data(), corr.data(), L, out + (size_t)i * maxHits, outCount + i, outStatus + i, &st);
     }
     delete sh;
@@ -85,6 +89,31 @@ int emu_index(const uint8_t *masked, const uint64_t *off, uint32_t nT, int kmerT
 
 // cfg 1 = dense, 2 = sparse (the two device configurations), 3 = a deliberately tiny one that pushes every list through its
 // global-memory fallback (items, non-empty k-mers, hash table -> sort path, sorts in global memory)
+// k_orf_scan's stop test (orf_is_stop over the 64-bit set of the genetic code) against the reference's rule -- the upper-cased three letters equal one of the
+// table's stop codons (Orf.cpp:54-64,206-228,266-269) -- for every byte triple and every genetic code; returns the number of disagreements (-1: unknown table id)
+long long emu_orf_stop_check(void) {
+    long long bad = 0; int tables = 0;
+    for (int t = 0; t < 40; t++) {
+        const char *code = mb200::genetic_code(t);
+        if (!code) continue;
+        tables++;
+        const unsigned long long set = orf_stop_set(code);
+        const char L[4] = {'T', 'C', 'A', 'G'};
+        for (int a = 0; a < 256; a++) for (int b = 0; b < 256; b++) for (int c = 0; c < 256; c++) {
+            const int u0 = a & ~0x20, u1 = b & ~0x20, u2 = c & ~0x20;
+            bool want = false;
+            for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) for (int z = 0; z < 4; z++)
+                if (code[16 * x + 4 * y + z] == '*' && u0 == L[x] && u1 == L[y] && u2 == L[z]) want = true;
+            if (orf_is_stop(u0, u1, u2, set) != want) bad++;
+        }
+    }
+    return tables == 25 ? bad : -1;
+}
+void emu_set_comp_bias_corr(int on) { g_compBiasCorr = on; }
+// capacities of the work lists: (2^17, 2^18, 2^19, 2^19) = the library's first pass; its second pass for overflowed queries uses
+// (2^22, 2^21, power-of-two allocation >= 2 max(10^6, #targets), that bound - 1) -- see mb200_prefilter_resident
+void emu_set_caps(uint32_t capI, uint32_t capK, uint32_t capMAlloc, uint32_t capM) { g_capI = capI; g_capK = capK; g_capMAlloc = capMAlloc; g_capM = capM; }
+
 int emu_prefilter(const uint8_t *masked, const uint64_t *toff, uint32_t nT, const uint8_t *q, const uint64_t *qOff, uint32_t nQ, int kmerThr, int maxHits,
                   int minDiag, int binSize, MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, unsigned long long *statsOut, int cfg) {
     if (cfg == 2) return emu_prefilter_t<MbPrefSharedT<MbPrefCfgSparse>>(masked, toff, nT, q, qOff, nQ, kmerThr, maxHits, minDiag, binSize, out, outCount, outStatus, statsOut);

@@ -78,3 +78,51 @@ def test_gpucreateindex_masks_like_the_reference_by_default(exe, emu, tmp_path):
     y, err = _open_indexdb(emu, d + "/unmasked.idx")
     u, _ = reflib.pack([s for _, s in c["targets"]])
     assert (y["masked"] == u).all() and y["meta"][4] == 0 and y["n_entries"] > x["n_entries"]
+
+
+def test_sensitivity_to_kmer_threshold_matches_the_reference_log():
+    """`-s` -> k-mer similarity threshold (mb200_kmer_threshold = Prefiltering::getKmerThreshold, k = 6): the values the reference logged for the
+    flags fixture and the whole range of sensitivities in steps of 0.1 against the restated float/double expression"""
+    L = mlib.load_library()
+    L.mb200_kmer_threshold.argtypes = [C.c_float]
+    v = reflib.load_case("flags")["variants"]
+    assert L.mb200_kmer_threshold(4.0) == v["default"]["kmer_thr"] == 127
+    assert L.mb200_kmer_threshold(6.0) == v["s6"]["kmer_thr"] and L.mb200_kmer_threshold(1.0) == v["s1"]["kmer_thr"] and L.mb200_kmer_threshold(7.5) == v["s7.5"]["kmer_thr"]
+    for s in np.arange(1.0, 9.05, 0.1):
+        assert L.mb200_kmer_threshold(float(s)) == reflib.sensitivity_to_kmer_thr(float(s)), s
+
+
+def test_cli_rejects_flags_it_would_otherwise_silently_ignore(exe, emu, tmp_path):  # noqa: F811
+    """a reference flag that changes results but is not implemented must stop the run (unless it carries the value `metaeuk predictexons` passes
+    itself); flags that never change results are accepted; unknown flags are errors; -s reaches the index builder"""
+    c = reflib.load_case("frag_small")
+    d = str(tmp_path)
+    reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"][:50]], 0)
+    base = [exe, "gpucreateindex", d + "/proteins"]
+    for bad in (["--alignment-mode", "3"], ["--orf-start-mode", "0"], ["--min-seq-id", "0.3"], ["-c", "0.8"], ["--comp-bias-corr-scale", "0.5"], ["--gap-open", "10"],
+                ["--no-such-flag", "1"], ["--exhaustive-search", "1"], ["--sub-mat", "VTML40.out"]):
+        r = subprocess.run(base + [d + "/bad.idx"] + bad, capture_output=True, text=True)
+        assert r.returncode != 0 and bad[0] in r.stderr and not os.path.exists(d + "/bad.idx"), bad
+    ok = ["--threads", "8", "-v", "3", "--compressed", "0", "--alignment-mode", "2", "--gap-open", "aa:11,nucl:5", "--gap-extend", "aa:1,nucl:2", "--sub-mat",
+          "aa:blosum62.out,nucl:nucleotide.out", "--seed-sub-mat", "aa:VTML80.out,nucl:nucleotide.out", "-k", "0", "--split", "1", "--orf-start-mode", "1",
+          "--k-score", "seq:2147483647,prof:2147483647", "--comp-bias-corr-scale", "1", "--max-seq-len", "65535", "--forward-frames", "1,2,3"]
+    subprocess.check_call(base + [d + "/s4.idx"] + ok)
+    subprocess.check_call(base + [d + "/s6.idx", "-s", "6"])
+    subprocess.check_call(base + [d + "/k109.idx", "--k-score", "seq:109,prof:109", "-s", "2"])
+    a, _ = _open_indexdb(emu, d + "/s4.idx"); b, _ = _open_indexdb(emu, d + "/s6.idx"); k, _ = _open_indexdb(emu, d + "/k109.idx")
+    assert a["meta"][6] == 127 and b["meta"][6] == 109 and k["meta"][6] == 109      # (the k-mer threshold is part of the index meta data)
+
+
+def test_predictexons_flags_follow_the_drivers_rules():
+    """modules.predictexons_flags (Python mirror of the driver's option rules) on the flag sets of the reference fixture"""
+    from metaeuk_b200 import modules as M
+    c = reflib.load_case("flags")
+    for name, v in c["variants"].items():
+        par, orf, mask = M.predictexons_flags(v["flags"])
+        assert par["kmer_thr"] == v["kmer_thr"], name
+        assert mask == (0 if name == "nomask" else 1)
+    par, orf, _ = M.predictexons_flags("--min-exon-aa 20 --min-length 30 --threads 4")
+    assert par["min_aln_len"] == 20 and par["min_exon_aa"] == 20 and orf == {"min_len": 30}
+    assert M.predictexons_flags("-s 2 --k-score seq:109,prof:109")[0]["kmer_thr"] == 109
+    with pytest.raises(ValueError):
+        M.predictexons_flags("--orf-start-mode 0")

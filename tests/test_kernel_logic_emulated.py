@@ -86,6 +86,62 @@ def test_prefilter_kernel_logic_matches_reference(emu, name, cfg):
     assert bad == 0
 
 
+@pytest.mark.parametrize("cfg", [1, 2, 3], ids=["dense", "sparse", "tiny-all-fallbacks"])
+@pytest.mark.parametrize("variant", ["s6", "s1", "s7.5", "kscore", "maxseqs10", "minungapped", "nocomp", "nomask", "reverse", "table6"])
+def test_prefilter_kernel_logic_under_non_default_flags(emu, variant, cfg):
+    """the prefilter kernel logic under the flag sets of tests/golden/flags.json.gz that reach it (k-mer thresholds 96..154, list length 10, minimal ungapped
+    score 30, composition bias off, unmasked targets, reversed fragments, genetic code 6 fragments) against the oracle's hit lists -- the oracle itself
+    is pinned on the reference's search_res and calls of every variant (test_predictexons_flags_match_reference)"""
+    c = reflib.load_case("flags")
+    v = c["variants"][variant]
+    par, _ = reflib.FLAG_VARIANTS[variant]
+    par = dict(par); nomask = par.pop("nomask", False); comp = par.pop("comp_bias_corr", True)
+    keys = [k for k, _ in c["targets"]]; unmasked = [s for _, s in c["targets"]]
+    masked = unmasked if nomask else c["masked_targets"]
+    qsrc = v if "queries" in v else c["variants"]["default"]
+    queries = [(s[::-1] if v.get("reversed") else s) for _, s in qsrc["queries"]]
+    o = reflib.Oracle()
+    o.set_params(**par); o.set_comp_bias_corr(comp); o.set_targets(masked, unmasked)
+    want, _ = o.prefilter(queries)
+    o.close()
+    m, toff = reflib.pack(masked); q, qoff = reflib.pack(queries)
+    nQ = len(queries); maxres = par.get("maxResListLen", 300)
+    hits = (PrefHit * (nQ * maxres))()
+    cnt = np.zeros(nQ, np.uint32); st = np.zeros(nQ, np.uint32); stats = np.zeros(6, np.uint64)
+    p = reflib._p
+    emu.emu_set_comp_bias_corr(int(comp))
+    try:
+        rc = emu.emu_prefilter(p(m, C.c_uint8), p(toff, C.c_uint64), len(keys), p(q, C.c_uint8), p(qoff, C.c_uint64), nQ, par.get("kmerThr", 127), maxres,
+                               par.get("minDiagScore", 15), 2, hits, p(cnt, C.c_uint32), p(st, C.c_uint32), p(stats, C.c_uint64), cfg)
+        assert rc == 0
+        got = [[(hits[i * maxres + j].seqId, hits[i * maxres + j].score, hits[i * maxres + j].diag) for j in range(cnt[i])] for i in range(nQ)]
+        again = [i for i in range(nQ) if st[i] == 2]          # MB_ST_OVERFLOW with the first pass' capacities: the library's second pass (larger lists)
+        assert (variant in ("s6", "s7.5")) == bool(again) and all(s in (0, 2) for s in st)
+        if again:
+            emu.emu_set_caps(1 << 22, 1 << 21, 1 << 21, 2 * 1000000 - 1)
+            q2, qoff2 = reflib.pack([queries[i] for i in again])
+            n2 = len(again); cnt2 = np.zeros(n2, np.uint32); st2 = np.zeros(n2, np.uint32)
+            hits2 = (PrefHit * (n2 * maxres))()
+            rc = emu.emu_prefilter(p(m, C.c_uint8), p(toff, C.c_uint64), len(keys), p(q2, C.c_uint8), p(qoff2, C.c_uint64), n2, par.get("kmerThr", 127), maxres,
+                                   par.get("minDiagScore", 15), 2, hits2, p(cnt2, C.c_uint32), p(st2, C.c_uint32), p(stats, C.c_uint64), cfg)
+            assert rc == 0 and (st2 == 0).all()
+            for x, i in enumerate(again):
+                got[i] = [(hits2[x * maxres + j].seqId, hits2[x * maxres + j].score, hits2[x * maxres + j].diag) for j in range(cnt2[x])]
+    finally:
+        emu.emu_set_comp_bias_corr(1)
+        emu.emu_set_caps(1 << 17, 1 << 18, 1 << 19, 1 << 19)
+    assert sum(len(w) for w in want) > (5 if variant == "reverse" else 50)
+    for i in range(nQ):
+        assert got[i] == [tuple(h) for h in want[i]], (variant, i, i in again)
+
+
+def test_orf_stop_codon_sets_of_all_genetic_codes(emu):
+    """the ORF scan kernel's stop test (a 64-bit codon set per genetic code, orf_kernels.cuh) agrees with the reference's letter comparison for all
+    256^3 byte triples under each of the 25 genetic codes the reference lists"""
+    emu.emu_orf_stop_check.restype = C.c_longlong
+    assert emu.emu_orf_stop_check() == 0
+
+
 def test_reduceredundancy_kernel_logic_matches_reference(emu):
     """reduce_core.cuh (one contig per thread on the device) compiled for the host: clustering, overlap exclusion and both output orders"""
     c = reflib.load_case("redundancy_family")
