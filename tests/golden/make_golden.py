@@ -62,11 +62,12 @@ DP_FLAGS = ("--metaeuk-eval 0.001 --metaeuk-tcov 0.5 --max-intron 10000 --min-in
             "--threads {thr} --compressed 0 -v 3")
 
 
-def run(cmd, log):
+def run(cmd, log, quiet=False):
     r = subprocess.run(cmd, shell=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append("$ " + cmd + "\n" + r.stdout)
     if r.returncode != 0:
-        sys.stderr.write(r.stdout)
+        if not quiet:
+            sys.stderr.write(r.stdout)
         raise SystemExit("reference command failed: " + cmd)
     return r.stdout
 
