@@ -135,6 +135,36 @@ def test_prefilter_kernel_logic_under_non_default_flags(emu, variant, cfg):
         assert got[i] == [tuple(h) for h in want[i]], (variant, i, i in again)
 
 
+@pytest.mark.parametrize("cfg", [1, 2], ids=["dense", "sparse"])
+def test_very_long_queries_take_the_second_pass(emu, cfg):
+    """fragments of 5 000 and 14 000 residues (a stop-free frame may reach 32 734 codons) overflow the first pass' per-CTA work lists at the default sensitivity;
+    with the capacities of the library's second pass the kernel logic returns the oracle's hit lists"""
+    import random
+    rng = random.Random(5)
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    W = [7.8, 1.9, 5.4, 6.3, 3.9, 7.4, 2.3, 5.1, 5.7, 9.0, 2.2, 4.5, 5.2, 4.3, 5.1, 7.1, 5.8, 6.4, 1.3, 3.2]      # Robinson-Robinson background (SURVEY.md 8d)
+    prots = ["".join(rng.choices(AA, weights=W, k=max(30, int(rng.gauss(330, 120))))) for _ in range(1500)]
+    big = "".join(rng.choice(AA) if rng.random() < 0.15 else ch for ch in "".join(rng.sample(prots, 50)))
+    queries = [big[:5000], big[:14000]]
+    o = reflib.Oracle(); o.set_params(); o.set_targets(prots, prots)
+    want, _ = o.prefilter(queries)
+    o.close()
+    m, toff = reflib.pack(prots); q, qoff = reflib.pack(queries)
+    p = reflib._p
+    res = {}
+    try:
+        for name, caps in (("first", (1 << 17, 1 << 18, 1 << 19, 1 << 19)), ("second", (1 << 22, 1 << 21, 1 << 21, 2 * 1000000 - 1))):
+            emu.emu_set_caps(*caps)
+            hits = (PrefHit * (2 * 300))(); cnt = np.zeros(2, np.uint32); st = np.zeros(2, np.uint32); stats = np.zeros(6, np.uint64)
+            assert emu.emu_prefilter(p(m, C.c_uint8), p(toff, C.c_uint64), len(prots), p(q, C.c_uint8), p(qoff, C.c_uint64), 2, 127, 300, 15, 2,
+                                     hits, p(cnt, C.c_uint32), p(st, C.c_uint32), p(stats, C.c_uint64), cfg) == 0
+            res[name] = (list(st), [[(hits[i * 300 + j].seqId, hits[i * 300 + j].score, hits[i * 300 + j].diag) for j in range(cnt[i])] for i in range(2)])
+    finally:
+        emu.emu_set_caps(1 << 17, 1 << 18, 1 << 19, 1 << 19)
+    assert res["first"][0] == [2, 2]                       # MB_ST_OVERFLOW, nothing returned
+    assert res["second"][0] == [0, 0] and res["second"][1] == [[tuple(h) for h in w] for w in want] and min(len(w) for w in want) > 20
+
+
 def test_orf_stop_codon_sets_of_all_genetic_codes(emu):
     """the ORF scan kernel's stop test (a 64-bit codon set per genetic code, orf_kernels.cuh) agrees with the reference's letter comparison for all
     256^3 byte triples under each of the 25 genetic codes the reference lists"""
