@@ -149,6 +149,11 @@ int mb200_index_commit(mb200_ctx *ctx);
  * Host only (no GPU, no context): unmasked / masked are numeric residue codes with the same offsets off[n_targets+1]; masked letters become X (20).
  * simd_width 4 reproduces the summation order of the reference's AVX2 build, 2 that of its SSE4.1 / NEON build (0 = 4). */
 int mb200_mask_targets(const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets, double mask_prob, int simd_width, uint8_t *masked, uint64_t *n_masked);
+/* the same with every switch of Masker::maskSequence: mask_tantan = --mask, mask_n_repeat = --mask-n-repeat (runs of more than that many equal letters, 0 = off;
+ * Masker::maskRepeats, Masker.cpp:83-116, including its blind spot for a run of A at the start of a sequence), lower_case = --mask-lower-case 1: one byte per
+ * residue, != 0 where the DB holds a lower-case letter (NULL = off).  n_masked = the reference's "Masked residues" count. */
+int mb200_mask_targets_ex(const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets, int mask_tantan, double mask_prob, int simd_width,
+                          const uint8_t *lower_case, int mask_n_repeat, uint8_t *masked, uint64_t *n_masked);
 
 /* persisted index: an MMseqs index database in the layout `createindex` / `indexdb` write (<path>, <path>.index, <path>.dbtype;
  * entries keyed as in M/src/prefiltering/PrefilteringIndexReader.cpp:10-34).  mb200_index_load mmaps such a DB -- written by

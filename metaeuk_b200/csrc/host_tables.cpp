@@ -122,6 +122,31 @@ uint64_t mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, doub
     return masked;
 }
 
+// Masker::maskSequence with all of its switches (Masker.cpp:14-58): tantan (--mask), then runs of more than `maskNRepeat` equal letters (--mask-n-repeat,
+// Masker::maskRepeats :83-116, applied to the codes tantan left behind, so a run of X counts too), then letters that were lower case in the DB
+// (--mask-lower-case).  The reference's run scan starts with previousChar = 0 and startOfRepeat = -1: code 0 is 'A', so a run of A at the very start of a
+// sequence is never masked (its masking loop starts at (unsigned) -1) and is counted one letter longer than it is -- reproduced here.  Returns what the
+// reference adds up as "Masked residues" (a letter masked by two rules counts twice).
+uint64_t mask_targets_ex(const uint8_t *res, const uint64_t *off, uint32_t nT, bool tantan, double maskProb, int simdWidth, const uint8_t *lowerCase, int maskNRepeat, uint8_t *out) {
+    const uint8_t X = (uint8_t)(AL - 1);
+    uint64_t masked = tantan ? mask_targets(res, off, nT, maskProb, out, simdWidth) : 0;
+    if (!tantan) memcpy(out + off[0], res + off[0], off[nT] - off[0]);
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : masked)
+    for (uint32_t t = 0; t < nT; t++) {
+        uint8_t *s = out + off[t]; const uint32_t n = (uint32_t)(off[t + 1] - off[t]);
+        if (maskNRepeat > 0) {
+            uint32_t count = 0; long start = -1; uint8_t prev = 0;
+            for (uint32_t pos = 0; pos <= n; pos++) {
+                if (pos < n && s[pos] == prev) { count++; continue; }
+                if (count > (uint32_t)maskNRepeat && start >= 0) for (uint32_t i = (uint32_t)start; i < pos; i++) { s[i] = X; masked++; }
+                if (pos < n) { count = 1; start = (long)pos; prev = s[pos]; }
+            }
+        }
+        if (lowerCase) for (uint32_t i = 0; i < n; i++) if (lowerCase[off[t] + i]) { s[i] = X; masked++; }
+    }
+    return masked;
+}
+
 // ---- 3-mer similarity table -----------------------------------------------------------------------
 // Stable descending order w.r.t. the cartesian enumeration (first letter outermost) == a counting sort over the
 // (small) score range that visits neighbours in cartesian order.

@@ -45,6 +45,9 @@ int import_index(const uint64_t *offsets, const uint8_t *entries6, uint64_t nEnt
 // res / out: numeric residue codes, off[nT + 1].  simdWidth = number of doubles the reference build's tantan loops add side by side (4 = AVX2 build,
 // 2 = SSE4.1 / NEON build): it fixes the summation order, so the double-precision sums -- and the result -- are those of that build.  Returns #masked.
 uint64_t mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, double maskProb, uint8_t *out, int simdWidth = 4);
+// all switches of Masker::maskSequence: tantan on/off (--mask), runs of more than maskNRepeat equal letters (--mask-n-repeat, 0 = off), letters that were
+// lower case in the DB (--mask-lower-case; lowerCase[i] != 0 per residue, or NULL)
+uint64_t mask_targets_ex(const uint8_t *res, const uint64_t *off, uint32_t nT, bool tantan, double maskProb, int simdWidth, const uint8_t *lowerCase, int maskNRepeat, uint8_t *out);
 
 // Gumbel/finite-size e-value model of the reference for BLOSUM62 gap 11/1
 // (reference/lib/mmseqs/src/alignment/EvalueComputation.h:18-40,56-69 -> Sls::AlignmentEvaluer::area)

@@ -420,6 +420,17 @@ int mb200_mask_targets(const uint8_t *unmasked, const uint64_t *off, uint32_t nT
     return 0;
 }
 
+int mb200_mask_targets_ex(const uint8_t *unmasked, const uint64_t *off, uint32_t nT, int maskTantan, double maskProb, int simdWidth, const uint8_t *lowerCase, int maskNRepeat,
+                          uint8_t *masked, uint64_t *nMasked) {
+    if (!unmasked || !off || !masked) return fail(MB200_E_ARG, "null argument");
+    if (simdWidth != 0 && simdWidth != 2 && simdWidth != 4) return fail(MB200_E_ARG, "simd_width: 0, 2 or 4");
+    if (maskNRepeat < 0) return fail(MB200_E_ARG, "mask_n_repeat < 0");
+    for (uint64_t i = off[0]; i < off[nT]; i++) if (unmasked[i] > 20) return fail(MB200_E_ARG, "residue code %u at position %llu is not in 0..20", unmasked[i], (unsigned long long)i);
+    const uint64_t n = mb200::mask_targets_ex(unmasked, off, nT, maskTantan != 0, maskProb, simdWidth ? simdWidth : 4, lowerCase, maskNRepeat, masked);
+    if (nMasked) *nMasked = n;
+    return 0;
+}
+
 // ---- persisted index ----
 int mb200_index_file_write(const char *path, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT, const uint32_t *keys, int kmerThr, int maskMode) {
     if (!path || !masked || !unmasked || !off) return fail(MB200_E_ARG, "null argument");

@@ -110,6 +110,7 @@ static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e
 
 struct Opt {
     mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb; int mask = 1; double maskProb = 0.9;
+    int maskLowerCase = 0, maskNRepeat = 0;   // --mask-lower-case, --mask-n-repeat (Masker::maskSequence, Masker.cpp:14-58)
     int minLen = 15, maxLen = 32734;   // --min-length / --max-length of extractorfs in codons (setPredictExonsDefaults, src/workflow/PredictExons.cpp:8-16)
 };
 
@@ -124,8 +125,8 @@ static const FixedFlag FIXED_FLAGS[] = {
     {"--alignment-mode", {"2"}}, {"--alignment-output-mode", {"0"}}, {"-a", {"0"}}, {"--gap-open", {"11", "aa:11,nucl:5"}}, {"--gap-extend", {"1", "aa:1,nucl:2"}},
     {"--sub-mat", {"blosum62.out", "aa:blosum62.out,nucl:nucleotide.out"}}, {"--seed-sub-mat", {"VTML80.out", "aa:VTML80.out,nucl:nucleotide.out"}},
     {"-k", {"0", "6"}}, {"--spaced-kmer-mode", {"1"}}, {"--alph-size", {"21", "aa:21,nucl:5"}}, {"--max-seq-len", {"65535"}}, {"--split", {"0", "1"}}, {"--split-mode", {"2"}},
-    {"-c", {"0"}}, {"--cov-mode", {"0"}}, {"--comp-bias-corr-scale", {"1"}}, {"--diag-score", {"1"}}, {"--exact-kmer-matching", {"0"}}, {"--mask-lower-case", {"0"}},
-    {"--mask-n-repeat", {"0"}}, {"--add-self-matches", {"0"}}, {"--min-seq-id", {"0"}}, {"--seq-id-mode", {"0"}}, {"--alt-ali", {"0"}}, {"--max-rejected", {"2147483647"}},
+    {"-c", {"0"}}, {"--cov-mode", {"0"}}, {"--comp-bias-corr-scale", {"1"}}, {"--diag-score", {"1"}}, {"--exact-kmer-matching", {"0"}},
+    {"--add-self-matches", {"0"}}, {"--min-seq-id", {"0"}}, {"--seq-id-mode", {"0"}}, {"--alt-ali", {"0"}}, {"--max-rejected", {"2147483647"}},
     {"--max-accept", {"2147483647"}}, {"--score-bias", {"0"}}, {"--realign", {"0"}}, {"--wrapped-scoring", {"0"}}, {"--corr-score-weight", {"0"}},
     {"--orf-start-mode", {"1"}}, {"--contig-start-mode", {"2"}}, {"--contig-end-mode", {"2"}}, {"--forward-frames", {"1,2,3"}}, {"--reverse-frames", {"1,2,3"}},
     {"--max-gaps", {"2147483647"}}, {"--translate", {"0"}}, {"--use-all-table-starts", {"0"}}, {"--id-offset", {"0"}}, {"--create-lookup", {"0"}}, {"--add-orf-stop", {"0"}},
@@ -173,6 +174,8 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--index-db") o.indexDb = val();
         else if (a == "--mask") o.mask = atoi(val().c_str());
         else if (a == "--mask-prob") o.maskProb = atof(val().c_str());
+        else if (a == "--mask-lower-case") o.maskLowerCase = atoi(val().c_str());
+        else if (a == "--mask-n-repeat") o.maskNRepeat = atoi(val().c_str());
         else if (a == "--text-stages") o.textStages = atoi(val().c_str());
         else if (a == "--batch-nt") o.batchNt = atoll(val().c_str());
         else if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) {
@@ -192,16 +195,24 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
     return o;
 }
 
+// the masked target residues the index is built from, as IndexBuilder::fillDatabase gets them from Masker::maskSequence (IndexBuilder.cpp:84-131)
+static void maskTargets(const Opt &o, const Db &tdb, const Seqs &t, Seqs &m) {
+    if (!o.mask && !o.maskLowerCase && !o.maskNRepeat) return;                        // m == t
+    std::vector<uint8_t> lower;
+    if (o.maskLowerCase) {
+        lower.reserve(t.res.size());
+        for (size_t i = 0; i < tdb.keys.size(); i++) { const char *e = tdb.entry(i); const size_t n = tdb.len[i] >= 2 ? tdb.len[i] - 2 : 0; for (size_t k = 0; k < n; k++) lower.push_back(islower((unsigned char)e[k]) ? 1 : 0); }
+    }
+    MB(mb200_mask_targets_ex(t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), o.mask, o.maskProb, 0, o.maskLowerCase ? lower.data() : nullptr, o.maskNRepeat, m.res.data(), nullptr));
+}
+
 struct Session {
     mb200_ctx *ctx = nullptr; Db tdb; Seqs t; std::vector<uint64_t> tlen;
     void open(const Opt &o, const std::string &targetDb) {
         MB(mb200_ctx_create(o.device, &ctx)); MB(mb200_params_set(ctx, &o.p)); MB(mb200_matrices_default(ctx));
         tdb = openDb(targetDb); t = encodeDb(tdb, false);
         Seqs m = t;
-        if (o.maskedDb.empty() && o.mask && o.indexDb.empty()) {
-            // --mask 1 (the reference's default): tantan masking on the host, as IndexBuilder::fillDatabase does before it indexes (IndexBuilder.cpp:84-131)
-            MB(mb200_mask_targets(t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), o.maskProb, 0, m.res.data(), nullptr));
-        }
+        if (o.maskedDb.empty() && o.indexDb.empty()) maskTargets(o, tdb, t, m);   // --mask 1 (the reference's default): tantan masking on the host before indexing
         if (!o.maskedDb.empty()) {
             Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
             for (size_t i = 0; i < tdb.keys.size(); i++) {   // align by key
@@ -460,7 +471,7 @@ int main(int argc, char **argv) {
         if (pos.size() != 2) DIE("gpucreateindex <targetDB> <o:indexDB> [--masked-db <DB>] [--k-score N]");
         initCodes();
         Db tdb = openDb(pos[0]); Seqs t = encodeDb(tdb, false); Seqs m = t;
-        if (o.maskedDb.empty() && o.mask) MB(mb200_mask_targets(t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), o.maskProb, 0, m.res.data(), nullptr));
+        if (o.maskedDb.empty()) maskTargets(o, tdb, t, m);
         if (!o.maskedDb.empty()) {
             Db md = openDb(o.maskedDb); Seqs raw = encodeDb(md, true);
             for (size_t i = 0; i < tdb.keys.size(); i++) {
@@ -468,7 +479,7 @@ int main(int argc, char **argv) {
                 memcpy(&m.res[t.off[i]], &raw.res[raw.off[j]], t.off[i + 1] - t.off[i]);
             }
         }
-        MB(mb200_index_file_write(pos[1].c_str(), m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), tdb.keys.data(), o.p.kmer_thr, (o.maskedDb.empty() && !o.mask) ? 0 : 1));
+        MB(mb200_index_file_write(pos[1].c_str(), m.res.data(), t.res.data(), t.off.data(), (uint32_t)tdb.keys.size(), tdb.keys.data(), o.p.kmer_thr, (o.maskedDb.empty() && !o.mask) ? 0 : 1));   // META's mask field = --mask only (PrefilteringIndexReader.cpp:78)
     } else if (cmd == "gpuextractorfs") {
         // extractorfs + translatenucs in one step (data/predictexons.sh: contigs -> nucl_6f(_h) -> aa_6f): writes the ORF header DB and the
         // translated fragment DB with the reference's renumbered keys

@@ -114,6 +114,20 @@ def mask_targets(unmasked, off, mask_prob=0.9, simd_width=4):
     return out[:len(unmasked)], int(n.value)
 
 
+def mask_targets_ex(unmasked, off, mask_tantan=True, mask_prob=0.9, lower_case=None, mask_n_repeat=0, simd_width=4):
+    """Masker::maskSequence with all of its switches (--mask, --mask-prob, --mask-lower-case via one byte per residue, --mask-n-repeat): host only
+    -> (masked codes, the reference's "Masked residues" count)"""
+    L = load_library()
+    unmasked = np.ascontiguousarray(unmasked, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+    lc = np.ascontiguousarray(lower_case, np.uint8) if lower_case is not None else None
+    out = np.zeros(max(1, len(unmasked)), np.uint8); n = C.c_uint64(0)
+    rc = L.mb200_mask_targets_ex(_p(unmasked if len(unmasked) else np.zeros(1, np.uint8)), _p(off), C.c_uint32(len(off) - 1), int(bool(mask_tantan)), C.c_double(mask_prob),
+                                 int(simd_width), _p(lc) if lc is not None else None, int(mask_n_repeat), _p(out), C.byref(n))
+    if rc != 0:
+        raise Mb200Error("mb200 error %d: %s" % (rc, L.mb200_last_error().decode()))
+    return out[:len(unmasked)], int(n.value)
+
+
 def index_file_write(path, masked, unmasked, off, keys=None, kmer_thr=127, mask_mode=1):
     """build the target index on the host and persist it in the reference's index-DB layout (no GPU needed)"""
     L = load_library()

@@ -966,6 +966,32 @@ int tantan_mask(uint8_t *seq, int n, const double lr[21][21], double minMaskProb
 
 extern "C" {
 // out = residues after masking; returns the number of masked residues (the reference's "Masked residues:" line) or -1
+// every switch of Masker::maskSequence (Masker.cpp:14-58): tantan, then maskRepeats (:83-116) on the codes tantan left, then lower-case letters
+long long mbo_mask_targets_ex(const uint8_t *res, const uint64_t *off, uint32_t nT, int tantan, double maskProb, const uint8_t *lowerCase, int maskNrepeating, uint8_t *out, int lanes) {
+    if (lanes != 2 && lanes != 4) return -1;
+    double lr[21][21]; tantan_lr(lr);
+    long long total = 0;
+    for (uint32_t t = 0; t < nT; t++) {
+        const uint64_t b = off[t]; const unsigned int seqLen = (unsigned int)(off[t + 1] - b);
+        unsigned char *numSequence = out + b;
+        for (unsigned int i = 0; i < seqLen; i++) numSequence[i] = res[b + i];
+        if (tantan) total += tantan_mask(numSequence, (int)seqLen, lr, maskProb, lanes);
+        if (maskNrepeating > 0) {                                   // Masker::maskRepeats, statement by statement (previousChar '\0' is the code of 'A')
+            unsigned int repeatCount = 0; int startOfRepeat = -1; char previousChar = '\0';
+            for (unsigned int pos = 0; pos < seqLen; ++pos) {
+                char currentChar = (char)numSequence[pos];
+                if (currentChar == previousChar) repeatCount++;
+                else {
+                    if (repeatCount > (unsigned int)maskNrepeating) for (unsigned int i = (unsigned int)startOfRepeat; i < pos; ++i) { numSequence[i] = XRES; total++; }
+                    repeatCount = 1; startOfRepeat = (int)pos; previousChar = currentChar;
+                }
+            }
+            if (repeatCount > (unsigned int)maskNrepeating) for (unsigned int i = (unsigned int)startOfRepeat; i < seqLen; ++i) { numSequence[i] = XRES; total++; }
+        }
+        if (lowerCase) for (unsigned int i = 0; i < seqLen; i++) if (lowerCase[b + i]) { numSequence[i] = XRES; total++; }
+    }
+    return total;
+}
 long long mbo_mask_targets(const uint8_t *res, const uint64_t *off, uint32_t nT, double maskProb, uint8_t *out, int lanes, int threads) {
     if (lanes != 2 && lanes != 4) return -1;
     double lr[21][21]; tantan_lr(lr);

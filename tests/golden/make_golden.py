@@ -104,7 +104,7 @@ IDX_FLAGS = ("--seed-sub-mat aa:VTML80.out,nucl:nucleotide.out -k 6 -s 4 --mask 
 NUM2AA = "ACDEFGHIKLMNPQRSTVWYX"
 
 
-def ref_index(tmp, db, mask, thr, log):
+def ref_index(tmp, db, mask, thr, log, extra=None):
     """Run the reference `indexdb` (same IndexBuilder::fillDatabase the prefilter calls,
     reference/lib/mmseqs/src/prefiltering/IndexBuilder.cpp:55) and pull out of the .idx DB
     (entry ids: PrefilteringIndexReader.cpp:10-34): the tantan-MASKED target sequences
@@ -112,7 +112,10 @@ def ref_index(tmp, db, mask, thr, log):
     (ENTRIES=9, ENTRIESOFFSETS=10) and of the 3-mer similarity table (SCOREMATRIX3MER=4)."""
     import hashlib
     import struct
-    out = run("%s indexdb %s/%s %s/%s %s" % (REF, tmp, db, tmp, db, IDX_FLAGS.format(mask=mask, thr=thr)), log)
+    flags = IDX_FLAGS.format(mask=mask, thr=thr)
+    for k, v in (extra or {}).items():
+        flags = flags.replace("%s 0" % k, "%s %s" % (k, v))
+    out = run("%s indexdb %s/%s %s/%s %s" % (REF, tmp, db, tmp, db, flags), log)
     ent = {}
     for line in open("%s/%s.idx.index" % (tmp, db)):
         k, o, l = line.split("\t")
@@ -472,6 +475,39 @@ def case_masking(name="mask_repeats", seed=606, thr=8):
     print(name, "targets", len(out["targets"]), "residues", sum(len(s) for _, s in out["targets"]), "masked", out["masked_residues"])
 
 
+def case_masking_flags(name="mask_flags", seed=707, thr=8):
+    """the other switches of Masker::maskSequence (--mask-lower-case, --mask-n-repeat, with and without tantan) on proteins with soft-masked (lower-case) stretches,
+    runs of 2..9 equal letters anywhere -- including runs of A at the very start of a sequence, which the reference's run scan cannot mask -- X runs, and
+    sequences that are one single run; the masked residues are read back from the reference's `indexdb` output per variant"""
+    rng = random.Random(seed)
+    tmp = tempfile.mkdtemp(prefix="mb200_golden_")
+    log = []
+    prots = []
+    for i in range(160):
+        p = list(rand_prot(rng, 160, 60, 20))
+        for _ in range(rng.randint(0, 4)):
+            a = rng.randrange(len(p)); p[a:a] = list(rng.choice(AA + "AAX") * rng.randint(2, 9))
+        if i % 5 == 0:
+            p[0:0] = list("A" * rng.randint(1, 7))
+        if i % 7 == 0:
+            p[0:0] = list(rng.choice("CDW") * rng.randint(2, 6))
+        for _ in range(rng.randint(0, 3)):
+            a = rng.randrange(len(p)); b = min(len(p), a + rng.randint(1, 40)); p[a:b] = [c.lower() for c in p[a:b]]
+        prots.append("".join(p))
+    prots += ["A" * 12, "AAAAc", "aaaa" + rand_prot(rng, 40, 5), "W" * 9, "ACAC", "x" * 8 + "KLMN" * 5, "MKKKKKKKKKK", "M"]
+    write_fasta(tmp + "/proteins.faa", prots, "P")
+    run("%s createdb %s/proteins.faa %s/proteins --shuffle 0 -v 3" % (REF, tmp, tmp), log)
+    out = {"case": name, "kind": "masking_flags", "seed": seed, "targets": seqdb(tmp + "/proteins"), "variants": {}}
+    for vn, mask, lower, nrep in (("tantan+lower", 1, 1, 0), ("lower+nrep3", 0, 1, 3), ("tantan+nrep2", 1, 0, 2), ("nrep1", 0, 0, 1), ("all", 1, 1, 4)):
+        idx = ref_index(tmp, "proteins", mask, thr, log, {"--mask-lower-case": lower, "--mask-n-repeat": nrep})
+        out["variants"][vn] = {"mask": mask, "mask_lower_case": lower, "mask_n_repeat": nrep, "masked_targets": idx["masked_targets"], "masked_residues": idx["idx_masked_residues"]}
+        print(vn, "masked residues", idx["idx_masked_residues"])
+    out["ref_version"] = run("%s version" % REF, log).strip()
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+        json.dump(out, f)
+    shutil.rmtree(tmp)
+
+
 REF_TESTS = [("minus_strand", -1, 0), ("multi_exon", -1, 0), ("two_contigs", -1, 0), ("target_overlap", -3, 0), ("cluster_rep", -3, 0), ("target_cov", -1, 0.7)]
 
 
@@ -604,3 +640,5 @@ if __name__ == "__main__":
         case_masking()
     if "flags" in which:
         case_flags()
+    if "mask_flags" in which:
+        case_masking_flags()

@@ -126,3 +126,30 @@ def test_predictexons_flags_follow_the_drivers_rules():
     assert M.predictexons_flags("-s 2 --k-score seq:109,prof:109")[0]["kmer_thr"] == 109
     with pytest.raises(ValueError):
         M.predictexons_flags("--orf-start-mode 0")
+
+
+@pytest.mark.parametrize("variant", ["tantan+lower", "lower+nrep3", "tantan+nrep2", "nrep1", "all"])
+def test_product_masking_switches_match_reference(variant):
+    """mb200_mask_targets_ex (product host code) on the reference's --mask-lower-case / --mask-n-repeat fixture"""
+    from test_oracle_golden import mask_flags_inputs
+    c = reflib.load_case("mask_flags"); v = c["variants"][variant]
+    u, off, lower = mask_flags_inputs(c)
+    want, _ = reflib.pack(v["masked_targets"])
+    for width in (4, 2):
+        got, n = mlib.mask_targets_ex(u, off, bool(v["mask"]), 0.9, lower if v["mask_lower_case"] else None, v["mask_n_repeat"], width)
+        assert (got == want).all() and n == v["masked_residues"], width
+
+
+def test_gpucreateindex_takes_the_masking_switches(exe, emu, tmp_path):  # noqa: F811
+    """--mask-lower-case / --mask-n-repeat reach the index builder of the driver: the residues stored in the index equal the reference's"""
+    c = reflib.load_case("mask_flags")
+    d = str(tmp_path)
+    reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"]], 0)
+    for name, v in c["variants"].items():
+        out = d + "/" + name.replace("+", "_") + ".idx"
+        subprocess.check_call([exe, "gpucreateindex", d + "/proteins", out, "--mask", str(v["mask"]), "--mask-lower-case", str(v["mask_lower_case"]),
+                               "--mask-n-repeat", str(v["mask_n_repeat"])])
+        x, err = _open_indexdb(emu, out)
+        assert x is not None, err
+        want, _ = reflib.pack(v["masked_targets"])
+        assert (x["masked"] == want).all() and x["meta"][4] == v["mask"], name
