@@ -120,6 +120,7 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
 int mb200_ctx_create(int device, mb200_ctx **out);
 void mb200_ctx_destroy(mb200_ctx *ctx);
 const char *mb200_last_error(void);
+const char *mb200_build_kind(void);   /* "sm_100a" for the library; "simt-emulation" only for the CPU test build under tests/simt (kernels as fibers; never shipped) */
 void mb200_params_default(mb200_params *p);
 /* what `-s <sensitivity>` means for kmer_thr: Prefiltering::getKmerThreshold for a sequence search with k = 6 (M/src/prefiltering/Prefiltering.cpp:1005-1064);
  * -s 4 (MetaEuk's default) -> 127 */

@@ -9,7 +9,7 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__) && !defined(MB200_EMULATE)
+#if (defined(__CUDACC__) || defined(MB200_SIMT_EMU)) && !defined(MB200_EMULATE)
 #define MB_DEVICE_BUILD 1
 #define MB_DEV __device__ __forceinline__
 #define MB_DEV_CALL __device__ __noinline__   // block-wide collectives used at several sites: one copy of the code

@@ -8,6 +8,13 @@
 //   tseqM/U  u8  [residues]     masked / unmasked target residues, read along diagonals / rows
 // Per-CTA scratch lists (window/item/k-mer/hit expansions) live in global memory but are sized to stay in L2.
 #include <cuda_runtime.h>
+#ifndef MB200_SIMT_EMU
+// kernel launch / dynamic shared memory as macros: tests/simt compiles this file with a stand-in <cuda_runtime.h> that runs kernels as cooperative fibers on the CPU
+// (test infrastructure for the GPU suite's logic; the library that ships is the nvcc build of this file and has no CPU path)
+#define MB_UNPAREN(...) __VA_ARGS__
+#define MB_LAUNCH(kern, grid, block, smem, stream, ...) MB_UNPAREN kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define MB_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 #include <algorithm>
 #include <parallel/algorithm>
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(SH::Cfg::NT, SH::Cfg::CTAS) k_prefilter(MbPref
                                                               const uint64_t *__restrict__ qoff, const float *__restrict__ bias, const int8_t *__restrict__ corr,
                                                               const uint32_t *__restrict__ order, uint32_t nQ, const int8_t *__restrict__ ungMat8,
                                                               MbPrefHit *out, uint32_t *outCount, uint32_t *outStatus, MbPrefStats *stats, uint32_t *nextQ) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    MB_DYN_SHARED(smemRaw);
     SH *sh = reinterpret_cast<SH *>(smemRaw);
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sh->ungMat[i] = ungMat8[i];
     if (T.phaseStats && threadIdx.x == 0) { for (int i = 0; i < 16; i++) sh->phaseAcc[i] = 0; sh->phaseT = clock64(); }
@@ -262,6 +269,14 @@ void mb200_params_default(mb200_params *p) {
     p->comp_bias_corr = 1; p->reverse_fragments = 0; p->translation_table = 1;
 }
 
+const char *mb200_build_kind(void) {
+#ifdef MB200_SIMT_EMU
+    return "simt-emulation";     // tests/simt: kernels run as CPU fibers -- test infrastructure, never measured, never shipped
+#else
+    return "sm_100a";
+#endif
+}
+
 int mb200_kmer_threshold(float sensitivity) { return mb200::kmer_threshold_for_sensitivity(sensitivity); }
 
 int mb200_ctx_create(int device, mb200_ctx **out) {
@@ -375,7 +390,7 @@ static int build_kmer_bits(mb200_ctx *c) {
     if (c->nEntries >= mb200::KMER_TABLE) return 0;   // dense index: nearly every k-mer has a list, the extra lookup would not pay
     const uint32_t nWords = (uint32_t)(mb200::KMER_TABLE / 32);
     TRY(c->dKmerBits.alloc(nWords));
-    k_kmer_bits<<<(nWords + 255) / 256, 256, 0, c->stream>>>(c->dOffsets.p, nWords, c->dKmerBits.p);
+    MB_LAUNCH((k_kmer_bits), (nWords + 255) / 256, 256, 0, c->stream, c->dOffsets.p, nWords, c->dKmerBits.p);
     CU(cudaGetLastError()); CU(cudaStreamSynchronize(c->stream));
     c->useBits = true; return 0;
 }
@@ -538,7 +553,7 @@ static int queries_install(mb200_ctx *c, const uint8_t *q, const uint8_t *qDev, 
         CU(cudaStreamSynchronize(c->stream)); c->st.ms_prep = 0;
     } else if (tot) {
         CU(cudaEventRecord(c->ev0, c->stream));
-        k_prep<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->dQ.p, c->dQoff.p, nQ, tot, c->dSeedMat.p, c->dSeedPB.p, c->dAlnMat.p, c->dAlnPB.p, c->dBias.p, c->dCorr.p, c->dCb.p);
+        MB_LAUNCH((k_prep), (unsigned)((tot + 255) / 256), 256, 0, c->stream, c->dQ.p, c->dQoff.p, nQ, tot, c->dSeedMat.p, c->dSeedPB.p, c->dAlnMat.p, c->dAlnPB.p, c->dBias.p, c->dCorr.p, c->dCb.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -614,7 +629,7 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     c->nOrfs = 0; c->nOrfAa = 0; *nOrfs = 0; *nAa = 0; *orfs = nullptr; *aa = nullptr;
     if (nContigs == 0) return 0;
     const int grid = (int)std::min<uint32_t>(units, (uint32_t)c->nSM * 8u);
-    k_orf_scan<false><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
+    MB_LAUNCH((k_orf_scan<false>), grid, MB_ORF_THREADS, 0, c->stream, c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
                                                               c->dOrfCnt.p, c->dOrfAaCnt.p, nullptr, nullptr, nullptr);
     CU(cudaGetLastError());
     std::vector<uint32_t> cnt(units); std::vector<uint64_t> acnt(units), rb(units + 1, 0), ab(units + 1, 0);
@@ -626,10 +641,10 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     TRY(c->dOrfRecs.alloc(n + 1)); TRY(c->dOrfAa.alloc(na + 16)); TRY(c->dOrfCodes.alloc(na + 16)); TRY(c->pOrfRecs.alloc(n + 1)); TRY(c->pOrfAa.alloc(na + 16));
     TRY(upload(c->dOrfRecBase.p, rb.data(), (size_t)(units + 1) * 8, c->stream)); TRY(upload(c->dOrfAaBase.p, ab.data(), (size_t)(units + 1) * 8, c->stream));
     if (n) {
-        k_orf_scan<true><<<grid, MB_ORF_THREADS, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
+        MB_LAUNCH((k_orf_scan<true>), grid, MB_ORF_THREADS, 0, c->stream, c->dNuc.p, c->dNucOff.p, nContigs, c->dOrfTab.p, (uint32_t)minLen, (uint32_t)maxLen, stopSet,
                                                                  nullptr, nullptr, c->dOrfRecBase.p, c->dOrfAaBase.p, c->dOrfRecs.p);
         CU(cudaGetLastError());
-        k_orf_translate<<<c->nSM * 8, 256, 0, c->stream>>>(c->dNuc.p, c->dNucOff.p, c->dOrfTab.p, c->dOrfRecs.p, n, c->par.reverse_fragments ? 1 : 0, c->dOrfAa.p, c->dOrfCodes.p);
+        MB_LAUNCH((k_orf_translate), c->nSM * 8, 256, 0, c->stream, c->dNuc.p, c->dNucOff.p, c->dOrfTab.p, c->dOrfRecs.p, n, c->par.reverse_fragments ? 1 : 0, c->dOrfAa.p, c->dOrfCodes.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaMemcpyAsync(c->pOrfRecs.p, c->dOrfRecs.p, (size_t)n * sizeof(MbOrfRec), cudaMemcpyDeviceToHost, c->stream));
@@ -674,7 +689,7 @@ int mb200_reduce_redundancy(mb200_ctx *c, const mb200_pred *preds, const uint64_
     if ((rc = upload(dP.p, preds, n * sizeof(MbPred), c->stream)) || (rc = upload(dOff.p, predOff, (size_t)(nContigs + 1) * 8, c->stream)) ||
         (rc = upload(dKeys.p, exonKeys, (size_t)nExonKeys * 4, c->stream))) return done(rc);
     cudaEventRecord(c->ev0, c->stream);
-    k_reduce<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(dP.p, dOff.p, nContigs, dKeys.p, dOut.p, dMem.p, dRep.p, dCnt.p, dFlag.p, dTmp.p);
+    MB_LAUNCH((k_reduce), (nContigs + 127) / 128, 128, 0, c->stream, dP.p, dOff.p, nContigs, dKeys.p, dOut.p, dMem.p, dRep.p, dCnt.p, dFlag.p, dTmp.p);
     cudaEventRecord(c->ev1, c->stream);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut.p, n * sizeof(MbPredOut), cudaMemcpyDeviceToHost, c->stream);
@@ -704,10 +719,10 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
         if (c->prefCfg == 1)
-            k_prefilter<MbPrefSharedT<MbPrefCfgDense>><<<c->nCta, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream>>>(
+            MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgDense>>), c->nCta, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream, 
                 T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
         else
-            k_prefilter<MbPrefSharedT<MbPrefCfgSparse>><<<c->nCta, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream>>>(
+            MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>), c->nCta, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream, 
                 T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
@@ -740,10 +755,10 @@ int mb200_prefilter_resident(mb200_ctx *c) {
             MbPrefTables T2 = T; T2.capI = capI2; T2.capK = capK2; T2.capM = capM2;
             CU(cudaEventRecord(c->ev0, c->stream));
             if (c->prefCfg == 1)
-                k_prefilter<MbPrefSharedT<MbPrefCfgDense>><<<nR, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream>>>(
+                MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgDense>>), nR, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream, 
                     T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
             else
-                k_prefilter<MbPrefSharedT<MbPrefCfgSparse>><<<nR, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream>>>(
+                MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>), nR, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream, 
                     T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
             CU(cudaGetLastError());
             CU(cudaEventRecord(c->ev1, c->stream));
@@ -782,7 +797,7 @@ static int align_pipeline(mb200_ctx *c) {
     // sw_kernel 4: queries of at most 64 residues with at most sw_lane_max_hits hits go to k_sw_lanes (one (query, 2 hits) item per lane), the rest to k_sw_rows2
     // sw_kernel 5: the other queries of at most 1024 residues go to k_sw_wave (the row blocks of one alignment on neighbouring lanes)
     const bool laneMode = c->optSwKernel >= 4 && maxHits <= 1024, waveMode = c->optSwKernel == 5 && maxHits <= 1024;
-    k_scan_counts<<<4, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 64u,
+    MB_LAUNCH((k_scan_counts), 4, MB_CTA_THREADS, 0, c->stream, c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 64u,
                                                        laneMode ? (uint32_t)c->optLaneMaxHits : 0u, waveMode ? 1024u : 0u);
     CU(cudaGetLastError());
     uint32_t nPairs = 0;
@@ -802,7 +817,7 @@ static int align_pipeline(mb200_ctx *c) {
     CU(cudaEventRecord(c->ev0, c->stream));   // ms_sw_fwd = hit permutation + forward kernels
     if (usePerm) {
         TRY(c->dPerm.alloc((size_t)nQ * maxHits));
-        k_perm_by_len<<<c->nSM * 8, 128, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dToff.p, nQ, maxHits, c->dPerm.p);
+        MB_LAUNCH((k_perm_by_len), c->nSM * 8, 128, 0, c->stream, c->dHits.p, c->dHitCount.p, c->dToff.p, nQ, maxHits, c->dPerm.p);
         CU(cudaGetLastError()); c->st.launches++;
     }
     uint32_t *dNPass = c->dCounter.p + 32, *dErr = c->dCounter.p + 33;
@@ -823,7 +838,7 @@ static int align_pipeline(mb200_ctx *c) {
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows3, W * 32, smem)); if (perSM < 1) perSM = 1;
             const int blocks = c->nSM * perSM;
             TRY(c->dBnd.alloc((size_t)blocks * W * maxT * 32u * 2u));
-            k_sw_rows3<<<blocks, W * 32, smem, c->stream>>>(c->dOrder.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+            MB_LAUNCH((k_sw_rows3), blocks, W * 32, smem, c->stream, c->dOrder.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                          c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                          strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
                                                          reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
@@ -834,7 +849,7 @@ static int align_pipeline(mb200_ctx *c) {
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows2<32>, W * 32, smem)); if (perSM < 1) perSM = 1;
             const int blocks = c->nSM * perSM;
             TRY(c->dBnd.alloc((size_t)blocks * W * maxT * 32u * 2u));
-            k_sw_rows2<32><<<blocks, W * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+            MB_LAUNCH((k_sw_rows2<32>), blocks, W * 32, smem, c->stream, c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                              c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                              strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
                                                              reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
@@ -844,7 +859,7 @@ static int align_pipeline(mb200_ctx *c) {
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows<32>, MB_SWR_WARPS * 32, smem)); if (perSM < 1) perSM = 1;
             const int blocks = c->nSM * perSM;
             TRY(c->dBnd.alloc((size_t)blocks * MB_SWR_WARPS * maxT * 32u));
-            k_sw_rows<32><<<blocks, MB_SWR_WARPS * 32, smem, c->stream>>>(c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+            MB_LAUNCH((k_sw_rows<32>), blocks, MB_SWR_WARPS * 32, smem, c->stream, c->dOrder.p, c->dChunkOff.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                                          c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                                          strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
                                                                          c->dBnd.p, maxT);
@@ -862,7 +877,7 @@ static int align_pipeline(mb200_ctx *c) {
             const size_t smem = (size_t)W * perWarpBytes;
             CU(cudaFuncSetAttribute(k_sw_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_wave, W * 32, smem)); if (perSM < 1) perSM = 1;
-            k_sw_wave<<<c->nSM * perSM, W * 32, smem, c->stream>>>(c->dOrder.p, c->dWaveOff.p, wbnd[k], wbnd[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+            MB_LAUNCH((k_sw_wave), c->nSM * perSM, W * 32, smem, c->stream, c->dOrder.p, c->dWaveOff.p, wbnd[k], wbnd[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                                  c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                                  wstr[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 4 + k, c->dCells.p, dErr, wG[k]);
             CU(cudaGetLastError()); c->st.launches++;
@@ -883,12 +898,12 @@ static int align_pipeline(mb200_ctx *c) {
             const int blocks = c->nSM * perSM;
             TRY(c->dBnd.alloc((size_t)blocks * (threads / 32) * maxT * 32u * 2u));
             if (k == 0)
-                k_sw_lanes<64><<<blocks, threads, smem, c->stream>>>(c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                MB_LAUNCH((k_sw_lanes<64>), blocks, threads, smem, c->stream, c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                                    c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                                    c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 2 + k, c->dCells.p, dErr,
                                                                    reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
             else
-                k_sw_lanes<32><<<blocks, threads, smem, c->stream>>>(c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
+                MB_LAUNCH((k_sw_lanes<32>), blocks, threads, smem, c->stream, c->dOrder.p, c->dLaneOff.p, lb[k], lb[k + 1], c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
                                                                    c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
                                                                    c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + 2 + k, c->dCells.p, dErr,
                                                                    reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
@@ -922,11 +937,11 @@ static int align_pipeline(mb200_ctx *c) {
         TRY(c->dTrace.alloc(nPass));
         if (c->optTraceKernel == 1) {
             TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32));
-            k_sw_trace<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+            MB_LAUNCH((k_sw_trace), blocks, 128, 0, c->stream, c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
                                                       c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
         } else {
             TRY(c->dHE.alloc(nWarps * maxT * 32));
-            k_sw_trace2<<<blocks, 128, 0, c->stream>>>(c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+            MB_LAUNCH((k_sw_trace2), blocks, 128, 0, c->stream, c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
                                                        c->par.gap_open, c->par.gap_extend, c->dHE.p, maxT, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
         }
         CU(cudaGetLastError());
@@ -979,7 +994,7 @@ static int download_hits_compact(mb200_ctx *c) {
     c->hHitOff.assign(nQ + 1, 0); c->nFlatHits = 0;
     if (nQ == 0) return 0;
     TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->pOff.alloc(nQ + 1));
-    k_scan_counts<<<2, MB_CTA_THREADS, 0, c->stream>>>(c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, nullptr, nullptr, c->dQoff.p, 0u, 0u, 0u);
+    MB_LAUNCH((k_scan_counts), 2, MB_CTA_THREADS, 0, c->stream, c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, nullptr, nullptr, c->dQoff.p, 0u, 0u, 0u);
     CU(cudaGetLastError());
     uint32_t *off = c->pOff.p;
     CU(cudaEventRecord(c->ev0, c->stream));
@@ -987,7 +1002,7 @@ static int download_hits_compact(mb200_ctx *c) {
     TRY(sync_check(c, "scan"));
     const uint32_t n = off[nQ];
     TRY(c->dFlatHits.alloc(n)); TRY(c->pFlatHits.alloc(n));
-    k_compact_hits<<<nQ, 64, 0, c->stream>>>(c->dHits.p, c->dHitCount.p, c->dPairOff.p, nQ, maxHits, c->dFlatHits.p);
+    MB_LAUNCH((k_compact_hits), nQ, 64, 0, c->stream, c->dHits.p, c->dHitCount.p, c->dPairOff.p, nQ, maxHits, c->dFlatHits.p);
     CU(cudaGetLastError());
     if (n) CU(cudaMemcpyAsync(c->pFlatHits.p, c->dFlatHits.p, (size_t)n * sizeof(MbPrefHit), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -1064,7 +1079,7 @@ static int trace_tids(mb200_ctx *c, std::vector<uint32_t> &tids) {
     // hTrace was sorted on the host; re-upload so the gather follows the same order
     TRY(c->dTrace.alloc(n)); TRY(c->dFlatSeq.alloc(n));
     TRY(upload(c->dTrace.p, c->hTrace.data(), n * sizeof(SwTraceOut), c->stream));
-    k_gather_tid<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->dHits.p, c->dTrace.p, (uint32_t)n, c->dFlatSeq.p);
+    MB_LAUNCH((k_gather_tid), (unsigned)((n + 255) / 256), 256, 0, c->stream, c->dHits.p, c->dTrace.p, (uint32_t)n, c->dFlatSeq.p);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(tids.data(), c->dFlatSeq.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "gather tid")); c->st.launches++;
@@ -1082,7 +1097,7 @@ int mb200_align(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff, uint32_t n
     TRY(c->dHits.alloc((size_t)nQ * maxHits)); TRY(c->dHitCount.alloc(nQ + 1)); TRY(c->dFlatSeq.alloc(n ? n : 1)); TRY(c->dHitOff64.alloc(nQ + 1));
     if (n) TRY(upload(c->dFlatSeq.p, hitSeq, n * 4, c->stream));
     TRY(upload(c->dHitOff64.p, hitOff, (size_t)(nQ + 1) * 8, c->stream));
-    if (nQ) { k_scatter_hits<<<nQ, 64, 0, c->stream>>>(c->dFlatSeq.p, c->dHitOff64.p, nQ, maxHits, c->dHits.p, c->dHitCount.p); CU(cudaGetLastError()); c->st.launches++; }
+    if (nQ) { MB_LAUNCH((k_scatter_hits), nQ, 64, 0, c->stream, c->dFlatSeq.p, c->dHitOff64.p, nQ, maxHits, c->dHits.p, c->dHitCount.p); CU(cudaGetLastError()); c->st.launches++; }
     c->havePref = true;
     TRY(align_pipeline(c));
     for (uint32_t i = 0; i < nQ; i++) for (uint64_t k = hitOff[i]; k < hitOff[i + 1]; k++) { memset(&alns[k], 0, sizeof(mb200_aln)); alns[k].seq_id = hitSeq[k]; alns[k].q_start = alns[k].db_start = -1; }
@@ -1132,7 +1147,7 @@ int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, 
     MbChainParams P; P.minIntron = c->par.min_intron; P.maxIntron = c->par.max_intron; P.minExonAa = c->par.min_exon_aa; P.maxOverlap = c->par.max_overlap;
     P.gapOpen = c->par.set_gap_open; P.gapExtend = c->par.set_gap_extend; P.maxSets = c->par.max_exon_sets; P.tcov = c->par.tcov;
     CU(cudaEventRecord(c->ev0, c->stream));
-    k_chain<<<(nContigs + 127) / 128, 128, 0, c->stream>>>(c->dChCand.p, c->dChOff.p, nContigs, P, c->dChPE.p, c->dChOp.p, c->dChOm.p, c->dChRows.p, c->dChCalls.p, c->dChEx.p,
+    MB_LAUNCH((k_chain), (nContigs + 127) / 128, 128, 0, c->stream, c->dChCand.p, c->dChOff.p, nContigs, P, c->dChPE.p, c->dChOp.p, c->dChOm.p, c->dChRows.p, c->dChCalls.p, c->dChEx.p,
                                                            c->dChCallCnt.p, c->dChExCnt.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));

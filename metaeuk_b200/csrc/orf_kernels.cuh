@@ -38,7 +38,7 @@ inline unsigned long long orf_stop_set(const char *ncbieaa) {
     return m;
 }
 
-#if defined(__CUDACC__)    // everything below is device code (the helpers above also compile for the host: tests/emu checks them exhaustively)
+#if defined(__CUDACC__) || defined(MB200_SIMT_EMU)    // everything below is device code (the helpers above also compile for the host: tests/emu checks them exhaustively)
 #define MB_ORF_THREADS 256
 #define MB_ORF_PER_THREAD 24                      // 8 codons of each frame
 #define MB_ORF_TILE (MB_ORF_THREADS * MB_ORF_PER_THREAD)

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows(
     const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
     uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
     uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint32_t *__restrict__ bnd, uint32_t maxT) {
-    extern __shared__ __align__(16) unsigned char dynProf[];
+    MB_DYN_SHARED(dynProf);
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
@@ -162,7 +162,11 @@ __device__ __forceinline__ uint32_t sw_pack_scores(uint32_t wa, uint32_t wb, int
     // (__byte_perm masks the selector nibbles to 3 bits, so the sign-replicating form needs the PTX instruction itself)
     const uint32_t sel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
     uint32_t d;
+#ifdef MB200_SIMT_EMU
+    d = simt_prmt(wa, wb, sel);      // (tests/simt: the same instruction restated in C)
+#else
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(wa), "r"(wb), "r"(sel));
+#endif
     return d;
 }
 
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_rows2(
     const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
     uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
     uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
-    extern __shared__ __align__(16) unsigned char dynProf[];
+    MB_DYN_SHARED(dynProf);
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(STRIDE == 32 ? 256 : 128) k_sw_lanes(
     uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
     constexpr int RB = 32;
     constexpr uint32_t LANE_BYTES = 22u * STRIDE + 16u;       // an odd multiple of 16 bytes: the 128-bit profile loads of 8 neighbouring lanes fall into 8 different bank groups
-    extern __shared__ __align__(16) unsigned char dynProf[];
+    MB_DYN_SHARED(dynProf);
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
     uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
     uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint32_t G /* lanes per item: 16 (L <= 512) or 32 */) {
     constexpr int RB = 32;
-    extern __shared__ __align__(16) unsigned char dynProf[];
+    MB_DYN_SHARED(dynProf);
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32, 2) k_sw_rows3(
     uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
     uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
     constexpr int RBK = 32;
-    extern __shared__ __align__(16) unsigned char dynProf[];
+    MB_DYN_SHARED(dynProf);
     __shared__ int8_t sMat8[448];
     for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
     __syncthreads();
