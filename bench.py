@@ -540,6 +540,10 @@ def main():
             "data": "synthetic (seeded; SURVEY.md 8d generator)", "config": {"workload": wl["desc"], "stages": "prefilter+align" if wl["align"] else "prefilter",
                                                                                "fragments_per_gpu": wl["n_frag"], "proteins": wl["n_prot"], "parallelism": "fragment shards x%d, index replicated by one NCCL broadcast" % args.gpus,
                                                                                "l2": "inputs exceed L2 (k-mer offsets 256 MB + index entries + similarity table >> 126 MB); no explicit flush"}}
+    if args.impl == "b200":
+        from metaeuk_b200 import lib as _mlib
+        if _mlib.build_kind() != "sm_100a":
+            raise SystemExit("bench.py measures the sm_100a library only (loaded: %s)" % _mlib.build_kind())
     # ------------------------------------------------------------------ reference arm: CPU path on the host cores
     if args.impl == "reference":
         if rank != 0:

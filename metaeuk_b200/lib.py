@@ -90,6 +90,13 @@ def load_library():
     return _lib
 
 
+def build_kind():
+    """"sm_100a" for the library; "simt-emulation" only when a test pointed MB200_LIB_PATH at tests/simt (kernels as CPU fibers)"""
+    L = load_library()
+    L.mb200_build_kind.restype = C.c_char_p
+    return L.mb200_build_kind().decode()
+
+
 def _p(a, t=C.c_void_p):
     return a.ctypes.data_as(t)
 
