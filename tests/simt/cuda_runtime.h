@@ -138,7 +138,12 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 2; strcpy(p->name, "simt emulation"); return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// device allocations are filled with a poison pattern: cudaMalloc does not zero memory, and a kernel that silently relies on zeros should fail here
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
+    const size_t m = (n + 255) & ~(size_t)255; *p = (T *)aligned_alloc(256, m ? m : 256);
+    if (*p) memset((void *)*p, getenv("MB200_SIMT_POISON") ? atoi(getenv("MB200_SIMT_POISON")) : 0xCD, m);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { *p = (T *)aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
