@@ -30,6 +30,7 @@ SLICE = [
     "tests/test_gpu_parity.py::test_reference_own_end_to_end_fixtures[multi_exon]",
     "tests/test_zz_gpu_adversarial.py::test_predictexons_flags_golden[table6]",
     "tests/test_zz_gpu_adversarial.py::test_very_long_fragments_take_the_second_prefilter_pass",
+    "tests/test_zz_gpu_adversarial.py::test_cli_gpupredictexons_takes_the_reference_flags[table4]",     # the C++ driver, linked against the emulation
 ]
 
 
@@ -50,7 +51,7 @@ def test_product_library_is_the_device_build():
 
 
 def test_gpu_suite_slice_on_the_simt_emulation(simt_lib):
-    env = dict(os.environ, MB200_LIB_PATH=simt_lib, OMP_NUM_THREADS="4")
+    env = dict(os.environ, MB200_LIB_PATH=simt_lib, MB200_CLI_PATH=os.path.join(SIMT_DIR, "mb200_simt"), OMP_NUM_THREADS="4")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + SLICE, cwd=reflib.ROOT, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "%d passed" % len(SLICE) in r.stdout, r.stdout[-500:]
