@@ -3,6 +3,7 @@
 // synchronisation point and is resumed once all participants of that point have arrived.  Blocks of a grid run one after the other.
 #include "cuda_runtime.h"
 
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <mutex>
@@ -11,12 +12,12 @@
 namespace simt {
 
 enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
-struct Fiber { ucontext_t ctx; Thread th; State state; uint64_t result; unsigned char *stack; };
+struct Fiber { ucontext_t ctx; jmp_buf jb; bool started; Thread th; State state; uint64_t result; unsigned char *stack; };
 struct Warp { unsigned arrived, exited; uint64_t val[32]; int param[32], width[32]; Op op[32]; };
 
 Thread *cur = nullptr;
 static const size_t STACK = 512 * 1024;
-static ucontext_t sched;
+static jmp_buf schedJb;      // fibers are entered once with setcontext and switched with _setjmp/_longjmp afterwards (no signal-mask system call per switch)
 static std::vector<Fiber *> fibers;
 static Fiber *curF = nullptr;
 static std::vector<Warp> warps;
@@ -28,7 +29,7 @@ static std::mutex launchMutex;
 
 unsigned char *dyn_smem() { return dynMem; }
 
-static void yield() { swapcontext(&curF->ctx, &sched); }
+static void yield() { if (!_setjmp(curF->jb)) _longjmp(schedJb, 1); }
 
 static void release_block() { barCount = 0; for (Fiber *f : fibers) if (f->state == WAIT_BLOCK) f->state = READY; }
 
@@ -73,7 +74,7 @@ uint64_t warp_collective(unsigned mask, Op op, uint64_t value, int param, int wi
 static void entry() {
     (*body)();
     curF->state = DONE;
-    swapcontext(&curF->ctx, &sched);
+    _longjmp(schedJb, 1);
 }
 
 void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &fn) {
@@ -89,8 +90,8 @@ void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &
         for (unsigned w = 0; w < warps.size(); w++) { warps[w].arrived = 0; warps[w].exited = 0; for (unsigned l = 0; l < 32; l++) if (w * 32 + l >= nt) warps[w].exited |= 1u << l; }
         for (unsigned t = 0; t < nt; t++) {
             Fiber *f = fibers[t];
-            f->th.tid = uint3{t, 0, 0}; f->th.bid = uint3{b, 0, 0}; f->th.bdim = block; f->th.gdim = grid; f->state = READY; f->result = 0;
-            getcontext(&f->ctx); f->ctx.uc_stack.ss_sp = f->stack; f->ctx.uc_stack.ss_size = STACK; f->ctx.uc_link = &sched;
+            f->th.tid = uint3{t, 0, 0}; f->th.bid = uint3{b, 0, 0}; f->th.bdim = block; f->th.gdim = grid; f->state = READY; f->result = 0; f->started = false;
+            getcontext(&f->ctx); f->ctx.uc_stack.ss_sp = f->stack; f->ctx.uc_stack.ss_size = STACK; f->ctx.uc_link = nullptr;
             makecontext(&f->ctx, entry, 0);
         }
         for (size_t t = nt; t < fibers.size(); t++) fibers[t]->state = DONE;
@@ -102,7 +103,7 @@ void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &
                 if (f->state != READY) continue;
                 progressed = true;
                 curF = f; cur = &f->th;
-                swapcontext(&sched, &f->ctx);
+                if (!_setjmp(schedJb)) { if (f->started) _longjmp(f->jb, 1); f->started = true; setcontext(&f->ctx); }
                 if (f->state == DONE) {
                     nLive--;
                     Warp &w = warps[t >> 5]; w.exited |= 1u << (t & 31u);
