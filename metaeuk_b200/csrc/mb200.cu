@@ -769,7 +769,11 @@ int mb200_prefilter_resident(mb200_ctx *c) {
         }
     }
     for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK)
-        return fail(status[i] == MB_ST_OVERFLOW ? MB200_E_OVERFLOW : MB200_E_LIMIT, "query %u: prefilter status %u (work list capacity exceeded or sequence too long)", i, status[i]);
+        return status[i] == MB_ST_OVERFLOW
+            ? fail(MB200_E_OVERFLOW, "query %u (%llu residues): more work than the prefilter's lists hold (explicit cap_*_log2, or the second pass' limits: 2^22 window/neighbour items, 2^21 similar k-mers, "
+                   "%llu index hits = where the reference's own overflow path starts) -- lower the sensitivity or shorten the fragment", i,
+                   (unsigned long long)(c->hQoff[i + 1] - c->hQoff[i]), (unsigned long long)(2ull * std::max<uint64_t>(1000000ull, c->nT) - 1))
+            : fail(MB200_E_LIMIT, "query %u: prefilter status %u (sequence of 32768 or more residues)", i, status[i]);
     MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
     c->st.kmers = hs.kmers; c->st.lookups = hs.lookups; c->st.db_matches = hs.dbMatches; c->st.double_hits = hs.doubleHits; c->st.diag_cells = hs.diagCells; c->st.pref_results = hs.results;
     for (int i = 0; i < 16; i++) c->st.pref_phase_cycles[i] = hs.phase[i];
