@@ -332,7 +332,7 @@ def test_cli_reduceredundancy_on_database_files(tmp_path):
     import os
     import subprocess
     from metaeuk_b200 import lib as mlib
-    exe = os.path.join(mlib.PKG, "bin", "mb200")
+    exe = os.environ.get("MB200_CLI_PATH", os.path.join(mlib.PKG, "bin", "mb200"))   # (tests/simt links the same driver against the SIMT emulation)
     c = reflib.load_case("redundancy_family")
     d = str(tmp_path)
     write_db(d + "/dp", [(int(k), v) for k, v in c["dp"].items()], 12)
@@ -447,7 +447,7 @@ def test_cli_modules_on_database_files(tmp_path):
     import os
     import subprocess
     from metaeuk_b200 import lib as mlib
-    exe = os.path.join(mlib.PKG, "bin", "mb200")
+    exe = os.environ.get("MB200_CLI_PATH", os.path.join(mlib.PKG, "bin", "mb200"))   # (tests/simt links the same driver against the SIMT emulation)
     assert os.path.exists(exe), "build the CLI first (__graft_entry__.build)"
     c = reflib.load_case("contigs_sets")
     d = str(tmp_path)
