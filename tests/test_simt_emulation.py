@@ -4,7 +4,7 @@ instructions in C.  TEST INFRASTRUCTURE: it exists so that kernel and launch log
 serial emulation in tests/emu covers the prefilter kernel only); it is never shipped, never measured and never a fallback -- the library refuses nothing here, but
 `mb200_build_kind()` says what it is and bench.py / the loader only ever use the nvcc build.
 
-The whole GPU suite passes on it (about 40 minutes of CPU time: `MB200_LIB_PATH=tests/simt/libmb200_simt.so pytest -m gpu -k "not cli"`); the slice below is sized for the
+The whole GPU suite passes on it (about 20 minutes of CPU time: `MB200_LIB_PATH=tests/simt/libmb200_simt.so pytest -m gpu -k "not cli"`); the slice below is sized for the
 CPU suite: every forward alignment layout + the start-position kernel, the ORF kernels with a non-default genetic code, composition bias off, the exon-chaining and
 redundancy kernels, and the second prefilter pass for fragments that overflow the default work lists."""
 import ctypes as C
