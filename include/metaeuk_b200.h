@@ -144,6 +144,18 @@ int mb200_index_sizes(mb200_ctx *ctx, uint64_t sizes[4] /* n_entries, n_targets,
 int mb200_index_alloc(mb200_ctx *ctx, const uint64_t sizes[4]);
 int mb200_index_buffers(mb200_ctx *ctx, void *dev_ptrs[8], uint64_t nbytes[8], int *n);
 int mb200_index_commit(mb200_ctx *ctx);
+/* Multi-GPU: the query side shards by contig with no data-path collective; the ONE collective of the path replicates the
+ * target index.  mb200_index_broadcast is collective over `nccl_comm` (an ncclComm_t; NULL = the communicator mb200_comm_init created for this
+ * context): the root's index arena (k-mer offsets | index entries | masked residues | unmasked residues | target offsets, one device
+ * allocation) reaches every rank with ONE ncclBroadcast over NVLink/NVSwitch, preceded by a 32-byte size header; communicator setup is not
+ * part of it.  nbytes / ms (optional) return the arena size and the CUDA-event time of the arena broadcast.  NCCL is resolved at run time
+ * (dlopen libnccl.so.2, an already loaded copy is joined), so the library has no link dependency on it.
+ * mb200_comm_unique_id: ncclGetUniqueId into a caller buffer of 128 bytes (rank 0; ship it to the other ranks by any means);
+ * mb200_comm_init: ncclCommInitRank, one rank per context / process;  mb200_comm_init_all: ncclCommInitAll for n contexts of ONE process. */
+int mb200_comm_unique_id(void *id128);
+int mb200_comm_init(mb200_ctx *ctx, const void *id128, int rank, int world);
+int mb200_comm_init_all(mb200_ctx **ctxs, int n);
+int mb200_index_broadcast(mb200_ctx *ctx, void *nccl_comm, int root, uint64_t *nbytes, double *ms);
 
 /* Repeat masking of the targets before indexing = Masker::maskSequence with the prefilter's default flags (--mask 1 --mask-prob 0.9;
  * M/src/commons/Masker.cpp:14-58 -> tantan, M/lib/tantan/tantan.cpp:401-433,478-540; called from IndexBuilder::fillDatabase, IndexBuilder.cpp:84-131).
@@ -211,6 +223,12 @@ int mb200_target_keys_set(mb200_ctx *ctx, const uint32_t *keys, uint32_t n_targe
 /* one 19-column dp_predictions line (Prediction::predictionToBuffer, PredictionParser.h:368-396) from the binary records, with the
  * digits the reference's text round trips leave; returns the length written (without the NUL) or MB200_E_ARG if cap is too small */
 int mb200_text_exon_line(const mb200_call *call, const mb200_pexon *exon, char *buf, size_t cap);
+/* the dp_predictions DB of contigs [0, n_contigs) as one text buffer: for every contig with at least one call ">contigKey\n" followed by the
+ * entry the reference writes for it (the 19-column lines of its calls in order, DBWriter entry without the trailing NUL;
+ * collectoptimalset.cpp:399-418).  contig_keys NULL = keys 0..n-1.  Returns the number of bytes the text needs (written only if <= cap);
+ * this is what bench.py / the tests hash against the reference's DB (tools/refrun.py: digest_entries). */
+int64_t mb200_text_dp_db(const uint64_t *call_off, uint32_t n_contigs, const uint32_t *contig_keys, const mb200_call *calls, const mb200_pexon *exons,
+                         char *buf, size_t cap);
 
 /* reduceredundancy (src/exonpredictor/reduceredundancy.cpp:24-147,273-296) for a batch of contigs: calls of contig c =
  * preds[pred_off[c] .. pred_off[c+1]) in the order of the calledExons entry.  Per call: cluster representative (target key, low coordinate),

@@ -119,17 +119,18 @@ __global__ void __launch_bounds__(128) k_reduce(const MbPred *__restrict__ preds
 // context
 // =====================================================================================================
 template <class T> struct DevBuf {
-    T *p = nullptr; size_t n = 0;
+    T *p = nullptr; size_t n = 0; bool view = false;   // view: a slice of another allocation (the index arena), never freed here
+    void set_view(void *ptr, size_t count) { if (p && !view) cudaFree(p); p = reinterpret_cast<T *>(ptr); n = count; view = true; }
     int alloc(size_t count) {
         if (count <= n && p) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
+        if (p && !view) cudaFree(p);
+        p = nullptr; n = 0; view = false;
         if (count == 0) count = 1;
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
         if (e != cudaSuccess) return fail(MB200_E_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
         n = count; return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
 };
 
 template <class T> struct PinBuf {   // grow-only page-locked host staging buffer
@@ -147,12 +148,57 @@ template <class T> struct PinBuf {   // grow-only page-locked host staging buffe
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
 };
 
+
+// ---- NCCL, resolved at run time: the library has no link-time dependency on libnccl (a process that already loaded one -- e.g. torch's bundled
+//      copy -- is joined through RTLD_NOLOAD so communicators and ours come from the same instance; MB200_NCCL_LIB overrides the name) ----
+#ifndef MB200_SIMT_EMU
+#include <dlfcn.h>
+#include <nccl.h>
+struct NcclApi {
+    void *h = nullptr; bool tried = false;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    NcclApi &N = g_nccl;
+    if (N.h) return 0;
+    if (N.tried) return fail(MB200_E_STATE, "libnccl.so.2 could not be loaded (set MB200_NCCL_LIB)");
+    N.tried = true;
+    const char *env = getenv("MB200_NCCL_LIB");
+    if (env) N.h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!N.h) N.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!N.h) N.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!N.h) return fail(MB200_E_STATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+#define MB_NCCL_SYM(f) do { *(void **)(&N.f) = dlsym(N.h, "nccl" #f); if (!N.f) { N.h = nullptr; return fail(MB200_E_STATE, "nccl" #f " not found in libnccl"); } } while (0)
+    MB_NCCL_SYM(GetUniqueId); MB_NCCL_SYM(CommInitRank); MB_NCCL_SYM(CommInitAll); MB_NCCL_SYM(CommDestroy); MB_NCCL_SYM(CommCount); MB_NCCL_SYM(CommUserRank);
+    MB_NCCL_SYM(Broadcast); MB_NCCL_SYM(GetErrorString);
+#undef MB_NCCL_SYM
+    return 0;
+}
+#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(MB200_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, g_nccl.GetErrorString(r_)); } while (0)
+
+#else
+
+#endif
+
+struct mb200_ctx;
+static void mb200_comm_release(mb200_ctx *c);
+
 struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
     DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
+    DevBuf<unsigned char> dIndexArena; size_t arenaBytes = 0;   // offsets | entries | masked | unmasked residues | target offsets in ONE allocation (one ncclBroadcast replicates it)
+    void *comm = nullptr;                                        // ncclComm_t created by mb200_comm_init (owned)
     DevBuf<int16_t> dSeedMat, dAlnMat; DevBuf<double> dSeedPB, dAlnPB; DevBuf<int8_t> dUng8;
     uint64_t nEntries = 0, totalRes = 0; uint32_t nT = 0; std::vector<uint64_t> hToff; bool haveIndex = false, haveSim3 = false;
     // prefilter scratch
@@ -179,7 +225,7 @@ struct mb200_ctx {
     // predictexons with binary hand-off
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
-    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20;
+    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0;
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -298,7 +344,7 @@ int mb200_ctx_create(int device, mb200_ctx **out) {
 void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
+    mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
@@ -320,6 +366,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
+    else if (n == "orf_key_base") { if (value < 0 || value >= (1ll << 32)) return fail(MB200_E_ARG, "orf_key_base must fit 32 bits"); c->optOrfKeyBase = (uint64_t)value; }   // contig shards: fragment keys count over the whole contig DB
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
     return 0;
 }
@@ -370,9 +417,23 @@ static int check_targets(const uint64_t *off, uint32_t nT) {
     for (uint32_t t = 0; t < nT; t++) if (off[t + 1] - off[t] >= 32768) return fail(MB200_E_LIMIT, "target %u has >= 32768 residues", t);
     return 0;
 }
+// The replicated index lives in one device allocation so that ONE ncclBroadcast moves it (mb200_index_broadcast); the typed buffers are views.
+static int index_arena_alloc(mb200_ctx *c, uint64_t nEntries, uint32_t nT, uint64_t totalRes) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t bOff = al((mb200::KMER_TABLE + 1) * 4), bEnt = al((size_t)std::max<uint64_t>(nEntries, 1) * 8), bSeq = al(totalRes + 16), bTo = al((size_t)(nT + 1) * 8);
+    const size_t total = bOff + bEnt + 2 * bSeq + bTo;
+    TRY(c->dIndexArena.alloc(total));
+    unsigned char *b = c->dIndexArena.p;
+    c->dOffsets.set_view(b, mb200::KMER_TABLE + 1); b += bOff;
+    c->dEntries.set_view(b, std::max<uint64_t>(nEntries, 1)); b += bEnt;
+    c->dTseqM.set_view(b, totalRes + 16); b += bSeq;
+    c->dTseqU.set_view(b, totalRes + 16); b += bSeq;
+    c->dToff.set_view(b, nT + 1);
+    c->arenaBytes = total;
+    return 0;
+}
 static int upload_targets(mb200_ctx *c, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT) {
     const uint64_t tot = off[nT];
-    TRY(c->dTseqM.alloc(tot + 16)); TRY(c->dTseqU.alloc(tot + 16)); TRY(c->dToff.alloc(nT + 1));
     TRY(upload(c->dTseqM.p, masked, tot, c->stream)); TRY(upload(c->dTseqU.p, unmasked, tot, c->stream)); TRY(upload(c->dToff.p, off, (nT + 1) * 8, c->stream));
     c->hToff.assign(off, off + nT + 1); c->nT = nT; c->totalRes = tot; c->minScore.clear();
     return 0;
@@ -395,7 +456,6 @@ static int build_kmer_bits(mb200_ctx *c) {
     c->useBits = true; return 0;
 }
 static int upload_index(mb200_ctx *c, const mb200::TargetIndex &idx) {
-    TRY(c->dOffsets.alloc(idx.offsets.size())); TRY(c->dEntries.alloc(idx.entries.size()));
     TRY(upload(c->dOffsets.p, idx.offsets.data(), idx.offsets.size() * 4, c->stream));
     TRY(upload(c->dEntries.p, idx.entries.data(), idx.entries.size() * 8, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -410,6 +470,7 @@ int mb200_index_build(mb200_ctx *c, const uint8_t *masked, const uint8_t *unmask
     TRY(check_targets(off, nT));
     mb200::TargetIndex idx;
     if (mb200::build_index(masked, off, nT, c->mat.seed, c->par.kmer_thr, idx)) return fail(MB200_E_LIMIT, "index build failed");
+    TRY(index_arena_alloc(c, idx.entries.size(), nT, off[nT]));
     TRY(upload_targets(c, masked, unmasked, off, nT));
     return upload_index(c, idx);
 }
@@ -421,6 +482,7 @@ int mb200_index_import(mb200_ctx *c, const uint64_t *offsets, const uint8_t *ent
     TRY(check_targets(off, nT));
     mb200::TargetIndex idx;
     if (mb200::import_index(offsets, entries6, nEntries, idx)) return fail(MB200_E_LIMIT, "index has >= 2^32 entries");
+    TRY(index_arena_alloc(c, idx.entries.size(), nT, off[nT]));
     TRY(upload_targets(c, masked, unmasked, off, nT));
     return upload_index(c, idx);
 }
@@ -500,9 +562,7 @@ int mb200_index_alloc(mb200_ctx *c, const uint64_t sizes[4]) {
     if (!c) return fail(MB200_E_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
     c->nEntries = sizes[0]; c->nT = (uint32_t)sizes[1]; c->totalRes = sizes[2];
-    TRY(c->dOffsets.alloc(mb200::KMER_TABLE + 1)); TRY(c->dEntries.alloc(c->nEntries)); TRY(c->dTseqM.alloc(c->totalRes + 16)); TRY(c->dTseqU.alloc(c->totalRes + 16));
-    TRY(c->dToff.alloc(c->nT + 1));
-    return 0;
+    return index_arena_alloc(c, c->nEntries, c->nT, c->totalRes);
 }
 int mb200_index_buffers(mb200_ctx *c, void *ptrs[8], uint64_t nbytes[8], int *n) {
     if (!c || !c->dOffsets.p) return fail(MB200_E_STATE, "index buffers not allocated");
@@ -521,6 +581,83 @@ int mb200_index_commit(mb200_ctx *c) {
     c->haveIndex = true; c->minScore.clear();
     return build_kmer_bits(c);
 }
+
+
+// ---- multi-GPU: replicate the index with ONE broadcast of the index arena --------------------------------------------
+#ifndef MB200_SIMT_EMU
+}  // extern "C"
+static void mb200_comm_release(mb200_ctx *c) { if (c->comm && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm); } c->comm = nullptr; }
+extern "C" {
+int mb200_comm_unique_id(void *id128) {
+    if (!id128) return fail(MB200_E_ARG, "null argument");
+    TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NC(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId *>(id128)));
+    return 0;
+}
+int mb200_comm_init(mb200_ctx *c, const void *id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(MB200_E_ARG, "bad argument");
+    TRY(nccl_load());
+    CU(cudaSetDevice(c->device));
+    mb200_comm_release(c);
+    ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, id, rank));
+    c->comm = comm;
+    return 0;
+}
+int mb200_comm_init_all(mb200_ctx **ctxs, int n) {   // one process, n contexts on n devices (bin/mb200 --gpus n)
+    if (!ctxs || n < 1) return fail(MB200_E_ARG, "bad argument");
+    TRY(nccl_load());
+    std::vector<int> dev(n); std::vector<ncclComm_t> comms(n, nullptr);
+    for (int i = 0; i < n; i++) { if (!ctxs[i]) return fail(MB200_E_ARG, "null ctx"); dev[i] = ctxs[i]->device; mb200_comm_release(ctxs[i]); }
+    NC(g_nccl.CommInitAll(comms.data(), n, dev.data()));
+    for (int i = 0; i < n; i++) ctxs[i]->comm = comms[i];
+    return 0;
+}
+// Collective over the communicator (NULL = the one mb200_comm_init created): the root's index (k-mer offsets, index entries, masked and unmasked
+// target residues, target offsets) is replicated on every rank.  Two device-side steps: a 32-byte header (sizes) so the other ranks can size
+// their arena, then ONE ncclBroadcast of the arena itself over NVLink.  Communicator setup is not part of it.  ms (optional) = CUDA-event time
+// of the arena broadcast on this rank's stream.
+int mb200_index_broadcast(mb200_ctx *c, void *ncclComm, int root, uint64_t *nbytes, double *ms) {
+    if (!c) return fail(MB200_E_ARG, "null ctx");
+    TRY(nccl_load());
+    ncclComm_t comm = ncclComm ? (ncclComm_t)ncclComm : (ncclComm_t)c->comm;
+    if (!comm) return fail(MB200_E_STATE, "no communicator (mb200_comm_init, or pass an ncclComm_t)");
+    CU(cudaSetDevice(c->device));
+    int rank = -1, world = 0; NC(g_nccl.CommUserRank(comm, &rank)); NC(g_nccl.CommCount(comm, &world));
+    if (root < 0 || root >= world) return fail(MB200_E_ARG, "root %d out of range", root);
+    if (rank == root && !c->haveIndex) return fail(MB200_E_STATE, "the root has no index");
+    uint64_t hdr[4] = {c->nEntries, c->nT, c->totalRes, (uint64_t)c->par.kmer_thr};
+    TRY(c->dCells.alloc(4));
+    if (rank == root) TRY(upload(c->dCells.p, hdr, sizeof(hdr), c->stream));
+    NC(g_nccl.Broadcast(c->dCells.p, c->dCells.p, sizeof(hdr), ncclUint8, root, comm, c->stream));
+    CU(cudaMemcpyAsync(hdr, c->dCells.p, sizeof(hdr), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (rank != root) {
+        if ((int)hdr[3] != c->par.kmer_thr) return fail(MB200_E_STATE, "the root's index was built with k-mer threshold %d, this context uses %d", (int)hdr[3], c->par.kmer_thr);
+        c->nEntries = hdr[0]; c->nT = (uint32_t)hdr[1]; c->totalRes = hdr[2];
+        TRY(index_arena_alloc(c, c->nEntries, c->nT, c->totalRes));
+    }
+    CU(cudaEventRecord(c->ev0, c->stream));
+    NC(g_nccl.Broadcast(c->dIndexArena.p, c->dIndexArena.p, c->arenaBytes, ncclUint8, root, comm, c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float f = 0; CU(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    if (ms) *ms = f;
+    if (nbytes) *nbytes = c->arenaBytes;
+    if (rank != root) return mb200_index_commit(c);
+    return 0;
+}
+#else
+}  // extern "C"
+static void mb200_comm_release(mb200_ctx *) {}
+extern "C" {
+int mb200_comm_unique_id(void *) { return fail(MB200_E_STATE, "no NCCL in the SIMT emulation"); }
+int mb200_comm_init(mb200_ctx *, const void *, int, int) { return fail(MB200_E_STATE, "no NCCL in the SIMT emulation"); }
+int mb200_comm_init_all(mb200_ctx **, int) { return fail(MB200_E_STATE, "no NCCL in the SIMT emulation"); }
+int mb200_index_broadcast(mb200_ctx *, void *, int, uint64_t *, double *) { return fail(MB200_E_STATE, "no NCCL in the SIMT emulation"); }
+#endif
 
 // ---- query upload + per-residue preparation ----------------------------------------------------------
 // q: host residues, or NULL with qDev = residues already in device memory (fragments produced by mb200_extract_orfs)
@@ -1189,6 +1326,21 @@ int mb200_text_exon_line(const mb200_call *call, const mb200_pexon *exon, char *
     return (int)l.size();
 }
 
+int64_t mb200_text_dp_db(const uint64_t *callOff, uint32_t nContigs, const uint32_t *contigKeys, const mb200_call *calls, const mb200_pexon *exons, char *buf, size_t cap) {
+    if (!callOff || (callOff[nContigs] && (!calls || !exons))) return fail(MB200_E_ARG, "null argument");
+    std::vector<std::string> part(nContigs);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (uint32_t ci = 0; ci < nContigs; ci++) {
+        if (callOff[ci + 1] == callOff[ci]) continue;
+        std::string &s = part[ci]; s = ">" + std::to_string(contigKeys ? contigKeys[ci] : ci) + "\n";
+        for (uint64_t k = callOff[ci]; k < callOff[ci + 1]; k++)
+            for (int x = 0; x < calls[k].n_exons; x++) s += mb200::text_exon_line(calls[k], exons[calls[k].exon_begin + x]);
+    }
+    size_t need = 0; for (const std::string &s : part) need += s.size();
+    if (buf && need <= cap) { size_t w = 0; for (const std::string &s : part) { memcpy(buf + w, s.data(), s.size()); w += s.size(); } }
+    return (int64_t)need;
+}
+
 int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen,
                         uint64_t *callOff, const mb200_call **calls, const mb200_pexon **exons, uint64_t *nExons) {
     if (!c || !nuc || !off || !callOff || !calls || !exons || !nExons) return fail(MB200_E_ARG, "null argument");
@@ -1198,7 +1350,7 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     c->peCalls.clear(); c->peExons.clear(); callOff[0] = 0; *calls = nullptr; *exons = nullptr; *nExons = 0;
     mb200_stats acc; memset(&acc, 0, sizeof(acc));
     const uint32_t launches0 = c->st.launches;
-    uint64_t orfBase = 0;
+    uint64_t orfBase = c->optOrfKeyBase;
     // wall-clock per host phase, printed when MB200_TRACE is set (diagnostic)
     double ph[9] = {0}; auto tp = std::chrono::steady_clock::now();
     auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double, std::milli>(now - tp).count(); tp = now; };

@@ -234,6 +234,22 @@ class Context:
     def index_commit(self):
         self._check(self.L.mb200_index_commit(self.h))
 
+    # ---- the path's one collective, issued by the library itself (NCCL resolved at run time) ----
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._check(self.L.mb200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid, rank, world):
+        self._check(self.L.mb200_comm_init(self.h, C.c_char_p(uid), int(rank), int(world)))
+
+    def index_broadcast(self, root=0, comm=None):
+        """-> (bytes broadcast, CUDA-event ms of the arena broadcast on this rank)"""
+        nb = C.c_uint64(0); ms = C.c_double(0)
+        self._check(self.L.mb200_index_broadcast(self.h, C.c_void_p(comm), int(root), C.byref(nb), C.byref(ms)))
+        self.n_targets = self.index_sizes()[1]
+        return int(nb.value), float(ms.value)
+
     # ---- host-buffer API ----
     def prefilter(self, q, qoff):
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
@@ -315,6 +331,21 @@ class Context:
         if n < 0:
             self._check(n)
         return buf.raw[:n].decode()
+
+    def text_dp_db(self, call_off, calls, exons, contig_keys=None):
+        """the dp_predictions DB of the contigs as canonical text: '>contigKey\\n' + the reference's entry, contigs without calls skipped"""
+        call_off = np.ascontiguousarray(call_off, np.uint64); nc = len(call_off) - 1
+        calls = np.ascontiguousarray(calls, CALL_DTYPE); exons = np.ascontiguousarray(exons, PEXON_DTYPE)
+        keys = np.ascontiguousarray(contig_keys, np.uint32) if contig_keys is not None else None
+        f = self.L.mb200_text_dp_db; f.restype = C.c_int64
+        args = (_p(call_off), C.c_uint32(nc), _p(keys) if keys is not None else None, _p(calls if len(calls) else np.zeros(1, CALL_DTYPE)),
+                _p(exons if len(exons) else np.zeros(1, PEXON_DTYPE)))
+        need = f(*args, None, C.c_size_t(0))
+        if need < 0:
+            self._check(int(need))
+        buf = C.create_string_buffer(int(need) + 1)
+        f(*args, buf, C.c_size_t(int(need)))
+        return buf.raw[:int(need)]
 
     # ---- reduceredundancy ----
     def reduce_redundancy(self, preds, pred_off, exon_keys):
