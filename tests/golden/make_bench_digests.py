@@ -35,7 +35,7 @@ def count_lines(rr, name):
 def main():
     todo = sys.argv[1:] or ["c4s", "c2"]
     out = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    thr = os.cpu_count() or 1
+    thr = int(os.environ.get("MB200_REF_THREADS", os.cpu_count() or 1))
     for spec in todo:
         name, _, limit = spec.partition(":")
         wl = bench.WORKLOADS[name]
