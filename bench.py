@@ -385,7 +385,7 @@ def bench_predict(args, wl, base, rank, world, local, threads):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     ctx.matrices_default()
-    for k, v in (("sw_kernel", args.sw_kernel), ("sw_lane_max_hits", args.lane_max_hits), ("prefilter_config", args.prefilter_config), ("predict_batch_nt", args.batch_nt)):
+    for k, v in (("sw_kernel", args.sw_kernel), ("sw_lane_max_hits", args.lane_max_hits), ("prefilter_config", args.prefilter_config), ("predict_batch_nt", args.batch_nt), ("predict_streams", args.streams)):
         if v:
             ctx.option_set(k, v)
     t0 = time.perf_counter()
@@ -489,6 +489,16 @@ def bench_predict(args, wl, base, rank, world, local, threads):
         base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
         base["roofline_sw"] = {"kernel": "k_sw_* forward + reverse", "bound": "integer ALU (DPX s16x2)", "achieved": base["gcups_sw"] / 1e3, "unit": "TCUPS",
                                "peak": 5.1, "peak_source": "DESIGN.md 4.2: 148 SMs x 4 schedulers x 32 lanes x 2 cells / 7 issue slots per cell pair x 1.9 GHz", "frac": base["gcups_sw"] / 1e3 / 5.1}
+    base["predict_streams"] = int(st.get("pe_streams", 1))
+    if args.phase_stats:     # one extra, untimed, instrumented pass for the per-phase breakdown of k_prefilter
+        ctx.option_set("phase_stats", 1)
+        ctx.predict_exons(nucP, offP, copy=False)
+        ph = ctx.stats().get("pref_phase_cycles") or []
+        ctx.option_set("phase_stats", 0)
+        if sum(ph) > 0:
+            names = ["clear", "P1 windows+scan", "P2 items+scan", "P3 kmers/offsets+scan", "P4 gather hits", "P5 split", "P6-7 double hits", "P8-9 diag scores",
+                     "P10 best diag", "P11-12 threshold/sort", "P13-14 output", "", "", "", "", "between queries"]
+            base["prefilter_phase_pct"] = {names[i]: round(100.0 * ph[i] / sum(ph), 1) for i in range(16) if ph[i]}
     if args.gpus == 1 and not args.no_cpu:
         base["cpu_baseline"] = cpu_baseline_predict(args, wl, prot, poff, threads)
     emit(base)
@@ -906,6 +916,8 @@ def main():
     ap.add_argument("--sw-kernel", type=int, default=0, help="forward alignment kernel variant (diagnostic; 0 = library default)")
     ap.add_argument("--lane-max-hits", type=int, default=0, help="sw_lane_max_hits (diagnostic; 0 = library default)")
     ap.add_argument("--prefilter-config", type=int, default=0, help="prefilter_config (diagnostic; 0 = library default)")
+    ap.add_argument("--streams", type=int, default=0, help="predict_streams (diagnostic; 0 = library default = 2 overlapped worker streams)")
+    ap.add_argument("--phase-stats", action="store_true", help="add the per-phase cycle breakdown of k_prefilter (one extra untimed pass)")
     ap.add_argument("--batch-nt", type=int, default=0, help="predict_batch_nt (diagnostic; 0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

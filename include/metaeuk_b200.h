@@ -115,6 +115,7 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     /* mb200_predict_exons: sums over its contig batches (the ms_* and counter fields above are then sums too) */
     double ms_join, ms_predict;       /* host join of alignments and fragments per contig / the whole call (wall clock) */
     uint64_t pe_batches, pe_contigs, pe_fragments, pe_alignments, pe_calls, pe_exons;
+    uint64_t pe_streams;              /* worker streams the last mb200_predict_exons call used (2: stage times are those of the busier stream) */
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);

@@ -26,6 +26,10 @@
 #include <string>
 #include <chrono>
 #include <vector>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "../../include/metaeuk_b200.h"
 #include "chain_core.cuh"
@@ -225,7 +229,7 @@ struct mb200_ctx {
     // predictexons with binary hand-off
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
-    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0;
+    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[2] = {nullptr, nullptr};
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -344,6 +348,7 @@ int mb200_ctx_create(int device, mb200_ctx **out) {
 void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int k = 0; k < 2; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
     mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
@@ -366,6 +371,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
+    else if (n == "predict_streams") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "predict_streams: 1 or 2"); c->optStreams = (int)value; }
     else if (n == "orf_key_base") { if (value < 0 || value >= (1ll << 32)) return fail(MB200_E_ARG, "orf_key_base must fit 32 bits"); c->optOrfKeyBase = (uint64_t)value; }   // contig shards: fragment keys count over the whole contig DB
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
     return 0;
@@ -1341,77 +1347,182 @@ int64_t mb200_text_dp_db(const uint64_t *callOff, uint32_t nContigs, const uint3
     return (int64_t)need;
 }
 
+// One batch of contigs [b0, b1) on context w (the caller's context, or one of its two workers): ORFs -> prefilter -> alignment -> join -> chaining.
+// Fragment keys count over the whole call, so a batch needs the number of fragments of all batches before it: it publishes its own count right after
+// its ORF stage and asks for its base just before the join (by then the earlier batches have long published theirs).
+struct PeBatchOut { std::vector<mb200_call> calls; std::vector<mb200_pexon> exons; std::vector<uint64_t> callEnd; uint64_t nFrag = 0, nAln = 0; mb200_stats st; };
+struct PeShared {
+    std::mutex mu; std::condition_variable cv; std::vector<int64_t> nFragOf; uint64_t base = 0; bool failed = false;
+    void publish(uint32_t b, uint64_t n) { { std::lock_guard<std::mutex> l(mu); nFragOf[b] = (int64_t)n; } cv.notify_all(); }
+    void abort() { { std::lock_guard<std::mutex> l(mu); failed = true; } cv.notify_all(); }
+    bool orfBase(uint32_t b, uint64_t &out) {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { if (failed) return true; for (uint32_t i = 0; i < b; i++) if (nFragOf[i] < 0) return false; return true; });
+        if (failed) return false;
+        out = base; for (uint32_t i = 0; i < b; i++) out += (uint64_t)nFragOf[i];
+        return true;
+    }
+};
+
+static int predict_batch(mb200_ctx *c, const char *nuc, const uint64_t *off, uint32_t b0, uint32_t b1, int minLen, int maxLen, PeShared &sh, uint32_t batchIdx, PeBatchOut &out, double *ph) {
+    const uint32_t nb = b1 - b0;
+    uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+    auto tp = std::chrono::steady_clock::now();
+    auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double, std::milli>(now - tp).count(); tp = now; };
+    memset(&c->st, 0, sizeof(c->st));
+    TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa)); lap(0);
+    sh.publish(batchIdx, n);
+    TRY(mb200_queries_from_orfs(c)); lap(1);
+    TRY(mb200_prefilter_resident(c)); lap(2);
+    TRY(align_pipeline(c)); lap(3);
+    std::vector<uint32_t> tids; TRY(trace_tids(c, tids)); lap(4);
+    TRY(collect_accepted(c, tids)); lap(5);
+    uint64_t orfBase = 0;
+    if (!sh.orfBase(batchIdx, orfBase)) return fail(MB200_E_INTERNAL, "another contig batch failed");
+    std::vector<mb200_cand> cands; std::vector<uint64_t> candOff, candAln; std::vector<mb200_call> bCalls; std::vector<mb200_exon> bExons; std::vector<uint32_t> bCnt;
+    const auto tj = std::chrono::steady_clock::now();
+    if (mb200::join_by_contig(orfs, n, nb, orfBase, c->hAlnOff.data(), c->hAlns.data(), c->tKeys.empty() ? nullptr : c->tKeys.data(), c->hToff.data(), cands, candOff, candAln))
+        return fail(MB200_E_LIMIT, "more than 2^32 fragments in one mb200_predict_exons call");
+    c->st.ms_join = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count();
+    const uint64_t nc = candOff[nb];
+    bCalls.resize(std::max<uint64_t>(1, 2 * nc)); bExons.resize(std::max<uint64_t>(1, nc)); bCnt.assign(nb, 0);
+    c->st.ms_chain = 0;
+    lap(6);
+    if (nc) TRY(mb200_chain(c, cands.data(), candOff.data(), nb, c->totalRes, bCalls.data(), bCnt.data(), bExons.data()));
+    lap(7);
+    out.calls.clear(); out.exons.clear(); out.callEnd.assign(nb, 0);
+    for (uint32_t ci = 0; ci < nb; ci++) {
+        const uint64_t base = candOff[ci];
+        for (uint32_t k = 0; k < bCnt[ci]; k++) {
+            mb200_call cl = bCalls[2 * base + k]; const uint32_t eb = cl.exon_begin;
+            cl.exon_begin = (uint32_t)out.exons.size();     // relative to the batch; shifted when the batches are concatenated
+            for (int x = 0; x < cl.n_exons; x++) {
+                const mb200_exon &ex = bExons[eb + x]; const mb200_cand &k2 = cands[base + ex.cand_idx]; const mb200_aln &al = c->hAlns[candAln[base + ex.cand_idx]];
+                mb200_pexon pe; memset(&pe, 0, sizeof(pe));
+                pe.orf_key = k2.orf_key; pe.bit_score = k2.bit_score; pe.seq_id_est = al.seq_id_est; pe.t_start = k2.t_start; pe.t_end = k2.t_end; pe.t_len = k2.t_len;
+                pe.contig_start = ex.contig_start; pe.contig_end = ex.contig_end; pe.nuc_len = ex.nuc_len; pe.frag_from = k2.frag_from; pe.frag_to = k2.frag_to; pe.evalue = al.evalue;
+                out.exons.push_back(pe);
+            }
+            out.calls.push_back(cl);
+        }
+        out.callEnd[ci] = out.calls.size();
+    }
+    out.nFrag = n; out.nAln = c->hAlns.size(); out.st = c->st;
+    lap(8);
+    return 0;
+}
+
+// A worker context shares the caller's read-only device tables (views) and owns its stream, query batch, hit lists and scratch: two of them take
+// the contig batches of one mb200_predict_exons call alternately, each on its own host thread, so the host phases of one batch (ORF record scan,
+// alignment epilogue, join, call assembly, PCIe copies) run while the kernels of the other batch occupy the GPU.
+static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
+    if (!w) {
+        w = new mb200_ctx(); w->device = p->device; w->nSM = p->nSM;
+        CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&w->ev0)); CU(cudaEventCreate(&w->ev1)); CU(cudaEventCreate(&w->evT0)); CU(cudaEventCreate(&w->evT1));
+        memset(&w->st, 0, sizeof(w->st));
+    }
+    if (w->par.eval_thr != p->par.eval_thr || w->totalRes != p->totalRes || w->par.translation_table != p->par.translation_table) { w->minScore.clear(); w->haveOrfTab = false; }
+    w->par = p->par; w->mat = p->mat; w->haveMat = p->haveMat; w->ev = p->ev;
+    w->dSim3.set_view(p->dSim3.p, p->dSim3.n); w->dCnt3.set_view(p->dCnt3.p, p->dCnt3.n); w->dOffsets.set_view(p->dOffsets.p, p->dOffsets.n);
+    w->dKmerBits.set_view(p->dKmerBits.p, p->dKmerBits.n); w->useBits = p->useBits; w->dEntries.set_view(p->dEntries.p, p->dEntries.n);
+    w->dTseqM.set_view(p->dTseqM.p, p->dTseqM.n); w->dTseqU.set_view(p->dTseqU.p, p->dTseqU.n); w->dToff.set_view(p->dToff.p, p->dToff.n);
+    w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
+    w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
+    w->nEntries = p->nEntries; w->totalRes = p->totalRes; w->nT = p->nT; w->hToff = p->hToff; w->haveIndex = p->haveIndex; w->haveSim3 = p->haveSim3; w->tKeys = p->tKeys;
+    w->optPrefCfg = p->optPrefCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
+    return 0;
+}
+
 int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint32_t nContigs, int minLen, int maxLen,
                         uint64_t *callOff, const mb200_call **calls, const mb200_pexon **exons, uint64_t *nExons) {
     if (!c || !nuc || !off || !callOff || !calls || !exons || !nExons) return fail(MB200_E_ARG, "null argument");
     if (!c->haveIndex || !c->haveSim3) return fail(MB200_E_STATE, "index / matrices not set");
     if (!c->tKeys.empty() && c->tKeys.size() != c->nT) return fail(MB200_E_STATE, "mb200_target_keys_set: %zu keys for %u targets", c->tKeys.size(), c->nT);
     const auto t0 = std::chrono::steady_clock::now();
+    CU(cudaSetDevice(c->device));
     c->peCalls.clear(); c->peExons.clear(); callOff[0] = 0; *calls = nullptr; *exons = nullptr; *nExons = 0;
-    mb200_stats acc; memset(&acc, 0, sizeof(acc));
-    const uint32_t launches0 = c->st.launches;
-    uint64_t orfBase = c->optOrfKeyBase;
-    // wall-clock per host phase, printed when MB200_TRACE is set (diagnostic)
-    double ph[9] = {0}; auto tp = std::chrono::steady_clock::now();
-    auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double, std::milli>(now - tp).count(); tp = now; };
-    std::vector<mb200_cand> cands; std::vector<uint64_t> candOff, candAln; std::vector<mb200_call> bCalls; std::vector<mb200_exon> bExons; std::vector<uint32_t> bCnt;
-    for (uint32_t b0 = 0; b0 < nContigs;) {
-        uint32_t b1 = b0 + 1;
-        while (b1 < nContigs && off[b1 + 1] - off[b0] <= c->optBatchNt) b1++;
-        const uint32_t nb = b1 - b0;
-        uint64_t n = 0, na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
-        tp = std::chrono::steady_clock::now();
-        TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa)); lap(0);
-        TRY(mb200_queries_from_orfs(c)); lap(1);
-        TRY(mb200_prefilter_resident(c)); lap(2);
-        TRY(align_pipeline(c)); lap(3);
-        std::vector<uint32_t> tids; TRY(trace_tids(c, tids)); lap(4);
-        TRY(collect_accepted(c, tids)); lap(5);
-        const auto tj = std::chrono::steady_clock::now();
-        if (mb200::join_by_contig(orfs, n, nb, orfBase, c->hAlnOff.data(), c->hAlns.data(), c->tKeys.empty() ? nullptr : c->tKeys.data(), c->hToff.data(), cands, candOff, candAln))
-            return fail(MB200_E_LIMIT, "more than 2^32 fragments in one mb200_predict_exons call");
-        acc.ms_join += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count();
-        const uint64_t nc = candOff[nb];
-        bCalls.resize(std::max<uint64_t>(1, 2 * nc)); bExons.resize(std::max<uint64_t>(1, nc)); bCnt.assign(nb, 0);
-        c->st.ms_chain = 0;
-        lap(6);
-        if (nc) TRY(mb200_chain(c, cands.data(), candOff.data(), nb, c->totalRes, bCalls.data(), bCnt.data(), bExons.data()));
-        lap(7);
-        for (uint32_t ci = 0; ci < nb; ci++) {
-            const uint64_t base = candOff[ci];
-            for (uint32_t k = 0; k < bCnt[ci]; k++) {
-                mb200_call cl = bCalls[2 * base + k]; const uint32_t eb = cl.exon_begin;
-                if (c->peExons.size() + (size_t)cl.n_exons >= (1ull << 32)) return fail(MB200_E_LIMIT, "more than 2^32 exons in one mb200_predict_exons call");
-                cl.exon_begin = (uint32_t)c->peExons.size();
-                for (int x = 0; x < cl.n_exons; x++) {
-                    const mb200_exon &ex = bExons[eb + x]; const mb200_cand &k2 = cands[base + ex.cand_idx]; const mb200_aln &al = c->hAlns[candAln[base + ex.cand_idx]];
-                    mb200_pexon pe; memset(&pe, 0, sizeof(pe));
-                    pe.orf_key = k2.orf_key; pe.bit_score = k2.bit_score; pe.seq_id_est = al.seq_id_est; pe.t_start = k2.t_start; pe.t_end = k2.t_end; pe.t_len = k2.t_len;
-                    pe.contig_start = ex.contig_start; pe.contig_end = ex.contig_end; pe.nuc_len = ex.nuc_len; pe.frag_from = k2.frag_from; pe.frag_to = k2.frag_to; pe.evalue = al.evalue;
-                    c->peExons.push_back(pe);
-                }
-                c->peCalls.push_back(cl);
-            }
-            callOff[b0 + ci + 1] = c->peCalls.size();
+    // contig batches of about predict_batch_nt nucleotides
+    std::vector<uint32_t> bnd(1, 0);
+    for (uint32_t b0 = 0; b0 < nContigs;) { uint32_t b1 = b0 + 1; while (b1 < nContigs && off[b1 + 1] - off[b0] <= c->optBatchNt) b1++; bnd.push_back(b1); b0 = b1; }
+    const uint32_t nBatches = (uint32_t)bnd.size() - 1;
+    std::vector<PeBatchOut> outs(nBatches);
+    PeShared sh; sh.nFragOf.assign(nBatches, -1); sh.base = c->optOrfKeyBase;
+    const int nW = (c->optStreams >= 2 && nBatches >= 2) ? 2 : 1;
+    double ph[2][9] = {{0}};
+    double stageSum[2] = {0, 0}; mb200_stats wst[2]; memset(wst, 0, sizeof(wst));
+    int rcs[2] = {0, 0}; std::string errs[2];
+    const mb200_stats before = c->st;
+    auto addStats = [](mb200_stats &a, const mb200_stats &s) {
+        a.kmers += s.kmers; a.lookups += s.lookups; a.db_matches += s.db_matches; a.double_hits += s.double_hits; a.diag_cells += s.diag_cells; a.pref_results += s.pref_results;
+        a.sw_pairs += s.sw_pairs; a.sw_cells_fwd += s.sw_cells_fwd; a.sw_cells_rev += s.sw_cells_rev; a.sw_target_bytes += s.sw_target_bytes;
+        a.query_residues += s.query_residues; a.n_queries += s.n_queries;
+        a.ms_prep += s.ms_prep; a.ms_prefilter += s.ms_prefilter; a.ms_sw_fwd += s.ms_sw_fwd; a.ms_sw_rev += s.ms_sw_rev; a.ms_chain += s.ms_chain; a.ms_h2d += s.ms_h2d; a.ms_join += s.ms_join;
+        a.ms_orf += s.ms_orf; a.ms_orf_host += s.ms_orf_host; a.orf_nucleotides += s.orf_nucleotides; a.orf_fragments += s.orf_fragments; a.orf_residues += s.orf_residues;
+        for (int i = 0; i < 16; i++) a.pref_phase_cycles[i] += s.pref_phase_cycles[i];
+        a.launches += s.launches;
+    };
+    if (nW == 1) {
+        for (uint32_t b = 0; b < nBatches && !rcs[0]; b++) {
+            rcs[0] = predict_batch(c, nuc, off, bnd[b], bnd[b + 1], minLen, maxLen, sh, b, outs[b], ph[0]);
+            if (!rcs[0]) addStats(wst[0], outs[b].st);
         }
-        // sums over the batches
-        const mb200_stats &s = c->st;
-        acc.kmers += s.kmers; acc.lookups += s.lookups; acc.db_matches += s.db_matches; acc.double_hits += s.double_hits; acc.diag_cells += s.diag_cells; acc.pref_results += s.pref_results;
-        acc.sw_pairs += s.sw_pairs; acc.sw_cells_fwd += s.sw_cells_fwd; acc.sw_cells_rev += s.sw_cells_rev; acc.sw_target_bytes += s.sw_target_bytes;
-        acc.query_residues += s.query_residues; acc.n_queries += s.n_queries;
-        acc.ms_prep += s.ms_prep; acc.ms_prefilter += s.ms_prefilter; acc.ms_sw_fwd += s.ms_sw_fwd; acc.ms_sw_rev += s.ms_sw_rev; acc.ms_chain += s.ms_chain; acc.ms_h2d += s.ms_h2d;
-        acc.ms_orf += s.ms_orf; acc.ms_orf_host += s.ms_orf_host; acc.orf_nucleotides += s.orf_nucleotides; acc.orf_fragments += s.orf_fragments; acc.orf_residues += s.orf_residues;
-        for (int i = 0; i < 16; i++) acc.pref_phase_cycles[i] += s.pref_phase_cycles[i];
-        acc.pe_batches++; acc.pe_contigs += nb; acc.pe_fragments += n; acc.pe_alignments += c->hAlns.size();
-        orfBase += n; b0 = b1; lap(8);
+        if (rcs[0]) return rcs[0];
+    } else {
+        for (int k = 0; k < 2; k++) TRY(worker_sync(c, c->workers[k]));
+        std::atomic<uint32_t> next(0);
+        auto run = [&](int k) {
+            mb200_ctx *w = c->workers[k];
+            cudaSetDevice(w->device);
+            for (;;) {
+                const uint32_t b = next.fetch_add(1);
+                if (b >= nBatches) break;
+                { std::lock_guard<std::mutex> l(sh.mu); if (sh.failed) break; }
+                const int rc = predict_batch(w, nuc, off, bnd[b], bnd[b + 1], minLen, maxLen, sh, b, outs[b], ph[k]);
+                if (rc) { rcs[k] = rc; errs[k] = mb200_last_error(); sh.abort(); break; }
+                addStats(wst[k], outs[b].st);
+            }
+        };
+        std::thread t1(run, 1);
+        run(0);
+        t1.join();
+        for (int k = 0; k < 2; k++) if (rcs[k]) return fail(rcs[k], "%s", errs[k].c_str());
     }
+    // concatenate the batches in contig order
+    size_t nCalls = 0, nEx = 0;
+    for (const PeBatchOut &o : outs) { nCalls += o.calls.size(); nEx += o.exons.size(); }
+    if (nEx >= (1ull << 32)) return fail(MB200_E_LIMIT, "more than 2^32 exons in one mb200_predict_exons call");
+    c->peCalls.reserve(nCalls); c->peExons.reserve(nEx);
+    mb200_stats acc; memset(&acc, 0, sizeof(acc));
+    for (uint32_t b = 0; b < nBatches; b++) {
+        const PeBatchOut &o = outs[b];
+        const uint64_t callBase = c->peCalls.size(); const uint32_t exBase = (uint32_t)c->peExons.size();
+        for (mb200_call cl : o.calls) { cl.exon_begin += exBase; c->peCalls.push_back(cl); }
+        c->peExons.insert(c->peExons.end(), o.exons.begin(), o.exons.end());
+        for (uint32_t ci = 0; ci < bnd[b + 1] - bnd[b]; ci++) callOff[bnd[b] + ci + 1] = callBase + o.callEnd[ci];
+        acc.pe_batches++; acc.pe_contigs += bnd[b + 1] - bnd[b]; acc.pe_fragments += o.nFrag; acc.pe_alignments += o.nAln;
+    }
+    // work counters: sums over all batches; stage times (CUDA events): those of the busier worker stream -- with two streams the kernels of two batches share
+    // the GPU, so the per-stream times overlap in wall-clock terms and their sum over both streams would count the same interval twice
+    addStats(acc, wst[0]);
+    if (nW == 2) {
+        mb200_stats both = wst[1];
+        auto dev = [](const mb200_stats &s) { return s.ms_orf + s.ms_prep + s.ms_prefilter + s.ms_sw_fwd + s.ms_sw_rev + s.ms_chain; };
+        const mb200_stats &busy = dev(wst[0]) >= dev(wst[1]) ? wst[0] : wst[1];
+        addStats(acc, both);
+        acc.ms_orf = busy.ms_orf; acc.ms_prep = busy.ms_prep; acc.ms_prefilter = busy.ms_prefilter; acc.ms_sw_fwd = busy.ms_sw_fwd; acc.ms_sw_rev = busy.ms_sw_rev; acc.ms_chain = busy.ms_chain;
+        acc.ms_join = busy.ms_join; acc.ms_h2d = busy.ms_h2d; acc.ms_orf_host = busy.ms_orf_host;
+    }
+    (void)stageSum;
     if (getenv("MB200_TRACE"))
-        fprintf(stderr, "mb200_predict_exons host phases (ms, wall): orfs %.1f install %.1f prefilter %.1f align %.1f tids %.1f accept %.1f join %.1f chain %.1f output %.1f\n",
-                ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7], ph[8]);
+        for (int k = 0; k < nW; k++)
+            fprintf(stderr, "mb200_predict_exons worker %d host phases (ms, wall): orfs %.1f install %.1f prefilter %.1f align %.1f tids %.1f accept %.1f join %.1f chain %.1f output %.1f\n",
+                    k, ph[k][0], ph[k][1], ph[k][2], ph[k][3], ph[k][4], ph[k][5], ph[k][6], ph[k][7], ph[k][8]);
     acc.pe_calls = c->peCalls.size(); acc.pe_exons = c->peExons.size();
-    acc.launches = c->st.launches; acc.ms_reduce = c->st.ms_reduce; acc.ms_d2h = c->st.ms_d2h; acc.ms_host = c->st.ms_host;
+    acc.launches += before.launches; acc.ms_reduce = before.ms_reduce; acc.ms_d2h = before.ms_d2h; acc.ms_host = before.ms_host;
+    acc.pe_streams = (uint64_t)nW;
     acc.ms_predict = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    c->st = acc; (void)launches0;
+    c->st = acc;
     *calls = c->peCalls.empty() ? nullptr : c->peCalls.data(); *exons = c->peExons.empty() ? nullptr : c->peExons.data(); *nExons = c->peExons.size();
     return 0;
 }
