@@ -388,6 +388,8 @@ def bench_predict(args, wl, base, rank, world, local, threads):
     for k, v in (("sw_kernel", args.sw_kernel), ("sw_lane_max_hits", args.lane_max_hits), ("prefilter_config", args.prefilter_config), ("predict_batch_nt", args.batch_nt), ("predict_streams", args.streams)):
         if v:
             ctx.option_set(k, v)
+    for kv in args.opt:
+        ctx.option_set(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.perf_counter()
     prot, poff = gen_proteins(wl["n_prot"])
     idx = {"gen_proteins_s": time.perf_counter() - t0}
@@ -697,6 +699,8 @@ def bench_fragments(args, wl, base, rank, world, local, threads):
     for k, v in (("sw_kernel", args.sw_kernel), ("sw_lane_max_hits", args.lane_max_hits), ("prefilter_config", args.prefilter_config)):
         if v:
             ctx.option_set(k, v)
+    for kv in args.opt:
+        ctx.option_set(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.perf_counter()
     prot, poff = gen_proteins(wl["n_prot"])
     idx = {"gen_proteins_s": time.perf_counter() - t0}
@@ -918,6 +922,7 @@ def main():
     ap.add_argument("--prefilter-config", type=int, default=0, help="prefilter_config (diagnostic; 0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="predict_streams (diagnostic; 0 = library default = 2 overlapped worker streams)")
     ap.add_argument("--phase-stats", action="store_true", help="add the per-phase cycle breakdown of k_prefilter (one extra untimed pass)")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="mb200_option_set(NAME, VALUE) before the run (diagnostic A/B runs; repeatable)")
     ap.add_argument("--batch-nt", type=int, default=0, help="predict_batch_nt (diagnostic; 0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

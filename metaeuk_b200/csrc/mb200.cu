@@ -206,7 +206,7 @@ struct mb200_ctx {
     DevBuf<int16_t> dSeedMat, dAlnMat; DevBuf<double> dSeedPB, dAlnPB; DevBuf<int8_t> dUng8;
     uint64_t nEntries = 0, totalRes = 0; uint32_t nT = 0; std::vector<uint64_t> hToff; bool haveIndex = false, haveSim3 = false;
     // prefilter scratch
-    int nCta = 0; DevBuf<MbPrefScratch> dScratch; DevBuf<unsigned char> dScratchMem; uint32_t capP = 0, capI = 0, capK = 0, capM = 0;
+    int nCta = 0; DevBuf<MbPrefScratch> dScratch, dScratchShort; DevBuf<unsigned char> dScratchMem, dScratchShortMem; uint32_t capP = 0, capI = 0, capK = 0, capM = 0;
     int nCtaRescue = 0; DevBuf<MbPrefScratch> dScratchRescue; DevBuf<unsigned char> dScratchRescueMem; DevBuf<uint32_t> dOrderRescue; uint32_t rescueCapM = 0;   // second pass for queries whose work lists overflowed
     uint64_t rescuedQueries = 0;
     // resident query batch
@@ -230,7 +230,7 @@ struct mb200_ctx {
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[2] = {nullptr, nullptr};
-    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse */, prefCfg = 0 /* config the scratch was sized for */, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
+    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
 };
@@ -272,28 +272,56 @@ static int pref_scratch_build(mb200_ctx *c, int n, uint32_t capP, uint32_t capI,
     return 0;
 }
 
+// ---- prefilter kernel configurations (prefilter_core.cuh): 1 dense, 2 sparse, 3 medium, 4 small
+template <class SH> static int pref_cfg_ctas(int nSM, int *nCta) {
+    int perSM = 0;
+    CU(cudaFuncSetAttribute(k_prefilter<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SH)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter<SH>, SH::Cfg::NT, sizeof(SH)));
+    if (perSM > (int)SH::Cfg::CTAS) perSM = SH::Cfg::CTAS;
+    if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
+    *nCta = nSM * perSM; return 0;
+}
+static int pref_cfg_ctas(int cfg, int nSM, int *nCta) {
+    switch (cfg) {
+    case 1: return pref_cfg_ctas<MbPrefSharedT<MbPrefCfgDense>>(nSM, nCta);
+    case 2: return pref_cfg_ctas<MbPrefSharedT<MbPrefCfgSparse>>(nSM, nCta);
+    case 3: return pref_cfg_ctas<MbPrefSharedT<MbPrefCfgMedium>>(nSM, nCta);
+    default: return pref_cfg_ctas<MbPrefSharedT<MbPrefCfgSmall>>(nSM, nCta);
+    }
+}
+template <class SH> static void pref_launch_t(mb200_ctx *c, const MbPrefTables &T, const MbPrefScratch *scratch, int nCta, const uint32_t *order, uint32_t n, uint32_t *counter) {
+    MB_LAUNCH((k_prefilter<SH>), nCta, SH::Cfg::NT, sizeof(SH), c->stream, T, scratch, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, order, n, c->dUng8.p, c->dHits.p, c->dHitCount.p,
+              c->dStatus.p, c->dStats.p, counter);
+}
+static void pref_launch(mb200_ctx *c, int cfg, const MbPrefTables &T, const MbPrefScratch *scratch, int nCta, const uint32_t *order, uint32_t n, uint32_t *counter) {
+    switch (cfg) {
+    case 1: pref_launch_t<MbPrefSharedT<MbPrefCfgDense>>(c, T, scratch, nCta, order, n, counter); break;
+    case 2: pref_launch_t<MbPrefSharedT<MbPrefCfgSparse>>(c, T, scratch, nCta, order, n, counter); break;
+    case 3: pref_launch_t<MbPrefSharedT<MbPrefCfgMedium>>(c, T, scratch, nCta, order, n, counter); break;
+    default: pref_launch_t<MbPrefSharedT<MbPrefCfgSmall>>(c, T, scratch, nCta, order, n, counter); break;
+    }
+}
+
 static int ctx_alloc_scratch(mb200_ctx *c) {
     const uint32_t capP = 32768, capI = 1u << (c->par.cap_items_log2 ? c->par.cap_items_log2 : 17), capK = 1u << (c->par.cap_kmers_log2 ? c->par.cap_kmers_log2 : 18),
                    capM = 1u << (c->par.cap_hits_log2 ? c->par.cap_hits_log2 : 19);
     if (capK > (1u << 21)) return fail(MB200_E_ARG, "cap_kmers_log2 > 21 (the k-mer ordinal is a 21-bit field)");
     if (capI > (1u << 24) || capM > (1u << 24)) return fail(MB200_E_ARG, "cap_items_log2 / cap_hits_log2 must be <= 24");
-    // dense config for indexes with long k-mer lists (>= 1 entry per k-mer slot on average), sparse config otherwise
-    const int cfg = c->optPrefCfg ? c->optPrefCfg : ((double)c->nEntries >= 1.0 * (double)mb200::KMER_TABLE ? 1 : 2);
-    if (c->nCta && cfg == c->prefCfg && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
-    int perSM = 0;
-    if (cfg == 1) {
-        CU(cudaFuncSetAttribute(k_prefilter<MbPrefSharedT<MbPrefCfgDense>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbPrefSharedT<MbPrefCfgDense>)));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter<MbPrefSharedT<MbPrefCfgDense>>, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>)));
-        if (perSM > (int)MbPrefCfgDense::CTAS) perSM = MbPrefCfgDense::CTAS;
-    } else {
-        CU(cudaFuncSetAttribute(k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbPrefSharedT<MbPrefCfgSparse>)));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>)));
-        if (perSM > (int)MbPrefCfgSparse::CTAS) perSM = MbPrefCfgSparse::CTAS;
-    }
-    if (perSM < 1) return fail(MB200_E_INTERNAL, "prefilter kernel does not fit on an SM");
-    c->nCta = c->nSM * perSM;
+    // dense config for indexes with long k-mer lists (>= 1 entry per k-mer slot on average), sparse config otherwise; short queries may take their own
+    // configuration in a second launch (prefilter_short_len / prefilter_short_config)
+    const bool denseIndex = (double)c->nEntries >= 1.0 * (double)mb200::KMER_TABLE;
+    const int cfg = c->optPrefCfg ? c->optPrefCfg : (denseIndex ? 1 : 2);
+    const int cfgS = (c->optPrefShortLen > 0 && c->optPrefShortCfg != cfg) ? c->optPrefShortCfg : 0;
+    if (c->nCta && cfg == c->prefCfg && cfgS == c->prefCfgShort && capI == c->capI && capK == c->capK && capM == c->capM) return 0;
+    TRY(pref_cfg_ctas(cfg, c->nSM, &c->nCta));
     TRY(pref_scratch_build(c, c->nCta, capP, capI, capM, c->dScratchMem, c->dScratch));
-    c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM; c->prefCfg = cfg;
+    c->nCtaShort = 0;
+    if (cfgS) {
+        // short queries: work lists sized for them (a query longer than prefilter_short_len never gets here; an overflow still takes the second pass)
+        TRY(pref_cfg_ctas(cfgS, c->nSM, &c->nCtaShort));
+        TRY(pref_scratch_build(c, c->nCtaShort, capP, std::min(capI, 1u << 15), std::min(capM, 1u << 17), c->dScratchShortMem, c->dScratchShort));
+    }
+    c->capP = capP; c->capI = capI; c->capK = capK; c->capM = capM; c->prefCfg = cfg; c->prefCfgShort = cfgS;
     return 0;
 }
 
@@ -350,7 +378,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     cudaSetDevice(c->device);
     for (int k = 0; k < 2; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
     mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
-    c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
+    c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchShort.release(); c->dScratchShortMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
@@ -366,7 +394,9 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return fail(MB200_E_ARG, "null argument");
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
-    else if (n == "prefilter_config") { if (value < 0 || value > 2) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense) or 2 (sparse)"); c->optPrefCfg = (int)value; }
+    else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
+    else if (n == "prefilter_short_len") { if (value < 0 || value > 32767) return fail(MB200_E_ARG, "prefilter_short_len: 0 (off) .. 32767"); c->optPrefShortLen = (int)value; }
+    else if (n == "prefilter_short_config") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "prefilter_short_config: 1..4"); c->optPrefShortCfg = (int)value; }
     else if (n == "sw_kernel") { if (value < 1 || value > 5) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane) or 5 (4 + row blocks of an alignment spread over lanes)"); c->optSwKernel = (int)value; }
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
@@ -861,12 +891,15 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     T.capM = (uint32_t)std::min<uint64_t>(c->capM, 2ull * std::max<uint64_t>(1000000ull, c->nT) - 1);   // beyond that the reference switches to its own overflow path (QueryMatcher.cpp:43,280-305)
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
-        if (c->prefCfg == 1)
-            MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgDense>>), c->nCta, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream, 
-                T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
-        else
-            MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>), c->nCta, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream, 
-                T, c->dScratch.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrder.p, nQ, c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+        // queries are taken longest first (dOrder); with a short-query configuration the order splits at prefilter_short_len
+        uint32_t pSplit = nQ;
+        if (c->prefCfgShort) { uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const uint32_t q = c->hOrder[mid];
+                                                                              if ((uint32_t)(c->hQoff[q + 1] - c->hQoff[q]) <= (uint32_t)c->optPrefShortLen) hi = mid; else lo = mid + 1; } pSplit = lo; }
+        if (pSplit) pref_launch(c, c->prefCfg, T, c->dScratch.p, c->nCta, c->dOrder.p, pSplit, c->dCounter.p);
+        if (pSplit < nQ) {
+            MbPrefTables TS = T; TS.capI = std::min(T.capI, 1u << 15); TS.capM = std::min(T.capM, 1u << 17);
+            pref_launch(c, c->prefCfgShort, TS, c->dScratchShort.p, c->nCtaShort, c->dOrder.p + pSplit, nQ - pSplit, c->dCounter.p + 1); c->st.launches++;
+        }
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -897,12 +930,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
             CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream));
             MbPrefTables T2 = T; T2.capI = capI2; T2.capK = capK2; T2.capM = capM2;
             CU(cudaEventRecord(c->ev0, c->stream));
-            if (c->prefCfg == 1)
-                MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgDense>>), nR, MbPrefCfgDense::NT, sizeof(MbPrefSharedT<MbPrefCfgDense>), c->stream, 
-                    T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
-            else
-                MB_LAUNCH((k_prefilter<MbPrefSharedT<MbPrefCfgSparse>>), nR, MbPrefCfgSparse::NT, sizeof(MbPrefSharedT<MbPrefCfgSparse>), c->stream, 
-                    T2, c->dScratchRescue.p, c->dQ.p, c->dQoff.p, c->dBias.p, c->dCorr.p, c->dOrderRescue.p, (uint32_t)again.size(), c->dUng8.p, c->dHits.p, c->dHitCount.p, c->dStatus.p, c->dStats.p, c->dCounter.p);
+            pref_launch(c, c->prefCfg, T2, c->dScratchRescue.p, nR, c->dOrderRescue.p, (uint32_t)again.size(), c->dCounter.p);
             CU(cudaGetLastError());
             CU(cudaEventRecord(c->ev1, c->stream));
             CU(cudaMemcpyAsync(status, c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1430,7 +1458,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
     w->nEntries = p->nEntries; w->totalRes = p->totalRes; w->nT = p->nT; w->hToff = p->hToff; w->haveIndex = p->haveIndex; w->haveSim3 = p->haveSim3; w->tKeys = p->tKeys;
-    w->optPrefCfg = p->optPrefCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
+    w->optPrefCfg = p->optPrefCfg; w->optPrefShortLen = p->optPrefShortLen; w->optPrefShortCfg = p->optPrefShortCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
     return 0;
 }
 

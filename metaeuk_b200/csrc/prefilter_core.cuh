@@ -71,6 +71,8 @@ template <int NT_, int CTAS_, int NSLOT_LOG_, int SM_I_, int SM_NZ_LOG_> struct 
 };
 typedef MbPrefCfg<512, 2, 17, 4096, 12> MbPrefCfgDense;
 typedef MbPrefCfg<256, 4, 15, 2048, 10> MbPrefCfgSparse;
+typedef MbPrefCfg<256, 4, 16, 2048, 11> MbPrefCfgMedium;   // short fragments against a dense index: four barrier domains per SM, occupancy map and hash table sized for a few thousand hits
+typedef MbPrefCfg<128, 8, 15, 1024, 10> MbPrefCfgSmall;    // eight queries per SM, four warps each
 
 template <class CFG> struct MbPrefSharedT {
     typedef CFG Cfg;
