@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(SH::Cfg::NT, SH::Cfg::CTAS) k_prefilter(MbPref
 }
 
 #include "sw_kernels.cuh"
+#include "sw_stream.cuh"
 #include "orf_kernels.cuh"
 
 // ---- exon chaining: one contig per thread -----------------------------------------------------------
@@ -217,6 +218,7 @@ struct mb200_ctx {
     // align
     DevBuf<uint32_t> dPairOff, dChunkOff, dLaneOff, dWaveOff, dPassList, dHE, dFlatSeq; DevBuf<int32_t> dScore, dMinScore; DevBuf<SwTraceOut> dTrace; DevBuf<MbPrefHit> dFlatHits;
     DevBuf<uint64_t> dHitOff64; DevBuf<uint16_t> dPerm; DevBuf<uint32_t> dBnd;
+    DevBuf<SwPair> dSwDesc, dSwDescRev; DevBuf<SwPassRec> dPassRec; DevBuf<SwTraceOut> dTrace2; DevBuf<uint32_t> dFallback;   // sw_kernel 6 (sw_stream.cuh)
     std::vector<int> minScore;   // per query length, -2 = not computed
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
@@ -230,9 +232,10 @@ struct mb200_ctx {
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[2] = {nullptr, nullptr};
-    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 5, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
+    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
+    cudaStream_t swSide[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t swFork = nullptr, swJoin[4] = {nullptr, nullptr, nullptr, nullptr};   // the alignment classes of one batch run side by side
 };
 
 static int upload(void *dst, const void *src, size_t bytes, cudaStream_t s) {
@@ -377,11 +380,14 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (int k = 0; k < 2; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
+    for (int k = 0; k < 4; k++) { if (c->swSide[k]) cudaStreamDestroy(c->swSide[k]); if (c->swJoin[k]) cudaEventDestroy(c->swJoin[k]); c->swSide[k] = nullptr; c->swJoin[k] = nullptr; }
+    if (c->swFork) { cudaEventDestroy(c->swFork); c->swFork = nullptr; }
     mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchShort.release(); c->dScratchShortMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
     c->dFlatSeq.release(); c->dScore.release(); c->dMinScore.release(); c->dTrace.release(); c->dFlatHits.release(); c->dHitOff64.release(); c->dPerm.release(); c->dBnd.release();
+    c->dSwDesc.release(); c->dSwDescRev.release(); c->dPassRec.release(); c->dTrace2.release(); c->dFallback.release();
     c->pFlatHits.release(); c->pOff.release(); c->pStatus.release(); c->pOrfRecs.release(); c->pOrfAa.release();
     c->dChCand.release(); c->dChOff.release(); c->dChPE.release(); c->dChOp.release(); c->dChOm.release(); c->dChCallCnt.release(); c->dChRows.release(); c->dChCalls.release();
     c->dChEx.release(); c->dChExCnt.release(); c->pChCalls.release(); c->pChEx.release(); c->pChCnt.release();
@@ -397,7 +403,8 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
     else if (n == "prefilter_short_len") { if (value < 0 || value > 32767) return fail(MB200_E_ARG, "prefilter_short_len: 0 (off) .. 32767"); c->optPrefShortLen = (int)value; }
     else if (n == "prefilter_short_config") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "prefilter_short_config: 1..4"); c->optPrefShortCfg = (int)value; }
-    else if (n == "sw_kernel") { if (value < 1 || value > 5) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane) or 5 (4 + row blocks of an alignment spread over lanes)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_kernel") { if (value < 1 || value > 6) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane), 5 (4 + row blocks of an alignment spread over lanes) or 6 (streams of pairs over persistent lane groups, end cells recorded by the forward pass)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_ring") { if (value < -1 || value > 16) return fail(MB200_E_ARG, "sw_ring: -1 (private profile per slot), 0 (auto) or 1..16 ring profiles per warp"); c->optSwRing = (int)value; }
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
@@ -959,6 +966,162 @@ static int min_score_for(mb200_ctx *c, uint32_t L) {
 }
 
 
+// ---- sw_kernel 6 (default): forward and reverse passes as streams of (query, two targets) pairs over persistent lane groups (sw_stream.cuh).
+// Shared-memory geometry of one launch: every warp has a 32-descriptor queue, the descriptors of the pairs in flight, ring tags and P query profiles of
+// 22 * stride + 16 bytes (stride = 32 * nb rows).
+struct SwStreamGeom { uint32_t nb, stride, slots, P, warpBytes; int W, mode; size_t smem; };
+static SwStreamGeom sw_stream_geom(uint32_t nb, int mode, double pairsPerQuery, int ringOpt) {
+    SwStreamGeom g; g.nb = nb; g.stride = 32u * nb; g.slots = 32u / nb; g.mode = mode;
+    const uint32_t entry = 22u * g.stride + 16u, fixed = MB_SWS_QUEUE_BYTES + MB_SWS_INFO_BYTES + MB_SWS_TAG_BYTES;
+    if (mode == 0) {
+        // ring: the pairs of a query are neighbours in the list, so slots / (pairs per query) profiles are live at a time; a few spare ones keep
+        // a slot from waiting for a free profile
+        uint32_t P = ringOpt > 0 ? (uint32_t)ringOpt : (uint32_t)std::ceil((double)g.slots / std::max(1.0, pairsPerQuery)) + 3u;
+        P = std::min(std::min(P, g.slots), 16u); if (P < 1) P = 1;
+        g.P = P;
+    } else g.P = g.slots;
+    g.warpBytes = fixed + g.P * entry;
+    int W = (int)((108u * 1024u) / g.warpBytes);                 // two CTAs per SM when they fit
+    if (W < 2) W = (int)((216u * 1024u) / g.warpBytes);
+    g.W = std::max(1, std::min(W, MB_SWS_MAXWARPS));
+    g.smem = (size_t)g.W * g.warpBytes;
+    return g;
+}
+static int sw_stream_launch(mb200_ctx *c, cudaStream_t st, const SwStreamGeom &g, const SwPair *desc, uint32_t nDesc, SwPassRec *passRec, uint32_t *nPass, uint32_t passCap,
+                            uint32_t *counter, unsigned long long *cells, uint32_t *err, SwTraceOut *outs) {
+    int perSM = 1;
+    if (g.mode == 0) { CU(cudaFuncSetAttribute(k_sw_stream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_stream<0>, g.W * 32, g.smem)); }
+    else if (g.mode == 1) { CU(cudaFuncSetAttribute(k_sw_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_stream<1>, g.W * 32, g.smem)); }
+    else { CU(cudaFuncSetAttribute(k_sw_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_stream<2>, g.W * 32, g.smem)); }
+    if (perSM < 1) perSM = 1;
+    const uint64_t perCta = (uint64_t)g.slots * g.W;               // pairs a CTA works on at a time
+    uint64_t blocks = (uint64_t)c->nSM * perSM; const uint64_t need = (nDesc + perCta - 1) / perCta;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+#define MB_SWS_ARGS desc, nDesc, g.nb, g.stride, g.P, g.warpBytes, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend, passRec, nPass, passCap, counter, cells, err, outs
+    if (g.mode == 0) MB_LAUNCH((k_sw_stream<0>), (unsigned)blocks, g.W * 32, g.smem, st, MB_SWS_ARGS);
+    else if (g.mode == 1) MB_LAUNCH((k_sw_stream<1>), (unsigned)blocks, g.W * 32, g.smem, st, MB_SWS_ARGS);
+    else MB_LAUNCH((k_sw_stream<2>), (unsigned)blocks, g.W * 32, g.smem, st, MB_SWS_ARGS);
+#undef MB_SWS_ARGS
+    CU(cudaGetLastError()); c->st.launches++;
+    return 0;
+}
+static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t maxT, bool usePerm) {
+    const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
+    auto lenAt = [&](uint32_t p) { const uint32_t q = c->hOrder[p]; return (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]); };
+    auto firstLE = [&](uint32_t x) { uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lenAt(mid) <= x) hi = mid; else lo = mid + 1; } return lo; };
+    // classes by number of 32-row blocks: class nb = positions [B[nb], B[nb - 1]) of the length-sorted order (lengths 32 (nb - 1) + 1 .. 32 nb); B[32] = pLong
+    uint32_t B[33], hOff[33];
+    for (uint32_t nb = 1; nb <= 32; nb++) B[nb] = firstLE(32u * nb);
+    B[0] = nQ;
+    for (uint32_t k = 0; k <= 32; k++) CU(cudaMemcpyAsync(&hOff[k], c->dLaneOff.p + B[k], 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "scan"));
+    const uint32_t nDescTotal = hOff[0] - hOff[32];
+    uint32_t *dNPass = c->dCounter.p + 32, *dErr = c->dCounter.p + 33;
+    TRY(c->dSwDesc.alloc(nDescTotal)); TRY(c->dPassRec.alloc(nPairs));
+    CU(cudaEventRecord(c->ev0, c->stream));   // ms_sw_fwd = hit permutation + descriptors + forward kernels
+    if (usePerm) {
+        TRY(c->dPerm.alloc((size_t)nQ * maxHits));
+        MB_LAUNCH((k_perm_by_len), c->nSM * 8, 128, 0, c->stream, c->dHits.p, c->dHitCount.p, c->dToff.p, nQ, maxHits, c->dPerm.p);
+        CU(cudaGetLastError()); c->st.launches++;
+    }
+    // Launch groups: all block counts that give the same number of slots per warp (32 / nb) share one launch with the geometry of the largest -- a query
+    // of 17..32 blocks has the warp to itself either way.  The groups are independent, so they run side by side on up to four streams (few long queries:
+    // a launch of its own would leave most SMs idle behind the last long alignment).
+    if (!c->swFork) {
+        CU(cudaEventCreateWithFlags(&c->swFork, cudaEventDisableTiming));
+        for (int k = 0; k < 4; k++) { CU(cudaStreamCreateWithFlags(&c->swSide[k], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->swJoin[k], cudaEventDisableTiming)); }
+    }
+    static const uint32_t grpHi[10] = {32, 16, 10, 8, 6, 5, 4, 3, 2, 1}, grpLo[10] = {17, 11, 9, 7, 6, 5, 4, 3, 2, 1};
+    for (int gI = 0; gI < 10; gI++) {
+        const uint32_t pB = B[grpHi[gI]], pE = B[grpLo[gI] - 1], nDesc = hOff[grpLo[gI] - 1] - hOff[grpHi[gI]];
+        if (pB >= pE || nDesc == 0) continue;
+        MB_LAUNCH((k_sw_desc_fwd), (unsigned)std::min<uint64_t>((uint64_t)c->nSM * 8, (nDesc + 255) / 256), 256, 0, c->stream, c->dOrder.p, c->dLaneOff.p, pB, pE, c->dHits.p, c->dHitCount.p,
+                  usePerm ? c->dPerm.p : nullptr, maxHits, c->dQoff.p, c->dToff.p, c->dMinScore.p, c->dSwDesc.p + (hOff[grpHi[gI]] - hOff[32]));
+        CU(cudaGetLastError()); c->st.launches++;
+    }
+    CU(cudaEventRecord(c->swFork, c->stream));
+    bool used[4] = {false, false, false, false}; int nLaunch = 0;
+    for (int gI = 0; gI < 10; gI++) {
+        const uint32_t pB = B[grpHi[gI]], pE = B[grpLo[gI] - 1], base = hOff[grpHi[gI]] - hOff[32], nDesc = hOff[grpLo[gI] - 1] - hOff[grpHi[gI]];
+        if (pB >= pE || nDesc == 0) continue;
+        const double ppq = (double)nDesc / (double)(pE - pB);
+        const SwStreamGeom g = sw_stream_geom(grpHi[gI], (c->optSwRing >= 0 && ppq >= 2.5) ? 0 : 1, ppq, c->optSwRing);
+        const int k = nLaunch++ & 3;
+        if (!used[k]) { CU(cudaStreamWaitEvent(c->swSide[k], c->swFork, 0)); used[k] = true; }
+        TRY(sw_stream_launch(c, c->swSide[k], g, c->dSwDesc.p + base, nDesc, c->dPassRec.p, dNPass, nPairs, c->dCounter.p + 64 + gI, c->dCells.p, dErr, nullptr));
+    }
+    for (int k = 0; k < 4; k++) if (used[k]) { CU(cudaEventRecord(c->swJoin[k], c->swSide[k])); CU(cudaStreamWaitEvent(c->stream, c->swJoin[k], 0)); }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    uint32_t hn[2] = {0, 0}; unsigned long long hc[2] = {0, 0};
+    CU(cudaMemcpyAsync(hn, dNPass, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "forward alignment kernel"));
+    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
+    if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
+    const uint32_t nPass = hn[0];
+    // queries longer than 1024 residues: every hit goes straight to the 32-bit kernel (forward + reverse; the host applies the e-value test)
+    std::vector<uint32_t> extra;
+    if (pLong > 0) {
+        std::vector<uint32_t> hcnt(nQ);
+        CU(cudaMemcpy(hcnt.data(), c->dHitCount.p, (size_t)nQ * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t p = 0; p < pLong; p++) { const uint32_t q = c->hOrder[p]; for (uint32_t k = 0; k < hcnt[q]; k++) extra.push_back(q * maxHits + k); }
+    }
+    if (!nPass && extra.empty()) return 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    uint32_t hcls[MB_SWS_REV_CLASSES + 1]; memset(hcls, 0, sizeof(hcls));
+    uint32_t *dCls = c->dCounter.p + 100, *dNFb = c->dCounter.p + 100 + MB_SWS_REV_CLASSES;
+    TRY(c->dFallback.alloc((size_t)nPass + extra.size()));
+    if (nPass) {
+        // reverse pass: the forward kernels recorded the end cell; descriptors binned by the number of row blocks of the query prefix [0..qEnd]
+        TRY(c->dTrace.alloc(nPass)); TRY(c->dSwDescRev.alloc((size_t)MB_SWS_REV_CLASSES * nPass));
+        MB_LAUNCH((k_sw_desc_rev), (unsigned)std::min<uint64_t>((uint64_t)c->nSM * 8, ((uint64_t)nPass + 255) / 256), 256, 0, c->stream, c->dPassRec.p, nPass, c->dHits.p, maxHits, c->dToff.p,
+                  c->dSwDescRev.p, nPass, dCls, c->dFallback.p, dNFb, c->dTrace.p);
+        CU(cudaGetLastError()); c->st.launches++;
+        CU(cudaMemcpyAsync(hcls, dCls, sizeof(hcls), cudaMemcpyDeviceToHost, c->stream));
+        TRY(sync_check(c, "reverse descriptors"));
+        CU(cudaEventRecord(c->swFork, c->stream));
+        bool usedR[4] = {false, false, false, false};
+        for (int cl = 0; cl < MB_SWS_REV_CLASSES; cl++) {
+            if (!hcls[cl]) continue;
+            const SwStreamGeom g = sw_stream_geom(cl < 4 ? (uint32_t)cl + 1u : 8u, 2, 1.0, 0);
+            const int k = cl & 3;
+            if (!usedR[k]) { CU(cudaStreamWaitEvent(c->swSide[k], c->swFork, 0)); usedR[k] = true; }
+            TRY(sw_stream_launch(c, c->swSide[k], g, c->dSwDescRev.p + (size_t)cl * nPass, hcls[cl], nullptr, nullptr, 0, c->dCounter.p + 110 + cl, c->dCells.p + 1, dErr, c->dTrace.p));
+        }
+        for (int k = 0; k < 4; k++) if (usedR[k]) { CU(cudaEventRecord(c->swJoin[k], c->swSide[k])); CU(cudaStreamWaitEvent(c->stream, c->swJoin[k], 0)); }
+    }
+    uint32_t nFb = hcls[MB_SWS_REV_CLASSES];
+    if (!extra.empty()) { TRY(upload(c->dFallback.p + nFb, extra.data(), extra.size() * 4, c->stream)); nFb += (uint32_t)extra.size(); }
+    if (nFb) {
+        // 32-bit cells, forward + reverse: query prefixes of more than 256 rows, scores beyond the packed 16-bit range, queries of more than 1024 residues
+        const int blocks = c->nSM * 4; const size_t nWarps = (size_t)blocks * 4;
+        TRY(c->dTrace2.alloc(nFb)); TRY(c->dHE.alloc(nWarps * maxT * 32));
+        MB_LAUNCH((k_sw_trace2), blocks, 128, 0, c->stream, c->dFallback.p, nFb, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                  c->par.gap_open, c->par.gap_extend, c->dHE.p, maxT, c->dTrace2.p, c->dCounter.p + 40, c->dCells.p + 1);
+        CU(cudaGetLastError()); c->st.launches++;
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->hTrace.resize((size_t)nPass + nFb);
+    if (nPass) CU(cudaMemcpyAsync(c->hTrace.data(), c->dTrace.p, (size_t)nPass * sizeof(SwTraceOut), cudaMemcpyDeviceToHost, c->stream));
+    if (nFb) CU(cudaMemcpyAsync(c->hTrace.data() + nPass, c->dTrace2.p, (size_t)nFb * sizeof(SwTraceOut), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    TRY(sync_check(c, "reverse alignment kernels"));
+    CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1];
+    size_t w = 0;
+    for (size_t r = 0; r < c->hTrace.size(); r++) {
+        const SwTraceOut &o = c->hTrace[r];
+        if (o.slot == 0xFFFFFFFFu) continue;     // handed to the 32-bit kernel (its own record follows)
+        if (o.flag & 1) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (query %u, hit %u)", o.slot / maxHits, o.slot % maxHits);
+        if (o.flag & 2) return fail(MB200_E_LIMIT, "alignment score of query %u against its hit %u exceeds 65000 (32-bit fallback kernel limit)", o.slot / maxHits, o.slot % maxHits);
+        c->hTrace[w++] = o;
+    }
+    c->hTrace.resize(w);
+    __gnu_parallel::sort(c->hTrace.begin(), c->hTrace.end(), [](const SwTraceOut &a, const SwTraceOut &b) { return a.slot < b.slot; });
+    return 0;
+}
+
+
 // Gapped alignment of the resident hit lists (dHits / dHitCount).  Leaves c->hTrace = every alignment whose score passes the
 // e-value gate (score, start/end coordinates), sorted by slot = query * maxHits + rank.
 static int align_pipeline(mb200_ctx *c) {
@@ -967,11 +1130,16 @@ static int align_pipeline(mb200_ctx *c) {
     c->st.sw_pairs = 0; c->st.sw_cells_fwd = c->st.sw_cells_rev = 0; c->st.ms_sw_fwd = c->st.ms_sw_rev = 0; c->st.sw_target_bytes = 0;
     if (nQ == 0) { c->haveAln = true; return 0; }
     if ((uint64_t)nQ * maxHits >= (1ull << 32)) return fail(MB200_E_LIMIT, "n_queries * max_res_list_len must be < 2^32 per call");
-    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dLaneOff.alloc(nQ + 1)); TRY(c->dWaveOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(64)); TRY(c->dCells.alloc(2));
-    CU(cudaMemsetAsync(c->dCounter.p, 0, 64 * 4, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 16, c->stream));
+    TRY(c->dPairOff.alloc(nQ + 1)); TRY(c->dChunkOff.alloc(nQ + 1)); TRY(c->dLaneOff.alloc(nQ + 1)); TRY(c->dWaveOff.alloc(nQ + 1)); TRY(c->dCounter.alloc(128)); TRY(c->dCells.alloc(2));
+    CU(cudaMemsetAsync(c->dCounter.p, 0, 128 * 4, c->stream)); CU(cudaMemsetAsync(c->dCells.p, 0, 16, c->stream));
     // sw_kernel 4: queries of at most 64 residues with at most sw_lane_max_hits hits go to k_sw_lanes (one (query, 2 hits) item per lane), the rest to k_sw_rows2
     // sw_kernel 5: the other queries of at most 1024 residues go to k_sw_wave (the row blocks of one alignment on neighbouring lanes)
-    const bool laneMode = c->optSwKernel >= 4 && maxHits <= 1024, waveMode = c->optSwKernel == 5 && maxHits <= 1024;
+    // sw_kernel 6 (default): every query of at most 1024 residues goes to the stream kernels (sw_stream.cuh); needs 32-bit target offsets and a gap-open penalty within the cell bias
+    const bool streamMode = c->optSwKernel == 6 && c->totalRes < (1ull << 32) && c->par.gap_open >= 0 && c->par.gap_open <= MB_SWS_BIAS && c->par.gap_extend >= 0 && c->par.gap_extend <= MB_SWS_BIAS;
+    const bool laneMode = !streamMode && c->optSwKernel >= 4 && maxHits <= 1024, waveMode = !streamMode && c->optSwKernel >= 5 && maxHits <= 1024;
+    if (streamMode)   // laneOff = scan of ceil(hits / 2) over the queries of at most 1024 residues, in length-sorted order
+        MB_LAUNCH((k_scan_counts), 4, MB_CTA_THREADS, 0, c->stream, c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 1024u, 0xFFFFFFFFu, 0u);
+    else
     MB_LAUNCH((k_scan_counts), 4, MB_CTA_THREADS, 0, c->stream, c->dHitCount.p, c->dOrder.p, nQ, c->dPairOff.p, c->dChunkOff.p, c->dLaneOff.p, c->dWaveOff.p, c->dQoff.p, 64u,
                                                        laneMode ? (uint32_t)c->optLaneMaxHits : 0u, waveMode ? 1024u : 0u);
     CU(cudaGetLastError());
@@ -987,8 +1155,16 @@ static int align_pipeline(mb200_ctx *c) {
         if (ms[L] == 0x7fffffff) { const int v = min_score_for(c, L); if (v < 0) return fail(MB200_E_INTERNAL, "e-value not monotone in the score for query length %u", L); ms[L] = v; }
     }
     TRY(c->dMinScore.alloc(ms.size())); TRY(upload(c->dMinScore.p, ms.data(), ms.size() * 4, c->stream));
-    TRY(c->dScore.alloc((size_t)nQ * maxHits)); TRY(c->dPassList.alloc(nPairs));
     const bool usePerm = maxHits <= 1024;
+    if (streamMode) {
+        auto lenAt0 = [&](uint32_t p) { const uint32_t q = c->hOrder[p]; return (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]); };
+        uint32_t lo = 0, hi = nQ; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lenAt0(mid) <= 1024u) hi = mid; else lo = mid + 1; }
+        uint32_t maxT0 = 1; for (uint32_t t = 0; t < c->nT; t++) maxT0 = std::max<uint32_t>(maxT0, (uint32_t)(c->hToff[t + 1] - c->hToff[t]));
+        TRY(align_stream(c, nPairs, lo, maxT0, usePerm));
+        c->haveAln = true;
+        return 0;
+    }
+    TRY(c->dScore.alloc((size_t)nQ * maxHits)); TRY(c->dPassList.alloc(nPairs));
     CU(cudaEventRecord(c->ev0, c->stream));   // ms_sw_fwd = hit permutation + forward kernels
     if (usePerm) {
         TRY(c->dPerm.alloc((size_t)nQ * maxHits));
@@ -1458,7 +1634,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
     w->nEntries = p->nEntries; w->totalRes = p->totalRes; w->nT = p->nT; w->hToff = p->hToff; w->haveIndex = p->haveIndex; w->haveSim3 = p->haveSim3; w->tKeys = p->tKeys;
-    w->optPrefCfg = p->optPrefCfg; w->optPrefShortLen = p->optPrefShortLen; w->optPrefShortCfg = p->optPrefShortCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
+    w->optPrefCfg = p->optPrefCfg; w->optPrefShortLen = p->optPrefShortLen; w->optPrefShortCfg = p->optPrefShortCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optSwRing = p->optSwRing; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
     return 0;
 }
 

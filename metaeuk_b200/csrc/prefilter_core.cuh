@@ -274,12 +274,14 @@ MB_DEV uint32_t mb_pref_expand(const MbPrefTables &T, const MbPrefScratch &W, SH
             for (int u = 0; u < 4; u++) a1[u] = ok[u] ? T.sim3[ad[u]] : 0u;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                km[u] = i0v[u] + (a1[u] >> 16) * 8000u; nz[u] = false;
-                if (ok[u]) nz[u] = T.kmerBits ? ((T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u) : (T.offsets[km[u] + 1] != T.offsets[km[u]]);
+                km[u] = i0v[u] + (a1[u] >> 16) * 8000u; nz[u] = ok[u];
+                if (ok[u] && T.kmerBits) nz[u] = (T.kmerBits[km[u] >> 5] >> (km[u] & 31u)) & 1u;
             }
+            // sparse index: only the k-mers whose list is non-empty (bitmap) are listed, in no particular order.  Dense index (no bitmap: nearly every
+            // k-mer has a list): every k-mer is listed at its own ordinal and the gather phase finds the few empty lists itself.
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t n = cta_append_slot(&sh->cnt[7], nz[u]);
+                const uint32_t n = T.kmerBits ? cta_append_slot(&sh->cnt[7], nz[u]) : k0 + u;
                 if (nz[u]) {
                     const uint64_t w = ((uint64_t)pv[u] << 47) | ((uint64_t)(k0 + u) << 26) | km[u];   // window[17] | k[21] | k-mer[26]
                     if (n < SH::Cfg::SM_NZ) sh->sNz[n] = w;
@@ -314,68 +316,101 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
                      : smP ? mb_pref_expand<true, false>(T, W, sh, P, I) : mb_pref_expand<false, false>(T, W, sh, P, I);
     if (K > T.capK) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
     CTA_SYNC();
-    const uint32_t nNz = sh->cnt[7];
+    const uint32_t nNz = T.kmerBits ? sh->cnt[7] : K;
     MB_PHASE(3);
     if (sh->cnt[3]) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }   // more non-empty k-mers than the list holds
 
-    // ---- P4 gather the index entries of the non-empty lists (thread per list, 4 in flight); mark slot occupancy (0 / 1 / >=2 hits).
-    //      Output slots are reserved with one shared-memory atomic per warp and round.
-    for (uint32_t r0 = 0; r0 < nNz; r0 += 4 * CTA_NT) {
-        uint64_t wv[4]; uint32_t lo[4], len[4], base[4]; uint2 e0[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t n = r0 + u * CTA_NT + CTA_TID; wv[u] = 0; if (n < nNz) wv[u] = (n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            lo[u] = 0; len[u] = 0;
-            if (r0 + u * CTA_NT + CTA_TID < nNz) { const uint32_t km = (uint32_t)wv[u] & 0x3FFFFFFu; lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u]; }
-        }
-        uint32_t mine = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) { base[u] = mine; mine += (len[u] <= T.capM) ? len[u] : T.capM + 1u; }
-        uint32_t b0 = 0; bool fits = true;
+    // ---- P4 gather the index entries of the listed k-mers; mark slot occupancy (0 / 1 / >=2 hits).
+    //      A warp takes 128 lists at a time: their (first entry, length) come from the offsets table with four loads in flight per lane, a warp scan lays
+    //      the lists end to end, and the entries of that flattened range are then fetched one per lane and step -- four steps (128 independent loads per
+    //      warp) in flight before the first is consumed -- whatever list they belong to (owner found by binary search over the 128 prefix sums, staged
+    //      in the warp's slice of the k-mer offset array, which is dead after P3).  Output slots are reserved with one shared-memory atomic per warp and round.
 #if MB_DEVICE_BUILD
-        {
-            const uint32_t lane = threadIdx.x & 31u;
-            uint32_t inc = mine;
+    {
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+        uint32_t *const wPre = sh->sKmerOff + warp * 256u, *const wLo = wPre + 128u;
+        for (uint32_t n0 = warp * 128u; n0 < nNz; n0 += nWarps * 128u) {
+            uint32_t lo[4], len[4];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
-            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
-            uint32_t wb = 0, wf = 1;
-            if (lane == 0 && wtot) {
-                if (*(volatile uint32_t *)&sh->cnt[3] == 0u) {   // cnt[3] = overflow flag until P11 reuses it
-                    wb = atomicAdd(&sh->cnt[6], wtot);
-                    wf = (wb <= T.capM && wtot <= T.capM - wb) ? 1u : 0u;
-                    if (!wf) sh->cnt[3] = 1u;
-                } else wf = 0;
+            for (int u = 0; u < 4; u++) {
+                const uint32_t n = n0 + (uint32_t)u * 32u + lane; lo[u] = 0; len[u] = 0;
+                if (n < nNz) {
+                    const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
+                    lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u];
+                }
             }
-            wb = __shfl_sync(0xffffffffu, wb, 0); wf = __shfl_sync(0xffffffffu, wf, 0);
-            b0 = wb + inc - mine; fits = wf != 0u;
-        }
-#else
-        if (mine) {
-            if (sh->cnt[3] == 0u) { b0 = sh->cnt[6]; sh->cnt[6] += mine; fits = b0 <= T.capM && mine <= T.capM - b0; if (!fits) sh->cnt[3] = 1u; }
-            else fits = false;
-        }
-#endif
-        if (!fits) {
+            uint32_t run = 0; bool big = false;
 #pragma unroll
-            for (int u = 0; u < 4; u++) len[u] = 0;
-        }
+            for (int u = 0; u < 4; u++) {
+                uint32_t l = len[u]; if (l > T.capM) { big = true; l = 0; }
+                uint32_t inc = l;
 #pragma unroll
-        for (int u = 0; u < 4; u++) { e0[u].x = 0; e0[u].y = 0; if (len[u]) e0[u] = T.entries[lo[u]]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t pp = (uint32_t)(wv[u] >> 47), kk = (uint32_t)(wv[u] >> 26) & 0x1FFFFFu;
-            for (uint32_t x = 0; x < len[u]; x++) {
-                const uint2 en = x ? T.entries[(size_t)lo[u] + x] : e0[u];
-                const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
-                W.A[b0 + base[u] + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
-                const uint32_t slot = en.x & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
-                const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
-                if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
+                wPre[u * 32 + lane] = run + inc - l; wLo[u * 32 + lane] = lo[u];
+                run += __shfl_sync(0xffffffffu, inc, 31);
             }
+            const uint32_t Tn = run;
+            big = __any_sync(0xffffffffu, big);
+            uint32_t b0 = 0, fits = 1;
+            if (lane == 0) {
+                if (big) { sh->cnt[3] = 1u; fits = 0; }
+                else if (Tn) {
+                    if (*(volatile uint32_t *)&sh->cnt[3] == 0u) {   // cnt[3] = overflow flag until P11 reuses it
+                        b0 = atomicAdd(&sh->cnt[6], Tn);
+                        fits = (b0 <= T.capM && Tn <= T.capM - b0) ? 1u : 0u;
+                        if (!fits) sh->cnt[3] = 1u;
+                    } else fits = 0;
+                }
+            }
+            b0 = __shfl_sync(0xffffffffu, b0, 0); fits = __shfl_sync(0xffffffffu, fits, 0);
+            __syncwarp();
+            if (fits) for (uint32_t e0 = 0; e0 < Tn; e0 += 128u) {
+                uint32_t own[4]; uint2 en[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t e = e0 + (uint32_t)j * 32u + lane; own[j] = 0xFFFFFFFFu; en[j].x = 0; en[j].y = 0;
+                    if (e < Tn) {
+                        uint32_t a = 0, b = 128;   // wPre[a] <= e < wPre[b]  (wPre[128] = Tn)
+#pragma unroll
+                        for (int it = 0; it < 7; it++) { const uint32_t mid = (a + b) >> 1; if (wPre[mid] <= e) a = mid; else b = mid; }
+                        own[j] = a; en[j] = T.entries[(size_t)wLo[a] + (e - wPre[a])];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (own[j] != 0xFFFFFFFFu) {
+                    const uint32_t e = e0 + (uint32_t)j * 32u + lane, n = n0 + own[j];
+                    const uint64_t wv = (n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ];
+                    const uint32_t pp = (uint32_t)(wv >> 47), kk = (uint32_t)(wv >> 26) & 0x1FFFFFu;
+                    const uint16_t diag16 = (uint16_t)(pp - (en[j].y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+                    W.A[b0 + e] = ((uint64_t)en[j].x << 37) | ((uint64_t)kk << 16) | diag16;
+                    const uint32_t slot = en[j].x & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
+                    const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+                    if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+                }
+            }
+            __syncwarp();
         }
     }
+#else
+    for (uint32_t n = 0; n < nNz; n++) {   // (serial restatement for tests/emu)
+        const uint64_t wv = (n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ];
+        const uint32_t km = (uint32_t)wv & 0x3FFFFFFu, lo = T.offsets[km], len = T.offsets[km + 1] - lo;
+        if (!len) continue;
+        if (sh->cnt[3] != 0u) break;
+        const uint32_t b0 = sh->cnt[6];
+        if (len > T.capM || b0 > T.capM || len > T.capM - b0) { sh->cnt[3] = 1u; break; }
+        sh->cnt[6] += len;
+        const uint32_t pp = (uint32_t)(wv >> 47), kk = (uint32_t)(wv >> 26) & 0x1FFFFFu;
+        for (uint32_t x = 0; x < len; x++) {
+            const uint2 en = T.entries[(size_t)lo + x];
+            const uint16_t diag16 = (uint16_t)(pp - (en.y & 0xFFFFu));   // position_i - position_j (CacheFriendlyOperations.cpp:342)
+            W.A[b0 + x] = ((uint64_t)en.x << 37) | ((uint64_t)kk << 16) | diag16;
+            const uint32_t slot = en.x & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
+            const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+            if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+        }
+    }
+#endif
     CTA_SYNC();
     const uint32_t M = sh->cnt[6];
     MB_PHASE(4);

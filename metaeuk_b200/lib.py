@@ -58,7 +58,7 @@ def _gxx():
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (it travels with the repo snapshot)."""
     srcs = [os.path.join(CSRC, f) for f in ("mb200.cu", "host_tables.cpp", "host_join.cpp", "host_indexdb.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "cta_prims.cuh", "host_tables.h", "host_join.h", "host_indexdb.h", "submat_data.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("prefilter_core.cuh", "chain_core.cuh", "reduce_core.cuh", "orf_kernels.cuh", "sw_kernels.cuh", "sw_stream.cuh", "cta_prims.cuh", "host_tables.h", "host_join.h", "host_indexdb.h", "submat_data.h")] + \
         [os.path.join(ROOT, "include", "metaeuk_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH

@@ -17,6 +17,10 @@ from test_kernel_logic_emulated import _open_indexdb, emu  # noqa: F401  (fixtur
 def exe():
     import __graft_entry__ as g
     p = os.path.join(mlib.PKG, "bin", "mb200")
+    srcs = [os.path.join(mlib.PKG, "csrc", "mb200_cli.cpp"), os.path.join(reflib.ROOT, "include", "metaeuk_b200.h")]
+    stale = os.path.exists(p) and any(os.path.getmtime(f) > os.path.getmtime(p) for f in srcs)     # never test a driver older than its sources
+    if stale:
+        os.remove(p)
     if not os.path.exists(p) or not os.path.exists(mlib.LIB_PATH):
         g.build()
     return p

@@ -40,17 +40,22 @@ def test_prefilter_golden(name, cfg):
     ctx.close()
 
 
-@pytest.mark.parametrize("sw", [1, 2, 3, 4, (4, 1), (4, 1024), 5, (5, 1)],
-                         ids=["rows", "rows2-packed", "rows3-state-machine", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2"])
+@pytest.mark.parametrize("sw", [1, 2, 3, 4, (4, 1), (4, 1024), 5, (5, 1), 6, (6, "sw_ring", -1), (6, "sw_ring", 1), (6, "sw_ring", 16)],
+                         ids=["rows", "rows2-packed", "rows3-state-machine", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2",
+                              "stream", "stream-private-profiles", "stream-ring1", "stream-ring16"])
 @pytest.mark.parametrize("name", FRAG + CONTIG)
 def test_align_golden(name, sw):
     """every forward alignment kernel variant (mb200_option_set "sw_kernel") must give the reference's result DB; 4 = queries of at most 64
     residues with at most sw_lane_max_hits hits take the one-item-per-lane kernel, the others the chunk kernel; 5 (default) = as 4, and the other
-    queries of at most 512 residues take the wavefront kernel (row blocks of one alignment on neighbouring lanes)"""
+    queries of at most 512 residues take the wavefront kernel (row blocks of one alignment on neighbouring lanes); 6 (default) = streams of
+    (query, two targets) pairs over persistent lane groups, end cells recorded by the forward pass, reverse pass only for the accepted ones"""
     c = reflib.load_case(name)
     ctx, tdb = ctx_for(c)
     if isinstance(sw, tuple):
-        ctx.option_set("sw_lane_max_hits", sw[1])
+        if len(sw) == 3:
+            ctx.option_set(sw[1], sw[2])
+        else:
+            ctx.option_set("sw_lane_max_hits", sw[1])
         sw = sw[0]
     ctx.option_set("sw_kernel", sw)
     pref = {k: c["pref"].get(str(k), "") for k, _ in c["queries"]}
