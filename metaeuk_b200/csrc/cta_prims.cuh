@@ -137,22 +137,52 @@ MB_DEV uint32_t mb_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1
 
 // Ascending sort of 64-bit keys a[0..n).  The buffer must have room for next_pow2(n) elements (padding is
 // written as ~0).  Bitonic network with block barriers; fine for the few-hundred-element lists the prefilter sorts.
+#if MB_DEVICE_BUILD
+// Up to 32 * R keys sorted by ONE warp: R keys per lane in registers (element r * 32 + lane), bitonic network with the compare-exchanges between
+// lanes through shuffles and those between registers in place -- no block barrier and no shared memory inside the sort.
+template <int R> __device__ __forceinline__ void warp_sort_u64(uint64_t *a, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t key[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { const uint32_t idx = (uint32_t)r * 32u + lane; key[r] = (idx < n) ? a[idx] : ~0ull; }
+#pragma unroll
+    for (uint32_t k = 2; k <= 32u * R; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32u) {
+                const int rj = (int)(j >> 5);
+#pragma unroll
+                for (int r = 0; r < R; r++) if ((r & rj) == 0) {
+                    const bool asc = ((((uint32_t)r * 32u) & k) == 0);      // k >= 64 here: the direction bit lies in the register index
+                    const uint64_t x = key[r], y = key[r | rj];
+                    const bool sw = (x > y) == asc;
+                    key[r] = sw ? y : x; key[r | rj] = sw ? x : y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], (int)j);
+                    const bool asc = (((uint32_t)r * 32u + lane) & k) == 0, lower = (lane & j) == 0;
+                    const uint64_t mn = key[r] < other ? key[r] : other, mx = key[r] < other ? other : key[r];
+                    key[r] = (asc == lower) ? mn : mx;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) { const uint32_t idx = (uint32_t)r * 32u + lane; if (idx < n) a[idx] = key[r]; }
+}
+#endif
+
 MB_DEV_CALL void cta_sort_u64(uint64_t *a, uint32_t n) {
 #if MB_DEVICE_BUILD
     const uint32_t n2 = mb_next_pow2(n);
-    if (n2 <= 32) {   // short lists: one warp, keys in registers, compare-exchange through shuffles, a single block barrier
+    if (n2 <= 256) {   // short lists (the usual case): one warp, keys in registers, a single block barrier
         if (threadIdx.x < 32) {
-            const uint32_t lane = threadIdx.x;
-            uint64_t key = (lane < n) ? a[lane] : ~0ull;
-            for (uint32_t k = 2; k <= 32; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
-                    const bool asc = ((lane & k) == 0), lower = ((lane & j) == 0);
-                    const uint64_t mn = key < other ? key : other, mx = key < other ? other : key;
-                    key = (asc == lower) ? mn : mx;
-                }
-            }
-            if (lane < n) a[lane] = key;
+            if (n2 <= 32) warp_sort_u64<1>(a, n);
+            else if (n2 <= 64) warp_sort_u64<2>(a, n);
+            else if (n2 <= 128) warp_sort_u64<4>(a, n);
+            else warp_sort_u64<8>(a, n);
         }
         __syncthreads();
         return;

@@ -200,7 +200,7 @@ struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
-    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false;
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optSortWalk = 0;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
     DevBuf<unsigned char> dIndexArena; size_t arenaBytes = 0;   // offsets | entries | masked | unmasked residues | target offsets in ONE allocation (one ncclBroadcast replicates it)
     void *comm = nullptr;                                        // ncclComm_t created by mb200_comm_init (owned)
@@ -382,7 +382,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     for (int k = 0; k < 2; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
     for (int k = 0; k < 4; k++) { if (c->swSide[k]) cudaStreamDestroy(c->swSide[k]); if (c->swJoin[k]) cudaEventDestroy(c->swJoin[k]); c->swSide[k] = nullptr; c->swJoin[k] = nullptr; }
     if (c->swFork) { cudaEventDestroy(c->swFork); c->swFork = nullptr; }
-    mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
+    mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dBuckets.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
     c->dSeedMat.release(); c->dAlnMat.release(); c->dSeedPB.release(); c->dAlnPB.release(); c->dUng8.release(); c->dScratch.release(); c->dScratchMem.release(); c->dScratchShort.release(); c->dScratchShortMem.release(); c->dScratchRescue.release(); c->dScratchRescueMem.release(); c->dOrderRescue.release();
     c->dQ.release(); c->dQoff.release(); c->dBias.release(); c->dCorr.release(); c->dCb.release(); c->dOrder.release(); c->dHits.release(); c->dHitCount.release();
     c->dStatus.release(); c->dCounter.release(); c->dStats.release(); c->dCells.release(); c->dHE.release(); c->dPairOff.release(); c->dChunkOff.release(); c->dLaneOff.release(); c->dWaveOff.release(); c->dPassList.release();
@@ -400,6 +400,8 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return fail(MB200_E_ARG, "null argument");
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
+    else if (n == "prefilter_sort_walk") { if (value < 0 || value > 256) return fail(MB200_E_ARG, "prefilter_sort_walk: 0..256"); c->optSortWalk = (int)value; }
+    else if (n == "prefilter_buckets") { if (value != 0 && value != 1) return fail(MB200_E_ARG, "prefilter_buckets: 0 (offsets + entries arrays) or 1 (inline bucket table)"); c->optBuckets = (int)value; }
     else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
     else if (n == "prefilter_short_len") { if (value < 0 || value > 32767) return fail(MB200_E_ARG, "prefilter_short_len: 0 (off) .. 32767"); c->optPrefShortLen = (int)value; }
     else if (n == "prefilter_short_config") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "prefilter_short_config: 1..4"); c->optPrefShortCfg = (int)value; }
@@ -489,8 +491,33 @@ __global__ void k_kmer_bits(const uint32_t *__restrict__ offsets, uint32_t nWord
     for (uint32_t b = 0; b < 32; b++) { const uint32_t k = w * 32u + b; if (offsets[k + 1] != offsets[k]) m |= 1u << b; }
     bits[w] = m;
 }
+// inline bucket table (prefilter_core.cuh): 2 GB, built on the device from offsets / entries when the prefilter first needs it
+__global__ void k_build_buckets(const uint32_t *__restrict__ offsets, const uint2 *__restrict__ entries, uint32_t nKmers, uint4 *__restrict__ buckets) {
+    for (uint32_t km = blockIdx.x * blockDim.x + threadIdx.x; km < nKmers; km += gridDim.x * blockDim.x) {
+    const uint32_t lo = offsets[km], len = offsets[km + 1] - lo;
+    uint32_t h[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) h[i] = 0;
+    h[0] = len < 0xFFFFu ? len : 0xFFFFu;
+    if (len <= MB_BUCKET_INLINE) {
+#pragma unroll
+        for (int j = 0; j < MB_BUCKET_INLINE; j++) if ((uint32_t)j < len) { const uint2 e = entries[(size_t)lo + j]; h[1 + 3 * j] = e.x & 0xFFFFu; h[2 + 3 * j] = e.x >> 16; h[3 + 3 * j] = e.y & 0xFFFFu; }
+    } else { h[2] = lo & 0xFFFFu; h[3] = lo >> 16; h[4] = len & 0xFFFFu; h[5] = len >> 16; }
+    uint4 a, b;
+    a.x = h[0] | (h[1] << 16); a.y = h[2] | (h[3] << 16); a.z = h[4] | (h[5] << 16); a.w = h[6] | (h[7] << 16);
+    b.x = h[8] | (h[9] << 16); b.y = h[10] | (h[11] << 16); b.z = h[12] | (h[13] << 16); b.w = h[14] | (h[15] << 16);
+    buckets[2 * (size_t)km] = a; buckets[2 * (size_t)km + 1] = b;
+    }
+}
+static int build_buckets(mb200_ctx *c) {
+    if (c->haveBuckets || !c->optBuckets) return 0;
+    TRY(c->dBuckets.alloc(2 * (size_t)mb200::KMER_TABLE));
+    MB_LAUNCH((k_build_buckets), c->nSM * 16, 256, 0, c->stream, c->dOffsets.p, c->dEntries.p, (uint32_t)mb200::KMER_TABLE, c->dBuckets.p);
+    CU(cudaGetLastError()); CU(cudaStreamSynchronize(c->stream));
+    c->haveBuckets = true; return 0;
+}
 static int build_kmer_bits(mb200_ctx *c) {
-    c->useBits = false;
+    c->useBits = false; c->haveBuckets = false;
     if (c->nEntries >= mb200::KMER_TABLE) return 0;   // dense index: nearly every k-mer has a list, the extra lookup would not pay
     const uint32_t nWords = (uint32_t)(mb200::KMER_TABLE / 32);
     TRY(c->dKmerBits.alloc(nWords));
@@ -887,14 +914,15 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     if (!c->haveIndex || !c->haveSim3) return fail(MB200_E_STATE, "index / matrices not set");
     CU(cudaSetDevice(c->device));
     TRY(ctx_alloc_scratch(c));
+    TRY(build_buckets(c));
     const uint32_t nQ = c->nQ; const uint32_t maxHits = (uint32_t)c->par.max_res_list_len;
     TRY(c->dHits.alloc((size_t)nQ * maxHits)); TRY(c->dHitCount.alloc(nQ + 1)); TRY(c->dStatus.alloc(nQ + 1)); TRY(c->dCounter.alloc(4)); TRY(c->dStats.alloc(1));
     CU(cudaMemsetAsync(c->dCounter.p, 0, 16, c->stream)); CU(cudaMemsetAsync(c->dStats.p, 0, sizeof(MbPrefStats), c->stream));
     CU(cudaMemsetAsync(c->dHitCount.p, 0, (size_t)(nQ + 1) * 4, c->stream)); CU(cudaMemsetAsync(c->dStatus.p, 0xFF, (size_t)(nQ + 1) * 4, c->stream));
     MbPrefTables T; memset(&T, 0, sizeof(T));
-    T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
+    T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.buckets = (c->optBuckets && c->haveBuckets) ? c->dBuckets.p : nullptr; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
     T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
-    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.phaseStats = c->optPhaseStats;
+    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.phaseStats = c->optPhaseStats; T.sortWalkMax = (uint32_t)c->optSortWalk;
     T.capM = (uint32_t)std::min<uint64_t>(c->capM, 2ull * std::max<uint64_t>(1000000ull, c->nT) - 1);   // beyond that the reference switches to its own overflow path (QueryMatcher.cpp:43,280-305)
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
@@ -1113,7 +1141,6 @@ static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t 
         const SwTraceOut &o = c->hTrace[r];
         if (o.slot == 0xFFFFFFFFu) continue;     // handed to the 32-bit kernel (its own record follows)
         if (o.flag & 1) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (query %u, hit %u)", o.slot / maxHits, o.slot % maxHits);
-        if (o.flag & 2) return fail(MB200_E_LIMIT, "alignment score of query %u against its hit %u exceeds 65000 (32-bit fallback kernel limit)", o.slot / maxHits, o.slot % maxHits);
         c->hTrace[w++] = o;
     }
     c->hTrace.resize(w);
@@ -1630,6 +1657,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->par = p->par; w->mat = p->mat; w->haveMat = p->haveMat; w->ev = p->ev;
     w->dSim3.set_view(p->dSim3.p, p->dSim3.n); w->dCnt3.set_view(p->dCnt3.p, p->dCnt3.n); w->dOffsets.set_view(p->dOffsets.p, p->dOffsets.n);
     w->dKmerBits.set_view(p->dKmerBits.p, p->dKmerBits.n); w->useBits = p->useBits; w->dEntries.set_view(p->dEntries.p, p->dEntries.n);
+    w->optBuckets = p->optBuckets; w->optSortWalk = p->optSortWalk; w->haveBuckets = p->haveBuckets; if (p->haveBuckets) w->dBuckets.set_view(p->dBuckets.p, p->dBuckets.n);
     w->dTseqM.set_view(p->dTseqM.p, p->dTseqM.n); w->dTseqU.set_view(p->dTseqU.p, p->dTseqU.n); w->dToff.set_view(p->dToff.p, p->dToff.n);
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
@@ -1673,6 +1701,7 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         }
         if (rcs[0]) return rcs[0];
     } else {
+        TRY(build_buckets(c));      // (shared with the workers as a view)
         for (int k = 0; k < 2; k++) TRY(worker_sync(c, c->workers[k]));
         std::atomic<uint32_t> next(0);
         auto run = [&](int k) {

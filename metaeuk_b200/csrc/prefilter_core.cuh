@@ -38,6 +38,7 @@ struct MbPrefTables {
     const uint32_t *offsets;   // [20^6 + 1]
     const uint32_t *kmerBits;  // optional [20^6 / 32] bitmap of k-mers with a non-empty list (L2 resident), or NULL
     const uint2 *entries;      // (seqId, pos_j)
+    const uint4 *buckets;      // optional [20^6][2]: one 32-byte sector per k-mer = u16 count | up to 5 inline (seqId lo, seqId hi, pos_j) entries; longer lists: count, first entry index, length
     const uint8_t *tseq;       // masked target residues
     const uint64_t *toff;      // [nT + 1]
     uint32_t nT;
@@ -45,6 +46,7 @@ struct MbPrefTables {
     uint32_t binMask;          // BINSIZE - 1 of the reference's CacheFriendlyOperations<BINSIZE>
     uint32_t capP, capI, capK, capM;
     uint32_t phaseStats;       // 1 = per-phase cycle accounting (diagnostic runs only)
+    uint32_t sortWalkMax;      // multi-hit lists of at most this many entries are sorted (one warp, registers) and walked instead of grouped by hashing (0: measured slower on C2, r02g)
 };
 
 struct MbPrefScratch {        // per-CTA global scratch
@@ -96,7 +98,9 @@ typedef MbPrefSharedT<MbPrefCfgDense> MbPrefShared;
 // sort a (usually short) global list: through shared memory when it fits
 template <class SH>
 MB_DEV_CALL void mb_sort_list(uint64_t *g, uint32_t n, SH *sh) {
-    if (n <= SH::Cfg::SM_S) {
+    if (n <= 256) {
+        cta_sort_u64(g, n);      // one warp sorts in registers, straight from and to the list
+    } else if (n <= SH::Cfg::SM_S) {
         CTA_FOR(i, n) sh->sSort[i] = g[i];
         CTA_SYNC();
         cta_sort_u64(sh->sSort, n);
@@ -112,6 +116,31 @@ MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t htLog, uint32_t id1) 
     uint32_t slot = (id1 * 2654435761u) >> (32 - htLog);
     while (htKey[slot] != id1) slot = (slot + 1u) & mask;
     return slot;
+}
+
+// ---- inline buckets: the index entries of a k-mer sit in the same 32-byte sector as their count, so a lookup is ONE random HBM access
+//      instead of offsets[k-mer] followed by entries[...] (the gather phase is bound by the rate of random DRAM accesses, not by bytes).
+//      16 halfwords: h[0] = list length (0xFFFF: 65535 or more), then either up to MB_BUCKET_INLINE entries of three halfwords
+//      (seqId low, seqId high, position) or, for longer lists, h[2..3] = index of the first entry in the classic array, h[4..5] = length.
+#define MB_BUCKET_INLINE 5
+#if MB_DEVICE_BUILD
+// one 256-bit load (LDG.E.256 on sm_100a): the whole sector in a single request
+__device__ __forceinline__ void mb_load_bucket(const uint4 *p, uint4 &a, uint4 &b) {
+#ifdef MB200_SIMT_EMU
+    a = p[0]; b = p[1];
+#else
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#endif
+}
+#endif
+MB_DEV uint32_t mb_bucket_h(const uint4 &a, const uint4 &b, int i) {   // halfword i of the 32-byte bucket (i is a compile-time constant at every call site)
+    const uint32_t w = (i < 8) ? ((i >> 1) == 0 ? a.x : (i >> 1) == 1 ? a.y : (i >> 1) == 2 ? a.z : a.w)
+                               : (((i - 8) >> 1) == 0 ? b.x : ((i - 8) >> 1) == 1 ? b.y : ((i - 8) >> 1) == 2 ? b.z : b.w);
+    return (i & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+MB_DEV void mb_bucket_entry(const uint4 &a, const uint4 &b, int j, uint32_t &seqId, uint32_t &pos) {
+    seqId = mb_bucket_h(a, b, 1 + 3 * j) | (mb_bucket_h(a, b, 2 + 3 * j) << 16); pos = mb_bucket_h(a, b, 3 + 3 * j);
 }
 
 struct MbPrefStats { unsigned long long kmers, lookups, dbMatches, doubleHits, diagCells, results; unsigned long long phase[16]; };
@@ -332,11 +361,67 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
         for (uint32_t n0 = warp * 128u; n0 < nNz; n0 += nWarps * 128u) {
             uint32_t lo[4], len[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t n = n0 + (uint32_t)u * 32u + lane; lo[u] = 0; len[u] = 0;
-                if (n < nNz) {
-                    const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
-                    lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u];
+            for (int u = 0; u < 4; u++) { lo[u] = 0; len[u] = 0; }
+            if (T.buckets) {
+                // inline buckets: the entries of a short list arrive with the lookup itself (two 128-bit loads per k-mer, two k-mers per lane in flight);
+                // only the lists of more than MB_BUCKET_INLINE entries go through the flattened gather below
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    uint4 ba[2], bb[2]; uint32_t nIn[2], inl = 0;
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const uint32_t n = n0 + (uint32_t)(2 * hh + v) * 32u + lane; nIn[v] = 0;
+                        if (n < nNz) {
+                            const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
+                            mb_load_bucket(T.buckets + 2 * (size_t)km, ba[v], bb[v]);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < 2; v++) if (n0 + (uint32_t)(2 * hh + v) * 32u + lane < nNz) {
+                        const uint32_t cnt = mb_bucket_h(ba[v], bb[v], 0);
+                        if (cnt <= MB_BUCKET_INLINE) { nIn[v] = cnt; inl += cnt; }
+                        else { lo[2 * hh + v] = ba[v].y; len[2 * hh + v] = ba[v].z; }     // (halfwords 2..3 and 4..5)
+                    }
+                    uint32_t inc = inl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += y; }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                    uint32_t ob = 0, ofits = 1;
+                    if (lane == 0 && tot) {
+                        if (*(volatile uint32_t *)&sh->cnt[3] == 0u) {
+                            ob = atomicAdd(&sh->cnt[6], tot);
+                            ofits = (ob <= T.capM && tot <= T.capM - ob) ? 1u : 0u;
+                            if (!ofits) sh->cnt[3] = 1u;
+                        } else ofits = 0;
+                    }
+                    ob = __shfl_sync(0xffffffffu, ob, 0); ofits = __shfl_sync(0xffffffffu, ofits, 0);
+                    if (ofits && tot) {
+                        uint32_t o = ob + inc - inl;
+#pragma unroll
+                        for (int v = 0; v < 2; v++) if (nIn[v]) {
+                            const uint32_t n = n0 + (uint32_t)(2 * hh + v) * 32u + lane;
+                            const uint64_t wv = (n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ];
+                            const uint32_t pp = (uint32_t)(wv >> 47), kk = (uint32_t)(wv >> 26) & 0x1FFFFFu;
+#pragma unroll
+                            for (int j = 0; j < MB_BUCKET_INLINE; j++) if ((uint32_t)j < nIn[v]) {
+                                uint32_t seqId, pos; mb_bucket_entry(ba[v], bb[v], j, seqId, pos);
+                                const uint16_t diag16 = (uint16_t)(pp - pos);                  // position_i - position_j (CacheFriendlyOperations.cpp:342)
+                                W.A[o++] = ((uint64_t)seqId << 37) | ((uint64_t)kk << 16) | diag16;
+                                const uint32_t slot = seqId & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
+                                const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+                                if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t n = n0 + (uint32_t)u * 32u + lane;
+                    if (n < nNz) {
+                        const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
+                        lo[u] = T.offsets[km]; len[u] = T.offsets[km + 1] - lo[u];
+                    }
                 }
             }
             uint32_t run = 0; bool big = false;
@@ -432,7 +517,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
     MB_PHASE(5);
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
     if (nMulti == 0) {
-    } else if (nMulti <= (1u << (SH::Cfg::HT_LOG_MAX - 1))) {
+    } else if (nMulti > T.sortWalkMax && nMulti <= (1u << (SH::Cfg::HT_LOG_MAX - 1))) {   // (up to 256 entries one warp sorts in registers: the sorted walk below is cheaper)
         // Sort-free: group the multi list by target with a shared-memory hash table (the k-mer list's space is free now), then every
         // hit looks up its predecessor *of the same target* (largest smaller arrival key) inside its group.
         uint32_t htLog = SH::Cfg::HT_LOG_MAX < 6u ? SH::Cfg::HT_LOG_MAX : 6u; while ((1u << htLog) < 2u * nMulti) htLog++;

@@ -740,7 +740,7 @@ __device__ __forceinline__ void sw_trace_pass(const int8_t *sMatT /* [22][32] : 
                 const int s = (int)sMatT[(QR[r] & 0xFFFFu) + tc] + (int)(int8_t)(QR[r] >> 16);
                 const int f = (r == 0) ? F : __viaddmax_s32(F, negE, gUp);
                 const int t1 = __viaddmax_s32(diag, s, E[r]);
-                const int h = __vimax_s32_relu(t1, f);
+                const int h = min(__vimax_s32_relu(t1, f), 32767);   // the reference's 16-bit cells saturate (_mm_adds_epi16, StripedSmithWaterman.cpp:942-1214)
                 diag = Hp[r]; Hp[r] = h;
                 const int g = h - gapO;
                 E[r] = __viaddmax_s32_relu(E[r], negE, g);
@@ -790,7 +790,6 @@ __global__ void __launch_bounds__(128) k_sw_trace2(const uint32_t *__restrict__ 
             o.dbStart = col - rcol; o.qStart = row - rrow;
             if (rs != sc) o.flag = 1;
         }
-        if (sc >= 32000) o.flag |= 2;
         outs[idx] = o;
     }
     if (cells) atomicAdd(cellCount, cells);

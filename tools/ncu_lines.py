@@ -17,7 +17,7 @@ for l in sass:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: loc = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if cur and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l): kern[cur].append(loc)
-name = [k for k in kern if kname in k][0]
+cands = [k for k in kern if kname in k]; name = ([k for k in cands if os.environ.get("MANGLED", "\0") in k] or cands)[0]
 locs = kern[name]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
