@@ -1110,12 +1110,13 @@ static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t 
         TRY(sync_check(c, "reverse descriptors"));
         CU(cudaEventRecord(c->swFork, c->stream));
         bool usedR[4] = {false, false, false, false};
+        static const uint32_t revNb[MB_SWS_REV_CLASSES] = {1, 2, 3, 4, 5, 6, 8, 10, 16, 32};
         for (int cl = 0; cl < MB_SWS_REV_CLASSES; cl++) {
             if (!hcls[cl]) continue;
-            const SwStreamGeom g = sw_stream_geom(cl < 4 ? (uint32_t)cl + 1u : 8u, 2, 1.0, 0);
+            const SwStreamGeom g = sw_stream_geom(revNb[cl], 2, 1.0, 0);
             const int k = cl & 3;
             if (!usedR[k]) { CU(cudaStreamWaitEvent(c->swSide[k], c->swFork, 0)); usedR[k] = true; }
-            TRY(sw_stream_launch(c, c->swSide[k], g, c->dSwDescRev.p + (size_t)cl * nPass, hcls[cl], nullptr, nullptr, 0, c->dCounter.p + 110 + cl, c->dCells.p + 1, dErr, c->dTrace.p));
+            TRY(sw_stream_launch(c, c->swSide[k], g, c->dSwDescRev.p + (size_t)cl * nPass, hcls[cl], nullptr, nullptr, 0, c->dCounter.p + 112 + cl, c->dCells.p + 1, dErr, c->dTrace.p));
         }
         for (int k = 0; k < 4; k++) if (usedR[k]) { CU(cudaEventRecord(c->swJoin[k], c->swSide[k])); CU(cudaStreamWaitEvent(c->stream, c->swJoin[k], 0)); }
     }

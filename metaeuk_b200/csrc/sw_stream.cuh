@@ -65,22 +65,24 @@ __global__ void __launch_bounds__(256) k_sw_desc_fwd(const uint32_t *__restrict_
     }
 }
 
-// ---- descriptors of the reverse pass, one per pass record with a known end cell, binned by the number of row blocks of the query prefix:
-//      class c in 0..4 holds prefixes of (32 c, 32 c + 32] rows for c < 4 and (128, 256] rows for c = 4; longer prefixes go to the fallback
-//      list (k_sw_trace2 recomputes them from scratch).  desc[c * cap + atomic index]; slotA = index of the record (= index of the output).
-#define MB_SWS_REV_CLASSES 5
+// ---- descriptors of the reverse pass, one per pass record with a known end cell, binned by the number of 32-row blocks of the query prefix [0..qEnd]
+//      into the launch groups of the forward pass (all block counts with the same number of slots per warp share a launch): classes of 1, 2, 3, 4, 5, 6,
+//      7..8, 9..10, 11..16 and 17..32 blocks.  Records without an end cell (16-bit range exhausted in the forward kernel) go to the fallback list
+//      (k_sw_trace2 recomputes them with 32-bit cells).  desc[c * cap + atomic index]; slotA = index of the record (= index of the output).
+#define MB_SWS_REV_CLASSES 10
+__device__ __forceinline__ uint32_t sws_group_of(uint32_t nb) { return nb <= 6u ? nb - 1u : (nb <= 8u ? 6u : (nb <= 10u ? 7u : (nb <= 16u ? 8u : 9u))); }
 __global__ void __launch_bounds__(256) k_sw_desc_rev(const SwPassRec *__restrict__ recs, uint32_t nRec, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
                                                      const uint64_t *__restrict__ toff, SwPair *__restrict__ desc, uint32_t cap, uint32_t *__restrict__ classCount,
                                                      uint32_t *__restrict__ fallback, uint32_t *__restrict__ nFallback, SwTraceOut *__restrict__ outs) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nRec; r += gridDim.x * blockDim.x) {
         const SwPassRec p = recs[r];
         const uint32_t rows = (uint32_t)p.qEnd + 1u;
-        if (p.dbEnd < 0 || rows > 256u) {      // end cell unknown (16-bit overflow in the forward kernel) or prefix too long for the stream kernel
+        if (p.dbEnd < 0 || rows > 1024u) {     // end cell unknown (16-bit overflow in the forward kernel)
             fallback[atomicAdd(nFallback, 1u)] = p.slot;
             SwTraceOut o; o.slot = 0xFFFFFFFFu; o.score = 0; o.qStart = o.qEnd = o.dbStart = o.dbEnd = -1; o.flag = 0; o.pad = 0; outs[r] = o;   // (dropped by the host; the fallback kernel writes its own)
             continue;
         }
-        const uint32_t c = rows <= 128u ? (rows - 1u) >> 5 : 4u;
+        const uint32_t c = sws_group_of((rows + 31u) >> 5);
         SwPair d; d.qi = p.slot / maxHits; d.slotA = r; d.slotB = p.slot; d.offA = (uint32_t)toff[hits[p.slot].seqId]; d.offB = 0;
         d.lens = (uint32_t)p.dbEnd + 1u; d.rows = rows; d.aux = (uint32_t)p.score;
         desc[(size_t)c * cap + atomicAdd(&classCount[c], 1u)] = d;

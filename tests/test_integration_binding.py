@@ -55,7 +55,7 @@ def test_compiled_binding_on_the_gpu(tmp_path):
         pytest.skip("integration/_build/metaeuk-b200 not built (needs /root/reference: build container)")
     t = reflib.load_case("ref_tests")["sets"]["two_contigs"]
     d = str(tmp_path)
-    reflib.write_db(d + "/contigs", [(k, s + "\n") for k, s in t["contigs"]], 2)
+    reflib.write_db(d + "/contigs", [(k, s + "\n") for k, s in t["contigs"]], 1)      # Parameters::DBTYPE_NUCLEOTIDES
     reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in t["targets"]], 0)
     subprocess.check_call([tool, "gpupredictexons", d + "/contigs", d + "/proteins", d + "/pred", "--set-gap-extend", str(t["set_gap_extend"]), "--metaeuk-tcov", str(t["tcov"])],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
