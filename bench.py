@@ -205,6 +205,15 @@ def algorithmic_bytes_prefilter(st):
     return 22 * st["query_residues"] + 16 * st["kmers"] + 6 * st["db_matches"] + st["diag_cells"] + 6 * st["double_hits"] + 10 * st["pref_results"]
 
 
+def random_access_roofline(st, kernel_ms):
+    """The prefilter's index lookups are independent random HBM reads (one 32-byte bucket per similar k-mer): HBM3e limits their RATE, not their bytes.  Ceiling = what
+    tools/microbench/randgather.cu measured on a B200 of this pool for 8-byte and single-instruction 32-byte random reads from a 1.5 GB buffer (profiles/r02_randgather.txt)."""
+    peak = 40.6
+    ach = st["kmers"] / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    return {"what": "index bucket lookups (one random 256-bit HBM read per similar k-mer)", "achieved": ach, "peak": peak, "unit": "G accesses/s", "frac": ach / peak,
+            "peak_source": "measured: tools/microbench/randgather.cu on B200, profiles/r02_randgather.txt (40.6 G/s from 1.5 GB; 37.8 G/s from 4 GB)"}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -482,7 +491,8 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                          "last_call_ms": {k: round(st[k], 3) for k in STAGES + ("ms_join", "ms_predict")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": abytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kms * 1e-3) / 1e9 / peak,
                               "peak_source": peak_src, "algorithmic_bytes_per_launch": int(abytes // nb), "kernel_ms": kms / nb, "launches_per_step": nb,
-                              "share_of_step": kms / (1000 * vals[0] / args.steps), "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload)},
+                              "share_of_step": kms / (1000 * vals[0] / args.steps), "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload),
+                              "random_access": random_access_roofline(st, kms)},
                  "stages_ms": {k: st[k] for k in STAGES + ("ms_join",)}, "stages_ms_per_rank": stage_all,
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons")},
                  "index": idx, "parity": parity,
@@ -490,7 +500,8 @@ def bench_predict(args, wl, base, rank, world, local, threads):
     if st["ms_sw_fwd"] + st["ms_sw_rev"] > 0:
         base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
         base["roofline_sw"] = {"kernel": "k_sw_* forward + reverse", "bound": "integer ALU (DPX s16x2)", "achieved": base["gcups_sw"] / 1e3, "unit": "TCUPS",
-                               "peak": 5.1, "peak_source": "DESIGN.md 4.2: 148 SMs x 4 schedulers x 32 lanes x 2 cells / 7 issue slots per cell pair x 1.9 GHz", "frac": base["gcups_sw"] / 1e3 / 5.1}
+                               "peak": 6.14, "peak_source": "DESIGN.md 4.2: SASS of k_sw_stream has 194 ALU-pipe instructions per column step of 32 rows x 2 targets, the ALU pipe issues one warp instruction per 2 cycles per scheduler: 148 SMs x 4 x 2048 cells / 388 cycles x 1.965 GHz",
+                               "frac": base["gcups_sw"] / 1e3 / 6.14, "share_of_step": (st["ms_sw_fwd"] + st["ms_sw_rev"]) / (1000 * vals[0] / args.steps) if world == 1 else None}
     base["predict_streams"] = int(st.get("pe_streams", 1))
     if args.phase_stats:     # one extra, untimed, instrumented pass for the per-phase breakdown of k_prefilter
         ctx.option_set("phase_stats", 1)
@@ -799,7 +810,7 @@ def bench_fragments(args, wl, base, rank, world, local, threads):
                          "last_call_ms": {k: round(st_e2e[k], 3) for k in ("ms_h2d", "ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_d2h", "ms_host")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                               "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kms, "share_of_step": kms / (1000 * dt / args.steps),
-                              "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload)},
+                              "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload), "random_access": random_access_roofline(st, kms)},
                  "stages_ms": {k: st[k] for k in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev")},
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev")},
                  "index": idx, "parity": parity,

@@ -45,6 +45,7 @@ MB_DEV float mb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 #define CTA_CHUNK(b, e, n) uint32_t b = 0, e = (uint32_t)(n);
 #include <algorithm>
 struct uint2 { unsigned int x, y; };
+struct uint4 { unsigned int x, y, z, w; };
 MB_DEV uint32_t mb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 MB_DEV uint32_t mb_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 MB_DEV uint32_t mb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }

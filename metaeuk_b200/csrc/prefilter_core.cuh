@@ -66,10 +66,10 @@ struct MbPrefScratch {        // per-CTA global scratch
 // small / sparse indexes (half the threads, twice the CTAs per SM: block barriers of one query overlap with work of three others).
 template <int NT_, int CTAS_, int NSLOT_LOG_, int SM_I_, int SM_NZ_LOG_> struct MbPrefCfg {
     static constexpr uint32_t NT = NT_, CTAS = CTAS_;
-    static constexpr uint32_t NSLOT = 1u << NSLOT_LOG_;     // 2-bit occupancy slots (target & (NSLOT - 1))
+    static constexpr uint32_t NSLOT = 1u << NSLOT_LOG_, NSLOT_LOG = NSLOT_LOG_;     // 2-bit occupancy slots (target & (NSLOT - 1))
     static constexpr uint32_t SM_I = SM_I_;                 // items (window, first-half neighbour)
     static constexpr uint32_t SM_NZ = 1u << SM_NZ_LOG_;     // non-empty similar k-mers; the same space then holds the hash table / sort buffer
-    static constexpr uint32_t SM_S = SM_NZ, HT_LOG_MAX = SM_NZ_LOG_;
+    static constexpr uint32_t SM_S = SM_NZ, HT_LOG_MAX = SM_NZ_LOG_, MUL_CAP = SM_NZ / 4;
 };
 typedef MbPrefCfg<512, 2, 17, 4096, 12> MbPrefCfgDense;
 typedef MbPrefCfg<256, 4, 15, 2048, 10> MbPrefCfgSparse;
@@ -91,6 +91,10 @@ template <class CFG> struct MbPrefSharedT {
         uint64_t sNz[CFG::SM_NZ];
         uint32_t sHitOff[2 * CFG::SM_NZ];   // hash table of the double-hit stage (keys | group offsets)
         uint64_t sSort[CFG::SM_S];
+        struct {                            // double-hit stage entirely in shared memory (multi-hit lists of at most MUL_CAP entries: the usual case)
+            uint64_t sMul[CFG::SM_NZ / 4], sGrp[CFG::SM_NZ / 4];
+            uint32_t sHt[CFG::SM_NZ];       // keys | group offsets, SM_NZ / 2 slots each
+        };
     };
 };
 typedef MbPrefSharedT<MbPrefCfgDense> MbPrefShared;
@@ -502,21 +506,106 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
     if (sh->cnt[3]) { CTA_SINGLE { *outCount = 0; *outStatus = MB_ST_OVERFLOW; } return; }
     // ---- P5 split: targets seen once -> candidate iff 8-bit diagonal == 0 (initial state of the reference's byte array);
     //               targets possibly seen more than once -> multi list
-    CTA_FOR(h, M) {
-        const uint64_t w = W.A[h];
-        const uint32_t slot = MB_W_SEQ(w) & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
-        const bool multi = (sh->slots[slot >> 4] >> sft) & 2u;
-        const uint32_t ib = cta_append_slot(&sh->cnt[0], multi);
-        if (multi) W.B[ib] = w;
-        const bool single0 = !multi && (w & 0xFFu) == 0;
-        const uint32_t ic = cta_append_slot(&sh->cnt[1], single0);
-        if (single0) W.C[ic] = w;
+    for (uint32_t h0 = 0; h0 < M; h0 += 4 * CTA_NT) {       // four hit words per thread in flight (the list lives in L2)
+        uint64_t wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t h = h0 + u * CTA_NT + CTA_TID; wv[u] = (h < M) ? W.A[h] : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (h0 + u * CTA_NT + CTA_TID < M) {
+            const uint64_t w = wv[u];
+            const uint32_t slot = MB_W_SEQ(w) & (SH::Cfg::NSLOT - 1), sft = (slot & 15u) * 2u;
+            const bool multi = (sh->slots[slot >> 4] >> sft) & 2u;
+            const uint32_t ib = cta_append_slot(&sh->cnt[0], multi);
+            if (multi) { W.B[ib] = w; if (ib < SH::Cfg::MUL_CAP) sh->sMul[ib] = w; }
+            const bool single0 = !multi && (w & 0xFFu) == 0;
+            const uint32_t ic = cta_append_slot(&sh->cnt[1], single0);
+            if (single0) W.C[ic] = w;
+        }
     }
     CTA_SYNC();
-    const uint32_t nMulti = sh->cnt[0];
+    uint32_t nMulti = sh->cnt[0];
+    // A long query has so many hits that unrelated targets share occupancy slots (M^2 / (2 NSLOT) colliding pairs: thousands for M = 30 000): filter the "possibly seen twice" list
+    // again with another hash of the target id -- the hits of a target seen once that collide neither time leave as singles -- until it fits the shared-memory stage below.
+    for (uint32_t round = 1; round <= 2u && nMulti > SH::Cfg::MUL_CAP; round++) {
+        const uint32_t mul = round == 1u ? 0x9E3779B1u : 0x85EBCA6Bu;
+        CTA_SYNC();      // (every thread has read the list length before it is reset)
+        CTA_FOR(i, SH::Cfg::NSLOT / 16) sh->slots[i] = 0;
+        CTA_SINGLE { sh->cnt[0] = 0; }
+        CTA_SYNC();
+        CTA_FOR(e, nMulti) {
+            const uint32_t slot = (MB_W_SEQ(W.B[e]) * mul) >> (32u - SH::Cfg::NSLOT_LOG), sft = (slot & 15u) * 2u;
+            const uint32_t old = mb_atomic_or(&sh->slots[slot >> 4], 1u << sft);
+            if ((old >> sft) & 1u) mb_atomic_or(&sh->slots[slot >> 4], 2u << sft);
+        }
+        CTA_SYNC();
+        for (uint32_t h0 = 0; h0 < nMulti; h0 += 4 * CTA_NT) {
+            uint64_t wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t h = h0 + u * CTA_NT + CTA_TID; wv[u] = (h < nMulti) ? W.B[h] : 0; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (h0 + u * CTA_NT + CTA_TID < nMulti) {
+                const uint64_t w = wv[u];
+                const uint32_t slot = (MB_W_SEQ(w) * mul) >> (32u - SH::Cfg::NSLOT_LOG), sft = (slot & 15u) * 2u;
+                const bool multi = (sh->slots[slot >> 4] >> sft) & 2u;
+                const uint32_t ib = cta_append_slot(&sh->cnt[0], multi);
+                if (multi) W.A[ib] = w;
+                const bool single0 = !multi && (w & 0xFFu) == 0;
+                const uint32_t ic = cta_append_slot(&sh->cnt[1], single0);
+                if (single0) W.C[ic] = w;
+            }
+        }
+        CTA_SYNC();
+        nMulti = sh->cnt[0];
+        CTA_FOR(e, nMulti) { const uint64_t w = W.A[e]; W.B[e] = w; if (e < SH::Cfg::MUL_CAP) sh->sMul[e] = w; }
+        CTA_SYNC();
+    }
     MB_PHASE(5);
     // ---- P6/P7 per-target replay of findDuplicates in arrival order  (CacheFriendlyOperations.cpp:193-262)
     if (nMulti == 0) {
+    } else if (nMulti > T.sortWalkMax && nMulti <= SH::Cfg::MUL_CAP) {
+        // The usual case: the whole stage in shared memory (list, group-ordered copy, hash table), same three passes as the global-memory variant below.
+        uint32_t htLog = SH::Cfg::HT_LOG_MAX - 1u < 6u ? SH::Cfg::HT_LOG_MAX - 1u : 6u; while ((1u << htLog) < 2u * nMulti) htLog++;
+        const uint32_t htN = 1u << htLog;                    // <= SM_NZ / 2
+        uint32_t *htKey = sh->sHt, *htOff = sh->sHt + htN;
+        CTA_FOR(i, 2 * htN) sh->sHt[i] = 0;
+        CTA_SYNC();
+        CTA_FOR(e, nMulti) {
+            const uint32_t id1 = MB_W_SEQ(sh->sMul[e]) + 1u;
+            uint32_t slot = (id1 * 2654435761u) >> (32 - htLog);
+            for (;;) {
+                const uint32_t old = mb_atomic_cas(&htKey[slot], 0u, id1);
+                if (old == 0u || old == id1) break;
+                slot = (slot + 1u) & (htN - 1u);
+            }
+            mb_atomic_add(&htOff[slot], 1u);
+        }
+        CTA_SYNC();
+        cta_exclusive_scan(htOff, htN - 1, &sh->cs);
+        CTA_FOR(e, nMulti) { const uint64_t w = sh->sMul[e]; const uint32_t slot = mb_ht_find(htKey, htLog, MB_W_SEQ(w) + 1u); sh->sGrp[mb_atomic_add(&htOff[slot], 1u)] = w; }   // afterwards htOff[s] = END of group s
+        CTA_SYNC();
+        CTA_FOR(e, nMulti) {      // pass X (see below); the flagged words go back into sMul, in group order
+            const uint64_t w = sh->sGrp[e];
+            const uint32_t slot = mb_ht_find(htKey, htLog, MB_W_SEQ(w) + 1u);
+            const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
+            uint64_t pred = 0; bool has = false;
+            for (uint32_t x = gb; x < ge; x++) { const uint64_t y = sh->sGrp[x]; if (y < w && (!has || y > pred)) { pred = y; has = true; } }
+            const uint32_t d8 = (uint32_t)(w & 0xFFu), last = has ? (uint32_t)(pred & 0xFFu) : 0u;
+            sh->sMul[e] = w | ((d8 == last) ? (1ull << 63) : 0ull);
+        }
+        CTA_SYNC();
+        CTA_FOR(e, nMulti) {      // pass Y
+            const uint64_t wf = sh->sMul[e];
+            if (wf >> 63) {
+                const uint64_t w = wf & ~(1ull << 63);
+                const uint32_t slot = mb_ht_find(htKey, htLog, MB_W_SEQ(w) + 1u);
+                const uint32_t gb = slot ? htOff[slot - 1] : 0u, ge = htOff[slot];
+                uint64_t pc = 0; bool has = false;
+                for (uint32_t x = gb; x < ge; x++) { const uint64_t yf = sh->sMul[x]; const uint64_t y = yf & ~(1ull << 63); if ((yf >> 63) && y < w && (!has || y > pc)) { pc = y; has = true; } }
+                const bool accept = !has || ((uint32_t)(pc & 0xFFu) != (uint32_t)(w & 0xFFu));
+                const uint32_t ic = cta_append_slot(&sh->cnt[1], accept);
+                if (accept) W.C[ic] = w;
+            } else { cta_append_slot(&sh->cnt[1], false); }
+        }
     } else if (nMulti > T.sortWalkMax && nMulti <= (1u << (SH::Cfg::HT_LOG_MAX - 1))) {   // (up to 256 entries one warp sorts in registers: the sorted walk below is cheaper)
         // Sort-free: group the multi list by target with a shared-memory hash table (the k-mer list's space is free now), then every
         // hit looks up its predecessor *of the same target* (largest smaller arrival key) inside its group.
