@@ -107,7 +107,9 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     uint64_t sw_pairs, sw_cells_fwd, sw_cells_rev, sw_target_bytes;
     uint64_t query_residues, n_queries;
     double ms_prep, ms_prefilter, ms_sw_fwd, ms_sw_rev, ms_chain, ms_h2d, ms_d2h, ms_host;
-    uint32_t launches, pad;
+    uint32_t launches;
+    uint32_t overflow_queries;        /* queries the prefilter could not process (work lists exhausted even in the second pass, or >= 32768 residues) and SKIPPED with an empty hit list --
+                                         only under overflow policy "skip" (the default of mb200_predict_exons; mb200_option_set "overflow_policy"); mb200_query_status_get tells which */
     uint64_t pref_phase_cycles[16];   /* k_prefilter: CTA cycles summed over queries, per phase; [15] = between queries */
     double ms_orf, ms_orf_host;       /* mb200_extract_orfs: kernels with the contigs resident (CUDA events) / whole call incl. H2D and D2H (wall clock) */
     uint64_t orf_nucleotides, orf_fragments, orf_residues;
@@ -126,6 +128,11 @@ void mb200_params_default(mb200_params *p);
 /* what `-s <sensitivity>` means for kmer_thr: Prefiltering::getKmerThreshold for a sequence search with k = 6 (M/src/prefiltering/Prefiltering.cpp:1005-1064);
  * -s 4 (MetaEuk's default) -> 127 */
 int mb200_kmer_threshold(float sensitivity);
+/* per-query status of the last prefilter pass over the resident batch: 0 ok, 1 sequence too long, 2 work lists exhausted (reference: QueryMatcher.cpp:280-316 takes its own
+ * overflow path there, which changes the result and is not reproduced).  Policy (mb200_option_set "overflow_policy"): 0 = such a query fails the call (MB200_E_OVERFLOW /
+ * MB200_E_LIMIT; default of the prefilter / search entry points: never a silent drop), 1 = it is skipped with an empty hit list and counted in mb200_stats.overflow_queries
+ * (default of mb200_predict_exons: one pathological fragment must not abort millions), -1 = those defaults. */
+int mb200_query_status_get(mb200_ctx *ctx, uint32_t *status /* n_queries */);
 int mb200_params_set(mb200_ctx *ctx, const mb200_params *p);
 
 /* matrices: built like the reference builds them, or supplied by a caller that already holds the reference's BaseMatrix objects */

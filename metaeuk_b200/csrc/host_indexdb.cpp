@@ -82,6 +82,9 @@ int open_index_db(const std::string &path, IndexDb &db, std::string &err) {
     memcpy(&db.nSeq, p, 8);
     if (!get(E_SEQINDEXSEQOFFSET, (db.nSeq + 1) * 8, p, len)) return bad(err, "SEQINDEXSEQOFFSET entry missing or too short");
     db.seqOff = (const uint64_t *)p;
+    // a corrupt lookup must not turn into out-of-bounds writes below: offsets start at 0 and never decrease; the last one is checked against SEQINDEXDATA next
+    if (db.seqOff[0] != 0) return bad(err, "SEQINDEXSEQOFFSET does not start at 0");
+    for (uint64_t i = 0; i < db.nSeq; i++) if (db.seqOff[i + 1] < db.seqOff[i]) return bad(err, "SEQINDEXSEQOFFSET is not monotonic at sequence " + std::to_string(i));
     if (!get(E_SEQINDEXDATA, db.seqOff[db.nSeq], p, len)) return bad(err, "SEQINDEXDATA entry missing or too short");
     db.masked = p;
     // the stored sequence DB: keys and unmasked residues

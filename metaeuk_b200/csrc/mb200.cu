@@ -200,7 +200,7 @@ struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
-    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optSortWalk = 0;
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optSortWalk = 0, optOverflowPolicy = -1; bool inPredict = false;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
     DevBuf<unsigned char> dIndexArena; size_t arenaBytes = 0;   // offsets | entries | masked | unmasked residues | target offsets in ONE allocation (one ncclBroadcast replicates it)
     void *comm = nullptr;                                        // ncclComm_t created by mb200_comm_init (owned)
@@ -400,6 +400,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return fail(MB200_E_ARG, "null argument");
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
+    else if (n == "overflow_policy") { if (value < -1 || value > 1) return fail(MB200_E_ARG, "overflow_policy: -1 (default per entry point), 0 (fail the call) or 1 (skip the query, count it)"); c->optOverflowPolicy = (int)value; }
     else if (n == "prefilter_sort_walk") { if (value < 0 || value > 256) return fail(MB200_E_ARG, "prefilter_sort_walk: 0..256"); c->optSortWalk = (int)value; }
     else if (n == "prefilter_buckets") { if (value != 0 && value != 1) return fail(MB200_E_ARG, "prefilter_buckets: 0 (offsets + entries arrays) or 1 (inline bucket table)"); c->optBuckets = (int)value; }
     else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
@@ -974,12 +975,17 @@ int mb200_prefilter_resident(mb200_ctx *c) {
             c->rescuedQueries += again.size();
         }
     }
-    for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK)
+    const bool skipBad = c->optOverflowPolicy == 1 || (c->optOverflowPolicy < 0 && c->inPredict);
+    uint32_t nBad = 0;
+    for (uint32_t i = 0; i < nQ; i++) if (status[i] != MB_ST_OK) {
+        if (skipBad) { nBad++; continue; }     // hit count 0 (written by the kernel), status readable through mb200_query_status_get, counted in the stats
         return status[i] == MB_ST_OVERFLOW
             ? fail(MB200_E_OVERFLOW, "query %u (%llu residues): more work than the prefilter's lists hold (explicit cap_*_log2, or the second pass' limits: 2^22 window/neighbour items, 2^21 similar k-mers, "
                    "%llu index hits = where the reference's own overflow path starts) -- lower the sensitivity or shorten the fragment", i,
                    (unsigned long long)(c->hQoff[i + 1] - c->hQoff[i]), (unsigned long long)(2ull * std::max<uint64_t>(1000000ull, c->nT) - 1))
             : fail(MB200_E_LIMIT, "query %u: prefilter status %u (sequence of 32768 or more residues)", i, status[i]);
+    }
+    c->st.overflow_queries = nBad;
     MbPrefStats hs; CU(cudaMemcpy(&hs, c->dStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
     c->st.kmers = hs.kmers; c->st.lookups = hs.lookups; c->st.db_matches = hs.dbMatches; c->st.double_hits = hs.doubleHits; c->st.diag_cells = hs.diagCells; c->st.pref_results = hs.results;
     for (int i = 0; i < 16; i++) c->st.pref_phase_cycles[i] = hs.phase[i];
@@ -1602,6 +1608,7 @@ static int predict_batch(mb200_ctx *c, const char *nuc, const uint64_t *off, uin
     auto tp = std::chrono::steady_clock::now();
     auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double, std::milli>(now - tp).count(); tp = now; };
     memset(&c->st, 0, sizeof(c->st));
+    struct InPredict { mb200_ctx *c; InPredict(mb200_ctx *x) : c(x) { c->inPredict = true; } ~InPredict() { c->inPredict = false; } } inPredictGuard(c);
     TRY(mb200_extract_orfs(c, nuc, off + b0, nb, minLen, maxLen, 1, &n, &orfs, &na, &aa)); lap(0);
     sh.publish(batchIdx, n);
     TRY(mb200_queries_from_orfs(c)); lap(1);
@@ -1658,7 +1665,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->par = p->par; w->mat = p->mat; w->haveMat = p->haveMat; w->ev = p->ev;
     w->dSim3.set_view(p->dSim3.p, p->dSim3.n); w->dCnt3.set_view(p->dCnt3.p, p->dCnt3.n); w->dOffsets.set_view(p->dOffsets.p, p->dOffsets.n);
     w->dKmerBits.set_view(p->dKmerBits.p, p->dKmerBits.n); w->useBits = p->useBits; w->dEntries.set_view(p->dEntries.p, p->dEntries.n);
-    w->optBuckets = p->optBuckets; w->optSortWalk = p->optSortWalk; w->haveBuckets = p->haveBuckets; if (p->haveBuckets) w->dBuckets.set_view(p->dBuckets.p, p->dBuckets.n);
+    w->optBuckets = p->optBuckets; w->optSortWalk = p->optSortWalk; w->optOverflowPolicy = p->optOverflowPolicy; w->haveBuckets = p->haveBuckets; if (p->haveBuckets) w->dBuckets.set_view(p->dBuckets.p, p->dBuckets.n);
     w->dTseqM.set_view(p->dTseqM.p, p->dTseqM.n); w->dTseqU.set_view(p->dTseqU.p, p->dTseqU.n); w->dToff.set_view(p->dToff.p, p->dToff.n);
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
@@ -1693,7 +1700,7 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         a.ms_prep += s.ms_prep; a.ms_prefilter += s.ms_prefilter; a.ms_sw_fwd += s.ms_sw_fwd; a.ms_sw_rev += s.ms_sw_rev; a.ms_chain += s.ms_chain; a.ms_h2d += s.ms_h2d; a.ms_join += s.ms_join;
         a.ms_orf += s.ms_orf; a.ms_orf_host += s.ms_orf_host; a.orf_nucleotides += s.orf_nucleotides; a.orf_fragments += s.orf_fragments; a.orf_residues += s.orf_residues;
         for (int i = 0; i < 16; i++) a.pref_phase_cycles[i] += s.pref_phase_cycles[i];
-        a.launches += s.launches;
+        a.launches += s.launches; a.overflow_queries += s.overflow_queries;
     };
     if (nW == 1) {
         for (uint32_t b = 0; b < nBatches && !rcs[0]; b++) {
@@ -1761,6 +1768,12 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     return 0;
 }
 
+int mb200_query_status_get(mb200_ctx *c, uint32_t *status) {
+    if (!c || !status) return fail(MB200_E_ARG, "null argument");
+    if (!c->havePref || !c->pStatus.p) return fail(MB200_E_STATE, "no resident prefilter result");
+    memcpy(status, c->pStatus.p, (size_t)c->nQ * 4);
+    return 0;
+}
 int mb200_stats_get(mb200_ctx *c, mb200_stats *out) { if (!c || !out) return fail(MB200_E_ARG, "null argument"); *out = c->st; return 0; }
 double mb200_evalue(mb200_ctx *c, int rawScore, int qLen) { return c->ev.evalue(rawScore, qLen, (double)c->totalRes); }
 int mb200_bit_score(mb200_ctx *c, int rawScore) { return c->ev.bitScore(rawScore); }

@@ -64,7 +64,9 @@ static Db openDb(const std::string &name) {
         char *q; E e; e.key = (uint32_t)strtoul(p, &q, 10); e.off = strtoull(q, &q, 10); e.len = strtoull(q, &q, 10);
         es.push_back(e); while (q < end && *q != '\n') q++; p = q + 1;
     }
-    std::stable_sort(es.begin(), es.end(), [](const E &a, const E &b) { return a.off < b.off; });
+    // local ids = key rank, as DBReader::sortIndex assigns them (M/src/commons/DBReader.cpp): the target ids in the index -- and with them the tie-breaks at the --max-seqs cut --
+    // must not depend on where an entry sits in the data file (createsubdb / merged multi-thread output are not in offset order)
+    std::stable_sort(es.begin(), es.end(), [](const E &a, const E &b) { return a.key < b.key; });
     for (auto &e : es) { d.byKey[e.key] = d.keys.size(); d.keys.push_back(e.key); d.off.push_back(e.off); d.len.push_back(e.len); }
     std::vector<char> t; if (readFile(name + ".dbtype", t, false) && t.size() >= 4) memcpy(&d.dbtype, t.data(), 4);
     return d;
@@ -401,6 +403,8 @@ int main(int argc, char **argv) {
             if (o.batchNt > 0) MB(mb200_option_set(s.ctx, "predict_batch_nt", o.batchNt));
             std::vector<uint64_t> coff(order.size() + 1); const mb200_call *calls = nullptr; const mb200_pexon *ex = nullptr; uint64_t nEx = 0;
             MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), o.minLen, o.maxLen, coff.data(), &calls, &ex, &nEx));
+            { mb200_stats st; MB(mb200_stats_get(s.ctx, &st));
+              if (st.overflow_queries) fprintf(stderr, "mb200: warning: %u fragment(s) exceeded the prefilter's work lists (where the reference takes its own overflow path) and were searched with an empty hit list\n", st.overflow_queries); }
             std::map<uint32_t, std::string> out; char line[512];
             for (size_t ci = 0; ci < order.size(); ci++) {
                 std::string e;

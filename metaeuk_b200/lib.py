@@ -35,7 +35,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kmers", "lookups", "db_matches", "double_hits", "diag_cells", "pref_results", "sw_pairs", "sw_cells_fwd",
                                            "sw_cells_rev", "sw_target_bytes", "query_residues", "n_queries")] + \
                [(n, C.c_double) for n in ("ms_prep", "ms_prefilter", "ms_sw_fwd", "ms_sw_rev", "ms_chain", "ms_h2d", "ms_d2h", "ms_host")] + \
-               [("launches", C.c_uint32), ("pad", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16), ("ms_orf", C.c_double), ("ms_orf_host", C.c_double),
+               [("launches", C.c_uint32), ("overflow_queries", C.c_uint32), ("pref_phase_cycles", C.c_uint64 * 16), ("ms_orf", C.c_double), ("ms_orf_host", C.c_double),
                 ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64), ("ms_reduce", C.c_double),
                 ("ms_join", C.c_double), ("ms_predict", C.c_double)] + \
                [(n, C.c_uint64) for n in ("pe_batches", "pe_contigs", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons", "pe_streams")]
@@ -409,6 +409,12 @@ class Context:
         ms = C.c_double(0)
         self._check(self.L.mb200_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def query_status(self, n_queries):
+        """per-query status of the last prefilter pass (0 ok, 1 too long, 2 work lists exhausted); see mb200_query_status_get"""
+        st = np.zeros(n_queries, np.uint32)
+        self._check(self.L.mb200_query_status_get(self.h, _p(st)))
+        return st
 
     def stats(self):
         s = Stats()

@@ -404,6 +404,13 @@ def test_limits_fail_loudly():
     ctx = M.make_context(tdb, cap_items_log2=6, cap_kmers_log2=8, cap_hits_log2=8)   # work lists far too small: error, never a silent drop
     with pytest.raises(Mb200Error):
         M.prefilter(ctx, [(0, prots[0])], tdb)
+    # overflow policy "skip" (the default of mb200_predict_exons): the query is left without hits, counted and reported -- the other queries of the batch keep theirs
+    ctx.option_set("overflow_policy", 1)
+    short = prots[1][:12]                                       # 3 windows: fits even these lists
+    q, qoff = M.encode_many([prots[0], short])
+    hits, cnt = ctx.prefilter(q, qoff)
+    assert cnt[0] == 0 and ctx.stats()["overflow_queries"] == 1
+    assert ctx.query_status(2).tolist() == [2, 0]
     ctx.close()
 
 
