@@ -231,7 +231,7 @@ struct mb200_ctx {
     // predictexons with binary hand-off
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
-    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[2] = {nullptr, nullptr};
+    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -379,7 +379,7 @@ int mb200_ctx_create(int device, mb200_ctx **out) {
 void mb200_ctx_destroy(mb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int k = 0; k < 2; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
+    for (int k = 0; k < 4; k++) { mb200_ctx_destroy(c->workers[k]); c->workers[k] = nullptr; }   // (their index / matrix buffers are views of ours)
     for (int k = 0; k < 4; k++) { if (c->swSide[k]) cudaStreamDestroy(c->swSide[k]); if (c->swJoin[k]) cudaEventDestroy(c->swJoin[k]); c->swSide[k] = nullptr; c->swJoin[k] = nullptr; }
     if (c->swFork) { cudaEventDestroy(c->swFork); c->swFork = nullptr; }
     mb200_comm_release(c); c->dIndexArena.release(); c->dSim3.release(); c->dCnt3.release(); c->dOffsets.release(); c->dKmerBits.release(); c->dEntries.release(); c->dBuckets.release(); c->dTseqM.release(); c->dTseqU.release(); c->dToff.release();
@@ -411,7 +411,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
-    else if (n == "predict_streams") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "predict_streams: 1 or 2"); c->optStreams = (int)value; }
+    else if (n == "predict_streams") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "predict_streams: 1..4"); c->optStreams = (int)value; }
     else if (n == "orf_key_base") { if (value < 0 || value >= (1ll << 32)) return fail(MB200_E_ARG, "orf_key_base must fit 32 bits"); c->optOrfKeyBase = (uint64_t)value; }   // contig shards: fragment keys count over the whole contig DB
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
     return 0;
@@ -1688,10 +1688,10 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     const uint32_t nBatches = (uint32_t)bnd.size() - 1;
     std::vector<PeBatchOut> outs(nBatches);
     PeShared sh; sh.nFragOf.assign(nBatches, -1); sh.base = c->optOrfKeyBase;
-    const int nW = (c->optStreams >= 2 && nBatches >= 2) ? 2 : 1;
-    double ph[2][9] = {{0}};
-    double stageSum[2] = {0, 0}; mb200_stats wst[2]; memset(wst, 0, sizeof(wst));
-    int rcs[2] = {0, 0}; std::string errs[2];
+    const int nW = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)c->optStreams, nBatches));
+    double ph[4][9] = {{0}};
+    mb200_stats wst[4]; memset(wst, 0, sizeof(wst));
+    int rcs[4] = {0, 0, 0, 0}; std::string errs[4];
     const mb200_stats before = c->st;
     auto addStats = [](mb200_stats &a, const mb200_stats &s) {
         a.kmers += s.kmers; a.lookups += s.lookups; a.db_matches += s.db_matches; a.double_hits += s.double_hits; a.diag_cells += s.diag_cells; a.pref_results += s.pref_results;
@@ -1710,7 +1710,7 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         if (rcs[0]) return rcs[0];
     } else {
         TRY(build_buckets(c));      // (shared with the workers as a view)
-        for (int k = 0; k < 2; k++) TRY(worker_sync(c, c->workers[k]));
+        for (int k = 0; k < nW; k++) TRY(worker_sync(c, c->workers[k]));
         std::atomic<uint32_t> next(0);
         auto run = [&](int k) {
             mb200_ctx *w = c->workers[k];
@@ -1724,10 +1724,11 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
                 addStats(wst[k], outs[b].st);
             }
         };
-        std::thread t1(run, 1);
+        std::vector<std::thread> th;
+        for (int k = 1; k < nW; k++) th.emplace_back(run, k);
         run(0);
-        t1.join();
-        for (int k = 0; k < 2; k++) if (rcs[k]) return fail(rcs[k], "%s", errs[k].c_str());
+        for (std::thread &t : th) t.join();
+        for (int k = 0; k < nW; k++) if (rcs[k]) return fail(rcs[k], "%s", errs[k].c_str());
     }
     // concatenate the batches in contig order
     size_t nCalls = 0, nEx = 0;
@@ -1746,15 +1747,14 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     // work counters: sums over all batches; stage times (CUDA events): those of the busier worker stream -- with two streams the kernels of two batches share
     // the GPU, so the per-stream times overlap in wall-clock terms and their sum over both streams would count the same interval twice
     addStats(acc, wst[0]);
-    if (nW == 2) {
-        mb200_stats both = wst[1];
+    if (nW >= 2) {
         auto dev = [](const mb200_stats &s) { return s.ms_orf + s.ms_prep + s.ms_prefilter + s.ms_sw_fwd + s.ms_sw_rev + s.ms_chain; };
-        const mb200_stats &busy = dev(wst[0]) >= dev(wst[1]) ? wst[0] : wst[1];
-        addStats(acc, both);
+        int busyK = 0;
+        for (int k = 1; k < nW; k++) { addStats(acc, wst[k]); if (dev(wst[k]) > dev(wst[busyK])) busyK = k; }
+        const mb200_stats &busy = wst[busyK];
         acc.ms_orf = busy.ms_orf; acc.ms_prep = busy.ms_prep; acc.ms_prefilter = busy.ms_prefilter; acc.ms_sw_fwd = busy.ms_sw_fwd; acc.ms_sw_rev = busy.ms_sw_rev; acc.ms_chain = busy.ms_chain;
         acc.ms_join = busy.ms_join; acc.ms_h2d = busy.ms_h2d; acc.ms_orf_host = busy.ms_orf_host;
     }
-    (void)stageSum;
     if (getenv("MB200_TRACE"))
         for (int k = 0; k < nW; k++)
             fprintf(stderr, "mb200_predict_exons worker %d host phases (ms, wall): orfs %.1f install %.1f prefilter %.1f align %.1f tids %.1f accept %.1f join %.1f chain %.1f output %.1f\n",
