@@ -431,12 +431,12 @@ def bench_predict(args, wl, base, rank, world, local, threads):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    dev_ms = 0.0; pre_ms = 0.0; sts = []
+    dev_ms = 0.0; pre_ms = 0.0; sw_ms = 0.0; devsum_ms = 0.0; sts = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         call_off, calls, exons = ctx.predict_exons(nucP, offP, copy=False)
         st = ctx.stats(); sts.append(st)
-        dev_ms += sum(st[k] for k in STAGES); pre_ms += st["ms_prefilter"]
+        dev_ms += sum(st[k] for k in STAGES); pre_ms += st["ms_prefilter_sum"]; sw_ms += st["ms_sw_fwd_sum"] + st["ms_sw_rev_sum"]; devsum_ms += st["ms_dev_sum"]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     st = sts[-1]
@@ -491,17 +491,19 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                          "last_call_ms": {k: round(st[k], 3) for k in STAGES + ("ms_join", "ms_predict")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": abytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kms * 1e-3) / 1e9 / peak,
                               "peak_source": peak_src, "algorithmic_bytes_per_launch": int(abytes // nb), "kernel_ms": kms / nb, "launches_per_step": nb,
-                              "share_of_step": kms / (1000 * vals[0] / args.steps), "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload),
+                              "share_of_step": pre_ms / devsum_ms if devsum_ms > 0 else None, "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload),
+                              "kernel_ms_note": "CUDA-event durations of k_prefilter summed over the worker streams of the timed steps (with two streams the kernels of two contig batches share the GPU, so each launch is longer than it would be alone; single-stream figures: DESIGN.md section 8)",
                               "random_access": random_access_roofline(st, kms)},
                  "stages_ms": {k: st[k] for k in STAGES + ("ms_join",)}, "stages_ms_per_rank": stage_all,
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons")},
                  "index": idx, "parity": parity,
                  "timing": "value: sum of the CUDA-event stage times of the library stream (contigs of a batch resident), max over ranks; e2e: wall clock of mb200_predict_exons (host contigs in, host call records out) between device synchronisations, max over ranks"})
-    if st["ms_sw_fwd"] + st["ms_sw_rev"] > 0:
-        base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) / ((st["ms_sw_fwd"] + st["ms_sw_rev"]) * 1e-3) / 1e9
-        base["roofline_sw"] = {"kernel": "k_sw_* forward + reverse", "bound": "integer ALU (DPX s16x2)", "achieved": base["gcups_sw"] / 1e3, "unit": "TCUPS",
+    if sw_ms > 0:
+        base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) * args.steps / (sw_ms * 1e-3) / 1e9
+        base["roofline_sw"] = {"kernel": "k_sw_stream forward + reverse", "bound": "integer ALU (DPX s16x2)", "achieved": base["gcups_sw"] / 1e3, "unit": "TCUPS",
                                "peak": 6.14, "peak_source": "DESIGN.md 4.2: SASS of k_sw_stream has 194 ALU-pipe instructions per column step of 32 rows x 2 targets, the ALU pipe issues one warp instruction per 2 cycles per scheduler: 148 SMs x 4 x 2048 cells / 388 cycles x 1.965 GHz",
-                               "frac": base["gcups_sw"] / 1e3 / 6.14, "share_of_step": (st["ms_sw_fwd"] + st["ms_sw_rev"]) / (1000 * vals[0] / args.steps) if world == 1 else None}
+                               "frac": base["gcups_sw"] / 1e3 / 6.14, "share_of_step": sw_ms / devsum_ms if devsum_ms > 0 else None,
+                               "kernel_ms_note": "stage times summed over the worker streams, as for roofline"}
     base["predict_streams"] = int(st.get("pe_streams", 1))
     if args.phase_stats:     # one extra, untimed, instrumented pass for the per-phase breakdown of k_prefilter
         ctx.option_set("phase_stats", 1)

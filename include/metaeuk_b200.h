@@ -118,6 +118,8 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     double ms_join, ms_predict;       /* host join of alignments and fragments per contig / the whole call (wall clock) */
     uint64_t pe_batches, pe_contigs, pe_fragments, pe_alignments, pe_calls, pe_exons;
     uint64_t pe_streams;              /* worker streams the last mb200_predict_exons call used (2: stage times are those of the busier stream) */
+    double ms_prefilter_sum, ms_sw_fwd_sum, ms_sw_rev_sum, ms_dev_sum;   /* mb200_predict_exons: CUDA-event stage times summed over ALL worker streams (kernels of two streams share the GPU, so each
+                                                                             is longer than it would be alone): the denominators of the rooflines in bench.py; ms_dev_sum = all device stages */
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);

@@ -78,40 +78,55 @@ MB_DEV int mb_dp_find(MbPE *pe, int32_t *ord, int32_t *pn, MbRow *rows, const Mb
     return best;
 }
 
+// One (contig, target) group: cands[0..m) all have the same target key (m candidates of one contig, sorted by orfKey); every array is the group's own slice.
+// idxBase = index of cands[0] inside its contig (candidate / exon indices in the output are contig-relative).  Returns the number of calls (appended to calls[0..)),
+// or -1 on an illegal codon segment length; the exons of the calls are appended to exons[0..) (at most m of each).
+MB_DEV int mb_chain_group(const MbCand *cands, uint32_t m, uint32_t idxBase, const MbChainParams &P, MbPE *pe, int32_t *ordPlus, int32_t *ordMinus, MbRow *rows,
+                          MbCall *calls, MbExon *exons) {
+    uint32_t nCalls = 0, nEx = 0;
+    int32_t np = 0, nm = 0;
+    for (uint32_t k = 0; k < m; k++) {
+        const MbCand &c = cands[k]; MbPE &e = pe[k];
+        e.cand = k; e.bitScore = c.bitScore; e.tStart = c.tStart; e.tEnd = c.tEnd; e.tLen = c.tLen; e.used = 0;
+        int strand;
+        if (c.fragFrom < c.fragTo) { e.cStart = c.fragFrom + c.qStart * 3; e.cEnd = c.fragFrom + c.qEnd * 3 + 2; strand = 1; }
+        else { e.cStart = -1 * (c.fragFrom - c.qStart * 3); e.cEnd = -1 * (c.fragFrom - c.qEnd * 3 - 2); strand = -1; }
+        e.nucLen = e.cEnd - e.cStart + 1;
+        if (e.nucLen % 3 != 0) return -1;
+        e.aaLen = e.nucLen / 3;
+        const int aal = (e.nucLen < 0 ? -e.nucLen : e.nucLen) / 3;
+        if (aal >= P.minExonAa) { if (strand == 1) ordPlus[np++] = (int32_t)k; else ordMinus[nm++] = (int32_t)k; }
+    }
+    int it = 0;
+    while (it < P.maxSets && (np > 0 || nm > 0)) {
+        for (int s = 0; s < 2; s++) {
+            const uint32_t exBegin = nEx;
+            const int tot = (s == 0) ? mb_dp_find(pe, ordPlus, &np, rows, P, exons, &nEx, 0u - idxBase) : mb_dp_find(pe, ordMinus, &nm, rows, P, exons, &nEx, 0u - idxBase);
+            if (nEx > exBegin) {
+                MbCall &cl = calls[nCalls++]; cl.targetKey = cands[0].targetKey; cl.strand = (s == 0) ? 1 : -1; cl.totalBitScore = tot; cl.nExons = (int32_t)(nEx - exBegin);
+                cl.exonBegin = idxBase + exBegin; cl.pad = 0; cl.evalue = 0.0;
+                const MbExon &f = exons[exBegin], &l = exons[nEx - 1];
+                cl.lowCoord = (s == 0) ? f.contigStart : (-1 * l.contigEnd); cl.highCoord = (s == 0) ? l.contigEnd : (-1 * f.contigStart);   // PredictionParser.h:236-237
+            }
+        }
+        it++;
+    }
+    return (int)nCalls;
+}
+
 // One contig: cands[0..n) sorted by (targetKey, orfKey).  Scratch arrays have n entries each.  Emits every optimal set
-// (host applies the e-value filter).  Returns the number of calls, or -1 on an illegal codon segment length.
+// (host applies the e-value filter).  Returns the number of calls, or -1 on an illegal codon segment length.  Calls land in calls[0..), in target order; the exons of a
+// group stay in the group's own slice of exons[] (calls carry contig-relative exon indices).
 MB_DEV int mb_chain_contig(const MbCand *cands, uint32_t n, const MbChainParams &P, MbPE *pe, int32_t *ordPlus, int32_t *ordMinus, MbRow *rows,
                            MbCall *calls, MbExon *exons, uint32_t *nExonsOut) {
     uint32_t nCalls = 0, nEx = 0, i = 0;
     while (i < n) {
         uint32_t j = i; while (j < n && cands[j].targetKey == cands[i].targetKey) j++;
-        int32_t np = 0, nm = 0;
-        for (uint32_t k = i; k < j; k++) {
-            const MbCand &c = cands[k]; MbPE &e = pe[k];
-            e.cand = k; e.bitScore = c.bitScore; e.tStart = c.tStart; e.tEnd = c.tEnd; e.tLen = c.tLen; e.used = 0;
-            int strand;
-            if (c.fragFrom < c.fragTo) { e.cStart = c.fragFrom + c.qStart * 3; e.cEnd = c.fragFrom + c.qEnd * 3 + 2; strand = 1; }
-            else { e.cStart = -1 * (c.fragFrom - c.qStart * 3); e.cEnd = -1 * (c.fragFrom - c.qEnd * 3 - 2); strand = -1; }
-            e.nucLen = e.cEnd - e.cStart + 1;
-            if (e.nucLen % 3 != 0) return -1;
-            e.aaLen = e.nucLen / 3;
-            const int aal = (e.nucLen < 0 ? -e.nucLen : e.nucLen) / 3;
-            if (aal >= P.minExonAa) { if (strand == 1) ordPlus[i + np++] = (int32_t)k; else ordMinus[i + nm++] = (int32_t)k; }
-        }
-        int it = 0;
-        while (it < P.maxSets && (np > 0 || nm > 0)) {
-            for (int s = 0; s < 2; s++) {
-                const uint32_t exBegin = nEx;
-                const int tot = (s == 0) ? mb_dp_find(pe, ordPlus + i, &np, rows + i, P, exons, &nEx, 0) : mb_dp_find(pe, ordMinus + i, &nm, rows + i, P, exons, &nEx, 0);
-                if (nEx > exBegin) {
-                    MbCall &cl = calls[nCalls++]; cl.targetKey = cands[i].targetKey; cl.strand = (s == 0) ? 1 : -1; cl.totalBitScore = tot; cl.nExons = (int32_t)(nEx - exBegin);
-                    cl.exonBegin = exBegin; cl.pad = 0; cl.evalue = 0.0;
-                    const MbExon &f = exons[exBegin], &l = exons[nEx - 1];
-                    cl.lowCoord = (s == 0) ? f.contigStart : (-1 * l.contigEnd); cl.highCoord = (s == 0) ? l.contigEnd : (-1 * f.contigStart);   // PredictionParser.h:236-237
-                }
-            }
-            it++;
-        }
+        // (the group writes its calls behind the contig's earlier ones: at most one call per candidate and strand round, so calls[nCalls..] never runs into a later group's slice)
+        const int r = mb_chain_group(cands + i, j - i, i, P, pe + i, ordPlus + i, ordMinus + i, rows + i, calls + nCalls, exons + i);
+        if (r < 0) return -1;
+        for (int k = 0; k < r; k++) nEx += (uint32_t)calls[nCalls + k].nExons;
+        nCalls += (uint32_t)r;
         i = j;
     }
     *nExonsOut = nEx;

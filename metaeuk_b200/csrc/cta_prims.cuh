@@ -188,10 +188,35 @@ MB_DEV_CALL void cta_sort_u64(uint64_t *a, uint32_t n) {
         __syncthreads();
         return;
     }
+    // Longer lists: bitonic network with every warp keeping a 64-key chunk in registers (two keys per lane).  Network steps between keys less than 64 apart stay inside a
+    // chunk (shuffles / register pairs, no barrier); only the steps with a distance of 64 or more go through memory with a block barrier: 10 barriers for 512 keys, not 45.
     for (uint32_t i = n + threadIdx.x; i < n2; i += blockDim.x) a[i] = ~0ull;
     __syncthreads();
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5, nChunks = n2 >> 6;
+    for (uint32_t c = warp; c < nChunks; c += nWarps) {       // chunks sorted on their own: network stages k = 2..64
+        const uint32_t base = c << 6;
+        uint64_t k0 = a[base + lane], k1 = a[base + 32u + lane];
+#pragma unroll
+        for (uint32_t k = 2; k <= 64u; k <<= 1) {
+#pragma unroll
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                if (j == 32u) {
+                    const bool asc = ((base & 64u) == 0);     // k == 64: the direction alternates from chunk to chunk
+                    const bool sw = (k0 > k1) == asc; const uint64_t x = k0; k0 = sw ? k1 : k0; k1 = sw ? x : k1;
+                } else {
+                    const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, (int)j), o1 = __shfl_xor_sync(0xffffffffu, k1, (int)j);
+                    const bool lower = (lane & j) == 0;
+                    const bool asc0 = k == 64u ? ((base & 64u) == 0) : ((lane & k) == 0), asc1 = k == 64u ? asc0 : (((32u + lane) & k) == 0);
+                    k0 = (asc0 == lower) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+                    k1 = (asc1 == lower) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+                }
+            }
+        }
+        a[base + lane] = k0; a[base + 32u + lane] = k1;
+    }
+    __syncthreads();
+    for (uint32_t k = 128; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= 64u; j >>= 1) {         // distances of 64 and more: through memory
             for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
                 const uint32_t l = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two: (t / j) * 2j + t % j
                 const uint32_t r = l + j;
@@ -201,6 +226,21 @@ MB_DEV_CALL void cta_sort_u64(uint64_t *a, uint32_t n) {
             }
             __syncthreads();
         }
+        for (uint32_t c = warp; c < nChunks; c += nWarps) {   // distances 32..1: inside the chunk, one direction for the whole chunk
+            const uint32_t base = c << 6;
+            const bool asc = ((base & k) == 0);
+            uint64_t k0 = a[base + lane], k1 = a[base + 32u + lane];
+            { const bool sw = (k0 > k1) == asc; const uint64_t x = k0; k0 = sw ? k1 : k0; k1 = sw ? x : k1; }
+#pragma unroll
+            for (uint32_t j = 16; j > 0; j >>= 1) {
+                const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, (int)j), o1 = __shfl_xor_sync(0xffffffffu, k1, (int)j);
+                const bool lower = (lane & j) == 0;
+                k0 = (asc == lower) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+                k1 = (asc == lower) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+            }
+            a[base + lane] = k0; a[base + 32u + lane] = k1;
+        }
+        __syncthreads();
     }
 #else
     std::sort(a, a + n);

@@ -99,18 +99,34 @@ __global__ void __launch_bounds__(SH::Cfg::NT, SH::Cfg::CTAS) k_prefilter(MbPref
 #include "sw_stream.cuh"
 #include "orf_kernels.cuh"
 
-// ---- exon chaining: one contig per thread -----------------------------------------------------------
-__global__ void __launch_bounds__(128) k_chain(const MbCand *__restrict__ cands, const uint64_t *__restrict__ candOff, uint32_t nContigs, MbChainParams P,
-                                               MbPE *pe, int32_t *ordPlus, int32_t *ordMinus, MbRow *rows, MbCall *calls, MbExon *exons,
-                                               int32_t *callCount, uint32_t *exonCount) {
+// ---- exon chaining: one thread per (contig, target) group -- a contig has hundreds of groups of a few candidates each, so a batch of 500 contigs gives ~10^5 independent DPs
+//      (round 1 ran one contig per thread: 500 threads on 4 CTAs, 8.8 ms per C4 batch).  A thread whose candidate is the first of its group runs the group; calls and exons
+//      land in the group's own slices (at most one call / exon per candidate), k_chain_compact then lines the calls of a contig up in target order.
+__global__ void __launch_bounds__(128) k_chain_groups(const MbCand *__restrict__ cands, const uint64_t *__restrict__ candOff, uint32_t nContigs, uint64_t n, MbChainParams P,
+                                                      MbPE *pe, int32_t *ordPlus, int32_t *ordMinus, MbRow *rows, MbCall *grpCalls, MbExon *exons, int32_t *grpCnt) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t lo = 0, hi = nContigs;   // candOff[lo] <= g < candOff[hi]
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (candOff[mid] <= g) lo = mid; else hi = mid; }
+    const uint64_t b = candOff[lo], e = candOff[lo + 1];
+    const uint32_t key = cands[g].targetKey;
+    if (g > b && cands[g - 1].targetKey == key) { grpCnt[g] = 0; return; }        // not the first candidate of its group
+    uint64_t j = g + 1; while (j < e && cands[j].targetKey == key) j++;
+    grpCnt[g] = mb_chain_group(cands + g, (uint32_t)(j - g), (uint32_t)(g - b), P, pe + g, ordPlus + g, ordMinus + g, rows + g, grpCalls + g, exons + g);
+}
+__global__ void __launch_bounds__(128) k_chain_compact(const uint64_t *__restrict__ candOff, uint32_t nContigs, const int32_t *__restrict__ grpCnt, const MbCall *__restrict__ grpCalls,
+                                                       MbCall *calls, int32_t *callCount) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nContigs) return;
-    const uint64_t b = candOff[c]; const uint32_t n = (uint32_t)(candOff[c + 1] - b);
-    uint32_t nEx = 0;
-    callCount[c] = mb_chain_contig(cands + b, n, P, pe + b, ordPlus + b, ordMinus + b, rows + b, calls + 2 * b, exons + b, &nEx);
-    exonCount[c] = nEx;
+    const uint64_t b = candOff[c], e = candOff[c + 1];
+    int32_t nC = 0;
+    for (uint64_t g = b; g < e; g++) {
+        const int32_t cnt = grpCnt[g];
+        if (cnt < 0) { nC = -1; break; }                                           // illegal codon segment length
+        for (int32_t k = 0; k < cnt; k++) calls[2 * b + (uint64_t)nC++] = grpCalls[g + (uint64_t)k];
+    }
+    callCount[c] = nC;
 }
-
 // ---- reduceredundancy: one contig per thread ---------------------------------------------------------
 __global__ void __launch_bounds__(128) k_reduce(const MbPred *__restrict__ preds, const uint64_t *__restrict__ predOff, uint32_t nContigs, const uint32_t *__restrict__ exonKeys,
                                                 MbPredOut *out, uint32_t *memberOrder, uint32_t *repOrder, uint32_t *repCount, uint32_t *flag, uint32_t *tmp) {
@@ -230,7 +246,7 @@ struct mb200_ctx {
     bool haveAln = false;
     // predictexons with binary hand-off
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
-    DevBuf<uint32_t> dChExCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
+    DevBuf<uint32_t> dChExCnt; DevBuf<MbCall> dChGrpCalls; DevBuf<int32_t> dChGrpCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
@@ -390,7 +406,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dSwDesc.release(); c->dSwDescRev.release(); c->dPassRec.release(); c->dTrace2.release(); c->dFallback.release();
     c->pFlatHits.release(); c->pOff.release(); c->pStatus.release(); c->pOrfRecs.release(); c->pOrfAa.release();
     c->dChCand.release(); c->dChOff.release(); c->dChPE.release(); c->dChOp.release(); c->dChOm.release(); c->dChCallCnt.release(); c->dChRows.release(); c->dChCalls.release();
-    c->dChEx.release(); c->dChExCnt.release(); c->pChCalls.release(); c->pChEx.release(); c->pChCnt.release();
+    c->dChEx.release(); c->dChExCnt.release(); c->dChGrpCalls.release(); c->dChGrpCnt.release(); c->pChCalls.release(); c->pChEx.release(); c->pChCnt.release();
     c->dNuc.release(); c->dNucOff.release(); c->dOrfAaCnt.release(); c->dOrfRecBase.release(); c->dOrfAaBase.release(); c->dOrfCnt.release(); c->dOrfTab.release(); c->dOrfRecs.release(); c->dOrfAa.release(); c->dOrfCodes.release();
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1532,9 +1548,12 @@ int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, 
     MbChainParams P; P.minIntron = c->par.min_intron; P.maxIntron = c->par.max_intron; P.minExonAa = c->par.min_exon_aa; P.maxOverlap = c->par.max_overlap;
     P.gapOpen = c->par.set_gap_open; P.gapExtend = c->par.set_gap_extend; P.maxSets = c->par.max_exon_sets; P.tcov = c->par.tcov;
     CU(cudaEventRecord(c->ev0, c->stream));
-    MB_LAUNCH((k_chain), (nContigs + 127) / 128, 128, 0, c->stream, c->dChCand.p, c->dChOff.p, nContigs, P, c->dChPE.p, c->dChOp.p, c->dChOm.p, c->dChRows.p, c->dChCalls.p, c->dChEx.p,
-                                                           c->dChCallCnt.p, c->dChExCnt.p);
+    TRY(c->dChGrpCalls.alloc(n)); TRY(c->dChGrpCnt.alloc(n));
+    MB_LAUNCH((k_chain_groups), (unsigned)((n + 127) / 128), 128, 0, c->stream, c->dChCand.p, c->dChOff.p, nContigs, n, P, c->dChPE.p, c->dChOp.p, c->dChOm.p, c->dChRows.p,
+              c->dChGrpCalls.p, c->dChEx.p, c->dChGrpCnt.p);
     CU(cudaGetLastError());
+    MB_LAUNCH((k_chain_compact), (nContigs + 127) / 128, 128, 0, c->stream, c->dChOff.p, nContigs, c->dChGrpCnt.p, c->dChGrpCalls.p, c->dChCalls.p, c->dChCallCnt.p);
+    CU(cudaGetLastError()); c->st.launches++;
     CU(cudaEventRecord(c->ev1, c->stream));
     // only the used prefix of every contig's call / exon range is meaningful, but the ranges are interleaved with unused slots: copy whole arrays
     CU(cudaMemcpyAsync(c->pChCalls.p, c->dChCalls.p, 2 * n * sizeof(MbCall), cudaMemcpyDeviceToHost, c->stream));
@@ -1747,6 +1766,10 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     // work counters: sums over all batches; stage times (CUDA events): those of the busier worker stream -- with two streams the kernels of two batches share
     // the GPU, so the per-stream times overlap in wall-clock terms and their sum over both streams would count the same interval twice
     addStats(acc, wst[0]);
+    for (int k = 0; k < nW; k++) {
+        acc.ms_prefilter_sum += wst[k].ms_prefilter; acc.ms_sw_fwd_sum += wst[k].ms_sw_fwd; acc.ms_sw_rev_sum += wst[k].ms_sw_rev;
+        acc.ms_dev_sum += wst[k].ms_orf + wst[k].ms_prep + wst[k].ms_prefilter + wst[k].ms_sw_fwd + wst[k].ms_sw_rev + wst[k].ms_chain;
+    }
     if (nW >= 2) {
         auto dev = [](const mb200_stats &s) { return s.ms_orf + s.ms_prep + s.ms_prefilter + s.ms_sw_fwd + s.ms_sw_rev + s.ms_chain; };
         int busyK = 0;
