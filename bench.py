@@ -211,7 +211,9 @@ def random_access_roofline(st, kernel_ms):
     peak = 40.6
     ach = st["kmers"] / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     return {"what": "index bucket lookups (one random 256-bit HBM read per similar k-mer)", "achieved": ach, "peak": peak, "unit": "G accesses/s", "frac": ach / peak,
-            "peak_source": "measured: tools/microbench/randgather.cu on B200, profiles/r02_randgather.txt (40.6 G/s from 1.5 GB; 37.8 G/s from 4 GB)"}
+            "peak_source": "measured: tools/microbench/randgather.cu on B200, profiles/r02_randgather.txt (40.6 G/s from 1.5 GB; 37.8 G/s from 4 GB)",
+            "bytes_note": "by default every random 8- or 32-byte read moves a 128-byte line of DRAM on this GPU (ncu: 3.83-4.07 dram sectors per access; 1.96 with the .L2::64B qualifier) and the rate is "
+                          "39.4 G/s either way (tools/microbench/randgather2.cu, profiles/r02s_randgather2.txt): a rate ceiling, not a byte ceiling"}
 
 
 def measured_peak():
@@ -436,7 +438,7 @@ def bench_predict(args, wl, base, rank, world, local, threads):
     for _ in range(args.steps):
         call_off, calls, exons = ctx.predict_exons(nucP, offP, copy=False)
         st = ctx.stats(); sts.append(st)
-        dev_ms += sum(st[k] for k in STAGES); pre_ms += st["ms_prefilter_sum"]; sw_ms += st["ms_sw_fwd_sum"] + st["ms_sw_rev_sum"]; devsum_ms += st["ms_dev_sum"]
+        dev_ms += st["ms_dev_busy"]; pre_ms += st["ms_prefilter_sum"]; sw_ms += st["ms_sw_fwd_sum"] + st["ms_sw_rev_sum"]; devsum_ms += st["ms_dev_sum"]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     st = sts[-1]
@@ -477,6 +479,7 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                   "against": "dp_predictions of the unmodified reference (metaeuk predictexons module chain, --mask 1) on the same contigs and proteins"}
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes_prefilter(st); kms = pre_ms / args.steps
+    per_kmer = ncu_traffic("dram_bytes_per_similar_kmer_c4")
     nb = max(1, int(st["pe_batches"]))
     base["config"].update({"fragments": total_frag, "fragments_per_gpu": nfrag_local, "contigs": nC, "contigs_per_gpu": c1 - c0, "nucleotides_per_gpu": int(nuc.nbytes),
                            "planted_genes_rank0": genes, "stages": "extractorfs+translatenucs+prefilter+align+resultspercontig+collectoptimalset",
@@ -491,13 +494,16 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                          "last_call_ms": {k: round(st[k], 3) for k in STAGES + ("ms_join", "ms_predict")}},
                  "roofline": {"kernel": "k_prefilter", "bound": "hbm", "achieved": abytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / (kms * 1e-3) / 1e9 / peak,
                               "peak_source": peak_src, "algorithmic_bytes_per_launch": int(abytes // nb), "kernel_ms": kms / nb, "launches_per_step": nb,
-                              "share_of_step": pre_ms / devsum_ms if devsum_ms > 0 else None, "traffic": ncu_traffic("dram_bytes_per_launch_" + args.workload),
+                              "share_of_step": pre_ms / devsum_ms if devsum_ms > 0 else None,
+                              "traffic": int(per_kmer * st["kmers"] / nb) if per_kmer else None,
+                              "traffic_frac": (per_kmer * st["kmers"] / (kms * 1e-3) / 1e9 / peak) if per_kmer and kms > 0 else None,
+                              "traffic_note": "DRAM bytes per launch = %.1f B per similar k-mer (ncu, dram__sectors_read + dram__sectors_write of both k_prefilter launches of a C4/10 step; profiles/prefilter_traffic.json) x the similar k-mers of a launch of THIS run; traffic_frac = that / kernel time / peak" % (per_kmer or 0),
                               "kernel_ms_note": "CUDA-event durations of k_prefilter summed over the worker streams of the timed steps (with two streams the kernels of two contig batches share the GPU, so each launch is longer than it would be alone; single-stream figures: DESIGN.md section 8)",
                               "random_access": random_access_roofline(st, kms)},
                  "stages_ms": {k: st[k] for k in STAGES + ("ms_join",)}, "stages_ms_per_rank": stage_all,
                  "work": {k: int(st[k]) for k in ("kmers", "db_matches", "double_hits", "pref_results", "sw_pairs", "sw_cells_fwd", "sw_cells_rev", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons")},
                  "index": idx, "parity": parity,
-                 "timing": "value: sum of the CUDA-event stage times of the library stream (contigs of a batch resident), max over ranks; e2e: wall clock of mb200_predict_exons (host contigs in, host call records out) between device synchronisations, max over ranks"})
+                 "timing": "value: fragments / device-busy time = length of the union, over the library's worker streams, of the CUDA-event intervals of every stage (ORFs, prep, prefilter, forward / reverse alignment, chaining; contigs of a batch resident) on one device timeline (mb200_stats.ms_dev_busy: no double counting of overlapped streams, host-only gaps excluded), max over ranks; e2e: wall clock of mb200_predict_exons (host contigs in, host call records out) between device synchronisations, max over ranks; stages_ms: per-stage event times of the busier worker stream (the streams share the GPU, so they do not add up to the busy time)"})
     if sw_ms > 0:
         base["gcups_sw"] = (st["sw_cells_fwd"] + st["sw_cells_rev"]) * args.steps / (sw_ms * 1e-3) / 1e9
         base["roofline_sw"] = {"kernel": "k_sw_stream forward + reverse", "bound": "integer ALU (DPX s16x2)", "achieved": base["gcups_sw"] / 1e3, "unit": "TCUPS",

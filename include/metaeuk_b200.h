@@ -120,6 +120,9 @@ typedef struct mb200_stats {   /* algorithmic work counters of the last prefilte
     uint64_t pe_streams;              /* worker streams the last mb200_predict_exons call used (2: stage times are those of the busier stream) */
     double ms_prefilter_sum, ms_sw_fwd_sum, ms_sw_rev_sum, ms_dev_sum;   /* mb200_predict_exons: CUDA-event stage times summed over ALL worker streams (kernels of two streams share the GPU, so each
                                                                              is longer than it would be alone): the denominators of the rooflines in bench.py; ms_dev_sum = all device stages */
+    double ms_dev_busy;               /* mb200_predict_exons: length of the UNION over all worker streams of the stage intervals [start event, end event] on one device timeline, i.e. the time at
+                                         least one stage of the call had work in flight on the GPU.  With one stream it equals the sum of the stage times; with two it is the device time of the
+                                         call without double counting (and without the host-only gaps): the denominator of bench.py's resident throughput */
 } mb200_stats;
 
 int mb200_ctx_create(int device, mb200_ctx **out);

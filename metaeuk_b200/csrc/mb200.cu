@@ -216,7 +216,7 @@ struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
-    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optSortWalk = 0, optOverflowPolicy = -1; bool inPredict = false;
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optStreamHint = 1, optSortWalk = 0, optOverflowPolicy = -1; bool inPredict = false;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
     DevBuf<unsigned char> dIndexArena; size_t arenaBytes = 0;   // offsets | entries | masked | unmasked residues | target offsets in ONE allocation (one ncclBroadcast replicates it)
     void *comm = nullptr;                                        // ncclComm_t created by mb200_comm_init (owned)
@@ -251,6 +251,8 @@ struct mb200_ctx {
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
+    cudaEvent_t evOrigin = nullptr, originRef = nullptr;    // mb200_predict_exons: origin of the call's device timeline (owned by the caller's context; workers hold a reference)
+    std::vector<std::pair<float, float>> busyIv;            // stage intervals of this context on that timeline (ms_dev_busy)
     cudaStream_t swSide[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t swFork = nullptr, swJoin[4] = {nullptr, nullptr, nullptr, nullptr};   // the alignment classes of one batch run side by side
 };
 
@@ -349,6 +351,13 @@ static int sync_check(mb200_ctx *c, const char *what) {
     if (e != cudaSuccess) return fail(MB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return 0;
 }
+// a finished stage [a, b] (both events complete) on the device timeline of the running mb200_predict_exons call
+static void stage_interval(mb200_ctx *c, cudaEvent_t a, cudaEvent_t b) {
+    if (!c->originRef) return;
+    float s0 = 0, s1 = 0;
+    if (cudaEventElapsedTime(&s0, c->originRef, a) != cudaSuccess || cudaEventElapsedTime(&s1, c->originRef, b) != cudaSuccess) { cudaGetLastError(); return; }
+    c->busyIv.emplace_back(s0, s1);
+}
 
 // =====================================================================================================
 // C ABI
@@ -408,7 +417,7 @@ void mb200_ctx_destroy(mb200_ctx *c) {
     c->dChCand.release(); c->dChOff.release(); c->dChPE.release(); c->dChOp.release(); c->dChOm.release(); c->dChCallCnt.release(); c->dChRows.release(); c->dChCalls.release();
     c->dChEx.release(); c->dChExCnt.release(); c->dChGrpCalls.release(); c->dChGrpCnt.release(); c->pChCalls.release(); c->pChEx.release(); c->pChCnt.release();
     c->dNuc.release(); c->dNucOff.release(); c->dOrfAaCnt.release(); c->dOrfRecBase.release(); c->dOrfAaBase.release(); c->dOrfCnt.release(); c->dOrfTab.release(); c->dOrfRecs.release(); c->dOrfAa.release(); c->dOrfCodes.release();
-    if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->evOrigin) cudaEventDestroy(c->evOrigin); if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->evT0) cudaEventDestroy(c->evT0); if (c->evT1) cudaEventDestroy(c->evT1); if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -417,6 +426,13 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
     else if (n == "overflow_policy") { if (value < -1 || value > 1) return fail(MB200_E_ARG, "overflow_policy: -1 (default per entry point), 0 (fail the call) or 1 (skip the query, count it)"); c->optOverflowPolicy = (int)value; }
+    else if (n == "prefilter_stream_hint") { if (value < 0 || value > 15) return fail(MB200_E_ARG, "prefilter_stream_hint: bit 0 = index reads L1 no-allocate + L2 evict-first, bit 1 = 64-byte HBM fetch, bit 2 = L2 prefetch of the second bucket pair, bit 3 = L2 prefetch of long lists"); c->optStreamHint = (int)value; }
+    else if (n == "l2_fetch_granularity") {   // diagnostic: cudaLimitMaxL2FetchGranularity of the context's device (32, 64 or 128 bytes; a hint the driver may ignore)
+        if (value != 32 && value != 64 && value != 128) return fail(MB200_E_ARG, "l2_fetch_granularity: 32, 64 or 128");
+#ifndef MB200_SIMT_EMU
+        CU(cudaSetDevice(c->device)); CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+#endif
+    }
     else if (n == "prefilter_sort_walk") { if (value < 0 || value > 256) return fail(MB200_E_ARG, "prefilter_sort_walk: 0..256"); c->optSortWalk = (int)value; }
     else if (n == "prefilter_buckets") { if (value != 0 && value != 1) return fail(MB200_E_ARG, "prefilter_buckets: 0 (offsets + entries arrays) or 1 (inline bucket table)"); c->optBuckets = (int)value; }
     else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
@@ -781,7 +797,7 @@ static int queries_install(mb200_ctx *c, const uint8_t *q, const uint8_t *qDev, 
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prep = ms; c->st.launches++;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prep = ms; c->st.launches++; stage_interval(c, c->ev0, c->ev1);
     }
     c->st.query_residues = tot; c->st.n_queries = nQ;
     return 0;
@@ -878,7 +894,7 @@ int mb200_extract_orfs(mb200_ctx *c, const char *nuc, const uint64_t *off, uint3
     }
     TRY(sync_check(c, "k_orf_scan (emit) / k_orf_translate"));
     float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->st.ms_orf = ms; c->st.orf_nucleotides = total; c->st.orf_fragments = n; c->st.orf_residues = na; c->st.launches += 3;
+    c->st.ms_orf = ms; stage_interval(c, c->ev0, c->ev1); c->st.orf_nucleotides = total; c->st.orf_fragments = n; c->st.orf_residues = na; c->st.launches += 3;
     c->st.ms_orf_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     c->nOrfs = n; c->nOrfAa = na;
     *nOrfs = n; *nAa = na; *orfs = reinterpret_cast<const mb200_orf *>(c->pOrfRecs.p); *aa = c->pOrfAa.p;
@@ -939,7 +955,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
     MbPrefTables T; memset(&T, 0, sizeof(T));
     T.sim3 = c->dSim3.p; T.cnt3 = c->dCnt3.p; T.offsets = c->dOffsets.p; T.kmerBits = c->useBits ? c->dKmerBits.p : nullptr; T.entries = c->dEntries.p; T.buckets = (c->optBuckets && c->haveBuckets) ? c->dBuckets.p : nullptr; T.tseq = c->dTseqM.p; T.toff = c->dToff.p; T.nT = c->nT;
     T.kmerThr = c->par.kmer_thr; T.maxHits = c->par.max_res_list_len; T.minDiag = c->par.min_diag_score; T.binMask = (uint32_t)c->par.bin_size - 1;
-    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.phaseStats = c->optPhaseStats; T.sortWalkMax = (uint32_t)c->optSortWalk;
+    T.capP = c->capP; T.capI = c->capI; T.capK = c->capK; T.phaseStats = c->optPhaseStats; T.sortWalkMax = (uint32_t)c->optSortWalk; T.streamHint = (uint32_t)c->optStreamHint;
     T.capM = (uint32_t)std::min<uint64_t>(c->capM, 2ull * std::max<uint64_t>(1000000ull, c->nT) - 1);   // beyond that the reference switches to its own overflow path (QueryMatcher.cpp:43,280-305)
     if (nQ) {
         CU(cudaEventRecord(c->ev0, c->stream));
@@ -955,7 +971,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prefilter = ms; c->st.launches++;
+        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_prefilter = ms; c->st.launches++; stage_interval(c, c->ev0, c->ev1);
     }
     // status check: any query that could not be processed is an error, never a silent drop
     TRY(c->pStatus.alloc(nQ + 1));
@@ -987,7 +1003,7 @@ int mb200_prefilter_resident(mb200_ctx *c) {
             CU(cudaEventRecord(c->ev1, c->stream));
             CU(cudaMemcpyAsync(status, c->dStatus.p, (size_t)(nQ + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
-            float ms2 = 0; CU(cudaEventElapsedTime(&ms2, c->ev0, c->ev1)); c->st.ms_prefilter += ms2; c->st.launches++;
+            float ms2 = 0; CU(cudaEventElapsedTime(&ms2, c->ev0, c->ev1)); c->st.ms_prefilter += ms2; c->st.launches++; stage_interval(c, c->ev0, c->ev1);
             c->rescuedQueries += again.size();
         }
     }
@@ -1107,7 +1123,7 @@ static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t 
     CU(cudaMemcpyAsync(hn, dNPass, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "forward alignment kernel"));
-    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
+    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0]; stage_interval(c, c->ev0, c->ev1);
     if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
     const uint32_t nPass = hn[0];
     // queries longer than 1024 residues: every hit goes straight to the 32-bit kernel (forward + reverse; the host applies the e-value test)
@@ -1158,7 +1174,7 @@ static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t 
     if (nFb) CU(cudaMemcpyAsync(c->hTrace.data() + nPass, c->dTrace2.p, (size_t)nFb * sizeof(SwTraceOut), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "reverse alignment kernels"));
-    CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1];
+    CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1]; stage_interval(c, c->ev0, c->ev1);
     size_t w = 0;
     for (size_t r = 0; r < c->hTrace.size(); r++) {
         const SwTraceOut &o = c->hTrace[r];
@@ -1317,7 +1333,7 @@ static int align_pipeline(mb200_ctx *c) {
     unsigned long long hc[2] = {0, 0};
     CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "forward alignment kernel"));
-    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0];
+    float ms1 = 0; CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_fwd = ms1; c->st.sw_cells_fwd = hc[0]; stage_interval(c, c->ev0, c->ev1);
     if (hn[1] == 1) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits (scores must stay below 32000)");
     if (hn[1] == 2) return fail(MB200_E_INTERNAL, "pass list overflow");
     // queries longer than 1024 residues: every hit goes straight to the trace kernel (host applies the e-value test)
@@ -1351,7 +1367,7 @@ static int align_pipeline(mb200_ctx *c) {
         CU(cudaMemcpyAsync(c->hTrace.data(), c->dTrace.p, (size_t)nPass * sizeof(SwTraceOut), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(hc, c->dCells.p, 16, cudaMemcpyDeviceToHost, c->stream));
         TRY(sync_check(c, "k_sw_trace"));
-        CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1]; c->st.launches++;
+        CU(cudaEventElapsedTime(&ms1, c->ev0, c->ev1)); c->st.ms_sw_rev = ms1; c->st.sw_cells_rev = hc[1]; stage_interval(c, c->ev0, c->ev1); c->st.launches++;
         for (const SwTraceOut &o : c->hTrace) {
             if (o.flag & 1) return fail(MB200_E_INTERNAL, "forward/backward SW scores differ (slot %u)", o.slot);
             if (o.flag & 2) return fail(MB200_E_LIMIT, "alignment score overflows 16 bits");
@@ -1560,7 +1576,7 @@ int mb200_chain(mb200_ctx *c, const mb200_cand *cands, const uint64_t *candOff, 
     CU(cudaMemcpyAsync(c->pChEx.p, c->dChEx.p, n * sizeof(MbExon), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->pChCnt.p, c->dChCallCnt.p, (size_t)nContigs * 4, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync_check(c, "chain kernel"));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_chain = ms; c->st.launches++;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->st.ms_chain = ms; c->st.launches++; stage_interval(c, c->ev0, c->ev1);
     // host epilogue: set e-value and --metaeuk-eval filter (collectoptimalset.cpp:323-330); compact per contig
     const MbCall *hCalls = c->pChCalls.p; const MbExon *hEx = c->pChEx.p; const int32_t *hCnt = c->pChCnt.p;
     for (uint32_t ci = 0; ci < nContigs; ci++) if (hCnt[ci] < 0) return fail(MB200_E_ARG, "contig %u: illegal codon segment length", ci);
@@ -1684,7 +1700,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->par = p->par; w->mat = p->mat; w->haveMat = p->haveMat; w->ev = p->ev;
     w->dSim3.set_view(p->dSim3.p, p->dSim3.n); w->dCnt3.set_view(p->dCnt3.p, p->dCnt3.n); w->dOffsets.set_view(p->dOffsets.p, p->dOffsets.n);
     w->dKmerBits.set_view(p->dKmerBits.p, p->dKmerBits.n); w->useBits = p->useBits; w->dEntries.set_view(p->dEntries.p, p->dEntries.n);
-    w->optBuckets = p->optBuckets; w->optSortWalk = p->optSortWalk; w->optOverflowPolicy = p->optOverflowPolicy; w->haveBuckets = p->haveBuckets; if (p->haveBuckets) w->dBuckets.set_view(p->dBuckets.p, p->dBuckets.n);
+    w->optBuckets = p->optBuckets; w->optStreamHint = p->optStreamHint; w->optSortWalk = p->optSortWalk; w->optOverflowPolicy = p->optOverflowPolicy; w->haveBuckets = p->haveBuckets; if (p->haveBuckets) w->dBuckets.set_view(p->dBuckets.p, p->dBuckets.n);
     w->dTseqM.set_view(p->dTseqM.p, p->dTseqM.n); w->dTseqU.set_view(p->dTseqU.p, p->dTseqU.n); w->dToff.set_view(p->dToff.p, p->dToff.n);
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
@@ -1708,6 +1724,11 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     std::vector<PeBatchOut> outs(nBatches);
     PeShared sh; sh.nFragOf.assign(nBatches, -1); sh.base = c->optOrfKeyBase;
     const int nW = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)c->optStreams, nBatches));
+    // origin of the call's device timeline: every stage of every worker stream records its [start, end] relative to it (ms_dev_busy = length of their union)
+    if (!c->evOrigin) CU(cudaEventCreate(&c->evOrigin));
+    CU(cudaEventRecord(c->evOrigin, c->stream)); CU(cudaEventSynchronize(c->evOrigin));
+    struct OriginGuard { mb200_ctx *c; int n; ~OriginGuard() { c->originRef = nullptr; for (int k = 0; k < n; k++) if (c->workers[k]) c->workers[k]->originRef = nullptr; } } originGuard{c, 4};
+    c->originRef = c->evOrigin; c->busyIv.clear();
     double ph[4][9] = {{0}};
     mb200_stats wst[4]; memset(wst, 0, sizeof(wst));
     int rcs[4] = {0, 0, 0, 0}; std::string errs[4];
@@ -1729,7 +1750,7 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         if (rcs[0]) return rcs[0];
     } else {
         TRY(build_buckets(c));      // (shared with the workers as a view)
-        for (int k = 0; k < nW; k++) TRY(worker_sync(c, c->workers[k]));
+        for (int k = 0; k < nW; k++) { TRY(worker_sync(c, c->workers[k])); c->workers[k]->originRef = c->evOrigin; c->workers[k]->busyIv.clear(); }
         std::atomic<uint32_t> next(0);
         auto run = [&](int k) {
             mb200_ctx *w = c->workers[k];
@@ -1777,6 +1798,18 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
         const mb200_stats &busy = wst[busyK];
         acc.ms_orf = busy.ms_orf; acc.ms_prep = busy.ms_prep; acc.ms_prefilter = busy.ms_prefilter; acc.ms_sw_fwd = busy.ms_sw_fwd; acc.ms_sw_rev = busy.ms_sw_rev; acc.ms_chain = busy.ms_chain;
         acc.ms_join = busy.ms_join; acc.ms_h2d = busy.ms_h2d; acc.ms_orf_host = busy.ms_orf_host;
+    }
+    {   // union of the stage intervals of all streams
+        std::vector<std::pair<float, float>> iv(c->busyIv);
+        if (nW >= 2) for (int k = 0; k < nW; k++) iv.insert(iv.end(), c->workers[k]->busyIv.begin(), c->workers[k]->busyIv.end());
+        std::sort(iv.begin(), iv.end());
+        double busy = 0; float curB = 0, curE = -1;
+        for (const auto &x : iv) {
+            if (curE < curB || x.first > curE) { if (curE >= curB) busy += (double)curE - curB; curB = x.first; curE = x.second; }
+            else if (x.second > curE) curE = x.second;
+        }
+        if (curE >= curB) busy += (double)curE - curB;
+        acc.ms_dev_busy = busy;
     }
     if (getenv("MB200_TRACE"))
         for (int k = 0; k < nW; k++)

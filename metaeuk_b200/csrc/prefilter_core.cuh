@@ -46,6 +46,8 @@ struct MbPrefTables {
     uint32_t binMask;          // BINSIZE - 1 of the reference's CacheFriendlyOperations<BINSIZE>
     uint32_t capP, capI, capK, capM;
     uint32_t phaseStats;       // 1 = per-phase cycle accounting (diagnostic runs only)
+    uint32_t streamHint;       // bit 0 = the index reads (bucket sectors, long entry lists: random, never reused) bypass L1 and are marked evict-first in L2, so that 100+ GB of them per launch do not
+                               //     push the per-CTA work lists and the similarity / count tables out of L2 (r02z ncu: 10.5 G DRAM sectors read per launch for 2.5 G bucket reads)
     uint32_t sortWalkMax;      // multi-hit lists of at most this many entries are sorted (one warp, registers) and walked instead of grouped by hashing (0: measured slower on C2, r02g)
 };
 
@@ -127,14 +129,47 @@ MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t htLog, uint32_t id1) 
 //      16 halfwords: h[0] = list length (0xFFFF: 65535 or more), then either up to MB_BUCKET_INLINE entries of three halfwords
 //      (seqId low, seqId high, position) or, for longer lists, h[2..3] = index of the first entry in the classic array, h[4..5] = length.
 #define MB_BUCKET_INLINE 5
+#ifndef MB_P4_QUAD
+#define MB_P4_QUAD 0
+#endif
 #if MB_DEVICE_BUILD
 // one 256-bit load (LDG.E.256 on sm_100a): the whole sector in a single request
-__device__ __forceinline__ void mb_load_bucket(const uint4 *p, uint4 &a, uint4 &b) {
+// hint bits (MbPrefTables::streamHint): 1 = L1 no-allocate + L2 evict-first, 2 = fetch 64 B instead of the default 128-byte line from HBM (.L2::64B; needs bit 1),
+//                                        4 = L2 prefetch of a warp's second pair of buckets while the first is in flight, 8 = L2 prefetch of a long list as soon as its bucket arrives
+__device__ __forceinline__ void mb_load_bucket(const uint4 *p, uint4 &a, uint4 &b, uint32_t hint) {
 #ifdef MB200_SIMT_EMU
-    a = p[0]; b = p[1];
+    (void)hint; a = p[0]; b = p[1];
 #else
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    if ((hint & 3u) == 3u)      // LDG.E.NA.EFL2.LTC64B.256.CONSTANT
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    else if (hint & 1u)         // LDG.E.NA.EFL2.256.CONSTANT
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    else
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void mb_prefetch_l2(const void *p) {
+#ifndef MB200_SIMT_EMU
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+// one index entry (seqId, position) of a long list: same policy
+__device__ __forceinline__ uint2 mb_load_entry(const uint2 *p, uint32_t hint) {
+#ifdef MB200_SIMT_EMU
+    (void)hint; return *p;
+#else
+    uint2 e;
+    if (hint & 1u) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(e.x), "=r"(e.y) : "l"(p), "l"(pol));
+    } else e = __ldg(p);
+    return e;
 #endif
 }
 #endif
@@ -369,22 +404,45 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
             if (T.buckets) {
                 // inline buckets: the entries of a short list arrive with the lookup itself (two 128-bit loads per k-mer, two k-mers per lane in flight);
                 // only the lists of more than MB_BUCKET_INLINE entries go through the flattened gather below
+                if (T.streamHint & 4u) {
+#pragma unroll
+                    for (int v = 2; v < 4; v++) {
+                        const uint32_t n = n0 + (uint32_t)v * 32u + lane;
+                        if (n < nNz) mb_prefetch_l2(T.buckets + 2 * (size_t)((uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu));
+                    }
+                }
+#if MB_P4_QUAD      // (experiment: all four buckets of a lane in flight before the first is consumed)
+                uint4 ba4[4], bb4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t n = n0 + (uint32_t)u * 32u + lane;
+                    if (n < nNz) {
+                        const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
+                        mb_load_bucket(T.buckets + 2 * (size_t)km, ba4[u], bb4[u], T.streamHint);
+                    }
+                }
+#endif
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
                     uint4 ba[2], bb[2]; uint32_t nIn[2], inl = 0;
 #pragma unroll
                     for (int v = 0; v < 2; v++) {
                         const uint32_t n = n0 + (uint32_t)(2 * hh + v) * 32u + lane; nIn[v] = 0;
+#if MB_P4_QUAD
+                        if (n < nNz) { ba[v] = ba4[2 * hh + v]; bb[v] = bb4[2 * hh + v]; }
+#else
                         if (n < nNz) {
                             const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
-                            mb_load_bucket(T.buckets + 2 * (size_t)km, ba[v], bb[v]);
+                            mb_load_bucket(T.buckets + 2 * (size_t)km, ba[v], bb[v], T.streamHint);
                         }
+#endif
                     }
 #pragma unroll
                     for (int v = 0; v < 2; v++) if (n0 + (uint32_t)(2 * hh + v) * 32u + lane < nNz) {
                         const uint32_t cnt = mb_bucket_h(ba[v], bb[v], 0);
                         if (cnt <= MB_BUCKET_INLINE) { nIn[v] = cnt; inl += cnt; }
-                        else { lo[2 * hh + v] = ba[v].y; len[2 * hh + v] = ba[v].z; }     // (halfwords 2..3 and 4..5)
+                        else { lo[2 * hh + v] = ba[v].y; len[2 * hh + v] = ba[v].z;       // (halfwords 2..3 and 4..5)
+                               if (T.streamHint & 8u) { const uint32_t nl = ba[v].z < 64u ? ba[v].z : 64u; for (uint32_t x = 0; x < nl; x += 16u) mb_prefetch_l2(T.entries + (size_t)ba[v].y + x); } }
                     }
                     uint32_t inc = inl;
 #pragma unroll
@@ -462,7 +520,7 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
                         uint32_t a = 0, b = 128;   // wPre[a] <= e < wPre[b]  (wPre[128] = Tn)
 #pragma unroll
                         for (int it = 0; it < 7; it++) { const uint32_t mid = (a + b) >> 1; if (wPre[mid] <= e) a = mid; else b = mid; }
-                        own[j] = a; en[j] = T.entries[(size_t)wLo[a] + (e - wPre[a])];
+                        own[j] = a; en[j] = mb_load_entry(T.entries + (size_t)wLo[a] + (e - wPre[a]), T.streamHint);
                     }
                 }
 #pragma unroll

@@ -39,7 +39,7 @@ class Stats(C.Structure):
                 ("orf_nucleotides", C.c_uint64), ("orf_fragments", C.c_uint64), ("orf_residues", C.c_uint64), ("ms_reduce", C.c_double),
                 ("ms_join", C.c_double), ("ms_predict", C.c_double)] + \
                [(n, C.c_uint64) for n in ("pe_batches", "pe_contigs", "pe_fragments", "pe_alignments", "pe_calls", "pe_exons", "pe_streams")] + \
-               [(n, C.c_double) for n in ("ms_prefilter_sum", "ms_sw_fwd_sum", "ms_sw_rev_sum", "ms_dev_sum")]
+               [(n, C.c_double) for n in ("ms_prefilter_sum", "ms_sw_fwd_sum", "ms_sw_rev_sum", "ms_dev_sum", "ms_dev_busy")]
 PEXON_DTYPE = np.dtype([("orf_key", "<u4"), ("bit_score", "<i4"), ("seq_id_est", "<f4"), ("t_start", "<i4"), ("t_end", "<i4"), ("t_len", "<i4"),
                         ("contig_start", "<i4"), ("contig_end", "<i4"), ("nuc_len", "<i4"), ("frag_from", "<i4"), ("frag_to", "<i4"), ("pad", "<i4"), ("evalue", "<f8")])
 PRED_DTYPE = np.dtype([("target_key", "<u4"), ("strand", "<i4"), ("total_bit_score", "<u4"), ("n_exons", "<u4"), ("low_coord", "<u4"), ("high_coord", "<u4"),
