@@ -950,7 +950,8 @@ def main():
     base = {"metric": "predictexons query-fragments/sec", "unit": "fragments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup) if args.impl == "b200" else args.warmup,
             "higher_is_better": True, "scaling": "strong" if wl.get("predict") else "weak", "vs_baseline": None,
             "dtype": "u8/int16x2/int32 (integer DP; float32+float64 only for the composition bias and e-values)",
-            "data": "synthetic (seeded; SURVEY.md 8d generator)", "config": {"workload": wl["desc"], "stages": "prefilter+align" if wl["align"] else "prefilter", "proteins": wl["n_prot"]}}
+            "data": "synthetic (seeded; SURVEY.md 8d generator)", "config": {"workload": wl["desc"], "stages": "extractorfs+translatenucs+prefilter+align+resultspercontig+collectoptimalset" if wl.get("predict") else ("prefilter+align" if wl["align"] else "prefilter"),
+                                                                   "proteins": wl["n_prot"]}}
     if args.impl == "reference":
         if rank != 0:
             return 0

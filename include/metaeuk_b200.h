@@ -226,7 +226,7 @@ int mb200_search_resident(mb200_ctx *ctx, uint64_t *aln_off, const mb200_aln **a
 /* predictexons with the contigs as the only input and binary records between the stages (data/predictexons.sh:40-82):
  * six-frame fragments (device) -> resident query batch -> prefilter -> gapped alignment -> join per contig (resultspercontig.cpp:64-196,
  * as a binary join) -> exon chaining -> calls.  Contigs are processed in batches of about "predict_batch_nt" nucleotides (mb200_option_set;
- * results do not depend on it).  Fragment keys (orf_key) count over the whole call in the reference's key order.  Target keys are the
+ * results do not depend on it; default 32 M, less for small calls so that every worker stream gets at least four batches, never below 4 M).  Fragment keys (orf_key) count over the whole call in the reference's key order.  Target keys are the
  * keys given to mb200_target_keys_set (default: local ids).  Calls of contig c = (*calls)[call_off[c] .. call_off[c+1]) in the order of the
  * reference's dp_predictions entry; the exons of a call = (*exons)[exon_begin .. exon_begin + n_exons).  call_off: caller buffer of
  * n_contigs + 1; *calls and *exons are owned by the context (valid until the next call on it). */

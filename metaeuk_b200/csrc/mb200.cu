@@ -216,7 +216,7 @@ struct mb200_ctx {
     int device = 0; cudaStream_t stream = nullptr; int nSM = 148;
     mb200_params par; mb200::Matrices mat; bool haveMat = false; mb200::EvalueModel ev;
     // tables
-    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optStreamHint = 1, optSortWalk = 0, optOverflowPolicy = -1; bool inPredict = false;
+    DevBuf<uint32_t> dSim3; DevBuf<uint16_t> dCnt3; DevBuf<uint32_t> dOffsets, dKmerBits; DevBuf<uint2> dEntries; bool useBits = false; DevBuf<uint4> dBuckets; bool haveBuckets = false; int optBuckets = 1, optStreamHint = 3, optSortWalk = 0, optOverflowPolicy = -1; bool inPredict = false;
     DevBuf<uint8_t> dTseqM, dTseqU; DevBuf<uint64_t> dToff;
     DevBuf<unsigned char> dIndexArena; size_t arenaBytes = 0;   // offsets | entries | masked | unmasked residues | target offsets in ONE allocation (one ncclBroadcast replicates it)
     void *comm = nullptr;                                        // ncclComm_t created by mb200_comm_init (owned)
@@ -247,7 +247,7 @@ struct mb200_ctx {
     // predictexons with binary hand-off
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; DevBuf<MbCall> dChGrpCalls; DevBuf<int32_t> dChGrpCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
-    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; int optStreams = 2; mb200_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; bool optBatchNtSet = false; int optStreams = 2; mb200_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
     int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -426,7 +426,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "phase_stats") c->optPhaseStats = value ? 1 : 0;
     else if (n == "overflow_policy") { if (value < -1 || value > 1) return fail(MB200_E_ARG, "overflow_policy: -1 (default per entry point), 0 (fail the call) or 1 (skip the query, count it)"); c->optOverflowPolicy = (int)value; }
-    else if (n == "prefilter_stream_hint") { if (value < 0 || value > 15) return fail(MB200_E_ARG, "prefilter_stream_hint: bit 0 = index reads L1 no-allocate + L2 evict-first, bit 1 = 64-byte HBM fetch, bit 2 = L2 prefetch of the second bucket pair, bit 3 = L2 prefetch of long lists"); c->optStreamHint = (int)value; }
+    else if (n == "prefilter_stream_hint") { if (value < 0 || value > 3) return fail(MB200_E_ARG, "prefilter_stream_hint: bit 0 = index reads L1 no-allocate + L2 evict-first, bit 1 = 64-byte HBM fetch (.L2::64B)"); c->optStreamHint = (int)value; }
     else if (n == "l2_fetch_granularity") {   // diagnostic: cudaLimitMaxL2FetchGranularity of the context's device (32, 64 or 128 bytes; a hint the driver may ignore)
         if (value != 32 && value != 64 && value != 128) return fail(MB200_E_ARG, "l2_fetch_granularity: 32, 64 or 128");
 #ifndef MB200_SIMT_EMU
@@ -442,7 +442,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "sw_ring") { if (value < -1 || value > 16) return fail(MB200_E_ARG, "sw_ring: -1 (private profile per slot), 0 (auto) or 1..16 ring profiles per warp"); c->optSwRing = (int)value; }
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
-    else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; }
+    else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; c->optBatchNtSet = true; }
     else if (n == "predict_streams") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "predict_streams: 1..4"); c->optStreams = (int)value; }
     else if (n == "orf_key_base") { if (value < 0 || value >= (1ll << 32)) return fail(MB200_E_ARG, "orf_key_base must fit 32 bits"); c->optOrfKeyBase = (uint64_t)value; }   // contig shards: fragment keys count over the whole contig DB
     else return fail(MB200_E_ARG, "unknown option '%s'", name);
@@ -1719,7 +1719,14 @@ int mb200_predict_exons(mb200_ctx *c, const char *nuc, const uint64_t *off, uint
     c->peCalls.clear(); c->peExons.clear(); callOff[0] = 0; *calls = nullptr; *exons = nullptr; *nExons = 0;
     // contig batches of about predict_batch_nt nucleotides
     std::vector<uint32_t> bnd(1, 0);
-    for (uint32_t b0 = 0; b0 < nContigs;) { uint32_t b1 = b0 + 1; while (b1 < nContigs && off[b1 + 1] - off[b0] <= c->optBatchNt) b1++; bnd.push_back(b1); b0 = b1; }
+    // Default size: 32 M nucleotides, but at least four batches per worker stream when the call is small (a rank's shard of a contig DB split over 4 or 8 GPUs), so that the host phases
+    // of one batch still hide under the kernels of another -- C4/10 (50 M nucleotides) on two streams: 866 -> 830 ms per call with 6 M-nucleotide batches (call u); never below 4 M.
+    uint64_t batchNt = c->optBatchNt;
+    if (!c->optBatchNtSet && c->optStreams > 1 && nContigs > 0) {
+        const uint64_t per = (off[nContigs] - off[0]) / (4ull * (uint64_t)c->optStreams);
+        batchNt = std::min<uint64_t>(batchNt, std::max<uint64_t>(per, 4ull << 20));
+    }
+    for (uint32_t b0 = 0; b0 < nContigs;) { uint32_t b1 = b0 + 1; while (b1 < nContigs && off[b1 + 1] - off[b0] <= batchNt) b1++; bnd.push_back(b1); b0 = b1; }
     const uint32_t nBatches = (uint32_t)bnd.size() - 1;
     std::vector<PeBatchOut> outs(nBatches);
     PeShared sh; sh.nFragOf.assign(nBatches, -1); sh.base = c->optOrfKeyBase;

@@ -129,13 +129,11 @@ MB_DEV uint32_t mb_ht_find(const uint32_t *htKey, uint32_t htLog, uint32_t id1) 
 //      16 halfwords: h[0] = list length (0xFFFF: 65535 or more), then either up to MB_BUCKET_INLINE entries of three halfwords
 //      (seqId low, seqId high, position) or, for longer lists, h[2..3] = index of the first entry in the classic array, h[4..5] = length.
 #define MB_BUCKET_INLINE 5
-#ifndef MB_P4_QUAD
-#define MB_P4_QUAD 0
-#endif
 #if MB_DEVICE_BUILD
 // one 256-bit load (LDG.E.256 on sm_100a): the whole sector in a single request
-// hint bits (MbPrefTables::streamHint): 1 = L1 no-allocate + L2 evict-first, 2 = fetch 64 B instead of the default 128-byte line from HBM (.L2::64B; needs bit 1),
-//                                        4 = L2 prefetch of a warp's second pair of buckets while the first is in flight, 8 = L2 prefetch of a long list as soon as its bucket arrives
+// hint bits (MbPrefTables::streamHint): 1 = L1 no-allocate + L2 evict-first, 2 = fetch 64 B instead of the default 128-byte line from HBM (.L2::64B; needs bit 1).
+// Measured and dropped (call t, C4/10): L2 prefetch of a warp's second pair of buckets while the first is in flight, L2 prefetch of a long list as soon as its bucket arrives, all four
+// buckets of a lane in flight at once (232 bytes of spills at 64 registers): the kernel time does not move or gets worse.
 __device__ __forceinline__ void mb_load_bucket(const uint4 *p, uint4 &a, uint4 &b, uint32_t hint) {
 #ifdef MB200_SIMT_EMU
     (void)hint; a = p[0]; b = p[1];
@@ -149,13 +147,6 @@ __device__ __forceinline__ void mb_load_bucket(const uint4 *p, uint4 &a, uint4 &
     else
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-#endif
-}
-__device__ __forceinline__ void mb_prefetch_l2(const void *p) {
-#ifndef MB200_SIMT_EMU
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#else
-    (void)p;
 #endif
 }
 // one index entry (seqId, position) of a long list: same policy
@@ -404,45 +395,22 @@ MB_DEV void mb_prefilter_query(const MbPrefTables &T, const MbPrefScratch &W, SH
             if (T.buckets) {
                 // inline buckets: the entries of a short list arrive with the lookup itself (two 128-bit loads per k-mer, two k-mers per lane in flight);
                 // only the lists of more than MB_BUCKET_INLINE entries go through the flattened gather below
-                if (T.streamHint & 4u) {
-#pragma unroll
-                    for (int v = 2; v < 4; v++) {
-                        const uint32_t n = n0 + (uint32_t)v * 32u + lane;
-                        if (n < nNz) mb_prefetch_l2(T.buckets + 2 * (size_t)((uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu));
-                    }
-                }
-#if MB_P4_QUAD      // (experiment: all four buckets of a lane in flight before the first is consumed)
-                uint4 ba4[4], bb4[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t n = n0 + (uint32_t)u * 32u + lane;
-                    if (n < nNz) {
-                        const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
-                        mb_load_bucket(T.buckets + 2 * (size_t)km, ba4[u], bb4[u], T.streamHint);
-                    }
-                }
-#endif
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
                     uint4 ba[2], bb[2]; uint32_t nIn[2], inl = 0;
 #pragma unroll
                     for (int v = 0; v < 2; v++) {
                         const uint32_t n = n0 + (uint32_t)(2 * hh + v) * 32u + lane; nIn[v] = 0;
-#if MB_P4_QUAD
-                        if (n < nNz) { ba[v] = ba4[2 * hh + v]; bb[v] = bb4[2 * hh + v]; }
-#else
                         if (n < nNz) {
                             const uint32_t km = (uint32_t)((n < SH::Cfg::SM_NZ) ? sh->sNz[n] : W.B[n - SH::Cfg::SM_NZ]) & 0x3FFFFFFu;
                             mb_load_bucket(T.buckets + 2 * (size_t)km, ba[v], bb[v], T.streamHint);
                         }
-#endif
                     }
 #pragma unroll
                     for (int v = 0; v < 2; v++) if (n0 + (uint32_t)(2 * hh + v) * 32u + lane < nNz) {
                         const uint32_t cnt = mb_bucket_h(ba[v], bb[v], 0);
                         if (cnt <= MB_BUCKET_INLINE) { nIn[v] = cnt; inl += cnt; }
-                        else { lo[2 * hh + v] = ba[v].y; len[2 * hh + v] = ba[v].z;       // (halfwords 2..3 and 4..5)
-                               if (T.streamHint & 8u) { const uint32_t nl = ba[v].z < 64u ? ba[v].z : 64u; for (uint32_t x = 0; x < nl; x += 16u) mb_prefetch_l2(T.entries + (size_t)ba[v].y + x); } }
+                        else { lo[2 * hh + v] = ba[v].y; len[2 * hh + v] = ba[v].z; }     // (halfwords 2..3 and 4..5)
                     }
                     uint32_t inc = inl;
 #pragma unroll

@@ -40,6 +40,19 @@ def test_prefilter_golden(name, cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("hint", [0, 1, 3], ids=["cached", "evict-first", "evict-first-64B"])
+@pytest.mark.parametrize("name", FRAG[:2] + CONTIG[:1])
+def test_prefilter_index_read_policies(name, hint):
+    """the cache policy of the index reads (mb200_option_set "prefilter_stream_hint": LDG.E.ENL2.256 / LDG.E.NA.EFL2.256 / ...LTC64B) must not change a result"""
+    c = reflib.load_case(name)
+    ctx, tdb = ctx_for(c)
+    ctx.option_set("prefilter_stream_hint", hint)
+    got = strkeys(M.prefilter(ctx, c["queries"], tdb))
+    bad = [k for k, _ in c["queries"] if got[str(k)] != c["pref"].get(str(k), "")]
+    assert not bad, (bad[:5], got[str(bad[0])][:300], c["pref"].get(str(bad[0]), "")[:300])
+    ctx.close()
+
+
 @pytest.mark.parametrize("sw", [1, 2, 3, 4, (4, 1), (4, 1024), 5, (5, 1), 6, (6, "sw_ring", -1), (6, "sw_ring", 1), (6, "sw_ring", 16)],
                          ids=["rows", "rows2-packed", "rows3-state-machine", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2",
                               "stream", "stream-private-profiles", "stream-ring1", "stream-ring16"])
