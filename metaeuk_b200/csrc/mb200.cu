@@ -248,7 +248,7 @@ struct mb200_ctx {
     DevBuf<MbCand> dChCand; DevBuf<uint64_t> dChOff; DevBuf<MbPE> dChPE; DevBuf<int32_t> dChOp, dChOm, dChCallCnt; DevBuf<MbRow> dChRows; DevBuf<MbCall> dChCalls; DevBuf<MbExon> dChEx;
     DevBuf<uint32_t> dChExCnt; DevBuf<MbCall> dChGrpCalls; DevBuf<int32_t> dChGrpCnt; PinBuf<MbCall> pChCalls; PinBuf<MbExon> pChEx; PinBuf<int32_t> pChCnt;   // exon chaining (mb200_chain)
     std::vector<uint32_t> tKeys; std::vector<mb200_call> peCalls; std::vector<mb200_pexon> peExons; uint64_t optBatchNt = 32ull << 20, optOrfKeyBase = 0; bool optBatchNtSet = false; int optStreams = 2; mb200_ctx *workers[4] = {nullptr, nullptr, nullptr, nullptr};
-    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
+    int optPrefCfg = 0 /* 0 auto, 1 dense, 2 sparse, 3 medium, 4 small */, prefCfg = 0 /* config the scratch was sized for */, optPrefShortLen = 0, optPrefShortCfg = 3, prefCfgShort = 0, nCtaShort = 0, optPhaseStats = 0, optSwKernel = 6, optSwRing = 0 /* ring profiles per warp: 0 auto, -1 private profile per slot */, optSwRingFit = 1, optTraceKernel = 2, optLaneMaxHits = 8;   // mb200_option_set
     mb200_stats st;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evT0 = nullptr, evT1 = nullptr;
     cudaEvent_t evOrigin = nullptr, originRef = nullptr;    // mb200_predict_exons: origin of the call's device timeline (owned by the caller's context; workers hold a reference)
@@ -439,6 +439,7 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "prefilter_short_len") { if (value < 0 || value > 32767) return fail(MB200_E_ARG, "prefilter_short_len: 0 (off) .. 32767"); c->optPrefShortLen = (int)value; }
     else if (n == "prefilter_short_config") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "prefilter_short_config: 1..4"); c->optPrefShortCfg = (int)value; }
     else if (n == "sw_kernel") { if (value < 1 || value > 6) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane), 5 (4 + row blocks of an alignment spread over lanes) or 6 (streams of pairs over persistent lane groups, end cells recorded by the forward pass)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_ring_fit") { if (value != 0 && value != 1) return fail(MB200_E_ARG, "sw_ring_fit: 0 or 1"); c->optSwRingFit = (int)value; }
     else if (n == "sw_ring") { if (value < -1 || value > 16) return fail(MB200_E_ARG, "sw_ring: -1 (private profile per slot), 0 (auto) or 1..16 ring profiles per warp"); c->optSwRing = (int)value; }
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
     else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
@@ -1036,7 +1037,7 @@ static int min_score_for(mb200_ctx *c, uint32_t L) {
 // Shared-memory geometry of one launch: every warp has a 32-descriptor queue, the descriptors of the pairs in flight, ring tags and P query profiles of
 // 22 * stride + 16 bytes (stride = 32 * nb rows).
 struct SwStreamGeom { uint32_t nb, stride, slots, P, warpBytes; int W, mode; size_t smem; };
-static SwStreamGeom sw_stream_geom(uint32_t nb, int mode, double pairsPerQuery, int ringOpt) {
+static SwStreamGeom sw_stream_geom(uint32_t nb, int mode, double pairsPerQuery, int ringOpt, int ringFit = 0) {
     SwStreamGeom g; g.nb = nb; g.stride = 32u * nb; g.slots = 32u / nb; g.mode = mode;
     const uint32_t entry = 22u * g.stride + 16u, fixed = MB_SWS_QUEUE_BYTES + MB_SWS_INFO_BYTES + MB_SWS_TAG_BYTES;
     if (mode == 0) {
@@ -1044,6 +1045,10 @@ static SwStreamGeom sw_stream_geom(uint32_t nb, int mode, double pairsPerQuery, 
         // a slot from waiting for a free profile
         uint32_t P = ringOpt > 0 ? (uint32_t)ringOpt : (uint32_t)std::ceil((double)g.slots / std::max(1.0, pairsPerQuery)) + 3u;
         P = std::min(std::min(P, g.slots), 16u); if (P < 1) P = 1;
+        // Long queries: a profile of 22 x 32 nb bytes is 5.6 KB at nb = 8 and 11 KB at nb = 16, and a ring sized for comfort leaves room for 4 warps per CTA only (8 warps per SM: one or two
+        // per scheduler, ALU pipe half idle).  ringFit: no more profiles than still let 8 warps x 2 CTAs fit -- the slots of a warp then work on one or two queries at a time, which is
+        // what they do anyway (a warp fetches as many pairs as it has slots, neighbours in the list, targets of a query sorted by length).
+        if (ringFit && ringOpt == 0) { const uint32_t fit = (13824u - fixed) / entry; P = std::min(P, std::max(fit, 1u)); }
         g.P = P;
     } else g.P = g.slots;
     g.warpBytes = fixed + g.P * entry;
@@ -1112,7 +1117,7 @@ static int align_stream(mb200_ctx *c, uint32_t nPairs, uint32_t pLong, uint32_t 
         const uint32_t pB = B[grpHi[gI]], pE = B[grpLo[gI] - 1], base = hOff[grpHi[gI]] - hOff[32], nDesc = hOff[grpLo[gI] - 1] - hOff[grpHi[gI]];
         if (pB >= pE || nDesc == 0) continue;
         const double ppq = (double)nDesc / (double)(pE - pB);
-        const SwStreamGeom g = sw_stream_geom(grpHi[gI], (c->optSwRing >= 0 && ppq >= 2.5) ? 0 : 1, ppq, c->optSwRing);
+        const SwStreamGeom g = sw_stream_geom(grpHi[gI], (c->optSwRing >= 0 && ppq >= 2.5) ? 0 : 1, ppq, c->optSwRing, c->optSwRingFit);
         const int k = nLaunch++ & 3;
         if (!used[k]) { CU(cudaStreamWaitEvent(c->swSide[k], c->swFork, 0)); used[k] = true; }
         TRY(sw_stream_launch(c, c->swSide[k], g, c->dSwDesc.p + base, nDesc, c->dPassRec.p, dNPass, nPairs, c->dCounter.p + 64 + gI, c->dCells.p, dErr, nullptr));
@@ -1705,7 +1710,7 @@ static int worker_sync(mb200_ctx *p, mb200_ctx *&w) {
     w->dSeedMat.set_view(p->dSeedMat.p, p->dSeedMat.n); w->dAlnMat.set_view(p->dAlnMat.p, p->dAlnMat.n); w->dSeedPB.set_view(p->dSeedPB.p, p->dSeedPB.n);
     w->dAlnPB.set_view(p->dAlnPB.p, p->dAlnPB.n); w->dUng8.set_view(p->dUng8.p, p->dUng8.n);
     w->nEntries = p->nEntries; w->totalRes = p->totalRes; w->nT = p->nT; w->hToff = p->hToff; w->haveIndex = p->haveIndex; w->haveSim3 = p->haveSim3; w->tKeys = p->tKeys;
-    w->optPrefCfg = p->optPrefCfg; w->optPrefShortLen = p->optPrefShortLen; w->optPrefShortCfg = p->optPrefShortCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optSwRing = p->optSwRing; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
+    w->optPrefCfg = p->optPrefCfg; w->optPrefShortLen = p->optPrefShortLen; w->optPrefShortCfg = p->optPrefShortCfg; w->optPhaseStats = p->optPhaseStats; w->optSwKernel = p->optSwKernel; w->optSwRing = p->optSwRing; w->optSwRingFit = p->optSwRingFit; w->optTraceKernel = p->optTraceKernel; w->optLaneMaxHits = p->optLaneMaxHits;
     return 0;
 }
 
