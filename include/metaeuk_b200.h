@@ -258,8 +258,19 @@ int mb200_align_resident(mb200_ctx *ctx);             /* aligns the resident pre
 /* dense layouts [n_q][max_res_list_len]; alns holds accepted alignments only, aln_count[i] of them */
 int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count, mb200_aln *alns, uint32_t *aln_count);
 
-/* tuning / diagnostic switches (results never depend on them): "phase_stats" 0|1 (per-phase cycle accounting in k_prefilter),
- * "sw_kernel" 1|2 (one or two targets per lane), "trace_kernel" 1|2 */
+/* tuning / diagnostic switches (results never depend on them, except "overflow_policy" and "orf_key_base" which are documented above / below):
+ *   "phase_stats" 0|1            per-phase cycle accounting in k_prefilter (mb200_stats.pref_phase_cycles)
+ *   "prefilter_config" 0..4      0 = chosen from the index density, 1 dense (512 threads x 2 CTAs/SM), 2 sparse, 3 medium, 4 small;  "prefilter_short_len" / "prefilter_short_config": a
+ *                                separate launch with another configuration for queries of at most that many residues (0 = off)
+ *   "prefilter_buckets" 0|1      inline 32-byte bucket per k-mer (default) or the offsets + entries arrays
+ *   "prefilter_stream_hint" 0..3 cache policy of the index reads: bit 0 = L1 no-allocate + L2 evict-first, bit 1 = 64-byte instead of 128-byte HBM fetch (default 3)
+ *   "prefilter_sort_walk" 0..256 multi-hit lists of at most this many entries are sorted and walked instead of grouped by hashing (default 0)
+ *   "l2_fetch_granularity" 32|64|128   cudaLimitMaxL2FetchGranularity of the device (diagnostic; measured: no effect on sm_100)
+ *   "sw_kernel" 1..6             alignment kernel family (6 = k_sw_stream, default; 1..5 = the round-1 layouts kept for A/B);  "sw_lane_max_hits", "trace_kernel" 1|2: their sub-variants
+ *   "sw_ring" -1|0|1..16         query profiles per warp of k_sw_stream: 0 = sized from the pairs per query (default), -1 = one private profile per slot
+ *   "sw_ring_fit" 0|1            cap that ring so that 8 warps x 2 CTAs fit on an SM (default 1: long queries no longer run at 8 warps per SM)
+ *   "predict_batch_nt" n         nucleotides per contig batch of mb200_predict_exons (default: 32 M, fewer for small calls);  "predict_streams" 1..4: worker streams (default 2)
+ *   "orf_key_base" n             fragment key of the first fragment of the next mb200_predict_exons call (a rank's shard of a contig DB) */
 int mb200_option_set(mb200_ctx *ctx, const char *name, int64_t value);
 int mb200_stats_get(mb200_ctx *ctx, mb200_stats *out);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel and copy of this library is issued on) */

@@ -21,7 +21,8 @@ int join_by_contig(const mb200_orf *orfs, uint64_t nOrfs, uint32_t nContigs, uin
     for (uint32_t c = 0; c < nContigs; c++) fb[c + 1] += fb[c];
     for (uint32_t c = 0; c < nContigs; c++) candOff[c + 1] = candOff[c] + (alnOff[fb[c + 1]] - alnOff[fb[c]]);
     const uint64_t n = candOff[nContigs];
-    cands.resize(n); candAln.resize(n);
+    if (cands.size() < n) cands.resize(n);          // grow only: the caller may pass the arrays of the previous batch (every element of [0, n) is written below)
+    if (candAln.size() < n) candAln.resize(n);
 #pragma omp parallel
     {
         std::vector<std::pair<uint64_t, uint64_t>> order;   // ((target key << 32) | ORF key, alignment index): keys are unique inside a contig

@@ -239,6 +239,9 @@ struct mb200_ctx {
     std::vector<uint32_t> hOrder;   // queries by descending length
     std::vector<SwTraceOut> hTrace;  // last alignment pass, sorted by slot
     std::vector<mb200_aln> hAlns; std::vector<uint64_t> hAlnOff; std::vector<uint64_t> hHitOff;
+    // host work arrays of mb200_predict_exons / collect_accepted: owned by the context and never shrunk, so that a batch does not pay the page faults and the zero fill of
+    // 100+ MB of fresh vectors (they were 40 % of the host-only time of a batch)
+    std::vector<mb200_aln> hAlnTmp; std::vector<mb200_cand> peCands; std::vector<uint64_t> peCandOff, peCandAln; std::vector<mb200_call> peBCalls; std::vector<mb200_exon> peBExons; std::vector<uint32_t> peBCnt;
     // ORF extraction
     DevBuf<unsigned char> dNuc; DevBuf<uint64_t> dNucOff, dOrfAaCnt, dOrfRecBase, dOrfAaBase; DevBuf<uint32_t> dOrfCnt; DevBuf<MbOrfTables> dOrfTab; bool haveOrfTab = false;
     DevBuf<MbOrfRec> dOrfRecs; DevBuf<char> dOrfAa; DevBuf<uint8_t> dOrfCodes; PinBuf<MbOrfRec> pOrfRecs; PinBuf<char> pOrfAa; uint64_t nOrfs = 0, nOrfAa = 0;
@@ -1478,14 +1481,32 @@ int mb200_prefilter_compact(mb200_ctx *c, const uint8_t *q, const uint64_t *qoff
 // accepted alignments of the resident pass, compact: fills c->hAlns / c->hAlnOff (prefilter order inside a query)
 static int collect_accepted(mb200_ctx *c, const std::vector<uint32_t> &tidOfTrace) {
     const uint32_t nQ = c->nQ, maxHits = (uint32_t)c->par.max_res_list_len;
-    std::vector<mb200_aln> tmp(c->hTrace.size());
-#pragma omp parallel for schedule(dynamic, 256)
-    for (size_t r = 0; r < c->hTrace.size(); r++) {
-        const uint32_t q = c->hTrace[r].slot / maxHits; const uint32_t L = (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]);
-        finish_aln(c, c->hTrace[r], tidOfTrace[r], L, tmp[r]);
+    const size_t n = c->hTrace.size();
+    if (c->hAlnTmp.size() < n) c->hAlnTmp.resize(n);
+    mb200_aln *tmp = c->hAlnTmp.data();
+    // records are sorted by slot (query-major): the accepted ones keep that order.  Chunks of the record list are finished and counted in parallel, then copied to their place.
+    const int nChunk = (int)std::min<size_t>(256, std::max<size_t>(1, n / 4096));
+    std::vector<size_t> cBeg(nChunk + 1), cOut(nChunk + 1, 0);
+    for (int k = 0; k <= nChunk; k++) cBeg[k] = n * (size_t)k / (size_t)nChunk;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < nChunk; k++) {
+        size_t cnt = 0;
+        for (size_t r = cBeg[k]; r < cBeg[k + 1]; r++) {
+            const uint32_t q = c->hTrace[r].slot / maxHits; const uint32_t L = (uint32_t)(c->hQoff[q + 1] - c->hQoff[q]);
+            finish_aln(c, c->hTrace[r], tidOfTrace[r], L, tmp[r]);
+            cnt += tmp[r].passed ? 1 : 0;
+        }
+        cOut[k + 1] = cnt;
     }
-    c->hAlnOff.assign(nQ + 1, 0); c->hAlns.clear();
-    for (size_t r = 0; r < tmp.size(); r++) if (tmp[r].passed) { c->hAlnOff[c->hTrace[r].slot / maxHits + 1]++; c->hAlns.push_back(tmp[r]); }
+    for (int k = 0; k < nChunk; k++) cOut[k + 1] += cOut[k];
+    c->hAlns.resize(cOut[nChunk]);
+    c->hAlnOff.assign((size_t)nQ + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < nChunk; k++) {
+        size_t w = cOut[k];
+        for (size_t r = cBeg[k]; r < cBeg[k + 1]; r++) if (tmp[r].passed) c->hAlns[w++] = tmp[r];
+    }
+    for (size_t r = 0; r < n; r++) if (tmp[r].passed) c->hAlnOff[c->hTrace[r].slot / maxHits + 1]++;
     for (uint32_t i = 0; i < nQ; i++) c->hAlnOff[i + 1] += c->hAlnOff[i];
     return 0;
 }
@@ -1658,13 +1679,16 @@ static int predict_batch(mb200_ctx *c, const char *nuc, const uint64_t *off, uin
     TRY(collect_accepted(c, tids)); lap(5);
     uint64_t orfBase = 0;
     if (!sh.orfBase(batchIdx, orfBase)) return fail(MB200_E_INTERNAL, "another contig batch failed");
-    std::vector<mb200_cand> cands; std::vector<uint64_t> candOff, candAln; std::vector<mb200_call> bCalls; std::vector<mb200_exon> bExons; std::vector<uint32_t> bCnt;
+    std::vector<mb200_cand> &cands = c->peCands; std::vector<uint64_t> &candOff = c->peCandOff, &candAln = c->peCandAln;
+    std::vector<mb200_call> &bCalls = c->peBCalls; std::vector<mb200_exon> &bExons = c->peBExons; std::vector<uint32_t> &bCnt = c->peBCnt;
     const auto tj = std::chrono::steady_clock::now();
     if (mb200::join_by_contig(orfs, n, nb, orfBase, c->hAlnOff.data(), c->hAlns.data(), c->tKeys.empty() ? nullptr : c->tKeys.data(), c->hToff.data(), cands, candOff, candAln))
         return fail(MB200_E_LIMIT, "more than 2^32 fragments in one mb200_predict_exons call");
     c->st.ms_join = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count();
     const uint64_t nc = candOff[nb];
-    bCalls.resize(std::max<uint64_t>(1, 2 * nc)); bExons.resize(std::max<uint64_t>(1, nc)); bCnt.assign(nb, 0);
+    if (bCalls.size() < std::max<uint64_t>(1, 2 * nc)) bCalls.resize(std::max<uint64_t>(1, 2 * nc));      // (grow only: mb200_chain writes every record that is read below)
+    if (bExons.size() < std::max<uint64_t>(1, nc)) bExons.resize(std::max<uint64_t>(1, nc));
+    bCnt.assign(nb, 0);
     c->st.ms_chain = 0;
     lap(6);
     if (nc) TRY(mb200_chain(c, cands.data(), candOff.data(), nb, c->totalRes, bCalls.data(), bCnt.data(), bExons.data()));

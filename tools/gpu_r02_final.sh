@@ -1,6 +1,6 @@
 # round 2, final measurement set: GPU suite, default bench line (full C4) + reference arm, C2 / C3-10 lines, launch list and ncu captures of the two top kernels
 mkdir -p gpurun_out
-T=${1:-r02z}
+T=${1:-r02f}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/${T}_pytest_gpu.log
 ( time python bench.py ) > gpurun_out/${T}_bench_c4.json 2> gpurun_out/${T}_bench_c4.err; echo "bench exit $?"; tail -4 gpurun_out/${T}_bench_c4.err
 ( time python bench.py --impl reference ) > gpurun_out/${T}_ref_c4.json 2> gpurun_out/${T}_ref_c4.err; echo "ref exit $?"; tail -4 gpurun_out/${T}_ref_c4.err
