@@ -185,7 +185,9 @@ int mb200_mask_targets_ex(const uint8_t *unmasked, const uint64_t *off, uint32_t
  * entries keyed as in M/src/prefiltering/PrefilteringIndexReader.cpp:10-34).  mb200_index_load mmaps such a DB -- written by
  * mb200_index_save / mb200_index_file_write or by the reference itself -- checks its META entry (k = 6, alphabet 21, spaced pattern, one split,
  * amino acids, k-mer threshold equal to params.kmer_thr), uploads k-mer table, masked and unmasked residues and takes the DB keys
- * (mb200_target_keys_set).  mb200_index_file_write builds the index on the host (no GPU needed; default seed matrix) and writes it. */
+ * (mb200_target_keys_set).  mb200_index_file_write builds the index on the host (no GPU needed; default seed matrix) and writes it.
+ * A DB written here also carries SCOREMATRIXNAME, SPACEDPATTERN and the 2-mer / 3-mer similarity tables (ScoreMatrix::serialize layout for AVX2 builds), so the
+ * unmodified reference runs `prefilter` / `align` from it as it does from its own `.idx` (tests/test_cli_cpu.py). */
 int mb200_index_save(mb200_ctx *ctx, const char *path);
 int mb200_index_load(mb200_ctx *ctx, const char *path);
 int mb200_index_file_write(const char *path, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t n_targets,

@@ -24,7 +24,7 @@ void aa2num_table(uint8_t t[256]) {
 }
 
 // entry ids (PrefilteringIndexReader.cpp:10-34)
-enum { E_VERSION = 0, E_META = 1, E_DBR1INDEX = 5, E_DBR1DATA = 6, E_DBR2INDEX = 7, E_DBR2DATA = 8, E_ENTRIES = 9, E_ENTRIESOFFSETS = 10, E_ENTRIESNUM = 12,
+enum { E_VERSION = 0, E_META = 1, E_SCOREMATRIXNAME = 2, E_SCOREMATRIX2MER = 3, E_SCOREMATRIX3MER = 4, E_SPACEDPATTERN = 23, E_DBR1INDEX = 5, E_DBR1DATA = 6, E_DBR2INDEX = 7, E_DBR2DATA = 8, E_ENTRIES = 9, E_ENTRIESOFFSETS = 10, E_ENTRIESNUM = 12,
        E_SEQCOUNT = 13, E_SEQINDEXDATA = 14, E_SEQINDEXDATASIZE = 15, E_SEQINDEXSEQOFFSET = 16, E_GENERATOR = 22 };
 static const char *INDEX_VERSION = "16";   // MMSEQS_CURRENT_INDEX_VERSION (reference/lib/mmseqs/src/MMseqsBase.cpp:6)
 static const int DBTYPE_INDEX_DB = 9, DBTYPE_AMINO_ACIDS = 0;   // Parameters.h:68-77
@@ -117,7 +117,7 @@ struct Writer {
 }  // namespace
 
 int write_index_db(const std::string &path, const TargetIndex &idx, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT,
-                   const uint32_t *keys, int kmerThr, int maskMode, std::string &err) {
+                   const uint32_t *keys, int kmerThr, int maskMode, std::string &err, const int16_t *seedMatrix, int rowAlign) {
     if (idx.offsets.size() != KMER_TABLE + 1) return bad(err, "index not built");
     Writer w; w.f = fopen(path.c_str(), "wb");
     if (!w.f) return bad(err, "cannot create " + path);
@@ -129,6 +129,43 @@ int write_index_db(const std::string &path, const TargetIndex &idx, const uint8_
     w.data(E_META, &M, sizeof(M));
     const char *gen = "metaeuk_b200";
     w.data(E_GENERATOR, gen, strlen(gen));
+    {   // What the reference's own prefilter needs besides the k-mer index to run from this DB (PrefilteringIndexReader.cpp:91-99,196-215,536-590): the name of the k-mer matrix
+        // ("<name>.out:<text>"; Prefiltering.cpp:156 stores it and printSummary prints the name -- the text is never parsed on that path, and the matrix file itself is not part of this
+        // library), the empty spaced pattern (= the default 1101010011), and the 2-mer / 3-mer similarity tables in ScoreMatrix::serialize layout (ScoreMatrix.h:26-41): int16 score[n][row]
+        // then uint32 index[n][row], neighbours in descending score order, row = n rounded up to the next multiple of the reader's MAX_ALIGN_INT (64 in AVX2 builds, 32 in SSE builds:
+        // the reader recomputes it, so an index is only readable by builds of the width it was written for), padded with -255 / 0.
+        static const char *name = "VTML80.out:# VTML80, bit factor 8, score bias -0.2: the k-mer similarity matrix of this index (its 2-mer / 3-mer tables are entries 3 and 4).\n"
+                                  "# Written by metaeuk_b200 gpucreateindex, which does not embed the matrix file.\n";
+        w.data(E_SCOREMATRIXNAME, name, strlen(name));
+        w.data(E_SPACEDPATTERN, "", 0);
+        Matrices mats; default_matrices(mats);
+        const int16_t *seed = seedMatrix ? seedMatrix : mats.seed;
+        const size_t align = rowAlign > 0 ? (size_t)rowAlign : 64;
+        auto writeTable = [&](unsigned key, size_t n, const std::vector<uint32_t> &tab) {   // tab[n][n] = (neighbour << 16) | (uint16) score
+            const size_t row = (n / align + 1) * align;
+            std::vector<int16_t> sc(row, (int16_t)-255); std::vector<uint32_t> ix(row, 0u);
+            w.begin(key);
+            for (size_t r = 0; r < n; r++) { for (size_t j = 0; j < n; j++) sc[j] = (int16_t)(uint16_t)(tab[r * n + j] & 0xFFFFu); w.raw(sc.data(), row * 2); }
+            for (size_t r = 0; r < n; r++) { for (size_t j = 0; j < n; j++) ix[j] = tab[r * n + j] >> 16; w.raw(ix.data(), row * 4); }
+            w.end(key);
+        };
+        {
+            std::vector<uint32_t> sim3; std::vector<uint16_t> cnt3;
+            build_sim3(seed, sim3, cnt3, -192, 384);
+            writeTable(E_SCOREMATRIX3MER, (size_t)N3, sim3);
+        }
+        {   // 2-mers: the same stable descending order over the cartesian enumeration (first letter outermost, lowest digit)
+            std::vector<uint32_t> sim2((size_t)400 * 400);
+            for (int r = 0; r < 400; r++) {
+                const int a0 = r % 20, a1 = r / 20;
+                std::vector<std::pair<int, uint32_t>> v; v.reserve(400);
+                for (int b0 = 0; b0 < 20; b0++) for (int b1 = 0; b1 < 20; b1++) v.push_back({seed[a0 * AL + b0] + seed[a1 * AL + b1], (uint32_t)(b0 + 20 * b1)});
+                std::stable_sort(v.begin(), v.end(), [](const std::pair<int, uint32_t> &x, const std::pair<int, uint32_t> &y) { return x.first > y.first; });
+                for (int j = 0; j < 400; j++) sim2[(size_t)r * 400 + j] = (v[j].second << 16) | (uint16_t)(int16_t)v[j].first;
+            }
+            writeTable(E_SCOREMATRIX2MER, 400, sim2);
+        }
+    }
     {   // DBR1INDEX: DBReader<unsigned int>::serialize layout
         const uint64_t total = off[nT]; const uint64_t dataSize = total + 2ull * nT;
         std::vector<uint8_t> b(HDR + (size_t)nT * REC, 0);

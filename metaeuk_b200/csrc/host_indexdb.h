@@ -41,9 +41,11 @@ struct IndexDb {
 // 0 on success; on failure returns -1 and sets err (missing entry, wrong version, split index, profile/nucleotide DB, inconsistent sizes)
 int open_index_db(const std::string &path, IndexDb &db, std::string &err);
 
-// targets as numeric codes (masked / unmasked share off[nT + 1]); keys[nT] or NULL (= local ids); idx = build_index() of the masked residues
+// targets as numeric codes (masked / unmasked share off[nT + 1]); keys[nT] or NULL (= local ids); idx = build_index() of the masked residues.
+// Also writes what the reference's own prefilter needs to run from this DB: SCOREMATRIXNAME, SPACEDPATTERN and the 2-mer / 3-mer similarity tables of seedMatrix (NULL = the default
+// VTML80 x 8) with rows padded to rowAlign int16 (0 = 64, the MAX_ALIGN_INT of AVX2 builds of the reference; 32 for SSE builds).
 int write_index_db(const std::string &path, const TargetIndex &idx, const uint8_t *masked, const uint8_t *unmasked, const uint64_t *off, uint32_t nT,
-                   const uint32_t *keys, int kmerThr, int maskMode, std::string &err);
+                   const uint32_t *keys, int kmerThr, int maskMode, std::string &err, const int16_t *seedMatrix = nullptr, int rowAlign = 0);
 
 extern const char NUM2AA[22];               // "ACDEFGHIKLMNPQRSTVWYX"
 void aa2num_table(uint8_t table[256]);      // SubstitutionMatrix::setupLetterMapping (SubstitutionMatrix.cpp:262-304)

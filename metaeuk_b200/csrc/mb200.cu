@@ -638,7 +638,7 @@ int mb200_index_save(mb200_ctx *c, const char *path) {
     if (c->totalRes) { CU(cudaMemcpy(m.data(), c->dTseqM.p, c->totalRes, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(u.data(), c->dTseqU.p, c->totalRes, cudaMemcpyDeviceToHost)); }
     bool masked = false; for (uint64_t i = 0; i < c->totalRes && !masked; i++) masked = m[i] != u[i];
     std::string err;
-    if (mb200::write_index_db(path, idx, m.data(), u.data(), c->hToff.data(), c->nT, c->tKeys.size() == c->nT ? c->tKeys.data() : nullptr, c->par.kmer_thr, masked ? 1 : 0, err))
+    if (mb200::write_index_db(path, idx, m.data(), u.data(), c->hToff.data(), c->nT, c->tKeys.size() == c->nT ? c->tKeys.data() : nullptr, c->par.kmer_thr, masked ? 1 : 0, err, c->haveMat ? c->mat.seed : nullptr))
         return fail(MB200_E_ARG, "%s", err.c_str());
     return 0;
 }

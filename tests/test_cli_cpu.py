@@ -84,6 +84,42 @@ def test_gpucreateindex_masks_like_the_reference_by_default(exe, emu, tmp_path):
     assert (y["masked"] == u).all() and y["meta"][4] == 0 and y["n_entries"] > x["n_entries"]
 
 
+def test_the_reference_prefilters_and_aligns_from_an_index_written_here(exe, tmp_path):
+    """SURVEY 8f-4, the other direction: `metaeuk prefilter` / `align` of the UNMODIFIED reference binary run from a `.idx` that `mb200 gpucreateindex` wrote (score-matrix name,
+    spaced pattern, 2-mer and 3-mer similarity tables in ScoreMatrix::serialize layout besides the k-mer index) and give the golden result DBs; build container only (oracle/_ref)"""
+    import sys
+    sys.path.insert(0, os.path.join(reflib.ROOT, "tools"))
+    import refrun
+    ref = refrun.ref_bin()
+    if not ref:
+        pytest.skip("oracle/_ref/metaeuk-ref not built (needs /root/reference: build container)")
+    c = reflib.load_case("frag_small")
+    d = str(tmp_path)
+    reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"]], 0)
+    reflib.write_db(d + "/q", [(k, s + "\n") for k, s in c["queries"]], 0)
+    subprocess.check_call([exe, "gpucreateindex", d + "/proteins", d + "/proteins.idx", "--k-score", str(c["kmer_thr"])])
+    pref = ("--sub-mat aa:blosum62.out,nucl:nucleotide.out --seed-sub-mat aa:VTML80.out,nucl:nucleotide.out -k 0 --target-search-mode 0 --k-score seq:%d,prof:%d "
+            "--alph-size aa:21,nucl:5 --max-seq-len 65535 --max-seqs %d --split 1 --split-mode 2 --split-memory-limit 0 -c 0 --cov-mode 0 --comp-bias-corr 1 --comp-bias-corr-scale 1 "
+            "--diag-score 1 --exact-kmer-matching 0 --mask 1 --mask-prob 0.9 --mask-lower-case 0 --mask-n-repeat 0 --min-ungapped-score 15 --add-self-matches 0 --spaced-kmer-mode 1 "
+            "--db-load-mode 0 --threads 4 --compressed 0 -v 3 -s 4.0") % (c["kmer_thr"], c["kmer_thr"], c.get("max_seqs", 300))
+    r = subprocess.run([ref, "prefilter", d + "/q", d + "/proteins.idx", d + "/pref"] + pref.split(), capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert "Generated by:  metaeuk_b200" in r.stdout and "ScoreMatrix:  VTML80.out" in r.stdout      # it did read our DB
+    keys, ents = refrun.read_result_db(d + "/pref")
+    got = {str(int(k)): e.decode() for k, e in zip(keys, ents)}
+    bad = [k for k, _ in c["queries"] if got.get(str(k), "") != c["pref"].get(str(k), "")]
+    assert not bad, bad[:5]
+    aln = ("--sub-mat aa:blosum62.out,nucl:nucleotide.out -a 0 --alignment-mode 2 --alignment-output-mode 0 --wrapped-scoring 0 -e 100 --min-seq-id 0 --min-aln-len 11 --seq-id-mode 0 "
+           "--alt-ali 0 -c 0 --cov-mode 0 --max-seq-len 65535 --comp-bias-corr 1 --comp-bias-corr-scale 1 --max-rejected 2147483647 --max-accept 2147483647 --add-self-matches 0 "
+           "--db-load-mode 0 --score-bias 0 --realign 0 --gap-open aa:11,nucl:5 --gap-extend aa:1,nucl:2 --zdrop 40 --threads 4 --compressed 0 -v 3")
+    r = subprocess.run([ref, "align", d + "/q", d + "/proteins.idx", d + "/pref", d + "/aln"] + aln.split(), capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    keys, ents = refrun.read_result_db(d + "/aln")
+    got = {str(int(k)): e.decode() for k, e in zip(keys, ents)}
+    bad = [k for k, _ in c["queries"] if got.get(str(k), "") != c["aln"].get(str(k), "")]
+    assert not bad, bad[:5]
+
+
 def test_sensitivity_to_kmer_threshold_matches_the_reference_log():
     """`-s` -> k-mer similarity threshold (mb200_kmer_threshold = Prefiltering::getKmerThreshold, k = 6): the values the reference logged for the
     flags fixture and the whole range of sensitivities in steps of 0.1 against the restated float/double expression"""
