@@ -479,7 +479,7 @@ def bench_predict(args, wl, base, rank, world, local, threads):
                   "against": "dp_predictions of the unmodified reference (metaeuk predictexons module chain, --mask 1) on the same contigs and proteins"}
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes_prefilter(st); kms = pre_ms / args.steps
-    per_kmer = ncu_traffic("dram_bytes_per_similar_kmer_c4")
+    per_kmer = ncu_traffic("dram_bytes_per_similar_kmer_c4") if args.workload in ("c4", "c4m") else None    # (measured on the 500 K-protein index only)
     nb = max(1, int(st["pe_batches"]))
     base["config"].update({"fragments": total_frag, "fragments_per_gpu": nfrag_local, "contigs": nC, "contigs_per_gpu": c1 - c0, "nucleotides_per_gpu": int(nuc.nbytes),
                            "planted_genes_rank0": genes, "stages": "extractorfs+translatenucs+prefilter+align+resultspercontig+collectoptimalset",
