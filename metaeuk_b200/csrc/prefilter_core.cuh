@@ -47,7 +47,8 @@ struct MbPrefTables {
     uint32_t capP, capI, capK, capM;
     uint32_t phaseStats;       // 1 = per-phase cycle accounting (diagnostic runs only)
     uint32_t streamHint;       // bit 0 = the index reads (bucket sectors, long entry lists: random, never reused) bypass L1 and are marked evict-first in L2, so that 100+ GB of them per launch do not
-                               //     push the per-CTA work lists and the similarity / count tables out of L2 (r02z ncu: 10.5 G DRAM sectors read per launch for 2.5 G bucket reads)
+                               //     push the per-CTA work lists out of L2 (ncu: every hit word was written back to DRAM before the next query overwrote it);
+                               // bit 1 = they fetch 64 bytes instead of the default 128-byte line from HBM (a random read moves a whole line otherwise: 4.07 DRAM sectors per access)
     uint32_t sortWalkMax;      // multi-hit lists of at most this many entries are sorted (one warp, registers) and walked instead of grouped by hashing (0: measured slower on C2, r02g)
 };
 
