@@ -169,6 +169,9 @@ int mb200_comm_unique_id(void *id128);
 int mb200_comm_init(mb200_ctx *ctx, const void *id128, int rank, int world);
 int mb200_comm_init_all(mb200_ctx **ctxs, int n);
 int mb200_index_broadcast(mb200_ctx *ctx, void *nccl_comm, int root, uint64_t *nbytes, double *ms);
+/* one process, several contexts on several devices: copy the index (and the target keys) of `src` device to device into `dst` (cudaMemcpyPeerAsync), commit it there.
+ * Replaces, for a single-process host driver (bin/mb200 gpupredictexons --gpus N), what mb200_index_broadcast does for one process per GPU. */
+int mb200_index_clone(mb200_ctx *dst, mb200_ctx *src, uint64_t *nbytes, double *ms);
 
 /* Repeat masking of the targets before indexing = Masker::maskSequence with the prefilter's default flags (--mask 1 --mask-prob 0.9;
  * M/src/commons/Masker.cpp:14-58 -> tantan, M/lib/tantan/tantan.cpp:401-433,478-540; called from IndexBuilder::fillDatabase, IndexBuilder.cpp:84-131).
@@ -268,7 +271,7 @@ int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count,
  *   "prefilter_stream_hint" 0..3 cache policy of the index reads: bit 0 = L1 no-allocate + L2 evict-first, bit 1 = 64-byte instead of 128-byte HBM fetch (default 3)
  *   "prefilter_sort_walk" 0..256 multi-hit lists of at most this many entries are sorted and walked instead of grouped by hashing (default 0)
  *   "l2_fetch_granularity" 32|64|128   cudaLimitMaxL2FetchGranularity of the device (diagnostic; measured: no effect on sm_100)
- *   "sw_kernel" 1..6             alignment kernel family (6 = k_sw_stream, default; 1..5 = the round-1 layouts kept for A/B);  "sw_lane_max_hits", "trace_kernel" 1|2: their sub-variants
+ *   "sw_kernel" 1|2|4|5|6        alignment kernel family (6 = k_sw_stream, default; 1, 2, 4, 5 = the round-1 layouts kept for A/B);  "sw_lane_max_hits": sub-variant of 4 / 5
  *   "sw_ring" -1|0|1..16         query profiles per warp of k_sw_stream: 0 = sized from the pairs per query (default), -1 = one private profile per slot
  *   "sw_ring_fit" 0|1            cap that ring so that 8 warps x 2 CTAs fit on an SM (default 1: long queries no longer run at 8 warps per SM)
  *   "predict_batch_nt" n         nucleotides per contig batch of mb200_predict_exons (default: 32 M, fewer for small calls);  "predict_streams" 1..4: worker streams (default 2)

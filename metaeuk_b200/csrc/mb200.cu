@@ -441,11 +441,11 @@ int mb200_option_set(mb200_ctx *c, const char *name, int64_t value) {
     else if (n == "prefilter_config") { if (value < 0 || value > 4) return fail(MB200_E_ARG, "prefilter_config: 0 (auto), 1 (dense), 2 (sparse), 3 (medium) or 4 (small)"); c->optPrefCfg = (int)value; }
     else if (n == "prefilter_short_len") { if (value < 0 || value > 32767) return fail(MB200_E_ARG, "prefilter_short_len: 0 (off) .. 32767"); c->optPrefShortLen = (int)value; }
     else if (n == "prefilter_short_config") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "prefilter_short_config: 1..4"); c->optPrefShortCfg = (int)value; }
-    else if (n == "sw_kernel") { if (value < 1 || value > 6) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 3 (packed, per-lane state machine), 4 (2 + one short query with few hits per lane), 5 (4 + row blocks of an alignment spread over lanes) or 6 (streams of pairs over persistent lane groups, end cells recorded by the forward pass)"); c->optSwKernel = (int)value; }
+    else if (n == "sw_kernel") { if (value < 1 || value > 6 || value == 3) return fail(MB200_E_ARG, "sw_kernel: 1 (one target per lane), 2 (two, packed 16-bit), 4 (2 + one short query with few hits per lane), 5 (4 + row blocks of an alignment spread over lanes) or 6 (streams of pairs over persistent lane groups, end cells recorded by the forward pass); 3 (per-lane state machine) lost its A/B and was removed"); c->optSwKernel = (int)value; }
     else if (n == "sw_ring_fit") { if (value != 0 && value != 1) return fail(MB200_E_ARG, "sw_ring_fit: 0 or 1"); c->optSwRingFit = (int)value; }
     else if (n == "sw_ring") { if (value < -1 || value > 16) return fail(MB200_E_ARG, "sw_ring: -1 (private profile per slot), 0 (auto) or 1..16 ring profiles per warp"); c->optSwRing = (int)value; }
     else if (n == "sw_lane_max_hits") { if (value < 1 || value > 1024) return fail(MB200_E_ARG, "sw_lane_max_hits: 1..1024"); c->optLaneMaxHits = (int)value; }
-    else if (n == "trace_kernel") { if (value != 1 && value != 2) return fail(MB200_E_ARG, "trace_kernel: 1 or 2"); c->optTraceKernel = (int)value; }
+    else if (n == "trace_kernel") { if (value != 2) return fail(MB200_E_ARG, "trace_kernel: 2 (k_sw_trace2; variant 1 was removed)"); c->optTraceKernel = (int)value; }
     else if (n == "predict_batch_nt") { if (value < 1) return fail(MB200_E_ARG, "predict_batch_nt must be >= 1"); c->optBatchNt = (uint64_t)value; c->optBatchNtSet = true; }
     else if (n == "predict_streams") { if (value < 1 || value > 4) return fail(MB200_E_ARG, "predict_streams: 1..4"); c->optStreams = (int)value; }
     else if (n == "orf_key_base") { if (value < 0 || value >= (1ll << 32)) return fail(MB200_E_ARG, "orf_key_base must fit 32 bits"); c->optOrfKeyBase = (uint64_t)value; }   // contig shards: fragment keys count over the whole contig DB
@@ -687,6 +687,30 @@ int mb200_index_commit(mb200_ctx *c) {
     CU(cudaMemcpy(c->hToff.data(), c->dToff.p, (size_t)(c->nT + 1) * 8, cudaMemcpyDeviceToHost));
     c->haveIndex = true; c->minScore.clear();
     return build_kmer_bits(c);
+}
+// One process, several contexts on several devices (bin/mb200 gpupredictexons --gpus N): the index of src -- offsets, entries, masked / unmasked residues, target offsets --
+// is copied device to device (cudaMemcpyPeerAsync: NVLink when peer access is possible, staged through the host otherwise) into dst's arena, together with the target keys.
+// The NCCL path (mb200_index_broadcast) is for one process per GPU.
+int mb200_index_clone(mb200_ctx *dst, mb200_ctx *src, uint64_t *nbytes, double *ms) {
+    if (!dst || !src || dst == src) return fail(MB200_E_ARG, "mb200_index_clone: two different contexts");
+    if (!src->haveIndex) return fail(MB200_E_STATE, "source context has no index");
+    uint64_t sizes[4]; TRY(mb200_index_sizes(src, sizes)); TRY(mb200_index_alloc(dst, sizes));
+    void *ps[8], *pd[8]; uint64_t ns[8], nd[8]; int n1 = 0, n2 = 0;
+    TRY(mb200_index_buffers(src, ps, ns, &n1)); TRY(mb200_index_buffers(dst, pd, nd, &n2));
+    CU(cudaSetDevice(src->device)); CU(cudaStreamSynchronize(src->stream));
+    CU(cudaSetDevice(dst->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t total = 0;
+    for (int i = 0; i < n1; i++) {
+        if (ns[i] != nd[i]) return fail(MB200_E_INTERNAL, "index arenas differ");
+        if (ns[i]) CU(cudaMemcpyPeerAsync(pd[i], dst->device, ps[i], src->device, ns[i], dst->stream));
+        total += ns[i];
+    }
+    CU(cudaStreamSynchronize(dst->stream));
+    if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (nbytes) *nbytes = total;
+    dst->tKeys = src->tKeys;
+    return mb200_index_commit(dst);
 }
 
 
@@ -1256,18 +1280,7 @@ static int align_pipeline(mb200_ctx *c) {
     for (int k = 0; k < 2; k++) {
         const uint32_t pB = bounds[k], pE = bounds[k + 1];
         if (pB >= pE) continue;
-        if (c->optSwKernel == 3) {
-            int W = (int)((100u * 1024u) / (2u * 22u * strides[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
-            const size_t smem = (size_t)W * 2u * 22u * strides[k];
-            CU(cudaFuncSetAttribute(k_sw_rows3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            int perSM = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sw_rows3, W * 32, smem)); if (perSM < 1) perSM = 1;
-            const int blocks = c->nSM * perSM;
-            TRY(c->dBnd.alloc((size_t)blocks * W * maxT * 32u * 2u));
-            MB_LAUNCH((k_sw_rows3), blocks, W * 32, smem, c->stream, c->dOrder.p, pB, pE, c->dHits.p, c->dHitCount.p, usePerm ? c->dPerm.p : nullptr, maxHits,
-                                                         c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p, c->par.gap_open, c->par.gap_extend,
-                                                         strides[k], c->dMinScore.p, c->dScore.p, c->dPassList.p, dNPass, nPairs, c->dCounter.p + k, c->dCells.p, dErr,
-                                                         reinterpret_cast<uint2 *>(c->dBnd.p), maxT);
-        } else if (packed) {
+        if (packed) {
             int W = (int)((100u * 1024u) / (2u * 22u * strides[k])); if (W > MB_SWR_WARPS) W = MB_SWR_WARPS; if (W < 1) W = 1;
             const size_t smem = (size_t)W * 2u * 22u * strides[k];
             CU(cudaFuncSetAttribute(k_sw_rows2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1360,15 +1373,9 @@ static int align_pipeline(mb200_ctx *c) {
         const int blocks = c->nSM * 4; const size_t nWarps = (size_t)blocks * 4;
         CU(cudaEventRecord(c->ev0, c->stream));
         TRY(c->dTrace.alloc(nPass));
-        if (c->optTraceKernel == 1) {
-            TRY(c->dHE.alloc(nWarps * (c->maxQLen ? c->maxQLen : 1) * 32));
-            MB_LAUNCH((k_sw_trace), blocks, 128, 0, c->stream, c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
-                                                      c->par.gap_open, c->par.gap_extend, c->dHE.p, c->maxQLen ? c->maxQLen : 1, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
-        } else {
-            TRY(c->dHE.alloc(nWarps * maxT * 32));
-            MB_LAUNCH((k_sw_trace2), blocks, 128, 0, c->stream, c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
-                                                       c->par.gap_open, c->par.gap_extend, c->dHE.p, maxT, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
-        }
+        TRY(c->dHE.alloc(nWarps * maxT * 32));
+        MB_LAUNCH((k_sw_trace2), blocks, 128, 0, c->stream, c->dPassList.p, nPass, c->dHits.p, maxHits, c->dQ.p, c->dQoff.p, c->dCb.p, c->dTseqU.p, c->dToff.p, c->dAlnMat.p,
+                                                   c->par.gap_open, c->par.gap_extend, c->dHE.p, maxT, c->dTrace.p, c->dCounter.p + 40, c->dCells.p + 1);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev1, c->stream));
         c->hTrace.resize(nPass);

@@ -17,7 +17,8 @@
 // --comp-bias-corr 0|1  --min-length N --max-length N --translation-table N (ORF extraction)  --reverse-fragments 0|1 (null model)  --mask 0|1 (default 1: tantan masking of the targets as the reference's
 // index builder does it, --mask-prob 0.9)  --masked-db <db> (take the masked target residues from a DB instead: lower case or X = masked)  --metaeuk-eval X
 // --metaeuk-tcov X --max-intron N --min-intron N --min-exon-aa N --max-overlap N --max-exon-sets N --set-gap-open N --set-gap-extend N
-// --device N.  Everything numeric happens in the library (GPU); this file is DB I/O and the reference's text formatting.
+// --device N  --gpus N (gpupredictexons <contigsDB> <targetDB> <predDB>: one context per device N .. N + gpus - 1 in this process, index copied device to device, contigs sharded by
+// nucleotide count, the merged DB equals the one-GPU DB).  Everything numeric happens in the library (GPU); this file is DB I/O and the reference's text formatting.
 #include <algorithm>
 #include <cctype>
 #include <cmath>
@@ -25,8 +26,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/metaeuk_b200.h"
@@ -111,7 +114,7 @@ static std::string fmtSeqId(float x, bool dropLastZero) {   // Util::fastSeqIdTo
 static std::string fmtE(double e) { char b[64]; snprintf(b, sizeof(b), "%.3E", e); return b; }
 
 struct Opt {
-    mb200_params p; std::string maskedDb; int device = 0; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb; int mask = 1; double maskProb = 0.9;
+    mb200_params p; std::string maskedDb; int device = 0, gpus = 1; int overlap = 0; int textStages = 0; long long batchNt = 0; std::string indexDb; int mask = 1; double maskProb = 0.9;
     int maskLowerCase = 0, maskNRepeat = 0;   // --mask-lower-case, --mask-n-repeat (Masker::maskSequence, Masker.cpp:14-58)
     int minLen = 15, maxLen = 32734;   // --min-length / --max-length of extractorfs in codons (setPredictExonsDefaults, src/workflow/PredictExons.cpp:8-16)
 };
@@ -172,6 +175,7 @@ static Opt parseOpts(int argc, char **argv, int first, std::vector<std::string> 
         else if (a == "--set-gap-open") o.p.set_gap_open = atoi(val().c_str());
         else if (a == "--set-gap-extend") o.p.set_gap_extend = atoi(val().c_str());
         else if (a == "--device") o.device = atoi(val().c_str());
+        else if (a == "--gpus") { o.gpus = atoi(val().c_str()); if (o.gpus < 1 || o.gpus > 64) DIE("--gpus: 1..64"); }
         else if (a == "--overlap") o.overlap = atoi(val().c_str());
         else if (a == "--index-db") o.indexDb = val();
         else if (a == "--mask") o.mask = atoi(val().c_str());
@@ -402,8 +406,65 @@ int main(int argc, char **argv) {
             MB(mb200_target_keys_set(s.ctx, s.tdb.keys.data(), (uint32_t)s.tdb.keys.size()));
             if (o.batchNt > 0) MB(mb200_option_set(s.ctx, "predict_batch_nt", o.batchNt));
             std::vector<uint64_t> coff(order.size() + 1); const mb200_call *calls = nullptr; const mb200_pexon *ex = nullptr; uint64_t nEx = 0;
-            MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), (uint32_t)order.size(), o.minLen, o.maxLen, coff.data(), &calls, &ex, &nEx));
-            { mb200_stats st; MB(mb200_stats_get(s.ctx, &st));
+            const uint32_t nC = (uint32_t)order.size();
+            std::vector<mb200_call> mCalls; std::vector<mb200_pexon> mEx;        // merged records of the shards (--gpus N)
+            const int G = (int)std::min<uint32_t>((uint32_t)o.gpus, std::max<uint32_t>(nC, 1u));
+            if (G <= 1) {
+                MB(mb200_predict_exons(s.ctx, nuc.data(), off.data(), nC, o.minLen, o.maxLen, coff.data(), &calls, &ex, &nEx));
+            } else {
+                // --gpus N: one context per device (--device d .. d + N - 1), the index copied device to device from the first one, the contigs sharded by nucleotide count
+                // (the reference splits a DB over its workers the same way, DBReader.cpp:1216-1256), every shard searched by its own host thread, the records concatenated in
+                // contig order.  Fragment keys count over the whole contig DB: a counting pass of the ORF stage gives every shard the number of fragments before it.
+                std::vector<mb200_ctx *> ctxs(G, nullptr); ctxs[0] = s.ctx;
+                for (int g = 1; g < G; g++) {
+                    MB(mb200_ctx_create(o.device + g, &ctxs[g])); MB(mb200_params_set(ctxs[g], &o.p)); MB(mb200_matrices_default(ctxs[g]));
+                    uint64_t nb = 0; double ms = 0; MB(mb200_index_clone(ctxs[g], s.ctx, &nb, &ms));
+                    if (o.batchNt > 0) MB(mb200_option_set(ctxs[g], "predict_batch_nt", o.batchNt));
+                }
+                std::vector<uint32_t> cb(G + 1, 0); cb[G] = nC;
+                for (int g = 1; g < G; g++) {
+                    const uint64_t want = off[nC] * (uint64_t)g / (uint64_t)G;
+                    uint32_t c = (uint32_t)(std::lower_bound(off.begin(), off.end(), want) - off.begin());
+                    cb[g] = std::min(std::max(c, cb[g - 1]), nC);
+                }
+                std::vector<std::string> errs(G);
+                auto eachShard = [&](const std::function<int(int)> &fn) {
+                    std::vector<std::thread> th;
+                    for (int g = 0; g < G; g++) th.emplace_back([&, g] { if (fn(g) != MB200_OK) errs[g] = mb200_last_error(); });
+                    for (auto &t : th) t.join();
+                    for (int g = 0; g < G; g++) if (!errs[g].empty()) DIE("%s (device %d)", errs[g].c_str(), o.device + g);
+                };
+                std::vector<uint64_t> nFrag(G, 0);
+                eachShard([&](int g) {
+                    if (cb[g + 1] == cb[g]) return (int)MB200_OK;
+                    std::vector<uint64_t> so(off.begin() + cb[g], off.begin() + cb[g + 1] + 1); const uint64_t base = so[0]; for (uint64_t &x : so) x -= base;
+                    uint64_t na = 0; const mb200_orf *orfs = nullptr; const char *aa = nullptr;
+                    return mb200_extract_orfs(ctxs[g], nuc.data() + base, so.data(), cb[g + 1] - cb[g], o.minLen, o.maxLen, 1, &nFrag[g], &orfs, &na, &aa);
+                });
+                std::vector<std::vector<uint64_t>> sOff(G); std::vector<const mb200_call *> sCalls(G, nullptr); std::vector<const mb200_pexon *> sEx(G, nullptr); std::vector<uint64_t> sNEx(G, 0);
+                uint64_t keyBase = 0; std::vector<uint64_t> keyBases(G, 0);
+                for (int g = 0; g < G; g++) { keyBases[g] = keyBase; keyBase += nFrag[g]; }
+                eachShard([&](int g) {
+                    sOff[g].assign(cb[g + 1] - cb[g] + 1, 0);
+                    if (cb[g + 1] == cb[g]) return (int)MB200_OK;
+                    std::vector<uint64_t> so(off.begin() + cb[g], off.begin() + cb[g + 1] + 1); const uint64_t base = so[0]; for (uint64_t &x : so) x -= base;
+                    int rc = mb200_option_set(ctxs[g], "orf_key_base", (int64_t)keyBases[g]);
+                    if (rc == MB200_OK) rc = mb200_predict_exons(ctxs[g], nuc.data() + base, so.data(), cb[g + 1] - cb[g], o.minLen, o.maxLen, sOff[g].data(), &sCalls[g], &sEx[g], &sNEx[g]);
+                    return rc;
+                });
+                coff[0] = 0;
+                for (int g = 0; g < G; g++) {
+                    const uint64_t callBase = mCalls.size(); const uint32_t exBase = (uint32_t)mEx.size();
+                    for (uint64_t k = 0; k < sOff[g].back(); k++) { mb200_call cl = sCalls[g][k]; cl.exon_begin += exBase; mCalls.push_back(cl); }
+                    mEx.insert(mEx.end(), sEx[g], sEx[g] + sNEx[g]);
+                    for (uint32_t ci = cb[g]; ci < cb[g + 1]; ci++) coff[ci + 1] = callBase + sOff[g][ci - cb[g] + 1];
+                    mb200_stats st; MB(mb200_stats_get(ctxs[g], &st));
+                    if (st.overflow_queries) fprintf(stderr, "mb200: warning: %u fragment(s) of shard %d exceeded the prefilter's work lists and were searched with an empty hit list\n", st.overflow_queries, g);
+                }
+                calls = mCalls.data(); ex = mEx.data(); nEx = mEx.size();
+                for (int g = 1; g < G; g++) mb200_ctx_destroy(ctxs[g]);
+            }
+            if (G <= 1) { mb200_stats st; MB(mb200_stats_get(s.ctx, &st));
               if (st.overflow_queries) fprintf(stderr, "mb200: warning: %u fragment(s) exceeded the prefilter's work lists (where the reference takes its own overflow path) and were searched with an empty hit list\n", st.overflow_queries); }
             std::map<uint32_t, std::string> out; char line[512];
             for (size_t ci = 0; ci < order.size(); ci++) {

@@ -10,8 +10,6 @@
 // Kernels (forward = score + e-value gate for all hits; trace = start coordinates for the few % that pass):
 //   k_sw_rows   forward, one target per lane, 32-bit cells, register-resident 32-row blocks (also used for queries > 1024 residues)
 //   k_sw_rows2  forward, two targets per lane in packed s16x2 cells (DPX), one (query, chunk of 32 hits) per half-warp  [default]
-//   k_sw_rows3  forward, the packed arithmetic as a per-lane state machine over (pair, block) units                   [option]
-//   k_sw_trace  pass list, forward with end tracking + reverse pass, state in a lane-interleaved global scratch         [option]
 //   k_sw_trace2 pass list, the same with 16-row register blocks                                                         [default]
 #pragma once
 #include <stdint.h>
@@ -467,234 +465,6 @@ __global__ void __launch_bounds__(MB_SWR_WARPS * 32) k_sw_wave(
             if (actB) { scoreOut[slotB] = sB; if (sB >= 32000) atomicExch(errFlag, 1u);
                         if (sB >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = (uint32_t)slotB; else atomicExch(errFlag, 2u); } }
         }
-    }
-    if (cells) atomicAdd(cellCount, cells);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// k_sw_rows3: the packed kernel reorganised as a per-lane state machine.  A half-warp owns one QUERY at a time (its profile sits in
-// shared memory); the query's hits, sorted by target length, are dealt to the 16 lanes two at a time in snake order (longest pairs
-// first, direction alternating per round) so every lane gets nearly the same number of columns.  Each lane walks its own sequence of
-// (pair, 32-row block) units; the warp executes ONE converged "column step" per iteration for all lanes that have a column left, and the
-// bookkeeping (next block / next pair / next query) runs only for the lanes that need it.  No lane waits for a longer target in a
-// neighbouring lane, and a half-warp waits for its sibling only while that one rebuilds its profile.
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MB_SWR_WARPS * 32, 2) k_sw_rows3(
-    const uint32_t *__restrict__ order, uint32_t pBegin, uint32_t pEnd,
-    const MbPrefHit *__restrict__ hits, const uint32_t *__restrict__ hitCount, const uint16_t *__restrict__ perm, uint32_t maxHits,
-    const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
-    const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat, int gapO, int gapE,
-    uint32_t profStride, const int32_t *__restrict__ minScore, int32_t *__restrict__ scoreOut, uint32_t *__restrict__ passList, uint32_t *nPass,
-    uint32_t passCap, uint32_t *counter, unsigned long long *cellCount, uint32_t *errFlag, uint2 *__restrict__ bnd, uint32_t maxT) {
-    constexpr int RBK = 32;
-    MB_DYN_SHARED(dynProf);
-    __shared__ int8_t sMat8[448];
-    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat8[i] = (int8_t)alnMat[i];
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15u;
-    const unsigned FULL = 0xffffffffu, hmask = 0xFFFFu << (16u * half);
-    int8_t *prof = reinterpret_cast<int8_t *>(dynProf) + (size_t)(wib * 2u + half) * 22u * profStride;   // row 21 = padding residue
-    // block-boundary rows: one private, contiguous strip per lane (the lanes of a warp sit at different columns, so a lane-interleaved
-    // layout would scatter every access over 32 sectors; here a 32-byte sector serves four consecutive columns of its lane)
-    uint2 *myBnd = bnd + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * maxT;
-    const uint32_t negE2 = (uint32_t)(uint16_t)(int16_t)(-gapE) * 0x10001u, go2 = (uint32_t)(uint16_t)(int16_t)(-gapO) * 0x10001u;
-    const uint32_t MIN2 = 0x80008000u;
-    const uint32_t nItems = pEnd - pBegin;
-    unsigned long long cells = 0;
-    // query state (uniform in the half-warp)
-    uint32_t qi = 0, cnt = 0, nPairs = 0; int L = 0, nb = 0; bool halfFinished = false;
-    // lane state
-    bool busy = false, laneDone = false /* first pass: no pairs -> done -> fetch a query */, newUnit = false, hasTop = false, hasBottom = false, actB = false;
-    int r = 0, b = 0, i = 0, n = 0, lenA = 0, lenB = 0;
-    uint32_t slotA = 0, slotB = 0, mx = 0, prevTop = 0, taNext = 21u, tbNext = 21u;
-    const uint8_t *tA = tseq, *tB = tseq; const int8_t *profB = prof;
-    uint2 topNext = make_uint2(0u, 0u);
-    uint32_t Hp[RBK], E[RBK];
-#pragma unroll
-    for (int x = 0; x < RBK; x++) { Hp[x] = 0; E[x] = 0; }
-    for (;;) {
-        if (__any_sync(FULL, busy ? (i >= n) : !laneDone)) {
-            // ---- bookkeeping: entered only when some lane finished a unit or can take a new pair
-            if (busy && i >= n) {                       // end of a (pair, block) unit
-                cells += (unsigned long long)(lenA + lenB) * (unsigned)((L - b * RBK) < RBK ? (L - b * RBK) : RBK);   // real cells (padding rows excluded)
-                b++; newUnit = true;
-                if (b >= nb) {                          // pair finished: scores out, e-value gate
-                    const int sA = (int)(int16_t)(mx & 0xFFFFu), sB = (int)(int16_t)(mx >> 16);
-                    scoreOut[slotA] = sA; if (sA >= 32000) atomicExch(errFlag, 1u);
-                    if (sA >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = slotA; else atomicExch(errFlag, 2u); }
-                    if (actB) {
-                        scoreOut[slotB] = sB; if (sB >= 32000) atomicExch(errFlag, 1u);
-                        if (sB >= minScore[L]) { const uint32_t idx = atomicAdd(nPass, 1u); if (idx < passCap) passList[idx] = slotB; else atomicExch(errFlag, 2u); }
-                    }
-                    busy = false;
-                }
-            }
-            if (!busy && !laneDone) {                   // next pair of this query (snake order over the length-sorted hit list)
-                const uint32_t pr = (uint32_t)r * 16u + ((r & 1) ? (15u - l16) : l16);
-                r++;
-                if (pr < nPairs) {
-                    // perm is ascending by target length: pair 0 = the two longest
-                    const uint32_t kA = cnt - 1u - 2u * pr; actB = (2u * pr + 1u) < cnt; const uint32_t kB = actB ? kA - 1u : kA;
-                    const uint32_t ia = perm ? (uint32_t)perm[(size_t)qi * maxHits + kA] : kA, ib = perm ? (uint32_t)perm[(size_t)qi * maxHits + kB] : kB;
-                    slotA = qi * maxHits + ia; slotB = qi * maxHits + ib;
-                    const uint32_t ta_ = hits[slotA].seqId; const uint64_t oa = toff[ta_]; lenA = (int)(toff[ta_ + 1] - oa); tA = tseq + oa;
-                    lenB = 0; tB = tseq;
-                    if (actB) { const uint32_t tb_ = hits[slotB].seqId; const uint64_t ob = toff[tb_]; lenB = (int)(toff[tb_ + 1] - ob); tB = tseq + ob; }
-                    n = lenA > lenB ? lenA : lenB; mx = 0; b = 0; busy = true; newUnit = true;
-                } else {
-                    laneDone = true;                    // rounds are filled in order: no later round holds a pair for this lane
-                }
-            }
-            // query switch: a half-warp whose 16 lanes are all out of pairs takes the next query
-            const unsigned doneMask = __ballot_sync(FULL, laneDone && !busy);
-            if (!halfFinished && (doneMask & hmask) == hmask) {
-                for (;;) {
-                    uint32_t p = 0;
-                    if (l16 == 0) p = atomicAdd(counter, 1u);
-                    p = __shfl_sync(hmask, p, (int)(16u * half));
-                    if (p >= nItems) { halfFinished = true; break; }
-                    qi = order[pBegin + p]; cnt = hitCount[qi];
-                    if (cnt == 0) continue;
-                    const uint64_t qb = qoff[qi]; L = (int)(qoff[qi + 1] - qb); nb = (L + RBK - 1) / RBK; nPairs = (cnt + 1u) >> 1;
-                    __syncwarp(hmask);
-                    for (uint32_t idx = l16; idx < 22u * profStride; idx += 16u) {
-                        const uint32_t t = idx / profStride, j = idx - t * profStride;
-                        prof[idx] = (t < 21u && j < (uint32_t)L) ? (int8_t)(sMat8[t * 21 + qres[qb + j]] + cb[qb + j]) : (int8_t)-64;
-                    }
-                    __syncwarp(hmask);
-                    r = 0; laneDone = false;
-                    break;
-                }
-            }
-            if (__all_sync(FULL, halfFinished && !busy && laneDone)) break;
-        }
-        if (busy) {
-            if (newUnit) {   // first column of a new (pair, block) unit
-                newUnit = false;
-                i = 0; hasTop = b > 0; hasBottom = b < nb - 1; profB = prof + b * RBK; prevTop = 0;
-#pragma unroll
-                for (int x = 0; x < RBK; x++) { Hp[x] = 0; E[x] = 0; }
-                topNext = make_uint2(0u, 0u);
-                if (hasTop && n > 0) topNext = myBnd[0];
-                taNext = lenA > 0 ? (uint32_t)tA[0] : 21u; tbNext = lenB > 0 ? (uint32_t)tB[0] : 21u;
-            }
-            if (i < n) {
-                // ---- one column of 32 rows for two targets (identical arithmetic to sw_sweep_block2)
-                const uint2 top = topNext; const uint32_t ta = taNext, tb = tbNext;
-                if (i + 1 < n) {
-                    taNext = (i + 1 < lenA) ? (uint32_t)tA[i + 1] : 21u; tbNext = (i + 1 < lenB) ? (uint32_t)tB[i + 1] : 21u;
-                    if (hasTop) topNext = myBnd[i + 1];
-                }
-                const uint4 *pa = reinterpret_cast<const uint4 *>(profB + ta * profStride);
-                const uint4 *pb = reinterpret_cast<const uint4 *>(profB + tb * profStride);
-                uint32_t wa[RBK / 4], wb[RBK / 4];
-#pragma unroll
-                for (int v = 0; v < RBK / 16; v++) {
-                    const uint4 x = pa[v], y = pb[v];
-                    wa[4 * v] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
-                    wb[4 * v] = y.x; wb[4 * v + 1] = y.y; wb[4 * v + 2] = y.z; wb[4 * v + 3] = y.w;
-                }
-                const uint32_t hTop = top.x;
-                uint32_t F = top.y;
-                uint32_t diag = prevTop; prevTop = hTop;
-                uint32_t gUp = 0;
-#pragma unroll
-                for (int x = 0; x < RBK; x++) {
-                    const uint32_t sc = sw_pack_scores(wa[x >> 2], wb[x >> 2], x & 3);
-                    const uint32_t f = (x == 0) ? F : __viaddmax_s16x2(F, negE2, gUp);
-                    const uint32_t t1 = __viaddmax_s16x2(diag, sc, E[x]);
-                    const uint32_t h = __vimax_s16x2_relu(t1, f);
-                    diag = Hp[x]; Hp[x] = h;
-                    const uint32_t g = __viaddmax_s16x2(h, go2, MIN2);
-                    E[x] = __viaddmax_s16x2_relu(E[x], negE2, g);
-                    F = f; gUp = g;
-                    mx = __vmaxs2(mx, h);
-                }
-                if (hasBottom) myBnd[i] = make_uint2(Hp[RBK - 1], __viaddmax_s16x2_relu(F, negE2, gUp));
-                i++;
-            }
-        }
-    }
-    if (cells) atomicAdd(cellCount, cells);
-}
-
-// one alignment per lane: forward with end tracking, then reverse to the start.  slot = query * maxHits + hit rank (slot < 2^32).
-__global__ void __launch_bounds__(128) k_sw_trace(const uint32_t *__restrict__ passList, uint32_t nPass, const MbPrefHit *__restrict__ hits, uint32_t maxHits,
-                                                  const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff, const int8_t *__restrict__ cb,
-                                                  const uint8_t *__restrict__ tseq, const uint64_t *__restrict__ toff, const int16_t *__restrict__ alnMat,
-                                                  int gapO, int gapE, uint32_t *__restrict__ he /* [warp][maxQn][32] */, uint32_t maxQn,
-                                                  SwTraceOut *__restrict__ outs, uint32_t *counter, unsigned long long *cellCount) {
-    __shared__ int8_t sMat[448];
-    for (int i = threadIdx.x; i < 441; i += blockDim.x) sMat[i] = (int8_t)alnMat[i];
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t *myHE = he + (size_t)warpGlobal * maxQn * 32u + lane;
-    unsigned long long cells = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nPass) break;
-        const uint32_t idx = base + lane;
-        if (idx >= nPass) continue;   // lanes are independent from here on (no warp collectives below)
-        const uint32_t slot = passList[idx];
-        const uint32_t qi = slot / maxHits;
-        const uint32_t tid = hits[slot].seqId;
-        const uint8_t *q = qres + qoff[qi]; const int8_t *c = cb + qoff[qi]; const int L = (int)(qoff[qi + 1] - qoff[qi]);
-        const uint8_t *t = tseq + toff[tid]; const int tLen = (int)(toff[tid + 1] - toff[tid]);
-        // ---- forward
-        for (int j = 0; j < L; j++) myHE[(size_t)j * 32u] = 0u;
-        int mx = 0, endDb = -1, endQ = L - 1;
-        for (int ti = 0; ti < tLen; ti++) {
-            const int8_t *row = sMat + t[ti] * 21;
-            int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
-            for (int j = 0; j < L; j++) {
-                const int s = row[q[j]] + c[j];
-                const uint32_t w = myHE[(size_t)j * 32u];
-                const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
-                int f = __viaddmax_s32(F, -gapE, hUp - gapO); f = f < 0 ? 0 : f;
-                const int h = sw_max3(hDiag + s, e, f);
-                hDiag = hPrev;
-                const int en = sw_max3(e - gapE, h - gapO, 0);
-                myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
-                F = f; hUp = h;
-                if (h > cm) { cm = h; jm = j; }
-            }
-            if (cm > mx) { mx = cm; endDb = ti; endQ = jm; }
-        }
-        cells += (unsigned long long)L * tLen;
-        SwTraceOut o; o.slot = slot; o.score = mx; o.qEnd = endQ; o.dbEnd = endDb; o.qStart = -1; o.dbStart = -1; o.flag = 0; o.pad = 0;
-        if (endDb >= 0) {
-            // ---- reverse: rows = query positions endQ, endQ-1, ... 0 ; columns = target positions endDb, endDb-1, ...
-            const int qn = endQ + 1;
-            for (int j = 0; j < qn; j++) myHE[(size_t)j * 32u] = 0u;
-            int rmx = 0, rDb = -1, rQ = qn - 1;
-            for (int ti = endDb; ti >= 0; ti--) {
-                const int8_t *row = sMat + t[ti] * 21;
-                int hDiag = 0, F = 0, hUp = 0, cm = 0, jm = 0;
-                for (int j = 0; j < qn; j++) {
-                    const int qj = endQ - j;
-                    const int s = row[q[qj]] + c[qj];
-                    const uint32_t w = myHE[(size_t)j * 32u];
-                    const int hPrev = (int)(w & 0xFFFFu), e = (int)(w >> 16);
-                    int f = __viaddmax_s32(F, -gapE, hUp - gapO); f = f < 0 ? 0 : f;
-                    const int h = sw_max3(hDiag + s, e, f);
-                    hDiag = hPrev;
-                    const int en = sw_max3(e - gapE, h - gapO, 0);
-                    myHE[(size_t)j * 32u] = ((uint32_t)en << 16) | (uint32_t)h;
-                    F = f; hUp = h;
-                    if (h > cm) { cm = h; jm = j; }
-                }
-                cells += (unsigned long long)qn;
-                if (cm > rmx) { rmx = cm; rDb = ti; rQ = jm; }
-                if (cm == mx) break;
-            }
-            o.dbStart = rDb; o.qStart = endQ - rQ;
-            if (rmx != mx) o.flag = 1;   // the reference EXITs on a forward/backward mismatch (StripedSmithWaterman.cpp:466-473)
-        }
-        if (mx >= 65000) o.flag |= 2;
-        outs[idx] = o;
     }
     if (cells) atomicAdd(cellCount, cells);
 }

@@ -135,7 +135,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "simt emulation error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("MB200_SIMT_DEVICES"); *n = e && atoi(e) > 0 ? atoi(e) : 1; return cudaSuccess; }   // (all emulated devices are the host)
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 2; strcpy(p->name, "simt emulation"); return cudaSuccess; }
 // device allocations are filled with a poison pattern: cudaMalloc does not zero memory, and a kernel that silently relies on zeros should fail here
@@ -149,6 +149,7 @@ template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsi
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = 0; return cudaSuccess; }

@@ -53,9 +53,9 @@ def test_prefilter_index_read_policies(name, hint):
     ctx.close()
 
 
-@pytest.mark.parametrize("sw", [1, 2, 3, 4, (4, 1), (4, 1024), 5, (5, 1), 6, (6, "sw_ring", -1), (6, "sw_ring", 1), (6, "sw_ring", 16)],
-                         ids=["rows", "rows2-packed", "rows3-state-machine", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2",
-                              "stream", "stream-private-profiles", "stream-ring1", "stream-ring16"])
+@pytest.mark.parametrize("sw", [1, 2, 4, (4, 1), (4, 1024), 5, (5, 1), 6, (6, "sw_ring", -1), (6, "sw_ring", 1), (6, "sw_ring", 16), (6, "sw_ring_fit", 0)],
+                         ids=["rows", "rows2-packed", "lanes+rows2", "lanes(1 hit)+rows2", "lanes(any hits)+rows2", "lanes+wave+rows2", "lanes(1 hit)+wave+rows2",
+                              "stream", "stream-private-profiles", "stream-ring1", "stream-ring16", "stream-ring-not-capped"])
 @pytest.mark.parametrize("name", FRAG + CONTIG)
 def test_align_golden(name, sw):
     """every forward alignment kernel variant (mb200_option_set "sw_kernel") must give the reference's result DB; 4 = queries of at most 64
