@@ -251,6 +251,14 @@ class Context:
         self.n_targets = self.index_sizes()[1]
         return int(nb.value), float(ms.value)
 
+    def index_clone_from(self, src):
+        """one process, several contexts: copy the index (and the target keys) of context `src` device to device into this one -> (bytes, wall-clock ms)"""
+        nb = C.c_uint64(0); ms = C.c_double(0)
+        self._check(self.L.mb200_index_clone(self.h, src.h, C.byref(nb), C.byref(ms)))
+        self.n_targets = self.index_sizes()[1]
+        self.target_off = getattr(src, "target_off", None)
+        return int(nb.value), float(ms.value)
+
     # ---- host-buffer API ----
     def prefilter(self, q, qoff):
         q = np.ascontiguousarray(q, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64)
