@@ -703,7 +703,8 @@ int mb200_index_clone(mb200_ctx *dst, mb200_ctx *src, uint64_t *nbytes, double *
     uint64_t total = 0;
     for (int i = 0; i < n1; i++) {
         if (ns[i] != nd[i]) return fail(MB200_E_INTERNAL, "index arenas differ");
-        if (ns[i]) CU(cudaMemcpyPeerAsync(pd[i], dst->device, ps[i], src->device, ns[i], dst->stream));
+        if (ns[i] && src->device != dst->device) CU(cudaMemcpyPeerAsync(pd[i], dst->device, ps[i], src->device, ns[i], dst->stream));
+        else if (ns[i]) CU(cudaMemcpyAsync(pd[i], ps[i], ns[i], cudaMemcpyDeviceToDevice, dst->stream));      // two contexts on one device
         total += ns[i];
     }
     CU(cudaStreamSynchronize(dst->stream));

@@ -40,24 +40,6 @@ def test_prefilter_golden(name, cfg):
     ctx.close()
 
 
-def test_index_clone_gives_a_second_context_the_same_index():
-    """mb200_index_clone (one process, several contexts; the --gpus N path of the C++ driver): the clone -- here on the same device, cudaMemcpyPeerAsync accepts that -- must
-    prefilter, align and call exons exactly like the context the index was built in, after the source context is gone"""
-    from metaeuk_b200.lib import Context
-    c = reflib.load_case("contigs_small")
-    a, tdb = ctx_for(c, max_exon_sets=c["max_exon_sets"])
-    b = Context(0)
-    b.set_params(kmer_thr=c["kmer_thr"], max_res_list_len=c.get("max_seqs", 300), max_exon_sets=c["max_exon_sets"])
-    b.matrices_default()
-    nbytes, _ms = b.index_clone_from(a)
-    assert nbytes > 0 and b.index_sizes() == a.index_sizes()
-    a.close()
-    got = strkeys(M.prefilter(b, c["queries"], tdb))
-    assert all(got[str(k)] == c["pref"].get(str(k), "") for k, _ in c["queries"])
-    assert strkeys(M.predictexons_contigs(b, [tuple(x) for x in c["contigs"]], tdb)) == c["dp"]
-    b.close()
-
-
 @pytest.mark.parametrize("hint", [0, 1, 3], ids=["cached", "evict-first", "evict-first-64B"])
 @pytest.mark.parametrize("name", FRAG[:2] + CONTIG[:1])
 def test_prefilter_index_read_policies(name, hint):

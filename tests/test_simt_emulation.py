@@ -29,7 +29,7 @@ SLICE = [
     "tests/test_zz_gpu_adversarial.py::test_predictexons_flags_golden[table6]",
     "tests/test_zz_gpu_adversarial.py::test_very_long_fragments_take_the_second_prefilter_pass",
     "tests/test_zz_gpu_adversarial.py::test_cli_gpupredictexons_takes_the_reference_flags[table4]",     # the C++ driver, linked against the emulation
-    "tests/test_gpu_parity.py::test_index_clone_gives_a_second_context_the_same_index",
+    "tests/test_zz_gpu_adversarial.py::test_index_clone_gives_a_second_context_the_same_index",
     "tests/test_zz_gpu_adversarial.py::test_cli_gpupredictexons_on_several_devices_gives_the_one_device_db",   # --gpus 2 / 3: sharding, key bases, merge (all "devices" = the host here)
 ]
 
