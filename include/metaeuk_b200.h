@@ -278,6 +278,7 @@ int mb200_results_download(mb200_ctx *ctx, mb200_hit *hits, uint32_t *hit_count,
  *   "orf_key_base" n             fragment key of the first fragment of the next mb200_predict_exons call (a rank's shard of a contig DB) */
 int mb200_option_set(mb200_ctx *ctx, const char *name, int64_t value);
 int mb200_stats_get(mb200_ctx *ctx, mb200_stats *out);
+int mb200_profile_dump(mb200_ctx *ctx, const char *json_path);   /* the same counters and stage times as one JSON object in a file */
 /* CUDA-event stopwatch on the context's stream (the stream every kernel and copy of this library is issued on) */
 int mb200_timer_start(mb200_ctx *ctx);
 int mb200_timer_stop(mb200_ctx *ctx, double *ms);

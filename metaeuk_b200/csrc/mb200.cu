@@ -1875,6 +1875,29 @@ int mb200_query_status_get(mb200_ctx *c, uint32_t *status) {
     return 0;
 }
 int mb200_stats_get(mb200_ctx *c, mb200_stats *out) { if (!c || !out) return fail(MB200_E_ARG, "null argument"); *out = c->st; return 0; }
+// the work counters and stage times of the last call as one JSON object (what bench.py reads through mb200_stats_get, for callers without a struct mirror)
+int mb200_profile_dump(mb200_ctx *c, const char *jsonPath) {
+    if (!c || !jsonPath) return fail(MB200_E_ARG, "null argument");
+    FILE *f = fopen(jsonPath, "w");
+    if (!f) return fail(MB200_E_ARG, "cannot create %s", jsonPath);
+    const mb200_stats &s = c->st;
+    fprintf(f, "{\"build\": \"%s\", \"device\": %d, \"sms\": %d,\n", mb200_build_kind(), c->device, c->nSM);
+#define MB_U(k) fprintf(f, " \"" #k "\": %llu,", (unsigned long long)s.k)
+#define MB_D(k) fprintf(f, " \"" #k "\": %.6f,", (double)s.k)
+    MB_U(kmers); MB_U(lookups); MB_U(db_matches); MB_U(double_hits); MB_U(diag_cells); MB_U(pref_results); fputc('\n', f);
+    MB_U(sw_pairs); MB_U(sw_cells_fwd); MB_U(sw_cells_rev); MB_U(sw_target_bytes); MB_U(query_residues); MB_U(n_queries); fputc('\n', f);
+    MB_D(ms_orf); MB_D(ms_orf_host); MB_D(ms_prep); MB_D(ms_prefilter); MB_D(ms_sw_fwd); MB_D(ms_sw_rev); MB_D(ms_chain); MB_D(ms_reduce); MB_D(ms_h2d); MB_D(ms_d2h); MB_D(ms_host); MB_D(ms_join); MB_D(ms_predict); fputc('\n', f);
+    MB_D(ms_prefilter_sum); MB_D(ms_sw_fwd_sum); MB_D(ms_sw_rev_sum); MB_D(ms_dev_sum); MB_D(ms_dev_busy); fputc('\n', f);
+    MB_U(orf_nucleotides); MB_U(orf_fragments); MB_U(orf_residues); MB_U(pe_batches); MB_U(pe_contigs); MB_U(pe_fragments); MB_U(pe_alignments); MB_U(pe_calls); MB_U(pe_exons); MB_U(pe_streams); fputc('\n', f);
+    MB_U(launches); MB_U(overflow_queries);
+#undef MB_U
+#undef MB_D
+    fprintf(f, " \"pref_phase_cycles\": [");
+    for (int i = 0; i < 16; i++) fprintf(f, "%s%llu", i ? ", " : "", (unsigned long long)s.pref_phase_cycles[i]);
+    fprintf(f, "]}\n");
+    if (fclose(f) != 0) return fail(MB200_E_ARG, "write error on %s", jsonPath);
+    return 0;
+}
 double mb200_evalue(mb200_ctx *c, int rawScore, int qLen) { return c->ev.evalue(rawScore, qLen, (double)c->totalRes); }
 int mb200_bit_score(mb200_ctx *c, int rawScore) { return c->ev.bitScore(rawScore); }
 

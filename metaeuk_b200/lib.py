@@ -425,6 +425,9 @@ class Context:
         self._check(self.L.mb200_query_status_get(self.h, _p(st)))
         return st
 
+    def profile_dump(self, path):
+        self._check(self.L.mb200_profile_dump(self.h, str(path).encode()))
+
     def stats(self):
         s = Stats()
         self._check(self.L.mb200_stats_get(self.h, C.byref(s)))
