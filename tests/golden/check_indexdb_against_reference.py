@@ -8,7 +8,7 @@ binary, so it is not part of the test suite; the suite pins the same entries thr
    similarity tables).
 2. open_index_db() on that file must return the sequences, masked residues, offsets and keys of the DB the reference indexed.
 3. write_index_db() on the same input must produce entries ENTRIES(9), ENTRIESOFFSETS(10), ENTRIESNUM(12), SEQCOUNT(13), SEQINDEXDATA(14),
-   SEQINDEXDATASIZE(15), SEQINDEXSEQOFFSET(16), DBR1DATA(6), VERSION(0) byte-identical to the reference's.
+   SEQINDEXDATASIZE(15), SEQINDEXSEQOFFSET(16), DBR1DATA(6), VERSION(0), SCOREMATRIX2MER(3), SCOREMATRIX3MER(4), SPACEDPATTERN(23) byte-identical to the reference's.
 Result recorded in DESIGN.md section 4.7 (run in the build container, reference built out of tree with the recipe of SURVEY.md 8c)."""
 import ctypes as C
 import os
@@ -63,13 +63,13 @@ def main():
     assert emu.emu_indexdb_write((work + "/mine.idx").encode(), p(m, C.c_uint8), p(u, C.c_uint8), p(off, C.c_uint64), C.c_uint32(len(keys)), p(keys, C.c_uint32), 127, 1) == 0
     ea, eb = entries(work + "/prot.idx"), entries(work + "/mine.idx")
     fa, fb = open(work + "/prot.idx", "rb"), open(work + "/mine.idx", "rb")
-    for k in (0, 6, 9, 10, 12, 13, 14, 15, 16):
+    for k in (0, 3, 4, 23, 6, 9, 10, 12, 13, 14, 15, 16):     # (3, 4 = the 2-mer / 3-mer similarity tables, 23 = the spaced pattern: written since the end of round 2)
         fa.seek(ea[k][0]); fb.seek(eb[k][0])
         a, b = fa.read(ea[k][1]), fb.read(eb[k][1])
         if k == 14:     # the reference writes getDataSize() + 1 bytes: the last one lies past the lookup's data (uninitialised there, 0 here)
             a, b = a[:-2], b[:-2]
         assert ea[k][1] == eb[k][1] and a == b, k
-    print("writer: entries 0 6 9 10 12 13 14 15 16 byte-identical to the reference's")
+    print("writer: entries 0 3 4 23 6 9 10 12 13 14 15 16 byte-identical to the reference's")
 
 
 if __name__ == "__main__":
