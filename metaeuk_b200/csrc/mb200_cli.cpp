@@ -334,6 +334,8 @@ int main(int argc, char **argv) {
     if (argc < 2) DIE("usage: mb200 <gpucreateindex|gpuextractorfs|gpureduceredundancy|gpuprefilter|gpualign|gpusearch|gpuresultspercontig|gpucollectoptimalset|gpupredictexons> <DBs...> [options]");
     initCodes();
     std::string cmd = argv[1]; std::vector<std::string> pos; Opt o = parseOpts(argc, argv, 2, pos);
+    if (o.gpus > 1 && !(cmd == "gpupredictexons" && pos.size() == 3 && !o.textStages))
+        DIE("--gpus N is implemented for `gpupredictexons <contigsDB> <targetDB> <predDB>` (binary hand-off) only; the other modules run on one device (--device N)");
     if (cmd == "gpuprefilter") {
         if (pos.size() != 3) DIE("gpuprefilter <queryDB> <targetDB> <prefDB>");
         Session s; s.open(o, pos[1]); Db qdb = openDb(pos[0]); Seqs q = encodeDb(qdb, false);

@@ -139,6 +139,8 @@ def test_cli_rejects_flags_it_would_otherwise_silently_ignore(exe, emu, tmp_path
     d = str(tmp_path)
     reflib.write_db(d + "/proteins", [(k, s + "\n") for k, s in c["targets"][:50]], 0)
     base = [exe, "gpucreateindex", d + "/proteins"]
+    r = subprocess.run([exe, "gpuprefilter", d + "/proteins", d + "/proteins", d + "/x", "--gpus", "2"], capture_output=True, text=True)     # --gpus is a gpupredictexons option
+    assert r.returncode != 0 and "--gpus" in r.stderr
     for bad in (["--alignment-mode", "3"], ["--orf-start-mode", "0"], ["--min-seq-id", "0.3"], ["-c", "0.8"], ["--comp-bias-corr-scale", "0.5"], ["--gap-open", "10"],
                 ["--no-such-flag", "1"], ["--exhaustive-search", "1"], ["--sub-mat", "VTML40.out"]):
         r = subprocess.run(base + [d + "/bad.idx"] + bad, capture_output=True, text=True)
